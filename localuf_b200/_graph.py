@@ -70,6 +70,7 @@ class FlatGraph:
     edge_v: np.ndarray            # int32[E]
     node_flags: np.ndarray        # uint8[N]
     node_id: np.ndarray           # int32[N]  reference index_to_id (initial cluster id of the CA decoders)
+    node_long: np.ndarray         # int32[N]  coordinate along LONG_AXIS (-1 west ... d-1 east)
     inc_off: np.ndarray           # int32[N+1]
     inc_edge: np.ndarray          # int32[2E]  ascending edge id within a node
     inc_other: np.ndarray         # int32[2E]
@@ -176,6 +177,7 @@ class FlatGraph:
             n_nodes=N, n_boundary=n_boundary, n_edges=E, d=d, height=h,
             edge_u=eu, edge_v=ev, node_flags=flags,
             node_id=np.fromiter((code.index_to_id(v) for v in nodes), dtype=np.int32, count=N),
+            node_long=np.fromiter((v[a] for v in nodes), dtype=np.int32, count=N),
             inc_off=off, inc_edge=inc_edge, inc_other=inc_other,
             west_edge_mask=west, edge_class=edge_class, n_classes=len(class_lists),
             dir_names=tuple(n for n, _ in dirs),

@@ -1,0 +1,127 @@
+"""ctypes binding of the CPU oracle (oracle/luf_oracle.c).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, '_build', 'libluf_oracle.so')
+
+P = C.POINTER
+
+
+class OracleGraph(C.Structure):
+    _fields_ = [
+        ('n_nodes', C.c_int32), ('n_boundary', C.c_int32), ('n_edges', C.c_int32),
+        ('d', C.c_int32), ('height', C.c_int32),
+        ('edge_u', C.c_void_p), ('edge_v', C.c_void_p),
+        ('node_flags', C.c_void_p), ('node_id', C.c_void_p), ('node_long', C.c_void_p),
+        ('inc_off', C.c_void_p), ('inc_edge', C.c_void_p), ('inc_other', C.c_void_p),
+        ('west_edge_mask', C.c_void_p), ('edge_class', C.c_void_p), ('n_classes', C.c_int32),
+        ('n_dirs', C.c_int32), ('nbr_edge', C.c_void_p), ('nbr_node', C.c_void_p),
+        ('nbr_owned', C.c_void_p), ('noise_kind', C.c_int32),
+    ]
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(('.c', '.h')) or f == 'Makefile']
+    stale = (not os.path.exists(LIB)) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs)
+    if force or stale:
+        subprocess.run(['make', '-C', HERE, '-B'], check=True, capture_output=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oracle_uf_decode.restype = C.c_int
+        _lib.oracle_decode_batch.restype = C.c_int
+        _lib.oracle_logical_batch.restype = C.c_int
+        _lib.oracle_mc_batch.restype = C.c_int64
+        _lib.oracle_mc_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_uint64, C.c_int64, C.c_int]
+        _lib.oracle_decode_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+NOISE_KIND = {'code capacity': 0, 'phenomenological': 1, 'circuit-level': 2}
+
+
+class Oracle:
+    """Oracle bound to one flat graph (anything with the FlatGraph fields)."""
+
+    def __init__(self, flat, noise_kind: int = 0):
+        self.flat = flat
+        self._keep = {}
+        g = OracleGraph()
+        g.n_nodes, g.n_boundary, g.n_edges = flat.n_nodes, flat.n_boundary, flat.n_edges
+        g.d, g.height = flat.d, flat.height
+        for name, dt in (('edge_u', np.int32), ('edge_v', np.int32), ('node_flags', np.uint8),
+                         ('node_id', np.int32), ('node_long', np.int32),
+                         ('inc_off', np.int32), ('inc_edge', np.int32), ('inc_other', np.int32),
+                         ('west_edge_mask', np.uint32), ('edge_class', np.uint8),
+                         ('nbr_edge', np.int32), ('nbr_node', np.int32), ('nbr_owned', np.uint8)):
+            a = np.ascontiguousarray(getattr(flat, name), dtype=dt)
+            self._keep[name] = a
+            setattr(g, name, a.ctypes.data)
+        g.n_classes = flat.n_classes
+        g.n_dirs = flat.nbr_edge.shape[1]
+        g.noise_kind = noise_kind
+        self.g = g
+        self.WE = (flat.n_edges + 31) // 32
+        self.WD = (flat.n_detectors + 31) // 32
+
+    @classmethod
+    def from_code(cls, code):
+        return cls(code.FLAT, NOISE_KIND[str(code.NOISE)])
+
+    def decode_batch(self, decoder: int, flags: int, syn_bits, want_growth=True):
+        syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, max(self.WD, 1) if self.WD else 0)
+        n = syn.shape[0]
+        corr = np.zeros((n, self.WE), np.uint32)
+        growth = np.zeros((n, self.flat.n_edges), np.uint8) if want_growth else None
+        steps = np.zeros((n, 2), np.int32)
+        rc = lib().oracle_decode_batch(C.byref(self.g), decoder, flags, n, syn.ctypes.data, corr.ctypes.data,
+                                       growth.ctypes.data if want_growth else None, steps.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f'oracle_decode_batch failed ({rc})')
+        return corr, growth, steps
+
+    def syndrome(self, err_bits):
+        err = np.ascontiguousarray(err_bits, dtype=np.uint32).reshape(-1, self.WE)
+        syn = np.zeros((err.shape[0], self.WD), np.uint32)
+        for s in range(err.shape[0]):
+            lib().oracle_syndrome(C.byref(self.g), err[s].ctypes.data_as(C.c_void_p),
+                                  syn[s].ctypes.data_as(C.c_void_p))
+        return syn
+
+    def logical_batch(self, err_bits, corr_bits):
+        err = np.ascontiguousarray(err_bits, dtype=np.uint32).reshape(-1, self.WE)
+        corr = np.ascontiguousarray(corr_bits, dtype=np.uint32).reshape(-1, self.WE)
+        return np.array([lib().oracle_logical_batch(C.byref(self.g), err[s].ctypes.data_as(C.c_void_p),
+                                                    corr[s].ctypes.data_as(C.c_void_p))
+                         for s in range(err.shape[0])], np.uint8)
+
+    def sample(self, class_p, seed: int, nshots: int):
+        rng = (C.c_uint64 * 4)(*[(seed * 0x9E3779B97F4A7C15 + k * 0xD1B54A32D192ED03 + 1) & (2**64 - 1) for k in range(4)])
+        cp = np.ascontiguousarray(class_p, dtype=np.float64)
+        err = np.zeros((nshots, self.WE), np.uint32)
+        for s in range(nshots):
+            lib().oracle_sample(C.byref(self.g), cp.ctypes.data_as(C.c_void_p), rng,
+                                err[s].ctypes.data_as(C.c_void_p))
+        return err
+
+    def mc_batch(self, decoder: int, flags: int, class_p, seed: int, nshots: int, nthreads: int = 1) -> int:
+        cp = np.ascontiguousarray(class_p, dtype=np.float64)
+        m = lib().oracle_mc_batch(C.addressof(self.g), decoder, flags, cp.ctypes.data, seed, nshots, nthreads)
+        if m < 0:
+            raise RuntimeError('oracle_mc_batch failed')
+        return int(m)
