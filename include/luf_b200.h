@@ -1,0 +1,152 @@
+/*
+ * luf_b200.h -- C ABI of the B200 batched Union-Find decoding engine
+ * (libluf_b200.so, built from localuf_b200/csrc by __graft_entry__.build()).
+ *
+ * The reference (timchan0/localuf) is pure Python and has no FFI boundary of
+ * its own; its boundary for the Monte-Carlo hot path is the Python class API
+ * (SURVEY.md section 8b).  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference repository).  The
+ * Python host layer (localuf_b200/) keeps the reference's class/method names
+ * and calls these through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types;
+ *   - every function returns 0 on success or a negative luf_status;
+ *     luf_last_error() gives the message of the calling thread's last failure;
+ *   - pointers named *_dev are device pointers owned by the caller, pointers
+ *     named *_host are host pointers; nothing is retained after the call
+ *     returns except inside the opaque luf_graph;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); the
+ *     *_dev functions are asynchronous on it, the *_host functions synchronise
+ *     it before returning;
+ *   - bit arrays are little-endian 32-bit words: bit k of word w is element
+ *     32*w + k.  W(x) = ceil(x/32) words.  Edge index = position in
+ *     code.EDGES; detector index k = node index B + k (boundary nodes are node
+ *     indices [0, B));
+ *   - no hidden global state: one process per GPU is safe, a luf_graph belongs
+ *     to the device it was created on.
+ */
+#ifndef LUF_B200_H
+#define LUF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct luf_graph luf_graph;
+
+typedef enum {
+    LUF_OK = 0,
+    LUF_ERR_INVALID = -1,      /* bad argument */
+    LUF_ERR_UNSUPPORTED = -2,  /* valid in the reference, not built here (yet) */
+    LUF_ERR_CUDA = -3,         /* CUDA runtime error, see luf_last_error() */
+    LUF_ERR_NO_DEVICE = -4     /* no CUDA device: there is no CPU fallback */
+} luf_status;
+
+enum { LUF_DEC_UF = 0, LUF_DEC_MACAR = 1, LUF_DEC_ACTIS = 2, LUF_DEC_SNOWFLAKE = 3 };
+enum {
+    LUF_UF_DYNAMIC = 1,        /* decoders/uf.py:23-28  UF(dynamic=True)       */
+    LUF_UF_WEST = 2,           /* decoders/uf.py:23-28  UF(inclination='west') */
+    LUF_ACTIS_UNOPTIMAL = 4    /* decoders/luf/__init__.py:31-41 Actis(_optimal=False) */
+};
+enum { LUF_NOISE_CODE_CAPACITY = 0, LUF_NOISE_PHENOMENOLOGICAL = 1, LUF_NOISE_CIRCUIT_LEVEL = 2 };
+
+/* Flat description of one decoding graph (host arrays, copied by luf_graph_create).
+ * Replaces the Python graph objects of localuf/_base_classes.py:165-175
+ * (EDGES, NODES, INCIDENT_EDGES), codes.py:64-82,287-311 (index_to_id) and the
+ * per-node NEIGHBORS tables of decoders/luf/main.py:743-783. */
+typedef struct {
+    int32_t n_nodes;             /* N */
+    int32_t n_boundary;          /* B: node indices [0,B) are boundary nodes */
+    int32_t n_edges;             /* E */
+    int32_t d;                   /* code distance */
+    int32_t height;              /* window height h */
+    int32_t noise_kind;          /* LUF_NOISE_* */
+    const int32_t *edge_u;       /* [E] first endpoint (north / west / down side) */
+    const int32_t *edge_v;       /* [E] second endpoint */
+    const uint8_t *node_flags;   /* [N] bit0 boundary, bit1 west, bit2 east, bit3 future boundary */
+    const int32_t *node_id;      /* [N] reference index_to_id */
+    const int32_t *node_long;    /* [N] coordinate along the long axis, -1 (west) .. d-1 (east) */
+    const int32_t *inc_off;      /* [N+1] CSR offsets into inc_edge / inc_other */
+    const int32_t *inc_edge;     /* [2E] incident edges, ascending edge id within a node */
+    const int32_t *inc_other;    /* [2E] the edge's other endpoint */
+    const uint32_t *west_edge_mask; /* [W(E)] edges whose first endpoint is on the west boundary */
+    const uint8_t *edge_class;   /* [E] probability class of the edge, 255 = never sampled */
+    int32_t n_classes;
+    int32_t n_dirs;              /* K: width of the cellular-automaton neighbour table */
+    const int32_t *nbr_edge;     /* [N*K] edge id in scan order, -1 if absent */
+    const int32_t *nbr_node;     /* [N*K] neighbour node index, -1 if absent */
+    const uint8_t *nbr_owned;    /* [N*K] 1 if the node is the edge's first endpoint */
+} luf_graph_desc;
+
+/* Message of the calling thread's most recent failure ("" if none). */
+const char *luf_last_error(void);
+
+/* Number of CUDA devices visible (0 => every other call fails with LUF_ERR_NO_DEVICE). */
+int luf_device_count(void);
+
+/* Upload a graph to `device`.  Replaces Code.__init__ (localuf/_base_classes.py:23-175)
+ * as far as the device is concerned; the host object is built by localuf_b200.codes. */
+int luf_graph_create(const luf_graph_desc *desc, int device, luf_graph **out);
+int luf_graph_destroy(luf_graph *g);
+
+/* Sizes (in 32-bit words per shot) of the bit arrays of this graph. */
+int luf_graph_words(const luf_graph *g, int32_t *edge_words, int32_t *detector_words,
+                    int32_t *growth_words);
+
+/* K1 -- replaces Noise.make_error (localuf/noise/main.py:114-115, 309-314) and
+ * Code.get_syndrome (localuf/_base_classes.py:427-450) for shots
+ * [shot0, shot0 + nshots): counter-based RNG keyed by (seed, shot), so any
+ * partition of the shot range over launches / GPUs gives the same samples.
+ * class_p_host[n_classes]: flip probability of each probability class.
+ * err_bits_dev [nshots][W(E)], syn_bits_dev [nshots][W(D)]. */
+int luf_sample(luf_graph *g, const double *class_p_host, uint64_t seed, uint64_t shot0,
+               int64_t nshots, uint32_t *err_bits_dev, uint32_t *syn_bits_dev, void *stream);
+
+/* K2/K3 -- replaces Decoder.reset() + Decoder.decode(syndrome)
+ * (localuf/decoders/uf.py:79-119,200-344; decoders/luf/main.py:83-188) for a
+ * batch of syndromes.  corr_bits_dev [nshots][W(E)] receives decoder.correction;
+ * growth2b_dev (optional) [nshots][ceil(E/16)] receives decoder.growth as 2-bit
+ * fields (0 ungrown, 1 half, 2 full, 3 burnt); steps_dev (optional) [nshots][2]
+ * receives (growth rounds, 0) for UF and (tSV, tBP) for Macar/Actis. */
+int luf_decode_batch(luf_graph *g, int decoder, int flags, int64_t nshots,
+                     const uint32_t *syn_bits_dev, uint32_t *corr_bits_dev,
+                     uint32_t *growth2b_dev, int32_t *steps_dev, void *stream);
+
+/* K4 -- replaces leftover = error ^ correction and Batch.get_logical_error
+ * (localuf/_schemes.py:123-129,154-155).  logical_dev (optional) [nshots] bytes;
+ * fail_count_dev: one uint64 that the failure count is atomically ADDED to. */
+int luf_check(luf_graph *g, int64_t nshots, const uint32_t *err_bits_dev,
+              const uint32_t *corr_bits_dev, uint8_t *logical_dev,
+              unsigned long long *fail_count_dev, void *stream);
+
+/* Fused K1+K2/3+K4 -- replaces the shot loop Batch.run
+ * (localuf/_schemes.py:116-121,131-155): nshots shots are sampled, decoded and
+ * checked without leaving the SM.  counts_dev[0] += failures, counts_dev[1] += nshots. */
+int luf_mc_run(luf_graph *g, int decoder, int flags, const double *class_p_host,
+               uint64_t seed, uint64_t shot0, int64_t nshots,
+               unsigned long long *counts_dev, void *stream);
+
+/* Host-buffer conveniences (the call a Python user of Scheme.run / Decoder.decode
+ * ends up in): stage through device scratch owned by the graph, synchronise. */
+int luf_mc_run_host(luf_graph *g, int decoder, int flags, const double *class_p_host,
+                    uint64_t seed, uint64_t shot0, int64_t nshots,
+                    unsigned long long counts_host[2]);
+int luf_decode_batch_host(luf_graph *g, int decoder, int flags, int64_t nshots,
+                          const uint32_t *syn_bits_host, uint32_t *corr_bits_host,
+                          uint32_t *growth2b_host, int32_t *steps_host);
+int luf_sample_host(luf_graph *g, const double *class_p_host, uint64_t seed, uint64_t shot0,
+                    int64_t nshots, uint32_t *err_bits_host, uint32_t *syn_bits_host);
+int luf_check_host(luf_graph *g, int64_t nshots, const uint32_t *err_bits_host,
+                   const uint32_t *corr_bits_host, uint8_t *logical_host,
+                   unsigned long long *fail_count_host);
+
+/* Number of kernel launches issued through this graph so far (bench.py's gpu_launches). */
+int64_t luf_launch_count(const luf_graph *g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUF_B200_H */

@@ -1,0 +1,222 @@
+"""ctypes binding of the CUDA engine (``libluf_b200.so``, C ABI in
+``include/luf_b200.h``).
+
+PyTorch is used for plumbing only: device buffers are ``torch`` tensors whose
+raw pointers are handed to the C ABI, and the current ``torch`` CUDA stream is
+the stream the kernels are launched on.  There is **no CPU fallback**: if the
+library or a CUDA device is missing, every entry point raises
+:class:`EngineUnavailable`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'csrc', 'libluf_b200.so')
+
+DEC_UF, DEC_MACAR, DEC_ACTIS, DEC_SNOWFLAKE = 0, 1, 2, 3
+UF_DYNAMIC, UF_WEST, ACTIS_UNOPTIMAL = 1, 2, 4
+NOISE_KIND = {'code capacity': 0, 'phenomenological': 1, 'circuit-level': 2}
+
+
+class EngineUnavailable(RuntimeError):
+    """The CUDA engine cannot run here (library not built, or no GPU)."""
+
+
+class GraphDesc(C.Structure):
+    """``luf_graph_desc`` of include/luf_b200.h."""
+    _fields_ = [
+        ('n_nodes', C.c_int32), ('n_boundary', C.c_int32), ('n_edges', C.c_int32),
+        ('d', C.c_int32), ('height', C.c_int32), ('noise_kind', C.c_int32),
+        ('edge_u', C.c_void_p), ('edge_v', C.c_void_p),
+        ('node_flags', C.c_void_p), ('node_id', C.c_void_p), ('node_long', C.c_void_p),
+        ('inc_off', C.c_void_p), ('inc_edge', C.c_void_p), ('inc_other', C.c_void_p),
+        ('west_edge_mask', C.c_void_p), ('edge_class', C.c_void_p), ('n_classes', C.c_int32),
+        ('n_dirs', C.c_int32), ('nbr_edge', C.c_void_p), ('nbr_node', C.c_void_p),
+        ('nbr_owned', C.c_void_p),
+    ]
+
+
+_FIELD_TYPES = (
+    ('edge_u', np.int32), ('edge_v', np.int32), ('node_flags', np.uint8), ('node_id', np.int32),
+    ('node_long', np.int32), ('inc_off', np.int32), ('inc_edge', np.int32), ('inc_other', np.int32),
+    ('west_edge_mask', np.uint32), ('edge_class', np.uint8),
+    ('nbr_edge', np.int32), ('nbr_node', np.int32), ('nbr_owned', np.uint8),
+)
+
+
+def make_desc(flat, noise_kind: int):
+    """Return ``(GraphDesc, keepalive)`` for a :class:`FlatGraph`."""
+    keep = {}
+    d = GraphDesc()
+    d.n_nodes, d.n_boundary, d.n_edges = flat.n_nodes, flat.n_boundary, flat.n_edges
+    d.d, d.height, d.noise_kind = flat.d, flat.height, noise_kind
+    for name, dt in _FIELD_TYPES:
+        a = np.ascontiguousarray(getattr(flat, name), dtype=dt)
+        keep[name] = a
+        setattr(d, name, a.ctypes.data)
+    d.n_classes = flat.n_classes
+    d.n_dirs = flat.nbr_edge.shape[1]
+    return d, keep
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def _load():
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise EngineUnavailable(
+                f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "The engine has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.luf_last_error.restype = C.c_char_p
+        lib.luf_launch_count.restype = C.c_int64
+        lib.luf_launch_count.argtypes = [C.c_void_p]
+        lib.luf_graph_create.argtypes = [C.POINTER(GraphDesc), C.c_int, C.POINTER(C.c_void_p)]
+        lib.luf_graph_destroy.argtypes = [C.c_void_p]
+        lib.luf_graph_words.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        v, u64, i64 = C.c_void_p, C.c_uint64, C.c_int64
+        lib.luf_sample.argtypes = [v, v, u64, u64, i64, v, v, v]
+        lib.luf_decode_batch.argtypes = [v, C.c_int, C.c_int, i64, v, v, v, v, v]
+        lib.luf_check.argtypes = [v, i64, v, v, v, v, v]
+        lib.luf_mc_run.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v, v]
+        lib.luf_mc_run_host.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v]
+        lib.luf_decode_batch_host.argtypes = [v, C.c_int, C.c_int, i64, v, v, v, v]
+        lib.luf_sample_host.argtypes = [v, v, u64, u64, i64, v, v]
+        lib.luf_check_host.argtypes = [v, i64, v, v, v, v]
+        _lib = lib
+        return lib
+
+
+def library():
+    return _load()
+
+
+def _check(rc: int):
+    if rc == 0:
+        return
+    msg = _load().luf_last_error().decode()
+    if rc == -4:
+        raise EngineUnavailable(msg or "no CUDA device; the engine has no CPU fallback")
+    if rc == -2:
+        raise NotImplementedError(msg)
+    if rc == -1:
+        raise ValueError(msg)
+    raise RuntimeError(f"luf_b200 error {rc}: {msg}")
+
+
+def _ptr(a):
+    """Raw pointer of a numpy array / torch tensor (None -> NULL)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def _stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Engine:
+    """One uploaded graph (``luf_graph``) on one CUDA device."""
+
+    def __init__(self, code, device: int | None = None):
+        lib = _load()
+        if lib.luf_device_count() <= 0:
+            raise EngineUnavailable("no CUDA device visible; the engine has no CPU fallback")
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', 0)) % lib.luf_device_count()
+        self.device = device
+        self.flat = code.FLAT
+        self.noise = code.NOISE
+        desc, self._keep = make_desc(self.flat, NOISE_KIND[str(code.NOISE)])
+        handle = C.c_void_p()
+        _check(lib.luf_graph_create(C.byref(desc), device, C.byref(handle)))
+        self._h = handle
+        we, wd, wg = C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib.luf_graph_words(self._h, C.byref(we), C.byref(wd), C.byref(wg)))
+        self.WE, self.WD, self.WG = we.value, wd.value, wg.value
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h and _lib is not None:
+            _lib.luf_graph_destroy(h)
+
+    # ------------------------------------------------------------- host API
+    def class_p(self, noise_level: float) -> np.ndarray:
+        return np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
+
+    def mc_run_host(self, decoder: int, flags: int, noise_level: float, seed: int, shot0: int, nshots: int):
+        """Fused sample+decode+check of ``nshots`` shots; returns (failures, shots)."""
+        cp = self.class_p(noise_level)
+        counts = (C.c_ulonglong * 2)(0, 0)
+        _check(_load().luf_mc_run_host(self._h, decoder, flags, cp.ctypes.data, seed, shot0, nshots, counts))
+        return int(counts[0]), int(counts[1])
+
+    def decode_batch_host(self, decoder: int, flags: int, syn_bits, want_growth=False, want_steps=True):
+        syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
+        n = syn.shape[0]
+        corr = np.zeros((n, self.WE), np.uint32)
+        growth = np.zeros((n, self.WG), np.uint32) if want_growth else None
+        steps = np.zeros((n, 2), np.int32) if want_steps else None
+        _check(_load().luf_decode_batch_host(self._h, decoder, flags, n, _ptr(syn), _ptr(corr),
+                                             _ptr(growth), _ptr(steps)))
+        return corr, growth, steps
+
+    def sample_host(self, noise_level: float, seed: int, shot0: int, nshots: int):
+        cp = self.class_p(noise_level)
+        err = np.zeros((nshots, self.WE), np.uint32)
+        syn = np.zeros((nshots, self.WD), np.uint32)
+        _check(_load().luf_sample_host(self._h, cp.ctypes.data, seed, shot0, nshots, _ptr(err), _ptr(syn)))
+        return err, syn
+
+    def check_host(self, err_bits, corr_bits):
+        err = np.ascontiguousarray(err_bits, dtype=np.uint32).reshape(-1, self.WE)
+        corr = np.ascontiguousarray(corr_bits, dtype=np.uint32).reshape(-1, self.WE)
+        n = err.shape[0]
+        logical = np.zeros(n, np.uint8)
+        fails = C.c_ulonglong(0)
+        _check(_load().luf_check_host(self._h, n, _ptr(err), _ptr(corr), _ptr(logical), C.byref(fails)))
+        return logical, int(fails.value)
+
+    # ----------------------------------------------------------- device API
+    def sample(self, noise_level, seed, shot0, nshots, err_bits, syn_bits):
+        cp = self.class_p(noise_level)
+        _check(_load().luf_sample(self._h, cp.ctypes.data, seed, shot0, nshots,
+                                  _ptr(err_bits), _ptr(syn_bits), _stream()))
+
+    def decode_batch(self, decoder, flags, nshots, syn_bits, corr_bits, growth2b=None, steps=None):
+        _check(_load().luf_decode_batch(self._h, decoder, flags, nshots, _ptr(syn_bits), _ptr(corr_bits),
+                                        _ptr(growth2b), _ptr(steps), _stream()))
+
+    def check(self, nshots, err_bits, corr_bits, logical, fail_count):
+        _check(_load().luf_check(self._h, nshots, _ptr(err_bits), _ptr(corr_bits), _ptr(logical),
+                                 _ptr(fail_count), _stream()))
+
+    def mc_run(self, decoder, flags, noise_level, seed, shot0, nshots, counts):
+        cp = self.class_p(noise_level)
+        _check(_load().luf_mc_run(self._h, decoder, flags, cp.ctypes.data, seed, shot0, nshots,
+                                  _ptr(counts), _stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(_load().luf_launch_count(self._h))
+
+
+def unpack_growth(growth2b: np.ndarray, n_edges: int) -> np.ndarray:
+    """[n, ceil(E/16)] words of 2-bit fields -> [n, E] uint8."""
+    g = np.ascontiguousarray(growth2b, dtype=np.uint32)
+    b = np.unpackbits(g.view(np.uint8), axis=-1, bitorder='little')
+    b = b.reshape(g.shape[0], -1, 2)
+    return (b[:, :, 0] | (b[:, :, 1] << 1)).astype(np.uint8)[:, :n_edges]

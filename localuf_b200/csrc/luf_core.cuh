@@ -1,0 +1,472 @@
+// luf_core.cuh -- per-shot phases of the B200 Union-Find decoding engine.
+//
+// One *tile* of NL cooperating lanes (a warp in the shipped kernels) owns one
+// shot at a time; the shot's whole decoder state lives in that tile's slice of
+// shared memory.  A shot is a sequence of phases separated by tile barriers;
+// inside a phase every lane runs the same function with its own lane index and
+// only touches shared state through atomics or through data it exclusively
+// owns.  The phases are written against a tiny portability layer (LUF_* macros
+// below) so that the very same source also compiles as plain C++
+// (-DLUF_HOST_EMU, tests/emu/): there the lanes of a phase simply run one after
+// the other.  That build is a test harness for the kernel logic, never a
+// product path -- the product has no CPU fallback.
+//
+// Algorithm (reference: localuf/decoders/uf.py, canonical order of
+// oracle/ref_canonical.py):
+//   K1  sample + syndrome   noise/main.py:114-115,309-314; _base_classes.py:427-450
+//   K2a validate            uf.py:200-301  (grow a half-edge per round, merge in ascending edge id)
+//   K2b peel                uf.py:305-344  (LIFO spanning tree in ascending edge id, leaf-up peeling)
+//   K4  logical parity      _schemes.py:123-129
+#pragma once
+#include <stdint.h>
+
+#if defined(LUF_HOST_EMU)
+  #include <math.h>
+  #define LUF_DEV static inline
+  static inline uint32_t luf_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+  static inline uint32_t luf_atomic_sub(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o - v; return o; }
+  static inline uint32_t luf_atomic_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+  static inline uint32_t luf_atomic_xor(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o ^ v; return o; }
+  static inline int luf_ffs(uint32_t x) { return __builtin_ffs((int)x); }
+  static inline uint32_t luf_mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+  static inline float luf_log2(float x) { return log2f(x); }
+  #define LUF_LDG(p) (*(p))
+  // a phase = every lane of the tile runs `stmt`, then the tile synchronises
+  #define LUF_PHASE(stmt) for (int lane = 0; lane < nl; ++lane) { stmt; }
+#else
+  #define LUF_DEV __device__ __forceinline__
+  LUF_DEV uint32_t luf_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+  LUF_DEV uint32_t luf_atomic_sub(uint32_t* p, uint32_t v) { return atomicSub(p, v); }
+  LUF_DEV uint32_t luf_atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+  LUF_DEV uint32_t luf_atomic_xor(uint32_t* p, uint32_t v) { return atomicXor(p, v); }
+  LUF_DEV int luf_ffs(uint32_t x) { return __ffs((int)x); }
+  LUF_DEV uint32_t luf_mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+  LUF_DEV float luf_log2(float x) { return __log2f(x); }
+  #define LUF_LDG(p) __ldg(p)
+  #define LUF_PHASE(stmt) { stmt; } __syncwarp();
+#endif
+
+namespace luf {
+
+typedef uint16_t idx_t;                 // node / edge index inside a shot's state
+static const uint32_t ROOT_BIT = 0x8000u;   // P[v]: root marker; low 15 bits = cluster size
+static const uint32_t ODD_BIT = 0x8000u;    // R[root]: odd defect parity; low 15 bits = boundary node + 1
+static const uint32_t NONE16 = 0xFFFFu;
+static const uint32_t TREE_ROOT = 0xFFFEu;
+static const int MAX_CLASSES = 32;
+
+enum { G_UNGROWN = 0, G_HALF = 1, G_FULL = 2, G_BURNT = 3 };
+enum { FLAG_DYNAMIC = 1, FLAG_WEST = 2 };
+
+// Read-only graph tables (global memory, read through L1).
+struct GraphView {
+    int N, B, E;            // nodes, boundary nodes (indices [0,B)), edges
+    int WE, WD, WN;         // 32-bit words of an edge / detector / node bitmap
+    const uint32_t* inc_off;    // [N+1] CSR offsets
+    const uint32_t* inc;        // [2E]  edge | other<<16 | first<<31, ascending edge id per node
+    const uint32_t* edge_uv;    // [E]   u | v<<16
+    const uint32_t* west_mask;  // [WE]  edges whose first endpoint is a west boundary node
+    const int16_t* node_long;   // [N]   coordinate along the long axis
+    // sampler tables: fresh edges sorted by probability class
+    int F, n_classes;
+    const uint16_t* fresh_perm; // [F]
+    const uint32_t* class_end;  // [n_classes] exclusive end position of each class in fresh_perm
+};
+
+// Per-class sampling parameters of one launch (kernel argument, by value).
+struct SampleParams {
+    float p[MAX_CLASSES];           // flip probability
+    float inv_log2_q[MAX_CLASSES];  // 1 / log2(1 - p)  (negative); unused when p <= 0 or p >= 1
+    uint32_t key0, key1;            // Philox key = seed
+};
+
+// Byte offsets of one shot's state inside its shared-memory slice.
+struct Layout {
+    uint32_t P, NX, R;                  // idx_t[N] each (aliased by the peel: tree edge, stack link, discovery link)
+    uint32_t growth;                    // uint32[ceil(E/16)]  2 bits per edge
+    uint32_t newfull;                   // uint32[WE]  edges that reached FULL this round
+    uint32_t defect;                    // uint32[WD]
+    uint32_t act0, act1;                // uint32[WD]  active roots (detector-indexed), ping-pong
+    uint32_t troot;                     // uint32[WN]  tree roots to peel from
+    uint32_t err, corr;                 // uint32[WE]  only in the staged kernels (0 = absent)
+    uint32_t misc;                      // uint32[4]   [0] any-active flag
+    uint32_t bytes;                     // slice size, multiple of 16
+};
+
+struct Shot {
+    idx_t *P, *NX, *R;
+    uint32_t *growth, *newfull, *defect, *act0, *act1, *troot, *err, *corr, *misc;
+};
+
+LUF_DEV Shot bind(const Layout& l, unsigned char* base)
+{
+    Shot s;
+    s.P = (idx_t*)(base + l.P); s.NX = (idx_t*)(base + l.NX); s.R = (idx_t*)(base + l.R);
+    s.growth = (uint32_t*)(base + l.growth); s.newfull = (uint32_t*)(base + l.newfull);
+    s.defect = (uint32_t*)(base + l.defect);
+    s.act0 = (uint32_t*)(base + l.act0); s.act1 = (uint32_t*)(base + l.act1);
+    s.troot = (uint32_t*)(base + l.troot);
+    s.err = l.err ? (uint32_t*)(base + l.err) : 0;
+    s.corr = l.corr ? (uint32_t*)(base + l.corr) : 0;
+    s.misc = (uint32_t*)(base + l.misc);
+    return s;
+}
+
+// ------------------------------------------------------------------ helpers
+LUF_DEV uint32_t growth_of(const Shot& s, uint32_t e) { return (s.growth[e >> 4] >> ((e & 15u) * 2u)) & 3u; }
+
+// find without compression: safe while other lanes read the forest
+LUF_DEV uint32_t find_ro(const Shot& s, uint32_t v)
+{
+    uint32_t p;
+    while (!((p = s.P[v]) & ROOT_BIT)) v = p;
+    return v;
+}
+
+// uf.py:247-254 -- find with full path compression (single lane only)
+LUF_DEV uint32_t find_compress(const Shot& s, uint32_t v)
+{
+    uint32_t r = v, p;
+    while (!((p = s.P[r]) & ROOT_BIT)) r = p;
+    while (v != r) { p = s.P[v]; s.P[v] = (idx_t)r; v = p; }
+    return r;
+}
+
+// ------------------------------------------------------------ phase 0: reset
+// uf.py:79-96,496-519 -- every node a singleton cluster; a boundary node is its
+// own cluster boundary.  (The reference re-allocates N Python objects here,
+// 40-58 % of its time; this is ~N*6 bytes of shared-memory stores.)
+LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int lane, int nl)
+{
+    for (int v = lane; v < g.N; v += nl) {
+        s.P[v] = (idx_t)(ROOT_BIT | 1u);
+        s.NX[v] = (idx_t)v;                                  // circular member list
+        s.R[v] = (idx_t)(v < g.B ? (uint32_t)v + 1u : 0u);
+    }
+    const int GW = (g.E + 15) >> 4;
+    for (int w = lane; w < GW; w += nl) s.growth[w] = 0;
+    for (int w = lane; w < g.WE; w += nl) {
+        s.newfull[w] = 0;
+        if (s.err) s.err[w] = 0;
+        if (s.corr) s.corr[w] = 0;
+    }
+    for (int w = lane; w < g.WD; w += nl) { s.defect[w] = 0; s.act0[w] = 0; s.act1[w] = 0; }
+    for (int w = lane; w < g.WN; w += nl) s.troot[w] = 0;
+    if (lane < 4) s.misc[lane] = 0;
+    (void)l;
+}
+
+// --------------------------------------------------- phase 1: sample + syndrome
+struct Philox {
+    uint32_t c0, c1, c2, c3, k0, k1;    // counter, key
+    uint32_t o0, o1, o2, o3;            // buffered outputs (shifted out, no indexing -> registers)
+    int have;
+};
+
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so shot k's stream does
+// not depend on which warp, launch or GPU draws it.
+LUF_DEV void philox_block(Philox& r)
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t c0 = r.c0, c1 = r.c1, c2 = r.c2, c3 = r.c3, k0 = r.k0, k1 = r.k1;
+#if !defined(LUF_HOST_EMU)
+    #pragma unroll
+#endif
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = luf_mulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = luf_mulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    r.o0 = c0; r.o1 = c1; r.o2 = c2; r.o3 = c3;
+    r.c3 += 1u;             // block counter
+    r.have = 4;
+}
+
+LUF_DEV uint32_t philox_next(Philox& r)
+{
+    if (r.have == 0) philox_block(r);
+    const uint32_t v = r.o0;
+    r.o0 = r.o1; r.o1 = r.o2; r.o2 = r.o3;
+    --r.have;
+    return v;
+}
+
+// Flip edge e: record it, toggle the defect bit of its detector endpoints
+// (_base_classes.py:427-450), and return whether it counts for the logical
+// parity (_schemes.py:127-128).
+LUF_DEV uint32_t flip_edge(const GraphView& g, const Shot& s, uint32_t e)
+{
+    if (s.err) luf_atomic_xor(&s.err[e >> 5], 1u << (e & 31u));
+    const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+    const uint32_t u = uv & 0xFFFFu, v = uv >> 16;
+    if (u >= (uint32_t)g.B) luf_atomic_xor(&s.defect[(u - g.B) >> 5], 1u << ((u - g.B) & 31u));
+    if (v >= (uint32_t)g.B) luf_atomic_xor(&s.defect[(v - g.B) >> 5], 1u << ((v - g.B) & 31u));
+    return (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
+}
+
+// Each lane owns a contiguous range of the class-sorted fresh-edge list and
+// walks it with geometric skips: the gap to the next flipped edge of a class
+// with flip probability p is floor(log(U)/log(1-p)).  Same distribution as the
+// reference's one Bernoulli draw per edge, ~p*F + classes draws per lane
+// instead of F/NL.  Returns this lane's parity of flipped west-boundary edges.
+LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams& sp,
+                           uint64_t shot, int lane, int nl)
+{
+    const uint32_t a = (uint32_t)(((uint64_t)g.F * (uint32_t)lane) / (uint32_t)nl);
+    const uint32_t b = (uint32_t)(((uint64_t)g.F * (uint32_t)(lane + 1)) / (uint32_t)nl);
+    if (a >= b) return 0;
+    Philox rng;
+    rng.c0 = (uint32_t)shot; rng.c1 = (uint32_t)(shot >> 32); rng.c2 = (uint32_t)lane; rng.c3 = 0;
+    rng.k0 = sp.key0; rng.k1 = sp.key1; rng.have = 0;
+    rng.o0 = rng.o1 = rng.o2 = rng.o3 = 0;
+    uint32_t parity = 0, start = 0;
+    for (int c = 0; c < g.n_classes; ++c) {
+        const uint32_t end = LUF_LDG(&g.class_end[c]);
+        const uint32_t lo = a > start ? a : start, hi = b < end ? b : end;
+        start = end;
+        if (lo >= hi) { if (end >= b) break; continue; }
+        const float p = sp.p[c];
+        if (p <= 0.0f) continue;
+        uint32_t pos = lo;
+        for (;;) {
+            if (p < 1.0f) {
+                const float u = ((float)philox_next(rng) + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+                const float gf = luf_log2(u) * sp.inv_log2_q[c];
+                const uint32_t gap = gf >= 1.0e9f ? 1000000000u : (uint32_t)gf;
+                if (gap >= hi - pos) break;
+                pos += gap;
+            }
+            parity ^= flip_edge(g, s, LUF_LDG(&g.fresh_perm[pos]));
+            if (++pos >= hi) break;
+        }
+    }
+    return parity;
+}
+
+// uf.py:98-104 load: every defect is an odd, active singleton cluster.
+LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    for (int w = lane; w < g.WD; w += nl) {
+        uint32_t bits = s.defect[w];
+        s.act0[w] = bits;
+        if (bits) s.misc[0] = 1;
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            s.R[g.B + 32 * w + b] = (idx_t)ODD_BIT;
+        }
+    }
+}
+
+// ------------------------------------------------------- phase 2a: grow a round
+// uf.py:221-222,234-245.  vision(C) = edges incident to C's members that are not
+// yet FULL/BURNT.  A lane takes active roots (one bitmap word at a time) and
+// walks each cluster's circular member list.  An edge inside one cluster is in
+// that cluster's vision once: only its first endpoint adds.  Two different
+// active clusters each add 1.  The 2-bit counters saturate at FULL.
+LUF_DEV void ph_grow(const GraphView& g, const Shot& s, int cur, int lane, int nl)
+{
+    const uint32_t* act = cur ? s.act1 : s.act0;
+    for (int w = lane; w < g.WD; w += nl) {
+        uint32_t bits = act[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t r = (uint32_t)(g.B + 32 * w + b);
+            uint32_t u = r;
+            do {
+                const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
+                for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
+                    const uint32_t ent = LUF_LDG(&g.inc[k]);
+                    const uint32_t e = ent & 0xFFFFu;
+                    const uint32_t sh = (e & 15u) * 2u;
+                    if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
+                    if (!(ent >> 31)) {                       // second endpoint: skip if same cluster
+                        const uint32_t o = (ent >> 16) & 0x7FFFu;
+                        if (o == r || find_ro(s, o) == r) continue;
+                    }
+                    const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+                    if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
+                    else if (old == G_HALF) luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
+                }
+                u = s.NX[u];
+            } while (u != r);
+        }
+    }
+}
+
+// --------------------------------------------------- phase 2b: merge (one lane)
+// uf.py:223-229,256-301 in canonical order: this round's newly FULL edges in
+// ascending edge id.  Union by size, ties keep the cluster of the edge's first
+// endpoint; parity XOR; boundary by inclination; member lists spliced.
+LUF_DEV void merge_edge(const GraphView& g, const Shot& s, int flags, uint32_t e)
+{
+    const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+    const uint32_t cu = find_compress(s, uv & 0xFFFFu), cv = find_compress(s, uv >> 16);
+    if (flags & FLAG_DYNAMIC) {                                   // uf.py:261-266
+        if (cu == cv || ((s.R[cu] & 0x7FFFu) && (s.R[cv] & 0x7FFFu))) {
+            s.growth[e >> 4] |= 3u << ((e & 15u) * 2u);           // FULL(2) -> BURNT(3)
+            return;
+        }
+    } else if (cu == cv) return;                                  // uf.py:256-259
+    const uint32_t su = s.P[cu] & 0x7FFFu, sv = s.P[cv] & 0x7FFFu;
+    const uint32_t L = su >= sv ? cu : cv, S = su >= sv ? cv : cu;    // uf.py:270-273
+    s.P[S] = (idx_t)L;
+    s.P[L] = (idx_t)(ROOT_BIT | (su + sv));
+    const uint32_t rl = s.R[L], rs = s.R[S];
+    uint32_t bl = rl & 0x7FFFu;
+    const uint32_t bs = rs & 0x7FFFu;
+    if (flags & FLAG_WEST) {                                      // uf.py:544-549
+        if (bs && (!bl || LUF_LDG(&g.node_long[bs - 1]) < LUF_LDG(&g.node_long[bl - 1]))) bl = bs;
+    } else if (!bl && bs) bl = bs;                                // uf.py:536-538
+    s.R[L] = (idx_t)(((rl ^ rs) & ODD_BIT) | bl);
+    const idx_t t = s.NX[L]; s.NX[L] = s.NX[S]; s.NX[S] = t;      // splice the circular lists
+}
+
+LUF_DEV void ph_merge(const GraphView& g, const Shot& s, int flags, int lane)
+{
+    if (lane != 0) return;
+    for (int w = 0; w < g.WE; ++w) {
+        uint32_t bits = s.newfull[w];
+        if (!bits) continue;
+        s.newfull[w] = 0;
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            merge_edge(g, s, flags, (uint32_t)(32 * w + b));
+        }
+    }
+    s.misc[0] = 0;
+}
+
+// ------------------------------------------ phase 2c: next round's active roots
+// uf.py:290-301: active <=> odd and without boundary.  Every active cluster of
+// the next round contains an active root of this round.
+LUF_DEV void ph_clear_next(const GraphView& g, const Shot& s, int cur, int lane, int nl)
+{
+    uint32_t* nxt = cur ? s.act0 : s.act1;
+    for (int w = lane; w < g.WD; w += nl) nxt[w] = 0;
+}
+
+LUF_DEV void ph_reactivate(const GraphView& g, const Shot& s, int cur, int lane, int nl)
+{
+    const uint32_t* act = cur ? s.act1 : s.act0;
+    uint32_t* nxt = cur ? s.act0 : s.act1;
+    for (int w = lane; w < g.WD; w += nl) {
+        uint32_t bits = act[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t r = find_ro(s, (uint32_t)(g.B + 32 * w + b));
+            if (s.R[r] == (idx_t)ODD_BIT) {                     // odd, no boundary
+                luf_atomic_or(&nxt[(r - g.B) >> 5], 1u << ((r - g.B) & 31u));
+                s.misc[0] = 1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------- phase 3: peel
+// uf.py:314-324: one tree per cluster, rooted at cluster.boundary or else the
+// union-find root.  Clusters without a defect cannot contribute a correction
+// edge, so only clusters of defects are rooted.
+LUF_DEV void ph_tree_roots(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    for (int w = lane; w < g.WD; w += nl) {
+        uint32_t bits = s.defect[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t r = find_ro(s, (uint32_t)(g.B + 32 * w + b));
+            const uint32_t bn = s.R[r] & 0x7FFFu;
+            const uint32_t t = bn ? bn - 1u : r;
+            luf_atomic_or(&s.troot[t >> 5], 1u << (t & 31u));
+        }
+    }
+}
+
+// The union-find arrays are dead now; reuse them for the traversal:
+//   P  -> tree edge towards the root (NONE16 = undiscovered)
+//   NX -> link of the LIFO stack          R -> link of the discovery chain
+LUF_DEV void ph_peel_init(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    for (int v = lane; v < g.N; v += nl) s.P[v] = (idx_t)NONE16;
+}
+
+// uf.py:326-344 (LIFO traversal, neighbours in ascending edge id) and
+// uf.py:305-312 (walk the discovery order backwards; a node still carrying a
+// defect sends it to its parent through the tree edge).  Returns this lane's
+// parity of correction edges on the west boundary.
+LUF_DEV uint32_t ph_peel(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    idx_t* tedge = s.P; idx_t* stk = s.NX; idx_t* chain = s.R;
+    uint32_t parity = 0;
+    for (int w = lane; w < g.WN; w += nl) {
+        uint32_t bits = s.troot[w];
+        s.troot[w] = 0;
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t root = (uint32_t)(32 * w + b);
+            tedge[root] = (idx_t)TREE_ROOT;
+            stk[root] = (idx_t)NONE16;
+            uint32_t top = root, last = NONE16;
+            while (top != NONE16) {
+                const uint32_t u = top;
+                top = stk[u];
+                const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
+                for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
+                    const uint32_t ent = LUF_LDG(&g.inc[k]);
+                    const uint32_t e = ent & 0xFFFFu;
+                    if (growth_of(s, e) != G_FULL) continue;
+                    const uint32_t o = (ent >> 16) & 0x7FFFu;
+                    if (tedge[o] != NONE16) continue;
+                    tedge[o] = (idx_t)e;
+                    stk[o] = (idx_t)top; top = o;
+                    chain[o] = (idx_t)last; last = o;
+                }
+            }
+            for (uint32_t v = last; v != NONE16; v = chain[v]) {
+                if (v < (uint32_t)g.B) continue;
+                const uint32_t dv = v - g.B;
+                if (!((s.defect[dv >> 5] >> (dv & 31u)) & 1u)) continue;
+                const uint32_t e = tedge[v];
+                if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
+                parity ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
+                const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+                const uint32_t par = (uv & 0xFFFFu) == v ? (uv >> 16) : (uv & 0xFFFFu);
+                if (par >= (uint32_t)g.B)
+                    luf_atomic_xor(&s.defect[(par - g.B) >> 5], 1u << ((par - g.B) & 31u));
+            }
+        }
+    }
+    return parity;
+}
+
+// ------------------------------------------------------------------ drivers
+// uf.py:200-209 validate: rounds of grow / merge until no cluster is active.
+// Returns the number of growth rounds.  `lane` is this thread's lane on the
+// device; the host emulation iterates it inside LUF_PHASE.
+LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, int nl)
+{
+    int cur = 0, rounds = 0;
+    (void)lane;
+    while (s.misc[0]) {
+        LUF_PHASE(ph_grow(g, s, cur, lane, nl));
+        LUF_PHASE(ph_clear_next(g, s, cur, lane, nl); ph_merge(g, s, flags, lane));
+        LUF_PHASE(ph_reactivate(g, s, cur, lane, nl));
+        cur ^= 1;
+        ++rounds;
+    }
+    return rounds;
+}
+
+// uf.py:305-312 peel.  Returns (per lane on the device, total in the
+// emulation) the parity of correction edges on the west boundary.
+LUF_DEV uint32_t uf_peel(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    uint32_t parity = 0;
+    (void)lane;
+    LUF_PHASE(ph_tree_roots(g, s, lane, nl));
+    LUF_PHASE(ph_peel_init(g, s, lane, nl));
+    LUF_PHASE(parity ^= ph_peel(g, s, lane, nl));
+    return parity;
+}
+
+}  // namespace luf

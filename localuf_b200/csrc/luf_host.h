@@ -1,0 +1,112 @@
+// luf_host.h -- host-side preparation shared by the CUDA library and by the
+// host emulation harness of the kernel phases (tests/emu): packing the flat
+// graph description into the tables of luf::GraphView and laying out one
+// shot's state.
+#pragma once
+#include <stdint.h>
+
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/luf_b200.h"
+#include "luf_core.cuh"
+
+namespace luf {
+
+inline int words32(int nbits) { return (nbits + 31) / 32; }
+
+struct PackedGraph {
+    int N = 0, B = 0, E = 0, F = 0, n_classes = 0;
+    std::vector<uint32_t> inc_off, inc, edge_uv, west_mask, class_end;
+    std::vector<int16_t> node_long;
+    std::vector<uint16_t> fresh_perm;
+};
+
+// Returns "" on success, else why the graph cannot be packed.
+inline std::string pack_graph(const luf_graph_desc& d, PackedGraph& out)
+{
+    const int N = d.n_nodes, B = d.n_boundary, E = d.n_edges;
+    if (N <= 0 || E <= 0 || B < 0 || B > N) return "empty or inconsistent graph";
+    if (N > 32767 || E > 0xFFFD)
+        return "graph too large for the 16-bit state layout (N <= 32767, E <= 65533)";
+    if (d.n_classes < 1 || d.n_classes > MAX_CLASSES) return "n_classes out of range";
+    out.N = N; out.B = B; out.E = E; out.n_classes = d.n_classes;
+    out.inc_off.assign(N + 1, 0);
+    out.inc.assign(2 * (size_t)E, 0);
+    out.edge_uv.assign(E, 0);
+    out.node_long.assign(N, 0);
+    for (int e = 0; e < E; ++e) {
+        const int u = d.edge_u[e], v = d.edge_v[e];
+        if (u < 0 || u >= N || v < 0 || v >= N) return "edge endpoint out of range";
+        out.edge_uv[e] = (uint32_t)u | ((uint32_t)v << 16);
+    }
+    for (int v = 0; v < N; ++v) {
+        if (((d.node_flags[v] & 1) != 0) != (v < B)) return "boundary nodes must be node indices [0, B)";
+        out.node_long[v] = (int16_t)d.node_long[v];
+    }
+    for (int v = 0; v <= N; ++v) out.inc_off[v] = (uint32_t)d.inc_off[v];
+    if (d.inc_off[N] != 2 * E) return "CSR size mismatch";
+    for (int v = 0; v < N; ++v) {
+        int prev = -1;
+        for (int k = d.inc_off[v]; k < d.inc_off[v + 1]; ++k) {
+            const int e = d.inc_edge[k], o = d.inc_other[k];
+            if (e <= prev) return "incident edges must ascend in edge id";
+            prev = e;
+            const bool first = d.edge_u[e] == v;
+            if ((first ? d.edge_v[e] : d.edge_u[e]) != o || (!first && d.edge_v[e] != v))
+                return "CSR entry does not match the edge list";
+            out.inc[k] = (uint32_t)e | ((uint32_t)o << 16) | (first ? 0x80000000u : 0u);
+        }
+    }
+    out.west_mask.assign(d.west_edge_mask, d.west_edge_mask + words32(E));
+    // fresh edges, stably sorted by probability class
+    out.class_end.assign(d.n_classes, 0);
+    out.fresh_perm.clear();
+    for (int c = 0; c < d.n_classes; ++c) {
+        for (int e = 0; e < E; ++e)
+            if (d.edge_class[e] == c) out.fresh_perm.push_back((uint16_t)e);
+        out.class_end[c] = (uint32_t)out.fresh_perm.size();
+    }
+    out.F = (int)out.fresh_perm.size();
+    return "";
+}
+
+inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr)
+{
+    Layout l;
+    uint32_t off = 0;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
+    const uint32_t WE = words32(E), WD = words32(N - B) ? words32(N - B) : 1, WN = words32(N);
+    l.P = take(2u * N); l.NX = take(2u * N); l.R = take(2u * N);
+    l.growth = take(4u * ((E + 15) / 16));
+    l.newfull = take(4u * WE);
+    l.defect = take(4u * WD); l.act0 = take(4u * WD); l.act1 = take(4u * WD);
+    l.troot = take(4u * WN);
+    l.misc = take(16);
+    l.err = keep_err ? take(4u * WE) : 0;
+    l.corr = keep_corr ? take(4u * WE) : 0;
+    l.bytes = off;
+    return l;
+}
+
+inline SampleParams make_sample_params(const double* class_p, int n_classes, uint64_t seed)
+{
+    SampleParams sp;
+    for (int c = 0; c < MAX_CLASSES; ++c) { sp.p[c] = 0.f; sp.inv_log2_q[c] = 0.f; }
+    for (int c = 0; c < n_classes; ++c) {
+        const double p = class_p[c];
+        sp.p[c] = p >= 1.0 ? 1.0f : (p <= 0.0 ? 0.0f : (float)p);
+        if (p > 0.0 && p < 1.0) {
+            if (sp.p[c] <= 0.0f) sp.p[c] = 1e-38f;          // keep tiny p "on"
+            if (sp.p[c] >= 1.0f) sp.p[c] = 0.99999994f;
+            sp.inv_log2_q[c] = (float)(1.0 / (std::log1p(-p) / std::log(2.0)));
+        }
+    }
+    sp.key0 = (uint32_t)seed; sp.key1 = (uint32_t)(seed >> 32);
+    return sp;
+}
+
+}  // namespace luf

@@ -1,0 +1,448 @@
+// luf_kernels.cu -- CUDA kernels (sm_100a) and C ABI of the B200 batched
+// Union-Find decoding engine.  See include/luf_b200.h for the interface and
+// luf_core.cuh for the per-shot phases.
+//
+// Execution model: one warp owns one shot at a time; a block is a handful of
+// independent warps; the grid is persistent (a multiple of the SM count) and
+// every warp strides over the shot range.  All decoder state of a shot lives
+// in the warp's slice of dynamic shared memory; the read-only graph tables sit
+// in global memory and are served by L1/L2.  There is no tensor-core work in
+// this path (no dense contraction) and nothing to tile with TMA at these sizes:
+// HBM sees only the bit-packed inputs/outputs of the staged kernels, and
+// nothing at all in the fused Monte-Carlo kernel.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "luf_host.h"
+
+using namespace luf;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return fail(LUF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ------------------------------------------------------------------ kernels
+static const int WARP = 32;
+
+__device__ __forceinline__ unsigned char* warp_slice(const Layout& l)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    return smem + (size_t)(threadIdx.x >> 5) * l.bytes;
+}
+
+// Fused K1 + K2 + K4 for the UF decoder, batch scheme (_schemes.py:116-155).
+__global__ void k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
+                        unsigned long long shot0, long long nshots, unsigned long long* counts)
+{
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    const Shot s = bind(l, warp_slice(l));
+    const long long stride = (long long)gridDim.x * wpb;
+    unsigned int fails = 0;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        uint32_t parity = 0;
+        LUF_PHASE(ph_reset(g, l, s, lane, nl));
+        LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
+        LUF_PHASE(ph_load(g, s, lane, nl));
+        uf_validate(g, s, flags, lane, nl);
+        parity ^= uf_peel(g, s, lane, nl);
+        fails += __reduce_xor_sync(0xffffffffu, parity) & 1u;
+    }
+    if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+}
+
+// Staged K2: syndromes in, corrections (+ growth, rounds) out (uf.py:106-119).
+__global__ void k_decode_uf(GraphView g, Layout l, int flags, long long nshots,
+                            const uint32_t* __restrict__ syn, uint32_t* __restrict__ corr,
+                            uint32_t* __restrict__ growth2b, int32_t* __restrict__ steps)
+{
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    const Shot s = bind(l, warp_slice(l));
+    const long long stride = (long long)gridDim.x * wpb;
+    const int GW = (g.E + 15) >> 4;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        LUF_PHASE(ph_reset(g, l, s, lane, nl));
+        LUF_PHASE(for (int w = lane; w < g.WD; w += nl) s.defect[w] = __ldg(&syn[k * g.WD + w]));
+        LUF_PHASE(ph_load(g, s, lane, nl));
+        const int rounds = uf_validate(g, s, flags, lane, nl);
+        if (growth2b)
+            for (int w = lane; w < GW; w += nl) growth2b[k * GW + w] = s.growth[w];
+        uf_peel(g, s, lane, nl);
+        for (int w = lane; w < g.WE; w += nl) corr[k * g.WE + w] = s.corr[w];
+        if (steps && lane == 0) { steps[2 * k] = rounds; steps[2 * k + 1] = 0; }
+        __syncwarp();
+    }
+}
+
+// Staged K1: bit-packed errors and syndromes to HBM
+// (noise/main.py:114-115,309-314; _base_classes.py:427-450).
+__global__ void k_sample(GraphView g, Layout l, SampleParams sp, unsigned long long shot0,
+                         long long nshots, uint32_t* __restrict__ err, uint32_t* __restrict__ syn)
+{
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    const Shot s = bind(l, warp_slice(l));
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        LUF_PHASE(for (int w = lane; w < g.WE; w += nl) s.err[w] = 0;
+                  for (int w = lane; w < g.WD; w += nl) s.defect[w] = 0);
+        LUF_PHASE(ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
+        for (int w = lane; w < g.WE; w += nl) err[k * g.WE + w] = s.err[w];
+        for (int w = lane; w < g.WD; w += nl) syn[k * g.WD + w] = s.defect[w];
+        __syncwarp();
+    }
+}
+
+// Staged K4: leftover parity on the west boundary (_schemes.py:123-129,154-155).
+__global__ void k_check(int WE, long long nshots, const uint32_t* __restrict__ west_mask,
+                        const uint32_t* __restrict__ err, const uint32_t* __restrict__ corr,
+                        uint8_t* __restrict__ logical, unsigned long long* fail_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const long long stride = (long long)gridDim.x * wpb;
+    unsigned int fails = 0;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        uint32_t acc = 0;
+        for (int w = lane; w < WE; w += WARP)
+            acc ^= (__ldg(&err[k * WE + w]) ^ __ldg(&corr[k * WE + w])) & __ldg(&west_mask[w]);
+        acc = __reduce_xor_sync(0xffffffffu, acc);
+        const unsigned int bit = __popc(acc) & 1u;
+        if (lane == 0 && logical) logical[k] = (uint8_t)bit;
+        fails += bit;
+    }
+    if (lane == 0 && fails) atomicAdd(fail_count, (unsigned long long)fails);
+}
+
+// ------------------------------------------------------------------- graph
+struct luf_graph {
+    int device = 0, sm_count = 0, max_smem = 0;
+    PackedGraph host;
+    GraphView view{};
+    std::vector<void*> allocs;
+    Layout lay_fused{}, lay_decode{}, lay_sample{};
+    // grow-only scratch for the *_host entry points
+    void* scratch[6] = {0, 0, 0, 0, 0, 0};
+    size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
+    long long launches = 0;
+    std::mutex mu;
+};
+
+template <class T>
+static int upload(luf_graph* g, const std::vector<T>& v, const T** out)
+{
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, v.size() * sizeof(T) + 16));
+    g->allocs.push_back(p);
+    CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)p;
+    return 0;
+}
+
+static int scratch_get(luf_graph* g, int slot, size_t bytes, void** out)
+{
+    if (bytes > g->scratch_bytes[slot]) {
+        if (g->scratch[slot]) CUDA_TRY(cudaFree(g->scratch[slot]));
+        g->scratch[slot] = nullptr; g->scratch_bytes[slot] = 0;
+        CUDA_TRY(cudaMalloc(&g->scratch[slot], bytes));
+        g->scratch_bytes[slot] = bytes;
+    }
+    *out = g->scratch[slot];
+    return 0;
+}
+
+struct LaunchCfg { int grid, block; size_t smem; };
+
+// Warps per block and a persistent grid: as many blocks per SM as the
+// shared-memory budget allows, never more blocks than there is work.
+template <class K>
+static int plan_launch(luf_graph* g, K kernel, const Layout& l, long long nshots, LaunchCfg* cfg)
+{
+    if (l.bytes > (uint32_t)g->max_smem)
+        return fail(LUF_ERR_UNSUPPORTED, "one shot's decoder state (" + std::to_string(l.bytes) +
+                    " B) exceeds the shared memory of an SM; CTA-per-shot kernels are not built yet");
+    int wpb = g->max_smem / (int)l.bytes;
+    if (wpb > 4) wpb = 4;
+    const size_t smem = (size_t)wpb * l.bytes;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * WARP, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)g->sm_count * per_sm;
+    const long long need = (nshots + wpb - 1) / wpb;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    cfg->grid = (int)blocks; cfg->block = wpb * WARP; cfg->smem = smem;
+    return 0;
+}
+
+static int check_device(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(LUF_ERR_NO_DEVICE, "no CUDA device visible; the engine has no CPU fallback");
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char* luf_last_error(void) { return g_last_error.c_str(); }
+
+int luf_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
+{
+    if (!desc || !out) return fail(LUF_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (int rc = check_device()) return rc;
+    luf_graph* g = new (std::nothrow) luf_graph();
+    if (!g) return fail(LUF_ERR_INVALID, "out of host memory");
+    const std::string why = pack_graph(*desc, g->host);
+    if (!why.empty()) {
+        delete g;
+        return fail(why.find("too large") != std::string::npos ? LUF_ERR_UNSUPPORTED : LUF_ERR_INVALID, why);
+    }
+    g->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete g; return fail(LUF_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+    cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&g->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    const PackedGraph& p = g->host;
+    GraphView& v = g->view;
+    v.N = p.N; v.B = p.B; v.E = p.E; v.F = p.F; v.n_classes = p.n_classes;
+    v.WE = words32(p.E); v.WD = words32(p.N - p.B); v.WN = words32(p.N);
+    int rc = 0;
+    if ((rc = upload(g, p.inc_off, &v.inc_off)) || (rc = upload(g, p.inc, &v.inc)) ||
+        (rc = upload(g, p.edge_uv, &v.edge_uv)) || (rc = upload(g, p.west_mask, &v.west_mask)) ||
+        (rc = upload(g, p.node_long, &v.node_long)) || (rc = upload(g, p.fresh_perm, &v.fresh_perm)) ||
+        (rc = upload(g, p.class_end, &v.class_end))) {
+        luf_graph_destroy(g);
+        return rc;
+    }
+    g->lay_fused = make_layout(p.N, p.B, p.E, false, false);
+    g->lay_decode = make_layout(p.N, p.B, p.E, false, true);
+    {   // the sampler only needs the error and defect bitmaps
+        Layout l; memset(&l, 0, sizeof(l));
+        uint32_t off = 0;
+        l.defect = off; off = align16(off + 4u * (uint32_t)(v.WD ? v.WD : 1));
+        l.err = off; off = align16(off + 4u * (uint32_t)v.WE);
+        l.bytes = off;
+        // keep every pointer inside the slice (unused arrays alias the start)
+        g->lay_sample = l;
+    }
+    *out = g;
+    return 0;
+}
+
+int luf_graph_destroy(luf_graph* g)
+{
+    if (!g) return 0;
+    cudaSetDevice(g->device);
+    for (void* p : g->allocs) cudaFree(p);
+    for (void* p : g->scratch) if (p) cudaFree(p);
+    delete g;
+    return 0;
+}
+
+int luf_graph_words(const luf_graph* g, int32_t* edge_words, int32_t* detector_words, int32_t* growth_words)
+{
+    if (!g) return fail(LUF_ERR_INVALID, "null graph");
+    if (edge_words) *edge_words = g->view.WE;
+    if (detector_words) *detector_words = g->view.WD;
+    if (growth_words) *growth_words = (g->view.E + 15) / 16;
+    return 0;
+}
+
+int64_t luf_launch_count(const luf_graph* g) { return g ? g->launches : 0; }
+
+static int check_decoder(int decoder, int flags)
+{
+    if (decoder == LUF_DEC_UF) {
+        if (flags & ~(LUF_UF_DYNAMIC | LUF_UF_WEST)) return fail(LUF_ERR_INVALID, "unknown UF flag");
+        return 0;
+    }
+    if (decoder == LUF_DEC_MACAR || decoder == LUF_DEC_ACTIS || decoder == LUF_DEC_SNOWFLAKE)
+        return fail(LUF_ERR_UNSUPPORTED, "decoder not built into this library yet");
+    return fail(LUF_ERR_INVALID, "unknown decoder");
+}
+
+int luf_sample(luf_graph* g, const double* class_p_host, uint64_t seed, uint64_t shot0, int64_t nshots,
+               uint32_t* err_bits_dev, uint32_t* syn_bits_dev, void* stream)
+{
+    if (!g || !class_p_host || !err_bits_dev || !syn_bits_dev || nshots < 0)
+        return fail(LUF_ERR_INVALID, "luf_sample: bad argument");
+    if (nshots == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
+    LaunchCfg c;
+    if (int rc = plan_launch(g, k_sample, g->lay_sample, nshots, &c)) return rc;
+    k_sample<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_sample, sp, shot0, nshots,
+                                                                 err_bits_dev, syn_bits_dev);
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
+int luf_decode_batch(luf_graph* g, int decoder, int flags, int64_t nshots, const uint32_t* syn_bits_dev,
+                     uint32_t* corr_bits_dev, uint32_t* growth2b_dev, int32_t* steps_dev, void* stream)
+{
+    if (!g || !syn_bits_dev || !corr_bits_dev || nshots < 0)
+        return fail(LUF_ERR_INVALID, "luf_decode_batch: bad argument");
+    if (int rc = check_decoder(decoder, flags)) return rc;
+    if (nshots == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    LaunchCfg c;
+    if (int rc = plan_launch(g, k_decode_uf, g->lay_decode, nshots, &c)) return rc;
+    k_decode_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_decode, flags, nshots,
+                                                                    syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
+int luf_check(luf_graph* g, int64_t nshots, const uint32_t* err_bits_dev, const uint32_t* corr_bits_dev,
+              uint8_t* logical_dev, unsigned long long* fail_count_dev, void* stream)
+{
+    if (!g || !err_bits_dev || !corr_bits_dev || !fail_count_dev || nshots < 0)
+        return fail(LUF_ERR_INVALID, "luf_check: bad argument");
+    if (nshots == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const int block = 256, wpb = block / WARP;
+    long long blocks = (nshots + wpb - 1) / wpb;
+    const long long cap = (long long)g->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    k_check<<<(int)blocks, block, 0, (cudaStream_t)stream>>>(g->view.WE, nshots, g->view.west_mask, err_bits_dev,
+                                                              corr_bits_dev, logical_dev, fail_count_dev);
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
+int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host, uint64_t seed,
+               uint64_t shot0, int64_t nshots, unsigned long long* counts_dev, void* stream)
+{
+    if (!g || !class_p_host || !counts_dev || nshots < 0) return fail(LUF_ERR_INVALID, "luf_mc_run: bad argument");
+    if (int rc = check_decoder(decoder, flags)) return rc;
+    if (nshots == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
+    LaunchCfg c;
+    if (int rc = plan_launch(g, k_mc_uf, g->lay_fused, nshots, &c)) return rc;
+    k_mc_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, shot0, nshots, counts_dev);
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
+// ------------------------------------------------------- host-buffer variants
+int luf_mc_run_host(luf_graph* g, int decoder, int flags, const double* class_p_host, uint64_t seed,
+                    uint64_t shot0, int64_t nshots, unsigned long long counts_host[2])
+{
+    if (!g || !counts_host) return fail(LUF_ERR_INVALID, "luf_mc_run_host: bad argument");
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    void* d = nullptr;
+    if (int rc = scratch_get(g, 0, 16, &d)) return rc;
+    CUDA_TRY(cudaMemsetAsync(d, 0, 16, 0));
+    if (int rc = luf_mc_run(g, decoder, flags, class_p_host, seed, shot0, nshots, (unsigned long long*)d, 0)) return rc;
+    unsigned long long tmp[2] = {0, 0};
+    CUDA_TRY(cudaMemcpy(tmp, d, 16, cudaMemcpyDeviceToHost));
+    counts_host[0] += tmp[0]; counts_host[1] += tmp[1];
+    return 0;
+}
+
+int luf_decode_batch_host(luf_graph* g, int decoder, int flags, int64_t nshots, const uint32_t* syn_bits_host,
+                          uint32_t* corr_bits_host, uint32_t* growth2b_host, int32_t* steps_host)
+{
+    if (!g || !syn_bits_host || !corr_bits_host || nshots < 0)
+        return fail(LUF_ERR_INVALID, "luf_decode_batch_host: bad argument");
+    if (nshots == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t n = (size_t)nshots, WE = g->view.WE, WD = g->view.WD, GW = (g->view.E + 15) / 16;
+    void *syn, *corr, *gr = nullptr, *st = nullptr;
+    int rc;
+    if ((rc = scratch_get(g, 1, n * WD * 4, &syn)) || (rc = scratch_get(g, 2, n * WE * 4, &corr))) return rc;
+    if (growth2b_host && (rc = scratch_get(g, 3, n * GW * 4, &gr))) return rc;
+    if (steps_host && (rc = scratch_get(g, 4, n * 8, &st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(syn, syn_bits_host, n * WD * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = luf_decode_batch(g, decoder, flags, nshots, (const uint32_t*)syn, (uint32_t*)corr,
+                               (uint32_t*)gr, (int32_t*)st, 0))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(corr_bits_host, corr, n * WE * 4, cudaMemcpyDeviceToHost, 0));
+    if (gr) CUDA_TRY(cudaMemcpyAsync(growth2b_host, gr, n * GW * 4, cudaMemcpyDeviceToHost, 0));
+    if (st) CUDA_TRY(cudaMemcpyAsync(steps_host, st, n * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int luf_sample_host(luf_graph* g, const double* class_p_host, uint64_t seed, uint64_t shot0, int64_t nshots,
+                    uint32_t* err_bits_host, uint32_t* syn_bits_host)
+{
+    if (!g || !err_bits_host || !syn_bits_host || nshots < 0) return fail(LUF_ERR_INVALID, "luf_sample_host: bad argument");
+    if (nshots == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t n = (size_t)nshots, WE = g->view.WE, WD = g->view.WD;
+    void *err, *syn;
+    int rc;
+    if ((rc = scratch_get(g, 1, n * WD * 4, &syn)) || (rc = scratch_get(g, 2, n * WE * 4, &err))) return rc;
+    if ((rc = luf_sample(g, class_p_host, seed, shot0, nshots, (uint32_t*)err, (uint32_t*)syn, 0))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(err_bits_host, err, n * WE * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(syn_bits_host, syn, n * WD * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int luf_check_host(luf_graph* g, int64_t nshots, const uint32_t* err_bits_host, const uint32_t* corr_bits_host,
+                   uint8_t* logical_host, unsigned long long* fail_count_host)
+{
+    if (!g || !err_bits_host || !corr_bits_host || !fail_count_host || nshots < 0)
+        return fail(LUF_ERR_INVALID, "luf_check_host: bad argument");
+    if (nshots == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t n = (size_t)nshots, WE = g->view.WE;
+    void *err, *corr, *lg, *cnt;
+    int rc;
+    if ((rc = scratch_get(g, 1, n * WE * 4, &err)) || (rc = scratch_get(g, 2, n * WE * 4, &corr)) ||
+        (rc = scratch_get(g, 3, n, &lg)) || (rc = scratch_get(g, 0, 16, &cnt))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(err, err_bits_host, n * WE * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(corr, corr_bits_host, n * WE * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, 0));
+    if ((rc = luf_check(g, nshots, (const uint32_t*)err, (const uint32_t*)corr, (uint8_t*)lg,
+                        (unsigned long long*)cnt, 0))) return rc;
+    unsigned long long tmp = 0;
+    if (logical_host) CUDA_TRY(cudaMemcpyAsync(logical_host, lg, n, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpy(&tmp, cnt, 8, cudaMemcpyDeviceToHost));
+    *fail_count_host += tmp;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,4 @@
+"""Decoders of the B200 engine (reference: ``localuf/decoders/__init__.py``)."""
+from localuf_b200.decoders.uf import UF  # noqa: F401
+
+__all__ = ['UF']

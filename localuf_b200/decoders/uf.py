@@ -1,0 +1,63 @@
+"""Union-Find decoder (Delfosse & Nickerson), device-backed.
+
+Same constructor, attributes and error behaviour as the reference ``UF``
+(``localuf/decoders/uf.py:16-119``); the work happens in the CUDA kernels of
+``csrc/luf_core.cuh`` (grow / merge / peel in shared memory, one warp per
+shot).  Where the reference leaves the order of a round's merges and of the
+peeling traversal to CPython's ``set`` layout, the kernels use ascending edge
+id -- one legal execution of the reference algorithm ("UF parity
+contract").
+"""
+from __future__ import annotations
+
+from localuf_b200 import _engine
+from localuf_b200.decoders._base import BaseUF
+from localuf_b200.schemes import Frugal
+
+
+class UF(BaseUF):
+    _DECODER_ID = _engine.DEC_UF
+
+    def __init__(self, code, dynamic: bool = False, inclination: str = 'default'):
+        if isinstance(code.SCHEME, Frugal):
+            raise ValueError('UF incompatible with frugal scheme.')
+        if inclination not in ('default', 'west'):
+            raise ValueError(f"Unknown inclination {inclination!r}.")
+        super().__init__(code)
+        self._flags = (_engine.UF_DYNAMIC if dynamic else 0) | (_engine.UF_WEST if inclination == 'west' else 0)
+        self._pending: set = set()
+        self.round_count = 0
+
+    def __repr__(self):
+        return f'UF(code={self.CODE}, syndrome={self.syndrome})'
+
+    def decode(self, syndrome, draw=False, fig_width=None):
+        """``uf.py:106-119``: validate then peel; result in ``self.correction``; returns None."""
+        if draw:
+            raise NotImplementedError("Drawing is outside this engine (SURVEY.md section 2, row 14).")
+        self.validate(syndrome)
+        self.peel()
+
+    def validate(self, syndrome, log_history=False):
+        """``uf.py:200-209``.  The device decodes in one go; ``peel`` publishes the correction."""
+        self.syndrome = set(syndrome)
+        self._pending, steps = self._decode_one(self.syndrome)
+        self.round_count = int(steps[0])
+
+    def peel(self):
+        """``uf.py:305-312``."""
+        self.correction = set(self._pending)
+
+    def reset(self, no_boundaries=False):
+        if no_boundaries:
+            raise NotImplementedError("no_boundaries (complementary gap) is outside the hot path.")
+        super().reset()
+        self._pending = set()
+        self.round_count = 0
+
+    # -------------------------------------------------------- batched entry
+    def _mc_batch(self, noise_level: float, n: int, seed=None) -> int:
+        """Failure count of ``n`` fused sample->decode->check shots (``_schemes.py:116-155``)."""
+        eng = self.engine
+        return self._sharded_counts(
+            lambda s, lo, cnt: eng.mc_run_host(self._DECODER_ID, self._flags, noise_level, s, lo, cnt), n, seed)

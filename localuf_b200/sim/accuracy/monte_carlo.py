@@ -1,0 +1,39 @@
+"""Threshold data: logical failures per (distance, noise level).
+
+Same signature and DataFrame shape as ``localuf/sim/accuracy/monte_carlo.py:25-114``
+(rows ``'m'``, ``'n'``; column MultiIndex ``('d', 'p')``); the shots of every
+point run inside ``code.SCHEME.run`` on the device.
+"""
+from __future__ import annotations
+
+from pandas import DataFrame
+
+from localuf_b200.sim._height_calculator import get_heights
+
+
+def monte_carlo(sample_counts, code_class, decoder_class, noise, scheme='batch',
+                get_commit_height=None, get_buffer_height=None, parametrization='balanced',
+                demolition=False, monolingual=False, _merge_redundant_edges=True,
+                **kwargs_for_decoder_class):
+    results = {}
+    for d, points in sample_counts.items():
+        window_height, commit_height, buffer_height = get_heights(
+            d, points[0][1], scheme, get_commit_height, get_buffer_height)
+        code = code_class(
+            d, noise, scheme=scheme, window_height=window_height, commit_height=commit_height,
+            buffer_height=buffer_height, parametrization=parametrization, demolition=demolition,
+            monolingual=monolingual, _merge_redundant_edges=_merge_redundant_edges)
+        decoder = decoder_class(code, **kwargs_for_decoder_class)
+        for noise_level, n in points:
+            results[d, noise_level] = code.SCHEME.run(decoder, noise_level, n)
+    df = DataFrame(results, index=('m', 'n'))
+    df.columns.set_names(['d', 'p'], inplace=True)
+    return df
+
+
+def monte_carlo_results_to_sample_counts(results: DataFrame):
+    """Inverse of :func:`monte_carlo`'s first argument (``monte_carlo.py:104-114``)."""
+    out: dict = {}
+    for (d, noise_level), (_, n) in results.items():
+        out.setdefault(d, []).append((noise_level, int(n)))
+    return out

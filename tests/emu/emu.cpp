@@ -1,0 +1,91 @@
+// Host emulation harness for the kernel phases of localuf_b200/csrc/luf_core.cuh.
+//
+// TEST INFRASTRUCTURE ONLY.  Compiles the *same* phase source the CUDA kernels
+// use with -DLUF_HOST_EMU, runs the 32 lanes of a tile one after the other
+// inside each phase, and exposes the result through a small C interface so that
+// the CPU test-suite can compare the kernel logic with the oracle without a
+// GPU.  It checks logic, not concurrency; the GPU parity tests do the rest.
+#define LUF_HOST_EMU 1
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../localuf_b200/csrc/luf_host.h"
+
+using namespace luf;
+
+static GraphView view_of(const PackedGraph& p)
+{
+    GraphView g;
+    g.N = p.N; g.B = p.B; g.E = p.E;
+    g.WE = words32(p.E); g.WD = words32(p.N - p.B); g.WN = words32(p.N);
+    g.inc_off = p.inc_off.data(); g.inc = p.inc.data(); g.edge_uv = p.edge_uv.data();
+    g.west_mask = p.west_mask.data(); g.node_long = p.node_long.data();
+    g.F = p.F; g.n_classes = p.n_classes;
+    g.fresh_perm = p.fresh_perm.data(); g.class_end = p.class_end.data();
+    return g;
+}
+
+static void export_growth(const GraphView& g, const Shot& s, uint32_t* out)
+{
+    std::memcpy(out, s.growth, 4u * ((g.E + 15) / 16));
+}
+
+extern "C" {
+
+// Staged decode: syndromes in, corrections (+ growth, rounds) out.
+int emu_decode_uf(const luf_graph_desc* d, int flags, long long nshots, const uint32_t* syn,
+                  uint32_t* corr, uint32_t* growth2b, int32_t* steps)
+{
+    PackedGraph p;
+    if (!pack_graph(*d, p).empty()) return -1;
+    const GraphView g = view_of(p);
+    const Layout l = make_layout(p.N, p.B, p.E, false, true);
+    std::vector<unsigned char> mem(l.bytes);
+    const Shot s = bind(l, mem.data());
+    const int nl = 32, GW = (g.E + 15) / 16;
+    for (long long k = 0; k < nshots; ++k) {
+        LUF_PHASE(ph_reset(g, l, s, lane, nl));
+        for (int w = 0; w < g.WD; ++w) s.defect[w] = syn[k * g.WD + w];
+        LUF_PHASE(ph_load(g, s, lane, nl));
+        const int rounds = uf_validate(g, s, flags, 0, nl);
+        if (growth2b) export_growth(g, s, growth2b + k * GW);
+        uf_peel(g, s, 0, nl);
+        std::memcpy(corr + k * g.WE, s.corr, 4u * g.WE);
+        if (steps) { steps[2 * k] = rounds; steps[2 * k + 1] = 0; }
+    }
+    return 0;
+}
+
+// Fused Monte-Carlo shot loop; optionally exports the sampled errors, their
+// syndromes and the corrections so that the oracle can re-decode them.
+int emu_mc_uf(const luf_graph_desc* d, int flags, const double* class_p, unsigned long long seed,
+              unsigned long long shot0, long long nshots, unsigned long long counts[2],
+              uint32_t* err_out, uint32_t* syn_out, uint32_t* corr_out)
+{
+    PackedGraph p;
+    if (!pack_graph(*d, p).empty()) return -1;
+    const GraphView g = view_of(p);
+    const Layout l = make_layout(p.N, p.B, p.E, true, true);
+    const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
+    std::vector<unsigned char> mem(l.bytes);
+    const Shot s = bind(l, mem.data());
+    const int nl = 32;
+    unsigned long long fails = 0;
+    for (long long k = 0; k < nshots; ++k) {
+        uint32_t parity = 0;
+        LUF_PHASE(ph_reset(g, l, s, lane, nl));
+        LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + k, lane, nl));
+        if (err_out) std::memcpy(err_out + k * g.WE, s.err, 4u * g.WE);
+        if (syn_out) std::memcpy(syn_out + k * g.WD, s.defect, 4u * g.WD);
+        LUF_PHASE(ph_load(g, s, lane, nl));
+        uf_validate(g, s, flags, 0, nl);
+        parity ^= uf_peel(g, s, 0, nl);
+        if (corr_out) std::memcpy(corr_out + k * g.WE, s.corr, 4u * g.WE);
+        fails += parity & 1u;
+    }
+    counts[0] += fails; counts[1] += (unsigned long long)nshots;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+"""Build + bind the host emulation of the kernel phases (tests/emu/emu.cpp).
+TEST INFRASTRUCTURE ONLY -- checks kernel *logic* on the CPU suite."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, '_build', 'libluf_emu.so')
+CSRC = os.path.join(ROOT, 'localuf_b200', 'csrc')
+SRCS = [os.path.join(HERE, 'emu.cpp')] + [
+    os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))
+] + [os.path.join(ROOT, 'include', 'luf_b200.h')]
+
+
+def build():
+    if (not os.path.exists(LIB)) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRCS):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.run(['g++', '-O1', '-g', '-fPIC', '-shared', '-std=c++17', '-Wall', '-Wextra',
+                        '-o', LIB, SRCS[0]], check=True, capture_output=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _vp(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class Emu:
+    def __init__(self, code):
+        from localuf_b200._engine import make_desc, NOISE_KIND
+        self.flat = code.FLAT
+        self.noise = code.NOISE
+        self.desc, self._keep = make_desc(self.flat, NOISE_KIND[str(code.NOISE)])
+        self.WE = (self.flat.n_edges + 31) // 32
+        self.WD = (self.flat.n_detectors + 31) // 32
+        self.WG = (self.flat.n_edges + 15) // 16
+
+    def decode_uf(self, flags, syn_bits):
+        syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
+        n = syn.shape[0]
+        corr = np.zeros((n, self.WE), np.uint32)
+        growth = np.zeros((n, self.WG), np.uint32)
+        steps = np.zeros((n, 2), np.int32)
+        rc = lib().emu_decode_uf(C.byref(self.desc), flags, C.c_longlong(n), _vp(syn),
+                                 _vp(corr), _vp(growth), _vp(steps))
+        assert rc == 0
+        return corr, growth, steps
+
+    def mc_uf(self, flags, noise_level, seed, shot0, nshots, export=True):
+        cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
+        counts = (C.c_ulonglong * 2)(0, 0)
+        err = np.zeros((nshots, self.WE), np.uint32) if export else None
+        syn = np.zeros((nshots, self.WD), np.uint32) if export else None
+        corr = np.zeros((nshots, self.WE), np.uint32) if export else None
+        rc = lib().emu_mc_uf(C.byref(self.desc), flags, _vp(cp), C.c_ulonglong(seed),
+                             C.c_ulonglong(shot0), C.c_longlong(nshots), counts,
+                             _vp(err), _vp(syn), _vp(corr))
+        assert rc == 0
+        return int(counts[0]), err, syn, corr

@@ -1,0 +1,69 @@
+"""Kernel phase logic (localuf_b200/csrc/luf_core.cuh compiled for the host,
+lanes run sequentially) vs. reference goldens and the C oracle.  CPU-only: the
+real kernels are checked on the GPU by tests/test_gpu_*.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, make_code, golden_names
+
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
+import binding  # noqa: E402
+import emu_binding  # noqa: E402
+from localuf_b200._engine import unpack_growth  # noqa: E402
+
+FLAGS = {'default': 0, 'dynamic': 1, 'west': 2}
+
+
+@pytest.mark.parametrize('name', golden_names('uf_'))
+def test_emu_decode_matches_reference(name):
+    meta, arr = load_golden(name)
+    code = make_code(meta['spec'])
+    emu = emu_binding.Emu(code)
+    for variant, flags in FLAGS.items():
+        corr, growth2b, steps = emu.decode_uf(flags, arr['syn_bits'])
+        np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{variant}_growth'])
+        np.testing.assert_array_equal(steps[:, 0], arr[f'{variant}_rounds'])
+        np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
+
+
+@pytest.mark.parametrize('spec,p', [
+    (dict(code='Repetition', d=5, noise='code capacity'), 0.05),
+    (dict(code='Surface', d=9, noise='code capacity'), 0.10),
+    (dict(code='Surface', d=5, noise='phenomenological'), 0.05),
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.02),
+    (dict(code='Surface', d=11, noise='phenomenological'), 0.02),
+])
+def test_emu_fused_mc_vs_oracle(spec, p):
+    """Fused sample -> decode -> check: the oracle re-derives syndrome,
+    correction and logical outcome from the sampled errors."""
+    code = make_code(spec)
+    emu = emu_binding.Emu(code)
+    orc = binding.Oracle.from_code(code)
+    n = 300
+    fails, err, syn, corr = emu.mc_uf(0, p, seed=1234, shot0=17, nshots=n)
+    np.testing.assert_array_equal(orc.syndrome(err), syn)
+    ocorr, _, _ = orc.decode_batch(0, 0, syn, want_growth=False)
+    np.testing.assert_array_equal(ocorr, corr)
+    assert fails == int(orc.logical_batch(err, ocorr).sum())
+    # sampler: flip frequency of every probability class within 5 sigma
+    g = code.FLAT
+    bits = np.unpackbits(err.view(np.uint8), axis=1, bitorder='little')[:, :g.n_edges]
+    for c, pc in enumerate(code.NOISE.class_probabilities(p)):
+        members = np.flatnonzero(g.edge_class == c)
+        k, tot = int(bits[:, members].sum()), n * len(members)
+        assert abs(k - tot * pc) < 5 * (tot * pc * (1 - pc)) ** 0.5 + 1
+    assert not bits[:, g.edge_class == 255].any()
+
+
+def test_emu_sampler_extremes():
+    code = make_code(dict(code='Surface', d=3, noise='phenomenological'))
+    emu = emu_binding.Emu(code)
+    _, err, _, _ = emu.mc_uf(0, 0.0, 1, 0, 20)
+    assert not err.any()
+    _, err, syn, _ = emu.mc_uf(0, 1.0, 1, 0, 20)
+    bits = np.unpackbits(err.view(np.uint8), axis=1, bitorder='little')[:, :code.N_EDGES]
+    assert bits.all()
