@@ -33,6 +33,11 @@
   #define LUF_LDG(p) (*(p))
   // a phase = every lane of the tile runs `stmt`, then the tile synchronises
   #define LUF_PHASE(stmt) for (int lane = 0; lane < nl; ++lane) { stmt; }
+  // tile-wide reductions of a value the lanes accumulated during a phase (the
+  // emulation accumulates into one variable, so they are identities there)
+  #define LUF_ANY(x) ((x) != 0)
+  #define LUF_XOR(x) (x)
+  static inline uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 #else
   #define LUF_DEV __device__ __forceinline__
   LUF_DEV uint32_t luf_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
@@ -44,6 +49,9 @@
   LUF_DEV float luf_log2(float x) { return __log2f(x); }
   #define LUF_LDG(p) __ldg(p)
   #define LUF_PHASE(stmt) { stmt; } __syncwarp();
+  #define LUF_ANY(x) __any_sync(0xffffffffu, (x) != 0)
+  #define LUF_XOR(x) __reduce_xor_sync(0xffffffffu, (x))
+  LUF_DEV uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 #endif
 
 namespace luf {
@@ -54,6 +62,7 @@ static const uint32_t ODD_BIT = 0x8000u;    // R[root]: odd defect parity; low 1
 static const uint32_t NONE16 = 0xFFFFu;
 static const uint32_t TREE_ROOT = 0xFFFEu;
 static const int MAX_CLASSES = 32;
+static const int CLAIM_SLOTS = 128;      // power of two
 
 enum { G_UNGROWN = 0, G_HALF = 1, G_FULL = 2, G_BURNT = 3 };
 enum { FLAG_DYNAMIC = 1, FLAG_WEST = 2 };
@@ -89,13 +98,13 @@ struct Layout {
     uint32_t act0, act1;                // uint32[WD]  active roots (detector-indexed), ping-pong
     uint32_t troot;                     // uint32[WN]  tree roots to peel from
     uint32_t err, corr;                 // uint32[WE]  only in the staged kernels (0 = absent)
-    uint32_t misc;                      // uint32[4]   [0] any-active flag
+    uint32_t claim;                     // uint32[CLAIM_SLOTS]  merge reservations (see ph_merge_claim)
     uint32_t bytes;                     // slice size, multiple of 16
 };
 
 struct Shot {
     idx_t *P, *NX, *R;
-    uint32_t *growth, *newfull, *defect, *act0, *act1, *troot, *err, *corr, *misc;
+    uint32_t *growth, *newfull, *defect, *act0, *act1, *troot, *err, *corr, *claim;
 };
 
 LUF_DEV Shot bind(const Layout& l, unsigned char* base)
@@ -108,7 +117,7 @@ LUF_DEV Shot bind(const Layout& l, unsigned char* base)
     s.troot = (uint32_t*)(base + l.troot);
     s.err = l.err ? (uint32_t*)(base + l.err) : 0;
     s.corr = l.corr ? (uint32_t*)(base + l.corr) : 0;
-    s.misc = (uint32_t*)(base + l.misc);
+    s.claim = (uint32_t*)(base + l.claim);
     return s;
 }
 
@@ -152,7 +161,7 @@ LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int la
     }
     for (int w = lane; w < g.WD; w += nl) { s.defect[w] = 0; s.act0[w] = 0; s.act1[w] = 0; }
     for (int w = lane; w < g.WN; w += nl) s.troot[w] = 0;
-    if (lane < 4) s.misc[lane] = 0;
+    for (int w = lane; w < CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu;
     (void)l;
 }
 
@@ -246,17 +255,20 @@ LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams
 }
 
 // uf.py:98-104 load: every defect is an odd, active singleton cluster.
-LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
+// Returns whether this lane saw a defect.
+LUF_DEV uint32_t ph_load(const GraphView& g, const Shot& s, int lane, int nl)
 {
+    uint32_t any = 0;
     for (int w = lane; w < g.WD; w += nl) {
         uint32_t bits = s.defect[w];
         s.act0[w] = bits;
-        if (bits) s.misc[0] = 1;
+        any |= bits;
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             s.R[g.B + 32 * w + b] = (idx_t)ODD_BIT;
         }
     }
+    return any;
 }
 
 // ------------------------------------------------------- phase 2a: grow a round
@@ -295,24 +307,22 @@ LUF_DEV void ph_grow(const GraphView& g, const Shot& s, int cur, int lane, int n
     }
 }
 
-// --------------------------------------------------- phase 2b: merge (one lane)
-// uf.py:223-229,256-301 in canonical order: this round's newly FULL edges in
-// ascending edge id.  Union by size, ties keep the cluster of the edge's first
-// endpoint; parity XOR; boundary by inclination; member lists spliced.
-LUF_DEV void merge_edge(const GraphView& g, const Shot& s, int flags, uint32_t e)
+// ------------------------------------------------------------ phase 2b: merge
+// uf.py:223-229,256-301 in canonical order: this round's newly FULL edges are
+// merged in ascending edge id.  Union by size, ties keep the cluster of the
+// edge's first endpoint; parity XOR; boundary by inclination; member lists
+// spliced.  The smaller root's R slot is dead after the union and keeps the
+// union edge (used by the peel for two-node clusters).
+LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t e, uint32_t cu, uint32_t cv)
 {
-    const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-    const uint32_t cu = find_compress(s, uv & 0xFFFFu), cv = find_compress(s, uv >> 16);
     if (flags & FLAG_DYNAMIC) {                                   // uf.py:261-266
         if (cu == cv || ((s.R[cu] & 0x7FFFu) && (s.R[cv] & 0x7FFFu))) {
-            s.growth[e >> 4] |= 3u << ((e & 15u) * 2u);           // FULL(2) -> BURNT(3)
+            luf_atomic_or(&s.growth[e >> 4], 3u << ((e & 15u) * 2u));     // FULL(2) -> BURNT(3)
             return;
         }
     } else if (cu == cv) return;                                  // uf.py:256-259
     const uint32_t su = s.P[cu] & 0x7FFFu, sv = s.P[cv] & 0x7FFFu;
     const uint32_t L = su >= sv ? cu : cv, S = su >= sv ? cv : cu;    // uf.py:270-273
-    s.P[S] = (idx_t)L;
-    s.P[L] = (idx_t)(ROOT_BIT | (su + sv));
     const uint32_t rl = s.R[L], rs = s.R[S];
     uint32_t bl = rl & 0x7FFFu;
     const uint32_t bs = rs & 0x7FFFu;
@@ -320,22 +330,61 @@ LUF_DEV void merge_edge(const GraphView& g, const Shot& s, int flags, uint32_t e
         if (bs && (!bl || LUF_LDG(&g.node_long[bs - 1]) < LUF_LDG(&g.node_long[bl - 1]))) bl = bs;
     } else if (!bl && bs) bl = bs;                                // uf.py:536-538
     s.R[L] = (idx_t)(((rl ^ rs) & ODD_BIT) | bl);
+    s.R[S] = (idx_t)e;
     const idx_t t = s.NX[L]; s.NX[L] = s.NX[S]; s.NX[S] = t;      // splice the circular lists
+    s.P[L] = (idx_t)(ROOT_BIT | (su + sv));
+    s.P[S] = (idx_t)L;
 }
 
-LUF_DEV void ph_merge(const GraphView& g, const Shot& s, int flags, int lane)
+// The serial order is reproduced in parallel by deterministic reservations:
+// every pending edge writes (iteration tag, edge id) with atomicMin into a
+// small table slot of each of its two current clusters; an edge that reads its
+// own id back from both slots is the lowest-id pending edge at both clusters.
+// No lower-id pending edge can touch -- or, through still lower edges, come to
+// touch -- those clusters before it, so running it now commutes with
+// everything the serial order would have run before it.  Winners of one
+// iteration touch pairwise disjoint clusters and run concurrently; losers
+// retry.  Slots are hashed (collisions only add ordering, never remove it) and
+// tagged with a decreasing iteration number, so stale entries always lose and
+// the table needs no clearing.
+LUF_DEV uint32_t claim_slot(uint32_t root) { return (root * 0x9E5u >> 3) & (uint32_t)(CLAIM_SLOTS - 1); }
+
+LUF_DEV void ph_merge_claim(const GraphView& g, const Shot& s, uint32_t tag, int lane, int nl)
 {
-    if (lane != 0) return;
-    for (int w = 0; w < g.WE; ++w) {
+    for (int w = lane; w < g.WE; w += nl) {
         uint32_t bits = s.newfull[w];
-        if (!bits) continue;
-        s.newfull[w] = 0;
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            merge_edge(g, s, flags, (uint32_t)(32 * w + b));
+            const uint32_t e = (uint32_t)(32 * w + b);
+            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+            const uint32_t cu = find_ro(s, uv & 0xFFFFu), cv = find_ro(s, uv >> 16);
+            luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
+            luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
         }
     }
-    s.misc[0] = 0;
+}
+
+// Returns whether this lane still has pending edges.
+LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uint32_t tag, int lane, int nl)
+{
+    uint32_t pending = 0;
+    for (int w = lane; w < g.WE; w += nl) {
+        uint32_t bits = s.newfull[w], keep = 0;
+        if (!bits) continue;
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t e = (uint32_t)(32 * w + b);
+            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+            const uint32_t cu = find_ro(s, uv & 0xFFFFu), cv = find_ro(s, uv >> 16);
+            if (s.claim[claim_slot(cu)] == (tag | e) && s.claim[claim_slot(cv)] == (tag | e))
+                union_roots(g, s, flags, e, cu, cv);
+            else
+                keep |= 1u << b;
+        }
+        s.newfull[w] = keep;
+        pending |= keep;
+    }
+    return pending;
 }
 
 // ------------------------------------------ phase 2c: next round's active roots
@@ -347,10 +396,11 @@ LUF_DEV void ph_clear_next(const GraphView& g, const Shot& s, int cur, int lane,
     for (int w = lane; w < g.WD; w += nl) nxt[w] = 0;
 }
 
-LUF_DEV void ph_reactivate(const GraphView& g, const Shot& s, int cur, int lane, int nl)
+LUF_DEV uint32_t ph_reactivate(const GraphView& g, const Shot& s, int cur, int lane, int nl)
 {
     const uint32_t* act = cur ? s.act1 : s.act0;
     uint32_t* nxt = cur ? s.act0 : s.act1;
+    uint32_t any = 0;
     for (int w = lane; w < g.WD; w += nl) {
         uint32_t bits = act[w];
         while (bits) {
@@ -358,28 +408,49 @@ LUF_DEV void ph_reactivate(const GraphView& g, const Shot& s, int cur, int lane,
             const uint32_t r = find_ro(s, (uint32_t)(g.B + 32 * w + b));
             if (s.R[r] == (idx_t)ODD_BIT) {                     // odd, no boundary
                 luf_atomic_or(&nxt[(r - g.B) >> 5], 1u << ((r - g.B) & 31u));
-                s.misc[0] = 1;
+                any = 1;
             }
         }
     }
+    return any;
 }
 
 // ------------------------------------------------------------- phase 3: peel
 // uf.py:314-324: one tree per cluster, rooted at cluster.boundary or else the
 // union-find root.  Clusters without a defect cannot contribute a correction
 // edge, so only clusters of defects are rooted.
-LUF_DEV void ph_tree_roots(const GraphView& g, const Shot& s, int lane, int nl)
+//
+// Two-node clusters (the common case at low noise: one flipped edge) need no
+// traversal: their only tree is the union edge, and it is in the correction
+// iff the cluster holds a defect.  One of the (at most two) defects acts.
+// Returns this lane's parity of pair corrections on the west boundary and
+// (bit 1) whether any cluster needs the general traversal.
+LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int nl)
 {
+    uint32_t out = 0;
     for (int w = lane; w < g.WD; w += nl) {
         uint32_t bits = s.defect[w];
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t r = find_ro(s, (uint32_t)(g.B + 32 * w + b));
+            const uint32_t dn = (uint32_t)(g.B + 32 * w + b);
+            const uint32_t r = find_ro(s, dn);
+            if ((s.P[r] & 0x7FFFu) == 2u) {
+                const uint32_t x = s.NX[r];                                  // the other member
+                const uint32_t rd = r >= (uint32_t)g.B ? (s.defect[(r - g.B) >> 5] >> ((r - g.B) & 31u)) & 1u : 0u;
+                if (dn == r || !rd) {
+                    const uint32_t e = s.R[x];
+                    if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
+                    out ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
+                }
+                continue;
+            }
             const uint32_t bn = s.R[r] & 0x7FFFu;
             const uint32_t t = bn ? bn - 1u : r;
             luf_atomic_or(&s.troot[t >> 5], 1u << (t & 31u));
+            out |= 2u;
         }
     }
+    return out;
 }
 
 // The union-find arrays are dead now; reuse them for the traversal:
@@ -441,16 +512,29 @@ LUF_DEV uint32_t ph_peel(const GraphView& g, const Shot& s, int lane, int nl)
 
 // ------------------------------------------------------------------ drivers
 // uf.py:200-209 validate: rounds of grow / merge until no cluster is active.
-// Returns the number of growth rounds.  `lane` is this thread's lane on the
-// device; the host emulation iterates it inside LUF_PHASE.
-LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, int nl)
+// `any_defect` is the tile-wide result of ph_load.  Returns the number of
+// growth rounds.  `lane` is this thread's lane on the device; the host
+// emulation iterates it inside LUF_PHASE.
+LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, uint32_t any_defect, int lane, int nl)
 {
     int cur = 0, rounds = 0;
+    uint32_t iter = 0xFFFFu;                 // decreasing reservation tag
+    uint32_t active = any_defect;
     (void)lane;
-    while (s.misc[0]) {
-        LUF_PHASE(ph_grow(g, s, cur, lane, nl));
-        LUF_PHASE(ph_clear_next(g, s, cur, lane, nl); ph_merge(g, s, flags, lane));
-        LUF_PHASE(ph_reactivate(g, s, cur, lane, nl));
+    while (active) {
+        LUF_PHASE(ph_grow(g, s, cur, lane, nl); ph_clear_next(g, s, cur, lane, nl));
+        uint32_t pending;
+        do {
+            const uint32_t tag = iter << 16;
+            --iter;
+            pending = 0;
+            LUF_PHASE(ph_merge_claim(g, s, tag, lane, nl));
+            LUF_PHASE(pending |= ph_merge_exec(g, s, flags, tag, lane, nl));
+            pending = LUF_ANY(pending);
+        } while (pending);
+        active = 0;
+        LUF_PHASE(active |= ph_reactivate(g, s, cur, lane, nl));
+        active = LUF_ANY(active);
         cur ^= 1;
         ++rounds;
     }
@@ -461,11 +545,13 @@ LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, 
 // emulation) the parity of correction edges on the west boundary.
 LUF_DEV uint32_t uf_peel(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    uint32_t parity = 0;
+    uint32_t parity = 0, general = 0;
     (void)lane;
-    LUF_PHASE(ph_tree_roots(g, s, lane, nl));
-    LUF_PHASE(ph_peel_init(g, s, lane, nl));
-    LUF_PHASE(parity ^= ph_peel(g, s, lane, nl));
+    LUF_PHASE(const uint32_t r = ph_tree_roots(g, s, lane, nl); parity ^= r & 1u; general |= r >> 1);
+    if (LUF_ANY(general)) {
+        LUF_PHASE(ph_peel_init(g, s, lane, nl));
+        LUF_PHASE(parity ^= ph_peel(g, s, lane, nl));
+    }
     return parity;
 }
 

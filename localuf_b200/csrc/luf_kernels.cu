@@ -12,6 +12,7 @@
 // nothing at all in the fused Monte-Carlo kernel.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -61,10 +62,11 @@ __global__ void k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
         uint32_t parity = 0;
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
-        LUF_PHASE(ph_load(g, s, lane, nl));
-        uf_validate(g, s, flags, lane, nl);
+        uint32_t any = 0;
+        LUF_PHASE(any |= ph_load(g, s, lane, nl));
+        uf_validate(g, s, flags, LUF_ANY(any), lane, nl);
         parity ^= uf_peel(g, s, lane, nl);
-        fails += __reduce_xor_sync(0xffffffffu, parity) & 1u;
+        fails += LUF_XOR(parity) & 1u;
     }
     if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
@@ -83,8 +85,9 @@ __global__ void k_decode_uf(GraphView g, Layout l, int flags, long long nshots,
     for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(for (int w = lane; w < g.WD; w += nl) s.defect[w] = __ldg(&syn[k * g.WD + w]));
-        LUF_PHASE(ph_load(g, s, lane, nl));
-        const int rounds = uf_validate(g, s, flags, lane, nl);
+        uint32_t any = 0;
+        LUF_PHASE(any |= ph_load(g, s, lane, nl));
+        const int rounds = uf_validate(g, s, flags, LUF_ANY(any), lane, nl);
         if (growth2b)
             for (int w = lane; w < GW; w += nl) growth2b[k * GW + w] = s.growth[w];
         uf_peel(g, s, lane, nl);
@@ -181,13 +184,28 @@ static int plan_launch(luf_graph* g, K kernel, const Layout& l, long long nshots
     if (l.bytes > (uint32_t)g->max_smem)
         return fail(LUF_ERR_UNSUPPORTED, "one shot's decoder state (" + std::to_string(l.bytes) +
                     " B) exceeds the shared memory of an SM; CTA-per-shot kernels are not built yet");
+    // Tunables (for sweeps; the defaults are what bench.py measures):
+    //   LUF_WARPS_PER_BLOCK  warps (= concurrent shots) per block
+    //   LUF_SMEM_KB_PER_SM   shared-memory budget per SM for shot state; the
+    //                        rest of the 228 KB stays L1 for the graph tables
+    static const int env_wpb = getenv("LUF_WARPS_PER_BLOCK") ? atoi(getenv("LUF_WARPS_PER_BLOCK")) : 0;
+    static const int env_kb = getenv("LUF_SMEM_KB_PER_SM") ? atoi(getenv("LUF_SMEM_KB_PER_SM")) : 0;
     int wpb = g->max_smem / (int)l.bytes;
-    if (wpb > 4) wpb = 4;
+    const int want_wpb = env_wpb > 0 ? env_wpb : 4;
+    if (wpb > want_wpb) wpb = want_wpb;
     const size_t smem = (size_t)wpb * l.bytes;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * WARP, smem));
     if (per_sm < 1) per_sm = 1;
+    const int budget_kb = env_kb > 0 ? env_kb : 172;
+    const int by_budget = (int)((size_t)budget_kb * 1024 / (smem + 1024));
+    if (by_budget >= 1 && per_sm > by_budget) per_sm = by_budget;
+    {   // ask for just enough shared memory for per_sm blocks, leave the rest to L1
+        int pct = (int)(((smem + 1024) * per_sm * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     long long blocks = (long long)g->sm_count * per_sm;
     const long long need = (nshots + wpb - 1) / wpb;
     if (blocks > need) blocks = need;
