@@ -37,6 +37,7 @@
   // emulation accumulates into one variable, so they are identities there)
   #define LUF_ANY(x) ((x) != 0)
   #define LUF_XOR(x) (x)
+  #define LUF_BALLOT(var, pred) { var = 0; for (int lane = 0; lane < nl; ++lane) if (pred) var |= 1u << lane; }
   static inline uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 #else
   #define LUF_DEV __device__ __forceinline__
@@ -51,6 +52,7 @@
   #define LUF_PHASE(stmt) { stmt; } __syncwarp();
   #define LUF_ANY(x) __any_sync(0xffffffffu, (x) != 0)
   #define LUF_XOR(x) __reduce_xor_sync(0xffffffffu, (x))
+  #define LUF_BALLOT(var, pred) { var = __ballot_sync(0xffffffffu, (pred)); }
   LUF_DEV uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 #endif
 
@@ -387,6 +389,26 @@ LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uin
     return pending;
 }
 
+// What the first reservation round could not place (stars around one defect,
+// chains, hash collisions) is merged by one lane in ascending edge id, with
+// path compression.  `mask` tells it which of the 32 words from `base` on
+// still hold edges.
+LUF_DEV void merge_rest(const GraphView& g, const Shot& s, int flags, int base, uint32_t mask)
+{
+    while (mask) {
+        const int w = base + luf_ffs(mask) - 1; mask &= mask - 1;
+        uint32_t bits = s.newfull[w];
+        s.newfull[w] = 0;
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t e = (uint32_t)(32 * w + b);
+            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+            const uint32_t cu = find_compress(s, uv & 0xFFFFu), cv = find_compress(s, uv >> 16);
+            union_roots(g, s, flags, e, cu, cv);
+        }
+    }
+}
+
 // ------------------------------------------ phase 2c: next round's active roots
 // uf.py:290-301: active <=> odd and without boundary.  Every active cluster of
 // the next round contains an active root of this round.
@@ -523,15 +545,20 @@ LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, uint32_t a
     (void)lane;
     while (active) {
         LUF_PHASE(ph_grow(g, s, cur, lane, nl); ph_clear_next(g, s, cur, lane, nl));
-        uint32_t pending;
-        do {
+        {   // one parallel reservation round places the independent merges ...
             const uint32_t tag = iter << 16;
             --iter;
-            pending = 0;
+            uint32_t pending = 0;
             LUF_PHASE(ph_merge_claim(g, s, tag, lane, nl));
             LUF_PHASE(pending |= ph_merge_exec(g, s, flags, tag, lane, nl));
-            pending = LUF_ANY(pending);
-        } while (pending);
+            if (LUF_ANY(pending)) {          // ... one lane finishes the rest in order
+                for (int base = 0; base < g.WE; base += 32) {
+                    uint32_t mask;
+                    LUF_BALLOT(mask, base + lane < g.WE && s.newfull[base + lane] != 0);
+                    if (mask) { LUF_PHASE(if (lane == 0) merge_rest(g, s, flags, base, mask)); }
+                }
+            }
+        }
         active = 0;
         LUF_PHASE(active |= ph_reactivate(g, s, cur, lane, nl));
         active = LUF_ANY(active);

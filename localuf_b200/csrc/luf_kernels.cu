@@ -198,7 +198,7 @@ static int plan_launch(luf_graph* g, K kernel, const Layout& l, long long nshots
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * WARP, smem));
     if (per_sm < 1) per_sm = 1;
-    const int budget_kb = env_kb > 0 ? env_kb : 172;
+    const int budget_kb = env_kb > 0 ? env_kb : 228;
     const int by_budget = (int)((size_t)budget_kb * 1024 / (smem + 1024));
     if (by_budget >= 1 && per_sm > by_budget) per_sm = by_budget;
     {   // ask for just enough shared memory for per_sm blocks, leave the rest to L1

@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Key metrics + per-phase breakdown of one kernel from an .ncu-rep.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep localuf_b200/csrc/libluf_b200.so k_mc_uf
+"""
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ncu_lines
+
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__grid_size',
+        'launch__block_size', 'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic',
+        'launch__occupancy_limit_shared_mem', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__thread_inst_executed_per_inst_executed.ratio',
+        'sm__inst_executed.sum', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio']
+
+
+def main():
+    rep, so, kernel = sys.argv[1:4]
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    row = next(r for r in rows[2:] if kernel in ' '.join(r[:8]))
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            print(f'{k:80s} {row[i]:>16s} {units[i]}')
+    src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    tmp = '/tmp/_ncu_src.csv'
+    open(tmp, 'w').write(src)
+    # per-function aggregation
+    core = open(os.path.join(os.path.dirname(os.path.abspath(so)), 'luf_core.cuh')).read().splitlines()
+    funcs = [(i, m.group(1)) for i, l in enumerate(core, 1) for m in [re.match(r'LUF_DEV\s+\S+\s+(\w+)\(', l)] if m]
+
+    def fn(f, line):
+        if f != 'luf_core.cuh':
+            return f
+        name = '?'
+        for i, n in funcs:
+            if i <= line:
+                name = n
+        return name
+
+    rows = list(csv.reader(open(tmp)))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
+    h = rows[hi]; col = {x: i for i, x in enumerate(h)}
+    body = [r for r in rows[hi + 1:] if len(r) == len(h)]
+    table = ncu_lines.line_table(so, kernel)
+    agg, tot = {}, [0, 0, 0]
+    for k, r in enumerate(body):
+        key = table[k] if k < len(table) and table[k] else ('?', 0)
+        name = fn(*key)
+        v = (int(r[col['Instructions Executed']] or 0), int(r[col['Thread Instructions Executed']] or 0), int(r[col['# Samples']] or 0))
+        a = agg.setdefault(name, [0, 0, 0])
+        for j in range(3):
+            a[j] += v[j]; tot[j] += v[j]
+    print(f'\nwarp-inst {tot[0]:,}  avg lanes {tot[1] / max(tot[0], 1):.2f}  samples {tot[2]:,}')
+    print(f'{"function":28s} {"inst%":>7s} {"lanes":>6s} {"samples%":>9s}')
+    for name, v in sorted(agg.items(), key=lambda kv: -kv[1][2]):
+        if v[2] * 200 < tot[2] and v[0] * 200 < tot[0]:
+            continue
+        print(f'{name:28s} {100 * v[0] / tot[0]:7.2f} {v[1] / max(v[0], 1):6.1f} {100 * v[2] / tot[2]:9.2f}')
+
+
+if __name__ == '__main__':
+    main()
