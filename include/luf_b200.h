@@ -79,6 +79,9 @@ typedef struct {
     const int32_t *nbr_edge;     /* [N*K] edge id in scan order, -1 if absent */
     const int32_t *nbr_node;     /* [N*K] neighbour node index, -1 if absent */
     const uint8_t *nbr_owned;    /* [N*K] 1 if the node is the edge's first endpoint */
+    const int32_t *actis_span;   /* [N] per-node countdown start of Actis (decoders/luf/main.py:970-976) */
+    const int32_t *actis_relay;  /* [N] neighbour towards node id 0 (decoders/luf/main.py:1138-1163), -1 = controller */
+    int32_t actis_global_span;   /* controller countdown start (decoders/luf/main.py:517-523) */
 } luf_graph_desc;
 
 /* Message of the calling thread's most recent failure ("" if none). */

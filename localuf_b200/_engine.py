@@ -38,6 +38,7 @@ class GraphDesc(C.Structure):
         ('west_edge_mask', C.c_void_p), ('edge_class', C.c_void_p), ('n_classes', C.c_int32),
         ('n_dirs', C.c_int32), ('nbr_edge', C.c_void_p), ('nbr_node', C.c_void_p),
         ('nbr_owned', C.c_void_p),
+        ('actis_span', C.c_void_p), ('actis_relay', C.c_void_p), ('actis_global_span', C.c_int32),
     ]
 
 
@@ -46,6 +47,7 @@ _FIELD_TYPES = (
     ('node_long', np.int32), ('inc_off', np.int32), ('inc_edge', np.int32), ('inc_other', np.int32),
     ('west_edge_mask', np.uint32), ('edge_class', np.uint8),
     ('nbr_edge', np.int32), ('nbr_node', np.int32), ('nbr_owned', np.uint8),
+    ('actis_span', np.int32), ('actis_relay', np.int32),
 )
 
 
@@ -61,6 +63,7 @@ def make_desc(flat, noise_kind: int):
         setattr(d, name, a.ctypes.data)
     d.n_classes = flat.n_classes
     d.n_dirs = flat.nbr_edge.shape[1]
+    d.actis_global_span = flat.actis_global_span
     return d, keep
 
 

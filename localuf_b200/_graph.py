@@ -81,6 +81,9 @@ class FlatGraph:
     nbr_edge: np.ndarray          # int32[N, K]  edge id in scan order, -1 if absent
     nbr_node: np.ndarray          # int32[N, K]  neighbour node index, -1 if absent
     nbr_owned: np.ndarray         # uint8[N, K]  1 if this node is the edge's first endpoint
+    actis_span: np.ndarray        # int32[N]  per-node countdown start of Actis (luf/main.py:970-976)
+    actis_relay: np.ndarray       # int32[N]  neighbour towards node id 0 (luf/main.py:1138-1163), -1 = the controller
+    actis_global_span: int        # controller countdown start (luf/main.py:517-523)
     dense_ids: bool               # node index == reference index_to_id
     node_index: dict = field(repr=False, default_factory=dict)   # coord -> node index
     edge_index: dict = field(repr=False, default_factory=dict)   # edge tuple -> edge index
@@ -173,6 +176,27 @@ class FlatGraph:
                     nbr_node[k, s] = node_index[w]
                     nbr_owned[k, s] = 1 if forward else 0
 
+        span = np.zeros(N, dtype=np.int32)
+        relay = np.full(N, -1, dtype=np.int32)
+        global_span = 0
+        kind = str(code.NOISE)
+        if code._CODE_DIMENSION == 2 and not streaming and bool(getattr(code, '_ID_IS_DENSE', False)):
+            global_span = {'code capacity': 2 * d, 'phenomenological': 3 * d - 1}.get(kind, d + 1)
+            for k, v in enumerate(nodes):
+                if kind == 'circuit-level':
+                    i, j, t = v
+                    span[k] = d - max(i, j + 1, t)
+                    w = (i - 1 if i > 0 else i, j - 1 if j > -1 else j, t - 1 if t > 0 else t)
+                else:
+                    span[k] = code.DIMENSION * (d - 1) - sum(v)
+                    if len(v) == 2:
+                        i, j = v
+                        w = (i, j - 1) if j > -1 else ((i - 1, j) if i > 0 else None)
+                    else:
+                        i, j, t = v
+                        w = (i, j, t - 1) if t > 0 else ((i, j - 1, t) if j > -1 else ((i - 1, j, t) if i > 0 else None))
+                relay[k] = -1 if (w is None or w == v) else node_index.get(w, -2)
+
         return cls(
             n_nodes=N, n_boundary=n_boundary, n_edges=E, d=d, height=h,
             edge_u=eu, edge_v=ev, node_flags=flags,
@@ -182,6 +206,7 @@ class FlatGraph:
             west_edge_mask=west, edge_class=edge_class, n_classes=len(class_lists),
             dir_names=tuple(n for n, _ in dirs),
             nbr_edge=nbr_edge, nbr_node=nbr_node, nbr_owned=nbr_owned,
+            actis_span=span, actis_relay=relay, actis_global_span=global_span,
             dense_ids=bool(getattr(code, '_ID_IS_DENSE', False)),
             node_index=node_index, edge_index=edge_index, nodes=nodes, edges=edges,
         )

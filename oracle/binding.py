@@ -22,7 +22,9 @@ class OracleGraph(C.Structure):
         ('inc_off', C.c_void_p), ('inc_edge', C.c_void_p), ('inc_other', C.c_void_p),
         ('west_edge_mask', C.c_void_p), ('edge_class', C.c_void_p), ('n_classes', C.c_int32),
         ('n_dirs', C.c_int32), ('nbr_edge', C.c_void_p), ('nbr_node', C.c_void_p),
-        ('nbr_owned', C.c_void_p), ('noise_kind', C.c_int32),
+        ('nbr_owned', C.c_void_p),
+        ('actis_span', C.c_void_p), ('actis_relay', C.c_void_p), ('actis_global_span', C.c_int32),
+        ('noise_kind', C.c_int32),
     ]
 
 
@@ -68,13 +70,15 @@ class Oracle:
                          ('node_id', np.int32), ('node_long', np.int32),
                          ('inc_off', np.int32), ('inc_edge', np.int32), ('inc_other', np.int32),
                          ('west_edge_mask', np.uint32), ('edge_class', np.uint8),
-                         ('nbr_edge', np.int32), ('nbr_node', np.int32), ('nbr_owned', np.uint8)):
+                         ('nbr_edge', np.int32), ('nbr_node', np.int32), ('nbr_owned', np.uint8),
+                         ('actis_span', np.int32), ('actis_relay', np.int32)):
             a = np.ascontiguousarray(getattr(flat, name), dtype=dt)
             self._keep[name] = a
             setattr(g, name, a.ctypes.data)
         g.n_classes = flat.n_classes
         g.n_dirs = flat.nbr_edge.shape[1]
         g.noise_kind = noise_kind
+        g.actis_global_span = flat.actis_global_span
         self.g = g
         self.WE = (flat.n_edges + 31) // 32
         self.WD = (flat.n_detectors + 31) // 32

@@ -37,6 +37,9 @@ typedef struct {
     int32_t n_dirs;                                 /* CA neighbour table width K */
     const int32_t *nbr_edge, *nbr_node;             /* [N*K] */
     const uint8_t *nbr_owned;                       /* [N*K] */
+    const int32_t *actis_span;   /* [N] per-node countdown start of Actis (decoders/luf/main.py:970-976) */
+    const int32_t *actis_relay;  /* [N] neighbour towards node id 0 (decoders/luf/main.py:1138-1163), -1 = controller */
+    int32_t actis_global_span;   /* controller countdown start (decoders/luf/main.py:517-523) */
     int32_t noise_kind;                             /* 0 code capacity, 1 phenomenological, 2 circuit-level */
 } oracle_graph;
 
