@@ -127,7 +127,9 @@ int luf_check(luf_graph *g, int64_t nshots, const uint32_t *err_bits_dev,
 
 /* Fused K1+K2/3+K4 -- replaces the shot loop Batch.run
  * (localuf/_schemes.py:116-121,131-155): nshots shots are sampled, decoded and
- * checked without leaving the SM.  counts_dev[0] += failures, counts_dev[1] += nshots. */
+ * checked without leaving the SM.  counts_dev is uint64[4]: [0] += failures,
+ * [1] += nshots, [2] += sum of tSV, [3] += sum of tBP (Macar / Actis timestep
+ * counts, decoders/luf/main.py:83-110; zero for UF). */
 int luf_mc_run(luf_graph *g, int decoder, int flags, const double *class_p_host,
                uint64_t seed, uint64_t shot0, int64_t nshots,
                unsigned long long *counts_dev, void *stream);
@@ -136,7 +138,7 @@ int luf_mc_run(luf_graph *g, int decoder, int flags, const double *class_p_host,
  * ends up in): stage through device scratch owned by the graph, synchronise. */
 int luf_mc_run_host(luf_graph *g, int decoder, int flags, const double *class_p_host,
                     uint64_t seed, uint64_t shot0, int64_t nshots,
-                    unsigned long long counts_host[2]);
+                    unsigned long long counts_host[4]);
 int luf_decode_batch_host(luf_graph *g, int decoder, int flags, int64_t nshots,
                           const uint32_t *syn_bits_host, uint32_t *corr_bits_host,
                           uint32_t *growth2b_host, int32_t *steps_host);

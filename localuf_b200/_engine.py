@@ -163,8 +163,9 @@ class Engine:
     def mc_run_host(self, decoder: int, flags: int, noise_level: float, seed: int, shot0: int, nshots: int):
         """Fused sample+decode+check of ``nshots`` shots; returns (failures, shots)."""
         cp = self.class_p(noise_level)
-        counts = (C.c_ulonglong * 2)(0, 0)
+        counts = (C.c_ulonglong * 4)(0, 0, 0, 0)
         _check(_load().luf_mc_run_host(self._h, decoder, flags, cp.ctypes.data, seed, shot0, nshots, counts))
+        self.last_step_sums = (int(counts[2]), int(counts[3]))
         return int(counts[0]), int(counts[1])
 
     def decode_batch_host(self, decoder: int, flags: int, syn_bits, want_growth=False, want_steps=True):

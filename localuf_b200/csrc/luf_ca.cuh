@@ -1,0 +1,414 @@
+// luf_ca.cuh -- Macar / Actis: the local Union-Find cellular automata
+// (reference: localuf/decoders/luf/main.py) as synchronous sweeps of one warp
+// over one shot's lattice held in shared memory.
+//
+// One reference timestep (`LUF._advance`, luf/main.py:182-188) is two phases:
+//   A  every node runs the action of the current stage, reading only committed
+//      state of its neighbours and writing its own `next_*` fields; effects on
+//      *other* nodes (a relayed anyon, a peeled defect, Actis signals) go to
+//      receive-bitmaps with shared-memory atomics;
+//   B  every node commits (`update_unphysicals`, luf/main.py:425-432,569-581),
+//      the warp votes busy/active, and the (warp-uniform) controller advances
+//      (luf/main.py:354-378).
+// Within-timestep updates of the reference are order independent (SURVEY.md
+// section 7, hard part 3), so the parallel sweep reproduces its timestep counts,
+// erasure and correction exactly.  Same dual-compilation scheme as
+// luf_core.cuh (LUF_HOST_EMU = lanes run sequentially; test harness only).
+#pragma once
+#include "luf_core.cuh"
+
+namespace luf {
+
+enum { ST_GROWING = 0, ST_MERGING = 1, ST_PRESYNCING = 2, ST_SYNCING = 3, ST_BURNING = 4, ST_PEELING = 5, ST_DONE = 6 };
+enum { FL_DEFECT = 1, FL_ACTIVE = 2, FL_ANYON = 4, FL_BUSY = 8, FL_SEEN_ANYON = 16, FL_SEEN_DEFECT = 32 };
+// Actis byte: stage (bits 0-1), next_stage (2-3), busy_signal (4), active_signal (5), own next_active_signal (6)
+enum { AS_BUSY_SIG = 16, AS_ACTIVE_SIG = 32, AS_OWN_NAS = 64 };
+static const uint32_t PTR_C = 0xFFu;
+static const uint32_t NBR_NONE = 0xFFFFFFFFu;
+enum { FLAG_ACTIS_UNOPTIMAL = 4 };
+
+struct CaView {
+    int N, B, E, K;             // K directions; slots >= K/2 are the edges a node owns (it is their first endpoint)
+    int WE, WD, WN, GW;
+    const uint32_t* nbr;        // [N*K] edge | node<<16 in scan order (luf/main.py:748-777), NBR_NONE if absent
+    const uint32_t* west_mask;  // [WE]
+    const uint8_t* span;        // [N]   Actis per-node countdown start (luf/main.py:970-976)
+    const uint16_t* relay;      // [N]   Actis neighbour towards node 0 (luf/main.py:1138-1163); 0xFFFF = controller
+    int global_span;            // luf/main.py:517-523
+};
+
+struct CaLayout {
+    uint32_t cid, ncid;         // u16[N]
+    uint32_t ptr, fl, ast, cnt; // u8[N]   (ast, cnt only for Actis)
+    uint32_t growth, gacc;      // u32[GW] live growth / snapshot at the last update_access (luf/main.py:434-440)
+    uint32_t rx_anyon, rx_defect;   // u32[WN] cumulative toggles received from neighbours
+    uint32_t rx_busy, rx_active;    // u32[2*WN] Actis signals received, double-buffered by timestep parity
+    uint32_t defect, err, corr; // u32[WD] / u32[WE] / u32[WE]
+    uint32_t glob;              // u32[4]  Actis collection-level next_busy_signal / next_active_signal
+    uint32_t bytes;
+};
+
+struct CaShot {
+    uint16_t *cid, *ncid;
+    uint8_t *ptr, *fl, *ast, *cnt;
+    uint32_t *growth, *gacc, *rx_anyon, *rx_defect, *rx_busy, *rx_active, *defect, *err, *corr, *glob;
+};
+
+LUF_DEV CaShot ca_bind(const CaLayout& l, unsigned char* b)
+{
+    CaShot s;
+    s.cid = (uint16_t*)(b + l.cid); s.ncid = (uint16_t*)(b + l.ncid);
+    s.ptr = b + l.ptr; s.fl = b + l.fl; s.ast = b + l.ast; s.cnt = b + l.cnt;
+    s.growth = (uint32_t*)(b + l.growth); s.gacc = (uint32_t*)(b + l.gacc);
+    s.rx_anyon = (uint32_t*)(b + l.rx_anyon); s.rx_defect = (uint32_t*)(b + l.rx_defect);
+    s.rx_busy = (uint32_t*)(b + l.rx_busy); s.rx_active = (uint32_t*)(b + l.rx_active);
+    s.defect = (uint32_t*)(b + l.defect);
+    s.err = l.err ? (uint32_t*)(b + l.err) : 0;
+    s.corr = (uint32_t*)(b + l.corr);
+    s.glob = (uint32_t*)(b + l.glob);
+    return s;
+}
+
+// Warp-uniform controller + (Actis) collection state; lives in registers.
+struct CaCtl {
+    int stage;                  // Controller.stage, luf/main.py:350-352
+    int step;                   // timestep parity for the double-buffered signal bitmaps
+    // ActisNodes, luf/main.py:545-553
+    int n_busy, n_valid, n_countdown, n_busy_signal, n_active_signal, n_next_active_signal;
+};
+static const int CA_MAX_STEPS = 1 << 20;    // safety net: a shot that runs this long is reported with steps = -1
+
+LUF_DEV uint32_t g2(const uint32_t* a, uint32_t e) { return (a[e >> 4] >> ((e & 15u) * 2u)) & 3u; }
+
+// LUF.reset / _Node.reset / ActisNode.reset (luf/main.py:173-180,799-809,1004-1012)
+template <bool ACTIS>
+LUF_DEV void ca_reset(const CaView& g, const CaShot& s, int lane, int nl)
+{
+    for (int v = lane; v < g.N; v += nl) {
+        s.cid[v] = (uint16_t)v; s.ncid[v] = (uint16_t)v;          // dense ids: node index == index_to_id
+        s.ptr[v] = (uint8_t)PTR_C; s.fl[v] = 0;
+        if (ACTIS) { s.ast[v] = 0; s.cnt[v] = 0; }
+    }
+    for (int w = lane; w < g.GW; w += nl) { s.growth[w] = 0; s.gacc[w] = 0; }
+    for (int w = lane; w < g.WN; w += nl) {
+        s.rx_anyon[w] = 0; s.rx_defect[w] = 0;
+        if (ACTIS) { s.rx_busy[w] = 0; s.rx_busy[g.WN + w] = 0; s.rx_active[w] = 0; s.rx_active[g.WN + w] = 0; }
+    }
+    for (int w = lane; w < g.WE; w += nl) { s.corr[w] = 0; if (s.err) s.err[w] = 0; }
+    for (int w = lane; w < g.WD; w += nl) s.defect[w] = 0;
+    if (lane < 4) s.glob[lane] = 0;
+}
+
+// Nodes.load / make_defect (luf/main.py:405-408,811-815)
+LUF_DEV void ca_load(const CaView& g, const CaShot& s, int lane, int nl)
+{
+    for (int w = lane; w < g.WD; w += nl) {
+        uint32_t bits = s.defect[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            s.fl[g.B + 32 * w + b] = (uint8_t)(FL_DEFECT | FL_ACTIVE | FL_ANYON);
+        }
+    }
+}
+
+// _Node.growing, luf/main.py:817-826 (saturating, like the in-place loop of the reference)
+LUF_DEV void ca_growing(const CaView& g, const CaShot& s, int v)
+{
+    if (!(s.fl[v] & FL_ACTIVE)) return;
+    for (int k = 0; k < g.K; ++k) {
+        const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
+        if (ent == NBR_NONE) continue;
+        const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+        if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
+        const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+        if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);
+    }
+}
+
+// _Node.merging, luf/main.py:839-854.  Returns busy.
+LUF_DEV uint32_t ca_merging(const CaView& g, const CaShot& s, int v)
+{
+    uint32_t fl = s.fl[v] & ~(uint32_t)FL_BUSY, ptr = s.ptr[v], busy = 0;
+    if (v >= g.B && ptr != PTR_C && (fl & FL_ANYON)) {             // relay the anyon along the pointer
+        busy = 1;
+        const uint32_t to = LUF_LDG(&g.nbr[v * g.K + ptr]) >> 16;
+        luf_atomic_xor(&s.rx_anyon[to >> 5], 1u << (to & 31u));
+        fl &= ~(uint32_t)FL_ANYON;
+    }
+    uint32_t best = s.ncid[v];
+    for (int k = 0; k < g.K; ++k) {
+        const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
+        if (ent == NBR_NONE || g2(s.gacc, ent & 0xFFFFu) != G_FULL) continue;
+        const uint32_t c = s.cid[ent >> 16];
+        if (c < best) { best = c; ptr = (uint32_t)k; busy = 1; }
+    }
+    s.ncid[v] = (uint16_t)best; s.ptr[v] = (uint8_t)ptr;
+    s.fl[v] = (uint8_t)(fl | (busy ? FL_BUSY : 0));
+    return busy;
+}
+
+// _Node.presyncing, luf/main.py:856-866.  Returns the new `active`.
+LUF_DEV uint32_t ca_presyncing(const CaView& g, const CaShot& s, int v)
+{
+    const uint32_t fl = s.fl[v];
+    const uint32_t act = (v >= g.B && s.ptr[v] == PTR_C && (fl & FL_ANYON)) ? 1u : 0u;
+    s.fl[v] = (uint8_t)((fl & ~(uint32_t)FL_ACTIVE) | (act ? FL_ACTIVE : 0));
+    return act;
+}
+
+// _Node.syncing, luf/main.py:880-884.  Returns busy.
+LUF_DEV uint32_t ca_syncing(const CaView& g, const CaShot& s, int v)
+{
+    const uint32_t fl = s.fl[v] & ~(uint32_t)FL_BUSY;
+    uint32_t busy = 0;
+    if (!(fl & FL_ACTIVE))
+        for (int k = 0; k < g.K; ++k) {
+            const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
+            if (ent == NBR_NONE || g2(s.gacc, ent & 0xFFFFu) != G_FULL) continue;
+            if (s.fl[ent >> 16] & FL_ACTIVE) { busy = 1; break; }
+        }
+    s.fl[v] = (uint8_t)(fl | (busy ? FL_BUSY : 0));
+    return busy;
+}
+
+// _Node.burning, luf/main.py:890-899; OPPOSITE[slot k] = slot K-1-k
+LUF_DEV void ca_burning(const CaView& g, const CaShot& s, int v)
+{
+    const uint32_t ptr = s.ptr[v];
+    for (int k = g.K >> 1; k < g.K; ++k) {                          // owned edges
+        const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
+        if (ent == NBR_NONE) continue;
+        const uint32_t e = ent & 0xFFFFu;
+        if (g2(s.growth, e) == G_FULL && ptr != (uint32_t)k && s.ptr[ent >> 16] != (uint32_t)(g.K - 1 - k))
+            luf_atomic_and(&s.growth[e >> 4], ~(3u << ((e & 15u) * 2u)));
+    }
+}
+
+// _Node.peeling, luf/main.py:901-916.  Returns busy | west-parity << 1.
+LUF_DEV uint32_t ca_peeling(const CaView& g, const CaShot& s, int v)
+{
+    uint32_t fl = s.fl[v] & ~(uint32_t)FL_BUSY;
+    uint32_t out = 0;
+    if (s.ptr[v] != PTR_C) {
+        uint32_t n_access = 0, only = 0;
+        for (int k = 0; k < g.K; ++k) {
+            const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
+            if (ent == NBR_NONE || g2(s.gacc, ent & 0xFFFFu) != G_FULL) continue;
+            ++n_access; only = ent;
+        }
+        if (n_access == 1) {
+            const uint32_t e = only & 0xFFFFu, to = only >> 16;
+            fl |= FL_BUSY; out = 1;
+            luf_atomic_and(&s.growth[e >> 4], ~(3u << ((e & 15u) * 2u)));
+            if (fl & FL_DEFECT) {
+                fl &= ~(uint32_t)FL_DEFECT;
+                luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
+                out |= ((LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u) << 1;
+                luf_atomic_xor(&s.rx_defect[to >> 5], 1u << (to & 31u));
+            }
+        }
+    }
+    s.fl[v] = (uint8_t)fl;
+    return out;
+}
+
+// Controller.advance, luf/main.py:354-378.  Returns growth_changed.
+LUF_DEV int ca_controller_advance(CaCtl& c, int nodes_busy, int nodes_valid)
+{
+    int growth_changed = c.stage == ST_PEELING;
+    if (!nodes_busy) {
+        if (c.stage < 4) {
+            if (c.stage == ST_SYNCING && nodes_valid) c.stage = ST_BURNING;
+            else {
+                if (c.stage == ST_GROWING) growth_changed = 1;
+                c.stage = (c.stage + 1) & 3;
+            }
+        } else {
+            growth_changed = 1;
+            c.stage += 1;
+        }
+    }
+    return growth_changed;
+}
+
+// ---------------------------------------------------------------- Macar step
+// Phase A: MacarNode.advance, luf/main.py:929-942.  Returns west parity of this lane's peels.
+LUF_DEV uint32_t macar_phase_a(const CaView& g, const CaShot& s, int stage, int lane, int nl)
+{
+    uint32_t parity = 0;
+    for (int v = lane; v < g.N; v += nl) {
+        switch (stage) {
+        case ST_GROWING: ca_growing(g, s, v); break;
+        case ST_MERGING: ca_merging(g, s, v); break;
+        case ST_PRESYNCING: ca_presyncing(g, s, v); break;
+        case ST_SYNCING: ca_syncing(g, s, v); break;
+        case ST_BURNING: ca_burning(g, s, v); break;
+        case ST_PEELING: parity ^= ca_peeling(g, s, v) >> 1; break;
+        }
+    }
+    return parity;
+}
+
+// Commit of one node: update_after_merge_step / update_after_sync_step
+// (luf/main.py:872-878,886-888) and the toggles received from neighbours.
+LUF_DEV uint32_t ca_commit_node(const CaShot& s, int stage, int v)
+{
+    uint32_t fl = s.fl[v];
+    if (stage == ST_MERGING) {
+        s.cid[v] = s.ncid[v];
+        const uint32_t rx = (s.rx_anyon[v >> 5] >> (v & 31)) & 1u;
+        if (rx != ((fl >> 4) & 1u)) fl ^= FL_ANYON | FL_SEEN_ANYON;
+    } else if (stage == ST_SYNCING) {
+        if (fl & FL_BUSY) fl |= FL_ACTIVE;
+    } else if (stage == ST_PEELING) {
+        const uint32_t rx = (s.rx_defect[v >> 5] >> (v & 31)) & 1u;
+        if (rx != ((fl >> 5) & 1u)) fl ^= FL_DEFECT | FL_SEEN_DEFECT;
+    }
+    s.fl[v] = (uint8_t)fl;
+    return fl;
+}
+
+// Phase B.  Returns bit0 any busy, bit1 any active (of this lane's nodes).
+LUF_DEV uint32_t macar_phase_b(const CaView& g, const CaShot& s, int stage, int lane, int nl)
+{
+    uint32_t acc = 0;
+    for (int v = lane; v < g.N; v += nl) {
+        const uint32_t fl = ca_commit_node(s, stage, v);
+        if (fl & FL_BUSY) acc |= 1u;
+        if (fl & FL_ACTIVE) acc |= 2u;
+    }
+    return acc;
+}
+
+// Nodes.update_access, luf/main.py:434-440: snapshot the growth the nodes may look through
+LUF_DEV void ca_snapshot_access(const CaView& g, const CaShot& s, int lane, int nl)
+{
+    for (int w = lane; w < g.GW; w += nl) s.gacc[w] = s.growth[w];
+}
+
+// ---------------------------------------------------------------- Actis step
+// ActisNode.advance (luf/main.py:1014-1049) + Friendship (luf/main.py:1090-1176)
+LUF_DEV void actis_phase_a(const CaView& g, const CaShot& s, const CaCtl& c, int lane, int nl)
+{
+    const int cur = c.step & 1;
+    uint32_t* rxb = s.rx_busy + (cur ? g.WN : 0);
+    uint32_t* rxa = s.rx_active + (cur ? g.WN : 0);
+    for (int v = lane; v < g.N; v += nl) {
+        uint32_t a = s.ast[v];
+        const uint32_t st = a & 3u;
+        if (LUF_LDG(&g.relay[v]) == 0xFFFFu) { s.glob[0] = 0; s.glob[1] = 0; }   // this timestep's collection inbox
+        if (st == ST_GROWING || st == ST_PRESYNCING) {               // advance_definite
+            const uint32_t cd = s.cnt[v];
+            if (cd == 0) {
+                if (st == ST_GROWING) ca_growing(g, s, v);
+                else if (ca_presyncing(g, s, v)) a |= AS_OWN_NAS;
+                a = (a & ~12u) | ((st + 1u) << 2);
+            } else s.cnt[v] = (uint8_t)(cd - 1);
+        } else {                                                     // advance_indefinite
+            const uint32_t relay = LUF_LDG(&g.relay[v]);
+            const uint32_t rs = relay == 0xFFFFu ? (uint32_t)c.stage : (s.ast[relay] & 3u);
+            if ((st == ST_MERGING && rs == ST_PRESYNCING) || (st == ST_SYNCING && rs == ST_GROWING)) {
+                a = (a & ~12u) | (rs << 2);
+                s.cnt[v] = LUF_LDG(&g.span[v]);
+            } else {
+                const uint32_t busy = st == ST_MERGING ? ca_merging(g, s, v) : ca_syncing(g, s, v);
+                if (relay == 0xFFFFu) {                               // ControllerFriendship.relay_signals
+                    s.glob[0] = (a >> 4) & 1u;
+                    if (a & AS_ACTIVE_SIG) s.glob[1] = 1;
+                } else {                                              // NodeFriendship.relay_signals
+                    if (busy) a |= AS_BUSY_SIG;
+                    if (a & AS_BUSY_SIG) luf_atomic_or(&rxb[relay >> 5], 1u << (relay & 31u));
+                    if (a & AS_ACTIVE_SIG) luf_atomic_or(&rxa[relay >> 5], 1u << (relay & 31u));
+                }
+            }
+        }
+        s.ast[v] = (uint8_t)a;
+    }
+}
+
+// Nodes.update_unphysicals + update_unphysicals_for_actis (luf/main.py:569-581,1051-1059)
+LUF_DEV void actis_phase_b(const CaView& g, const CaShot& s, const CaCtl& c, int lane, int nl)
+{
+    const int cur = c.step & 1;
+    uint32_t* rxb = s.rx_busy + (cur ? g.WN : 0);
+    uint32_t* rxa = s.rx_active + (cur ? g.WN : 0);
+    uint32_t* nxb = s.rx_busy + (cur ? 0 : g.WN);
+    uint32_t* nxa = s.rx_active + (cur ? 0 : g.WN);
+    for (int v = lane; v < g.N; v += nl) {
+        ca_commit_node(s, c.stage, v);
+        const uint32_t old = s.ast[v];
+        const uint32_t nst = (old >> 2) & 3u;
+        uint32_t a = nst | (nst << 2);
+        if ((rxb[v >> 5] >> (v & 31)) & 1u) a |= AS_BUSY_SIG;
+        if (((rxa[v >> 5] >> (v & 31)) & 1u) || (old & AS_OWN_NAS)) a |= AS_ACTIVE_SIG;
+        s.ast[v] = (uint8_t)a;
+    }
+    for (int w = lane; w < g.WN; w += nl) { nxb[w] = 0; nxa[w] = 0; }   // buffers of the next timestep
+}
+
+// Waiter.advance, luf/main.py:613-679
+LUF_DEV void actis_waiter_advance(const CaView& g, CaCtl& c, int flags)
+{
+    const int optimal = !(flags & FLAG_ACTIS_UNOPTIMAL);
+    c.n_busy = 1;
+    if (c.n_countdown == 0) {
+        c.n_busy = 0;
+        c.n_countdown = g.global_span;
+        if (c.stage == ST_GROWING) c.n_countdown += 1;
+        else if (c.stage == ST_SYNCING) {                            // ActisNodes.update_valid, :559-563
+            c.n_valid = !c.n_active_signal; c.n_active_signal = 0; c.n_next_active_signal = 0;
+        }
+    } else if (optimal ? (c.n_busy_signal && (c.n_countdown == 1 || c.n_countdown == 2)) : c.n_busy_signal)
+        c.n_countdown = optimal ? 2 : g.global_span + 1;
+    else
+        c.n_countdown -= 1;
+}
+
+// ------------------------------------------------------------------- driver
+// LUF.decode = validate (luf/main.py:112-145) then peel (:147-166).  Writes
+// (tSV, tBP) to steps; exports the growth after validation if growth_out.
+// Returns the west parity of the correction (per lane on the device).
+template <bool ACTIS>
+LUF_DEV uint32_t ca_decode(const CaView& g, const CaShot& s, int flags, int* t_sv, int* t_bp,
+                           uint32_t* growth_out, int lane, int nl)
+{
+    CaCtl c;
+    c.stage = ST_GROWING; c.step = 0;
+    c.n_busy = 0; c.n_valid = ACTIS ? 0 : 1; c.n_countdown = 0; c.n_busy_signal = 0; c.n_active_signal = 0;
+    c.n_next_active_signal = 0;
+    int tsv = 0, tbp = 0, exported = 0;
+    uint32_t parity = 0;
+    (void)lane;
+    while (c.stage != ST_DONE) {
+        if (c.stage == ST_BURNING && !exported) {
+            exported = 1;
+            if (growth_out) { LUF_PHASE(for (int w = lane; w < g.GW; w += nl) growth_out[w] = s.growth[w]); }
+        }
+        const int in_sv = c.stage < ST_BURNING;
+        int busy, valid;
+        if (ACTIS) {
+            LUF_PHASE(actis_phase_a(g, s, c, lane, nl));
+            // what node 0 handed to the collection this timestep (ControllerFriendship.relay_signals)
+            const int next_busy_signal = (int)s.glob[0];
+            c.n_next_active_signal |= (int)s.glob[1];
+            actis_waiter_advance(g, c, flags);                       // ActisNodes.advance, :565-567
+            LUF_PHASE(actis_phase_b(g, s, c, lane, nl));
+            c.n_busy_signal = next_busy_signal;                      // _update_unphysicals_for_actis, :575-581
+            c.n_active_signal = c.n_next_active_signal;
+            busy = c.n_busy; valid = c.n_valid;
+        } else {
+            uint32_t acc = 0;
+            LUF_PHASE(parity ^= macar_phase_a(g, s, c.stage, lane, nl));
+            LUF_PHASE(acc |= macar_phase_b(g, s, c.stage, lane, nl));
+            busy = LUF_ANY(acc & 1u); valid = !LUF_ANY(acc & 2u);
+        }
+        if (ca_controller_advance(c, busy, valid)) { LUF_PHASE(ca_snapshot_access(g, s, lane, nl)); }
+        c.step += 1;
+        if (in_sv) ++tsv; else ++tbp;
+        if (tsv + tbp >= CA_MAX_STEPS) { tsv = -1; tbp = -1; break; }
+    }
+    *t_sv = tsv; *t_bp = tbp;
+    return parity;
+}
+
+}  // namespace luf

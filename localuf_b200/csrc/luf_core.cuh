@@ -27,6 +27,7 @@
   static inline uint32_t luf_atomic_sub(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o - v; return o; }
   static inline uint32_t luf_atomic_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
   static inline uint32_t luf_atomic_xor(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o ^ v; return o; }
+  static inline uint32_t luf_atomic_and(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o & v; return o; }
   static inline int luf_ffs(uint32_t x) { return __builtin_ffs((int)x); }
   static inline uint32_t luf_mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
   static inline float luf_log2(float x) { return log2f(x); }
@@ -45,6 +46,7 @@
   LUF_DEV uint32_t luf_atomic_sub(uint32_t* p, uint32_t v) { return atomicSub(p, v); }
   LUF_DEV uint32_t luf_atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
   LUF_DEV uint32_t luf_atomic_xor(uint32_t* p, uint32_t v) { return atomicXor(p, v); }
+  LUF_DEV uint32_t luf_atomic_and(uint32_t* p, uint32_t v) { return atomicAnd(p, v); }
   LUF_DEV int luf_ffs(uint32_t x) { return __ffs((int)x); }
   LUF_DEV uint32_t luf_mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
   LUF_DEV float luf_log2(float x) { return __log2f(x); }

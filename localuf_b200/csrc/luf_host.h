@@ -11,6 +11,7 @@
 
 #include "../../include/luf_b200.h"
 #include "luf_core.cuh"
+#include "luf_ca.cuh"
 
 namespace luf {
 
@@ -107,6 +108,63 @@ inline SampleParams make_sample_params(const double* class_p, int n_classes, uin
     }
     sp.key0 = (uint32_t)seed; sp.key1 = (uint32_t)(seed >> 32);
     return sp;
+}
+
+// ------------------------------------------------------------- Macar / Actis
+struct PackedCa {
+    int N = 0, B = 0, E = 0, K = 0, global_span = 0;
+    bool actis_ok = false;
+    std::vector<uint32_t> nbr;
+    std::vector<uint8_t> span;
+    std::vector<uint16_t> relay;
+};
+
+// Returns "" on success, else why the cellular-automaton decoders cannot run on this graph.
+inline std::string pack_ca(const luf_graph_desc& d, PackedCa& out)
+{
+    const int N = d.n_nodes, K = d.n_dirs;
+    if (K < 2 || K > 16 || (K & 1)) return "neighbour table width must be even and at most 16";
+    if (N > 0xFFFE || d.n_edges > 0xFFFE) return "graph too large for the 16-bit cellular-automaton layout";
+    out.N = N; out.B = d.n_boundary; out.E = d.n_edges; out.K = K; out.global_span = d.actis_global_span;
+    out.nbr.assign((size_t)N * K, NBR_NONE);
+    for (int v = 0; v < N; ++v) {
+        if (d.node_id[v] != v) return "Macar/Actis need node index == index_to_id (surface-code graphs)";
+        for (int k = 0; k < K; ++k) {
+            const int e = d.nbr_edge[v * K + k], w = d.nbr_node[v * K + k];
+            if (e < 0) continue;
+            if ((d.nbr_owned[v * K + k] != 0) != (k >= K / 2)) return "unexpected edge ownership in the neighbour table";
+            out.nbr[(size_t)v * K + k] = (uint32_t)e | ((uint32_t)w << 16);
+        }
+    }
+    out.span.assign(N, 0); out.relay.assign(N, 0xFFFF);
+    out.actis_ok = d.actis_global_span > 0 && d.actis_global_span < 255;
+    for (int v = 0; v < N && out.actis_ok; ++v) {
+        const int sp = d.actis_span[v], r = d.actis_relay[v];
+        if (sp < 0 || sp > 255 || r < -1 || r >= N) { out.actis_ok = false; break; }
+        out.span[v] = (uint8_t)sp;
+        out.relay[v] = r < 0 ? (uint16_t)0xFFFF : (uint16_t)r;
+    }
+    return "";
+}
+
+inline CaLayout make_ca_layout(int N, int B, int E, bool actis, bool keep_err)
+{
+    CaLayout l;
+    uint32_t off = 0;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
+    const uint32_t WE = words32(E), WD = words32(N - B) ? words32(N - B) : 1, WN = words32(N), GW = (E + 15) / 16;
+    l.cid = take(2u * N); l.ncid = take(2u * N);
+    l.ptr = take(N); l.fl = take(N);
+    l.ast = actis ? take(N) : 0; l.cnt = actis ? take(N) : 0;
+    l.growth = take(4u * GW); l.gacc = take(4u * GW);
+    l.rx_anyon = take(4u * WN); l.rx_defect = take(4u * WN);
+    l.rx_busy = actis ? take(8u * WN) : 0; l.rx_active = actis ? take(8u * WN) : 0;
+    l.defect = take(4u * WD);
+    l.corr = take(4u * WE);
+    l.glob = take(16);
+    l.err = keep_err ? take(4u * WE) : 0;
+    l.bytes = off;
+    return l;
 }
 
 }  // namespace luf

@@ -97,6 +97,62 @@ __global__ void k_decode_uf(GraphView g, Layout l, int flags, long long nshots,
     }
 }
 
+// Staged K3a: Macar / Actis (decoders/luf/main.py:83-166): syndromes in;
+// correction, growth after validation and (tSV, tBP) out.
+template <bool ACTIS>
+__global__ void k_decode_ca(CaView g, CaLayout l, int flags, long long nshots,
+                            const uint32_t* __restrict__ syn, uint32_t* __restrict__ corr,
+                            uint32_t* __restrict__ growth2b, int32_t* __restrict__ steps)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    const CaShot s = ca_bind(l, smem + (size_t)(threadIdx.x >> 5) * l.bytes);
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        LUF_PHASE(ca_reset<ACTIS>(g, s, lane, nl));
+        LUF_PHASE(for (int w = lane; w < g.WD; w += nl) s.defect[w] = __ldg(&syn[k * g.WD + w]));
+        LUF_PHASE(ca_load(g, s, lane, nl));
+        int tsv, tbp;
+        ca_decode<ACTIS>(g, s, flags, &tsv, &tbp, growth2b ? growth2b + k * g.GW : nullptr, lane, nl);
+        for (int w = lane; w < g.WE; w += nl) corr[k * g.WE + w] = s.corr[w];
+        if (steps && lane == 0) { steps[2 * k] = tsv; steps[2 * k + 1] = tbp; }
+        __syncwarp();
+    }
+}
+
+// Fused K1 + K3a + K4 (batch scheme): counts[0] += failures, [1] += shots,
+// [2] += sum of tSV, [3] += sum of tBP.
+template <bool ACTIS>
+__global__ void k_mc_ca(GraphView gv, CaView g, CaLayout l, SampleParams sp, int flags,
+                        unsigned long long shot0, long long nshots, unsigned long long* counts)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    const CaShot s = ca_bind(l, smem + (size_t)(threadIdx.x >> 5) * l.bytes);
+    Shot samp;                       // the sampler only touches the error / defect bitmaps
+    samp.err = nullptr; samp.defect = s.defect;
+    const long long stride = (long long)gridDim.x * wpb;
+    unsigned int fails = 0;
+    unsigned long long sum_sv = 0, sum_bp = 0;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        uint32_t parity = 0;
+        LUF_PHASE(ca_reset<ACTIS>(g, s, lane, nl));
+        LUF_PHASE(parity ^= ph_sample(gv, samp, sp, shot0 + (unsigned long long)k, lane, nl));
+        LUF_PHASE(ca_load(g, s, lane, nl));
+        int tsv, tbp;
+        parity ^= ca_decode<ACTIS>(g, s, flags, &tsv, &tbp, nullptr, lane, nl);
+        fails += LUF_XOR(parity) & 1u;
+        sum_sv += (unsigned long long)tsv; sum_bp += (unsigned long long)tbp;
+    }
+    if (lane == 0) {
+        if (fails) atomicAdd(&counts[0], (unsigned long long)fails);
+        atomicAdd(&counts[2], sum_sv); atomicAdd(&counts[3], sum_bp);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+}
+
 // Staged K1: bit-packed errors and syndromes to HBM
 // (noise/main.py:114-115,309-314; _base_classes.py:427-450).
 __global__ void k_sample(GraphView g, Layout l, SampleParams sp, unsigned long long shot0,
@@ -144,6 +200,10 @@ struct luf_graph {
     GraphView view{};
     std::vector<void*> allocs;
     Layout lay_fused{}, lay_decode{}, lay_sample{};
+    PackedCa ca_host;
+    std::string ca_why;           // why Macar/Actis cannot run on this graph ("" = they can)
+    CaView ca_view{};
+    CaLayout lay_macar{}, lay_actis{};
     // grow-only scratch for the *_host entry points
     void* scratch[6] = {0, 0, 0, 0, 0, 0};
     size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -179,8 +239,9 @@ struct LaunchCfg { int grid, block; size_t smem; };
 // Warps per block and a persistent grid: as many blocks per SM as the
 // shared-memory budget allows, never more blocks than there is work.
 template <class K>
-static int plan_launch(luf_graph* g, K kernel, const Layout& l, long long nshots, LaunchCfg* cfg)
+static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long nshots, LaunchCfg* cfg)
 {
+    struct { uint32_t bytes; } l = {slice_bytes};
     if (l.bytes > (uint32_t)g->max_smem)
         return fail(LUF_ERR_UNSUPPORTED, "one shot's decoder state (" + std::to_string(l.bytes) +
                     " B) exceeds the shared memory of an SM; CTA-per-shot kernels are not built yet");
@@ -275,6 +336,20 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
         // keep every pointer inside the slice (unused arrays alias the start)
         g->lay_sample = l;
     }
+    g->ca_why = pack_ca(*desc, g->ca_host);
+    if (g->ca_why.empty()) {
+        CaView& c = g->ca_view;
+        const PackedCa& q = g->ca_host;
+        c.N = q.N; c.B = q.B; c.E = q.E; c.K = q.K; c.global_span = q.global_span;
+        c.WE = v.WE; c.WD = v.WD; c.WN = v.WN; c.GW = (q.E + 15) / 16;
+        c.west_mask = v.west_mask;
+        if ((rc = upload(g, q.nbr, &c.nbr)) || (rc = upload(g, q.span, &c.span)) || (rc = upload(g, q.relay, &c.relay))) {
+            luf_graph_destroy(g);
+            return rc;
+        }
+        g->lay_macar = make_ca_layout(q.N, q.B, q.E, false, false);
+        g->lay_actis = make_ca_layout(q.N, q.B, q.E, true, false);
+    }
     *out = g;
     return 0;
 }
@@ -300,14 +375,23 @@ int luf_graph_words(const luf_graph* g, int32_t* edge_words, int32_t* detector_w
 
 int64_t luf_launch_count(const luf_graph* g) { return g ? g->launches : 0; }
 
-static int check_decoder(int decoder, int flags)
+static int check_decoder(const luf_graph* g, int decoder, int flags)
 {
     if (decoder == LUF_DEC_UF) {
         if (flags & ~(LUF_UF_DYNAMIC | LUF_UF_WEST)) return fail(LUF_ERR_INVALID, "unknown UF flag");
         return 0;
     }
-    if (decoder == LUF_DEC_MACAR || decoder == LUF_DEC_ACTIS || decoder == LUF_DEC_SNOWFLAKE)
-        return fail(LUF_ERR_UNSUPPORTED, "decoder not built into this library yet");
+    if (decoder == LUF_DEC_MACAR || decoder == LUF_DEC_ACTIS) {
+        if (!g->ca_why.empty()) return fail(LUF_ERR_UNSUPPORTED, g->ca_why);
+        if (decoder == LUF_DEC_MACAR && flags) return fail(LUF_ERR_INVALID, "Macar takes no flags");
+        if (decoder == LUF_DEC_ACTIS) {
+            if (flags & ~LUF_ACTIS_UNOPTIMAL) return fail(LUF_ERR_INVALID, "unknown Actis flag");
+            if (!g->ca_host.actis_ok) return fail(LUF_ERR_UNSUPPORTED, "Actis needs a batch-scheme surface-code graph");
+        }
+        return 0;
+    }
+    if (decoder == LUF_DEC_SNOWFLAKE)
+        return fail(LUF_ERR_UNSUPPORTED, "Snowflake runs through the streaming entry points");
     return fail(LUF_ERR_INVALID, "unknown decoder");
 }
 
@@ -320,7 +404,7 @@ int luf_sample(luf_graph* g, const double* class_p_host, uint64_t seed, uint64_t
     CUDA_TRY(cudaSetDevice(g->device));
     const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
     LaunchCfg c;
-    if (int rc = plan_launch(g, k_sample, g->lay_sample, nshots, &c)) return rc;
+    if (int rc = plan_launch(g, k_sample, g->lay_sample.bytes, nshots, &c)) return rc;
     k_sample<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_sample, sp, shot0, nshots,
                                                                  err_bits_dev, syn_bits_dev);
     CUDA_TRY(cudaGetLastError());
@@ -333,13 +417,23 @@ int luf_decode_batch(luf_graph* g, int decoder, int flags, int64_t nshots, const
 {
     if (!g || !syn_bits_dev || !corr_bits_dev || nshots < 0)
         return fail(LUF_ERR_INVALID, "luf_decode_batch: bad argument");
-    if (int rc = check_decoder(decoder, flags)) return rc;
+    if (int rc = check_decoder(g, decoder, flags)) return rc;
     if (nshots == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
     LaunchCfg c;
-    if (int rc = plan_launch(g, k_decode_uf, g->lay_decode, nshots, &c)) return rc;
-    k_decode_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_decode, flags, nshots,
-                                                                    syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+    if (decoder == LUF_DEC_MACAR) {
+        if (int rc = plan_launch(g, k_decode_ca<false>, g->lay_macar.bytes, nshots, &c)) return rc;
+        k_decode_ca<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(
+            g->ca_view, g->lay_macar, flags, nshots, syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+    } else if (decoder == LUF_DEC_ACTIS) {
+        if (int rc = plan_launch(g, k_decode_ca<true>, g->lay_actis.bytes, nshots, &c)) return rc;
+        k_decode_ca<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(
+            g->ca_view, g->lay_actis, flags, nshots, syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+    } else {
+        if (int rc = plan_launch(g, k_decode_uf, g->lay_decode.bytes, nshots, &c)) return rc;
+        k_decode_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_decode, flags, nshots,
+                                                                        syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+    }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;
     return 0;
@@ -367,13 +461,23 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
                uint64_t shot0, int64_t nshots, unsigned long long* counts_dev, void* stream)
 {
     if (!g || !class_p_host || !counts_dev || nshots < 0) return fail(LUF_ERR_INVALID, "luf_mc_run: bad argument");
-    if (int rc = check_decoder(decoder, flags)) return rc;
+    if (int rc = check_decoder(g, decoder, flags)) return rc;
     if (nshots == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
     const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
     LaunchCfg c;
-    if (int rc = plan_launch(g, k_mc_uf, g->lay_fused, nshots, &c)) return rc;
-    k_mc_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, shot0, nshots, counts_dev);
+    if (decoder == LUF_DEC_MACAR) {
+        if (int rc = plan_launch(g, k_mc_ca<false>, g->lay_macar.bytes, nshots, &c)) return rc;
+        k_mc_ca<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_macar, sp, flags,
+                                                                           shot0, nshots, counts_dev);
+    } else if (decoder == LUF_DEC_ACTIS) {
+        if (int rc = plan_launch(g, k_mc_ca<true>, g->lay_actis.bytes, nshots, &c)) return rc;
+        k_mc_ca<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_actis, sp, flags,
+                                                                          shot0, nshots, counts_dev);
+    } else {
+        if (int rc = plan_launch(g, k_mc_uf, g->lay_fused.bytes, nshots, &c)) return rc;
+        k_mc_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, shot0, nshots, counts_dev);
+    }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;
     return 0;
@@ -387,12 +491,12 @@ int luf_mc_run_host(luf_graph* g, int decoder, int flags, const double* class_p_
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
     void* d = nullptr;
-    if (int rc = scratch_get(g, 0, 16, &d)) return rc;
-    CUDA_TRY(cudaMemsetAsync(d, 0, 16, 0));
+    if (int rc = scratch_get(g, 0, 32, &d)) return rc;
+    CUDA_TRY(cudaMemsetAsync(d, 0, 32, 0));
     if (int rc = luf_mc_run(g, decoder, flags, class_p_host, seed, shot0, nshots, (unsigned long long*)d, 0)) return rc;
-    unsigned long long tmp[2] = {0, 0};
-    CUDA_TRY(cudaMemcpy(tmp, d, 16, cudaMemcpyDeviceToHost));
-    counts_host[0] += tmp[0]; counts_host[1] += tmp[1];
+    unsigned long long tmp[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpy(tmp, d, 32, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) counts_host[i] += tmp[i];
     return 0;
 }
 
@@ -450,7 +554,7 @@ int luf_check_host(luf_graph* g, int64_t nshots, const uint32_t* err_bits_host, 
     void *err, *corr, *lg, *cnt;
     int rc;
     if ((rc = scratch_get(g, 1, n * WE * 4, &err)) || (rc = scratch_get(g, 2, n * WE * 4, &corr)) ||
-        (rc = scratch_get(g, 3, n, &lg)) || (rc = scratch_get(g, 0, 16, &cnt))) return rc;
+        (rc = scratch_get(g, 3, n, &lg)) || (rc = scratch_get(g, 0, 32, &cnt))) return rc;
     CUDA_TRY(cudaMemcpyAsync(err, err_bits_host, n * WE * 4, cudaMemcpyHostToDevice, 0));
     CUDA_TRY(cudaMemcpyAsync(corr, corr_bits_host, n * WE * 4, cudaMemcpyHostToDevice, 0));
     CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, 0));

@@ -1,0 +1,27 @@
+"""Runtime (timestep-count) data of the cellular-automaton decoders.
+
+Same signatures and DataFrame shapes as ``localuf/sim/runtime.py:25-75``
+(``batch``): columns ``(stage, d, p)`` with stage ``'SV'`` / ``'BP'``, one row
+per sample.  Samples are drawn and decoded on the device.
+"""
+from __future__ import annotations
+
+from pandas import DataFrame
+
+from localuf_b200.codes import Surface
+from localuf_b200.decoders import Macar
+
+
+def batch(ds, noise_levels, n, noise, decoder_class=Macar, validate_only=True, **kwargs_for_Surface):
+    data = {}
+    for d in ds:
+        code = Surface(d, noise, scheme='batch', window_height=None, **kwargs_for_Surface)
+        decoder = decoder_class(code)
+        for noise_level in noise_levels:
+            steps = decoder.sample_steps(noise_level, n)
+            data['SV', d, noise_level] = steps[:, 0].tolist()
+            if not validate_only:
+                data['BP', d, noise_level] = steps[:, 1].tolist()
+    df = DataFrame(data).sort_index(axis=1)
+    df.columns.set_names(['stage', 'd', 'p'], inplace=True)
+    return df

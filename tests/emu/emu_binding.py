@@ -69,3 +69,14 @@ class Emu:
                              _vp(err), _vp(syn), _vp(corr))
         assert rc == 0
         return int(counts[0]), err, syn, corr
+
+    def decode_ca(self, decoder, flags, syn_bits):
+        syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
+        n = syn.shape[0]
+        corr = np.zeros((n, self.WE), np.uint32)
+        growth = np.zeros((n, self.WG), np.uint32)
+        steps = np.zeros((n, 2), np.int32)
+        rc = lib().emu_decode_ca(C.byref(self.desc), decoder, flags, C.c_longlong(n), _vp(syn),
+                                 _vp(corr), _vp(growth), _vp(steps))
+        assert rc == 0, rc
+        return corr, growth, steps

@@ -1,0 +1,29 @@
+"""Macar / Actis kernel phases (localuf_b200/csrc/luf_ca.cuh compiled for the
+host) vs. goldens exported from the unmodified reference.  CPU-only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, make_code, golden_names
+
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
+import emu_binding  # noqa: E402
+from localuf_b200._engine import unpack_growth  # noqa: E402
+
+DECODERS = {'macar': (1, 0), 'actis': (2, 0), 'actis_unopt': (2, 4)}
+
+
+@pytest.mark.parametrize('name', golden_names('ca_'))
+def test_emu_ca_matches_reference(name):
+    meta, arr = load_golden(name)
+    code = make_code(meta['spec'])
+    emu = emu_binding.Emu(code)
+    for key in meta['decoders']:
+        dec, flags = DECODERS[key]
+        corr, growth2b, steps = emu.decode_ca(dec, flags, arr['syn_bits'])
+        np.testing.assert_array_equal(steps, arr[f'{key}_steps'], err_msg=f'{name} {key} (tSV, tBP)')
+        np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{key}_growth'],
+                                      err_msg=f'{name} {key} erasure after validate')
+        np.testing.assert_array_equal(corr, arr[f'{key}_corr'], err_msg=f'{name} {key} correction')
