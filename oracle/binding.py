@@ -54,6 +54,71 @@ def lib():
     return _lib
 
 
+class OracleWindow(C.Structure):
+    _fields_ = [
+        ('d', C.c_int32), ('h', C.c_int32), ('NLb', C.c_int32), ('NLd', C.c_int32), ('EL', C.c_int32), ('K', C.c_int32),
+        ('nb_valid', C.c_void_p), ('nb_q', C.c_void_p), ('nb_dt', C.c_void_p), ('nb_el', C.c_void_p), ('nb_et', C.c_void_p),
+        ('edge_q', C.c_void_p), ('edge_dt', C.c_void_p), ('edge_class', C.c_void_p), ('edge_fb', C.c_void_p),
+        ('pos_long', C.c_void_p), ('n_classes', C.c_int32), ('merger_slow', C.c_int32), ('schedule_11', C.c_int32),
+    ]
+
+
+class StreamOracle:
+    """Snowflake + frugal oracle bound to one window (localuf_b200._window.WindowTables)."""
+
+    def __init__(self, tables, merger='fast', schedule='2:1'):
+        self.t = tables
+        self._keep = {}
+        w = OracleWindow()
+        for f in ('d', 'h', 'NLb', 'NLd', 'EL', 'K', 'n_classes'):
+            setattr(w, f, int(getattr(tables, f)))
+        for name, dt in (('nb_valid', np.uint8), ('nb_q', np.int32), ('nb_dt', np.int32), ('nb_el', np.int32),
+                         ('nb_et', np.int32), ('edge_q', np.int32), ('edge_dt', np.int32),
+                         ('edge_class', np.uint8), ('edge_fb', np.uint8), ('pos_long', np.int32)):
+            a = np.ascontiguousarray(getattr(tables, name), dtype=dt)
+            self._keep[name] = a
+            setattr(w, name, a.ctypes.data)
+        w.merger_slow = int(merger == 'slow')
+        w.schedule_11 = int(schedule == '1:1')
+        self.w = w
+        self.W = (tables.EL + 31) // 32
+
+    def stream(self, fresh_local_bits):
+        fresh = np.ascontiguousarray(fresh_local_bits, dtype=np.uint32).reshape(-1, self.W)
+        n = fresh.shape[0]
+        rt_all = np.zeros(n, np.int32); rt_unr = np.zeros(n, np.int32); m = np.zeros(n, np.int32)
+        floor = np.zeros((n, self.W), np.uint32)
+        lib().oracle_sf_stream.restype = C.c_int
+        rc = lib().oracle_sf_stream(C.byref(self.w), C.c_int32(n), C.c_void_p(fresh.ctypes.data),
+                                    C.c_void_p(rt_all.ctypes.data), C.c_void_p(rt_unr.ctypes.data),
+                                    C.c_void_p(floor.ctypes.data), C.c_void_p(m.ctypes.data))
+        if rc != 0:
+            raise RuntimeError('oracle_sf_stream failed')
+        return rt_all, rt_unr, floor, m
+
+    def mc(self, class_p, seed, nshots, n, nthreads=1):
+        cp = np.ascontiguousarray(class_p, dtype=np.float64)
+        cycles = C.c_int64(0)
+        lib().oracle_sf_mc.restype = C.c_int64
+        m = lib().oracle_sf_mc(C.byref(self.w), C.c_void_p(cp.ctypes.data), C.c_uint64(seed), C.c_int64(nshots),
+                               C.c_int32(n), C.c_int(nthreads), C.byref(cycles))
+        return int(m), int(cycles.value)
+
+
+def code_bits_to_local(tables, bits, block):
+    """[n, W(E)] bits over code edge ids -> [n, W(EL)] bits over the local index of layer block `block`
+    (block 0 = freshly sampled sheet, block h-1 = floor sheet); asserts nothing lies outside the block."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint32)
+    E = tables.layered_of_code.shape[0]
+    u = np.unpackbits(bits.view(np.uint8), axis=1, bitorder='little')[:, :E]
+    lay = tables.layered_of_code
+    inside = (lay >= block * tables.EL) & (lay < (block + 1) * tables.EL)
+    assert not u[:, ~inside].any()
+    out = np.zeros((bits.shape[0], 32 * ((tables.EL + 31) // 32)), np.uint8)
+    out[:, lay[inside] - block * tables.EL] = u[:, inside]
+    return np.packbits(out, axis=1, bitorder='little').view(np.uint32)
+
+
 NOISE_KIND = {'code capacity': 0, 'phenomenological': 1, 'circuit-level': 2}
 
 

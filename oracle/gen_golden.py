@@ -231,11 +231,11 @@ def main():
     jobs = {'graphs': lambda: graph_cases()}
     for case in UF_CASES:
         jobs[case[0]] = (lambda c=case: uf_case(*c))
-    try:
-        import gen_golden_ca
-        jobs.update(gen_golden_ca.jobs())
-    except ImportError:
-        pass
+    for extra in ('gen_golden_ca', 'gen_golden_sf'):
+        try:
+            jobs.update(__import__(extra).jobs())
+        except ImportError:
+            pass
     for name, job in jobs.items():
         if args.only and name not in args.only:
             continue

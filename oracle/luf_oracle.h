@@ -75,6 +75,37 @@ int oracle_decode_batch(const oracle_graph *g, int decoder, int flags, int64_t n
 int64_t oracle_mc_batch(const oracle_graph *g, int decoder, int flags, const double *class_p,
                         uint64_t seed, int64_t nshots, int nthreads);
 
+/* ---- streaming: Snowflake under the frugal scheme -------------------------
+ * Layered window tables (see localuf_b200/_window.py for the conventions):
+ * node (q, t) -> Snowflake id; edge (block tmin, local l) -> (h-1-tmin)*EL + l. */
+typedef struct {
+    int32_t d, h, NLb, NLd, EL, K;
+    const uint8_t *nb_valid;                        /* [NL*K] */
+    const int32_t *nb_q, *nb_dt, *nb_el, *nb_et;    /* [NL*K] */
+    const int32_t *edge_q, *edge_dt;                /* [EL*2] endpoints (first, second), layer relative to the block */
+    const uint8_t *edge_class, *edge_fb;            /* [EL] */
+    const int32_t *pos_long;                        /* [NL] */
+    int32_t n_classes;
+    int32_t merger_slow;                            /* Snowflake(merger='slow'), snowflake/main.py:1237-1256 */
+    int32_t schedule_11;                            /* Snowflake(schedule='1:1'), snowflake/main.py:1284-1305 */
+} oracle_window;
+
+/* One Frugal.run-like stream (_schemes.py:504-564,626-644) of ncycles decoding
+ * cycles with the fresh errors GIVEN: fresh_bits [ncycles][W(EL)] over the local
+ * edge index of the top block (the exclude_future_boundary filter already
+ * applied by the caller).  Outputs per cycle: runtime with time_only='all' and
+ * 'unrooting' (snowflake/main.py:340-347), the floor-sheet correction bits
+ * committed at that cycle's drop [ncycles][W(EL)], and the logical errors
+ * counted after the cycle (_pairs.py:90-111). */
+int oracle_sf_stream(const oracle_window *w, int32_t ncycles, const uint32_t *fresh_bits,
+                     int32_t *rt_all, int32_t *rt_unrooting, uint32_t *floor_bits, int32_t *m_cycle);
+
+/* Monte Carlo: nshots independent Frugal.run(n) streams (_schemes.py:566-649)
+ * with per-edge Bernoulli sampling; returns total logical errors, adds the
+ * decoding cycles simulated to *cycles. */
+int64_t oracle_sf_mc(const oracle_window *w, const double *class_p, uint64_t seed, int64_t nshots,
+                     int32_t n, int nthreads, int64_t *cycles);
+
 #ifdef __cplusplus
 }
 #endif
