@@ -148,6 +148,68 @@ int luf_check_host(luf_graph *g, int64_t nshots, const uint32_t *err_bits_host,
                    const uint32_t *corr_bits_host, uint8_t *logical_host,
                    unsigned long long *fail_count_host);
 
+/* ---- streaming: Snowflake under the frugal scheme ---------------------------
+ * Layered tables of one sliding window (localuf_b200/_window.py): node (q, t),
+ * edge (block tmin, local l).  Replaces the per-node / per-edge Python objects
+ * of localuf/decoders/snowflake/main.py:82-98,900-1031,1452-1496 and the
+ * window bookkeeping of localuf/_schemes.py:480-564. */
+typedef struct {
+    int32_t d, h;                 /* distance, window height (commit height is 1) */
+    int32_t n_boundary_per_layer; /* NLb: positions [0, NLb) of a layer are space-boundary nodes */
+    int32_t n_detectors_per_layer;/* NLd */
+    int32_t edges_per_layer;      /* EL */
+    int32_t n_dirs;               /* K neighbour slots, in the decoder's scan order */
+    const uint8_t *nb_valid;      /* [NL*K] */
+    const int32_t *nb_q;          /* [NL*K] neighbour's in-layer position */
+    const int32_t *nb_dt;         /* [NL*K] neighbour's layer minus the node's layer (-1, 0, 1) */
+    const int32_t *nb_el;         /* [NL*K] local index of the connecting edge */
+    const int32_t *nb_et;         /* [NL*K] edge block minus the node's layer (0 or -1) */
+    const int32_t *edge_q;        /* [EL*2] endpoint positions (first, second endpoint) */
+    const int32_t *edge_dt;       /* [EL*2] endpoint layer minus edge block (0 or 1) */
+    const uint8_t *edge_class;    /* [EL] probability class of the edge when freshly sampled */
+    const uint8_t *edge_fb;       /* [EL] 1 if the fresh edge touches the future boundary */
+    const int32_t *pos_long;      /* [NL] coordinate along the long axis */
+    int32_t n_classes;
+} luf_window_desc;
+
+typedef struct luf_stream luf_stream;
+enum {
+    LUF_SF_SLOW_MERGER = 1,       /* Snowflake(merger='slow'),  snowflake/main.py:1237-1246 */
+    LUF_SF_ONE_ONE = 2            /* Snowflake(schedule='1:1'), snowflake/main.py:1284-1305 */
+};
+
+int luf_stream_create(const luf_window_desc *desc, int device, luf_stream **out);
+int luf_stream_destroy(luf_stream *s);
+
+/* K3b, parity path -- replaces Frugal.advance + get_logical_error
+ * (localuf/_schemes.py:504-564,262-276) and Snowflake.decode
+ * (localuf/decoders/snowflake/main.py:216-353) for ncycles consecutive cycles of
+ * nstreams independent windows whose fresh errors are GIVEN:
+ * fresh_bits_dev [nstreams][ncycles][W(EL)] over the local index of the top
+ * layer block.  Outputs: rt_dev [nstreams][ncycles][2] = decode's return value
+ * for time_only='all' and 'unrooting'; floor_bits_dev (optional)
+ * [nstreams][ncycles][W(EL)] = the floor-sheet correction committed by each
+ * drop; m_dev [nstreams][ncycles] = logical errors counted after each cycle. */
+int luf_stream_decode(luf_stream *s, int flags, int64_t nstreams, int32_t ncycles,
+                      const uint32_t *fresh_bits_dev, int32_t *rt_dev, uint32_t *floor_bits_dev,
+                      int32_t *m_dev, void *stream);
+
+/* Fused K1+K3b+K4 -- replaces Frugal.run(decoder, p, n) (localuf/_schemes.py:566-649)
+ * for nstreams independent memory experiments [stream0, stream0 + nstreams):
+ * counts_dev uint64[4]: [0] += logical errors, [1] += decoding cycles run,
+ * [2] / [3] += runtime 'all' / 'unrooting' summed over the timed cycles.
+ * steps_dev (optional) [nstreams][n][2]: the same two sums per timed block of d
+ * cycles (Frugal.step_counts). */
+int luf_stream_mc(luf_stream *s, int flags, const double *class_p_host, uint64_t seed, uint64_t stream0,
+                  int64_t nstreams, int32_t n, unsigned long long *counts_dev, int32_t *steps_dev, void *stream);
+
+int luf_stream_decode_host(luf_stream *s, int flags, int64_t nstreams, int32_t ncycles,
+                           const uint32_t *fresh_bits_host, int32_t *rt_host, uint32_t *floor_bits_host,
+                           int32_t *m_host);
+int luf_stream_mc_host(luf_stream *s, int flags, const double *class_p_host, uint64_t seed, uint64_t stream0,
+                       int64_t nstreams, int32_t n, unsigned long long counts_host[4], int32_t *steps_host);
+int64_t luf_stream_launch_count(const luf_stream *s);
+
 /* Number of kernel launches issued through this graph so far (bench.py's gpu_launches). */
 int64_t luf_launch_count(const luf_graph *g);
 

@@ -67,6 +67,34 @@ def make_desc(flat, noise_kind: int):
     return d, keep
 
 
+class WindowDesc(C.Structure):
+    """``luf_window_desc`` of include/luf_b200.h."""
+    _fields_ = [
+        ('d', C.c_int32), ('h', C.c_int32), ('n_boundary_per_layer', C.c_int32),
+        ('n_detectors_per_layer', C.c_int32), ('edges_per_layer', C.c_int32), ('n_dirs', C.c_int32),
+        ('nb_valid', C.c_void_p), ('nb_q', C.c_void_p), ('nb_dt', C.c_void_p), ('nb_el', C.c_void_p),
+        ('nb_et', C.c_void_p), ('edge_q', C.c_void_p), ('edge_dt', C.c_void_p), ('edge_class', C.c_void_p),
+        ('edge_fb', C.c_void_p), ('pos_long', C.c_void_p), ('n_classes', C.c_int32),
+    ]
+
+
+def make_window_desc(t):
+    """Return ``(WindowDesc, keepalive)`` for a :class:`localuf_b200._window.WindowTables`."""
+    keep = {}
+    d = WindowDesc()
+    d.d, d.h, d.n_boundary_per_layer, d.n_detectors_per_layer = t.d, t.h, t.NLb, t.NLd
+    d.edges_per_layer, d.n_dirs, d.n_classes = t.EL, t.K, t.n_classes
+    for name, dt in (('nb_valid', np.uint8), ('nb_q', np.int32), ('nb_dt', np.int32), ('nb_el', np.int32),
+                     ('nb_et', np.int32), ('edge_q', np.int32), ('edge_dt', np.int32), ('edge_class', np.uint8),
+                     ('edge_fb', np.uint8), ('pos_long', np.int32)):
+        a = np.ascontiguousarray(getattr(t, name), dtype=dt)
+        keep[name] = a
+        setattr(d, name, a.ctypes.data)
+    return d, keep
+
+
+SF_SLOW_MERGER, SF_ONE_ONE = 1, 2
+
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -96,6 +124,14 @@ def _load():
         lib.luf_decode_batch_host.argtypes = [v, C.c_int, C.c_int, i64, v, v, v, v]
         lib.luf_sample_host.argtypes = [v, v, u64, u64, i64, v, v]
         lib.luf_check_host.argtypes = [v, i64, v, v, v, v]
+        lib.luf_stream_create.argtypes = [C.POINTER(WindowDesc), C.c_int, C.POINTER(C.c_void_p)]
+        lib.luf_stream_destroy.argtypes = [v]
+        lib.luf_stream_launch_count.restype = C.c_int64
+        lib.luf_stream_launch_count.argtypes = [v]
+        lib.luf_stream_decode.argtypes = [v, C.c_int, i64, C.c_int32, v, v, v, v, v]
+        lib.luf_stream_mc.argtypes = [v, C.c_int, v, u64, u64, i64, C.c_int32, v, v, v]
+        lib.luf_stream_decode_host.argtypes = [v, C.c_int, i64, C.c_int32, v, v, v, v]
+        lib.luf_stream_mc_host.argtypes = [v, C.c_int, v, u64, u64, i64, C.c_int32, v, v]
         _lib = lib
         return lib
 
@@ -216,6 +252,62 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(_load().luf_launch_count(self._h))
+
+
+class StreamEngine:
+    """One uploaded sliding window (``luf_stream``) on one CUDA device."""
+
+    def __init__(self, code, tables=None, device: int | None = None):
+        from localuf_b200 import _window
+        lib = _load()
+        if lib.luf_device_count() <= 0:
+            raise EngineUnavailable("no CUDA device visible; the engine has no CPU fallback")
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', 0)) % lib.luf_device_count()
+        self.device = device
+        self.noise = code.NOISE
+        self.tables = tables if tables is not None else _window.build(code)
+        desc, self._keep = make_window_desc(self.tables)
+        handle = C.c_void_p()
+        _check(lib.luf_stream_create(C.byref(desc), device, C.byref(handle)))
+        self._h = handle
+        self.W = (self.tables.EL + 31) // 32
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h and _lib is not None:
+            _lib.luf_stream_destroy(h)
+
+    def class_p(self, noise_level: float) -> np.ndarray:
+        return np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
+
+    def decode_host(self, flags: int, fresh_bits, want_floor=True):
+        """fresh_bits [nstreams, ncycles, W] -> (rt [.., 2], floor [.., W] or None, m [..])."""
+        fresh = np.ascontiguousarray(fresh_bits, dtype=np.uint32)
+        ns, nc = fresh.shape[0], fresh.shape[1]
+        rt = np.zeros((ns, nc, 2), np.int32)
+        m = np.zeros((ns, nc), np.int32)
+        floor = np.zeros((ns, nc, self.W), np.uint32) if want_floor else None
+        _check(_load().luf_stream_decode_host(self._h, flags, ns, nc, _ptr(fresh), _ptr(rt), _ptr(floor), _ptr(m)))
+        return rt, floor, m
+
+    def mc_host(self, flags: int, noise_level: float, seed: int, stream0: int, nstreams: int, n: int,
+                want_steps=False):
+        cp = self.class_p(noise_level)
+        counts = (C.c_ulonglong * 4)(0, 0, 0, 0)
+        steps = np.zeros((nstreams, n, 2), np.int32) if want_steps else None
+        _check(_load().luf_stream_mc_host(self._h, flags, cp.ctypes.data, seed, stream0, nstreams, n, counts,
+                                          _ptr(steps)))
+        return [int(x) for x in counts], steps
+
+    def mc(self, flags, noise_level, seed, stream0, nstreams, n, counts, steps=None):
+        cp = self.class_p(noise_level)
+        _check(_load().luf_stream_mc(self._h, flags, cp.ctypes.data, seed, stream0, nstreams, n,
+                                     _ptr(counts), _ptr(steps), _stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(_load().luf_stream_launch_count(self._h))
 
 
 def unpack_growth(growth2b: np.ndarray, n_edges: int) -> np.ndarray:

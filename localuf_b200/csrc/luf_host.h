@@ -12,6 +12,7 @@
 #include "../../include/luf_b200.h"
 #include "luf_core.cuh"
 #include "luf_ca.cuh"
+#include "luf_sf.cuh"
 
 namespace luf {
 
@@ -163,6 +164,70 @@ inline CaLayout make_ca_layout(int N, int B, int E, bool actis, bool keep_err)
     l.corr = take(4u * WE);
     l.glob = take(16);
     l.err = keep_err ? take(4u * WE) : 0;
+    l.bytes = off;
+    return l;
+}
+
+// ----------------------------------------------------- Snowflake / frugal
+struct PackedWindow {
+    int d = 0, h = 0, NLb = 0, NLd = 0, NL = 0, EL = 0, K = 0, n_classes = 0;
+    std::vector<uint32_t> nbr, edge_ends, class_end;
+    std::vector<int8_t> pos_long;
+    std::vector<uint16_t> fresh_perm;
+};
+
+inline std::string pack_window(const luf_window_desc& d, PackedWindow& out)
+{
+    const int NL = d.n_boundary_per_layer + d.n_detectors_per_layer, K = d.n_dirs, EL = d.edges_per_layer;
+    if (d.h < 3 || NL <= 0 || EL <= 0 || K <= 0 || K > 16) return "inconsistent window";
+    if (NL > 1023 || EL > 4095) return "window layer too large for the packed tables (NL <= 1023, EL <= 4095)";
+    if ((long long)NL * d.h > 0xFFFE) return "window too large for 16-bit cluster ids";
+    if (d.n_classes < 1 || d.n_classes > MAX_CLASSES) return "n_classes out of range";
+    out.d = d.d; out.h = d.h; out.NLb = d.n_boundary_per_layer; out.NLd = d.n_detectors_per_layer;
+    out.NL = NL; out.EL = EL; out.K = K; out.n_classes = d.n_classes;
+    out.nbr.assign((size_t)NL * K, 0);
+    for (int x = 0; x < NL * K; ++x) {
+        if (!d.nb_valid[x]) continue;
+        const int dt = d.nb_dt[x], et = d.nb_et[x];
+        if (dt < -1 || dt > 1 || et < -1 || et > 0 || d.nb_q[x] < 0 || d.nb_q[x] >= NL || d.nb_el[x] < 0 || d.nb_el[x] >= EL)
+            return "neighbour table entry out of range";
+        out.nbr[x] = 1u | ((uint32_t)d.nb_q[x] << 1) | ((uint32_t)d.nb_el[x] << 11) |
+                     ((uint32_t)(dt + 1) << 23) | ((uint32_t)(et + 1) << 25);
+    }
+    out.edge_ends.assign(EL, 0);
+    for (int l = 0; l < EL; ++l) {
+        for (int x = 0; x < 2; ++x) {
+            const int q = d.edge_q[2 * l + x], dt = d.edge_dt[2 * l + x];
+            if (q < 0 || q >= NL || dt < 0 || dt > 1) return "edge endpoint out of range";
+            out.edge_ends[l] |= ((uint32_t)q | ((uint32_t)dt << 10)) << (11 * x);
+        }
+        if (d.edge_fb[l]) out.edge_ends[l] |= 1u << 22;
+    }
+    out.pos_long.assign(NL, 0);
+    for (int q = 0; q < NL; ++q) out.pos_long[q] = (int8_t)d.pos_long[q];
+    out.class_end.assign(d.n_classes, 0);
+    out.fresh_perm.clear();
+    for (int c = 0; c < d.n_classes; ++c) {
+        for (int l = 0; l < EL; ++l)
+            if (d.edge_class[l] == c) out.fresh_perm.push_back((uint16_t)l);
+        out.class_end[c] = (uint32_t)out.fresh_perm.size();
+    }
+    if ((int)out.fresh_perm.size() != EL) return "every edge of the fresh sheet needs a probability class";
+    return "";
+}
+
+inline SfLayout make_sf_layout(const PackedWindow& p)
+{
+    SfLayout l;
+    uint32_t off = 0;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
+    const uint32_t N = (uint32_t)p.NL * p.h, ELw = words32(p.EL), WLn = words32(p.NL);
+    l.cid = take(2u * N); l.ncid = take(2u * N); l.fl = take(2u * N); l.ptr = take(N);
+    l.ndef = take(4u * p.h * WLn);
+    l.growth = take(4u * p.h * 2u * ELw);
+    l.corr = take(4u * p.h * ELw); l.err = take(4u * p.h * ELw);
+    l.top = take(4u * WLn); l.fb = take(4u * WLn);
+    l.partner = take(2u * 2u * p.NL);
     l.bytes = off;
     return l;
 }

@@ -153,6 +153,49 @@ __global__ void k_mc_ca(GraphView gv, CaView g, CaLayout l, SampleParams sp, int
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
 }
 
+// K3b parity path: Snowflake + frugal bookkeeping on GIVEN fresh errors.
+__global__ void k_sf_decode(SfView g, SfLayout l, int flags, long long nstreams, int ncycles,
+                            const uint32_t* __restrict__ fresh, int32_t* __restrict__ rt,
+                            uint32_t* __restrict__ floor_bits, int32_t* __restrict__ m_out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    const SfShot s = sf_bind(l, smem + (size_t)(threadIdx.x >> 5) * l.bytes);
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nstreams; k += stride) {
+        LUF_PHASE(sf_reset(g, s, lane, nl));
+        for (int c = 0; c < ncycles; ++c) {
+            const size_t row = (size_t)k * ncycles + c;
+            int m = 0, ra = 0, ru = 0;
+            sf_cycle_head(g, s, m, lane, nl);
+            LUF_PHASE(sf_given_sheet(g, s, fresh + row * g.ELw, lane, nl));
+            sf_cycle_tail(g, s, flags, floor_bits ? floor_bits + row * g.ELw : nullptr, m, ra, ru, lane, nl);
+            if (lane == 0) { rt[2 * row] = ra; rt[2 * row + 1] = ru; m_out[row] = m; }
+        }
+    }
+}
+
+// Fused K1 + K3b + K4: one Frugal.run(n) memory experiment per warp.
+__global__ void k_sf_mc(SfView g, SfLayout l, SampleParams sp, int flags, unsigned long long stream0,
+                        long long nstreams, int n, unsigned long long* counts, int32_t* steps)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    const SfShot s = sf_bind(l, smem + (size_t)(threadIdx.x >> 5) * l.bytes);
+    const long long stride = (long long)gridDim.x * wpb;
+    int m_total = 0;
+    long long cycles = 0, ra = 0, ru = 0;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nstreams; k += stride)
+        sf_run(g, s, sp, flags, stream0 + (unsigned long long)k, n, m_total, cycles, ra, ru,
+               steps ? steps + (size_t)k * n * 2 : nullptr, lane, nl);
+    if (lane == 0) {
+        atomicAdd(&counts[0], (unsigned long long)m_total); atomicAdd(&counts[1], (unsigned long long)cycles);
+        atomicAdd(&counts[2], (unsigned long long)ra); atomicAdd(&counts[3], (unsigned long long)ru);
+    }
+}
+
 // Staged K1: bit-packed errors and syndromes to HBM
 // (noise/main.py:114-115,309-314; _base_classes.py:427-450).
 __global__ void k_sample(GraphView g, Layout l, SampleParams sp, unsigned long long shot0,
@@ -285,7 +328,192 @@ static int check_device(void)
     return 0;
 }
 
+// ------------------------------------------------------------------ streams
+struct luf_stream {
+    int device = 0, sm_count = 0, max_smem = 0;
+    PackedWindow host;
+    SfView view{};
+    SfLayout lay{};
+    std::vector<void*> allocs;
+    void* scratch[5] = {0, 0, 0, 0, 0};
+    size_t scratch_bytes[5] = {0, 0, 0, 0, 0};
+    long long launches = 0;
+    std::mutex mu;
+};
+
+template <class T>
+static int upload_s(luf_stream* g, const std::vector<T>& v, const T** out)
+{
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, v.size() * sizeof(T) + 16));
+    g->allocs.push_back(p);
+    CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)p;
+    return 0;
+}
+
+static int scratch_s(luf_stream* g, int slot, size_t bytes, void** out)
+{
+    if (bytes > g->scratch_bytes[slot]) {
+        if (g->scratch[slot]) CUDA_TRY(cudaFree(g->scratch[slot]));
+        g->scratch[slot] = nullptr; g->scratch_bytes[slot] = 0;
+        CUDA_TRY(cudaMalloc(&g->scratch[slot], bytes));
+        g->scratch_bytes[slot] = bytes;
+    }
+    *out = g->scratch[slot];
+    return 0;
+}
+
+// one warp per stream; as many blocks per SM as shared memory allows
+template <class K>
+static int plan_stream_launch(luf_stream* g, K kernel, long long nstreams, LaunchCfg* cfg)
+{
+    const uint32_t bytes = g->lay.bytes;
+    if (bytes > (uint32_t)g->max_smem)
+        return fail(LUF_ERR_UNSUPPORTED, "one window's decoder state (" + std::to_string(bytes) +
+                    " B) exceeds the shared memory of an SM");
+    int wpb = g->max_smem / (int)bytes;
+    if (wpb > 4) wpb = 4;
+    const size_t smem = (size_t)wpb * bytes;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * WARP, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)g->sm_count * per_sm;
+    const long long need = (nstreams + wpb - 1) / wpb;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    cfg->grid = (int)blocks; cfg->block = wpb * WARP; cfg->smem = smem;
+    return 0;
+}
+
 extern "C" {
+
+int luf_stream_create(const luf_window_desc* desc, int device, luf_stream** out)
+{
+    if (!desc || !out) return fail(LUF_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (int rc = check_device()) return rc;
+    luf_stream* g = new (std::nothrow) luf_stream();
+    if (!g) return fail(LUF_ERR_INVALID, "out of host memory");
+    const std::string why = pack_window(*desc, g->host);
+    if (!why.empty()) {
+        delete g;
+        return fail(why.find("too large") != std::string::npos ? LUF_ERR_UNSUPPORTED : LUF_ERR_INVALID, why);
+    }
+    g->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete g; return fail(LUF_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+    cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&g->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    const PackedWindow& p = g->host;
+    SfView& v = g->view;
+    v.d = p.d; v.h = p.h; v.NLb = p.NLb; v.NLd = p.NLd; v.NL = p.NL; v.EL = p.EL; v.K = p.K;
+    v.ELw = words32(p.EL); v.WLn = words32(p.NL); v.N = p.NL * p.h; v.n_classes = p.n_classes;
+    int rc = 0;
+    if ((rc = upload_s(g, p.nbr, &v.nbr)) || (rc = upload_s(g, p.edge_ends, &v.edge_ends)) ||
+        (rc = upload_s(g, p.pos_long, &v.pos_long)) || (rc = upload_s(g, p.fresh_perm, &v.fresh_perm)) ||
+        (rc = upload_s(g, p.class_end, &v.class_end))) {
+        luf_stream_destroy(g);
+        return rc;
+    }
+    g->lay = make_sf_layout(p);
+    *out = g;
+    return 0;
+}
+
+int luf_stream_destroy(luf_stream* g)
+{
+    if (!g) return 0;
+    cudaSetDevice(g->device);
+    for (void* p : g->allocs) cudaFree(p);
+    for (void* p : g->scratch) if (p) cudaFree(p);
+    delete g;
+    return 0;
+}
+
+int64_t luf_stream_launch_count(const luf_stream* g) { return g ? g->launches : 0; }
+
+int luf_stream_decode(luf_stream* g, int flags, int64_t nstreams, int32_t ncycles, const uint32_t* fresh_bits_dev,
+                      int32_t* rt_dev, uint32_t* floor_bits_dev, int32_t* m_dev, void* stream)
+{
+    if (!g || !fresh_bits_dev || !rt_dev || !m_dev || nstreams < 0 || ncycles < 0)
+        return fail(LUF_ERR_INVALID, "luf_stream_decode: bad argument");
+    if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE)) return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
+    if (nstreams == 0 || ncycles == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    LaunchCfg c;
+    if (int rc = plan_stream_launch(g, k_sf_decode, nstreams, &c)) return rc;
+    k_sf_decode<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, flags, nstreams, ncycles,
+                                                                    fresh_bits_dev, rt_dev, floor_bits_dev, m_dev);
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
+int luf_stream_mc(luf_stream* g, int flags, const double* class_p_host, uint64_t seed, uint64_t stream0,
+                  int64_t nstreams, int32_t n, unsigned long long* counts_dev, int32_t* steps_dev, void* stream)
+{
+    if (!g || !class_p_host || !counts_dev || nstreams < 0) return fail(LUF_ERR_INVALID, "luf_stream_mc: bad argument");
+    if (n < 1) return fail(LUF_ERR_INVALID, "n must be positive integer.");
+    if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE)) return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
+    if (nstreams == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
+    LaunchCfg c;
+    if (int rc = plan_stream_launch(g, k_sf_mc, nstreams, &c)) return rc;
+    k_sf_mc<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, sp, flags, stream0, nstreams, n,
+                                                                counts_dev, steps_dev);
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
+int luf_stream_decode_host(luf_stream* g, int flags, int64_t nstreams, int32_t ncycles, const uint32_t* fresh_bits_host,
+                           int32_t* rt_host, uint32_t* floor_bits_host, int32_t* m_host)
+{
+    if (!g || !fresh_bits_host || !rt_host || !m_host || nstreams < 0 || ncycles < 0)
+        return fail(LUF_ERR_INVALID, "luf_stream_decode_host: bad argument");
+    if (nstreams == 0 || ncycles == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t rows = (size_t)nstreams * ncycles, W = g->view.ELw;
+    void *fr, *rt, *fl = nullptr, *mm;
+    int rc;
+    if ((rc = scratch_s(g, 0, rows * W * 4, &fr)) || (rc = scratch_s(g, 1, rows * 8, &rt)) ||
+        (rc = scratch_s(g, 2, rows * 4, &mm))) return rc;
+    if (floor_bits_host && (rc = scratch_s(g, 3, rows * W * 4, &fl))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(fr, fresh_bits_host, rows * W * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = luf_stream_decode(g, flags, nstreams, ncycles, (const uint32_t*)fr, (int32_t*)rt, (uint32_t*)fl,
+                                (int32_t*)mm, 0))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(rt_host, rt, rows * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(m_host, mm, rows * 4, cudaMemcpyDeviceToHost, 0));
+    if (fl) CUDA_TRY(cudaMemcpyAsync(floor_bits_host, fl, rows * W * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int luf_stream_mc_host(luf_stream* g, int flags, const double* class_p_host, uint64_t seed, uint64_t stream0,
+                       int64_t nstreams, int32_t n, unsigned long long counts_host[4], int32_t* steps_host)
+{
+    if (!g || !counts_host || nstreams < 0) return fail(LUF_ERR_INVALID, "luf_stream_mc_host: bad argument");
+    if (n < 1) return fail(LUF_ERR_INVALID, "n must be positive integer.");
+    if (nstreams == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    void *cnt, *st = nullptr;
+    int rc;
+    if ((rc = scratch_s(g, 4, 32, &cnt))) return rc;
+    if (steps_host && (rc = scratch_s(g, 1, (size_t)nstreams * n * 8, &st))) return rc;
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 32, 0));
+    if ((rc = luf_stream_mc(g, flags, class_p_host, seed, stream0, nstreams, n, (unsigned long long*)cnt,
+                            (int32_t*)st, 0))) return rc;
+    unsigned long long tmp[4];
+    if (st) CUDA_TRY(cudaMemcpyAsync(steps_host, st, (size_t)nstreams * n * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpy(tmp, cnt, 32, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) counts_host[i] += tmp[i];
+    return 0;
+}
 
 const char* luf_last_error(void) { return g_last_error.c_str(); }
 

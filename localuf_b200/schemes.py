@@ -302,10 +302,14 @@ class Frugal(_Streaming):
     def get_logical_error(self) -> int:
         return self._count_and_lower()
 
-    def run(self, decoder, noise_level: float, n: int, time_only='merging', **kwargs):
+    def run(self, decoder, noise_level: float, n: int, time_only='merging', shots: int = 1, **kwargs):
+        """``shots`` independent memory experiments of ``n*d`` timed decoding cycles each
+        (``_schemes.py:566-649``; the reference runs exactly one, ``shots=1``).  Returns
+        ``(logical errors, slenderness)`` summed over the experiments; ``step_counts`` gets
+        ``n`` entries per experiment."""
         if n < 1:
             raise ValueError("n must be positive integer.")
         self.reset()
-        m, steps = decoder._mc_frugal(noise_level, n, time_only=time_only, **kwargs)
+        m, steps = decoder._mc_frugal(noise_level, n, time_only=time_only, shots=shots, **kwargs)
         self.step_counts.extend(steps)
-        return m, math.ceil(self.WINDOW_HEIGHT / self._COMMIT_HEIGHT) / self._CODE.D + n + 1
+        return m, shots * (math.ceil(self.WINDOW_HEIGHT / self._COMMIT_HEIGHT) / self._CODE.D + n + 1)

@@ -80,3 +80,32 @@ class Emu:
                                  _vp(corr), _vp(growth), _vp(steps))
         assert rc == 0, rc
         return corr, growth, steps
+
+
+class EmuStream:
+    """Host emulation of the Snowflake / frugal kernel phases for one window."""
+
+    def __init__(self, code):
+        from localuf_b200 import _window
+        from localuf_b200._engine import make_window_desc
+        self.tables = _window.build(code)
+        self.noise = code.NOISE
+        self.desc, self._keep = make_window_desc(self.tables)
+        self.W = (self.tables.EL + 31) // 32
+
+    def stream(self, flags, fresh_local_bits):
+        fresh = np.ascontiguousarray(fresh_local_bits, dtype=np.uint32).reshape(-1, self.W)
+        n = fresh.shape[0]
+        rt = np.zeros((n, 2), np.int32); m = np.zeros(n, np.int32); floor = np.zeros((n, self.W), np.uint32)
+        rc = lib().emu_sf_stream(C.byref(self.desc), flags, n, _vp(fresh), _vp(rt), _vp(floor), _vp(m))
+        assert rc == 0, rc
+        return rt, floor, m
+
+    def mc(self, flags, noise_level, seed, stream0, nstreams, n):
+        cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
+        counts = (C.c_ulonglong * 4)(0, 0, 0, 0)
+        steps = np.zeros((nstreams, n, 2), np.int32)
+        rc = lib().emu_sf_mc(C.byref(self.desc), flags, _vp(cp), C.c_ulonglong(seed), C.c_ulonglong(stream0),
+                             C.c_longlong(nstreams), n, counts, _vp(steps))
+        assert rc == 0, rc
+        return [int(x) for x in counts], steps

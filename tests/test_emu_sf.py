@@ -1,0 +1,45 @@
+"""Snowflake / frugal kernel phases (localuf_b200/csrc/luf_sf.cuh compiled for
+the host) vs. goldens exported from the unmodified reference.  CPU-only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, make_code, golden_names
+
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
+import binding  # noqa: E402
+import emu_binding  # noqa: E402
+
+
+def flags_of(kw):
+    return (1 if kw.get('merger') == 'slow' else 0) | (2 if kw.get('schedule') == '1:1' else 0)
+
+
+@pytest.mark.parametrize('name', golden_names('sf_'))
+def test_emu_sf_matches_reference(name):
+    meta, arr = load_golden(name)
+    code = make_code(meta['spec'])
+    emu = emu_binding.EmuStream(code)
+    t = emu.tables
+    fresh = binding.code_bits_to_local(t, arr['fresh_bits'], 0)
+    rt, floor, m = emu.stream(flags_of(meta['decoder_kwargs']), fresh)
+    np.testing.assert_array_equal(rt[:, 0], arr['runtime_all'], err_msg=f'{name} runtime (all)')
+    np.testing.assert_array_equal(rt[:, 1], arr['runtime_unrooting'], err_msg=f'{name} runtime (unrooting)')
+    np.testing.assert_array_equal(floor, binding.code_bits_to_local(t, arr['floor_bits'], t.h - 1))
+    np.testing.assert_array_equal(m, arr['m_cycle'])
+
+
+def test_emu_sf_mc_runs_and_is_quiet_without_noise():
+    code = make_code(dict(code='Surface', d=3, noise='circuit-level', kwargs=dict(scheme='frugal')))
+    emu = emu_binding.EmuStream(code)
+    h, d, n = emu.tables.h, 3, 2
+    counts, steps = emu.mc(0, 0.0, 5, 0, 3, n)
+    total = h + n * d + d + 2 * h
+    assert counts[0] == 0 and counts[1] == 3 * total
+    assert counts[2] == 3 * n * d * 4 and counts[3] == 0       # idle cycle: runtime 'all' = 2 loops x (1 + 1)
+    assert (steps[:, :, 0] == 4 * d).all()
+    counts, _ = emu.mc(0, 0.02, 5, 0, 40, n)
+    assert counts[1] == 40 * total and counts[2] > 40 * n * d * 4
