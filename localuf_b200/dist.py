@@ -34,8 +34,10 @@ def allreduce_counts(values, device=None):
         return [int(v) for v in values]
     import torch
     import torch.distributed as dist
-    backend = dist.get_backend()
-    dev = device if (device is not None and backend == 'nccl') else 'cpu'
+    if dist.get_backend() == 'nccl':        # NCCL reduces device tensors only
+        dev = device if device is not None else f'cuda:{torch.cuda.current_device()}'
+    else:
+        dev = 'cpu'
     t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [int(v) for v in t.cpu().tolist()]
