@@ -163,3 +163,52 @@ def build(code, neighbor_order=None) -> WindowTables:
                         edge_q=edge_q, edge_dt=edge_dt, edge_class=edge_class, edge_fb=edge_fb,
                         pos_long=pos_long, code_edge=code_edge, layered_of_code=layered_of_code,
                         n_classes=len(classes))
+
+
+# ---------------------------------------------------------------------------
+@dataclass
+class ForwardTables:
+    """Window bookkeeping of the forward scheme (``_schemes.py:282-450``) over
+    the flat graph of the same code: edge / node indices are those of
+    :class:`localuf_b200._graph.FlatGraph`."""
+    c: int                       # commit height
+    b: int                       # buffer height
+    n_cleanse: int               # h // c noiseless cycles at the end
+    lower_edge: np.ndarray       # int32[E]   edge lowered by c layers (-1 if it leaves the window)
+    commit_mask: np.ndarray      # uint32[W(E)]  edges of the commit region
+    art_node: np.ndarray         # int32[E, 2]  per endpoint: the detector it makes artificial after the commit
+                                 #              (endpoint on layer t == c, lowered to t == 0), else -1
+    edge_fb: np.ndarray          # uint8[E]   edge touches the future boundary t == h
+    node_lower: np.ndarray       # int32[N]   node lowered by c layers (-1 if it leaves the window)
+    node_side: np.ndarray        # uint8[N]   1 west boundary, 2 east boundary, 0 otherwise
+
+
+def build_forward(code) -> ForwardTables:
+    scheme = code.SCHEME
+    flat = code.FLAT
+    c, b = scheme._COMMIT_HEIGHT, scheme._BUFFER_HEIGHT
+    h, ta, a, d = c + b, code.TIME_AXIS, code.LONG_AXIS, code.D
+    E, N = flat.n_edges, flat.n_nodes
+    lower_edge = np.full(E, -1, np.int32)
+    art_node = np.full((E, 2), -1, np.int32)
+    edge_fb = np.zeros(E, np.uint8)
+    commit = set(scheme._COMMIT_EDGES)
+    commit_idx = []
+    for k, e in enumerate(flat.edges):
+        low = code.raise_edge(e, -c)
+        lower_edge[k] = flat.edge_index.get(low, -1)
+        edge_fb[k] = 1 if any(v[ta] == h for v in e) else 0
+        if e in commit:
+            commit_idx.append(k)
+            for x, v in enumerate(e):
+                if v[ta] == c and not code.is_boundary(v):
+                    art_node[k, x] = flat.node_index[code.raise_node(v, -c)]
+    from localuf_b200._graph import pack_bits
+    node_lower = np.full(N, -1, np.int32)
+    node_side = np.zeros(N, np.uint8)
+    for k, v in enumerate(flat.nodes):
+        node_lower[k] = flat.node_index.get(code.raise_node(v, -c), -1)
+        node_side[k] = 1 if v[a] == -1 else 2 if v[a] == d - 1 else 0
+    return ForwardTables(c=c, b=b, n_cleanse=h // c, lower_edge=lower_edge,
+                         commit_mask=pack_bits(commit_idx, E), art_node=art_node, edge_fb=edge_fb,
+                         node_lower=node_lower, node_side=node_side)

@@ -54,6 +54,43 @@ def lib():
     return _lib
 
 
+class OracleForward(C.Structure):
+    _fields_ = [('c', C.c_int32), ('lower_edge', C.c_void_p), ('commit_mask', C.c_void_p), ('art_node', C.c_void_p),
+                ('node_lower', C.c_void_p), ('node_side', C.c_void_p)]
+
+
+class ForwardOracle:
+    """Forward-scheme oracle bound to one code (flat graph + localuf_b200._window.ForwardTables)."""
+
+    def __init__(self, code, tables):
+        self.orc = Oracle.from_code(code)
+        self.t = tables
+        self._keep = {}
+        f = OracleForward()
+        f.c = tables.c
+        for name, dt in (('lower_edge', np.int32), ('commit_mask', np.uint32), ('art_node', np.int32),
+                         ('node_lower', np.int32), ('node_side', np.uint8)):
+            a = np.ascontiguousarray(getattr(tables, name), dtype=dt)
+            self._keep[name] = a
+            setattr(f, name, a.ctypes.data)
+        self.f = f
+
+    def stream(self, decoder, flags, init_bits, fresh_bits):
+        WE = self.orc.WE
+        fresh = np.ascontiguousarray(fresh_bits, dtype=np.uint32).reshape(-1, WE)
+        init = np.ascontiguousarray(init_bits, dtype=np.uint32).reshape(WE)
+        n = fresh.shape[0]
+        steps = np.zeros((n, 2), np.int32); commit = np.zeros((n, WE), np.uint32); m = np.zeros(n, np.int32)
+        lib().oracle_forward_stream.restype = C.c_int
+        rc = lib().oracle_forward_stream(C.byref(self.orc.g), C.byref(self.f), decoder, flags, C.c_int32(n),
+                                         C.c_void_p(init.ctypes.data), C.c_void_p(fresh.ctypes.data),
+                                         C.c_void_p(steps.ctypes.data), C.c_void_p(commit.ctypes.data),
+                                         C.c_void_p(m.ctypes.data))
+        if rc != 0:
+            raise RuntimeError('oracle_forward_stream failed')
+        return steps, commit, m
+
+
 class OracleWindow(C.Structure):
     _fields_ = [
         ('d', C.c_int32), ('h', C.c_int32), ('NLb', C.c_int32), ('NLd', C.c_int32), ('EL', C.c_int32), ('K', C.c_int32),

@@ -231,7 +231,7 @@ def main():
     jobs = {'graphs': lambda: graph_cases()}
     for case in UF_CASES:
         jobs[case[0]] = (lambda c=case: uf_case(*c))
-    for extra in ('gen_golden_ca', 'gen_golden_sf'):
+    for extra in ('gen_golden_ca', 'gen_golden_sf', 'gen_golden_fw'):
         try:
             jobs.update(__import__(extra).jobs())
         except ImportError:

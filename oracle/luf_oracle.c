@@ -320,3 +320,91 @@ int64_t oracle_mc_batch(const oracle_graph *g, int decoder, int flags, const dou
     free(jobs); free(th);
     return bad ? -1 : total;
 }
+
+/* ---------------------------------------------------------- forward scheme */
+#define FP_NONE (-1)
+#define FP_WEST (-2)
+#define FP_EAST (-3)
+#define FP_DEAD (-4)
+
+static int fw_key(const oracle_forward *f, int v)
+{
+    return f->node_side[v] == 1 ? FP_WEST : f->node_side[v] == 2 ? FP_EAST : v;
+}
+static void fw_add(int32_t *partner, int a, int b, int *count)
+{
+    if (a >= 0) partner[a] = b;
+    if (b >= 0) partner[b] = a;
+    if ((a == FP_WEST && b == FP_EAST) || (a == FP_EAST && b == FP_WEST)) ++*count;   /* _pairs.py:103-105 */
+}
+static int fw_take(int32_t *partner, int u)
+{
+    const int w = partner[u];
+    partner[u] = FP_NONE;
+    if (w >= 0) partner[w] = FP_NONE;
+    return w;
+}
+/* Pairs.load, _pairs.py:49-66 */
+static void fw_load(int32_t *partner, int u, int v, int *count)
+{
+    if (u >= 0 && partner[u] != FP_NONE) {
+        const int w = fw_take(partner, u);
+        if (v >= 0 && partner[v] != FP_NONE) fw_add(partner, w, fw_take(partner, v), count);
+        else if (v != w || v < 0) fw_add(partner, v, w, count);
+    } else if (v >= 0 && partner[v] != FP_NONE)
+        fw_add(partner, u, fw_take(partner, v), count);
+    else
+        fw_add(partner, u, v, count);
+}
+
+int oracle_forward_stream(const oracle_graph *g, const oracle_forward *f, int decoder, int flags, int32_t ncycles,
+                          const uint32_t *init_buffer_bits, const uint32_t *fresh_bits,
+                          int32_t *steps, uint32_t *commit_bits, int32_t *m_cycle)
+{
+    const int N = g->n_nodes, B = g->n_boundary, E = g->n_edges, WE = WORDS(E), WD = WORDS(N - B);
+    uint32_t *error = calloc(WE, 4), *buffer = calloc(WE, 4), *commit = calloc(WE, 4), *corr = calloc(WE, 4);
+    uint32_t *syn = calloc(WD ? WD : 1, 4);
+    int32_t *partner = malloc(4 * N), *np2 = malloc(4 * N);
+    for (int v = 0; v < N; ++v) partner[v] = FP_NONE;
+    memcpy(buffer, init_buffer_bits, 4 * WE);
+    int rc = 0;
+    for (int c = 0; c < ncycles && !rc; ++c) {
+        /* Forward._make_error (:302-324): lower the buffer leftover by the commit height, add the fresh sheet */
+        memcpy(error, fresh_bits + (size_t)c * WE, 4 * WE);
+        for (int e = 0; e < E; ++e)
+            if (GETBIT(buffer, e) && f->lower_edge[e] >= 0) error[f->lower_edge[e] >> 5] |= 1u << (f->lower_edge[e] & 31);
+        /* syndrome xor artificial defects of the previous commit (:351-368) */
+        oracle_syndrome(g, error, syn);
+        for (int e = 0; e < E; ++e)
+            if (GETBIT(commit, e))
+                for (int x = 0; x < 2; ++x) {
+                    const int a = f->art_node[2 * e + x];
+                    if (a >= 0) FLIPBIT(syn, a - B);
+                }
+        /* decoder.reset(); decoder.decode(syndrome) (:440-441) */
+        rc = oracle_decode_batch(g, decoder, flags, 1, syn, corr, NULL, steps + 2 * c);
+        /* Forward._get_leftover (:326-339) */
+        for (int w = 0; w < WE; ++w) {
+            commit[w] = (error[w] ^ corr[w]) & f->commit_mask[w];
+            buffer[w] = error[w] & ~f->commit_mask[w];
+        }
+        memcpy(commit_bits + (size_t)c * WE, commit, 4 * WE);
+        /* Forward.get_logical_error (:341-349), ascending edge id */
+        int count = 0;
+        for (int e = 0; e < E; ++e)
+            if (GETBIT(commit, e)) fw_load(partner, fw_key(f, g->edge_u[e]), fw_key(f, g->edge_v[e]), &count);
+        m_cycle[c] = count;
+        /* LogicalCounter.count's lowering (_pairs.py:82-111) */
+        for (int v = 0; v < N; ++v) np2[v] = FP_NONE;
+        for (int v = 0; v < N; ++v) {
+            const int p = partner[v];
+            if (p == FP_NONE) continue;
+            const int lv = f->node_lower[v];
+            if (lv < 0) continue;                               /* this end is out of reach now */
+            np2[lv] = p >= 0 ? (f->node_lower[p] >= 0 ? f->node_lower[p] : FP_DEAD) : p;
+        }
+        memcpy(partner, np2, 4 * N);
+    }
+    free(error); free(buffer); free(commit); free(corr); free(syn); free(partner); free(np2);
+    return rc;
+}

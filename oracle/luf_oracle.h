@@ -75,6 +75,24 @@ int oracle_decode_batch(const oracle_graph *g, int decoder, int flags, int64_t n
 int64_t oracle_mc_batch(const oracle_graph *g, int decoder, int flags, const double *class_p,
                         uint64_t seed, int64_t nshots, int nthreads);
 
+/* ---- forward scheme (localuf/_schemes.py:282-450) on the flat window graph ---- */
+typedef struct {
+    int32_t c;                      /* commit height */
+    const int32_t *lower_edge;      /* [E] edge lowered by c layers, -1 if it leaves the window */
+    const uint32_t *commit_mask;    /* [W(E)] */
+    const int32_t *art_node;        /* [E*2] detector made artificial by an endpoint on layer c, else -1 */
+    const int32_t *node_lower;      /* [N] node lowered by c layers, -1 if it leaves the window */
+    const uint8_t *node_side;       /* [N] 1 west, 2 east, 0 otherwise */
+} oracle_forward;
+
+/* ncycles forward-decoding cycles with the fresh errors GIVEN (bits over code edge
+ * ids): init_buffer_bits = the buffer-region error before the first cycle
+ * (_schemes.py:370-390).  Per cycle: decoder steps (UF: rounds, 0; Macar: tSV, tBP),
+ * the commit-region leftover, and the logical errors counted. */
+int oracle_forward_stream(const oracle_graph *g, const oracle_forward *f, int decoder, int flags, int32_t ncycles,
+                          const uint32_t *init_buffer_bits, const uint32_t *fresh_bits,
+                          int32_t *steps, uint32_t *commit_bits, int32_t *m_cycle);
+
 /* ---- streaming: Snowflake under the frugal scheme -------------------------
  * Layered window tables (see localuf_b200/_window.py for the conventions):
  * node (q, t) -> Snowflake id; edge (block tmin, local l) -> (h-1-tmin)*EL + l. */
