@@ -148,6 +148,51 @@ int luf_check_host(luf_graph *g, int64_t nshots, const uint32_t *err_bits_host,
                    const uint32_t *corr_bits_host, uint8_t *logical_host,
                    unsigned long long *fail_count_host);
 
+/* ---- forward scheme (UF / Macar on a sliding window) ------------------------
+ * Window bookkeeping tables over the flat graph of a forward-scheme code;
+ * replaces Forward._make_error / _get_artificial_defects / _get_leftover /
+ * get_logical_error (localuf/_schemes.py:302-368) and Pairs / LogicalCounter
+ * (localuf/_pairs.py). */
+typedef struct {
+    int32_t commit_height;        /* c */
+    int32_t n_cleanse;            /* h // c noiseless cycles that end a run */
+    const int32_t *lower_edge;    /* [E] edge lowered by c layers, -1 if it leaves the window */
+    const uint32_t *commit_mask;  /* [W(E)] edges of the commit region */
+    const int32_t *art_node;      /* [E*2] per endpoint: detector made artificial after the commit, else -1 */
+    const uint8_t *edge_fb;       /* [E] edge touches the future boundary */
+    const int32_t *node_lower;    /* [N] node lowered by c layers, -1 if it leaves the window */
+    const uint8_t *node_side;     /* [N] 1 west boundary, 2 east boundary, 0 otherwise */
+    const uint8_t *buffer_class;  /* [E] probability class of a buffer-region edge, 255 in the commit region */
+} luf_forward_desc;
+
+/* Attach forward-scheme tables to a graph created from a forward-scheme code. */
+int luf_forward_attach(luf_graph *g, const luf_forward_desc *desc);
+
+/* Parity path -- ncycles cycles of Forward.run's loop body (localuf/_schemes.py:433-447)
+ * for nstreams independent windows with the fresh errors GIVEN as bits over code
+ * edge ids: init_buffer_dev [nstreams][W(E)] (buffer-region error before the first
+ * cycle), fresh_bits_dev [nstreams][ncycles][W(E)].  decoder = LUF_DEC_UF or
+ * LUF_DEC_MACAR.  Outputs: steps_dev [nstreams][ncycles][2] (decoder.decode's
+ * return value: UF (rounds, 0), Macar (tSV, tBP)); commit_bits_dev (optional)
+ * [nstreams][ncycles][W(E)] the commit-region leftover; m_dev [nstreams][ncycles]. */
+int luf_forward_decode(luf_graph *g, int decoder, int flags, int64_t nstreams, int32_t ncycles,
+                       const uint32_t *init_buffer_dev, const uint32_t *fresh_bits_dev, int32_t *steps_dev,
+                       uint32_t *commit_bits_dev, int32_t *m_dev, void *stream);
+
+/* Fused -- replaces Forward.run(decoder, p, n) (localuf/_schemes.py:392-450) for
+ * nstreams independent runs: counts_dev uint64[4]: [0] += logical errors,
+ * [1] += decoding cycles, [2] / [3] += the two step counts summed over the n timed
+ * cycles; steps_dev (optional) [nstreams][n][2] = Forward.step_counts. */
+int luf_forward_mc(luf_graph *g, int decoder, int flags, const double *class_p_host, uint64_t seed,
+                   uint64_t stream0, int64_t nstreams, int32_t n, unsigned long long *counts_dev,
+                   int32_t *steps_dev, void *stream);
+int luf_forward_decode_host(luf_graph *g, int decoder, int flags, int64_t nstreams, int32_t ncycles,
+                            const uint32_t *init_buffer_host, const uint32_t *fresh_bits_host, int32_t *steps_host,
+                            uint32_t *commit_bits_host, int32_t *m_host);
+int luf_forward_mc_host(luf_graph *g, int decoder, int flags, const double *class_p_host, uint64_t seed,
+                        uint64_t stream0, int64_t nstreams, int32_t n, unsigned long long counts_host[4],
+                        int32_t *steps_host);
+
 /* ---- streaming: Snowflake under the frugal scheme ---------------------------
  * Layered tables of one sliding window (localuf_b200/_window.py): node (q, t),
  * edge (block tmin, local l).  Replaces the per-node / per-edge Python objects

@@ -67,6 +67,27 @@ def make_desc(flat, noise_kind: int):
     return d, keep
 
 
+class ForwardDesc(C.Structure):
+    """``luf_forward_desc`` of include/luf_b200.h."""
+    _fields_ = [('commit_height', C.c_int32), ('n_cleanse', C.c_int32), ('lower_edge', C.c_void_p),
+                ('commit_mask', C.c_void_p), ('art_node', C.c_void_p), ('edge_fb', C.c_void_p),
+                ('node_lower', C.c_void_p), ('node_side', C.c_void_p), ('buffer_class', C.c_void_p)]
+
+
+def make_forward_desc(t):
+    """Return ``(ForwardDesc, keepalive)`` for a :class:`localuf_b200._window.ForwardTables`."""
+    keep = {}
+    d = ForwardDesc()
+    d.commit_height, d.n_cleanse = t.c, t.n_cleanse
+    for name, dt in (('lower_edge', np.int32), ('commit_mask', np.uint32), ('art_node', np.int32),
+                     ('edge_fb', np.uint8), ('node_lower', np.int32), ('node_side', np.uint8),
+                     ('buffer_class', np.uint8)):
+        a = np.ascontiguousarray(getattr(t, name), dtype=dt)
+        keep[name] = a
+        setattr(d, name, a.ctypes.data)
+    return d, keep
+
+
 class WindowDesc(C.Structure):
     """``luf_window_desc`` of include/luf_b200.h."""
     _fields_ = [
@@ -124,6 +145,11 @@ def _load():
         lib.luf_decode_batch_host.argtypes = [v, C.c_int, C.c_int, i64, v, v, v, v]
         lib.luf_sample_host.argtypes = [v, v, u64, u64, i64, v, v]
         lib.luf_check_host.argtypes = [v, i64, v, v, v, v]
+        lib.luf_forward_attach.argtypes = [v, C.POINTER(ForwardDesc)]
+        lib.luf_forward_decode_host.argtypes = [v, C.c_int, C.c_int, i64, C.c_int32, v, v, v, v, v]
+        lib.luf_forward_mc_host.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, C.c_int32, v, v]
+        lib.luf_forward_decode.argtypes = [v, C.c_int, C.c_int, i64, C.c_int32, v, v, v, v, v, v]
+        lib.luf_forward_mc.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, C.c_int32, v, v, v]
         lib.luf_stream_create.argtypes = [C.POINTER(WindowDesc), C.c_int, C.POINTER(C.c_void_p)]
         lib.luf_stream_destroy.argtypes = [v]
         lib.luf_stream_launch_count.restype = C.c_int64
@@ -177,6 +203,7 @@ class Engine:
         if device is None:
             device = int(os.environ.get('LOCAL_RANK', 0)) % lib.luf_device_count()
         self.device = device
+        self._code = code
         self.flat = code.FLAT
         self.noise = code.NOISE
         desc, self._keep = make_desc(self.flat, NOISE_KIND[str(code.NOISE)])
@@ -252,6 +279,39 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(_load().luf_launch_count(self._h))
+
+    # ------------------------------------------------------- forward scheme
+    def attach_forward(self, tables=None):
+        """Upload the forward-scheme bookkeeping tables (once)."""
+        if getattr(self, 'forward_tables', None) is None:
+            from localuf_b200 import _window
+            self.forward_tables = tables if tables is not None else _window.build_forward(self._code)
+            desc, self._keep_fw = make_forward_desc(self.forward_tables)
+            _check(_load().luf_forward_attach(self._h, C.byref(desc)))
+        return self.forward_tables
+
+    def forward_decode_host(self, decoder: int, flags: int, init_bits, fresh_bits, want_commit=True):
+        """init_bits [ns, WE], fresh_bits [ns, nc, WE] -> (steps [ns, nc, 2], commit [ns, nc, WE] | None, m [ns, nc])."""
+        self.attach_forward()
+        fresh = np.ascontiguousarray(fresh_bits, dtype=np.uint32)
+        init = np.ascontiguousarray(init_bits, dtype=np.uint32).reshape(fresh.shape[0], self.WE)
+        ns, nc = fresh.shape[0], fresh.shape[1]
+        steps = np.zeros((ns, nc, 2), np.int32)
+        m = np.zeros((ns, nc), np.int32)
+        commit = np.zeros((ns, nc, self.WE), np.uint32) if want_commit else None
+        _check(_load().luf_forward_decode_host(self._h, decoder, flags, ns, nc, _ptr(init), _ptr(fresh),
+                                               _ptr(steps), _ptr(commit), _ptr(m)))
+        return steps, commit, m
+
+    def forward_mc_host(self, decoder: int, flags: int, noise_level: float, seed: int, stream0: int,
+                        nstreams: int, n: int, want_steps=False):
+        self.attach_forward()
+        cp = self.class_p(noise_level)
+        counts = (C.c_ulonglong * 4)(0, 0, 0, 0)
+        steps = np.zeros((nstreams, n, 2), np.int32) if want_steps else None
+        _check(_load().luf_forward_mc_host(self._h, decoder, flags, cp.ctypes.data, seed, stream0, nstreams, n,
+                                           counts, _ptr(steps)))
+        return [int(x) for x in counts], steps
 
 
 class StreamEngine:

@@ -181,6 +181,7 @@ class ForwardTables:
     edge_fb: np.ndarray          # uint8[E]   edge touches the future boundary t == h
     node_lower: np.ndarray       # int32[N]   node lowered by c layers (-1 if it leaves the window)
     node_side: np.ndarray        # uint8[N]   1 west boundary, 2 east boundary, 0 otherwise
+    buffer_class: np.ndarray     # uint8[E]   probability class of a buffer-region edge (its fresh translate's), 255 in the commit region
 
 
 def build_forward(code) -> ForwardTables:
@@ -204,6 +205,14 @@ def build_forward(code) -> ForwardTables:
                 if v[ta] == c and not code.is_boundary(v):
                     art_node[k, x] = flat.node_index[code.raise_node(v, -c)]
     from localuf_b200._graph import pack_bits
+    buffer_class = np.full(E, 255, np.uint8)
+    for k, e in enumerate(flat.edges):
+        if e in commit:
+            continue
+        up = e
+        while flat.edge_class[flat.edge_index[up]] == 255:      # translate upwards into the fresh sheet
+            up = code.raise_edge(up, c)
+        buffer_class[k] = flat.edge_class[flat.edge_index[up]]
     node_lower = np.full(N, -1, np.int32)
     node_side = np.zeros(N, np.uint8)
     for k, v in enumerate(flat.nodes):
@@ -211,4 +220,4 @@ def build_forward(code) -> ForwardTables:
         node_side[k] = 1 if v[a] == -1 else 2 if v[a] == d - 1 else 0
     return ForwardTables(c=c, b=b, n_cleanse=h // c, lower_edge=lower_edge,
                          commit_mask=pack_bits(commit_idx, E), art_node=art_node, edge_fb=edge_fb,
-                         node_lower=node_lower, node_side=node_side)
+                         node_lower=node_lower, node_side=node_side, buffer_class=buffer_class)

@@ -23,6 +23,7 @@
 #if defined(LUF_HOST_EMU)
   #include <math.h>
   #define LUF_DEV static inline
+  #define LUF_MEM inline
   static inline uint32_t luf_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
   static inline uint32_t luf_atomic_sub(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o - v; return o; }
   static inline uint32_t luf_atomic_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
@@ -42,6 +43,7 @@
   static inline uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 #else
   #define LUF_DEV __device__ __forceinline__
+  #define LUF_MEM __device__ __forceinline__
   LUF_DEV uint32_t luf_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
   LUF_DEV uint32_t luf_atomic_sub(uint32_t* p, uint32_t v) { return atomicSub(p, v); }
   LUF_DEV uint32_t luf_atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
@@ -219,24 +221,35 @@ LUF_DEV uint32_t flip_edge(const GraphView& g, const Shot& s, uint32_t e)
     return (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
 }
 
-// Each lane owns a contiguous range of the class-sorted fresh-edge list and
-// walks it with geometric skips: the gap to the next flipped edge of a class
-// with flip probability p is floor(log(U)/log(1-p)).  Same distribution as the
+// A list of edges sorted by probability class (the freshly exposed edges of a
+// shot / cycle, or the buffer region of a forward window).
+struct SampleTab {
+    int F, n_classes;
+    const uint16_t* perm;       // [F]
+    const uint32_t* class_end;  // [n_classes]
+};
+
+// Each lane owns a contiguous range of the class-sorted edge list and walks it
+// with geometric skips: the gap to the next flipped edge of a class with flip
+// probability p is floor(log(U)/log(1-p)).  Same distribution as the
 // reference's one Bernoulli draw per edge, ~p*F + classes draws per lane
-// instead of F/NL.  Returns this lane's parity of flipped west-boundary edges.
-LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams& sp,
-                           uint64_t shot, int lane, int nl)
+// instead of F/NL.  `cycle` decorrelates the sheets of a streaming window;
+// edges whose bit is set in `skip_mask` (optional) are never flipped
+// (exclude_future_boundary, _base_classes.py:418-424).  Returns this lane's
+// parity of flipped west-boundary edges.
+LUF_DEV uint32_t ph_sample_tab(const GraphView& g, const SampleTab& t, const Shot& s, const SampleParams& sp,
+                               uint64_t shot, uint32_t cycle, const uint32_t* skip_mask, int lane, int nl)
 {
-    const uint32_t a = (uint32_t)(((uint64_t)g.F * (uint32_t)lane) / (uint32_t)nl);
-    const uint32_t b = (uint32_t)(((uint64_t)g.F * (uint32_t)(lane + 1)) / (uint32_t)nl);
+    const uint32_t a = (uint32_t)(((uint64_t)t.F * (uint32_t)lane) / (uint32_t)nl);
+    const uint32_t b = (uint32_t)(((uint64_t)t.F * (uint32_t)(lane + 1)) / (uint32_t)nl);
     if (a >= b) return 0;
     Philox rng;
-    rng.c0 = (uint32_t)shot; rng.c1 = (uint32_t)(shot >> 32); rng.c2 = (uint32_t)lane; rng.c3 = 0;
+    rng.c0 = (uint32_t)shot; rng.c1 = (uint32_t)(shot >> 32); rng.c2 = (uint32_t)lane; rng.c3 = cycle << 6;
     rng.k0 = sp.key0; rng.k1 = sp.key1; rng.have = 0;
     rng.o0 = rng.o1 = rng.o2 = rng.o3 = 0;
     uint32_t parity = 0, start = 0;
-    for (int c = 0; c < g.n_classes; ++c) {
-        const uint32_t end = LUF_LDG(&g.class_end[c]);
+    for (int c = 0; c < t.n_classes; ++c) {
+        const uint32_t end = LUF_LDG(&t.class_end[c]);
         const uint32_t lo = a > start ? a : start, hi = b < end ? b : end;
         start = end;
         if (lo >= hi) { if (end >= b) break; continue; }
@@ -251,11 +264,20 @@ LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams
                 if (gap >= hi - pos) break;
                 pos += gap;
             }
-            parity ^= flip_edge(g, s, LUF_LDG(&g.fresh_perm[pos]));
+            const uint32_t e = LUF_LDG(&t.perm[pos]);
+            if (!skip_mask || !((LUF_LDG(&skip_mask[e >> 5]) >> (e & 31u)) & 1u)) parity ^= flip_edge(g, s, e);
             if (++pos >= hi) break;
         }
     }
     return parity;
+}
+
+LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams& sp,
+                           uint64_t shot, int lane, int nl)
+{
+    SampleTab t;
+    t.F = g.F; t.n_classes = g.n_classes; t.perm = g.fresh_perm; t.class_end = g.class_end;
+    return ph_sample_tab(g, t, s, sp, shot, 0u, (const uint32_t*)0, lane, nl);
 }
 
 // uf.py:98-104 load: every defect is an odd, active singleton cluster.

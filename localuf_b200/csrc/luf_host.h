@@ -13,10 +13,13 @@
 #include "luf_core.cuh"
 #include "luf_ca.cuh"
 #include "luf_sf.cuh"
+#include "luf_fw.cuh"
 
 namespace luf {
 
 inline int words32(int nbits) { return (nbits + 31) / 32; }
+
+struct luf_graph_desc_dims { int N, B, E, n_classes; };
 
 struct PackedGraph {
     int N = 0, B = 0, E = 0, F = 0, n_classes = 0;
@@ -164,6 +167,58 @@ inline CaLayout make_ca_layout(int N, int B, int E, bool actis, bool keep_err)
     l.corr = take(4u * WE);
     l.glob = take(16);
     l.err = keep_err ? take(4u * WE) : 0;
+    l.bytes = off;
+    return l;
+}
+
+// ------------------------------------------------------------ forward scheme
+struct PackedForward {
+    int c = 0, n_cleanse = 0, n_buffer = 0;
+    std::vector<uint16_t> lower_edge, art_node, node_lower, buffer_perm;
+    std::vector<uint32_t> commit_mask, fb_mask, buffer_class_end;
+    std::vector<uint8_t> node_side;
+};
+
+inline std::string pack_forward(const luf_graph_desc_dims& dims, const luf_forward_desc& d, PackedForward& out)
+{
+    const int N = dims.N, E = dims.E, B = dims.B, C = dims.n_classes;
+    if (d.commit_height < 1 || d.n_cleanse < 1) return "bad commit height";
+    out.c = d.commit_height; out.n_cleanse = d.n_cleanse;
+    out.lower_edge.assign(E, 0xFFFF); out.art_node.assign(2 * (size_t)E, 0xFFFF);
+    out.commit_mask.assign(d.commit_mask, d.commit_mask + words32(E));
+    out.fb_mask.assign(words32(E), 0);
+    for (int e = 0; e < E; ++e) {
+        if (d.lower_edge[e] >= E) return "lower_edge out of range";
+        if (d.lower_edge[e] >= 0) out.lower_edge[e] = (uint16_t)d.lower_edge[e];
+        for (int x = 0; x < 2; ++x) {
+            const int a = d.art_node[2 * e + x];
+            if (a >= N || (a >= 0 && a < B)) return "artificial defect must be a detector";
+            if (a >= 0) out.art_node[2 * e + x] = (uint16_t)a;
+        }
+        if (d.edge_fb[e]) out.fb_mask[e >> 5] |= 1u << (e & 31);
+    }
+    out.node_lower.assign(N, 0xFFFF); out.node_side.assign(d.node_side, d.node_side + N);
+    for (int v = 0; v < N; ++v) {
+        if (d.node_lower[v] >= N) return "node_lower out of range";
+        if (d.node_lower[v] >= 0) out.node_lower[v] = (uint16_t)d.node_lower[v];
+    }
+    out.buffer_class_end.assign(C, 0); out.buffer_perm.clear();
+    for (int c = 0; c < C; ++c) {
+        for (int e = 0; e < E; ++e)
+            if (d.buffer_class[e] == c) out.buffer_perm.push_back((uint16_t)e);
+        out.buffer_class_end[c] = (uint32_t)out.buffer_perm.size();
+    }
+    out.n_buffer = (int)out.buffer_perm.size();
+    return "";
+}
+
+inline FwLayout make_fw_layout(int N, int E, uint32_t base)
+{
+    FwLayout l;
+    uint32_t off = base;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
+    l.buf = take(4u * words32(E)); l.commit = take(4u * words32(E));
+    l.partner = take(2u * N); l.partner2 = take(2u * N);
     l.bytes = off;
     return l;
 }

@@ -153,6 +153,68 @@ __global__ void k_mc_ca(GraphView gv, CaView g, CaLayout l, SampleParams sp, int
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
 }
 
+// Forward scheme (_schemes.py:392-450) around UF (MACAR = false) or Macar.
+struct FwArgs {
+    GraphView gv; Layout ul; CaView cv; CaLayout cl; FwView fw; FwLayout fl; SampleTab buffer_tab;
+    int flags, n_cleanse;
+};
+
+template <bool MACAR, class F>
+__device__ __forceinline__ void fw_with_decoder(const FwArgs& a, unsigned char* slice, F&& body)
+{
+    if constexpr (MACAR) { FwMacar d{a.cv, ca_bind(a.cl, slice)}; body(d); }
+    else { FwUf d{a.gv, a.ul, bind(a.ul, slice), a.flags}; body(d); }
+}
+
+template <bool MACAR>
+__global__ void k_fw_decode(FwArgs a, long long nstreams, int ncycles, const uint32_t* __restrict__ init_buf,
+                            const uint32_t* __restrict__ fresh, int32_t* __restrict__ steps,
+                            uint32_t* __restrict__ commit_out, int32_t* __restrict__ m_out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    unsigned char* slice = smem + (size_t)(threadIdx.x >> 5) * a.fl.bytes;
+    const FwState f = fw_bind(a.fl, slice);
+    const long long stride = (long long)gridDim.x * wpb;
+    const int WE = a.fw.WE;
+    fw_with_decoder<MACAR>(a, slice, [&](auto& d) {
+        for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nstreams; k += stride) {
+            LUF_PHASE(fw_reset(a.fw, f, init_buf + (size_t)k * WE, lane, nl));
+            for (int c = 0; c < ncycles; ++c) {
+                const size_t row = (size_t)k * ncycles + c;
+                int s0 = 0, s1 = 0;
+                const int m = fw_cycle_given(a.fw, f, d, fresh + row * WE, commit_out ? commit_out + row * WE : nullptr,
+                                             s0, s1, lane, nl);
+                if (lane == 0) { steps[2 * row] = s0; steps[2 * row + 1] = s1; m_out[row] = m; }
+            }
+        }
+    });
+}
+
+template <bool MACAR>
+__global__ void k_fw_mc(FwArgs a, SampleParams sp, unsigned long long stream0, long long nstreams, int n,
+                        unsigned long long* counts, int32_t* steps)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    unsigned char* slice = smem + (size_t)(threadIdx.x >> 5) * a.fl.bytes;
+    const FwState f = fw_bind(a.fl, slice);
+    const long long stride = (long long)gridDim.x * wpb;
+    int m_total = 0;
+    long long cycles = 0, s0 = 0, s1 = 0;
+    fw_with_decoder<MACAR>(a, slice, [&](auto& d) {
+        for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nstreams; k += stride)
+            fw_run(a.gv, a.fw, f, d, a.buffer_tab, sp, stream0 + (unsigned long long)k, n, a.n_cleanse, m_total, cycles,
+                   s0, s1, steps ? steps + (size_t)k * n * 2 : nullptr, lane, nl);
+    });
+    if (lane == 0) {
+        atomicAdd(&counts[0], (unsigned long long)m_total); atomicAdd(&counts[1], (unsigned long long)cycles);
+        atomicAdd(&counts[2], (unsigned long long)s0); atomicAdd(&counts[3], (unsigned long long)s1);
+    }
+}
+
 // K3b parity path: Snowflake + frugal bookkeeping on GIVEN fresh errors.
 __global__ void k_sf_decode(SfView g, SfLayout l, int flags, long long nstreams, int ncycles,
                             const uint32_t* __restrict__ fresh, int32_t* __restrict__ rt,
@@ -247,6 +309,14 @@ struct luf_graph {
     std::string ca_why;           // why Macar/Actis cannot run on this graph ("" = they can)
     CaView ca_view{};
     CaLayout lay_macar{}, lay_actis{};
+    // forward scheme (luf_forward_attach)
+    bool has_forward = false;
+    PackedForward fw_host;
+    FwView fw_view{};
+    SampleTab fw_buffer_tab{};
+    Layout fw_lay_uf{};
+    CaLayout fw_lay_macar{};
+    FwLayout fw_ext_uf{}, fw_ext_macar{};
     // grow-only scratch for the *_host entry points
     void* scratch[6] = {0, 0, 0, 0, 0, 0};
     size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -708,6 +778,142 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
     }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;
+    return 0;
+}
+
+// ------------------------------------------------------------ forward scheme
+int luf_forward_attach(luf_graph* g, const luf_forward_desc* d)
+{
+    if (!g || !d) return fail(LUF_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    const luf_graph_desc_dims dims = {g->view.N, g->view.B, g->view.E, g->view.n_classes};
+    const std::string why = pack_forward(dims, *d, g->fw_host);
+    if (!why.empty()) return fail(LUF_ERR_INVALID, why);
+    const PackedForward& p = g->fw_host;
+    FwView& v = g->fw_view;
+    v.N = dims.N; v.B = dims.B; v.E = dims.E; v.WE = g->view.WE; v.WD = g->view.WD; v.c = p.c;
+    v.edge_uv = g->view.edge_uv;
+    int rc = 0;
+    if ((rc = upload(g, p.lower_edge, &v.lower_edge)) || (rc = upload(g, p.commit_mask, &v.commit_mask)) ||
+        (rc = upload(g, p.art_node, &v.art_node)) || (rc = upload(g, p.fb_mask, &v.fb_mask)) ||
+        (rc = upload(g, p.node_lower, &v.node_lower)) || (rc = upload(g, p.node_side, &v.node_side)) ||
+        (rc = upload(g, p.buffer_perm, &g->fw_buffer_tab.perm)) ||
+        (rc = upload(g, p.buffer_class_end, &g->fw_buffer_tab.class_end))) return rc;
+    g->fw_buffer_tab.F = p.n_buffer; g->fw_buffer_tab.n_classes = dims.n_classes;
+    g->fw_lay_uf = make_layout(dims.N, dims.B, dims.E, true, true);
+    g->fw_ext_uf = make_fw_layout(dims.N, dims.E, g->fw_lay_uf.bytes);
+    g->fw_lay_macar = make_ca_layout(dims.N, dims.B, dims.E, false, true);
+    g->fw_ext_macar = make_fw_layout(dims.N, dims.E, g->fw_lay_macar.bytes);
+    g->has_forward = true;
+    return 0;
+}
+
+static int fw_args(luf_graph* g, int decoder, int flags, FwArgs* a)
+{
+    if (!g->has_forward) return fail(LUF_ERR_INVALID, "luf_forward_attach was not called for this graph");
+    if (decoder != LUF_DEC_UF && decoder != LUF_DEC_MACAR)
+        return fail(LUF_ERR_UNSUPPORTED, "the forward scheme runs UF or Macar (decoders/uf.py:48-49, luf/__init__.py:22-23)");
+    if (int rc = check_decoder(g, decoder, flags)) return rc;
+    a->gv = g->view; a->ul = g->fw_lay_uf; a->cv = g->ca_view; a->cl = g->fw_lay_macar; a->fw = g->fw_view;
+    a->fl = decoder == LUF_DEC_MACAR ? g->fw_ext_macar : g->fw_ext_uf;
+    a->buffer_tab = g->fw_buffer_tab; a->flags = flags; a->n_cleanse = g->fw_host.n_cleanse;
+    return 0;
+}
+
+int luf_forward_decode(luf_graph* g, int decoder, int flags, int64_t nstreams, int32_t ncycles,
+                       const uint32_t* init_buffer_dev, const uint32_t* fresh_bits_dev, int32_t* steps_dev,
+                       uint32_t* commit_bits_dev, int32_t* m_dev, void* stream)
+{
+    if (!g || !init_buffer_dev || !fresh_bits_dev || !steps_dev || !m_dev || nstreams < 0 || ncycles < 0)
+        return fail(LUF_ERR_INVALID, "luf_forward_decode: bad argument");
+    FwArgs a;
+    if (int rc = fw_args(g, decoder, flags, &a)) return rc;
+    if (nstreams == 0 || ncycles == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    LaunchCfg c;
+    if (decoder == LUF_DEC_MACAR) {
+        if (int rc = plan_launch(g, k_fw_decode<true>, a.fl.bytes, nstreams, &c)) return rc;
+        k_fw_decode<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(a, nstreams, ncycles, init_buffer_dev,
+                                                                           fresh_bits_dev, steps_dev, commit_bits_dev, m_dev);
+    } else {
+        if (int rc = plan_launch(g, k_fw_decode<false>, a.fl.bytes, nstreams, &c)) return rc;
+        k_fw_decode<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(a, nstreams, ncycles, init_buffer_dev,
+                                                                            fresh_bits_dev, steps_dev, commit_bits_dev, m_dev);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
+int luf_forward_mc(luf_graph* g, int decoder, int flags, const double* class_p_host, uint64_t seed, uint64_t stream0,
+                   int64_t nstreams, int32_t n, unsigned long long* counts_dev, int32_t* steps_dev, void* stream)
+{
+    if (!g || !class_p_host || !counts_dev || nstreams < 0) return fail(LUF_ERR_INVALID, "luf_forward_mc: bad argument");
+    if (n < 1) return fail(LUF_ERR_INVALID, "n must be positive integer.");
+    FwArgs a;
+    if (int rc = fw_args(g, decoder, flags, &a)) return rc;
+    if (nstreams == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
+    LaunchCfg c;
+    if (decoder == LUF_DEC_MACAR) {
+        if (int rc = plan_launch(g, k_fw_mc<true>, a.fl.bytes, nstreams, &c)) return rc;
+        k_fw_mc<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(a, sp, stream0, nstreams, n, counts_dev, steps_dev);
+    } else {
+        if (int rc = plan_launch(g, k_fw_mc<false>, a.fl.bytes, nstreams, &c)) return rc;
+        k_fw_mc<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(a, sp, stream0, nstreams, n, counts_dev, steps_dev);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
+int luf_forward_decode_host(luf_graph* g, int decoder, int flags, int64_t nstreams, int32_t ncycles,
+                            const uint32_t* init_buffer_host, const uint32_t* fresh_bits_host, int32_t* steps_host,
+                            uint32_t* commit_bits_host, int32_t* m_host)
+{
+    if (!g || !init_buffer_host || !fresh_bits_host || !steps_host || !m_host || nstreams < 0 || ncycles < 0)
+        return fail(LUF_ERR_INVALID, "luf_forward_decode_host: bad argument");
+    if (nstreams == 0 || ncycles == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t rows = (size_t)nstreams * ncycles, W = g->view.WE;
+    void *ib, *fr, *st, *cm = nullptr, *mm;
+    int rc;
+    if ((rc = scratch_get(g, 1, (size_t)nstreams * W * 4, &ib)) || (rc = scratch_get(g, 2, rows * W * 4, &fr)) ||
+        (rc = scratch_get(g, 4, rows * 8, &st)) || (rc = scratch_get(g, 5, rows * 4, &mm))) return rc;
+    if (commit_bits_host && (rc = scratch_get(g, 3, rows * W * 4, &cm))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ib, init_buffer_host, (size_t)nstreams * W * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(fr, fresh_bits_host, rows * W * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = luf_forward_decode(g, decoder, flags, nstreams, ncycles, (const uint32_t*)ib, (const uint32_t*)fr,
+                                 (int32_t*)st, (uint32_t*)cm, (int32_t*)mm, 0))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(steps_host, st, rows * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(m_host, mm, rows * 4, cudaMemcpyDeviceToHost, 0));
+    if (cm) CUDA_TRY(cudaMemcpyAsync(commit_bits_host, cm, rows * W * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int luf_forward_mc_host(luf_graph* g, int decoder, int flags, const double* class_p_host, uint64_t seed,
+                        uint64_t stream0, int64_t nstreams, int32_t n, unsigned long long counts_host[4],
+                        int32_t* steps_host)
+{
+    if (!g || !counts_host || nstreams < 0) return fail(LUF_ERR_INVALID, "luf_forward_mc_host: bad argument");
+    if (n < 1) return fail(LUF_ERR_INVALID, "n must be positive integer.");
+    if (nstreams == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    void *cnt, *st = nullptr;
+    int rc;
+    if ((rc = scratch_get(g, 0, 32, &cnt))) return rc;
+    if (steps_host && (rc = scratch_get(g, 4, (size_t)nstreams * n * 8, &st))) return rc;
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 32, 0));
+    if ((rc = luf_forward_mc(g, decoder, flags, class_p_host, seed, stream0, nstreams, n, (unsigned long long*)cnt,
+                             (int32_t*)st, 0))) return rc;
+    unsigned long long tmp[4];
+    if (st) CUDA_TRY(cudaMemcpyAsync(steps_host, st, (size_t)nstreams * n * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpy(tmp, cnt, 32, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) counts_host[i] += tmp[i];
     return 0;
 }
 

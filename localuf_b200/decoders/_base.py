@@ -59,6 +59,26 @@ class Decoder:
         return fails
 
 
+    def _mc_forward(self, noise_level: float, n: int, shots: int = 1, seed=None, draw=False, log_history=False,
+                    **kwargs):
+        """``shots`` independent ``Forward.run(n)`` experiments on the device
+        (``_schemes.py:392-450``); returns (logical errors, step counts [shots*n][2])."""
+        if draw or log_history:
+            raise NotImplementedError("Drawing / history is outside this engine (SURVEY.md section 2, row 14).")
+        eng = self.engine
+        rank, size = dist.world()
+        seed = self._draw_seed(seed)
+        if size > 1:
+            seed = dist.allreduce_counts([seed if rank == 0 else 0])[0]
+        lo, cnt = dist.shard(shots, rank, size)
+        counts, steps = ([0, 0, 0, 0], None)
+        if cnt:
+            counts, steps = eng.forward_mc_host(self._DECODER_ID, self._flags, noise_level, seed, lo, cnt, n,
+                                                want_steps=True)
+        m = dist.allreduce_counts([counts[0]], device=f'cuda:{eng.device}')[0]
+        return m, ([] if steps is None else steps.reshape(-1, 2))
+
+
 class BaseUF(Decoder):
     """Adds ``growth`` / ``erasure`` / ``syndrome`` (``_base_uf.py:33-99``)."""
 

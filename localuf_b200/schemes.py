@@ -274,13 +274,18 @@ class Forward(_Streaming):
         return ({e for e in error if e in commit} ^ {e for e in correction if e in commit},
                 {e for e in error if e not in commit})
 
-    def run(self, decoder, noise_level: float, n: int, **kwargs):
+    def run(self, decoder, noise_level: float, n: int, shots: int = 1, **kwargs):
+        """``shots`` independent runs of ``n`` steady-state decoding cycles each
+        (``_schemes.py:392-450``; the reference runs exactly one).  ``step_counts``
+        gets ``decoder.decode``'s return value per timed cycle: ``None`` for UF,
+        ``(tSV, tBP)`` for Macar."""
         if n < 1:
             raise ValueError("n must be positive integer.")
         self.reset()
-        m, steps = decoder._mc_forward(noise_level, n, **kwargs)
-        self.step_counts.extend(steps)
-        return m, (self._BUFFER_HEIGHT + (n + 1) * self._COMMIT_HEIGHT) / self._CODE.D
+        m, steps = decoder._mc_forward(noise_level, n, shots=shots, **kwargs)
+        returns_steps = getattr(decoder, '_DECODER_ID', 0) != 0
+        self.step_counts.extend((int(a), int(b)) if returns_steps else None for a, b in steps)
+        return m, shots * (self._BUFFER_HEIGHT + (n + 1) * self._COMMIT_HEIGHT) / self._CODE.D
 
 
 class Frugal(_Streaming):

@@ -25,3 +25,21 @@ def batch(ds, noise_levels, n, noise, decoder_class=Macar, validate_only=True, *
     df = DataFrame(data).sort_index(axis=1)
     df.columns.set_names(['stage', 'd', 'p'], inplace=True)
     return df
+
+
+def forward(ds, noise_levels, n, noise, get_commit_height=None, get_buffer_height=None, **kwargs_for_Surface):
+    """Runtime data of Macar under the forward scheme (``localuf/sim/runtime.py:78-136``)."""
+    from localuf_b200.sim._height_calculator import get_heights
+    data = {}
+    for d in ds:
+        _, commit_height, buffer_height = get_heights(d, n, 'forward', get_commit_height, get_buffer_height)
+        code = Surface(d, noise, scheme='forward', window_height=None, commit_height=commit_height,
+                       buffer_height=buffer_height, **kwargs_for_Surface)
+        decoder = Macar(code)
+        for noise_level in noise_levels:
+            code.SCHEME.run(decoder, noise_level, n)
+            data['SV', d, noise_level] = [sv for sv, _ in code.SCHEME.step_counts]
+            data['BP', d, noise_level] = [bp for _, bp in code.SCHEME.step_counts]
+    df = DataFrame(data).sort_index(axis=1)
+    df.columns.set_names(['stage', 'd', 'p'], inplace=True)
+    return df

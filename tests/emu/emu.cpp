@@ -123,6 +123,52 @@ int emu_decode_ca(const luf_graph_desc* d, int decoder, int flags, long long nsh
     return 0;
 }
 
+// Forward scheme on given fresh errors (one stream); decoder 0 = UF, 1 = Macar.
+int emu_fw_stream(const luf_graph_desc* gd, const luf_forward_desc* fd, int decoder, int flags, int ncycles,
+                  const uint32_t* init_buf, const uint32_t* fresh, int32_t* steps, uint32_t* commit_out, int32_t* m_out)
+{
+    PackedGraph pg; PackedCa pc; PackedForward pf;
+    if (!pack_graph(*gd, pg).empty()) return -1;
+    if (decoder == 1 && !pack_ca(*gd, pc).empty()) return -2;
+    const luf_graph_desc_dims dims = {pg.N, pg.B, pg.E, pg.n_classes};
+    if (!pack_forward(dims, *fd, pf).empty()) return -3;
+    const GraphView gv = view_of(pg);
+    FwView g;
+    g.N = pg.N; g.B = pg.B; g.E = pg.E; g.WE = words32(pg.E); g.WD = words32(pg.N - pg.B); g.c = pf.c;
+    g.edge_uv = pg.edge_uv.data(); g.lower_edge = pf.lower_edge.data(); g.commit_mask = pf.commit_mask.data();
+    g.art_node = pf.art_node.data(); g.fb_mask = pf.fb_mask.data(); g.node_lower = pf.node_lower.data();
+    g.node_side = pf.node_side.data();
+    const int nl = 32;
+    if (decoder == 0) {
+        const Layout ul = make_layout(pg.N, pg.B, pg.E, true, true);
+        const FwLayout fl = make_fw_layout(pg.N, pg.E, ul.bytes);
+        std::vector<unsigned char> mem(fl.bytes);
+        const FwState f = fw_bind(fl, mem.data());
+        FwUf d{gv, ul, bind(ul, mem.data()), flags};
+        LUF_PHASE(fw_reset(g, f, init_buf, lane, nl));
+        for (int c = 0; c < ncycles; ++c)
+            m_out[c] = fw_cycle_given(g, f, d, fresh + (size_t)c * g.WE, commit_out + (size_t)c * g.WE,
+                                      steps[2 * c], steps[2 * c + 1], 0, nl);
+    } else {
+        std::vector<uint32_t> west(gd->west_edge_mask, gd->west_edge_mask + words32(pg.E));
+        CaView cv;
+        cv.N = pc.N; cv.B = pc.B; cv.E = pc.E; cv.K = pc.K;
+        cv.WE = words32(pc.E); cv.WD = words32(pc.N - pc.B); cv.WN = words32(pc.N); cv.GW = (pc.E + 15) / 16;
+        cv.nbr = pc.nbr.data(); cv.west_mask = west.data(); cv.span = pc.span.data(); cv.relay = pc.relay.data();
+        cv.global_span = pc.global_span;
+        const CaLayout cl = make_ca_layout(pc.N, pc.B, pc.E, false, true);
+        const FwLayout fl = make_fw_layout(pg.N, pg.E, cl.bytes);
+        std::vector<unsigned char> mem(fl.bytes);
+        const FwState f = fw_bind(fl, mem.data());
+        FwMacar d{cv, ca_bind(cl, mem.data())};
+        LUF_PHASE(fw_reset(g, f, init_buf, lane, nl));
+        for (int c = 0; c < ncycles; ++c)
+            m_out[c] = fw_cycle_given(g, f, d, fresh + (size_t)c * g.WE, commit_out + (size_t)c * g.WE,
+                                      steps[2 * c], steps[2 * c + 1], 0, nl);
+    }
+    return 0;
+}
+
 // Snowflake + frugal bookkeeping on given fresh errors (one stream).
 int emu_sf_stream(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
                   int32_t* rt, uint32_t* floor_bits, int32_t* m_out)

@@ -81,6 +81,19 @@ class Emu:
         assert rc == 0, rc
         return corr, growth, steps
 
+    def forward_stream(self, code, decoder, flags, init_bits, fresh_bits):
+        from localuf_b200 import _window
+        from localuf_b200._engine import make_forward_desc
+        fdesc, keep = make_forward_desc(_window.build_forward(code))
+        fresh = np.ascontiguousarray(fresh_bits, dtype=np.uint32).reshape(-1, self.WE)
+        init = np.ascontiguousarray(init_bits, dtype=np.uint32).reshape(self.WE)
+        n = fresh.shape[0]
+        steps = np.zeros((n, 2), np.int32); commit = np.zeros((n, self.WE), np.uint32); m = np.zeros(n, np.int32)
+        rc = lib().emu_fw_stream(C.byref(self.desc), C.byref(fdesc), decoder, flags, n, _vp(init), _vp(fresh),
+                                 _vp(steps), _vp(commit), _vp(m))
+        assert rc == 0, rc
+        return steps, commit, m
+
 
 class EmuStream:
     """Host emulation of the Snowflake / frugal kernel phases for one window."""
