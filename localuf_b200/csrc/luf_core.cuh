@@ -103,6 +103,7 @@ struct Layout {
     uint32_t defect;                    // uint32[WD]
     uint32_t act0, act1;                // uint32[WD]  active roots (detector-indexed), ping-pong
     uint32_t troot;                     // uint32[WN]  tree roots to peel from
+    uint32_t bdef;                      // uint32[W(B)]  defects pushed onto boundary nodes while peeling
     uint32_t err, corr;                 // uint32[WE]  only in the staged kernels (0 = absent)
     uint32_t claim;                     // uint32[CLAIM_SLOTS]  merge reservations (see ph_merge_claim)
     uint32_t bytes;                     // slice size, multiple of 16
@@ -110,7 +111,7 @@ struct Layout {
 
 struct Shot {
     idx_t *P, *NX, *R;
-    uint32_t *growth, *newfull, *defect, *act0, *act1, *troot, *err, *corr, *claim;
+    uint32_t *growth, *newfull, *defect, *act0, *act1, *troot, *bdef, *err, *corr, *claim;
 };
 
 LUF_DEV Shot bind(const Layout& l, unsigned char* base)
@@ -121,6 +122,7 @@ LUF_DEV Shot bind(const Layout& l, unsigned char* base)
     s.defect = (uint32_t*)(base + l.defect);
     s.act0 = (uint32_t*)(base + l.act0); s.act1 = (uint32_t*)(base + l.act1);
     s.troot = (uint32_t*)(base + l.troot);
+    s.bdef = (uint32_t*)(base + l.bdef);
     s.err = l.err ? (uint32_t*)(base + l.err) : 0;
     s.corr = l.corr ? (uint32_t*)(base + l.corr) : 0;
     s.claim = (uint32_t*)(base + l.claim);
@@ -167,6 +169,7 @@ LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int la
     }
     for (int w = lane; w < g.WD; w += nl) { s.defect[w] = 0; s.act0[w] = 0; s.act1[w] = 0; }
     for (int w = lane; w < g.WN; w += nl) s.troot[w] = 0;
+    for (int w = lane; w < ((g.B + 31) >> 5); w += nl) s.bdef[w] = 0;
     for (int w = lane; w < CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu;
     (void)l;
 }
@@ -539,10 +542,12 @@ LUF_DEV uint32_t ph_peel(const GraphView& g, const Shot& s, int lane, int nl)
                     chain[o] = (idx_t)last; last = o;
                 }
             }
+            // A boundary node that is neither the root nor a leaf (future-boundary nodes of a
+            // streaming window have degree > 1) carries pushed defects like any other node.
             for (uint32_t v = last; v != NONE16; v = chain[v]) {
-                if (v < (uint32_t)g.B) continue;
-                const uint32_t dv = v - g.B;
-                if (!((s.defect[dv >> 5] >> (dv & 31u)) & 1u)) continue;
+                uint32_t* dw = v >= (uint32_t)g.B ? &s.defect[(v - g.B) >> 5] : &s.bdef[v >> 5];
+                const uint32_t db = v >= (uint32_t)g.B ? (v - g.B) & 31u : v & 31u;
+                if (!((*dw >> db) & 1u)) continue;
                 const uint32_t e = tedge[v];
                 if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
                 parity ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
@@ -550,6 +555,8 @@ LUF_DEV uint32_t ph_peel(const GraphView& g, const Shot& s, int lane, int nl)
                 const uint32_t par = (uv & 0xFFFFu) == v ? (uv >> 16) : (uv & 0xFFFFu);
                 if (par >= (uint32_t)g.B)
                     luf_atomic_xor(&s.defect[(par - g.B) >> 5], 1u << ((par - g.B) & 31u));
+                else
+                    luf_atomic_xor(&s.bdef[par >> 5], 1u << (par & 31u));
             }
         }
     }

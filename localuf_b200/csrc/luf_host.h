@@ -90,6 +90,7 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr)
     l.newfull = take(4u * WE);
     l.defect = take(4u * WD); l.act0 = take(4u * WD); l.act1 = take(4u * WD);
     l.troot = take(4u * WN);
+    l.bdef = take(4u * (words32(B) ? words32(B) : 1));
     l.claim = take(4u * CLAIM_SLOTS);
     l.err = keep_err ? take(4u * WE) : 0;
     l.corr = keep_corr ? take(4u * WE) : 0;

@@ -92,6 +92,11 @@ UF_CASES = [
     ('uf_sf5_cl_p03', dict(code='Surface', d=5, noise='circuit-level'), 0.03, 100, 23),
     ('uf_sf4_phen_fwd_p04', dict(code='Surface', d=4, noise='phenomenological',
                                  kwargs=dict(scheme='forward')), 0.04, 150, 24),
+    # circuit-level forward window: future-boundary nodes have degree > 1 (interior nodes of the peeling tree)
+    ('uf_sf4_cl_fwd_p03', dict(code='Surface', d=4, noise='circuit-level',
+                               kwargs=dict(scheme='forward')), 0.03, 200, 25),
+    ('uf_sf5_cl_fwd_p015', dict(code='Surface', d=5, noise='circuit-level',
+                                kwargs=dict(scheme='forward', commit_height=2, buffer_height=3)), 0.015, 150, 26),
 ]
 
 

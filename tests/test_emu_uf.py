@@ -67,3 +67,30 @@ def test_emu_sampler_extremes():
     _, err, syn, _ = emu.mc_uf(0, 1.0, 1, 0, 20)
     bits = np.unpackbits(err.view(np.uint8), axis=1, bitorder='little')[:, :code.N_EDGES]
     assert bits.all()
+
+
+@pytest.mark.parametrize('spec', [
+    dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='forward')),
+    dict(code='Surface', d=5, noise='phenomenological', kwargs=dict(scheme='forward')),
+    dict(code='Surface', d=4, noise='circuit-level', kwargs=dict(scheme='forward', commit_height=2, buffer_height=3)),
+    dict(code='Surface', d=5, noise='circuit-level'),
+    dict(code='Surface', d=7, noise='code capacity'),
+], ids=lambda s: f"{s['noise'].split()[0]}-{s.get('kwargs', {}).get('scheme', 'batch')}")
+def test_emu_decode_random_syndromes_vs_oracle(spec):
+    """Dense random errors on every edge of the graph (also the non-fresh ones of a
+    forward window, whose future-boundary nodes have degree > 1): kernel phases == oracle."""
+    code = make_code(spec)
+    emu = emu_binding.Emu(code)
+    orc = binding.Oracle.from_code(code)
+    g = code.FLAT
+    rng = np.random.default_rng(11)
+    n = 1500
+    pad = np.zeros((n, 32 * emu.WE), np.uint8)
+    pad[:, :g.n_edges] = rng.random((n, g.n_edges)) < rng.choice([0.01, 0.03, 0.08], size=(n, 1))
+    syn = orc.syndrome(np.packbits(pad, axis=1, bitorder='little').view(np.uint32))
+    for flags in (0, 1, 2):
+        corr, growth2b, steps = emu.decode_uf(flags, syn)
+        ocorr, ogrowth, osteps = orc.decode_batch(0, flags, syn)
+        np.testing.assert_array_equal(unpack_growth(growth2b, g.n_edges), ogrowth)
+        np.testing.assert_array_equal(steps[:, 0], osteps[:, 0])
+        np.testing.assert_array_equal(corr, ocorr)
