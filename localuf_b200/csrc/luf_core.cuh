@@ -97,32 +97,29 @@ struct SampleParams {
 
 // Byte offsets of one shot's state inside its shared-memory slice.
 struct Layout {
-    uint32_t P, NX, R;                  // idx_t[N] each (aliased by the peel: tree edge, stack link, discovery link)
+    uint32_t P, R;                      // idx_t[N] each (aliased by the peel: tree edge, stack link)
     uint32_t growth;                    // uint32[ceil(E/16)]  2 bits per edge
     uint32_t newfull;                   // uint32[WE]  edges that reached FULL this round
     uint32_t defect;                    // uint32[WD]
-    uint32_t act0, act1;                // uint32[WD]  active roots (detector-indexed), ping-pong
+    uint32_t touched;                   // uint32[WN]  nodes that are a defect or belong to a cluster of size > 1
     uint32_t troot;                     // uint32[WN]  tree roots to peel from
-    uint32_t bdef;                      // uint32[W(B)]  defects pushed onto boundary nodes while peeling
     uint32_t err, corr;                 // uint32[WE]  only in the staged kernels (0 = absent)
     uint32_t claim;                     // uint32[CLAIM_SLOTS]  merge reservations (see ph_merge_claim)
     uint32_t bytes;                     // slice size, multiple of 16
 };
 
 struct Shot {
-    idx_t *P, *NX, *R;
-    uint32_t *growth, *newfull, *defect, *act0, *act1, *troot, *bdef, *err, *corr, *claim;
+    idx_t *P, *R;
+    uint32_t *growth, *newfull, *defect, *touched, *troot, *err, *corr, *claim;
 };
 
 LUF_DEV Shot bind(const Layout& l, unsigned char* base)
 {
     Shot s;
-    s.P = (idx_t*)(base + l.P); s.NX = (idx_t*)(base + l.NX); s.R = (idx_t*)(base + l.R);
+    s.P = (idx_t*)(base + l.P); s.R = (idx_t*)(base + l.R);
     s.growth = (uint32_t*)(base + l.growth); s.newfull = (uint32_t*)(base + l.newfull);
-    s.defect = (uint32_t*)(base + l.defect);
-    s.act0 = (uint32_t*)(base + l.act0); s.act1 = (uint32_t*)(base + l.act1);
+    s.defect = (uint32_t*)(base + l.defect); s.touched = (uint32_t*)(base + l.touched);
     s.troot = (uint32_t*)(base + l.troot);
-    s.bdef = (uint32_t*)(base + l.bdef);
     s.err = l.err ? (uint32_t*)(base + l.err) : 0;
     s.corr = l.corr ? (uint32_t*)(base + l.corr) : 0;
     s.claim = (uint32_t*)(base + l.claim);
@@ -152,13 +149,15 @@ LUF_DEV uint32_t find_compress(const Shot& s, uint32_t v)
 // ------------------------------------------------------------ phase 0: reset
 // uf.py:79-96,496-519 -- every node a singleton cluster; a boundary node is its
 // own cluster boundary.  (The reference re-allocates N Python objects here,
-// 40-58 % of its time; this is ~N*6 bytes of shared-memory stores.)
+// 40-58 % of its time; this is ~N*4 bytes of shared-memory stores.)
 LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int lane, int nl)
 {
-    for (int v = lane; v < g.N; v += nl) {
-        s.P[v] = (idx_t)(ROOT_BIT | 1u);
-        s.NX[v] = (idx_t)v;                                  // circular member list
-        s.R[v] = (idx_t)(v < g.B ? (uint32_t)v + 1u : 0u);
+    uint32_t* P2 = (uint32_t*)s.P;
+    uint32_t* R2 = (uint32_t*)s.R;
+    const uint32_t root1 = (ROOT_BIT | 1u) * 0x10001u;               // two singleton roots per 32-bit store
+    for (int v = 2 * lane; v < g.N; v += 2 * nl) {
+        P2[v >> 1] = root1;
+        R2[v >> 1] = (v < g.B ? (uint32_t)v + 1u : 0u) | ((v + 1 < g.B ? (uint32_t)v + 2u : 0u) << 16);
     }
     const int GW = (g.E + 15) >> 4;
     for (int w = lane; w < GW; w += nl) s.growth[w] = 0;
@@ -167,9 +166,8 @@ LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int la
         if (s.err) s.err[w] = 0;
         if (s.corr) s.corr[w] = 0;
     }
-    for (int w = lane; w < g.WD; w += nl) { s.defect[w] = 0; s.act0[w] = 0; s.act1[w] = 0; }
-    for (int w = lane; w < g.WN; w += nl) s.troot[w] = 0;
-    for (int w = lane; w < ((g.B + 31) >> 5); w += nl) s.bdef[w] = 0;
+    for (int w = lane; w < g.WD; w += nl) s.defect[w] = 0;
+    for (int w = lane; w < g.WN; w += nl) { s.troot[w] = 0; s.touched[w] = 0; }
     for (int w = lane; w < CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu;
     (void)l;
 }
@@ -283,65 +281,66 @@ LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams
     return ph_sample_tab(g, t, s, sp, shot, 0u, (const uint32_t*)0, lane, nl);
 }
 
-// uf.py:98-104 load: every defect is an odd, active singleton cluster.
-// Returns whether this lane saw a defect.
-LUF_DEV uint32_t ph_load(const GraphView& g, const Shot& s, int lane, int nl)
+// uf.py:98-104 load: every defect is an odd singleton cluster (hence active).
+LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    uint32_t any = 0;
     for (int w = lane; w < g.WD; w += nl) {
         uint32_t bits = s.defect[w];
-        s.act0[w] = bits;
-        any |= bits;
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            s.R[g.B + 32 * w + b] = (idx_t)ODD_BIT;
+            const uint32_t v = (uint32_t)(g.B + 32 * w + b);
+            s.R[v] = (idx_t)ODD_BIT;
+            luf_atomic_or(&s.touched[v >> 5], 1u << (v & 31u));
+        }
+    }
+}
+
+// ------------------------------------------------------- phase 2a: grow a round
+// uf.py:221-222,234-245.  vision(C) = edges incident to C's members that are not
+// yet FULL/BURNT; a cluster is active iff it is odd and has no boundary
+// (uf.py:296-301), i.e. R[root] == ODD_BIT.  Members are not kept in lists:
+// every *touched* node (defect, or member of a cluster of size > 1 -- singleton
+// non-defects are never active) looks its root up and grows its own incident
+// edges if the root is active.  An edge inside one cluster is in that cluster's
+// vision once: only its first endpoint adds.  Two different active clusters
+// each add 1.  The 2-bit counters saturate at FULL.  Returns whether this lane
+// saw an active node.
+LUF_DEV uint32_t ph_grow(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    uint32_t any = 0;
+    for (int w = lane; w < g.WN; w += nl) {
+        uint32_t bits = s.touched[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t u = (uint32_t)(32 * w + b);
+            const uint32_t r = find_ro(s, u);
+            if (s.R[r] != ODD_BIT) continue;
+            any = 1;
+            const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
+            for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
+                const uint32_t ent = LUF_LDG(&g.inc[k]);
+                const uint32_t e = ent & 0xFFFFu;
+                const uint32_t sh = (e & 15u) * 2u;
+                if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
+                if (!(ent >> 31)) {                       // second endpoint: skip if same cluster
+                    const uint32_t o = (ent >> 16) & 0x7FFFu;
+                    if (o == r || find_ro(s, o) == r) continue;
+                }
+                const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+                if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
+                else if (old == G_HALF) luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
+            }
         }
     }
     return any;
 }
 
-// ------------------------------------------------------- phase 2a: grow a round
-// uf.py:221-222,234-245.  vision(C) = edges incident to C's members that are not
-// yet FULL/BURNT.  A lane takes active roots (one bitmap word at a time) and
-// walks each cluster's circular member list.  An edge inside one cluster is in
-// that cluster's vision once: only its first endpoint adds.  Two different
-// active clusters each add 1.  The 2-bit counters saturate at FULL.
-LUF_DEV void ph_grow(const GraphView& g, const Shot& s, int cur, int lane, int nl)
-{
-    const uint32_t* act = cur ? s.act1 : s.act0;
-    for (int w = lane; w < g.WD; w += nl) {
-        uint32_t bits = act[w];
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t r = (uint32_t)(g.B + 32 * w + b);
-            uint32_t u = r;
-            do {
-                const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
-                for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
-                    const uint32_t ent = LUF_LDG(&g.inc[k]);
-                    const uint32_t e = ent & 0xFFFFu;
-                    const uint32_t sh = (e & 15u) * 2u;
-                    if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
-                    if (!(ent >> 31)) {                       // second endpoint: skip if same cluster
-                        const uint32_t o = (ent >> 16) & 0x7FFFu;
-                        if (o == r || find_ro(s, o) == r) continue;
-                    }
-                    const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-                    if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
-                    else if (old == G_HALF) luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
-                }
-                u = s.NX[u];
-            } while (u != r);
-        }
-    }
-}
-
 // ------------------------------------------------------------ phase 2b: merge
 // uf.py:223-229,256-301 in canonical order: this round's newly FULL edges are
 // merged in ascending edge id.  Union by size, ties keep the cluster of the
-// edge's first endpoint; parity XOR; boundary by inclination; member lists
-// spliced.  The smaller root's R slot is dead after the union and keeps the
-// union edge (used by the peel for two-node clusters).
+// edge's first endpoint; parity XOR; boundary by inclination.  The smaller
+// root's R slot is dead after the union and keeps the union edge (used by the
+// peel for two-node clusters).
 LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t e, uint32_t cu, uint32_t cv)
 {
     if (flags & FLAG_DYNAMIC) {                                   // uf.py:261-266
@@ -360,9 +359,10 @@ LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t 
     } else if (!bl && bs) bl = bs;                                // uf.py:536-538
     s.R[L] = (idx_t)(((rl ^ rs) & ODD_BIT) | bl);
     s.R[S] = (idx_t)e;
-    const idx_t t = s.NX[L]; s.NX[L] = s.NX[S]; s.NX[S] = t;      // splice the circular lists
     s.P[L] = (idx_t)(ROOT_BIT | (su + sv));
     s.P[S] = (idx_t)L;
+    if (su == 1u) luf_atomic_or(&s.touched[cu >> 5], 1u << (cu & 31u));   // no longer a singleton
+    if (sv == 1u) luf_atomic_or(&s.touched[cv >> 5], 1u << (cv & 31u));
 }
 
 // The serial order is reproduced in parallel by deterministic reservations:
@@ -436,42 +436,17 @@ LUF_DEV void merge_rest(const GraphView& g, const Shot& s, int flags, int base, 
     }
 }
 
-// ------------------------------------------ phase 2c: next round's active roots
-// uf.py:290-301: active <=> odd and without boundary.  Every active cluster of
-// the next round contains an active root of this round.
-LUF_DEV void ph_clear_next(const GraphView& g, const Shot& s, int cur, int lane, int nl)
-{
-    uint32_t* nxt = cur ? s.act0 : s.act1;
-    for (int w = lane; w < g.WD; w += nl) nxt[w] = 0;
-}
-
-LUF_DEV uint32_t ph_reactivate(const GraphView& g, const Shot& s, int cur, int lane, int nl)
-{
-    const uint32_t* act = cur ? s.act1 : s.act0;
-    uint32_t* nxt = cur ? s.act0 : s.act1;
-    uint32_t any = 0;
-    for (int w = lane; w < g.WD; w += nl) {
-        uint32_t bits = act[w];
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t r = find_ro(s, (uint32_t)(g.B + 32 * w + b));
-            if (s.R[r] == (idx_t)ODD_BIT) {                     // odd, no boundary
-                luf_atomic_or(&nxt[(r - g.B) >> 5], 1u << ((r - g.B) & 31u));
-                any = 1;
-            }
-        }
-    }
-    return any;
-}
-
 // ------------------------------------------------------------- phase 3: peel
 // uf.py:314-324: one tree per cluster, rooted at cluster.boundary or else the
 // union-find root.  Clusters without a defect cannot contribute a correction
 // edge, so only clusters of defects are rooted.
 //
 // Two-node clusters (the common case at low noise: one flipped edge) need no
-// traversal: their only tree is the union edge, and it is in the correction
-// iff the cluster holds a defect.  One of the (at most two) defects acts.
+// traversal: their only tree is the union edge, kept in the R slot of the
+// member that is not the root, and it is in the correction iff the cluster
+// holds a defect.  Exactly one member acts: the non-root member if it is a
+// defect; else the root, whose partner is then the cluster's boundary node
+// (an odd cluster that stopped growing has one).
 // Returns this lane's parity of pair corrections on the west boundary and
 // (bit 1) whether any cluster needs the general traversal.
 LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int nl)
@@ -483,17 +458,19 @@ LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int 
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             const uint32_t dn = (uint32_t)(g.B + 32 * w + b);
             const uint32_t r = find_ro(s, dn);
+            const uint32_t rr = s.R[r];
             if ((s.P[r] & 0x7FFFu) == 2u) {
-                const uint32_t x = s.NX[r];                                  // the other member
-                const uint32_t rd = r >= (uint32_t)g.B ? (s.defect[(r - g.B) >> 5] >> ((r - g.B) & 31u)) & 1u : 0u;
-                if (dn == r || !rd) {
-                    const uint32_t e = s.R[x];
-                    if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
-                    out ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
+                uint32_t x = dn;                                  // the member whose R slot holds the union edge
+                if (dn == r) {
+                    if (!(rr & ODD_BIT)) continue;                // both are defects: the other member acts
+                    x = (rr & 0x7FFFu) - 1u;                      // single defect: its partner is the boundary node
                 }
+                const uint32_t e = s.R[x];
+                if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
+                out ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
                 continue;
             }
-            const uint32_t bn = s.R[r] & 0x7FFFu;
+            const uint32_t bn = rr & 0x7FFFu;
             const uint32_t t = bn ? bn - 1u : r;
             luf_atomic_or(&s.troot[t >> 5], 1u << (t & 31u));
             out |= 2u;
@@ -503,21 +480,19 @@ LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int 
 }
 
 // The union-find arrays are dead now; reuse them for the traversal:
-//   P  -> tree edge towards the root (NONE16 = undiscovered)
-//   NX -> link of the LIFO stack          R -> link of the discovery chain
+//   P -> tree edge towards the root (NONE16 = undiscovered)    R -> link of the LIFO stack
 LUF_DEV void ph_peel_init(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    for (int v = lane; v < g.N; v += nl) s.P[v] = (idx_t)NONE16;
+    uint32_t* P2 = (uint32_t*)s.P;
+    for (int v = lane; 2 * v < g.N; v += nl) P2[v] = 0xFFFFFFFFu;
 }
 
-// uf.py:326-344 (LIFO traversal, neighbours in ascending edge id) and
-// uf.py:305-312 (walk the discovery order backwards; a node still carrying a
-// defect sends it to its parent through the tree edge).  Returns this lane's
-// parity of correction edges on the west boundary.
-LUF_DEV uint32_t ph_peel(const GraphView& g, const Shot& s, int lane, int nl)
+// uf.py:326-344: the reference's LIFO traversal (neighbours in ascending edge
+// id) from every tree root; one lane per root.  Only the tree (the edge towards
+// the root of every discovered node) is kept.
+LUF_DEV void ph_peel_build(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    idx_t* tedge = s.P; idx_t* stk = s.NX; idx_t* chain = s.R;
-    uint32_t parity = 0;
+    idx_t* tedge = s.P; idx_t* stk = s.R;
     for (int w = lane; w < g.WN; w += nl) {
         uint32_t bits = s.troot[w];
         s.troot[w] = 0;
@@ -526,7 +501,7 @@ LUF_DEV uint32_t ph_peel(const GraphView& g, const Shot& s, int lane, int nl)
             const uint32_t root = (uint32_t)(32 * w + b);
             tedge[root] = (idx_t)TREE_ROOT;
             stk[root] = (idx_t)NONE16;
-            uint32_t top = root, last = NONE16;
+            uint32_t top = root;
             while (top != NONE16) {
                 const uint32_t u = top;
                 top = stk[u];
@@ -539,24 +514,34 @@ LUF_DEV uint32_t ph_peel(const GraphView& g, const Shot& s, int lane, int nl)
                     if (tedge[o] != NONE16) continue;
                     tedge[o] = (idx_t)e;
                     stk[o] = (idx_t)top; top = o;
-                    chain[o] = (idx_t)last; last = o;
                 }
             }
-            // A boundary node that is neither the root nor a leaf (future-boundary nodes of a
-            // streaming window have degree > 1) carries pushed defects like any other node.
-            for (uint32_t v = last; v != NONE16; v = chain[v]) {
-                uint32_t* dw = v >= (uint32_t)g.B ? &s.defect[(v - g.B) >> 5] : &s.bdef[v >> 5];
-                const uint32_t db = v >= (uint32_t)g.B ? (v - g.B) & 31u : v & 31u;
-                if (!((*dw >> db) & 1u)) continue;
-                const uint32_t e = tedge[v];
+        }
+    }
+}
+
+// uf.py:305-312: peeling the forest leaf-up puts a tree edge in the correction
+// iff an odd number of defects hang below it -- the XOR over all defects of
+// their paths to the root.  Every defect of a traversed cluster walks its own
+// path (defects of two-node clusters were handled above and are undiscovered
+// here).  Returns this lane's parity of correction edges on the west boundary.
+LUF_DEV uint32_t ph_peel_paths(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    const idx_t* tedge = s.P;
+    uint32_t parity = 0;
+    for (int w = lane; w < g.WD; w += nl) {
+        uint32_t bits = s.defect[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            uint32_t v = (uint32_t)(g.B + 32 * w + b);
+            uint32_t e = tedge[v];
+            if (e == NONE16) continue;
+            while (e != TREE_ROOT) {
                 if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
                 parity ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
                 const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-                const uint32_t par = (uv & 0xFFFFu) == v ? (uv >> 16) : (uv & 0xFFFFu);
-                if (par >= (uint32_t)g.B)
-                    luf_atomic_xor(&s.defect[(par - g.B) >> 5], 1u << ((par - g.B) & 31u));
-                else
-                    luf_atomic_xor(&s.bdef[par >> 5], 1u << (par & 31u));
+                v = (uv & 0xFFFFu) == v ? (uv >> 16) : (uv & 0xFFFFu);
+                e = tedge[v];
             }
         }
     }
@@ -565,17 +550,17 @@ LUF_DEV uint32_t ph_peel(const GraphView& g, const Shot& s, int lane, int nl)
 
 // ------------------------------------------------------------------ drivers
 // uf.py:200-209 validate: rounds of grow / merge until no cluster is active.
-// `any_defect` is the tile-wide result of ph_load.  Returns the number of
-// growth rounds.  `lane` is this thread's lane on the device; the host
-// emulation iterates it inside LUF_PHASE.
-LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, uint32_t any_defect, int lane, int nl)
+// Returns the number of growth rounds.  `lane` is this thread's lane on the
+// device; the host emulation iterates it inside LUF_PHASE.
+LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, int nl)
 {
-    int cur = 0, rounds = 0;
+    int rounds = 0;
     uint32_t iter = 0xFFFFu;                 // decreasing reservation tag
-    uint32_t active = any_defect;
     (void)lane;
-    while (active) {
-        LUF_PHASE(ph_grow(g, s, cur, lane, nl); ph_clear_next(g, s, cur, lane, nl));
+    for (;;) {
+        uint32_t active = 0;
+        LUF_PHASE(active |= ph_grow(g, s, lane, nl));
+        if (!LUF_ANY(active)) break;
         {   // one parallel reservation round places the independent merges ...
             const uint32_t tag = iter << 16;
             --iter;
@@ -590,10 +575,6 @@ LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, uint32_t a
                 }
             }
         }
-        active = 0;
-        LUF_PHASE(active |= ph_reactivate(g, s, cur, lane, nl));
-        active = LUF_ANY(active);
-        cur ^= 1;
         ++rounds;
     }
     return rounds;
@@ -608,7 +589,8 @@ LUF_DEV uint32_t uf_peel(const GraphView& g, const Shot& s, int lane, int nl)
     LUF_PHASE(const uint32_t r = ph_tree_roots(g, s, lane, nl); parity ^= r & 1u; general |= r >> 1);
     if (LUF_ANY(general)) {
         LUF_PHASE(ph_peel_init(g, s, lane, nl));
-        LUF_PHASE(parity ^= ph_peel(g, s, lane, nl));
+        LUF_PHASE(ph_peel_build(g, s, lane, nl));
+        LUF_PHASE(parity ^= ph_peel_paths(g, s, lane, nl));
     }
     return parity;
 }

@@ -203,9 +203,8 @@ LUF_DEV void fw_dec_reset(const FwMacar& d, int lane, int nl) { ca_reset<false>(
 // decoder.decode(syndrome): steps = (rounds, 0) for UF, (tSV, tBP) for Macar
 LUF_DEV void fw_dec_decode(const FwUf& d, int& s0, int& s1, int lane, int nl)
 {
-    uint32_t any = 0;
-    LUF_PHASE(any |= ph_load(d.g, d.s, lane, nl));
-    s0 = uf_validate(d.g, d.s, d.flags, LUF_ANY(any), lane, nl);
+    LUF_PHASE(ph_load(d.g, d.s, lane, nl));
+    s0 = uf_validate(d.g, d.s, d.flags, lane, nl);
     s1 = 0;
     uf_peel(d.g, d.s, lane, nl);
 }

@@ -85,12 +85,11 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr)
     uint32_t off = 0;
     auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
     const uint32_t WE = words32(E), WD = words32(N - B) ? words32(N - B) : 1, WN = words32(N);
-    l.P = take(2u * N); l.NX = take(2u * N); l.R = take(2u * N);
+    l.P = take(2u * (N + 1)); l.R = take(2u * (N + 1));
     l.growth = take(4u * ((E + 15) / 16));
     l.newfull = take(4u * WE);
-    l.defect = take(4u * WD); l.act0 = take(4u * WD); l.act1 = take(4u * WD);
+    l.defect = take(4u * WD); l.touched = take(4u * WN);
     l.troot = take(4u * WN);
-    l.bdef = take(4u * (words32(B) ? words32(B) : 1));
     l.claim = take(4u * CLAIM_SLOTS);
     l.err = keep_err ? take(4u * WE) : 0;
     l.corr = keep_corr ? take(4u * WE) : 0;

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -62,9 +63,8 @@ __global__ void k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
         uint32_t parity = 0;
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
-        uint32_t any = 0;
-        LUF_PHASE(any |= ph_load(g, s, lane, nl));
-        uf_validate(g, s, flags, LUF_ANY(any), lane, nl);
+        LUF_PHASE(ph_load(g, s, lane, nl));
+        uf_validate(g, s, flags, lane, nl);
         parity ^= uf_peel(g, s, lane, nl);
         fails += LUF_XOR(parity) & 1u;
     }
@@ -85,9 +85,8 @@ __global__ void k_decode_uf(GraphView g, Layout l, int flags, long long nshots,
     for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(for (int w = lane; w < g.WD; w += nl) s.defect[w] = __ldg(&syn[k * g.WD + w]));
-        uint32_t any = 0;
-        LUF_PHASE(any |= ph_load(g, s, lane, nl));
-        const int rounds = uf_validate(g, s, flags, LUF_ANY(any), lane, nl);
+        LUF_PHASE(ph_load(g, s, lane, nl));
+        const int rounds = uf_validate(g, s, flags, lane, nl);
         if (growth2b)
             for (int w = lane; w < GW; w += nl) growth2b[k * GW + w] = s.growth[w];
         uf_peel(g, s, lane, nl);
@@ -322,6 +321,7 @@ struct luf_graph {
     size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
     long long launches = 0;
     std::mutex mu;
+    std::map<std::pair<const void*, uint32_t>, std::pair<int, int>> plans;   // (kernel, slice bytes) -> (warps per block, blocks per SM)
 };
 
 template <class T>
@@ -364,17 +364,27 @@ static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long n
     //                        rest of the 228 KB stays L1 for the graph tables
     static const int env_wpb = getenv("LUF_WARPS_PER_BLOCK") ? atoi(getenv("LUF_WARPS_PER_BLOCK")) : 0;
     static const int env_kb = getenv("LUF_SMEM_KB_PER_SM") ? atoi(getenv("LUF_SMEM_KB_PER_SM")) : 0;
-    int wpb = g->max_smem / (int)l.bytes;
-    const int want_wpb = env_wpb > 0 ? env_wpb : 4;
-    if (wpb > want_wpb) wpb = want_wpb;
+    // pick the block size that keeps the most warps (= shots) resident per SM (cached per kernel)
+    const int budget_kb = env_kb > 0 ? env_kb : 228;
+    int wpb = 1, per_sm = 1, best = 0;
+    const std::pair<const void*, uint32_t> key((const void*)kernel, slice_bytes);
+    auto hit = g->plans.find(key);
+    if (hit != g->plans.end()) { wpb = hit->second.first; per_sm = hit->second.second; best = wpb * per_sm; }
+    else for (int cand = 1; cand <= 32; ++cand) {
+        if (env_wpb > 0 && cand != env_wpb) continue;
+        const size_t sm = (size_t)cand * l.bytes;
+        if (sm > (size_t)g->max_smem) break;
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, cand * WARP, sm));
+        const int by_budget = (int)((size_t)budget_kb * 1024 / (sm + 1024));
+        if (occ > by_budget) occ = by_budget;
+        if (occ * cand > best) { best = occ * cand; wpb = cand; per_sm = occ; }
+    }
+    if (best == 0) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    g->plans[key] = std::make_pair(wpb, per_sm);
     const size_t smem = (size_t)wpb * l.bytes;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * WARP, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int budget_kb = env_kb > 0 ? env_kb : 228;
-    const int by_budget = (int)((size_t)budget_kb * 1024 / (smem + 1024));
-    if (by_budget >= 1 && per_sm > by_budget) per_sm = by_budget;
     {   // ask for just enough shared memory for per_sm blocks, leave the rest to L1
         int pct = (int)(((smem + 1024) * per_sm * 100 + 228 * 1024 - 1) / (228 * 1024));
         if (pct > 100) pct = 100;

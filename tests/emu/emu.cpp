@@ -47,9 +47,8 @@ int emu_decode_uf(const luf_graph_desc* d, int flags, long long nshots, const ui
     for (long long k = 0; k < nshots; ++k) {
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         for (int w = 0; w < g.WD; ++w) s.defect[w] = syn[k * g.WD + w];
-        uint32_t any = 0;
-        LUF_PHASE(any |= ph_load(g, s, lane, nl));
-        const int rounds = uf_validate(g, s, flags, any, 0, nl);
+        LUF_PHASE(ph_load(g, s, lane, nl));
+        const int rounds = uf_validate(g, s, flags, 0, nl);
         if (growth2b) export_growth(g, s, growth2b + k * GW);
         uf_peel(g, s, 0, nl);
         std::memcpy(corr + k * g.WE, s.corr, 4u * g.WE);
@@ -79,9 +78,8 @@ int emu_mc_uf(const luf_graph_desc* d, int flags, const double* class_p, unsigne
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + k, lane, nl));
         if (err_out) std::memcpy(err_out + k * g.WE, s.err, 4u * g.WE);
         if (syn_out) std::memcpy(syn_out + k * g.WD, s.defect, 4u * g.WD);
-        uint32_t any = 0;
-        LUF_PHASE(any |= ph_load(g, s, lane, nl));
-        uf_validate(g, s, flags, any, 0, nl);
+        LUF_PHASE(ph_load(g, s, lane, nl));
+        uf_validate(g, s, flags, 0, nl);
         parity ^= uf_peel(g, s, 0, nl);
         if (corr_out) std::memcpy(corr_out + k * g.WE, s.corr, 4u * g.WE);
         fails += parity & 1u;
