@@ -69,6 +69,11 @@ static const uint32_t NONE16 = 0xFFFFu;
 static const uint32_t TREE_ROOT = 0xFFFEu;
 static const int MAX_CLASSES = 32;
 static const int CLAIM_SLOTS = 128;      // power of two
+#ifndef LUF_LIST_CAP
+  #define LUF_LIST_CAP 128
+#endif
+static const uint32_t LIST_CAP = LUF_LIST_CAP;   // work-list capacity (tests shrink it to force the overflow paths)
+static const uint32_t LIST_DONE = 0xFFFFFFFFu;
 
 enum { G_UNGROWN = 0, G_HALF = 1, G_FULL = 2, G_BURNT = 3 };
 enum { FLAG_DYNAMIC = 1, FLAG_WEST = 2 };
@@ -105,12 +110,13 @@ struct Layout {
     uint32_t troot;                     // uint32[WN]  tree roots to peel from
     uint32_t err, corr;                 // uint32[WE]  only in the staged kernels (0 = absent)
     uint32_t claim;                     // uint32[CLAIM_SLOTS]  merge reservations (see ph_merge_claim)
+    uint32_t list, cnt;                 // uint32[LIST_CAP] work list shared by the phases that balance work over lanes; uint32[4] its fill counter
     uint32_t bytes;                     // slice size, multiple of 16
 };
 
 struct Shot {
     idx_t *P, *R;
-    uint32_t *growth, *newfull, *defect, *touched, *troot, *err, *corr, *claim;
+    uint32_t *growth, *newfull, *defect, *touched, *troot, *err, *corr, *claim, *list, *cnt;
 };
 
 LUF_DEV Shot bind(const Layout& l, unsigned char* base)
@@ -123,6 +129,7 @@ LUF_DEV Shot bind(const Layout& l, unsigned char* base)
     s.err = l.err ? (uint32_t*)(base + l.err) : 0;
     s.corr = l.corr ? (uint32_t*)(base + l.corr) : 0;
     s.claim = (uint32_t*)(base + l.claim);
+    s.list = (uint32_t*)(base + l.list); s.cnt = (uint32_t*)(base + l.cnt);
     return s;
 }
 
@@ -169,6 +176,7 @@ LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int la
     for (int w = lane; w < g.WD; w += nl) s.defect[w] = 0;
     for (int w = lane; w < g.WN; w += nl) { s.troot[w] = 0; s.touched[w] = 0; }
     for (int w = lane; w < CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu;
+    if (lane < 4) s.cnt[lane] = 0;
     (void)l;
 }
 
@@ -305,9 +313,29 @@ LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
 // vision once: only its first endpoint adds.  Two different active clusters
 // each add 1.  The 2-bit counters saturate at FULL.  Returns whether this lane
 // saw an active node.
-LUF_DEV uint32_t ph_grow(const GraphView& g, const Shot& s, int lane, int nl)
+LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r)
 {
-    uint32_t any = 0;
+    const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
+    for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
+        const uint32_t ent = LUF_LDG(&g.inc[k]);
+        const uint32_t e = ent & 0xFFFFu;
+        const uint32_t sh = (e & 15u) * 2u;
+        if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
+        if (!(ent >> 31)) {                       // second endpoint: skip if same cluster
+            const uint32_t o = (ent >> 16) & 0x7FFFu;
+            if (o == r || find_ro(s, o) == r) continue;
+        }
+        const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+        if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
+        else if (old == G_HALF) luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
+    }
+}
+
+// Gather the active nodes into the work list (cheap per touched node), so that
+// the edge loops of ph_grow_exec are spread evenly over the lanes however the
+// defects are distributed over the bitmap words.
+LUF_DEV void ph_grow_gather(const GraphView& g, const Shot& s, int lane, int nl)
+{
     for (int w = lane; w < g.WN; w += nl) {
         uint32_t bits = s.touched[w];
         while (bits) {
@@ -315,24 +343,23 @@ LUF_DEV uint32_t ph_grow(const GraphView& g, const Shot& s, int lane, int nl)
             const uint32_t u = (uint32_t)(32 * w + b);
             const uint32_t r = find_ro(s, u);
             if (s.R[r] != ODD_BIT) continue;
-            any = 1;
-            const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
-            for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
-                const uint32_t ent = LUF_LDG(&g.inc[k]);
-                const uint32_t e = ent & 0xFFFFu;
-                const uint32_t sh = (e & 15u) * 2u;
-                if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
-                if (!(ent >> 31)) {                       // second endpoint: skip if same cluster
-                    const uint32_t o = (ent >> 16) & 0x7FFFu;
-                    if (o == r || find_ro(s, o) == r) continue;
-                }
-                const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-                if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
-                else if (old == G_HALF) luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
-            }
+            const uint32_t idx = luf_atomic_add(&s.cnt[0], 1u);
+            if (idx < LIST_CAP) s.list[idx] = u | (r << 16);
+            else grow_node(g, s, u, r);
         }
     }
-    return any;
+}
+
+// Returns whether any node was active this round.
+LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    const uint32_t total = s.cnt[0];
+    const uint32_t n = total < LIST_CAP ? total : LIST_CAP;
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
+        const uint32_t it = s.list[i];
+        grow_node(g, s, it & 0xFFFFu, it >> 16);
+    }
+    return total;
 }
 
 // ------------------------------------------------------------ phase 2b: merge
@@ -417,9 +444,53 @@ LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uin
 }
 
 // What the first reservation round could not place (stars around one defect,
-// chains, hash collisions) is merged by one lane in ascending edge id, with
-// path compression.  `mask` tells it which of the 32 words from `base` on
-// still hold edges.
+// chains, hash collisions) continues as further reservation rounds over a
+// compact work list, one pending edge per lane: the lowest-id pending edge of
+// every cluster wins each round, so a star of k edges takes k rounds, all
+// stars side by side.
+LUF_DEV void ph_rest_gather(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    for (int w = lane; w < g.WE; w += nl) {
+        uint32_t bits = s.newfull[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t idx = luf_atomic_add(&s.cnt[1], 1u);
+            if (idx < LIST_CAP) s.list[idx] = (uint32_t)(32 * w + b);
+        }
+    }
+}
+
+LUF_DEV void ph_rest_claim(const GraphView& g, const Shot& s, uint32_t n, uint32_t tag, int lane, int nl)
+{
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
+        const uint32_t e = s.list[i];
+        if (e == LIST_DONE) continue;
+        const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+        const uint32_t cu = find_ro(s, uv & 0xFFFFu), cv = find_ro(s, uv >> 16);
+        luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
+        luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
+    }
+}
+
+LUF_DEV uint32_t ph_rest_exec(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, int lane, int nl)
+{
+    uint32_t pending = 0;
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
+        const uint32_t e = s.list[i];
+        if (e == LIST_DONE) continue;
+        const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+        const uint32_t cu = find_ro(s, uv & 0xFFFFu), cv = find_ro(s, uv >> 16);
+        if (s.claim[claim_slot(cu)] == (tag | e) && s.claim[claim_slot(cv)] == (tag | e)) {
+            union_roots(g, s, flags, e, cu, cv);
+            s.list[i] = LIST_DONE;
+        } else pending = 1;
+    }
+    return pending;
+}
+
+// Overflow path (more pending edges than the list holds): one lane merges them
+// in ascending edge id, with path compression.  `mask` tells it which of the
+// 32 words from `base` on still hold edges.
 LUF_DEV void merge_rest(const GraphView& g, const Shot& s, int flags, int base, uint32_t mask)
 {
     while (mask) {
@@ -481,43 +552,62 @@ LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int 
 
 // The union-find arrays are dead now; reuse them for the traversal:
 //   P -> tree edge towards the root (NONE16 = undiscovered)    R -> link of the LIFO stack
-LUF_DEV void ph_peel_init(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    uint32_t* P2 = (uint32_t*)s.P;
-    for (int v = lane; 2 * v < g.N; v += nl) P2[v] = 0xFFFFFFFFu;
-}
-
 // uf.py:326-344: the reference's LIFO traversal (neighbours in ascending edge
-// id) from every tree root; one lane per root.  Only the tree (the edge towards
-// the root of every discovered node) is kept.
-LUF_DEV void ph_peel_build(const GraphView& g, const Shot& s, int lane, int nl)
+// id) from a tree root; only the tree (the edge towards the root of every
+// discovered node) is kept.
+LUF_DEV void build_tree(const GraphView& g, const Shot& s, uint32_t root)
 {
     idx_t* tedge = s.P; idx_t* stk = s.R;
-    for (int w = lane; w < g.WN; w += nl) {
-        uint32_t bits = s.troot[w];
-        s.troot[w] = 0;
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t root = (uint32_t)(32 * w + b);
-            tedge[root] = (idx_t)TREE_ROOT;
-            stk[root] = (idx_t)NONE16;
-            uint32_t top = root;
-            while (top != NONE16) {
-                const uint32_t u = top;
-                top = stk[u];
-                const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
-                for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
-                    const uint32_t ent = LUF_LDG(&g.inc[k]);
-                    const uint32_t e = ent & 0xFFFFu;
-                    if (growth_of(s, e) != G_FULL) continue;
-                    const uint32_t o = (ent >> 16) & 0x7FFFu;
-                    if (tedge[o] != NONE16) continue;
-                    tedge[o] = (idx_t)e;
-                    stk[o] = (idx_t)top; top = o;
-                }
-            }
+    tedge[root] = (idx_t)TREE_ROOT;
+    stk[root] = (idx_t)NONE16;
+    uint32_t top = root;
+    while (top != NONE16) {
+        const uint32_t u = top;
+        top = stk[u];
+        const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
+        for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
+            const uint32_t ent = LUF_LDG(&g.inc[k]);
+            const uint32_t e = ent & 0xFFFFu;
+            if (growth_of(s, e) != G_FULL) continue;
+            const uint32_t o = (ent >> 16) & 0x7FFFu;
+            if (tedge[o] != NONE16) continue;
+            tedge[o] = (idx_t)e;
+            stk[o] = (idx_t)top; top = o;
         }
     }
+}
+
+// one lane per tree root, roots handed out through the work list
+LUF_DEV void ph_peel_gather(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    uint32_t* P2 = (uint32_t*)s.P;
+    for (int v = lane; 2 * v < g.N; v += nl) P2[v] = 0xFFFFFFFFu;        // every node undiscovered
+    for (int w = lane; w < g.WN; w += nl) {
+        uint32_t bits = s.troot[w], keep = 0;
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t idx = luf_atomic_add(&s.cnt[2], 1u);
+            if (idx < LIST_CAP) s.list[idx] = (uint32_t)(32 * w + b);
+            else keep |= 1u << b;                                        // overflow: stays in the bitmap
+        }
+        s.troot[w] = keep;
+    }
+}
+
+LUF_DEV void ph_peel_build(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    const uint32_t total = s.cnt[2];
+    const uint32_t n = total < LIST_CAP ? total : LIST_CAP;
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) build_tree(g, s, s.list[i]);
+    if (total > LIST_CAP)                                              // overflow roots, by bitmap word
+        for (int w = lane; w < g.WN; w += nl) {
+            uint32_t bits = s.troot[w];
+            s.troot[w] = 0;
+            while (bits) {
+                const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+                build_tree(g, s, (uint32_t)(32 * w + b));
+            }
+        }
 }
 
 // uf.py:305-312: peeling the forest leaf-up puts a tree edge in the correction
@@ -559,15 +649,27 @@ LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, 
     (void)lane;
     for (;;) {
         uint32_t active = 0;
-        LUF_PHASE(active |= ph_grow(g, s, lane, nl));
+        LUF_PHASE(ph_grow_gather(g, s, lane, nl));
+        LUF_PHASE(active |= ph_grow_exec(g, s, lane, nl));
         if (!LUF_ANY(active)) break;
-        {   // one parallel reservation round places the independent merges ...
-            const uint32_t tag = iter << 16;
-            --iter;
-            uint32_t pending = 0;
-            LUF_PHASE(ph_merge_claim(g, s, tag, lane, nl));
-            LUF_PHASE(pending |= ph_merge_exec(g, s, flags, tag, lane, nl));
-            if (LUF_ANY(pending)) {          // ... one lane finishes the rest in order
+        // one reservation round over the bitmap places the independent merges ...
+        uint32_t tag = iter-- << 16, pending = 0;
+        LUF_PHASE(ph_merge_claim(g, s, tag, lane, nl); if (lane == 0) s.cnt[0] = 0);
+        LUF_PHASE(pending |= ph_merge_exec(g, s, flags, tag, lane, nl));
+        if (LUF_ANY(pending)) {              // ... the rest goes on over a compact list
+            LUF_PHASE(ph_rest_gather(g, s, lane, nl));
+            uint32_t n = 0;
+            LUF_PHASE(n = s.cnt[1]);
+            if (n <= LIST_CAP) {
+                LUF_PHASE(for (int w = lane; w < g.WE; w += nl) s.newfull[w] = 0; if (lane == 0) s.cnt[1] = 0);
+                for (uint32_t guard = 0; guard <= n; ++guard) {       // at least one edge is placed per round
+                    tag = iter-- << 16; pending = 0;
+                    LUF_PHASE(ph_rest_claim(g, s, n, tag, lane, nl));
+                    LUF_PHASE(pending |= ph_rest_exec(g, s, flags, n, tag, lane, nl));
+                    if (!LUF_ANY(pending)) break;
+                }
+            } else {                         // overflow: one lane, ascending edge id
+                LUF_PHASE(if (lane == 0) s.cnt[1] = 0);
                 for (int base = 0; base < g.WE; base += 32) {
                     uint32_t mask;
                     LUF_BALLOT(mask, base + lane < g.WE && s.newfull[base + lane] != 0);
@@ -577,6 +679,7 @@ LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, 
         }
         ++rounds;
     }
+    LUF_PHASE(if (lane == 0) s.cnt[0] = 0);
     return rounds;
 }
 
@@ -588,9 +691,9 @@ LUF_DEV uint32_t uf_peel(const GraphView& g, const Shot& s, int lane, int nl)
     (void)lane;
     LUF_PHASE(const uint32_t r = ph_tree_roots(g, s, lane, nl); parity ^= r & 1u; general |= r >> 1);
     if (LUF_ANY(general)) {
-        LUF_PHASE(ph_peel_init(g, s, lane, nl));
+        LUF_PHASE(ph_peel_gather(g, s, lane, nl));
         LUF_PHASE(ph_peel_build(g, s, lane, nl));
-        LUF_PHASE(parity ^= ph_peel_paths(g, s, lane, nl));
+        LUF_PHASE(parity ^= ph_peel_paths(g, s, lane, nl); if (lane == 0) s.cnt[2] = 0);
     }
     return parity;
 }

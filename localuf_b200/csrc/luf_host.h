@@ -91,6 +91,7 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr)
     l.defect = take(4u * WD); l.touched = take(4u * WN);
     l.troot = take(4u * WN);
     l.claim = take(4u * CLAIM_SLOTS);
+    l.list = take(4u * LIST_CAP); l.cnt = take(16);
     l.err = keep_err ? take(4u * WE) : 0;
     l.corr = keep_corr ? take(4u * WE) : 0;
     l.bytes = off;

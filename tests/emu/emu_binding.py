@@ -15,15 +15,20 @@ SRCS = [os.path.join(HERE, 'emu.cpp')] + [
 ] + [os.path.join(ROOT, 'include', 'luf_b200.h')]
 
 
-def build():
-    if (not os.path.exists(LIB)) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRCS):
-        os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.run(['g++', '-O1', '-g', '-fPIC', '-shared', '-std=c++17', '-Wall', '-Wextra',
-                        '-o', LIB, SRCS[0]], check=True, capture_output=True)
-    return LIB
+def build(tiny_lists=False):
+    """``tiny_lists``: a second build whose in-kernel work lists hold 3 entries, so that
+    every overflow path of the kernel phases runs on ordinary test inputs."""
+    out = LIB.replace('.so', '_tiny.so') if tiny_lists else LIB
+    if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in SRCS):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(['g++', '-O1', '-g', '-fPIC', '-shared', '-std=c++17', '-Wall', '-Wextra']
+                       + (['-DLUF_LIST_CAP=3'] if tiny_lists else []) + ['-o', out, SRCS[0]],
+                       check=True, capture_output=True)
+    return out
 
 
 _lib = None
+_libs = {}
 
 
 def lib():
@@ -31,6 +36,12 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
     return _lib
+
+
+def use_tiny_lists(on: bool):
+    """Switch the library the bindings call (tests only)."""
+    global _lib
+    _lib = _libs.setdefault(on, C.CDLL(build(tiny_lists=on)))
 
 
 def _vp(a):

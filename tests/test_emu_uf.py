@@ -94,3 +94,21 @@ def test_emu_decode_random_syndromes_vs_oracle(spec):
         np.testing.assert_array_equal(unpack_growth(growth2b, g.n_edges), ogrowth)
         np.testing.assert_array_equal(steps[:, 0], osteps[:, 0])
         np.testing.assert_array_equal(corr, ocorr)
+
+
+def test_emu_overflow_paths_with_tiny_work_lists():
+    """Same goldens through a build whose work lists hold 3 entries: the in-place
+    growth of overflowing active nodes, the serial ascending-order merge and the
+    bitmap fallback of the tree roots all run."""
+    emu_binding.use_tiny_lists(True)
+    try:
+        for name in ('uf_sf9_cc_p10', 'uf_sf7_cc_p25', 'uf_sf5_phen_p08', 'uf_sf5_cl_p03', 'uf_sf4_cl_fwd_p03'):
+            meta, arr = load_golden(name)
+            emu = emu_binding.Emu(make_code(meta['spec']))
+            for variant, flags in FLAGS.items():
+                corr, growth2b, steps = emu.decode_uf(flags, arr['syn_bits'])
+                np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{variant}_growth'])
+                np.testing.assert_array_equal(steps[:, 0], arr[f'{variant}_rounds'])
+                np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
+    finally:
+        emu_binding.use_tiny_lists(False)
