@@ -70,7 +70,7 @@ static const uint32_t TREE_ROOT = 0xFFFEu;
 static const int MAX_CLASSES = 32;
 static const int CLAIM_SLOTS = 128;      // power of two
 #ifndef LUF_LIST_CAP
-  #define LUF_LIST_CAP 128
+  #define LUF_LIST_CAP 112
 #endif
 static const uint32_t LIST_CAP = LUF_LIST_CAP;   // work-list capacity (tests shrink it to force the overflow paths)
 static const uint32_t LIST_DONE = 0xFFFFFFFFu;
@@ -107,7 +107,8 @@ struct Layout {
     uint32_t newfull;                   // uint32[WE]  edges that reached FULL this round
     uint32_t defect;                    // uint32[WD]
     uint32_t touched;                   // uint32[WN]  nodes that are a defect or belong to a cluster of size > 1
-    uint32_t troot;                     // uint32[WN]  tree roots to peel from
+    uint32_t troot;                     // uint32[WN]  tree roots to peel from (aliases newfull, which is idle by then)
+    uint32_t deg;                       // uint32[ceil(N/16)]  per node: has >= 1 / >= 2 fully grown incident edges
     uint32_t err, corr;                 // uint32[WE]  only in the staged kernels (0 = absent)
     uint32_t claim;                     // uint32[CLAIM_SLOTS]  merge reservations (see ph_merge_claim)
     uint32_t list, cnt;                 // uint32[LIST_CAP] work list shared by the phases that balance work over lanes; uint32[4] its fill counter
@@ -116,7 +117,7 @@ struct Layout {
 
 struct Shot {
     idx_t *P, *R;
-    uint32_t *growth, *newfull, *defect, *touched, *troot, *err, *corr, *claim, *list, *cnt;
+    uint32_t *growth, *newfull, *defect, *touched, *troot, *deg, *err, *corr, *claim, *list, *cnt;
 };
 
 LUF_DEV Shot bind(const Layout& l, unsigned char* base)
@@ -125,7 +126,7 @@ LUF_DEV Shot bind(const Layout& l, unsigned char* base)
     s.P = (idx_t*)(base + l.P); s.R = (idx_t*)(base + l.R);
     s.growth = (uint32_t*)(base + l.growth); s.newfull = (uint32_t*)(base + l.newfull);
     s.defect = (uint32_t*)(base + l.defect); s.touched = (uint32_t*)(base + l.touched);
-    s.troot = (uint32_t*)(base + l.troot);
+    s.troot = (uint32_t*)(base + l.troot); s.deg = (uint32_t*)(base + l.deg);
     s.err = l.err ? (uint32_t*)(base + l.err) : 0;
     s.corr = l.corr ? (uint32_t*)(base + l.corr) : 0;
     s.claim = (uint32_t*)(base + l.claim);
@@ -175,6 +176,7 @@ LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int la
     }
     for (int w = lane; w < g.WD; w += nl) s.defect[w] = 0;
     for (int w = lane; w < g.WN; w += nl) { s.troot[w] = 0; s.touched[w] = 0; }
+    for (int w = lane; w < ((g.N + 15) >> 4); w += nl) s.deg[w] = 0;
     for (int w = lane; w < CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu;
     if (lane < 4) s.cnt[lane] = 0;
     (void)l;
@@ -313,6 +315,15 @@ LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
 // vision once: only its first endpoint adds.  Two different active clusters
 // each add 1.  The 2-bit counters saturate at FULL.  Returns whether this lane
 // saw an active node.
+// Two flag bits per node: "has a fully grown incident edge" / "has at least
+// two".  Set with atomicOr only, so concurrent lanes cannot overflow a field.
+LUF_DEV void deg_bump(const Shot& s, uint32_t v)
+{
+    const uint32_t sh = (v & 15u) * 2u;
+    if ((luf_atomic_or(&s.deg[v >> 4], 1u << sh) >> sh) & 1u) luf_atomic_or(&s.deg[v >> 4], 2u << sh);
+}
+LUF_DEV bool deg_is_one(const Shot& s, uint32_t v) { return ((s.deg[v >> 4] >> ((v & 15u) * 2u)) & 3u) == 1u; }
+
 LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r)
 {
     const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
@@ -327,7 +338,10 @@ LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r
         }
         const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
         if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
-        else if (old == G_HALF) luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
+        else if (old == G_HALF) {                                           // newly FULL
+            luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
+            deg_bump(s, u); deg_bump(s, (ent >> 16) & 0x7FFFu);
+        }
     }
 }
 
@@ -463,12 +477,14 @@ LUF_DEV void ph_rest_gather(const GraphView& g, const Shot& s, int lane, int nl)
 LUF_DEV void ph_rest_claim(const GraphView& g, const Shot& s, uint32_t n, uint32_t tag, int lane, int nl)
 {
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t e = s.list[i];
-        if (e == LIST_DONE) continue;
+        const uint32_t it = s.list[i];
+        if (it == LIST_DONE) continue;
+        const uint32_t e = it & 0xFFFFu;
         const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
         const uint32_t cu = find_ro(s, uv & 0xFFFFu), cv = find_ro(s, uv >> 16);
         luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
         luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
+        s.list[i] = e | (cu << 16);           // the root of the first endpoint cannot change before this edge runs
     }
 }
 
@@ -476,11 +492,12 @@ LUF_DEV uint32_t ph_rest_exec(const GraphView& g, const Shot& s, int flags, uint
 {
     uint32_t pending = 0;
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t e = s.list[i];
-        if (e == LIST_DONE) continue;
-        const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-        const uint32_t cu = find_ro(s, uv & 0xFFFFu), cv = find_ro(s, uv >> 16);
-        if (s.claim[claim_slot(cu)] == (tag | e) && s.claim[claim_slot(cv)] == (tag | e)) {
+        const uint32_t it = s.list[i];
+        if (it == LIST_DONE) continue;
+        const uint32_t e = it & 0xFFFFu, cu = it >> 16;
+        if (s.claim[claim_slot(cu)] != (tag | e)) { pending = 1; continue; }
+        const uint32_t cv = find_ro(s, LUF_LDG(&g.edge_uv[e]) >> 16);
+        if (s.claim[claim_slot(cv)] == (tag | e)) {
             union_roots(g, s, flags, e, cu, cv);
             s.list[i] = LIST_DONE;
         } else pending = 1;
@@ -572,6 +589,7 @@ LUF_DEV void build_tree(const GraphView& g, const Shot& s, uint32_t root)
             const uint32_t o = (ent >> 16) & 0x7FFFu;
             if (tedge[o] != NONE16) continue;
             tedge[o] = (idx_t)e;
+            if (deg_is_one(s, o)) continue;       // a leaf: nothing to discover from it
             stk[o] = (idx_t)top; top = o;
         }
     }

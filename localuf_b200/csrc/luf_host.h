@@ -87,9 +87,10 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr)
     const uint32_t WE = words32(E), WD = words32(N - B) ? words32(N - B) : 1, WN = words32(N);
     l.P = take(2u * (N + 1)); l.R = take(2u * (N + 1));
     l.growth = take(4u * ((E + 15) / 16));
-    l.newfull = take(4u * WE);
+    l.newfull = take(4u * (WE > WN ? WE : WN));
+    l.troot = l.newfull;                              // the peel runs after the last merge round
     l.defect = take(4u * WD); l.touched = take(4u * WN);
-    l.troot = take(4u * WN);
+    l.deg = take(4u * ((N + 15) / 16));
     l.claim = take(4u * CLAIM_SLOTS);
     l.list = take(4u * LIST_CAP); l.cnt = take(16);
     l.err = keep_err ? take(4u * WE) : 0;
