@@ -251,7 +251,9 @@ def run_ours(args):
                              'the fused kernel reads only ~50 KB of graph tables from HBM',
                        'failures': fails, 'failure_rate': fails / shots, 'wall_s_timed_region': t_wall},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None, 'kernel': 'k_mc_uf',
+                         'frac': achieved / peak, 'traffic': 88576, 'kernel': 'k_mc_uf',
+                         'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of one k_mc_uf launch '
+                                         '(ncu --set full, profiles/r01_v5_k_mc_uf_summary.txt): graph tables only',
                          'algorithmic_bytes_per_shot': bps, 'peak_source': peak_src,
                          'note': 'fused kernel keeps a shot in shared memory: the HBM fraction is low by '
                                  'construction; the kernel is bound by shared-memory latency (see profiles/)'},

@@ -70,7 +70,7 @@ static const uint32_t TREE_ROOT = 0xFFFEu;
 static const int MAX_CLASSES = 32;
 static const int CLAIM_SLOTS = 128;      // power of two
 #ifndef LUF_LIST_CAP
-  #define LUF_LIST_CAP 112
+  #define LUF_LIST_CAP 80
 #endif
 static const uint32_t LIST_CAP = LUF_LIST_CAP;   // work-list capacity (tests shrink it to force the overflow paths)
 static const uint32_t LIST_DONE = 0xFFFFFFFFu;
@@ -143,6 +143,21 @@ LUF_DEV uint32_t find_ro(const Shot& s, uint32_t v)
     uint32_t p;
     while (!((p = s.P[v]) & ROOT_BIT)) v = p;
     return v;
+}
+
+// find that also shortcuts the start node to the root it found.  Safe next to
+// concurrent finds and unions of other lanes: a non-root node never becomes a
+// root again and the value written is one of its ancestors (16-bit stores are
+// atomic), so every interleaving leaves a valid forest with the same roots.
+LUF_DEV uint32_t find_pc(const Shot& s, uint32_t v)
+{
+    uint32_t p = s.P[v];
+    if (p & ROOT_BIT) return v;
+    uint32_t r = p, q;
+    int hops = 0;
+    while (!((q = s.P[r]) & ROOT_BIT)) { r = q; ++hops; }
+    if (hops) s.P[v] = (idx_t)r;
+    return r;
 }
 
 // uf.py:247-254 -- find with full path compression (single lane only)
@@ -355,7 +370,7 @@ LUF_DEV void ph_grow_gather(const GraphView& g, const Shot& s, int lane, int nl)
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             const uint32_t u = (uint32_t)(32 * w + b);
-            const uint32_t r = find_ro(s, u);
+            const uint32_t r = find_pc(s, u);
             if (s.R[r] != ODD_BIT) continue;
             const uint32_t idx = luf_atomic_add(&s.cnt[0], 1u);
             if (idx < LIST_CAP) s.list[idx] = u | (r << 16);
@@ -427,7 +442,7 @@ LUF_DEV void ph_merge_claim(const GraphView& g, const Shot& s, uint32_t tag, int
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             const uint32_t e = (uint32_t)(32 * w + b);
             const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-            const uint32_t cu = find_ro(s, uv & 0xFFFFu), cv = find_ro(s, uv >> 16);
+            const uint32_t cu = find_pc(s, uv & 0xFFFFu), cv = find_pc(s, uv >> 16);
             luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
             luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
         }
@@ -481,7 +496,7 @@ LUF_DEV void ph_rest_claim(const GraphView& g, const Shot& s, uint32_t n, uint32
         if (it == LIST_DONE) continue;
         const uint32_t e = it & 0xFFFFu;
         const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-        const uint32_t cu = find_ro(s, uv & 0xFFFFu), cv = find_ro(s, uv >> 16);
+        const uint32_t cu = find_pc(s, uv & 0xFFFFu), cv = find_pc(s, uv >> 16);
         luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
         luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
         s.list[i] = e | (cu << 16);           // the root of the first endpoint cannot change before this edge runs

@@ -51,7 +51,7 @@ __device__ __forceinline__ unsigned char* warp_slice(const Layout& l)
 }
 
 // Fused K1 + K2 + K4 for the UF decoder, batch scheme (_schemes.py:116-155).
-__global__ void k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
+__global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
                         unsigned long long shot0, long long nshots, unsigned long long* counts)
 {
     const int lane = threadIdx.x & 31, nl = WARP;
@@ -352,7 +352,7 @@ struct LaunchCfg { int grid, block; size_t smem; };
 // Warps per block and a persistent grid: as many blocks per SM as the
 // shared-memory budget allows, never more blocks than there is work.
 template <class K>
-static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long nshots, LaunchCfg* cfg)
+static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long nshots, LaunchCfg* cfg, int max_wpb = 32)
 {
     struct { uint32_t bytes; } l = {slice_bytes};
     if (l.bytes > (uint32_t)g->max_smem)
@@ -370,7 +370,7 @@ static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long n
     const std::pair<const void*, uint32_t> key((const void*)kernel, slice_bytes);
     auto hit = g->plans.find(key);
     if (hit != g->plans.end()) { wpb = hit->second.first; per_sm = hit->second.second; best = wpb * per_sm; }
-    else for (int cand = 1; cand <= 32; ++cand) {
+    else for (int cand = 1; cand <= max_wpb; ++cand) {
         if (env_wpb > 0 && cand != env_wpb) continue;
         const size_t sm = (size_t)cand * l.bytes;
         if (sm > (size_t)g->max_smem) break;
@@ -379,9 +379,11 @@ static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long n
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, cand * WARP, sm));
         const int by_budget = (int)((size_t)budget_kb * 1024 / (sm + 1024));
         if (occ > by_budget) occ = by_budget;
-        if (occ * cand > best) { best = occ * cand; wpb = cand; per_sm = occ; }
+        if (occ * cand >= best && occ > 0) { best = occ * cand; wpb = cand; per_sm = occ; }   // ties: fewer, larger blocks
     }
     if (best == 0) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    if (hit == g->plans.end() && getenv("LUF_DEBUG_PLAN"))
+        fprintf(stderr, "[luf] launch plan: %u B per shot, %d warps per block, %d blocks per SM\n", slice_bytes, wpb, per_sm);
     g->plans[key] = std::make_pair(wpb, per_sm);
     const size_t smem = (size_t)wpb * l.bytes;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -783,7 +785,7 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
         k_mc_ca<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_actis, sp, flags,
                                                                           shot0, nshots, counts_dev);
     } else {
-        if (int rc = plan_launch(g, k_mc_uf, g->lay_fused.bytes, nshots, &c)) return rc;
+        if (int rc = plan_launch(g, k_mc_uf, g->lay_fused.bytes, nshots, &c, 14)) return rc;
         k_mc_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, shot0, nshots, counts_dev);
     }
     CUDA_TRY(cudaGetLastError());
