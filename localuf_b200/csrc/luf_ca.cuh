@@ -44,6 +44,7 @@ struct CaLayout {
     uint32_t rx_anyon, rx_defect;   // u32[WN] cumulative toggles received from neighbours
     uint32_t rx_busy, rx_active;    // u32[2*WN] Actis signals received, double-buffered by timestep parity
     uint32_t defect, err, corr; // u32[WD] / u32[WE] / u32[WE]
+    uint32_t touched;           // u32[WN]  Macar: nodes that are a defect or touch a fully grown edge (the only ones that can act)
     uint32_t glob;              // u32[4]  Actis collection-level next_busy_signal / next_active_signal
     uint32_t bytes;
 };
@@ -51,7 +52,7 @@ struct CaLayout {
 struct CaShot {
     uint16_t *cid, *ncid;
     uint8_t *ptr, *fl, *ast, *cnt;
-    uint32_t *growth, *gacc, *rx_anyon, *rx_defect, *rx_busy, *rx_active, *defect, *err, *corr, *glob;
+    uint32_t *growth, *gacc, *rx_anyon, *rx_defect, *rx_busy, *rx_active, *defect, *err, *corr, *glob, *touched;
 };
 
 LUF_DEV CaShot ca_bind(const CaLayout& l, unsigned char* b)
@@ -66,6 +67,7 @@ LUF_DEV CaShot ca_bind(const CaLayout& l, unsigned char* b)
     s.err = l.err ? (uint32_t*)(b + l.err) : 0;
     s.corr = (uint32_t*)(b + l.corr);
     s.glob = (uint32_t*)(b + l.glob);
+    s.touched = (uint32_t*)(b + l.touched);
     return s;
 }
 
@@ -91,7 +93,7 @@ LUF_DEV void ca_reset(const CaView& g, const CaShot& s, int lane, int nl)
     }
     for (int w = lane; w < g.GW; w += nl) { s.growth[w] = 0; s.gacc[w] = 0; }
     for (int w = lane; w < g.WN; w += nl) {
-        s.rx_anyon[w] = 0; s.rx_defect[w] = 0;
+        s.rx_anyon[w] = 0; s.rx_defect[w] = 0; s.touched[w] = 0;
         if (ACTIS) { s.rx_busy[w] = 0; s.rx_busy[g.WN + w] = 0; s.rx_active[w] = 0; s.rx_active[g.WN + w] = 0; }
     }
     for (int w = lane; w < g.WE; w += nl) { s.corr[w] = 0; if (s.err) s.err[w] = 0; }
@@ -106,7 +108,9 @@ LUF_DEV void ca_load(const CaView& g, const CaShot& s, int lane, int nl)
         uint32_t bits = s.defect[w];
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            s.fl[g.B + 32 * w + b] = (uint8_t)(FL_DEFECT | FL_ACTIVE | FL_ANYON);
+            const uint32_t v = (uint32_t)(g.B + 32 * w + b);
+            s.fl[v] = (uint8_t)(FL_DEFECT | FL_ACTIVE | FL_ANYON);
+            luf_atomic_or(&s.touched[v >> 5], 1u << (v & 31u));
         }
     }
 }
@@ -122,7 +126,31 @@ LUF_DEV void ca_growing(const CaView& g, const CaShot& s, int v)
         if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
         const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
         if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);
+        else if (old == G_HALF) {                                   // newly FULL: both ends can act from now on
+            const uint32_t o = ent >> 16;
+            luf_atomic_or(&s.touched[v >> 5], 1u << (v & 31));
+            luf_atomic_or(&s.touched[o >> 5], 1u << (o & 31u));
+        }
     }
+}
+
+// Macar only ever has work at touched nodes: an untouched node has no defect,
+// no anyon, is inactive and sees no fully grown edge, so every stage action and
+// every commit leaves it unchanged and idle.  (Actis nodes also relay stages
+// and signals, so Actis sweeps all nodes.)
+template <bool SPARSE, class F>
+LUF_DEV void ca_for_nodes(const CaView& g, const CaShot& s, int lane, int nl, F&& f)
+{
+    if (SPARSE) {
+        for (int w = lane; w < g.WN; w += nl) {
+            uint32_t bits = s.touched[w];
+            while (bits) {
+                const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+                f(32 * w + b);
+            }
+        }
+    } else
+        for (int v = lane; v < g.N; v += nl) f(v);
 }
 
 // _Node.merging, luf/main.py:839-854.  Returns busy.
@@ -236,7 +264,7 @@ LUF_DEV int ca_controller_advance(CaCtl& c, int nodes_busy, int nodes_valid)
 LUF_DEV uint32_t macar_phase_a(const CaView& g, const CaShot& s, int stage, int lane, int nl)
 {
     uint32_t parity = 0;
-    for (int v = lane; v < g.N; v += nl) {
+    ca_for_nodes<true>(g, s, lane, nl, [&](int v) {
         switch (stage) {
         case ST_GROWING: ca_growing(g, s, v); break;
         case ST_MERGING: ca_merging(g, s, v); break;
@@ -245,7 +273,7 @@ LUF_DEV uint32_t macar_phase_a(const CaView& g, const CaShot& s, int stage, int 
         case ST_BURNING: ca_burning(g, s, v); break;
         case ST_PEELING: parity ^= ca_peeling(g, s, v) >> 1; break;
         }
-    }
+    });
     return parity;
 }
 
@@ -272,11 +300,11 @@ LUF_DEV uint32_t ca_commit_node(const CaShot& s, int stage, int v)
 LUF_DEV uint32_t macar_phase_b(const CaView& g, const CaShot& s, int stage, int lane, int nl)
 {
     uint32_t acc = 0;
-    for (int v = lane; v < g.N; v += nl) {
+    ca_for_nodes<true>(g, s, lane, nl, [&](int v) {
         const uint32_t fl = ca_commit_node(s, stage, v);
         if (fl & FL_BUSY) acc |= 1u;
         if (fl & FL_ACTIVE) acc |= 2u;
-    }
+    });
     return acc;
 }
 
