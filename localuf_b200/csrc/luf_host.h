@@ -281,7 +281,7 @@ inline SfLayout make_sf_layout(const PackedWindow& p)
     auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
     const uint32_t N = (uint32_t)p.NL * p.h, ELw = words32(p.EL), WLn = words32(p.NL);
     l.cid = take(2u * N); l.ncid = take(2u * N); l.fl = take(2u * N); l.ptr = take(N);
-    l.ndef = take(4u * p.h * WLn);
+    l.ndef = take(4u * p.h * WLn); l.awake = take(4u * p.h * WLn);
     l.growth = take(4u * p.h * 2u * ELw);
     l.corr = take(4u * p.h * ELw); l.err = take(4u * p.h * ELw);
     l.top = take(4u * WLn); l.fb = take(4u * WLn);

@@ -28,7 +28,7 @@ static const uint32_t SF_RESET = 0xFFFFu;     // snowflake/constants.py:5 (RESET
 static const uint32_t SF_PTR_C = 0xFFu;
 // per-node flag word (written by the owning lane only)
 enum { SF_ACTIVE = 1, SF_WHOLE = 2, SF_DEFECT = 4, SF_GROWN = 8, SF_UNROOTED = 16, SF_BUSY = 32,
-       SF_N_ACTIVE = 64, SF_N_GROWN = 128, SF_N_UNROOTED = 256, SF_HAS_ACCESS = 512 };
+       SF_N_ACTIVE = 64, SF_N_GROWN = 128, SF_N_UNROOTED = 256 };
 enum { SF_FLAG_SLOW = 1, SF_FLAG_ONE_ONE = 2 };
 // string-pair codes of an endpoint's partner (see oracle/luf_oracle_snowflake.c)
 static const int SFP_NONE = -1, SFP_WEST = -2, SFP_EAST = -3, SFP_DEAD = -4;
@@ -48,6 +48,7 @@ struct SfLayout {
     uint32_t fl;                // u16[N]
     uint32_t ptr;               // u8[N]
     uint32_t ndef;              // u32[h*WLn]  next_defect (toggled by neighbours)
+    uint32_t awake;             // u32[h*WLn]  nodes that ever saw a defect or a fully grown edge while in the window
     uint32_t growth;            // u32[h*2*ELw]  2 bits per edge: block b at word b*2*ELw
     uint32_t corr, err;         // u32[h*ELw]
     uint32_t top, fb;           // u32[WLn]  this cycle's top-sheet syndrome / defects on the future boundary
@@ -58,7 +59,7 @@ struct SfLayout {
 struct SfShot {
     uint16_t *cid, *ncid, *fl;
     uint8_t* ptr;
-    uint32_t *ndef, *growth, *corr, *err, *top, *fb;
+    uint32_t *ndef, *awake, *growth, *corr, *err, *top, *fb;
     int16_t* partner;
 };
 
@@ -67,7 +68,7 @@ LUF_DEV SfShot sf_bind(const SfLayout& l, unsigned char* b)
     SfShot s;
     s.cid = (uint16_t*)(b + l.cid); s.ncid = (uint16_t*)(b + l.ncid); s.fl = (uint16_t*)(b + l.fl);
     s.ptr = b + l.ptr;
-    s.ndef = (uint32_t*)(b + l.ndef); s.growth = (uint32_t*)(b + l.growth);
+    s.ndef = (uint32_t*)(b + l.ndef); s.awake = (uint32_t*)(b + l.awake); s.growth = (uint32_t*)(b + l.growth);
     s.corr = (uint32_t*)(b + l.corr); s.err = (uint32_t*)(b + l.err);
     s.top = (uint32_t*)(b + l.top); s.fb = (uint32_t*)(b + l.fb);
     s.partner = (int16_t*)(b + l.partner);
@@ -108,7 +109,7 @@ LUF_DEV void sf_reset(const SfView& g, const SfShot& s, int lane, int nl)
             s.cid[v] = (uint16_t)id; s.ncid[v] = (uint16_t)id;
             s.fl[v] = (uint16_t)SF_WHOLE; s.ptr[v] = (uint8_t)SF_PTR_C;
         }
-    for (int w = lane; w < g.h * g.WLn; w += nl) s.ndef[w] = 0;
+    for (int w = lane; w < g.h * g.WLn; w += nl) { s.ndef[w] = 0; s.awake[w] = 0; }
     for (int w = lane; w < g.h * 2 * g.ELw; w += nl) s.growth[w] = 0;
     for (int w = lane; w < g.h * g.ELw; w += nl) { s.corr[w] = 0; s.err[w] = 0; }
     for (int w = lane; w < g.WLn; w += nl) { s.top[w] = 0; s.fb[w] = 0; }
@@ -297,8 +298,31 @@ LUF_DEV void sf_drop(const SfView& g, const SfShot& s, int lane, int nl)
     // next_defect == defect for every node before a drop (r.next_defect = node.defect, :1195),
     // so it shifts like everything else; the top sheet receives the new syndrome (:312-322)
     for (int c = lane; c < g.WLn; c += nl) {
-        for (int r = h - 1; r >= 1; --r) s.ndef[r * g.WLn + c] = s.ndef[(r - 1) * g.WLn + c];
+        for (int r = h - 1; r >= 1; --r) {
+            s.ndef[r * g.WLn + c] = s.ndef[(r - 1) * g.WLn + c];
+            s.awake[r * g.WLn + c] = s.awake[(r - 1) * g.WLn + c];
+        }
         s.ndef[c] = s.top[c];
+        s.awake[c] = s.top[c];
+    }
+}
+
+// Only awake nodes can act in a grow or merging step: an un-awake node has no
+// defect, is inactive, has cid == ID, pointer C and no fully grown edge, so
+// growing, flooding and syncing all leave it unchanged and idle.
+template <class F>
+LUF_DEV void sf_for_awake(const SfView& g, const SfShot& s, int lane, int nl, F&& f)
+{
+    const int words = g.h * g.WLn;
+    for (int x = lane; x < words; x += nl) {
+        uint32_t bits = s.awake[x];
+        if (!bits) continue;
+        const int r = x / g.WLn, w = x - r * g.WLn;
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const int q = 32 * w + b;
+            f(r, q, r * g.NL + q);
+        }
     }
 }
 
@@ -312,6 +336,10 @@ LUF_DEV void sf_grow_node(const SfView& g, const SfShot& s, int r, int q)
         if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
         const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
         if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);
+        else if (old == G_HALF) {                                  // newly FULL: both ends have access from now on
+            luf_atomic_or(&s.awake[r * g.WLn + (q >> 5)], 1u << (q & 31));
+            luf_atomic_or(&s.awake[nb.r2 * g.WLn + (nb.q2 >> 5)], 1u << (nb.q2 & 31));
+        }
     }
 }
 
@@ -319,42 +347,25 @@ LUF_DEV void sf_grow_node(const SfView& g, const SfShot& s, int r, int q)
 // (:1221-1223) + _FullUnrooter.start (:1387-1389).  mode: 0 = 1:1 grow, 1 = whole, 2 = half.
 LUF_DEV void sf_grow(const SfView& g, const SfShot& s, int mode, int lane, int nl)
 {
-    for (int r = 0; r < g.h; ++r)
-        for (int q = lane; q < g.NL; q += nl) {
-            const int v = r * g.NL + q;
-            uint32_t f = s.fl[v];
-            if (mode == 2) {
-                f &= ~(uint32_t)(SF_UNROOTED | SF_N_UNROOTED);
-                if ((f & SF_ACTIVE) && !(f & SF_WHOLE) && !(f & SF_GROWN)) { sf_grow_node(g, s, r, q); f ^= SF_WHOLE; }
-            } else {
-                if ((f & SF_ACTIVE) && (mode == 0 || (f & SF_WHOLE))) {
-                    sf_grow_node(g, s, r, q); f ^= SF_WHOLE;
-                    if (mode == 1) f |= SF_GROWN | SF_N_GROWN;
-                }
-                if (r == g.h - 1) {                                   // bottom sheet: a downward pointer is broken
-                    const uint32_t p = s.ptr[v];
-                    if (p != SF_PTR_C && ((LUF_LDG(&g.nbr[q * g.K + p]) >> 23) & 3u) == 0u) {
-                        s.cid[v] = (uint16_t)SF_RESET; s.ptr[v] = (uint8_t)SF_PTR_C;
-                    }
+    sf_for_awake(g, s, lane, nl, [&](int r, int q, int v) {
+        uint32_t f = s.fl[v];
+        if (mode == 2) {
+            f &= ~(uint32_t)(SF_UNROOTED | SF_N_UNROOTED);
+            if ((f & SF_ACTIVE) && !(f & SF_WHOLE) && !(f & SF_GROWN)) { sf_grow_node(g, s, r, q); f ^= SF_WHOLE; }
+        } else {
+            if ((f & SF_ACTIVE) && (mode == 0 || (f & SF_WHOLE))) {
+                sf_grow_node(g, s, r, q); f ^= SF_WHOLE;
+                if (mode == 1) f |= SF_GROWN | SF_N_GROWN;
+            }
+            if (r == g.h - 1) {                                   // bottom sheet: a downward pointer is broken
+                const uint32_t p = s.ptr[v];
+                if (p != SF_PTR_C && ((LUF_LDG(&g.nbr[q * g.K + p]) >> 23) & 3u) == 0u) {
+                    s.cid[v] = (uint16_t)SF_RESET; s.ptr[v] = (uint8_t)SF_PTR_C;
                 }
             }
-            s.fl[v] = (uint16_t)f;
         }
-}
-
-// _Node.update_access (snowflake/main.py:1086-1095), reduced to "has any fully grown edge"
-LUF_DEV void sf_update_access(const SfView& g, const SfShot& s, int lane, int nl)
-{
-    for (int r = 0; r < g.h; ++r)
-        for (int q = lane; q < g.NL; q += nl) {
-            const int v = r * g.NL + q;
-            uint32_t f = s.fl[v] & ~(uint32_t)SF_HAS_ACCESS;
-            for (int k = 0; k < g.K; ++k) {
-                SfNbr nb;
-                if (sf_nbr(g, r, q, k, nb) && sf_growth(s, nb.e) == G_FULL) { f |= SF_HAS_ACCESS; break; }
-            }
-            s.fl[v] = (uint16_t)f;
-        }
+        s.fl[v] = (uint16_t)f;
+    });
 }
 
 // _Node.flooding: _FullUnrooter.flooding_whole (:1394-1409) / flooding_half (:1359-1362)
@@ -367,7 +378,6 @@ LUF_DEV void sf_flooding(const SfView& g, const SfShot& s, int r, int q, int v, 
         s.ncid[v] = (uint16_t)sf_id(g, r, q);
         return;
     }
-    if (!(f & SF_HAS_ACCESS)) return;
     for (int k = 0; k < g.K; ++k) {
         SfNbr nb;
         if (!sf_nbr(g, r, q, k, nb) || sf_growth(s, nb.e) != G_FULL) continue;
@@ -406,34 +416,30 @@ LUF_DEV void sf_syncing(const SfView& g, const SfShot& s, int r, int q, int v, u
 // One merging timestep, phase A: _Node.merging (:1097-1104) with the fast or slow merger (:1237-1256)
 LUF_DEV void sf_merge_a(const SfView& g, const SfShot& s, bool whole, bool slow, int lane, int nl)
 {
-    for (int r = 0; r < g.h; ++r)
-        for (int q = lane; q < g.NL; q += nl) {
-            const int v = r * g.NL + q;
-            uint32_t f = s.fl[v] & ~(uint32_t)SF_BUSY, ptr = s.ptr[v];
-            if (slow) { sf_syncing(g, s, r, q, v, f, ptr); sf_flooding(g, s, r, q, v, whole, f, ptr); }
-            else { sf_flooding(g, s, r, q, v, whole, f, ptr); sf_syncing(g, s, r, q, v, f, ptr); }
-            s.fl[v] = (uint16_t)f; s.ptr[v] = (uint8_t)ptr;
-        }
+    sf_for_awake(g, s, lane, nl, [&](int r, int q, int v) {
+        uint32_t f = s.fl[v] & ~(uint32_t)SF_BUSY, ptr = s.ptr[v];
+        if (slow) { sf_syncing(g, s, r, q, v, f, ptr); sf_flooding(g, s, r, q, v, whole, f, ptr); }
+        else { sf_flooding(g, s, r, q, v, whole, f, ptr); sf_syncing(g, s, r, q, v, f, ptr); }
+        s.fl[v] = (uint16_t)f; s.ptr[v] = (uint8_t)ptr;
+    });
 }
 
 // phase B: update_after_merging (:1131-1137).  Returns bit0 any busy, bit1 any cid == RESET.
 LUF_DEV uint32_t sf_merge_b(const SfView& g, const SfShot& s, int lane, int nl)
 {
     uint32_t acc = 0;
-    for (int r = 0; r < g.h; ++r)
-        for (int q = lane; q < g.NL; q += nl) {
-            const int v = r * g.NL + q;
-            uint32_t f = s.fl[v];
-            const uint32_t c = s.ncid[v];
-            s.cid[v] = (uint16_t)c;
-            const uint32_t nd = (s.ndef[r * g.WLn + (q >> 5)] >> (q & 31)) & 1u;
-            f = (f & ~(uint32_t)(SF_DEFECT | SF_ACTIVE | SF_UNROOTED | SF_GROWN))
-                | (nd ? SF_DEFECT : 0) | ((f & SF_N_ACTIVE) ? SF_ACTIVE : 0)
-                | ((f & SF_N_UNROOTED) ? SF_UNROOTED : 0) | ((f & SF_N_GROWN) ? SF_GROWN : 0);
-            s.fl[v] = (uint16_t)f;
-            if (f & SF_BUSY) acc |= 1u;
-            if (c == SF_RESET) acc |= 2u;
-        }
+    sf_for_awake(g, s, lane, nl, [&](int r, int q, int v) {
+        uint32_t f = s.fl[v];
+        const uint32_t c = s.ncid[v];
+        s.cid[v] = (uint16_t)c;
+        const uint32_t nd = (s.ndef[r * g.WLn + (q >> 5)] >> (q & 31)) & 1u;
+        f = (f & ~(uint32_t)(SF_DEFECT | SF_ACTIVE | SF_UNROOTED | SF_GROWN))
+            | (nd ? SF_DEFECT : 0) | ((f & SF_N_ACTIVE) ? SF_ACTIVE : 0)
+            | ((f & SF_N_UNROOTED) ? SF_UNROOTED : 0) | ((f & SF_N_GROWN) ? SF_GROWN : 0);
+        s.fl[v] = (uint16_t)f;
+        if (f & SF_BUSY) acc |= 1u;
+        if (c == SF_RESET) acc |= 2u;
+    });
     return acc;
 }
 
@@ -469,14 +475,11 @@ LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t
     LUF_PHASE(sf_drop(g, s, lane, nl));
     if (one_one) {
         LUF_PHASE(sf_grow(g, s, 0, lane, nl));
-        LUF_PHASE(sf_update_access(g, s, lane, nl));
         sf_merge(g, s, true, slow, rt_all, rt_unr, lane, nl);
     } else {
         LUF_PHASE(sf_grow(g, s, 1, lane, nl));
-        LUF_PHASE(sf_update_access(g, s, lane, nl));
         sf_merge(g, s, true, slow, rt_all, rt_unr, lane, nl);
         LUF_PHASE(sf_grow(g, s, 2, lane, nl));
-        LUF_PHASE(sf_update_access(g, s, lane, nl));
         sf_merge(g, s, false, slow, rt_all, rt_unr, lane, nl);
     }
     LUF_PHASE(if (lane == 0) sf_pairs_lower(g, s));
