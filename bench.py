@@ -30,18 +30,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (code class, d, noise, p, description)
+    # name: (code class, d, noise, p, description[, scheme, decoder])
     'cfg1': ('Repetition', 5, 'code capacity', 0.05, 'Repetition d=5 code-capacity p=0.05 UF batch'),
     'cfg2': ('Surface', 9, 'code capacity', 0.05, 'Surface d=9 code-capacity p=0.05 UF batch'),
     'cfg3': ('Surface', 11, 'phenomenological', 0.01, 'Surface d=11 phenomenological p=0.01 h=11 UF batch'),
+    'cfg3-macar': ('Surface', 11, 'phenomenological', 0.01, 'Surface d=11 phenomenological p=0.01 h=11 Macar batch',
+                   'batch', 'Macar'),
+    'cfg3-actis': ('Surface', 11, 'phenomenological', 0.01, 'Surface d=11 phenomenological p=0.01 h=11 Actis batch',
+                   'batch', 'Actis'),
+    'cfg4': ('Surface', 13, 'circuit-level', 0.003,
+             'Surface d=13 circuit-level p=0.003 frugal (c=1, b=12) Snowflake; unit = decoding cycle', 'frugal', 'Snowflake'),
 }
 SEED = 20260101
+DECODER_ID = {'UF': 0, 'Macar': 1, 'Actis': 2}
 
 
 def make_code(name):
     import localuf_b200 as L
-    cls, d, noise, p, desc = WORKLOADS[name]
-    return getattr(L, cls)(d, noise), p, desc
+    cls, d, noise, p, desc = WORKLOADS[name][:5]
+    scheme = WORKLOADS[name][5] if len(WORKLOADS[name]) > 5 else 'batch'
+    return getattr(L, cls)(d, noise, scheme=scheme), p, desc
+
+
+def decoder_name(name):
+    return WORKLOADS[name][6] if len(WORKLOADS[name]) > 6 else 'UF'
 
 
 def algorithmic_bytes_per_shot(flat) -> int:
@@ -50,6 +62,11 @@ def algorithmic_bytes_per_shot(flat) -> int:
     we = 4 * ((flat.n_edges + 31) // 32)
     wd = 4 * ((flat.n_detectors + 31) // 32)
     return 4 * we + 2 * wd
+
+
+def algorithmic_bytes_per_cycle(tables) -> int:
+    """per decoding cycle 4 W(fresh edges) + 2 W(new detectors) bytes."""
+    return 4 * 4 * ((tables.EL + 31) // 32) + 2 * 4 * ((tables.NLd + 31) // 32)
 
 
 def measured_peak_hbm():
@@ -62,52 +79,101 @@ def measured_peak_hbm():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled every ~10 ms through NVML (in
+    process; `nvidia-smi -lms` as the fallback).  `mark()` is called at the start
+    and at the end of the timed region; only samples between the marks count."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NAMES = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.marks, self.index = [], [], index      # rows: (t, sm_mhz, max_mhz, [reasons])
+        self.stop, self.proc, self.thread, self.source = threading.Event(), None, None, None
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
+
+    def _physical_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            ids = [x.strip() for x in vis.split(',') if x.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _nvml_loop(self, nv, h):
+        bits = (('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, 'nvmlClocksEventReasonHwSlowdown')
+                 else nv.nvmlClocksThrottleReasonHwSlowdown),
+                ('hw_thermal_slowdown', getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown',
+                                                getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0))),
+                ('sw_thermal_slowdown', getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown',
+                                                getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0))),
+                ('sw_power_cap', getattr(nv, 'nvmlClocksEventReasonSwPowerCap',
+                                         getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0))))
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(h))
+                self.rows.append((time.perf_counter(), sm, mx, [n for n, b in bits if b and (r & b)]))
+            except Exception:
+                pass
+            self.stop.wait(0.01)
+
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm, mx = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            self.rows.append((time.perf_counter(), sm, mx,
+                              [n for n, v in zip(self.NAMES, parts[2:6]) if v.lower().startswith('active')]))
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.source = 'nvml'
         except Exception:
-            self.proc = None
+            try:
+                self.proc = subprocess.Popen(
+                    ['nvidia-smi', f'--id={self._physical_index()}', f'--query-gpu={self.Q}',
+                     '--format=csv,noheader,nounits', '-lms', '20'],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+                self.source = 'nvidia-smi'
+            except Exception:
+                self.thread = None
+        if self.thread:
+            self.thread.start()
         return self
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for r in self.rows:
-            parts = [x.strip() for x in r.split(',')]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        lo, hi = (self.marks[0], self.marks[-1]) if len(self.marks) >= 2 else (0.0, float('inf'))
+        inside = [r for r in self.rows if lo <= r[0] <= hi]
+        rows = inside or self.rows          # a timed region shorter than the sampling period: nearest samples
+        sm = [r[1] for r in rows]
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(r[2] for r in rows) if rows else None,
+                'reasons': reasons, 'samples': len(inside), 'source': self.source}
 
 
 def cpu_oracle(code):
@@ -116,13 +182,26 @@ def cpu_oracle(code):
     return binding.Oracle.from_code(code)
 
 
-def time_cpu(orc, class_p, target_s, threads, seed=SEED):
+def time_cpu(orc, class_p, target_s, threads, seed=SEED, decoder=0):
     """shots/s of the oracle port on `threads` host threads over ~target_s seconds."""
-    n = 2000 * threads
-    t0 = time.perf_counter(); orc.mc_batch(0, 0, class_p, seed, n, threads); dt = time.perf_counter() - t0
+    n = (2000 if decoder == 0 else 40 if decoder == 1 else 4) * threads
+    t0 = time.perf_counter(); orc.mc_batch(decoder, 0, class_p, seed, n, threads); dt = time.perf_counter() - t0
     n = max(n, int(n * target_s / max(dt, 1e-3)))
-    t0 = time.perf_counter(); m = orc.mc_batch(0, 0, class_p, seed + 1, n, threads); dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); m = orc.mc_batch(decoder, 0, class_p, seed + 1, n, threads); dt = time.perf_counter() - t0
     return n / dt, n, m, dt
+
+
+def time_cpu_stream(code, class_p, target_s, threads, seed=SEED):
+    """decoding cycles/s of the Snowflake/frugal oracle port (Frugal.run(n=1) streams)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import binding
+    from localuf_b200 import _window
+    orc = binding.StreamOracle(_window.build(code))
+    n = 2 * threads
+    t0 = time.perf_counter(); orc.mc(class_p, seed, n, 1, threads); dt = time.perf_counter() - t0
+    n = max(n, int(n * target_s / max(dt, 1e-3)))
+    t0 = time.perf_counter(); m, cycles = orc.mc(class_p, seed + 1, n, 1, threads); dt = time.perf_counter() - t0
+    return cycles / dt, n, m, dt
 
 
 def run_reference(args):
@@ -133,29 +212,60 @@ def run_reference(args):
     if rank != 0:
         return
     code, p, desc = make_code(args.workload)
-    orc = cpu_oracle(code)
+    dec = decoder_name(args.workload)
     threads = len(os.sched_getaffinity(0))
     class_p = code.NOISE.class_probabilities(p)
-    for _ in range(args.warmup):
-        orc.mc_batch(0, 0, class_p, 1, 500 * threads, threads)
     per_step_target = max(2.0, min(20.0, 60.0 / max(args.steps, 1)))
-    rate0, n, _, _ = time_cpu(orc, class_p, per_step_target, threads)
-    times = []
+    if dec == 'Snowflake':
+        unit = 'decoding cycles/s'
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import binding
+        from localuf_b200 import _window
+        orc = binding.StreamOracle(_window.build(code))
+        for _ in range(args.warmup):
+            orc.mc(class_p, 1, threads, 1, threads)
+        _, n, _, _ = time_cpu_stream(code, class_p, per_step_target, threads)
+
+        def one(k):
+            return orc.mc(class_p, SEED + 10 + k, n, 1, threads)[1]
+        what = f'{n} Frugal.run(n=1) memory experiments'
+    else:
+        unit = 'shots/s'
+        orc = cpu_oracle(code)
+        did = DECODER_ID[dec]
+        for _ in range(args.warmup):
+            orc.mc_batch(did, 0, class_p, 1, (500 if did == 0 else 8) * threads, threads)
+        _, n, _, _ = time_cpu(orc, class_p, per_step_target, threads, decoder=did)
+
+        def one(k):
+            orc.mc_batch(did, 0, class_p, SEED + 10 + k, n, threads)
+            return n
+        what = f'{n} shots'
+    times, units = [], 0
     for k in range(args.steps):
-        t0 = time.perf_counter(); orc.mc_batch(0, 0, class_p, SEED + 10 + k, n, threads)
+        t0 = time.perf_counter(); units += one(k)
         times.append(time.perf_counter() - t0)
     total = sum(times)
-    value = n * args.steps / total
+    value = units / total
     print(json.dumps({
-        'impl': 'reference', 'metric': 'decoded shots/s', 'value': value, 'unit': 'shots/s',
+        'impl': 'reference', 'metric': METRIC[unit], 'value': value, 'unit': unit,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'u32 bit-packed / u16 indices', 'data': 'synthetic',
-        'config': {'workload': desc, 'shots_per_step': n, 'rng': 'xoshiro256** per thread'},
-        'cpu_baseline': {'value': value, 'unit': 'shots/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{n} shots per step on {threads} threads (C oracle of the reference algorithm)'},
-        'e2e': {'value': value, 'unit': 'shots/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
+        'config': {'workload': desc, 'units_per_step': units // max(args.steps, 1), 'rng': 'xoshiro256** per thread'},
+        'cpu_baseline': {'value': value, 'unit': unit, 'cores': threads, 'kind': 'port',
+                         'sample': f'{what} per step on {threads} threads (C oracle of the reference algorithm; '
+                                   'the pure-Python reference cannot travel to the GPU box)'},
+        'e2e': {'value': value, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
+
+
+DTYPE = 'u32 bit-packed / u16 indices'
+METRIC = {'shots/s': 'decoded shots/s', 'decoding cycles/s': 'decoding cycles/s'}
+DEFAULT_UNITS = {'cfg1': 1 << 26, 'cfg2': 1 << 24, 'cfg3': 1 << 22, 'cfg3-macar': 1 << 19, 'cfg3-actis': 1 << 14,
+                 'cfg4': 1 << 16}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full; profiles/)
+TRAFFIC = {'cfg3': (104960, 'profiles/r01_v7_k_mc_uf_summary.txt')}
 
 
 def run_ours(args):
@@ -174,22 +284,46 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     code, p, desc = make_code(args.workload)
-    decoder = L.decoders.UF(code)
-    eng = _engine.Engine(code, device=local_rank)
-    decoder._engine = eng
-    flat = code.FLAT
-    S = args.shots_per_step
+    dec = decoder_name(args.workload)
+    decoder = getattr(L.decoders, dec)(code)
+    S = args.shots_per_step or DEFAULT_UNITS[args.workload]
     counts = torch.zeros(4, dtype=torch.int64, device='cuda')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')     # > 126 MB L2
+    stream_mode = dec == 'Snowflake'
+    if stream_mode:
+        # a step = S independent Frugal.run(n=1) memory experiments per GPU; unit = decoding cycle
+        eng = _engine.StreamEngine(code, device=local_rank)
+        decoder._engine = eng
+        unit, kernel = 'decoding cycles/s', 'k_stream_mc'
+        bpu = algorithmic_bytes_per_cycle(eng.tables)
+        h2d = 8 * eng.tables.n_classes + 40
+
+        def step(k):
+            eng.mc(decoder._flags, p, SEED, (k * world + rank) * S, S, 1, counts)
+
+        def e2e_run(n_units, seed):
+            return code.SCHEME.run(decoder, p, 1, shots=n_units, seed=seed)[0]
+        api = 'code.SCHEME.run(decoder, p, n=1, shots=S) -> luf_stream_mc_host'
+    else:
+        eng = _engine.Engine(code, device=local_rank)
+        decoder._engine = eng
+        unit, kernel = 'shots/s', {'UF': 'k_mc_uf', 'Macar': 'k_mc_ca', 'Actis': 'k_mc_ca'}[dec]
+        bpu = algorithmic_bytes_per_shot(code.FLAT)
+        h2d = 8 * code.FLAT.n_classes + 40
+        did = DECODER_ID[dec]
+
+        def step(k):
+            # rank r, step k owns global shots [(k*world + r)*S, +S)
+            eng.mc_run(did, 0, p, SEED, (k * world + rank) * S, S, counts)
+
+        def e2e_run(n_units, seed):
+            return code.SCHEME.run(decoder, p, n_units, seed=seed)[0]
+        api = 'code.SCHEME.run(decoder, p, n) -> luf_mc_run_host'
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def step(k):
-        # rank r, step k owns global shots [(k*world + r)*S, +S)
-        eng.mc_run(_engine.DEC_UF, 0, p, SEED, (k * world + rank) * S, S, counts)
 
     for k in range(args.warmup):
         step(k)
@@ -199,6 +333,7 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local_rank) as clocks:
         barrier()
+        clocks.mark()
         t_wall0 = time.perf_counter()
         for k in range(args.steps):
             flush.fill_(k & 0xFF)                       # L2 flush between timed steps
@@ -207,6 +342,7 @@ def run_ours(args):
             ev[k][1].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
+        clocks.mark()
     launches = eng.launch_count - launches0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device='cuda')
@@ -214,61 +350,66 @@ def run_ours(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     total_ms = float(total_ms.item())
-    fails, shots = (int(x) for x in counts.tolist()[:2])
-    assert shots == S * args.steps * world, (shots, S, args.steps, world)
-    value = shots / (total_ms / 1e3)
+    fails, units = (int(x) for x in counts.tolist()[:2])
+    if not stream_mode:
+        assert units == S * args.steps * world, (units, S, args.steps, world)
+    value = units / (total_ms / 1e3)
+    units_per_step_gpu = units // (args.steps * world)
 
-    # ---- end to end through the public API (the call a reference user makes)
-    e2e_n = S
+    # ---- end to end through the public API (the call a reference user makes):
+    # host arguments in (class probabilities, seed, counts), counters back on the host
     for _ in range(2):
-        code.SCHEME.run(decoder, p, min(e2e_n, 1 << 16), seed=1)
+        e2e_run(max(1, min(S, 1 << 12)) * world, 1)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     m_e2e = 0
     for k in range(e2e_steps):
-        m, _ = code.SCHEME.run(decoder, p, e2e_n * world, seed=SEED + 1000 + k)
-        m_e2e += m
+        m_e2e += e2e_run(S * world, SEED + 1000 + k)
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_n * world * e2e_steps / float(t_e2e.item())
+    e2e_value = units_per_step_gpu * world * e2e_steps / float(t_e2e.item())
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        bps = algorithmic_bytes_per_shot(flat)
         kern_ms = statistics.mean(step_ms)
-        achieved = bps * S / (kern_ms / 1e3) / 1e9
+        achieved = bpu * units_per_step_gpu / (kern_ms / 1e3) / 1e9
+        traffic, traffic_src = TRAFFIC.get(args.workload, (None, None))
         line = {
-            'metric': 'decoded shots/s', 'value': value, 'unit': 'shots/s', 'n_gpus': world,
+            'metric': METRIC[unit], 'value': value, 'unit': unit, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'u32 bit-packed / u16 indices', 'data': 'synthetic',
-            'config': {'workload': desc, 'shots_per_step_per_gpu': S, 'seed': SEED,
+            'dtype': DTYPE, 'data': 'synthetic',
+            'config': {'workload': desc, 'units_per_step_per_gpu': units_per_step_gpu, 'seed': SEED,
                        'parallelism': f'dp{world} (shots sharded, one all-reduce of counters)',
                        'l2': '256 MiB write between timed steps (outside the per-step events); '
-                             'the fused kernel reads only ~50 KB of graph tables from HBM',
-                       'failures': fails, 'failure_rate': fails / shots, 'wall_s_timed_region': t_wall},
+                             'the fused kernel reads only the graph tables (~100 KB) from HBM',
+                       'failures': fails, 'failure_rate': fails / max(units, 1), 'wall_s_timed_region': t_wall},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': 88576, 'kernel': 'k_mc_uf',
-                         'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of one k_mc_uf launch '
-                                         '(ncu --set full, profiles/r01_v5_k_mc_uf_summary.txt): graph tables only',
-                         'algorithmic_bytes_per_shot': bps, 'peak_source': peak_src,
-                         'note': 'fused kernel keeps a shot in shared memory: the HBM fraction is low by '
-                                 'construction; the kernel is bound by shared-memory latency (see profiles/)'},
-            'e2e': {'value': e2e_value, 'unit': 'shots/s',
-                    'h2d_bytes_per_step': 8 * flat.n_classes + 40, 'd2h_bytes_per_step': 16,
-                    'api': 'code.SCHEME.run(decoder, p, n) -> luf_mc_run_host', 'failures': m_e2e},
+                         'frac': achieved / peak, 'traffic': traffic, 'kernel': kernel,
+                         'traffic_source': traffic_src,
+                         'algorithmic_bytes_per_unit': bpu, 'peak_source': peak_src,
+                         'note': 'the fused kernel keeps a shot in shared memory, so the HBM fraction is low by '
+                                 'construction (SURVEY 8d); the kernel is bound by issue slots and shared-memory '
+                                 'latency (profiles/)'},
+            'e2e': {'value': e2e_value, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 32,
+                    'api': api, 'failures': m_e2e},
             'gpu_launches': launches,
             'clocks': clocks.summary(),
         }
         if world == 1 and not args.no_cpu:
-            orc = cpu_oracle(code)
             threads = len(os.sched_getaffinity(0))
-            rate, n, m, dt = time_cpu(orc, code.NOISE.class_probabilities(p), args.cpu_seconds, threads)
-            line['cpu_baseline'] = {'value': rate, 'unit': 'shots/s', 'cores': threads, 'kind': 'port',
-                                    'sample': f'{n} shots of the same workload in {dt:.1f} s '
+            class_p = code.NOISE.class_probabilities(p)
+            if stream_mode:
+                rate, n, m, dt = time_cpu_stream(code, class_p, args.cpu_seconds, threads)
+                what = f'{n} Frugal.run(n=1) memory experiments'
+            else:
+                rate, n, m, dt = time_cpu(cpu_oracle(code), class_p, args.cpu_seconds, threads, decoder=DECODER_ID[dec])
+                what = f'{n} shots'
+            line['cpu_baseline'] = {'value': rate, 'unit': unit, 'cores': threads, 'kind': 'port',
+                                    'sample': f'{what} of the same workload in {dt:.1f} s '
                                               f'(C oracle of the reference algorithm, {m} failures)'}
         print(json.dumps(line))
     if world > 1:
@@ -282,7 +423,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
-    ap.add_argument('--shots-per-step', type=int, default=1 << 22)
+    ap.add_argument('--shots-per-step', type=int, default=0, help='units per step per GPU (0 = workload default)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
