@@ -32,6 +32,10 @@
   static inline int luf_ffs(uint32_t x) { return __builtin_ffs((int)x); }
   static inline uint32_t luf_mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
   static inline float luf_log2(float x) { return log2f(x); }
+  static inline int luf_popc(uint32_t x) { return __builtin_popcount(x); }
+  struct luf_u32x2 { uint32_t x, y; };
+  struct luf_u32x4 { uint32_t x, y, z, w; };
+  #define LUF_LDG2(p) (*(const luf_u32x2*)(p))
   #define LUF_LDG(p) (*(p))
   // a phase = every lane of the tile runs `stmt`, then the tile synchronises
   #define LUF_PHASE(stmt) for (int lane = 0; lane < nl; ++lane) { stmt; }
@@ -52,6 +56,10 @@
   LUF_DEV int luf_ffs(uint32_t x) { return __ffs((int)x); }
   LUF_DEV uint32_t luf_mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
   LUF_DEV float luf_log2(float x) { return __log2f(x); }
+  LUF_DEV int luf_popc(uint32_t x) { return __popc(x); }
+  typedef uint2 luf_u32x2;
+  typedef uint4 luf_u32x4;
+  #define LUF_LDG2(p) __ldg((const uint2*)(p))
   #define LUF_LDG(p) __ldg(p)
   #define LUF_PHASE(stmt) { stmt; } __syncwarp();
   #define LUF_ANY(x) __any_sync(0xffffffffu, (x) != 0)
@@ -63,16 +71,28 @@
 namespace luf {
 
 typedef uint16_t idx_t;                 // node / edge index inside a shot's state
-static const uint32_t ROOT_BIT = 0x8000u;   // P[v]: root marker; low 15 bits = cluster size
-static const uint32_t ODD_BIT = 0x8000u;    // R[root]: odd defect parity; low 15 bits = boundary node + 1
+// One 32-bit word per node, S[v]:
+//   root      bit 15 set, bits 0..14 = cluster size, bit 31 = odd defect parity,
+//             bits 16..30 = boundary node of the cluster + 1 (0 = none)
+//   non-root  bit 15 clear, bits 0..14 = parent, bits 16..31 = the edge whose
+//             union made it a non-root (the whole tree of a two-node cluster)
+static const uint32_t ROOT_BIT = 0x8000u;
+static const uint32_t ODD_BIT = 0x80000000u;
+static const uint32_t BND_MASK = 0x7FFF0000u;
+static const uint32_t SIZE_MASK = 0x7FFFu;
 static const uint32_t NONE16 = 0xFFFFu;
 static const uint32_t TREE_ROOT = 0xFFFEu;
+static const uint32_t ADJ_PAD = 0xFFFFFFFFu;
 static const int MAX_CLASSES = 32;
 static const int CLAIM_SLOTS = 128;      // power of two
 #ifndef LUF_LIST_CAP
-  #define LUF_LIST_CAP 80
+  #define LUF_LIST_CAP 96
 #endif
-static const uint32_t LIST_CAP = LUF_LIST_CAP;   // work-list capacity (tests shrink it to force the overflow paths)
+#ifndef LUF_LIST2_CAP
+  #define LUF_LIST2_CAP 64
+#endif
+static const uint32_t LIST_CAP = LUF_LIST_CAP;     // compacted bitmap (defects / touched nodes / newly full edges)
+static const uint32_t LIST2_CAP = LUF_LIST2_CAP;   // active nodes of a round / tree roots (tests shrink both to force the overflow paths)
 static const uint32_t LIST_DONE = 0xFFFFFFFFu;
 
 enum { G_UNGROWN = 0, G_HALF = 1, G_FULL = 2, G_BURNT = 3 };
@@ -82,8 +102,8 @@ enum { FLAG_DYNAMIC = 1, FLAG_WEST = 2 };
 struct GraphView {
     int N, B, E;            // nodes, boundary nodes (indices [0,B)), edges
     int WE, WD, WN;         // 32-bit words of an edge / detector / node bitmap
-    const uint32_t* inc_off;    // [N+1] CSR offsets
-    const uint32_t* inc;        // [2E]  edge | other<<16 | first<<31, ascending edge id per node
+    int DEG;                // row length of adj (maximum degree rounded up to even)
+    const uint32_t* adj;        // [N][DEG] edge | other<<16 | first<<31, ascending edge id; ADJ_PAD fills a row
     const uint32_t* edge_uv;    // [E]   u | v<<16
     const uint32_t* west_mask;  // [WE]  edges whose first endpoint is a west boundary node
     const int16_t* node_long;   // [N]   coordinate along the long axis
@@ -102,99 +122,135 @@ struct SampleParams {
 
 // Byte offsets of one shot's state inside its shared-memory slice.
 struct Layout {
-    uint32_t P, R;                      // idx_t[N] each (aliased by the peel: tree edge, stack link)
+    uint32_t S;                         // uint32[4*ceil(N/4)]  node words (the peel re-uses them: tree edge | stack link << 16)
     uint32_t growth;                    // uint32[ceil(E/16)]  2 bits per edge
-    uint32_t newfull;                   // uint32[WE]  edges that reached FULL this round
+    uint32_t newfull;                   // uint32[max(WE,WN)]  edges that reached FULL this round; tree roots during the peel
     uint32_t defect;                    // uint32[WD]
-    uint32_t touched;                   // uint32[WN]  nodes that are a defect or belong to a cluster of size > 1
-    uint32_t troot;                     // uint32[WN]  tree roots to peel from (aliases newfull, which is idle by then)
-    uint32_t deg;                       // uint32[ceil(N/16)]  per node: has >= 1 / >= 2 fully grown incident edges
+    uint32_t touched;                   // uint32[WN]  nodes that are a defect or an end of a fully grown edge
+    uint32_t full2;                     // uint32[WN]  nodes with two or more fully grown edges (defects: one or more)
     uint32_t err, corr;                 // uint32[WE]  only in the staged kernels (0 = absent)
-    uint32_t claim;                     // uint32[CLAIM_SLOTS]  merge reservations (see ph_merge_claim)
-    uint32_t list, cnt;                 // uint32[LIST_CAP] work list shared by the phases that balance work over lanes; uint32[4] its fill counter
+    uint32_t zero_off, zero_bytes;      // growth .. corr are contiguous: what ph_reset clears
+    uint32_t claim;                     // uint32[max(CLAIM_SLOTS,WN)]  merge reservations; visited bitmap of the peel
+    uint32_t list, list2, cnt;          // uint32[LIST_CAP], uint32[LIST2_CAP] work lists; uint32[4] their fill counters
     uint32_t bytes;                     // slice size, multiple of 16
 };
 
 struct Shot {
-    idx_t *P, *R;
-    uint32_t *growth, *newfull, *defect, *touched, *troot, *deg, *err, *corr, *claim, *list, *cnt;
+    uint32_t *S, *growth, *newfull, *defect, *touched, *full2, *err, *corr, *claim, *list, *list2, *cnt;
 };
 
 LUF_DEV Shot bind(const Layout& l, unsigned char* base)
 {
     Shot s;
-    s.P = (idx_t*)(base + l.P); s.R = (idx_t*)(base + l.R);
+    s.S = (uint32_t*)(base + l.S);
     s.growth = (uint32_t*)(base + l.growth); s.newfull = (uint32_t*)(base + l.newfull);
     s.defect = (uint32_t*)(base + l.defect); s.touched = (uint32_t*)(base + l.touched);
-    s.troot = (uint32_t*)(base + l.troot); s.deg = (uint32_t*)(base + l.deg);
+    s.full2 = (uint32_t*)(base + l.full2);
     s.err = l.err ? (uint32_t*)(base + l.err) : 0;
     s.corr = l.corr ? (uint32_t*)(base + l.corr) : 0;
     s.claim = (uint32_t*)(base + l.claim);
-    s.list = (uint32_t*)(base + l.list); s.cnt = (uint32_t*)(base + l.cnt);
+    s.list = (uint32_t*)(base + l.list); s.list2 = (uint32_t*)(base + l.list2); s.cnt = (uint32_t*)(base + l.cnt);
     return s;
 }
 
 // ------------------------------------------------------------------ helpers
 LUF_DEV uint32_t growth_of(const Shot& s, uint32_t e) { return (s.growth[e >> 4] >> ((e & 15u) * 2u)) & 3u; }
+LUF_DEV bool bit_of(const uint32_t* bm, uint32_t i) { return (bm[i >> 5] >> (i & 31u)) & 1u; }
 
-// find without compression: safe while other lanes read the forest
-LUF_DEV uint32_t find_ro(const Shot& s, uint32_t v)
+// find without writes: safe while other lanes read or extend the forest.  `wr` = the root's word.
+LUF_DEV uint32_t find_ro(const Shot& s, uint32_t v, uint32_t& wr)
 {
-    uint32_t p;
-    while (!((p = s.P[v]) & ROOT_BIT)) v = p;
+    uint32_t w;
+    while (!((w = s.S[v]) & ROOT_BIT)) v = w & SIZE_MASK;
+    wr = w;
     return v;
 }
 
 // find that also shortcuts the start node to the root it found.  Safe next to
 // concurrent finds and unions of other lanes: a non-root node never becomes a
-// root again and the value written is one of its ancestors (16-bit stores are
-// atomic), so every interleaving leaves a valid forest with the same roots.
-LUF_DEV uint32_t find_pc(const Shot& s, uint32_t v)
+// root again and the value written is one of its ancestors (32-bit stores are
+// atomic; the union edge in the upper half is kept), so every interleaving
+// leaves a valid forest with the same roots.
+LUF_DEV uint32_t find_pc(const Shot& s, uint32_t v, uint32_t& wr)
 {
-    uint32_t p = s.P[v];
-    if (p & ROOT_BIT) return v;
-    uint32_t r = p, q;
+    const uint32_t w = s.S[v];
+    if (w & ROOT_BIT) { wr = w; return v; }
+    uint32_t r = w & SIZE_MASK, q;
     int hops = 0;
-    while (!((q = s.P[r]) & ROOT_BIT)) { r = q; ++hops; }
-    if (hops) s.P[v] = (idx_t)r;
+    while (!((q = s.S[r]) & ROOT_BIT)) { r = q & SIZE_MASK; ++hops; }
+    if (hops) s.S[v] = (w & 0xFFFF0000u) | r;
+    wr = q;
     return r;
 }
 
 // uf.py:247-254 -- find with full path compression (single lane only)
 LUF_DEV uint32_t find_compress(const Shot& s, uint32_t v)
 {
-    uint32_t r = v, p;
-    while (!((p = s.P[r]) & ROOT_BIT)) r = p;
-    while (v != r) { p = s.P[v]; s.P[v] = (idx_t)r; v = p; }
+    uint32_t r = v, w;
+    while (!((w = s.S[r]) & ROOT_BIT)) r = w & SIZE_MASK;
+    while (v != r) { w = s.S[v]; s.S[v] = (w & 0xFFFF0000u) | r; v = w & SIZE_MASK; }
     return r;
+}
+
+// Compact the set bits of a bitmap into the work list: every lane owns a
+// contiguous range of words, reserves room for its bits with one atomic add
+// and writes `id0 + bit index` for each.  When the total exceeds the list the
+// consumers walk the bitmap itself (same per-item code, unbalanced lanes).
+LUF_DEV void gather_bits(const uint32_t* bm, int nwords, uint32_t id0, uint32_t* list, uint32_t* counter, int lane, int nl)
+{
+    const int wpl = (nwords + nl - 1) / nl;
+    const int w0 = lane * wpl, w1 = w0 + wpl < nwords ? w0 + wpl : nwords;
+    uint32_t c = 0;
+    for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(bm[w]);
+    if (!c) return;
+    uint32_t pos = luf_atomic_add(counter, c);
+    if (pos + c > LIST_CAP) return;
+    for (int w = w0; w < w1; ++w) {
+        uint32_t bits = bm[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            list[pos++] = id0 + (uint32_t)(32 * w + b);
+        }
+    }
+}
+
+// Run f(id) for every item: from the list if it held them all, else from the bitmap.
+template <class F>
+LUF_DEV void for_items(const uint32_t* bm, int nwords, uint32_t id0, const uint32_t* list, uint32_t total,
+                       int lane, int nl, F f)
+{
+    if (total <= LIST_CAP) {
+        for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) f(list[i]);
+    } else {
+        for (int w = lane; w < nwords; w += nl) {
+            uint32_t bits = bm[w];
+            while (bits) {
+                const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+                f(id0 + (uint32_t)(32 * w + b));
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------ phase 0: reset
 // uf.py:79-96,496-519 -- every node a singleton cluster; a boundary node is its
 // own cluster boundary.  (The reference re-allocates N Python objects here,
-// 40-58 % of its time; this is ~N*4 bytes of shared-memory stores.)
+// 40-58 % of its time; this is N*4 + ~3 KB of 16-byte shared-memory stores.)
+LUF_DEV uint32_t fresh_word(const GraphView& g, int v) { return ROOT_BIT | 1u | (v < g.B ? ((uint32_t)v + 1u) << 16 : 0u); }
+
 LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int lane, int nl)
 {
-    uint32_t* P2 = (uint32_t*)s.P;
-    uint32_t* R2 = (uint32_t*)s.R;
-    const uint32_t root1 = (ROOT_BIT | 1u) * 0x10001u;               // two singleton roots per 32-bit store
-    for (int v = 2 * lane; v < g.N; v += 2 * nl) {
-        P2[v >> 1] = root1;
-        R2[v >> 1] = (v < g.B ? (uint32_t)v + 1u : 0u) | ((v + 1 < g.B ? (uint32_t)v + 2u : 0u) << 16);
+    luf_u32x4* S4 = (luf_u32x4*)s.S;
+    for (int v = 4 * lane; v < g.N; v += 4 * nl) {
+        luf_u32x4 w;
+        w.x = fresh_word(g, v); w.y = fresh_word(g, v + 1); w.z = fresh_word(g, v + 2); w.w = fresh_word(g, v + 3);
+        S4[v >> 2] = w;
     }
-    const int GW = (g.E + 15) >> 4;
-    for (int w = lane; w < GW; w += nl) s.growth[w] = 0;
-    for (int w = lane; w < g.WE; w += nl) {
-        s.newfull[w] = 0;
-        if (s.err) s.err[w] = 0;
-        if (s.corr) s.corr[w] = 0;
-    }
-    for (int w = lane; w < g.WD; w += nl) s.defect[w] = 0;
-    for (int w = lane; w < g.WN; w += nl) { s.troot[w] = 0; s.touched[w] = 0; }
-    for (int w = lane; w < ((g.N + 15) >> 4); w += nl) s.deg[w] = 0;
+    luf_u32x4* Z4 = (luf_u32x4*)((unsigned char*)s.S + (l.zero_off - l.S));
+    luf_u32x4 z; z.x = z.y = z.z = z.w = 0u;
+    for (int i = lane; i < (int)(l.zero_bytes >> 4); i += nl) Z4[i] = z;
     for (int w = lane; w < CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu;
     if (lane < 4) s.cnt[lane] = 0;
-    (void)l;
 }
 
 // --------------------------------------------------- phase 1: sample + syndrome
@@ -307,15 +363,25 @@ LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams
 }
 
 // uf.py:98-104 load: every defect is an odd singleton cluster (hence active).
+// Also compacts the defects into the work list for the first growth round
+// (cnt[0] = their number; must be 0 on entry, ph_reset leaves it so).
 LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    for (int w = lane; w < g.WD; w += nl) {
+    const int wpl = (g.WD + nl - 1) / nl;
+    const int w0 = lane * wpl, w1 = w0 + wpl < g.WD ? w0 + wpl : g.WD;
+    uint32_t c = 0;
+    for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(s.defect[w]);
+    if (!c) return;
+    uint32_t pos = luf_atomic_add(&s.cnt[0], c);
+    const bool fits = pos + c <= LIST_CAP;
+    for (int w = w0; w < w1; ++w) {
         uint32_t bits = s.defect[w];
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             const uint32_t v = (uint32_t)(g.B + 32 * w + b);
-            s.R[v] = (idx_t)ODD_BIT;
+            s.S[v] = ODD_BIT | ROOT_BIT | 1u;
             luf_atomic_or(&s.touched[v >> 5], 1u << (v & 31u));
+            if (fits) s.list[pos++] = v;
         }
     }
 }
@@ -323,69 +389,109 @@ LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
 // ------------------------------------------------------- phase 2a: grow a round
 // uf.py:221-222,234-245.  vision(C) = edges incident to C's members that are not
 // yet FULL/BURNT; a cluster is active iff it is odd and has no boundary
-// (uf.py:296-301), i.e. R[root] == ODD_BIT.  Members are not kept in lists:
-// every *touched* node (defect, or member of a cluster of size > 1 -- singleton
-// non-defects are never active) looks its root up and grows its own incident
-// edges if the root is active.  An edge inside one cluster is in that cluster's
-// vision once: only its first endpoint adds.  Two different active clusters
-// each add 1.  The 2-bit counters saturate at FULL.  Returns whether this lane
-// saw an active node.
-// Two flag bits per node: "has a fully grown incident edge" / "has at least
-// two".  Set with atomicOr only, so concurrent lanes cannot overflow a field.
-LUF_DEV void deg_bump(const Shot& s, uint32_t v)
+// (uf.py:296-301), i.e. the upper half of its root word is exactly the odd
+// bit.  Members are not kept in lists: every *touched* node (a defect, or an
+// end of a fully grown edge -- other singletons are never active) looks its
+// root up and grows its own incident edges if the root is active.  An edge
+// inside one cluster is in that cluster's vision once: only its first endpoint
+// adds.  Two different active clusters each add 1.  The 2-bit counters
+// saturate at FULL.
+//
+// touched / full2 flags, set with atomicOr only.  full2 over-approximates
+// "two or more fully grown edges" for defects (their touched bit is set by
+// ph_load); it only decides whether the peel traversal may skip a leaf.
+LUF_DEV void bump(const Shot& s, uint32_t v)
 {
-    const uint32_t sh = (v & 15u) * 2u;
-    if ((luf_atomic_or(&s.deg[v >> 4], 1u << sh) >> sh) & 1u) luf_atomic_or(&s.deg[v >> 4], 2u << sh);
+    const uint32_t bit = 1u << (v & 31u);
+    if (luf_atomic_or(&s.touched[v >> 5], bit) & bit) luf_atomic_or(&s.full2[v >> 5], bit);
 }
-LUF_DEV bool deg_is_one(const Shot& s, uint32_t v) { return ((s.deg[v >> 4] >> ((v & 15u) * 2u)) & 3u) == 1u; }
+
+LUF_DEV void became_full(const Shot& s, uint32_t e, uint32_t u, uint32_t o)
+{
+    luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
+    bump(s, u); bump(s, o);
+}
+
+// First round: every cluster is a singleton and every edge ungrown, so each
+// defect adds 1 to all its edges with no look-ups; an edge is newly FULL iff
+// the other end got there first.
+LUF_DEV void grow_first_ent(const Shot& s, uint32_t v, uint32_t ent)
+{
+    if (ent == ADJ_PAD) return;
+    const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+    const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+    if (old == G_HALF) became_full(s, e, v, (ent >> 16) & 0x7FFFu);
+}
+
+LUF_DEV void grow_first(const GraphView& g, const Shot& s, uint32_t v)
+{
+    const uint32_t* row = g.adj + (size_t)v * (uint32_t)g.DEG;
+    for (int k = 0; k < g.DEG; k += 2) {
+        const luf_u32x2 p = LUF_LDG2(row + k);
+        grow_first_ent(s, v, p.x); grow_first_ent(s, v, p.y);
+    }
+}
+
+// Returns the number of defects (0 = nothing to decode).
+LUF_DEV uint32_t ph_grow_first(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    const uint32_t total = s.cnt[0];
+    for_items(s.defect, g.WD, (uint32_t)g.B, s.list, total, lane, nl, [&](uint32_t v) { grow_first(g, s, v); });
+    return total;
+}
+
+LUF_DEV void grow_ent(const Shot& s, uint32_t u, uint32_t r, uint32_t ent)
+{
+    if (ent == ADJ_PAD) return;
+    const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+    if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
+    const uint32_t o = (ent >> 16) & 0x7FFFu;
+    if (!(ent >> 31)) {                           // second endpoint: skip if same cluster
+        uint32_t wr;
+        if (o == r || find_ro(s, o, wr) == r) return;
+    }
+    const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+    if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
+    else if (old == G_HALF) became_full(s, e, u, o);
+}
 
 LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r)
 {
-    const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
-    for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
-        const uint32_t ent = LUF_LDG(&g.inc[k]);
-        const uint32_t e = ent & 0xFFFFu;
-        const uint32_t sh = (e & 15u) * 2u;
-        if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
-        if (!(ent >> 31)) {                       // second endpoint: skip if same cluster
-            const uint32_t o = (ent >> 16) & 0x7FFFu;
-            if (o == r || find_ro(s, o) == r) continue;
-        }
-        const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-        if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
-        else if (old == G_HALF) {                                           // newly FULL
-            luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
-            deg_bump(s, u); deg_bump(s, (ent >> 16) & 0x7FFFu);
-        }
+    const uint32_t* row = g.adj + (size_t)u * (uint32_t)g.DEG;
+    for (int k = 0; k < g.DEG; k += 2) {
+        const luf_u32x2 p = LUF_LDG2(row + k);
+        grow_ent(s, u, r, p.x); grow_ent(s, u, r, p.y);
     }
 }
 
-// Gather the active nodes into the work list (cheap per touched node), so that
-// the edge loops of ph_grow_exec are spread evenly over the lanes however the
-// defects are distributed over the bitmap words.
+// Later rounds: compact the touched nodes (cnt[0]; cnt[0] = cnt[1] = 0 on entry) ...
 LUF_DEV void ph_grow_gather(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    for (int w = lane; w < g.WN; w += nl) {
-        uint32_t bits = s.touched[w];
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t u = (uint32_t)(32 * w + b);
-            const uint32_t r = find_pc(s, u);
-            if (s.R[r] != ODD_BIT) continue;
-            const uint32_t idx = luf_atomic_add(&s.cnt[0], 1u);
-            if (idx < LIST_CAP) s.list[idx] = u | (r << 16);
-            else grow_node(g, s, u, r);
-        }
-    }
+    gather_bits(s.touched, g.WN, 0u, s.list, &s.cnt[0], lane, nl);
+    if (lane == 0) s.cnt[2] = 0;
 }
 
-// Returns whether any node was active this round.
+// ... keep those whose cluster is active (cnt[1], list2), one per lane ...
+LUF_DEV void ph_grow_filter(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    for_items(s.touched, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
+        uint32_t wr;
+        const uint32_t r = find_pc(s, u, wr);
+        if ((wr >> 16) != (ODD_BIT >> 16)) return;
+        const uint32_t idx = luf_atomic_add(&s.cnt[1], 1u);
+        if (idx < LIST2_CAP) s.list2[idx] = u | (r << 16);
+        else grow_node(g, s, u, r);
+    });
+}
+
+// ... and grow them, the edge loops spread evenly over the lanes.  Returns the
+// number of active nodes of the round.
 LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    const uint32_t total = s.cnt[0];
-    const uint32_t n = total < LIST_CAP ? total : LIST_CAP;
+    const uint32_t total = s.cnt[1];
+    const uint32_t n = total < LIST2_CAP ? total : LIST2_CAP;
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t it = s.list[i];
+        const uint32_t it = s.list2[i];
         grow_node(g, s, it & 0xFFFFu, it >> 16);
     }
     return total;
@@ -394,31 +500,30 @@ LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int lane, int n
 // ------------------------------------------------------------ phase 2b: merge
 // uf.py:223-229,256-301 in canonical order: this round's newly FULL edges are
 // merged in ascending edge id.  Union by size, ties keep the cluster of the
-// edge's first endpoint; parity XOR; boundary by inclination.  The smaller
-// root's R slot is dead after the union and keeps the union edge (used by the
-// peel for two-node clusters).
+// edge's first endpoint; parity XOR; boundary by inclination.  TF >= 0 fixes
+// the decoder flags at compile time (the fused kernel), TF < 0 reads `flags`.
+template <int TF>
 LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t e, uint32_t cu, uint32_t cv)
 {
-    if (flags & FLAG_DYNAMIC) {                                   // uf.py:261-266
-        if (cu == cv || ((s.R[cu] & 0x7FFFu) && (s.R[cv] & 0x7FFFu))) {
+    const int f = TF >= 0 ? TF : flags;
+    const uint32_t wu = s.S[cu], wv = s.S[cv];
+    if (f & FLAG_DYNAMIC) {                                       // uf.py:261-266
+        if (cu == cv || ((wu & BND_MASK) && (wv & BND_MASK))) {
             luf_atomic_or(&s.growth[e >> 4], 3u << ((e & 15u) * 2u));     // FULL(2) -> BURNT(3)
             return;
         }
     } else if (cu == cv) return;                                  // uf.py:256-259
-    const uint32_t su = s.P[cu] & 0x7FFFu, sv = s.P[cv] & 0x7FFFu;
-    const uint32_t L = su >= sv ? cu : cv, S = su >= sv ? cv : cu;    // uf.py:270-273
-    const uint32_t rl = s.R[L], rs = s.R[S];
-    uint32_t bl = rl & 0x7FFFu;
-    const uint32_t bs = rs & 0x7FFFu;
-    if (flags & FLAG_WEST) {                                      // uf.py:544-549
-        if (bs && (!bl || LUF_LDG(&g.node_long[bs - 1]) < LUF_LDG(&g.node_long[bl - 1]))) bl = bs;
-    } else if (!bl && bs) bl = bs;                                // uf.py:536-538
-    s.R[L] = (idx_t)(((rl ^ rs) & ODD_BIT) | bl);
-    s.R[S] = (idx_t)e;
-    s.P[L] = (idx_t)(ROOT_BIT | (su + sv));
-    s.P[S] = (idx_t)L;
-    if (su == 1u) luf_atomic_or(&s.touched[cu >> 5], 1u << (cu & 31u));   // no longer a singleton
-    if (sv == 1u) luf_atomic_or(&s.touched[cv >> 5], 1u << (cv & 31u));
+    const uint32_t su = wu & SIZE_MASK, sv = wv & SIZE_MASK;
+    const bool ul = su >= sv;                                     // uf.py:270-273
+    const uint32_t L = ul ? cu : cv, Sm = ul ? cv : cu;
+    const uint32_t wl = ul ? wu : wv, ws = ul ? wv : wu;
+    uint32_t bl = wl & BND_MASK;
+    const uint32_t bs = ws & BND_MASK;
+    if (f & FLAG_WEST) {                                          // uf.py:544-549
+        if (bs && (!bl || LUF_LDG(&g.node_long[(bs >> 16) - 1]) < LUF_LDG(&g.node_long[(bl >> 16) - 1]))) bl = bs;
+    } else if (!bl) bl = bs;                                      // uf.py:536-538
+    s.S[L] = ((wl ^ ws) & ODD_BIT) | bl | ROOT_BIT | (su + sv);
+    s.S[Sm] = L | (e << 16);
 }
 
 // The serial order is reproduced in parallel by deterministic reservations:
@@ -429,81 +534,49 @@ LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t 
 // touch -- those clusters before it, so running it now commutes with
 // everything the serial order would have run before it.  Winners of one
 // iteration touch pairwise disjoint clusters and run concurrently; losers
-// retry.  Slots are hashed (collisions only add ordering, never remove it) and
-// tagged with a decreasing iteration number, so stale entries always lose and
-// the table needs no clearing.
+// retry: a star of k edges around one cluster takes k iterations, all stars
+// side by side.  Slots are hashed (collisions only add ordering, never remove
+// it) and tagged with a decreasing iteration number, so stale entries always
+// lose and the table needs no clearing.
 LUF_DEV uint32_t claim_slot(uint32_t root) { return (root * 0x9E5u >> 3) & (uint32_t)(CLAIM_SLOTS - 1); }
 
-LUF_DEV void ph_merge_claim(const GraphView& g, const Shot& s, uint32_t tag, int lane, int nl)
+// Compact this round's newly FULL edges into the list
+// (cnt[2] = their number; 0 on entry).
+LUF_DEV void ph_merge_gather(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    for (int w = lane; w < g.WE; w += nl) {
-        uint32_t bits = s.newfull[w];
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t e = (uint32_t)(32 * w + b);
-            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-            const uint32_t cu = find_pc(s, uv & 0xFFFFu), cv = find_pc(s, uv >> 16);
-            luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
-            luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
-        }
-    }
+    gather_bits(s.newfull, g.WE, 0u, s.list, &s.cnt[2], lane, nl);
+    if (lane == 0) { s.cnt[0] = 0; s.cnt[1] = 0; }
 }
 
-// Returns whether this lane still has pending edges.
-LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uint32_t tag, int lane, int nl)
+template <int TF>
+LUF_DEV void ph_merge_claim(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, bool first, int lane, int nl)
 {
-    uint32_t pending = 0;
-    for (int w = lane; w < g.WE; w += nl) {
-        uint32_t bits = s.newfull[w], keep = 0;
-        if (!bits) continue;
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t e = (uint32_t)(32 * w + b);
-            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-            const uint32_t cu = find_ro(s, uv & 0xFFFFu), cv = find_ro(s, uv >> 16);
-            if (s.claim[claim_slot(cu)] == (tag | e) && s.claim[claim_slot(cv)] == (tag | e))
-                union_roots(g, s, flags, e, cu, cv);
-            else
-                keep |= 1u << b;
-        }
-        s.newfull[w] = keep;
-        pending |= keep;
+    if (first) {                                  // the edges live in the list now
+        const int wpl = (g.WE + nl - 1) / nl;
+        const int w1 = (lane + 1) * wpl < g.WE ? (lane + 1) * wpl : g.WE;
+        for (int w = lane * wpl; w < w1; ++w) s.newfull[w] = 0;
     }
-    return pending;
-}
-
-// What the first reservation round could not place (stars around one defect,
-// chains, hash collisions) continues as further reservation rounds over a
-// compact work list, one pending edge per lane: the lowest-id pending edge of
-// every cluster wins each round, so a star of k edges takes k rounds, all
-// stars side by side.
-LUF_DEV void ph_rest_gather(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    for (int w = lane; w < g.WE; w += nl) {
-        uint32_t bits = s.newfull[w];
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t idx = luf_atomic_add(&s.cnt[1], 1u);
-            if (idx < LIST_CAP) s.list[idx] = (uint32_t)(32 * w + b);
-        }
-    }
-}
-
-LUF_DEV void ph_rest_claim(const GraphView& g, const Shot& s, uint32_t n, uint32_t tag, int lane, int nl)
-{
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
         const uint32_t it = s.list[i];
         if (it == LIST_DONE) continue;
         const uint32_t e = it & 0xFFFFu;
         const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-        const uint32_t cu = find_pc(s, uv & 0xFFFFu), cv = find_pc(s, uv >> 16);
+        uint32_t wr;
+        const uint32_t cu = find_pc(s, first ? (uv & 0xFFFFu) : (it >> 16), wr), cv = find_pc(s, uv >> 16, wr);
+        if (cu == cv) {                           // inside one cluster whatever runs before it
+            union_roots<TF>(g, s, flags, e, cu, cv);
+            s.list[i] = LIST_DONE;
+            continue;
+        }
         luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
         luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
-        s.list[i] = e | (cu << 16);           // the root of the first endpoint cannot change before this edge runs
+        s.list[i] = e | (cu << 16);               // the root of the first endpoint cannot change before this edge runs
     }
 }
 
-LUF_DEV uint32_t ph_rest_exec(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, int lane, int nl)
+// Returns whether this lane still has pending edges.
+template <int TF>
+LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, int lane, int nl)
 {
     uint32_t pending = 0;
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
@@ -511,18 +584,20 @@ LUF_DEV uint32_t ph_rest_exec(const GraphView& g, const Shot& s, int flags, uint
         if (it == LIST_DONE) continue;
         const uint32_t e = it & 0xFFFFu, cu = it >> 16;
         if (s.claim[claim_slot(cu)] != (tag | e)) { pending = 1; continue; }
-        const uint32_t cv = find_ro(s, LUF_LDG(&g.edge_uv[e]) >> 16);
+        uint32_t wr;
+        const uint32_t cv = find_ro(s, LUF_LDG(&g.edge_uv[e]) >> 16, wr);
         if (s.claim[claim_slot(cv)] == (tag | e)) {
-            union_roots(g, s, flags, e, cu, cv);
+            union_roots<TF>(g, s, flags, e, cu, cv);
             s.list[i] = LIST_DONE;
         } else pending = 1;
     }
     return pending;
 }
 
-// Overflow path (more pending edges than the list holds): one lane merges them
-// in ascending edge id, with path compression.  `mask` tells it which of the
-// 32 words from `base` on still hold edges.
+// Overflow path (more newly FULL edges than the list holds): one lane merges
+// them in ascending edge id, with path compression.  `mask` tells it which of
+// the 32 words from `base` on still hold edges.
+template <int TF>
 LUF_DEV void merge_rest(const GraphView& g, const Shot& s, int flags, int base, uint32_t mask)
 {
     while (mask) {
@@ -534,7 +609,7 @@ LUF_DEV void merge_rest(const GraphView& g, const Shot& s, int flags, int base, 
             const uint32_t e = (uint32_t)(32 * w + b);
             const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
             const uint32_t cu = find_compress(s, uv & 0xFFFFu), cv = find_compress(s, uv >> 16);
-            union_roots(g, s, flags, e, cu, cv);
+            union_roots<TF>(g, s, flags, e, cu, cv);
         }
     }
 }
@@ -545,102 +620,100 @@ LUF_DEV void merge_rest(const GraphView& g, const Shot& s, int flags, int base, 
 // edge, so only clusters of defects are rooted.
 //
 // Two-node clusters (the common case at low noise: one flipped edge) need no
-// traversal: their only tree is the union edge, kept in the R slot of the
-// member that is not the root, and it is in the correction iff the cluster
-// holds a defect.  Exactly one member acts: the non-root member if it is a
-// defect; else the root, whose partner is then the cluster's boundary node
-// (an odd cluster that stopped growing has one).
+// traversal: their only tree is the union edge, kept in the word of the member
+// that is not the root, and it is in the correction iff the cluster holds a
+// defect.  Exactly one member acts: the non-root member if it is a defect;
+// else the root, whose partner is then the cluster's boundary node (an odd
+// cluster that stopped growing has one).
+//
+// Entry state: cnt[0..2] = 0 and the visited bitmap (aliasing the claim table) cleared.
+LUF_DEV void ph_peel_gather(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    gather_bits(s.defect, g.WD, (uint32_t)g.B, s.list, &s.cnt[0], lane, nl);
+}
+
 // Returns this lane's parity of pair corrections on the west boundary and
-// (bit 1) whether any cluster needs the general traversal.
+// (bit 1) whether any cluster needs the general traversal.  Tree roots go to
+// list2 (cnt[1]); their bit in the troot bitmap (= newfull, idle by now)
+// de-duplicates them and serves the overflow path.
 LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int nl)
 {
     uint32_t out = 0;
-    for (int w = lane; w < g.WD; w += nl) {
-        uint32_t bits = s.defect[w];
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t dn = (uint32_t)(g.B + 32 * w + b);
-            const uint32_t r = find_ro(s, dn);
-            const uint32_t rr = s.R[r];
-            if ((s.P[r] & 0x7FFFu) == 2u) {
-                uint32_t x = dn;                                  // the member whose R slot holds the union edge
-                if (dn == r) {
-                    if (!(rr & ODD_BIT)) continue;                // both are defects: the other member acts
-                    x = (rr & 0x7FFFu) - 1u;                      // single defect: its partner is the boundary node
-                }
-                const uint32_t e = s.R[x];
-                if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
-                out ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
-                continue;
+    uint32_t* troot = s.newfull;
+    for_items(s.defect, g.WD, (uint32_t)g.B, s.list, s.cnt[0], lane, nl, [&](uint32_t dn) {
+        uint32_t rr;
+        const uint32_t r = find_ro(s, dn, rr);
+        if ((rr & SIZE_MASK) == 2u) {
+            uint32_t x = dn;                                  // the member whose word holds the union edge
+            if (dn == r) {
+                if (!(rr & ODD_BIT)) return;                  // both are defects: the other member acts
+                x = ((rr & BND_MASK) >> 16) - 1u;             // single defect: its partner is the boundary node
             }
-            const uint32_t bn = rr & 0x7FFFu;
-            const uint32_t t = bn ? bn - 1u : r;
-            luf_atomic_or(&s.troot[t >> 5], 1u << (t & 31u));
-            out |= 2u;
+            const uint32_t e = s.S[x] >> 16;
+            if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
+            out ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
+            return;
         }
-    }
+        const uint32_t bn = (rr & BND_MASK) >> 16;
+        const uint32_t t = bn ? bn - 1u : r;
+        out |= 2u;
+        const uint32_t bit = 1u << (t & 31u);
+        if (luf_atomic_or(&troot[t >> 5], bit) & bit) return;
+        const uint32_t idx = luf_atomic_add(&s.cnt[1], 1u);
+        if (idx < LIST2_CAP) s.list2[idx] = t;
+    });
     return out;
 }
 
-// The union-find arrays are dead now; reuse them for the traversal:
-//   P -> tree edge towards the root (NONE16 = undiscovered)    R -> link of the LIFO stack
+// The union-find forest is dead now; the node words are re-used by the traversal:
+//   bits 0..15 tree edge towards the root    bits 16..31 link of the LIFO stack
 // uf.py:326-344: the reference's LIFO traversal (neighbours in ascending edge
 // id) from a tree root; only the tree (the edge towards the root of every
-// discovered node) is kept.
+// discovered node) is kept.  `visited` marks discovered nodes.
 LUF_DEV void build_tree(const GraphView& g, const Shot& s, uint32_t root)
 {
-    idx_t* tedge = s.P; idx_t* stk = s.R;
-    tedge[root] = (idx_t)TREE_ROOT;
-    stk[root] = (idx_t)NONE16;
+    uint32_t* visited = s.claim;
+    luf_atomic_or(&visited[root >> 5], 1u << (root & 31u));
+    s.S[root] = TREE_ROOT | (NONE16 << 16);
     uint32_t top = root;
     while (top != NONE16) {
         const uint32_t u = top;
-        top = stk[u];
-        const uint32_t k1 = LUF_LDG(&g.inc_off[u + 1]);
-        for (uint32_t k = LUF_LDG(&g.inc_off[u]); k < k1; ++k) {
-            const uint32_t ent = LUF_LDG(&g.inc[k]);
+        top = s.S[u] >> 16;
+        const uint32_t* row = g.adj + (size_t)u * (uint32_t)g.DEG;
+        for (int k = 0; k < g.DEG; ++k) {
+            const uint32_t ent = LUF_LDG(&row[k]);
+            if (ent == ADJ_PAD) break;
             const uint32_t e = ent & 0xFFFFu;
             if (growth_of(s, e) != G_FULL) continue;
             const uint32_t o = (ent >> 16) & 0x7FFFu;
-            if (tedge[o] != NONE16) continue;
-            tedge[o] = (idx_t)e;
-            if (deg_is_one(s, o)) continue;       // a leaf: nothing to discover from it
-            stk[o] = (idx_t)top; top = o;
+            const uint32_t bit = 1u << (o & 31u);
+            if (visited[o >> 5] & bit) continue;
+            luf_atomic_or(&visited[o >> 5], bit);
+            if (!(s.full2[o >> 5] & bit)) { s.S[o] = e | (NONE16 << 16); continue; }   // a leaf: nothing to discover from it
+            s.S[o] = e | (top << 16); top = o;
         }
     }
 }
 
-// one lane per tree root, roots handed out through the work list
-LUF_DEV void ph_peel_gather(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    uint32_t* P2 = (uint32_t*)s.P;
-    for (int v = lane; 2 * v < g.N; v += nl) P2[v] = 0xFFFFFFFFu;        // every node undiscovered
-    for (int w = lane; w < g.WN; w += nl) {
-        uint32_t bits = s.troot[w], keep = 0;
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t idx = luf_atomic_add(&s.cnt[2], 1u);
-            if (idx < LIST_CAP) s.list[idx] = (uint32_t)(32 * w + b);
-            else keep |= 1u << b;                                        // overflow: stays in the bitmap
-        }
-        s.troot[w] = keep;
-    }
-}
-
+// one lane per tree root
 LUF_DEV void ph_peel_build(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    const uint32_t total = s.cnt[2];
-    const uint32_t n = total < LIST_CAP ? total : LIST_CAP;
-    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) build_tree(g, s, s.list[i]);
-    if (total > LIST_CAP)                                              // overflow roots, by bitmap word
-        for (int w = lane; w < g.WN; w += nl) {
-            uint32_t bits = s.troot[w];
-            s.troot[w] = 0;
-            while (bits) {
-                const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-                build_tree(g, s, (uint32_t)(32 * w + b));
-            }
+    const uint32_t total = s.cnt[1];
+    const uint32_t n = total < LIST2_CAP ? total : LIST2_CAP;
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) build_tree(g, s, s.list2[i]);
+}
+
+// overflow: roots that did not fit the list are still undiscovered; by bitmap word
+LUF_DEV void ph_peel_build_rest(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    const uint32_t* troot = s.newfull;
+    for (int w = lane; w < g.WN; w += nl) {
+        uint32_t bits = troot[w] & ~s.claim[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            build_tree(g, s, (uint32_t)(32 * w + b));
         }
+    }
 }
 
 // uf.py:305-312: peeling the forest leaf-up puts a tree edge in the correction
@@ -650,70 +723,71 @@ LUF_DEV void ph_peel_build(const GraphView& g, const Shot& s, int lane, int nl)
 // here).  Returns this lane's parity of correction edges on the west boundary.
 LUF_DEV uint32_t ph_peel_paths(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    const idx_t* tedge = s.P;
     uint32_t parity = 0;
-    for (int w = lane; w < g.WD; w += nl) {
-        uint32_t bits = s.defect[w];
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            uint32_t v = (uint32_t)(g.B + 32 * w + b);
-            uint32_t e = tedge[v];
-            if (e == NONE16) continue;
-            while (e != TREE_ROOT) {
-                if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
-                parity ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
-                const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-                v = (uv & 0xFFFFu) == v ? (uv >> 16) : (uv & 0xFFFFu);
-                e = tedge[v];
-            }
+    const uint32_t* visited = s.claim;
+    for_items(s.defect, g.WD, (uint32_t)g.B, s.list, s.cnt[0], lane, nl, [&](uint32_t v) {
+        if (!bit_of(visited, v)) return;
+        uint32_t e = s.S[v] & 0xFFFFu;
+        while (e != TREE_ROOT) {
+            if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
+            parity ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
+            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+            v = (uv & 0xFFFFu) == v ? (uv >> 16) : (uv & 0xFFFFu);
+            e = s.S[v] & 0xFFFFu;
         }
-    }
+    });
     return parity;
 }
 
 // ------------------------------------------------------------------ drivers
 // uf.py:200-209 validate: rounds of grow / merge until no cluster is active.
 // Returns the number of growth rounds.  `lane` is this thread's lane on the
-// device; the host emulation iterates it inside LUF_PHASE.
-LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, int nl)
+// device; the host emulation iterates it inside LUF_PHASE.  Expects ph_load
+// to have run just before (defects in the work list).
+template <int TF>
+LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane, int nl)
 {
     int rounds = 0;
     uint32_t iter = 0xFFFFu;                 // decreasing reservation tag
     (void)lane;
     for (;;) {
         uint32_t active = 0;
-        LUF_PHASE(ph_grow_gather(g, s, lane, nl));
-        LUF_PHASE(active |= ph_grow_exec(g, s, lane, nl));
+        if (rounds == 0) {
+            LUF_PHASE(active |= ph_grow_first(g, s, lane, nl));
+        } else {
+            LUF_PHASE(ph_grow_gather(g, s, lane, nl));
+            LUF_PHASE(ph_grow_filter(g, s, lane, nl));
+            LUF_PHASE(active |= ph_grow_exec(g, s, lane, nl));
+        }
         if (!LUF_ANY(active)) break;
-        // one reservation round over the bitmap places the independent merges ...
-        uint32_t tag = iter-- << 16, pending = 0;
-        LUF_PHASE(ph_merge_claim(g, s, tag, lane, nl); if (lane == 0) s.cnt[0] = 0);
-        LUF_PHASE(pending |= ph_merge_exec(g, s, flags, tag, lane, nl));
-        if (LUF_ANY(pending)) {              // ... the rest goes on over a compact list
-            LUF_PHASE(ph_rest_gather(g, s, lane, nl));
-            uint32_t n = 0;
-            LUF_PHASE(n = s.cnt[1]);
-            if (n <= LIST_CAP) {
-                LUF_PHASE(for (int w = lane; w < g.WE; w += nl) s.newfull[w] = 0; if (lane == 0) s.cnt[1] = 0);
-                for (uint32_t guard = 0; guard <= n; ++guard) {       // at least one edge is placed per round
-                    tag = iter-- << 16; pending = 0;
-                    LUF_PHASE(ph_rest_claim(g, s, n, tag, lane, nl));
-                    LUF_PHASE(pending |= ph_rest_exec(g, s, flags, n, tag, lane, nl));
-                    if (!LUF_ANY(pending)) break;
-                }
-            } else {                         // overflow: one lane, ascending edge id
-                LUF_PHASE(if (lane == 0) s.cnt[1] = 0);
-                for (int base = 0; base < g.WE; base += 32) {
-                    uint32_t mask;
-                    LUF_BALLOT(mask, base + lane < g.WE && s.newfull[base + lane] != 0);
-                    if (mask) { LUF_PHASE(if (lane == 0) merge_rest(g, s, flags, base, mask)); }
-                }
+        ++rounds;
+        uint32_t n = 0;
+        LUF_PHASE(ph_merge_gather(g, s, lane, nl));
+        LUF_PHASE(n = s.cnt[2]);
+        if (n <= LIST_CAP) {
+            for (uint32_t guard = 0; guard <= n; ++guard) {           // at least one edge is placed per iteration
+                const uint32_t tag = iter-- << 16;
+                uint32_t pending = 0;
+                LUF_PHASE(ph_merge_claim<TF>(g, s, flags, n, tag, guard == 0, lane, nl));
+                LUF_PHASE(pending |= ph_merge_exec<TF>(g, s, flags, n, tag, lane, nl));
+                if (!LUF_ANY(pending)) break;
+            }
+        } else {                             // overflow: one lane, ascending edge id, straight from the bitmap
+            for (int base = 0; base < g.WE; base += 32) {
+                uint32_t mask;
+                LUF_BALLOT(mask, base + lane < g.WE && s.newfull[base + lane] != 0);
+                if (mask) { LUF_PHASE(if (lane == 0) merge_rest<TF>(g, s, flags, base, mask)); }
             }
         }
-        ++rounds;
     }
-    LUF_PHASE(if (lane == 0) s.cnt[0] = 0);
+    // hand over to the peel: counters cleared, visited bitmap (in the claim table) cleared
+    LUF_PHASE(if (lane < 3) s.cnt[lane] = 0; for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0);
     return rounds;
+}
+
+LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, int nl)
+{
+    return uf_validate_t<-1>(g, s, flags, lane, nl);
 }
 
 // uf.py:305-312 peel.  Returns (per lane on the device, total in the
@@ -722,11 +796,13 @@ LUF_DEV uint32_t uf_peel(const GraphView& g, const Shot& s, int lane, int nl)
 {
     uint32_t parity = 0, general = 0;
     (void)lane;
+    LUF_PHASE(ph_peel_gather(g, s, lane, nl));
     LUF_PHASE(const uint32_t r = ph_tree_roots(g, s, lane, nl); parity ^= r & 1u; general |= r >> 1);
     if (LUF_ANY(general)) {
-        LUF_PHASE(ph_peel_gather(g, s, lane, nl));
-        LUF_PHASE(ph_peel_build(g, s, lane, nl));
-        LUF_PHASE(parity ^= ph_peel_paths(g, s, lane, nl); if (lane == 0) s.cnt[2] = 0);
+        uint32_t roots = 0;
+        LUF_PHASE(ph_peel_build(g, s, lane, nl); roots = s.cnt[1]);
+        if (roots > LIST2_CAP) { LUF_PHASE(ph_peel_build_rest(g, s, lane, nl)); }
+        LUF_PHASE(parity ^= ph_peel_paths(g, s, lane, nl));
     }
     return parity;
 }

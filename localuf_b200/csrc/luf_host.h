@@ -5,6 +5,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <algorithm>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -23,7 +24,8 @@ struct luf_graph_desc_dims { int N, B, E, n_classes; };
 
 struct PackedGraph {
     int N = 0, B = 0, E = 0, F = 0, n_classes = 0;
-    std::vector<uint32_t> inc_off, inc, edge_uv, west_mask, class_end;
+    int DEG = 0;
+    std::vector<uint32_t> adj, edge_uv, west_mask, class_end;
     std::vector<int16_t> node_long;
     std::vector<uint16_t> fresh_perm;
 };
@@ -37,8 +39,6 @@ inline std::string pack_graph(const luf_graph_desc& d, PackedGraph& out)
         return "graph too large for the 16-bit state layout (N <= 32767, E <= 65533)";
     if (d.n_classes < 1 || d.n_classes > MAX_CLASSES) return "n_classes out of range";
     out.N = N; out.B = B; out.E = E; out.n_classes = d.n_classes;
-    out.inc_off.assign(N + 1, 0);
-    out.inc.assign(2 * (size_t)E, 0);
     out.edge_uv.assign(E, 0);
     out.node_long.assign(N, 0);
     for (int e = 0; e < E; ++e) {
@@ -50,8 +50,11 @@ inline std::string pack_graph(const luf_graph_desc& d, PackedGraph& out)
         if (((d.node_flags[v] & 1) != 0) != (v < B)) return "boundary nodes must be node indices [0, B)";
         out.node_long[v] = (int16_t)d.node_long[v];
     }
-    for (int v = 0; v <= N; ++v) out.inc_off[v] = (uint32_t)d.inc_off[v];
     if (d.inc_off[N] != 2 * E) return "CSR size mismatch";
+    int deg = 2;
+    for (int v = 0; v < N; ++v) deg = std::max(deg, d.inc_off[v + 1] - d.inc_off[v]);
+    out.DEG = (deg + 1) & ~1;                     // rows of adj are read as 64-bit pairs
+    out.adj.assign((size_t)N * out.DEG, ADJ_PAD);
     for (int v = 0; v < N; ++v) {
         int prev = -1;
         for (int k = d.inc_off[v]; k < d.inc_off[v + 1]; ++k) {
@@ -61,7 +64,7 @@ inline std::string pack_graph(const luf_graph_desc& d, PackedGraph& out)
             const bool first = d.edge_u[e] == v;
             if ((first ? d.edge_v[e] : d.edge_u[e]) != o || (!first && d.edge_v[e] != v))
                 return "CSR entry does not match the edge list";
-            out.inc[k] = (uint32_t)e | ((uint32_t)o << 16) | (first ? 0x80000000u : 0u);
+            out.adj[(size_t)v * out.DEG + (k - d.inc_off[v])] = (uint32_t)e | ((uint32_t)o << 16) | (first ? 0x80000000u : 0u);
         }
     }
     out.west_mask.assign(d.west_edge_mask, d.west_edge_mask + words32(E));
@@ -85,16 +88,16 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr)
     uint32_t off = 0;
     auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
     const uint32_t WE = words32(E), WD = words32(N - B) ? words32(N - B) : 1, WN = words32(N);
-    l.P = take(2u * (N + 1)); l.R = take(2u * (N + 1));
+    l.S = take(16u * ((N + 3) / 4));
+    l.zero_off = off;                                 // ---- cleared by ph_reset
     l.growth = take(4u * ((E + 15) / 16));
-    l.newfull = take(4u * (WE > WN ? WE : WN));
-    l.troot = l.newfull;                              // the peel runs after the last merge round
-    l.defect = take(4u * WD); l.touched = take(4u * WN);
-    l.deg = take(4u * ((N + 15) / 16));
-    l.claim = take(4u * CLAIM_SLOTS);
-    l.list = take(4u * LIST_CAP); l.cnt = take(16);
+    l.newfull = take(4u * (WE > WN ? WE : WN));       // tree-root bitmap of the peel (after the last merge round)
+    l.defect = take(4u * WD); l.touched = take(4u * WN); l.full2 = take(4u * WN);
     l.err = keep_err ? take(4u * WE) : 0;
     l.corr = keep_corr ? take(4u * WE) : 0;
+    l.zero_bytes = off - l.zero_off;                  // ----
+    l.claim = take(4u * ((uint32_t)CLAIM_SLOTS > WN ? (uint32_t)CLAIM_SLOTS : WN));   // visited bitmap of the peel
+    l.list = take(4u * LIST_CAP); l.list2 = take(4u * LIST2_CAP); l.cnt = take(16);
     l.bytes = off;
     return l;
 }

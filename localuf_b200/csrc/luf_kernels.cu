@@ -51,7 +51,8 @@ __device__ __forceinline__ unsigned char* warp_slice(const Layout& l)
 }
 
 // Fused K1 + K2 + K4 for the UF decoder, batch scheme (_schemes.py:116-155).
-__global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
+template <int TF>
+__global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleParams sp,
                         unsigned long long shot0, long long nshots, unsigned long long* counts)
 {
     const int lane = threadIdx.x & 31, nl = WARP;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleP
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
         LUF_PHASE(ph_load(g, s, lane, nl));
-        uf_validate(g, s, flags, lane, nl);
+        uf_validate_t<TF>(g, s, TF, lane, nl);
         parity ^= uf_peel(g, s, lane, nl);
         fails += LUF_XOR(parity) & 1u;
     }
@@ -625,10 +626,10 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     cudaDeviceGetAttribute(&g->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const PackedGraph& p = g->host;
     GraphView& v = g->view;
-    v.N = p.N; v.B = p.B; v.E = p.E; v.F = p.F; v.n_classes = p.n_classes;
+    v.N = p.N; v.B = p.B; v.E = p.E; v.F = p.F; v.n_classes = p.n_classes; v.DEG = p.DEG;
     v.WE = words32(p.E); v.WD = words32(p.N - p.B); v.WN = words32(p.N);
     int rc = 0;
-    if ((rc = upload(g, p.inc_off, &v.inc_off)) || (rc = upload(g, p.inc, &v.inc)) ||
+    if ((rc = upload(g, p.adj, &v.adj)) ||
         (rc = upload(g, p.edge_uv, &v.edge_uv)) || (rc = upload(g, p.west_mask, &v.west_mask)) ||
         (rc = upload(g, p.node_long, &v.node_long)) || (rc = upload(g, p.fresh_perm, &v.fresh_perm)) ||
         (rc = upload(g, p.class_end, &v.class_end))) {
@@ -785,8 +786,16 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
         k_mc_ca<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_actis, sp, flags,
                                                                           shot0, nshots, counts_dev);
     } else {
-        if (int rc = plan_launch(g, k_mc_uf, g->lay_fused.bytes, nshots, &c, 14)) return rc;
-        k_mc_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, shot0, nshots, counts_dev);
+        // the decoder flags are compile-time constants of the fused kernel
+#define LUF_MC_UF(TF) { if (int rc = plan_launch(g, k_mc_uf<TF>, g->lay_fused.bytes, nshots, &c, 14)) return rc; \
+        k_mc_uf<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, shot0, nshots, counts_dev); }
+        switch (flags & 3) {
+            case 0: LUF_MC_UF(0) break;
+            case 1: LUF_MC_UF(1) break;
+            case 2: LUF_MC_UF(2) break;
+            default: LUF_MC_UF(3) break;
+        }
+#undef LUF_MC_UF
     }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;

@@ -19,7 +19,7 @@ static GraphView view_of(const PackedGraph& p)
     GraphView g;
     g.N = p.N; g.B = p.B; g.E = p.E;
     g.WE = words32(p.E); g.WD = words32(p.N - p.B); g.WN = words32(p.N);
-    g.inc_off = p.inc_off.data(); g.inc = p.inc.data(); g.edge_uv = p.edge_uv.data();
+    g.DEG = p.DEG; g.adj = p.adj.data(); g.edge_uv = p.edge_uv.data();
     g.west_mask = p.west_mask.data(); g.node_long = p.node_long.data();
     g.F = p.F; g.n_classes = p.n_classes;
     g.fresh_perm = p.fresh_perm.data(); g.class_end = p.class_end.data();
