@@ -16,7 +16,8 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'libluf_b200.so')
+# LUF_B200_LIB: an alternative build of the same sources (tools/variants.py), never a different implementation
+LIB_PATH = os.environ.get('LUF_B200_LIB') or os.path.join(HERE, 'csrc', 'libluf_b200.so')
 
 DEC_UF, DEC_MACAR, DEC_ACTIS, DEC_SNOWFLAKE = 0, 1, 2, 3
 UF_DYNAMIC, UF_WEST, ACTIS_UNOPTIMAL = 1, 2, 4

@@ -36,6 +36,14 @@
   struct luf_u32x2 { uint32_t x, y; };
   struct luf_u32x4 { uint32_t x, y, z, w; };
   #define LUF_LDG2(p) (*(const luf_u32x2*)(p))
+  // lanes run one after the other: the counts are stored by one phase and summed in the next
+  static uint32_t luf_scan_scratch[64];
+  #define LUF_SCAN_PREP(expr) LUF_PHASE(luf_scan_scratch[lane] = (expr))
+  static inline void luf_exscan(uint32_t c, int lane, int nl, uint32_t& pos, uint32_t& total)
+  {
+      (void)c; pos = 0; total = 0;
+      for (int j = 0; j < nl; ++j) { if (j < lane) pos += luf_scan_scratch[j]; total += luf_scan_scratch[j]; }
+  }
   #define LUF_LDG(p) (*(p))
   // a phase = every lane of the tile runs `stmt`, then the tile synchronises
   #define LUF_PHASE(stmt) for (int lane = 0; lane < nl; ++lane) { stmt; }
@@ -43,6 +51,7 @@
   // emulation accumulates into one variable, so they are identities there)
   #define LUF_ANY(x) ((x) != 0)
   #define LUF_XOR(x) (x)
+  #define LUF_SUM(x) (x)
   #define LUF_BALLOT(var, pred) { var = 0; for (int lane = 0; lane < nl; ++lane) if (pred) var |= 1u << lane; }
   static inline uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 #else
@@ -60,12 +69,30 @@
   typedef uint2 luf_u32x2;
   typedef uint4 luf_u32x4;
   #define LUF_LDG2(p) __ldg((const uint2*)(p))
+  #define LUF_SCAN_PREP(expr)
+  // exclusive prefix sum of c over the lanes of the warp
+  LUF_DEV void luf_exscan(uint32_t c, int lane, int nl, uint32_t& pos, uint32_t& total)
+  {
+      uint32_t x = c;
+      #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+      pos = x - c; total = __shfl_sync(0xffffffffu, x, 31); (void)nl;
+  }
   #define LUF_LDG(p) __ldg(p)
   #define LUF_PHASE(stmt) { stmt; } __syncwarp();
   #define LUF_ANY(x) __any_sync(0xffffffffu, (x) != 0)
   #define LUF_XOR(x) __reduce_xor_sync(0xffffffffu, (x))
+  #define LUF_SUM(x) __reduce_add_sync(0xffffffffu, (x))
   #define LUF_BALLOT(var, pred) { var = __ballot_sync(0xffffffffu, (pred)); }
   LUF_DEV uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
+#endif
+
+// Optional event counters of the host emulation (tools/uf_stats.py); compiled out everywhere else.
+#if defined(LUF_HOST_EMU) && defined(LUF_STATS)
+  extern "C" { unsigned long long luf_stats[32]; }
+  #define LUF_STAT(i, x) (luf_stats[i] += (unsigned long long)(x))
+#else
+  #define LUF_STAT(i, x) ((void)0)
 #endif
 
 namespace luf {
@@ -126,8 +153,8 @@ struct Layout {
     uint32_t growth;                    // uint32[ceil(E/16)]  2 bits per edge
     uint32_t newfull;                   // uint32[max(WE,WN)]  edges that reached FULL this round; tree roots during the peel
     uint32_t defect;                    // uint32[WD]
-    uint32_t touched;                   // uint32[WN]  nodes that are a defect or an end of a fully grown edge
-    uint32_t full2;                     // uint32[WN]  nodes with two or more fully grown edges (defects: one or more)
+    uint32_t full1, full2;              // uint32[WN] each: touched nodes (a defect, or an end of a fully grown edge) /
+                                        // nodes with two or more fully grown edges (defects: one or more)
     uint32_t err, corr;                 // uint32[WE]  only in the staged kernels (0 = absent)
     uint32_t zero_off, zero_bytes;      // growth .. corr are contiguous: what ph_reset clears
     uint32_t claim;                     // uint32[max(CLAIM_SLOTS,WN)]  merge reservations; visited bitmap of the peel
@@ -136,7 +163,7 @@ struct Layout {
 };
 
 struct Shot {
-    uint32_t *S, *growth, *newfull, *defect, *touched, *full2, *err, *corr, *claim, *list, *list2, *cnt;
+    uint32_t *S, *growth, *newfull, *defect, *full1, *full2, *err, *corr, *claim, *list, *list2, *cnt;
 };
 
 LUF_DEV Shot bind(const Layout& l, unsigned char* base)
@@ -144,7 +171,7 @@ LUF_DEV Shot bind(const Layout& l, unsigned char* base)
     Shot s;
     s.S = (uint32_t*)(base + l.S);
     s.growth = (uint32_t*)(base + l.growth); s.newfull = (uint32_t*)(base + l.newfull);
-    s.defect = (uint32_t*)(base + l.defect); s.touched = (uint32_t*)(base + l.touched);
+    s.defect = (uint32_t*)(base + l.defect); s.full1 = (uint32_t*)(base + l.full1);
     s.full2 = (uint32_t*)(base + l.full2);
     s.err = l.err ? (uint32_t*)(base + l.err) : 0;
     s.corr = l.corr ? (uint32_t*)(base + l.corr) : 0;
@@ -196,17 +223,19 @@ LUF_DEV uint32_t find_compress(const Shot& s, uint32_t v)
 // contiguous range of words, reserves room for its bits with one atomic add
 // and writes `id0 + bit index` for each.  When the total exceeds the list the
 // consumers walk the bitmap itself (same per-item code, unbalanced lanes).
-LUF_DEV void gather_bits(const uint32_t* bm, int nwords, uint32_t id0, uint32_t* list, uint32_t* counter, int lane, int nl)
+// `word(w)` yields word w of the bitmap.
+template <class W>
+LUF_DEV void gather_bits(W word, int nwords, uint32_t id0, uint32_t* list, uint32_t* counter, int lane, int nl)
 {
     const int wpl = (nwords + nl - 1) / nl;
     const int w0 = lane * wpl, w1 = w0 + wpl < nwords ? w0 + wpl : nwords;
     uint32_t c = 0;
-    for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(bm[w]);
+    for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(word(w));
     if (!c) return;
     uint32_t pos = luf_atomic_add(counter, c);
     if (pos + c > LIST_CAP) return;
     for (int w = w0; w < w1; ++w) {
-        uint32_t bits = bm[w];
+        uint32_t bits = word(w);
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             list[pos++] = id0 + (uint32_t)(32 * w + b);
@@ -214,21 +243,39 @@ LUF_DEV void gather_bits(const uint32_t* bm, int nwords, uint32_t id0, uint32_t*
     }
 }
 
+// Run f(id) for every set bit, straight from the bitmap (short bodies: cheaper than compacting first).
+template <class W, class F>
+LUF_DEV void for_bits(W word, int nwords, uint32_t id0, int lane, int nl, F f)
+{
+    for (int w = lane; w < nwords; w += nl) {
+        uint32_t bits = word(w);
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            f(id0 + (uint32_t)(32 * w + b));
+        }
+    }
+}
+
 // Run f(id) for every item: from the list if it held them all, else from the bitmap.
-template <class F>
-LUF_DEV void for_items(const uint32_t* bm, int nwords, uint32_t id0, const uint32_t* list, uint32_t total,
+template <class W, class F>
+LUF_DEV void for_items(W word, int nwords, uint32_t id0, const uint32_t* list, uint32_t total,
                        int lane, int nl, F f)
 {
     if (total <= LIST_CAP) {
         for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) f(list[i]);
-    } else {
-        for (int w = lane; w < nwords; w += nl) {
-            uint32_t bits = bm[w];
-            while (bits) {
-                const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-                f(id0 + (uint32_t)(32 * w + b));
-            }
-        }
+    } else for_bits(word, nwords, id0, lane, nl, f);
+}
+
+// Row v of the adjacency table, read as 64-bit pairs; f(entry) for every real entry.
+template <class F>
+LUF_DEV void for_row(const GraphView& g, uint32_t v, F f)
+{
+    const uint32_t* row = g.adj + (size_t)v * (uint32_t)g.DEG;
+    for (int k = 0; k < g.DEG; k += 2) {
+        const luf_u32x2 p = LUF_LDG2(row + k);
+        if (p.x == ADJ_PAD) break;
+        f(p.x);
+        if (p.y != ADJ_PAD) f(p.y);
     }
 }
 
@@ -380,7 +427,7 @@ LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             const uint32_t v = (uint32_t)(g.B + 32 * w + b);
             s.S[v] = ODD_BIT | ROOT_BIT | 1u;
-            luf_atomic_or(&s.touched[v >> 5], 1u << (v & 31u));
+            luf_atomic_or(&s.full1[v >> 5], 1u << (v & 31u));
             if (fits) s.list[pos++] = v;
         }
     }
@@ -397,13 +444,14 @@ LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
 // adds.  Two different active clusters each add 1.  The 2-bit counters
 // saturate at FULL.
 //
-// touched / full2 flags, set with atomicOr only.  full2 over-approximates
-// "two or more fully grown edges" for defects (their touched bit is set by
-// ph_load); it only decides whether the peel traversal may skip a leaf.
+// Node flags, set with atomicOr only.  full1 = touched: a defect, or an end of
+// a fully grown edge.  full2 = a second fully grown edge arrived at a touched
+// node, i.e. two or more such edges (one or more for defects); it only decides
+// whether the peel traversal may skip a leaf.
 LUF_DEV void bump(const Shot& s, uint32_t v)
 {
     const uint32_t bit = 1u << (v & 31u);
-    if (luf_atomic_or(&s.touched[v >> 5], bit) & bit) luf_atomic_or(&s.full2[v >> 5], bit);
+    if (luf_atomic_or(&s.full1[v >> 5], bit) & bit) luf_atomic_or(&s.full2[v >> 5], bit);
 }
 
 LUF_DEV void became_full(const Shot& s, uint32_t e, uint32_t u, uint32_t o)
@@ -415,66 +463,51 @@ LUF_DEV void became_full(const Shot& s, uint32_t e, uint32_t u, uint32_t o)
 // First round: every cluster is a singleton and every edge ungrown, so each
 // defect adds 1 to all its edges with no look-ups; an edge is newly FULL iff
 // the other end got there first.
-LUF_DEV void grow_first_ent(const Shot& s, uint32_t v, uint32_t ent)
-{
-    if (ent == ADJ_PAD) return;
-    const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
-    const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-    if (old == G_HALF) became_full(s, e, v, (ent >> 16) & 0x7FFFu);
-}
-
 LUF_DEV void grow_first(const GraphView& g, const Shot& s, uint32_t v)
 {
-    const uint32_t* row = g.adj + (size_t)v * (uint32_t)g.DEG;
-    for (int k = 0; k < g.DEG; k += 2) {
-        const luf_u32x2 p = LUF_LDG2(row + k);
-        grow_first_ent(s, v, p.x); grow_first_ent(s, v, p.y);
-    }
+    for_row(g, v, [&](uint32_t ent) {
+        const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+        const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+        if (old == G_HALF) became_full(s, e, v, (ent >> 16) & 0x7FFFu);
+    });
 }
 
 // Returns the number of defects (0 = nothing to decode).
 LUF_DEV uint32_t ph_grow_first(const GraphView& g, const Shot& s, int lane, int nl)
 {
     const uint32_t total = s.cnt[0];
-    for_items(s.defect, g.WD, (uint32_t)g.B, s.list, total, lane, nl, [&](uint32_t v) { grow_first(g, s, v); });
+    for_items([&](int w) { return s.defect[w]; }, g.WD, (uint32_t)g.B, s.list, total, lane, nl,
+              [&](uint32_t v) { grow_first(g, s, v); });
     return total;
-}
-
-LUF_DEV void grow_ent(const Shot& s, uint32_t u, uint32_t r, uint32_t ent)
-{
-    if (ent == ADJ_PAD) return;
-    const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
-    if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
-    const uint32_t o = (ent >> 16) & 0x7FFFu;
-    if (!(ent >> 31)) {                           // second endpoint: skip if same cluster
-        uint32_t wr;
-        if (o == r || find_ro(s, o, wr) == r) return;
-    }
-    const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-    if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
-    else if (old == G_HALF) became_full(s, e, u, o);
 }
 
 LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r)
 {
-    const uint32_t* row = g.adj + (size_t)u * (uint32_t)g.DEG;
-    for (int k = 0; k < g.DEG; k += 2) {
-        const luf_u32x2 p = LUF_LDG2(row + k);
-        grow_ent(s, u, r, p.x); grow_ent(s, u, r, p.y);
-    }
+    for_row(g, u, [&](uint32_t ent) {
+        const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+        if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
+        const uint32_t o = (ent >> 16) & 0x7FFFu;
+        if (!(ent >> 31)) {                           // second endpoint: skip if same cluster
+            uint32_t wr;
+            if (o == r || find_ro(s, o, wr) == r) return;
+        }
+        const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+        if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
+        else if (old == G_HALF) became_full(s, e, u, o);
+    });
 }
 
 // Later rounds: compact the touched nodes (cnt[0]; cnt[0] = cnt[1] = 0 on entry) ...
 LUF_DEV void ph_grow_gather(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    gather_bits(s.touched, g.WN, 0u, s.list, &s.cnt[0], lane, nl);
-    if (lane == 0) s.cnt[2] = 0;
+    gather_bits([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, &s.cnt[0], lane, nl);
+    if (lane == 0) { s.cnt[2] = 0; s.cnt[3] = 0; }
 }
 
 // ... keep those whose cluster is active (cnt[1], list2), one per lane ...
 LUF_DEV void ph_grow_filter(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    for_items(s.touched, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
+    for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
         uint32_t wr;
         const uint32_t r = find_pc(s, u, wr);
         if ((wr >> 16) != (ODD_BIT >> 16)) return;
@@ -534,64 +567,87 @@ LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t 
 // touch -- those clusters before it, so running it now commutes with
 // everything the serial order would have run before it.  Winners of one
 // iteration touch pairwise disjoint clusters and run concurrently; losers
-// retry: a star of k edges around one cluster takes k iterations, all stars
-// side by side.  Slots are hashed (collisions only add ordering, never remove
-// it) and tagged with a decreasing iteration number, so stale entries always
-// lose and the table needs no clearing.
+// retry.  Slots are hashed (collisions only add ordering, never remove it) and
+// tagged with a decreasing iteration number, so stale entries always lose and
+// the tables need no clearing.
+//
 LUF_DEV uint32_t claim_slot(uint32_t root) { return (root * 0x9E5u >> 3) & (uint32_t)(CLAIM_SLOTS - 1); }
 
-// Compact this round's newly FULL edges into the list
-// (cnt[2] = their number; 0 on entry).
-LUF_DEV void ph_merge_gather(const GraphView& g, const Shot& s, int lane, int nl)
+LUF_DEV uint32_t merge_count(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    gather_bits(s.newfull, g.WE, 0u, s.list, &s.cnt[2], lane, nl);
-    if (lane == 0) { s.cnt[0] = 0; s.cnt[1] = 0; }
+    const int wpl = (g.WE + nl - 1) / nl;
+    const int w1 = (lane + 1) * wpl < g.WE ? (lane + 1) * wpl : g.WE;
+    uint32_t c = 0;
+    for (int w = lane * wpl; w < w1; ++w) c += (uint32_t)luf_popc(s.newfull[w]);
+    return c;
 }
 
-template <int TF>
-LUF_DEV void ph_merge_claim(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, bool first, int lane, int nl)
+// Compact this round's newly FULL edges into the list in ascending edge id
+// (cnt[2] = their number) and clear the bitmap;
+// if they do not fit, the bitmap is left for merge_rest.
+LUF_DEV void ph_merge_gather(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    if (first) {                                  // the edges live in the list now
-        const int wpl = (g.WE + nl - 1) / nl;
-        const int w1 = (lane + 1) * wpl < g.WE ? (lane + 1) * wpl : g.WE;
-        for (int w = lane * wpl; w < w1; ++w) s.newfull[w] = 0;
+    const int wpl = (g.WE + nl - 1) / nl;
+    const int w0 = lane * wpl, w1 = w0 + wpl < g.WE ? w0 + wpl : g.WE;
+    uint32_t pos, total;
+    luf_exscan(merge_count(g, s, lane, nl), lane, nl, pos, total);
+    if (lane == 0) { s.cnt[0] = 0; s.cnt[1] = 0; s.cnt[2] = total; s.cnt[3] = 0; }
+    if (total > LIST_CAP) return;
+    for (int w = w0; w < w1; ++w) {
+        uint32_t bits = s.newfull[w];
+        if (!bits) continue;
+        s.newfull[w] = 0;
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            s.list[pos++] = (uint32_t)(32 * w + b);
+        }
     }
+}
+
+// Returns how many edges this lane placed (edges inside one cluster).
+template <int TF>
+LUF_DEV uint32_t ph_merge_claim(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, bool first, int lane, int nl)
+{
+    uint32_t placed = 0;
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
         const uint32_t it = s.list[i];
         if (it == LIST_DONE) continue;
         const uint32_t e = it & 0xFFFFu;
+        uint32_t wu, wv;
         const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-        uint32_t wr;
-        const uint32_t cu = find_pc(s, first ? (uv & 0xFFFFu) : (it >> 16), wr), cv = find_pc(s, uv >> 16, wr);
-        if (cu == cv) {                           // inside one cluster whatever runs before it
+        const uint32_t u = uv & 0xFFFFu, v = uv >> 16;
+        const uint32_t cu = find_pc(s, first ? u : (it >> 16), wu), cv = find_pc(s, v, wv);
+        if (cu == cv) {                               // inside one cluster whatever runs before it
             union_roots<TF>(g, s, flags, e, cu, cv);
             s.list[i] = LIST_DONE;
+            ++placed;
             continue;
         }
         luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
         luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
-        s.list[i] = e | (cu << 16);               // the root of the first endpoint cannot change before this edge runs
+        s.list[i] = e | (cu << 16);                   // the root of the first endpoint cannot change before this edge runs
     }
+    return placed;
 }
 
-// Returns whether this lane still has pending edges.
+// Returns how many edges this lane placed.
 template <int TF>
 LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, int lane, int nl)
 {
-    uint32_t pending = 0;
+    uint32_t placed = 0;
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
         const uint32_t it = s.list[i];
         if (it == LIST_DONE) continue;
-        const uint32_t e = it & 0xFFFFu, cu = it >> 16;
-        if (s.claim[claim_slot(cu)] != (tag | e)) { pending = 1; continue; }
+        const uint32_t e = it & 0xFFFFu, r0 = (it >> 16) & 0x7FFFu;
+        if (s.claim[claim_slot(r0)] != (tag | e)) continue;
         uint32_t wr;
         const uint32_t cv = find_ro(s, LUF_LDG(&g.edge_uv[e]) >> 16, wr);
-        if (s.claim[claim_slot(cv)] == (tag | e)) {
-            union_roots<TF>(g, s, flags, e, cu, cv);
-            s.list[i] = LIST_DONE;
-        } else pending = 1;
+        if (s.claim[claim_slot(cv)] != (tag | e)) continue;
+        union_roots<TF>(g, s, flags, e, r0, cv);
+        s.list[i] = LIST_DONE;
+        ++placed;
     }
-    return pending;
+    return placed;
 }
 
 // Overflow path (more newly FULL edges than the list holds): one lane merges
@@ -626,10 +682,16 @@ LUF_DEV void merge_rest(const GraphView& g, const Shot& s, int flags, int base, 
 // else the root, whose partner is then the cluster's boundary node (an odd
 // cluster that stopped growing has one).
 //
-// Entry state: cnt[0..2] = 0 and the visited bitmap (aliasing the claim table) cleared.
+// Entry state: cnt[0..3] = 0 and the visited bitmap (aliasing the claim table) cleared.
+template <class F>
+LUF_DEV void for_defects(const GraphView& g, const Shot& s, int lane, int nl, F f)
+{
+    for_items([&](int w) { return s.defect[w]; }, g.WD, (uint32_t)g.B, s.list, s.cnt[0], lane, nl, f);
+}
+
 LUF_DEV void ph_peel_gather(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    gather_bits(s.defect, g.WD, (uint32_t)g.B, s.list, &s.cnt[0], lane, nl);
+    gather_bits([&](int w) { return s.defect[w]; }, g.WD, (uint32_t)g.B, s.list, &s.cnt[0], lane, nl);
 }
 
 // Returns this lane's parity of pair corrections on the west boundary and
@@ -640,7 +702,7 @@ LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int 
 {
     uint32_t out = 0;
     uint32_t* troot = s.newfull;
-    for_items(s.defect, g.WD, (uint32_t)g.B, s.list, s.cnt[0], lane, nl, [&](uint32_t dn) {
+    for_defects(g, s, lane, nl, [&](uint32_t dn) {
         uint32_t rr;
         const uint32_t r = find_ro(s, dn, rr);
         if ((rr & SIZE_MASK) == 2u) {
@@ -679,19 +741,16 @@ LUF_DEV void build_tree(const GraphView& g, const Shot& s, uint32_t root)
     while (top != NONE16) {
         const uint32_t u = top;
         top = s.S[u] >> 16;
-        const uint32_t* row = g.adj + (size_t)u * (uint32_t)g.DEG;
-        for (int k = 0; k < g.DEG; ++k) {
-            const uint32_t ent = LUF_LDG(&row[k]);
-            if (ent == ADJ_PAD) break;
+        for_row(g, u, [&](uint32_t ent) {
             const uint32_t e = ent & 0xFFFFu;
-            if (growth_of(s, e) != G_FULL) continue;
+            if (growth_of(s, e) != G_FULL) return;
             const uint32_t o = (ent >> 16) & 0x7FFFu;
             const uint32_t bit = 1u << (o & 31u);
-            if (visited[o >> 5] & bit) continue;
+            if (visited[o >> 5] & bit) return;
             luf_atomic_or(&visited[o >> 5], bit);
-            if (!(s.full2[o >> 5] & bit)) { s.S[o] = e | (NONE16 << 16); continue; }   // a leaf: nothing to discover from it
+            if (!(s.full2[o >> 5] & bit)) { s.S[o] = e | (NONE16 << 16); return; }     // a leaf: nothing to discover from it
             s.S[o] = e | (top << 16); top = o;
-        }
+        });
     }
 }
 
@@ -725,7 +784,7 @@ LUF_DEV uint32_t ph_peel_paths(const GraphView& g, const Shot& s, int lane, int 
 {
     uint32_t parity = 0;
     const uint32_t* visited = s.claim;
-    for_items(s.defect, g.WD, (uint32_t)g.B, s.list, s.cnt[0], lane, nl, [&](uint32_t v) {
+    for_defects(g, s, lane, nl, [&](uint32_t v) {
         if (!bit_of(visited, v)) return;
         uint32_t e = s.S[v] & 0xFFFFu;
         while (e != TREE_ROOT) {
@@ -761,18 +820,25 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
         }
         if (!LUF_ANY(active)) break;
         ++rounds;
+        LUF_STAT(0, 1); LUF_STAT(rounds == 1 ? 1 : 2, active);
         uint32_t n = 0;
+        LUF_SCAN_PREP(merge_count(g, s, lane, nl));
         LUF_PHASE(ph_merge_gather(g, s, lane, nl));
         LUF_PHASE(n = s.cnt[2]);
+        LUF_STAT(3, n); LUF_STAT(4, n > 32); LUF_STAT(rounds == 1 ? 8 : 9, n);
         if (n <= LIST_CAP) {
+            uint32_t done = 0;
             for (uint32_t guard = 0; guard <= n; ++guard) {           // at least one edge is placed per iteration
                 const uint32_t tag = iter-- << 16;
-                uint32_t pending = 0;
-                LUF_PHASE(ph_merge_claim<TF>(g, s, flags, n, tag, guard == 0, lane, nl));
-                LUF_PHASE(pending |= ph_merge_exec<TF>(g, s, flags, n, tag, lane, nl));
-                if (!LUF_ANY(pending)) break;
+                uint32_t placed = 0;
+                LUF_PHASE(placed += ph_merge_claim<TF>(g, s, flags, n, tag, guard == 0, lane, nl));
+                LUF_PHASE(placed += ph_merge_exec<TF>(g, s, flags, n, tag, lane, nl));
+                done += LUF_SUM(placed);
+                LUF_STAT(5, 1); LUF_STAT(rounds == 1 ? 6 : 7, 1);
+                if (done >= n) break;
             }
-        } else {                             // overflow: one lane, ascending edge id, straight from the bitmap
+        }
+        else {                             // overflow: one lane, ascending edge id, straight from the bitmap
             for (int base = 0; base < g.WE; base += 32) {
                 uint32_t mask;
                 LUF_BALLOT(mask, base + lane < g.WE && s.newfull[base + lane] != 0);
@@ -781,7 +847,7 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
         }
     }
     // hand over to the peel: counters cleared, visited bitmap (in the claim table) cleared
-    LUF_PHASE(if (lane < 3) s.cnt[lane] = 0; for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0);
+    LUF_PHASE(if (lane < 4) s.cnt[lane] = 0; for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0);
     return rounds;
 }
 
@@ -801,6 +867,7 @@ LUF_DEV uint32_t uf_peel(const GraphView& g, const Shot& s, int lane, int nl)
     if (LUF_ANY(general)) {
         uint32_t roots = 0;
         LUF_PHASE(ph_peel_build(g, s, lane, nl); roots = s.cnt[1]);
+        LUF_STAT(10, 1); LUF_STAT(11, roots);
         if (roots > LIST2_CAP) { LUF_PHASE(ph_peel_build_rest(g, s, lane, nl)); }
         LUF_PHASE(parity ^= ph_peel_paths(g, s, lane, nl));
     }

@@ -92,7 +92,7 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr)
     l.zero_off = off;                                 // ---- cleared by ph_reset
     l.growth = take(4u * ((E + 15) / 16));
     l.newfull = take(4u * (WE > WN ? WE : WN));       // tree-root bitmap of the peel (after the last merge round)
-    l.defect = take(4u * WD); l.touched = take(4u * WN); l.full2 = take(4u * WN);
+    l.defect = take(4u * WD); l.full1 = take(4u * WN); l.full2 = take(4u * WN);
     l.err = keep_err ? take(4u * WE) : 0;
     l.corr = keep_corr ? take(4u * WE) : 0;
     l.zero_bytes = off - l.zero_off;                  // ----

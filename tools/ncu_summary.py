@@ -30,6 +30,7 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 
 def main():
     rep, so, kernel = sys.argv[1:4]
+    mangled = sys.argv[4] if len(sys.argv) > 4 else kernel      # nvdisasm section name (template instances)
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -58,7 +59,7 @@ def main():
     hi = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
     h = rows[hi]; col = {x: i for i, x in enumerate(h)}
     body = [r for r in rows[hi + 1:] if len(r) == len(h)]
-    table = ncu_lines.line_table(so, kernel)
+    table = ncu_lines.line_table(so, mangled)
     agg, tot = {}, [0, 0, 0]
     for k, r in enumerate(body):
         key = table[k] if k < len(table) and table[k] else ('?', 0)
