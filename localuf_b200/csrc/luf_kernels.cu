@@ -371,7 +371,11 @@ static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long n
     const std::pair<const void*, uint32_t> key((const void*)kernel, slice_bytes);
     auto hit = g->plans.find(key);
     if (hit != g->plans.end()) { wpb = hit->second.first; per_sm = hit->second.second; best = wpb * per_sm; }
-    else for (int cand = 1; cand <= max_wpb; ++cand) {
+    else {
+        // the occupancy query honours the carve-out preference a previous plan left on the kernel
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    if (hit == g->plans.end()) for (int cand = 1; cand <= max_wpb; ++cand) {
         if (env_wpb > 0 && cand != env_wpb) continue;
         const size_t sm = (size_t)cand * l.bytes;
         if (sm > (size_t)g->max_smem) break;
@@ -459,6 +463,7 @@ static int plan_stream_launch(luf_stream* g, K kernel, long long nstreams, Launc
     if (wpb > 4) wpb = 4;
     const size_t smem = (size_t)wpb * bytes;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * WARP, smem));
     if (per_sm < 1) per_sm = 1;
