@@ -21,7 +21,7 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h'))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h', '.inl'))]
     deps.append(os.path.join(os.path.dirname(HERE), 'include', 'luf_b200.h'))
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -37,7 +37,7 @@
   struct luf_u32x4 { uint32_t x, y, z, w; };
   #define LUF_LDG2(p) (*(const luf_u32x2*)(p))
   // lanes run one after the other: the counts are stored by one phase and summed in the next
-  static uint32_t luf_scan_scratch[64];
+  static uint32_t luf_scan_scratch[1024];
   #define LUF_SCAN_PREP(expr) LUF_PHASE(luf_scan_scratch[lane] = (expr))
   static inline void luf_exscan(uint32_t c, int lane, int nl, uint32_t& pos, uint32_t& total)
   {
@@ -52,7 +52,6 @@
   #define LUF_ANY(x) ((x) != 0)
   #define LUF_XOR(x) (x)
   #define LUF_SUM(x) (x)
-  #define LUF_BALLOT(var, pred) { var = 0; for (int lane = 0; lane < nl; ++lane) if (pred) var |= 1u << lane; }
   static inline uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 #else
   #define LUF_DEV __device__ __forceinline__
@@ -83,7 +82,6 @@
   #define LUF_ANY(x) __any_sync(0xffffffffu, (x) != 0)
   #define LUF_XOR(x) __reduce_xor_sync(0xffffffffu, (x))
   #define LUF_SUM(x) __reduce_add_sync(0xffffffffu, (x))
-  #define LUF_BALLOT(var, pred) { var = __ballot_sync(0xffffffffu, (pred)); }
   LUF_DEV uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 #endif
 
@@ -111,7 +109,7 @@ static const uint32_t NONE16 = 0xFFFFu;
 static const uint32_t TREE_ROOT = 0xFFFEu;
 static const uint32_t ADJ_PAD = 0xFFFFFFFFu;
 static const int MAX_CLASSES = 32;
-static const int CLAIM_SLOTS = 128;      // power of two
+static const int CLAIM_SLOTS = 128;      // power of two (warp tiles)
 #ifndef LUF_LIST_CAP
   #define LUF_LIST_CAP 96
 #endif
@@ -183,122 +181,6 @@ LUF_DEV Shot bind(const Layout& l, unsigned char* base)
 // ------------------------------------------------------------------ helpers
 LUF_DEV uint32_t growth_of(const Shot& s, uint32_t e) { return (s.growth[e >> 4] >> ((e & 15u) * 2u)) & 3u; }
 LUF_DEV bool bit_of(const uint32_t* bm, uint32_t i) { return (bm[i >> 5] >> (i & 31u)) & 1u; }
-
-// find without writes: safe while other lanes read or extend the forest.  `wr` = the root's word.
-LUF_DEV uint32_t find_ro(const Shot& s, uint32_t v, uint32_t& wr)
-{
-    uint32_t w;
-    while (!((w = s.S[v]) & ROOT_BIT)) v = w & SIZE_MASK;
-    wr = w;
-    return v;
-}
-
-// find that also shortcuts the start node to the root it found.  Safe next to
-// concurrent finds and unions of other lanes: a non-root node never becomes a
-// root again and the value written is one of its ancestors (32-bit stores are
-// atomic; the union edge in the upper half is kept), so every interleaving
-// leaves a valid forest with the same roots.
-LUF_DEV uint32_t find_pc(const Shot& s, uint32_t v, uint32_t& wr)
-{
-    const uint32_t w = s.S[v];
-    if (w & ROOT_BIT) { wr = w; return v; }
-    uint32_t r = w & SIZE_MASK, q;
-    int hops = 0;
-    while (!((q = s.S[r]) & ROOT_BIT)) { r = q & SIZE_MASK; ++hops; }
-    if (hops) s.S[v] = (w & 0xFFFF0000u) | r;
-    wr = q;
-    return r;
-}
-
-// uf.py:247-254 -- find with full path compression (single lane only)
-LUF_DEV uint32_t find_compress(const Shot& s, uint32_t v)
-{
-    uint32_t r = v, w;
-    while (!((w = s.S[r]) & ROOT_BIT)) r = w & SIZE_MASK;
-    while (v != r) { w = s.S[v]; s.S[v] = (w & 0xFFFF0000u) | r; v = w & SIZE_MASK; }
-    return r;
-}
-
-// Compact the set bits of a bitmap into the work list: every lane owns a
-// contiguous range of words, reserves room for its bits with one atomic add
-// and writes `id0 + bit index` for each.  When the total exceeds the list the
-// consumers walk the bitmap itself (same per-item code, unbalanced lanes).
-// `word(w)` yields word w of the bitmap.
-template <class W>
-LUF_DEV void gather_bits(W word, int nwords, uint32_t id0, uint32_t* list, uint32_t* counter, int lane, int nl)
-{
-    const int wpl = (nwords + nl - 1) / nl;
-    const int w0 = lane * wpl, w1 = w0 + wpl < nwords ? w0 + wpl : nwords;
-    uint32_t c = 0;
-    for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(word(w));
-    if (!c) return;
-    uint32_t pos = luf_atomic_add(counter, c);
-    if (pos + c > LIST_CAP) return;
-    for (int w = w0; w < w1; ++w) {
-        uint32_t bits = word(w);
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            list[pos++] = id0 + (uint32_t)(32 * w + b);
-        }
-    }
-}
-
-// Run f(id) for every set bit, straight from the bitmap (short bodies: cheaper than compacting first).
-template <class W, class F>
-LUF_DEV void for_bits(W word, int nwords, uint32_t id0, int lane, int nl, F f)
-{
-    for (int w = lane; w < nwords; w += nl) {
-        uint32_t bits = word(w);
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            f(id0 + (uint32_t)(32 * w + b));
-        }
-    }
-}
-
-// Run f(id) for every item: from the list if it held them all, else from the bitmap.
-template <class W, class F>
-LUF_DEV void for_items(W word, int nwords, uint32_t id0, const uint32_t* list, uint32_t total,
-                       int lane, int nl, F f)
-{
-    if (total <= LIST_CAP) {
-        for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) f(list[i]);
-    } else for_bits(word, nwords, id0, lane, nl, f);
-}
-
-// Row v of the adjacency table, read as 64-bit pairs; f(entry) for every real entry.
-template <class F>
-LUF_DEV void for_row(const GraphView& g, uint32_t v, F f)
-{
-    const uint32_t* row = g.adj + (size_t)v * (uint32_t)g.DEG;
-    for (int k = 0; k < g.DEG; k += 2) {
-        const luf_u32x2 p = LUF_LDG2(row + k);
-        if (p.x == ADJ_PAD) break;
-        f(p.x);
-        if (p.y != ADJ_PAD) f(p.y);
-    }
-}
-
-// ------------------------------------------------------------ phase 0: reset
-// uf.py:79-96,496-519 -- every node a singleton cluster; a boundary node is its
-// own cluster boundary.  (The reference re-allocates N Python objects here,
-// 40-58 % of its time; this is N*4 + ~3 KB of 16-byte shared-memory stores.)
-LUF_DEV uint32_t fresh_word(const GraphView& g, int v) { return ROOT_BIT | 1u | (v < g.B ? ((uint32_t)v + 1u) << 16 : 0u); }
-
-LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int lane, int nl)
-{
-    luf_u32x4* S4 = (luf_u32x4*)s.S;
-    for (int v = 4 * lane; v < g.N; v += 4 * nl) {
-        luf_u32x4 w;
-        w.x = fresh_word(g, v); w.y = fresh_word(g, v + 1); w.z = fresh_word(g, v + 2); w.w = fresh_word(g, v + 3);
-        S4[v >> 2] = w;
-    }
-    luf_u32x4* Z4 = (luf_u32x4*)((unsigned char*)s.S + (l.zero_off - l.S));
-    luf_u32x4 z; z.x = z.y = z.z = z.w = 0u;
-    for (int i = lane; i < (int)(l.zero_bytes >> 4); i += nl) Z4[i] = z;
-    for (int w = lane; w < CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu;
-    if (lane < 4) s.cnt[lane] = 0;
-}
 
 // --------------------------------------------------- phase 1: sample + syndrome
 struct Philox {
@@ -409,469 +291,89 @@ LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams
     return ph_sample_tab(g, t, s, sp, shot, 0u, (const uint32_t*)0, lane, nl);
 }
 
-// uf.py:98-104 load: every defect is an odd singleton cluster (hence active).
-// Also compacts the defects into the work list for the first growth round
-// (cnt[0] = their number; must be 0 on entry, ph_reset leaves it so).
-LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    const int wpl = (g.WD + nl - 1) / nl;
-    const int w0 = lane * wpl, w1 = w0 + wpl < g.WD ? w0 + wpl : g.WD;
-    uint32_t c = 0;
-    for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(s.defect[w]);
-    if (!c) return;
-    uint32_t pos = luf_atomic_add(&s.cnt[0], c);
-    const bool fits = pos + c <= LIST_CAP;
-    for (int w = w0; w < w1; ++w) {
-        uint32_t bits = s.defect[w];
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t v = (uint32_t)(g.B + 32 * w + b);
-            s.S[v] = ODD_BIT | ROOT_BIT | 1u;
-            luf_atomic_or(&s.full1[v >> 5], 1u << (v & 31u));
-            if (fits) s.list[pos++] = v;
-        }
-    }
-}
-
-// ------------------------------------------------------- phase 2a: grow a round
-// uf.py:221-222,234-245.  vision(C) = edges incident to C's members that are not
-// yet FULL/BURNT; a cluster is active iff it is odd and has no boundary
-// (uf.py:296-301), i.e. the upper half of its root word is exactly the odd
-// bit.  Members are not kept in lists: every *touched* node (a defect, or an
-// end of a fully grown edge -- other singletons are never active) looks its
-// root up and grows its own incident edges if the root is active.  An edge
-// inside one cluster is in that cluster's vision once: only its first endpoint
-// adds.  Two different active clusters each add 1.  The 2-bit counters
-// saturate at FULL.
-//
-// Node flags, set with atomicOr only.  full1 = touched: a defect, or an end of
-// a fully grown edge.  full2 = a second fully grown edge arrived at a touched
-// node, i.e. two or more such edges (one or more for defects); it only decides
-// whether the peel traversal may skip a leaf.
-LUF_DEV void bump(const Shot& s, uint32_t v)
-{
-    const uint32_t bit = 1u << (v & 31u);
-    if (luf_atomic_or(&s.full1[v >> 5], bit) & bit) luf_atomic_or(&s.full2[v >> 5], bit);
-}
-
-LUF_DEV void became_full(const Shot& s, uint32_t e, uint32_t u, uint32_t o)
-{
-    luf_atomic_or(&s.newfull[e >> 5], 1u << (e & 31u));
-    bump(s, u); bump(s, o);
-}
-
-// First round: every cluster is a singleton and every edge ungrown, so each
-// defect adds 1 to all its edges with no look-ups; an edge is newly FULL iff
-// the other end got there first.
-LUF_DEV void grow_first(const GraphView& g, const Shot& s, uint32_t v)
-{
-    for_row(g, v, [&](uint32_t ent) {
-        const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
-        const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-        if (old == G_HALF) became_full(s, e, v, (ent >> 16) & 0x7FFFu);
-    });
-}
-
-// Returns the number of defects (0 = nothing to decode).
-LUF_DEV uint32_t ph_grow_first(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    const uint32_t total = s.cnt[0];
-    for_items([&](int w) { return s.defect[w]; }, g.WD, (uint32_t)g.B, s.list, total, lane, nl,
-              [&](uint32_t v) { grow_first(g, s, v); });
-    return total;
-}
-
-LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r)
-{
-    for_row(g, u, [&](uint32_t ent) {
-        const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
-        if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
-        const uint32_t o = (ent >> 16) & 0x7FFFu;
-        if (!(ent >> 31)) {                           // second endpoint: skip if same cluster
-            uint32_t wr;
-            if (o == r || find_ro(s, o, wr) == r) return;
-        }
-        const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-        if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);     // saturate
-        else if (old == G_HALF) became_full(s, e, u, o);
-    });
-}
-
-// Later rounds: compact the touched nodes (cnt[0]; cnt[0] = cnt[1] = 0 on entry) ...
-LUF_DEV void ph_grow_gather(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    gather_bits([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, &s.cnt[0], lane, nl);
-    if (lane == 0) { s.cnt[2] = 0; s.cnt[3] = 0; }
-}
-
-// ... keep those whose cluster is active (cnt[1], list2), one per lane ...
-LUF_DEV void ph_grow_filter(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
-        uint32_t wr;
-        const uint32_t r = find_pc(s, u, wr);
-        if ((wr >> 16) != (ODD_BIT >> 16)) return;
-        const uint32_t idx = luf_atomic_add(&s.cnt[1], 1u);
-        if (idx < LIST2_CAP) s.list2[idx] = u | (r << 16);
-        else grow_node(g, s, u, r);
-    });
-}
-
-// ... and grow them, the edge loops spread evenly over the lanes.  Returns the
-// number of active nodes of the round.
-LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    const uint32_t total = s.cnt[1];
-    const uint32_t n = total < LIST2_CAP ? total : LIST2_CAP;
-    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t it = s.list2[i];
-        grow_node(g, s, it & 0xFFFFu, it >> 16);
-    }
-    return total;
-}
-
-// ------------------------------------------------------------ phase 2b: merge
-// uf.py:223-229,256-301 in canonical order: this round's newly FULL edges are
-// merged in ascending edge id.  Union by size, ties keep the cluster of the
-// edge's first endpoint; parity XOR; boundary by inclination.  TF >= 0 fixes
-// the decoder flags at compile time (the fused kernel), TF < 0 reads `flags`.
-template <int TF>
-LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t e, uint32_t cu, uint32_t cv)
-{
-    const int f = TF >= 0 ? TF : flags;
-    const uint32_t wu = s.S[cu], wv = s.S[cv];
-    if (f & FLAG_DYNAMIC) {                                       // uf.py:261-266
-        if (cu == cv || ((wu & BND_MASK) && (wv & BND_MASK))) {
-            luf_atomic_or(&s.growth[e >> 4], 3u << ((e & 15u) * 2u));     // FULL(2) -> BURNT(3)
-            return;
-        }
-    } else if (cu == cv) return;                                  // uf.py:256-259
-    const uint32_t su = wu & SIZE_MASK, sv = wv & SIZE_MASK;
-    const bool ul = su >= sv;                                     // uf.py:270-273
-    const uint32_t L = ul ? cu : cv, Sm = ul ? cv : cu;
-    const uint32_t wl = ul ? wu : wv, ws = ul ? wv : wu;
-    uint32_t bl = wl & BND_MASK;
-    const uint32_t bs = ws & BND_MASK;
-    if (f & FLAG_WEST) {                                          // uf.py:544-549
-        if (bs && (!bl || LUF_LDG(&g.node_long[(bs >> 16) - 1]) < LUF_LDG(&g.node_long[(bl >> 16) - 1]))) bl = bs;
-    } else if (!bl) bl = bs;                                      // uf.py:536-538
-    s.S[L] = ((wl ^ ws) & ODD_BIT) | bl | ROOT_BIT | (su + sv);
-    s.S[Sm] = L | (e << 16);
-}
-
-// The serial order is reproduced in parallel by deterministic reservations:
-// every pending edge writes (iteration tag, edge id) with atomicMin into a
-// small table slot of each of its two current clusters; an edge that reads its
-// own id back from both slots is the lowest-id pending edge at both clusters.
-// No lower-id pending edge can touch -- or, through still lower edges, come to
-// touch -- those clusters before it, so running it now commutes with
-// everything the serial order would have run before it.  Winners of one
-// iteration touch pairwise disjoint clusters and run concurrently; losers
-// retry.  Slots are hashed (collisions only add ordering, never remove it) and
-// tagged with a decreasing iteration number, so stale entries always lose and
-// the tables need no clearing.
-//
-LUF_DEV uint32_t claim_slot(uint32_t root) { return (root * 0x9E5u >> 3) & (uint32_t)(CLAIM_SLOTS - 1); }
-
-LUF_DEV uint32_t merge_count(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    const int wpl = (g.WE + nl - 1) / nl;
-    const int w1 = (lane + 1) * wpl < g.WE ? (lane + 1) * wpl : g.WE;
-    uint32_t c = 0;
-    for (int w = lane * wpl; w < w1; ++w) c += (uint32_t)luf_popc(s.newfull[w]);
-    return c;
-}
-
-// Compact this round's newly FULL edges into the list in ascending edge id
-// (cnt[2] = their number) and clear the bitmap;
-// if they do not fit, the bitmap is left for merge_rest.
-LUF_DEV void ph_merge_gather(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    const int wpl = (g.WE + nl - 1) / nl;
-    const int w0 = lane * wpl, w1 = w0 + wpl < g.WE ? w0 + wpl : g.WE;
-    uint32_t pos, total;
-    luf_exscan(merge_count(g, s, lane, nl), lane, nl, pos, total);
-    if (lane == 0) { s.cnt[0] = 0; s.cnt[1] = 0; s.cnt[2] = total; s.cnt[3] = 0; }
-    if (total > LIST_CAP) return;
-    for (int w = w0; w < w1; ++w) {
-        uint32_t bits = s.newfull[w];
-        if (!bits) continue;
-        s.newfull[w] = 0;
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            s.list[pos++] = (uint32_t)(32 * w + b);
-        }
-    }
-}
-
-// Returns how many edges this lane placed (edges inside one cluster).
-template <int TF>
-LUF_DEV uint32_t ph_merge_claim(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, bool first, int lane, int nl)
-{
-    uint32_t placed = 0;
-    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t it = s.list[i];
-        if (it == LIST_DONE) continue;
-        const uint32_t e = it & 0xFFFFu;
-        uint32_t wu, wv;
-        const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-        const uint32_t u = uv & 0xFFFFu, v = uv >> 16;
-        const uint32_t cu = find_pc(s, first ? u : (it >> 16), wu), cv = find_pc(s, v, wv);
-        if (cu == cv) {                               // inside one cluster whatever runs before it
-            union_roots<TF>(g, s, flags, e, cu, cv);
-            s.list[i] = LIST_DONE;
-            ++placed;
-            continue;
-        }
-        luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
-        luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
-        s.list[i] = e | (cu << 16);                   // the root of the first endpoint cannot change before this edge runs
-    }
-    return placed;
-}
-
-// Returns how many edges this lane placed.
-template <int TF>
-LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, int lane, int nl)
-{
-    uint32_t placed = 0;
-    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t it = s.list[i];
-        if (it == LIST_DONE) continue;
-        const uint32_t e = it & 0xFFFFu, r0 = (it >> 16) & 0x7FFFu;
-        if (s.claim[claim_slot(r0)] != (tag | e)) continue;
-        uint32_t wr;
-        const uint32_t cv = find_ro(s, LUF_LDG(&g.edge_uv[e]) >> 16, wr);
-        if (s.claim[claim_slot(cv)] != (tag | e)) continue;
-        union_roots<TF>(g, s, flags, e, r0, cv);
-        s.list[i] = LIST_DONE;
-        ++placed;
-    }
-    return placed;
-}
-
-// Overflow path (more newly FULL edges than the list holds): one lane merges
-// them in ascending edge id, with path compression.  `mask` tells it which of
-// the 32 words from `base` on still hold edges.
-template <int TF>
-LUF_DEV void merge_rest(const GraphView& g, const Shot& s, int flags, int base, uint32_t mask)
-{
-    while (mask) {
-        const int w = base + luf_ffs(mask) - 1; mask &= mask - 1;
-        uint32_t bits = s.newfull[w];
-        s.newfull[w] = 0;
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t e = (uint32_t)(32 * w + b);
-            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-            const uint32_t cu = find_compress(s, uv & 0xFFFFu), cv = find_compress(s, uv >> 16);
-            union_roots<TF>(g, s, flags, e, cu, cv);
-        }
-    }
-}
-
-// ------------------------------------------------------------- phase 3: peel
-// uf.py:314-324: one tree per cluster, rooted at cluster.boundary or else the
-// union-find root.  Clusters without a defect cannot contribute a correction
-// edge, so only clusters of defects are rooted.
-//
-// Two-node clusters (the common case at low noise: one flipped edge) need no
-// traversal: their only tree is the union edge, kept in the word of the member
-// that is not the root, and it is in the correction iff the cluster holds a
-// defect.  Exactly one member acts: the non-root member if it is a defect;
-// else the root, whose partner is then the cluster's boundary node (an odd
-// cluster that stopped growing has one).
-//
-// Entry state: cnt[0..3] = 0 and the visited bitmap (aliasing the claim table) cleared.
-template <class F>
-LUF_DEV void for_defects(const GraphView& g, const Shot& s, int lane, int nl, F f)
-{
-    for_items([&](int w) { return s.defect[w]; }, g.WD, (uint32_t)g.B, s.list, s.cnt[0], lane, nl, f);
-}
-
-LUF_DEV void ph_peel_gather(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    gather_bits([&](int w) { return s.defect[w]; }, g.WD, (uint32_t)g.B, s.list, &s.cnt[0], lane, nl);
-}
-
-// Returns this lane's parity of pair corrections on the west boundary and
-// (bit 1) whether any cluster needs the general traversal.  Tree roots go to
-// list2 (cnt[1]); their bit in the troot bitmap (= newfull, idle by now)
-// de-duplicates them and serves the overflow path.
-LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    uint32_t out = 0;
-    uint32_t* troot = s.newfull;
-    for_defects(g, s, lane, nl, [&](uint32_t dn) {
-        uint32_t rr;
-        const uint32_t r = find_ro(s, dn, rr);
-        if ((rr & SIZE_MASK) == 2u) {
-            uint32_t x = dn;                                  // the member whose word holds the union edge
-            if (dn == r) {
-                if (!(rr & ODD_BIT)) return;                  // both are defects: the other member acts
-                x = ((rr & BND_MASK) >> 16) - 1u;             // single defect: its partner is the boundary node
-            }
-            const uint32_t e = s.S[x] >> 16;
-            if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
-            out ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
-            return;
-        }
-        const uint32_t bn = (rr & BND_MASK) >> 16;
-        const uint32_t t = bn ? bn - 1u : r;
-        out |= 2u;
-        const uint32_t bit = 1u << (t & 31u);
-        if (luf_atomic_or(&troot[t >> 5], bit) & bit) return;
-        const uint32_t idx = luf_atomic_add(&s.cnt[1], 1u);
-        if (idx < LIST2_CAP) s.list2[idx] = t;
-    });
-    return out;
-}
-
-// The union-find forest is dead now; the node words are re-used by the traversal:
-//   bits 0..15 tree edge towards the root    bits 16..31 link of the LIFO stack
-// uf.py:326-344: the reference's LIFO traversal (neighbours in ascending edge
-// id) from a tree root; only the tree (the edge towards the root of every
-// discovered node) is kept.  `visited` marks discovered nodes.
-LUF_DEV void build_tree(const GraphView& g, const Shot& s, uint32_t root)
-{
-    uint32_t* visited = s.claim;
-    luf_atomic_or(&visited[root >> 5], 1u << (root & 31u));
-    s.S[root] = TREE_ROOT | (NONE16 << 16);
-    uint32_t top = root;
-    while (top != NONE16) {
-        const uint32_t u = top;
-        top = s.S[u] >> 16;
-        for_row(g, u, [&](uint32_t ent) {
-            const uint32_t e = ent & 0xFFFFu;
-            if (growth_of(s, e) != G_FULL) return;
-            const uint32_t o = (ent >> 16) & 0x7FFFu;
-            const uint32_t bit = 1u << (o & 31u);
-            if (visited[o >> 5] & bit) return;
-            luf_atomic_or(&visited[o >> 5], bit);
-            if (!(s.full2[o >> 5] & bit)) { s.S[o] = e | (NONE16 << 16); return; }     // a leaf: nothing to discover from it
-            s.S[o] = e | (top << 16); top = o;
-        });
-    }
-}
-
-// one lane per tree root
-LUF_DEV void ph_peel_build(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    const uint32_t total = s.cnt[1];
-    const uint32_t n = total < LIST2_CAP ? total : LIST2_CAP;
-    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) build_tree(g, s, s.list2[i]);
-}
-
-// overflow: roots that did not fit the list are still undiscovered; by bitmap word
-LUF_DEV void ph_peel_build_rest(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    const uint32_t* troot = s.newfull;
-    for (int w = lane; w < g.WN; w += nl) {
-        uint32_t bits = troot[w] & ~s.claim[w];
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            build_tree(g, s, (uint32_t)(32 * w + b));
-        }
-    }
-}
-
-// uf.py:305-312: peeling the forest leaf-up puts a tree edge in the correction
-// iff an odd number of defects hang below it -- the XOR over all defects of
-// their paths to the root.  Every defect of a traversed cluster walks its own
-// path (defects of two-node clusters were handled above and are undiscovered
-// here).  Returns this lane's parity of correction edges on the west boundary.
-LUF_DEV uint32_t ph_peel_paths(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    uint32_t parity = 0;
-    const uint32_t* visited = s.claim;
-    for_defects(g, s, lane, nl, [&](uint32_t v) {
-        if (!bit_of(visited, v)) return;
-        uint32_t e = s.S[v] & 0xFFFFu;
-        while (e != TREE_ROOT) {
-            if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
-            parity ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
-            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-            v = (uv & 0xFFFFu) == v ? (uv >> 16) : (uv & 0xFFFFu);
-            e = s.S[v] & 0xFFFFu;
-        }
-    });
-    return parity;
-}
-
-// ------------------------------------------------------------------ drivers
-// uf.py:200-209 validate: rounds of grow / merge until no cluster is active.
-// Returns the number of growth rounds.  `lane` is this thread's lane on the
-// device; the host emulation iterates it inside LUF_PHASE.  Expects ph_load
-// to have run just before (defects in the work list).
-template <int TF>
-LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane, int nl)
-{
-    int rounds = 0;
-    uint32_t iter = 0xFFFFu;                 // decreasing reservation tag
-    (void)lane;
-    for (;;) {
-        uint32_t active = 0;
-        if (rounds == 0) {
-            LUF_PHASE(active |= ph_grow_first(g, s, lane, nl));
-        } else {
-            LUF_PHASE(ph_grow_gather(g, s, lane, nl));
-            LUF_PHASE(ph_grow_filter(g, s, lane, nl));
-            LUF_PHASE(active |= ph_grow_exec(g, s, lane, nl));
-        }
-        if (!LUF_ANY(active)) break;
-        ++rounds;
-        LUF_STAT(0, 1); LUF_STAT(rounds == 1 ? 1 : 2, active);
-        uint32_t n = 0;
-        LUF_SCAN_PREP(merge_count(g, s, lane, nl));
-        LUF_PHASE(ph_merge_gather(g, s, lane, nl));
-        LUF_PHASE(n = s.cnt[2]);
-        LUF_STAT(3, n); LUF_STAT(4, n > 32); LUF_STAT(rounds == 1 ? 8 : 9, n);
-        if (n <= LIST_CAP) {
-            uint32_t done = 0;
-            for (uint32_t guard = 0; guard <= n; ++guard) {           // at least one edge is placed per iteration
-                const uint32_t tag = iter-- << 16;
-                uint32_t placed = 0;
-                LUF_PHASE(placed += ph_merge_claim<TF>(g, s, flags, n, tag, guard == 0, lane, nl));
-                LUF_PHASE(placed += ph_merge_exec<TF>(g, s, flags, n, tag, lane, nl));
-                done += LUF_SUM(placed);
-                LUF_STAT(5, 1); LUF_STAT(rounds == 1 ? 6 : 7, 1);
-                if (done >= n) break;
-            }
-        }
-        else {                             // overflow: one lane, ascending edge id, straight from the bitmap
-            for (int base = 0; base < g.WE; base += 32) {
-                uint32_t mask;
-                LUF_BALLOT(mask, base + lane < g.WE && s.newfull[base + lane] != 0);
-                if (mask) { LUF_PHASE(if (lane == 0) merge_rest<TF>(g, s, flags, base, mask)); }
-            }
-        }
-    }
-    // hand over to the peel: counters cleared, visited bitmap (in the claim table) cleared
-    LUF_PHASE(if (lane < 4) s.cnt[lane] = 0; for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0);
-    return rounds;
-}
-
-LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, int nl)
-{
-    return uf_validate_t<-1>(g, s, flags, lane, nl);
-}
-
-// uf.py:305-312 peel.  Returns (per lane on the device, total in the
-// emulation) the parity of correction edges on the west boundary.
-LUF_DEV uint32_t uf_peel(const GraphView& g, const Shot& s, int lane, int nl)
-{
-    uint32_t parity = 0, general = 0;
-    (void)lane;
-    LUF_PHASE(ph_peel_gather(g, s, lane, nl));
-    LUF_PHASE(const uint32_t r = ph_tree_roots(g, s, lane, nl); parity ^= r & 1u; general |= r >> 1);
-    if (LUF_ANY(general)) {
-        uint32_t roots = 0;
-        LUF_PHASE(ph_peel_build(g, s, lane, nl); roots = s.cnt[1]);
-        LUF_STAT(10, 1); LUF_STAT(11, roots);
-        if (roots > LIST2_CAP) { LUF_PHASE(ph_peel_build_rest(g, s, lane, nl)); }
-        LUF_PHASE(parity ^= ph_peel_paths(g, s, lane, nl));
-    }
-    return parity;
-}
-
 }  // namespace luf
+
+// ------------------------------------------------------------- the UF phases
+// Tile = one warp (the default everywhere: luf::ph_reset, luf::uf_validate, ...).
+#define LUF_UF_NS uf_warp
+#define LUF_T_LIST_CAP ((uint32_t)LUF_LIST_CAP)
+#define LUF_T_LIST2_CAP ((uint32_t)LUF_LIST2_CAP)
+#define LUF_T_CLAIM_SLOTS 128
+#define LUF_T_PHASE(stmt) LUF_PHASE(stmt)
+#define LUF_T_ANY(x) LUF_ANY(x)
+#define LUF_T_SUM(x) LUF_SUM(x)
+#define LUF_T_EXSCAN(c, lane, nl, pos, total) luf_exscan(c, lane, nl, pos, total)
+#define LUF_T_SCAN_PREP(expr) LUF_SCAN_PREP(expr)
+#include "luf_uf_phases.inl"
+#undef LUF_UF_NS
+#undef LUF_T_LIST_CAP
+#undef LUF_T_LIST2_CAP
+#undef LUF_T_CLAIM_SLOTS
+#undef LUF_T_PHASE
+#undef LUF_T_ANY
+#undef LUF_T_SUM
+#undef LUF_T_EXSCAN
+#undef LUF_T_SCAN_PREP
+namespace luf { using namespace uf_warp; }
+
+// Tile = one thread block, one shot per block: graphs whose shot state would
+// leave only a few warps per SM.  Barriers, votes and scans span the block.
+#ifndef LUF_CTA_LIST_CAP
+  #define LUF_CTA_LIST_CAP 2048
+#endif
+#ifndef LUF_CTA_LIST2_CAP
+  #define LUF_CTA_LIST2_CAP 1024
+#endif
+#define LUF_CTA_CLAIM_SLOTS 1024
+#if defined(LUF_HOST_EMU)
+  #define LUF_T_PHASE(stmt) LUF_PHASE(stmt)
+  #define LUF_T_ANY(x) LUF_ANY(x)
+  #define LUF_T_SUM(x) LUF_SUM(x)
+  #define LUF_T_EXSCAN(c, lane, nl, pos, total) luf_exscan(c, lane, nl, pos, total)
+  #define LUF_T_SCAN_PREP(expr) LUF_SCAN_PREP(expr)
+#else
+  // block-wide sum / exclusive scan through a small static shared array (at most 32 warps)
+  LUF_DEV uint32_t luf_block_sum(uint32_t x)
+  {
+      __shared__ uint32_t red[32];
+      x = __reduce_add_sync(0xffffffffu, x);
+      if ((threadIdx.x & 31u) == 0) red[threadIdx.x >> 5] = x;
+      __syncthreads();
+      uint32_t t = 0;
+      for (unsigned w = 0; w < (blockDim.x + 31u) >> 5; ++w) t += red[w];
+      __syncthreads();
+      return t;
+  }
+  LUF_DEV void luf_block_exscan(uint32_t c, int lane, int nl, uint32_t& pos, uint32_t& total)
+  {
+      __shared__ uint32_t red[32];
+      uint32_t x = c;
+      #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((lane & 31) >= d) x += y; }
+      if ((lane & 31) == 31) red[lane >> 5] = x;
+      __syncthreads();
+      uint32_t before = 0, all = 0;
+      for (int w = 0; w < (nl + 31) >> 5; ++w) { const uint32_t r = red[w]; if (w < (lane >> 5)) before += r; all += r; }
+      __syncthreads();
+      pos = before + x - c; total = all;
+  }
+  #define LUF_T_PHASE(stmt) { stmt; } __syncthreads();
+  #define LUF_T_ANY(x) __syncthreads_or((x) != 0)
+  #define LUF_T_SUM(x) luf_block_sum(x)
+  #define LUF_T_EXSCAN(c, lane, nl, pos, total) luf_block_exscan(c, lane, nl, pos, total)
+  #define LUF_T_SCAN_PREP(expr)
+#endif
+#define LUF_UF_NS uf_cta
+#define LUF_T_LIST_CAP ((uint32_t)LUF_CTA_LIST_CAP)
+#define LUF_T_LIST2_CAP ((uint32_t)LUF_CTA_LIST2_CAP)
+#define LUF_T_CLAIM_SLOTS LUF_CTA_CLAIM_SLOTS
+#include "luf_uf_phases.inl"
+#undef LUF_UF_NS
+#undef LUF_T_LIST_CAP
+#undef LUF_T_LIST2_CAP
+#undef LUF_T_CLAIM_SLOTS
+#undef LUF_T_PHASE
+#undef LUF_T_ANY
+#undef LUF_T_SUM
+#undef LUF_T_EXSCAN
+#undef LUF_T_SCAN_PREP

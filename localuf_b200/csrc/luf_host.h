@@ -82,7 +82,10 @@ inline std::string pack_graph(const luf_graph_desc& d, PackedGraph& out)
 
 inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr)
+// list_cap / list2_cap / claim_slots: the work-list sizes of the tile shape the layout is for
+// (defaults: warp tiles; luf::uf_cta uses LUF_CTA_*).
+inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr, uint32_t list_cap = LIST_CAP,
+                          uint32_t list2_cap = LIST2_CAP, uint32_t claim_slots = CLAIM_SLOTS)
 {
     Layout l;
     uint32_t off = 0;
@@ -96,8 +99,8 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr)
     l.err = keep_err ? take(4u * WE) : 0;
     l.corr = keep_corr ? take(4u * WE) : 0;
     l.zero_bytes = off - l.zero_off;                  // ----
-    l.claim = take(4u * ((uint32_t)CLAIM_SLOTS > WN ? (uint32_t)CLAIM_SLOTS : WN));   // visited bitmap of the peel
-    l.list = take(4u * LIST_CAP); l.list2 = take(4u * LIST2_CAP); l.cnt = take(16);
+    l.claim = take(4u * (claim_slots > WN ? claim_slots : WN));   // visited bitmap of the peel
+    l.list = take(4u * list_cap); l.list2 = take(4u * list2_cap); l.cnt = take(16);
     l.bytes = off;
     return l;
 }

@@ -97,6 +97,59 @@ __global__ void k_decode_uf(GraphView g, Layout l, int flags, long long nshots,
     }
 }
 
+// The same two kernels with one thread block per shot (luf::uf_cta): graphs
+// whose shot state leaves only a few warps per SM (Surface d >= 13 with
+// measurement rounds).  The first warp samples, so that a shot's noise does not
+// depend on the tile shape; every other phase runs on all threads of the block.
+template <int TF>
+__global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, SampleParams sp,
+                        unsigned long long shot0, long long nshots, unsigned long long* counts)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x, nl = blockDim.x;
+    const Shot s = bind(l, smem);
+    unsigned int fails = 0;
+    for (long long k = blockIdx.x; k < nshots; k += gridDim.x) {
+        uint32_t parity = 0;
+        uf_cta::ph_reset(g, l, s, lane, nl);
+        __syncthreads();
+        if (lane < WARP) parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, WARP);
+        __syncthreads();
+        uf_cta::ph_load(g, s, lane, nl);
+        __syncthreads();
+        uf_cta::uf_validate_t<TF>(g, s, TF, lane, nl);
+        parity ^= uf_cta::uf_peel(g, s, lane, nl);
+        fails += (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
+    }
+    if (threadIdx.x == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+}
+
+__global__ void __launch_bounds__(448, 2) k_decode_uf_cta(GraphView g, Layout l, int flags, long long nshots,
+                            const uint32_t* __restrict__ syn, uint32_t* __restrict__ corr,
+                            uint32_t* __restrict__ growth2b, int32_t* __restrict__ steps)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x, nl = blockDim.x;
+    const Shot s = bind(l, smem);
+    const int GW = (g.E + 15) >> 4;
+    for (long long k = blockIdx.x; k < nshots; k += gridDim.x) {
+        uf_cta::ph_reset(g, l, s, lane, nl);
+        __syncthreads();
+        for (int w = lane; w < g.WD; w += nl) s.defect[w] = __ldg(&syn[k * g.WD + w]);
+        __syncthreads();
+        uf_cta::ph_load(g, s, lane, nl);
+        __syncthreads();
+        const int rounds = uf_cta::uf_validate_t<-1>(g, s, flags, lane, nl);
+        if (growth2b)
+            for (int w = lane; w < GW; w += nl) growth2b[k * GW + w] = s.growth[w];
+        uf_cta::uf_peel(g, s, lane, nl);
+        for (int w = lane; w < g.WE; w += nl) corr[k * g.WE + w] = s.corr[w];
+        if (steps && lane == 0) { steps[2 * k] = rounds; steps[2 * k + 1] = 0; }
+        __syncthreads();
+    }
+}
+
 // Staged K3a: Macar / Actis (decoders/luf/main.py:83-166): syndromes in;
 // correction, growth after validation and (tSV, tBP) out.
 template <bool ACTIS>
@@ -305,6 +358,7 @@ struct luf_graph {
     GraphView view{};
     std::vector<void*> allocs;
     Layout lay_fused{}, lay_decode{}, lay_sample{};
+    Layout lay_fused_cta{}, lay_decode_cta{};     // one block per shot (luf::uf_cta work-list sizes)
     PackedCa ca_host;
     std::string ca_why;           // why Macar/Actis cannot run on this graph ("" = they can)
     CaView ca_view{};
@@ -403,6 +457,52 @@ static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long n
     if (blocks < 1) blocks = 1;
     cfg->grid = (int)blocks; cfg->block = wpb * WARP; cfg->smem = smem;
     return 0;
+}
+
+// One block per shot: the block size that keeps the most warps resident.
+template <class K>
+static int plan_cta_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long nshots, LaunchCfg* cfg)
+{
+    if (slice_bytes > (uint32_t)g->max_smem)
+        return fail(LUF_ERR_UNSUPPORTED, "one shot's decoder state (" + std::to_string(slice_bytes) +
+                    " B) exceeds the shared memory of an SM");
+    static const int env_threads = getenv("LUF_CTA_THREADS") ? atoi(getenv("LUF_CTA_THREADS")) : 0;
+    const std::pair<const void*, uint32_t> key((const void*)kernel, slice_bytes);
+    auto hit = g->plans.find(key);
+    int threads = 0, per_sm = 0;
+    if (hit != g->plans.end()) { threads = hit->second.first; per_sm = hit->second.second; }
+    else {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int best = 0;
+        for (int cand = 448; cand >= 64; cand -= 32) {
+            if (env_threads > 0 && cand != env_threads) continue;
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, cand, slice_bytes));
+            if (occ * cand > best) { best = occ * cand; threads = cand; per_sm = occ; }    // ties: larger blocks
+        }
+        if (best == 0) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+        if (getenv("LUF_DEBUG_PLAN"))
+            fprintf(stderr, "[luf] launch plan (block per shot): %u B per shot, %d threads per block, %d blocks per SM\n",
+                    slice_bytes, threads, per_sm);
+        g->plans[key] = std::make_pair(threads, per_sm);
+    }
+    long long blocks = (long long)g->sm_count * per_sm;
+    if (blocks > nshots) blocks = nshots;
+    if (blocks < 1) blocks = 1;
+    cfg->grid = (int)blocks; cfg->block = threads; cfg->smem = slice_bytes;
+    return 0;
+}
+
+// Warp tiles while a shot's state leaves at least 16 warps per SM, else one
+// block per shot (LUF_TILE=warp|cta overrides, for measurements).
+static bool use_cta_tiles(const luf_graph* g, uint32_t warp_slice_bytes, uint32_t cta_slice_bytes)
+{
+    static const char* env = getenv("LUF_TILE");
+    if (cta_slice_bytes > (uint32_t)g->max_smem) return false;
+    if (env && !strcmp(env, "warp")) return false;
+    if (env && !strcmp(env, "cta")) return true;
+    return (size_t)16 * warp_slice_bytes > (size_t)g->max_smem;
 }
 
 static int check_device(void)
@@ -643,6 +743,8 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     }
     g->lay_fused = make_layout(p.N, p.B, p.E, false, false);
     g->lay_decode = make_layout(p.N, p.B, p.E, false, true);
+    g->lay_fused_cta = make_layout(p.N, p.B, p.E, false, false, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS);
+    g->lay_decode_cta = make_layout(p.N, p.B, p.E, false, true, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS);
     {   // the sampler only needs the error and defect bitmaps
         Layout l; memset(&l, 0, sizeof(l));
         uint32_t off = 0;
@@ -746,9 +848,15 @@ int luf_decode_batch(luf_graph* g, int decoder, int flags, int64_t nshots, const
         k_decode_ca<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(
             g->ca_view, g->lay_actis, flags, nshots, syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
     } else {
-        if (int rc = plan_launch(g, k_decode_uf, g->lay_decode.bytes, nshots, &c)) return rc;
-        k_decode_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_decode, flags, nshots,
-                                                                        syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+        if (use_cta_tiles(g, g->lay_decode.bytes, g->lay_decode_cta.bytes)) {
+            if (int rc = plan_cta_launch(g, k_decode_uf_cta, g->lay_decode_cta.bytes, nshots, &c)) return rc;
+            k_decode_uf_cta<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_decode_cta, flags, nshots,
+                                                                                syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+        } else {
+            if (int rc = plan_launch(g, k_decode_uf, g->lay_decode.bytes, nshots, &c)) return rc;
+            k_decode_uf<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_decode, flags, nshots,
+                                                                            syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+        }
     }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;
@@ -794,13 +902,17 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
         // the decoder flags are compile-time constants of the fused kernel
 #define LUF_MC_UF(TF) { if (int rc = plan_launch(g, k_mc_uf<TF>, g->lay_fused.bytes, nshots, &c, 14)) return rc; \
         k_mc_uf<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, shot0, nshots, counts_dev); }
+#define LUF_MC_UF_CTA(TF) { if (int rc = plan_cta_launch(g, k_mc_uf_cta<TF>, g->lay_fused_cta.bytes, nshots, &c)) return rc; \
+        k_mc_uf_cta<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused_cta, sp, shot0, nshots, counts_dev); }
+        const bool cta = use_cta_tiles(g, g->lay_fused.bytes, g->lay_fused_cta.bytes);
         switch (flags & 3) {
-            case 0: LUF_MC_UF(0) break;
-            case 1: LUF_MC_UF(1) break;
-            case 2: LUF_MC_UF(2) break;
-            default: LUF_MC_UF(3) break;
+            case 0: if (cta) LUF_MC_UF_CTA(0) else LUF_MC_UF(0) break;
+            case 1: if (cta) LUF_MC_UF_CTA(1) else LUF_MC_UF(1) break;
+            case 2: if (cta) LUF_MC_UF_CTA(2) else LUF_MC_UF(2) break;
+            default: if (cta) LUF_MC_UF_CTA(3) else LUF_MC_UF(3) break;
         }
 #undef LUF_MC_UF
+#undef LUF_MC_UF_CTA
     }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;

@@ -57,6 +57,30 @@ int emu_decode_uf(const luf_graph_desc* d, int flags, long long nshots, const ui
     return 0;
 }
 
+// The same with the block-per-shot instance of the phases (luf::uf_cta): a tile of `nl` lanes.
+int emu_decode_uf_cta(const luf_graph_desc* d, int flags, int nl, long long nshots, const uint32_t* syn,
+                      uint32_t* corr, uint32_t* growth2b, int32_t* steps)
+{
+    PackedGraph p;
+    if (!pack_graph(*d, p).empty() || nl < 32 || nl > 1024) return -1;
+    const GraphView g = view_of(p);
+    const Layout l = make_layout(p.N, p.B, p.E, false, true, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS);
+    std::vector<unsigned char> mem(l.bytes);
+    const Shot s = bind(l, mem.data());
+    const int GW = (g.E + 15) / 16;
+    for (long long k = 0; k < nshots; ++k) {
+        LUF_PHASE(uf_cta::ph_reset(g, l, s, lane, nl));
+        for (int w = 0; w < g.WD; ++w) s.defect[w] = syn[k * g.WD + w];
+        LUF_PHASE(uf_cta::ph_load(g, s, lane, nl));
+        const int rounds = uf_cta::uf_validate_t<-1>(g, s, flags, 0, nl);
+        if (growth2b) export_growth(g, s, growth2b + k * GW);
+        uf_cta::uf_peel(g, s, 0, nl);
+        std::memcpy(corr + k * g.WE, s.corr, 4u * g.WE);
+        if (steps) { steps[2 * k] = rounds; steps[2 * k + 1] = 0; }
+    }
+    return 0;
+}
+
 // Fused Monte-Carlo shot loop; optionally exports the sampled errors, their
 // syndromes and the corrections so that the oracle can re-decode them.
 int emu_mc_uf(const luf_graph_desc* d, int flags, const double* class_p, unsigned long long seed,

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, '_build', 'libluf_emu.so')
 CSRC = os.path.join(ROOT, 'localuf_b200', 'csrc')
 SRCS = [os.path.join(HERE, 'emu.cpp')] + [
-    os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))
+    os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h', '.inl'))
 ] + [os.path.join(ROOT, 'include', 'luf_b200.h')]
 
 
@@ -22,7 +22,7 @@ def build(tiny_lists=False):
     if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in SRCS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(['g++', '-O1', '-g', '-fPIC', '-shared', '-std=c++17', '-Wall', '-Wextra']
-                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2'] if tiny_lists else []) + ['-o', out, SRCS[0]],
+                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2', '-DLUF_CTA_LIST_CAP=5', '-DLUF_CTA_LIST2_CAP=3'] if tiny_lists else []) + ['-o', out, SRCS[0]],
                        check=True, capture_output=True)
     return out
 
@@ -66,6 +66,18 @@ class Emu:
         steps = np.zeros((n, 2), np.int32)
         rc = lib().emu_decode_uf(C.byref(self.desc), flags, C.c_longlong(n), _vp(syn),
                                  _vp(corr), _vp(growth), _vp(steps))
+        assert rc == 0
+        return corr, growth, steps
+
+    def decode_uf_cta(self, flags, syn_bits, nl=128):
+        """The block-per-shot instance of the phases (luf::uf_cta) with a tile of ``nl`` lanes."""
+        syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
+        n = syn.shape[0]
+        corr = np.zeros((n, self.WE), np.uint32)
+        growth = np.zeros((n, self.WG), np.uint32)
+        steps = np.zeros((n, 2), np.int32)
+        rc = lib().emu_decode_uf_cta(C.byref(self.desc), flags, nl, C.c_longlong(n), _vp(syn),
+                                     _vp(corr), _vp(growth), _vp(steps))
         assert rc == 0
         return corr, growth, steps
 

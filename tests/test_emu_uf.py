@@ -30,6 +30,20 @@ def test_emu_decode_matches_reference(name):
         np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
 
 
+@pytest.mark.parametrize('name', golden_names('uf_'))
+@pytest.mark.parametrize('nl', [64, 448])
+def test_emu_block_tile_matches_reference(name, nl):
+    """The block-per-shot instance of the phases (luf::uf_cta; tiles of 64 and 448 lanes)."""
+    meta, arr = load_golden(name)
+    code = make_code(meta['spec'])
+    emu = emu_binding.Emu(code)
+    for variant, flags in FLAGS.items():
+        corr, growth2b, steps = emu.decode_uf_cta(flags, arr['syn_bits'], nl=nl)
+        np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{variant}_growth'])
+        np.testing.assert_array_equal(steps[:, 0], arr[f'{variant}_rounds'])
+        np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
+
+
 @pytest.mark.parametrize('spec,p', [
     (dict(code='Repetition', d=5, noise='code capacity'), 0.05),
     (dict(code='Surface', d=9, noise='code capacity'), 0.10),
@@ -109,6 +123,9 @@ def test_emu_overflow_paths_with_tiny_work_lists():
                 corr, growth2b, steps = emu.decode_uf(flags, arr['syn_bits'])
                 np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{variant}_growth'])
                 np.testing.assert_array_equal(steps[:, 0], arr[f'{variant}_rounds'])
+                np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
+                corr, growth2b, steps = emu.decode_uf_cta(flags, arr['syn_bits'], nl=96)
+                np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{variant}_growth'])
                 np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
     finally:
         emu_binding.use_tiny_lists(False)

@@ -63,6 +63,9 @@ CASES = [
     (dict(code='Surface', d=5, noise='circuit-level'), 0.01, 5000),
     (dict(code='Surface', d=7, noise='circuit-level', kwargs=dict(parametrization='standard')), 0.005, 3000),
     (dict(code='Surface', d=13, noise='phenomenological'), 0.02, 2000),
+    # large graphs: one thread block per shot (luf::uf_cta) is chosen automatically
+    (dict(code='Surface', d=15, noise='phenomenological'), 0.02, 600),
+    (dict(code='Surface', d=19, noise='phenomenological'), 0.028, 120),
 ]
 
 
@@ -93,6 +96,19 @@ def test_pipeline_vs_oracle_on_gpu_samples(spec, p, n, variant):
     assert fails == int(ological.sum())
     fused, shots = eng.mc_run_host(_engine.DEC_UF, flags, p, seed, shot0, n)
     assert (fused, shots) == (fails, n)
+
+
+@pytest.mark.skipif(os.environ.get('LUF_TILE') is not None, reason='already inside the forced-tile run')
+@pytest.mark.parametrize('tile', ['cta', 'warp'])
+def test_both_tile_shapes_on_every_case(tile):
+    """Golden and oracle parity again with the tile shape forced: one thread block
+    per shot on the small graphs, one warp per shot on the large ones."""
+    import subprocess
+    env = dict(os.environ, LUF_TILE=tile)
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-x', '-q', '-m', 'gpu',
+                        '-k', 'goldens or pipeline', '-p', 'no:cacheprovider'],
+                       env=env, cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_sampler_statistics_and_counter_based_stream():
