@@ -108,6 +108,16 @@ int luf_graph_words(const luf_graph *g, int32_t *edge_words, int32_t *detector_w
 int luf_sample(luf_graph *g, const double *class_p_host, uint64_t seed, uint64_t shot0,
                int64_t nshots, uint32_t *err_bits_dev, uint32_t *syn_bits_dev, void *stream);
 
+/* Subset sampling -- replaces Noise.force_error(weight) for the uniform noise
+ * models (localuf/noise/main.py:116-122: random.sample(FRESH_EDGES, weight)) and
+ * Code.get_syndrome: every shot flips exactly `weight` distinct fresh edges,
+ * every subset equally likely; same counter-based keying as luf_sample.
+ * weight outside [0, #fresh edges] -> LUF_ERR_INVALID (random.sample's ValueError). */
+int luf_sample_weight(luf_graph *g, int32_t weight, uint64_t seed, uint64_t shot0, int64_t nshots,
+                      uint32_t *err_bits_dev, uint32_t *syn_bits_dev, void *stream);
+int luf_sample_weight_host(luf_graph *g, int32_t weight, uint64_t seed, uint64_t shot0, int64_t nshots,
+                           uint32_t *err_bits_host, uint32_t *syn_bits_host);
+
 /* K2/K3 -- replaces Decoder.reset() + Decoder.decode(syndrome)
  * (localuf/decoders/uf.py:79-119,200-344; decoders/luf/main.py:83-188) for a
  * batch of syndromes.  corr_bits_dev [nshots][W(E)] receives decoder.correction;

@@ -146,6 +146,8 @@ def _load():
         lib.luf_decode_batch_host.argtypes = [v, C.c_int, C.c_int, i64, v, v, v, v]
         lib.luf_sample_host.argtypes = [v, v, u64, u64, i64, v, v]
         lib.luf_check_host.argtypes = [v, i64, v, v, v, v]
+        lib.luf_sample_weight.argtypes = [v, C.c_int32, u64, u64, i64, v, v, v]
+        lib.luf_sample_weight_host.argtypes = [v, C.c_int32, u64, u64, i64, v, v]
         lib.luf_forward_attach.argtypes = [v, C.POINTER(ForwardDesc)]
         lib.luf_forward_decode_host.argtypes = [v, C.c_int, C.c_int, i64, C.c_int32, v, v, v, v, v]
         lib.luf_forward_mc_host.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, C.c_int32, v, v]
@@ -248,6 +250,41 @@ class Engine:
         syn = np.zeros((nshots, self.WD), np.uint32)
         _check(_load().luf_sample_host(self._h, cp.ctypes.data, seed, shot0, nshots, _ptr(err), _ptr(syn)))
         return err, syn
+
+    def sample_weight_host(self, weight: int, seed: int, shot0: int, nshots: int):
+        """Exactly ``weight`` distinct fresh edges flipped per shot (``Noise.force_error``)."""
+        err = np.zeros((nshots, self.WE), np.uint32)
+        syn = np.zeros((nshots, self.WD), np.uint32)
+        _check(_load().luf_sample_weight_host(self._h, int(weight), seed, shot0, nshots, _ptr(err), _ptr(syn)))
+        return err, syn
+
+    def mc_weight(self, decoder: int, flags: int, weight: int, seed: int, shot0: int, nshots: int,
+                  chunk: int = 1 << 18):
+        """Failures among ``nshots`` shots of fixed-weight errors: staged K1' -> K2/K3a -> K4 on
+        device buffers, a chunk of shots at a time; returns (failures, shots)."""
+        import torch
+        dev = torch.device('cuda', self.device)
+        chunk = min(chunk, max(1, nshots))
+        err = torch.empty((chunk, self.WE), dtype=torch.int32, device=dev)
+        syn = torch.empty((chunk, self.WD), dtype=torch.int32, device=dev)
+        corr = torch.empty((chunk, self.WE), dtype=torch.int32, device=dev)
+        fails = torch.zeros(1, dtype=torch.int64, device=dev)
+        lib, done = _load(), 0
+        with torch.cuda.device(dev):
+            st = _stream()
+            while done < nshots:
+                k = min(chunk, nshots - done)
+                _check(lib.luf_sample_weight(self._h, int(weight), seed, shot0 + done, k, _ptr(err), _ptr(syn), st))
+                _check(lib.luf_decode_batch(self._h, decoder, flags, k, _ptr(syn), _ptr(corr), None, None, st))
+                _check(lib.luf_check(self._h, k, _ptr(err), _ptr(corr), None, _ptr(fails), st))
+                done += k
+            return int(fails.item()), nshots
+
+    def mc_given_errors(self, decoder: int, flags: int, err_bits, syn_bits):
+        """Failures among given (error, syndrome) bit arrays: K2/K3a -> K4; returns (failures, shots)."""
+        corr, _, _ = self.decode_batch_host(decoder, flags, syn_bits, want_steps=False)
+        _, fails = self.check_host(err_bits, corr)
+        return fails, len(corr)
 
     def check_host(self, err_bits, corr_bits):
         err = np.ascontiguousarray(err_bits, dtype=np.uint32).reshape(-1, self.WE)

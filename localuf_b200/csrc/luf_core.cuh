@@ -291,6 +291,31 @@ LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams
     return ph_sample_tab(g, t, s, sp, shot, 0u, (const uint32_t*)0, lane, nl);
 }
 
+// Fixed-weight sampling (noise/main.py:116-122, _Uniform.force_error =
+// random.sample(FRESH_EDGES, weight)): exactly `weight` distinct fresh edges,
+// every subset equally likely.  Floyd's algorithm: for j = F - weight .. F - 1
+// draw t uniformly from [0, j]; take t, or j if t was taken already.  The error
+// bitmap itself records what was taken, so the staged sampler layout suffices.
+// One lane (the picks are a dependent chain; weights of interest are small).
+// Index draws are mulhi(r32, j + 1): relative bias <= (j + 1) / 2^32 < 2e-5.
+LUF_DEV void ph_force(const GraphView& g, const Shot& s, const SampleParams& sp, uint32_t weight,
+                      uint64_t shot, int lane)
+{
+    if (lane != 0) return;
+    Philox rng;
+    rng.c0 = (uint32_t)shot; rng.c1 = (uint32_t)(shot >> 32); rng.c2 = 0xF0CEu; rng.c3 = 0u;
+    rng.k0 = sp.key0; rng.k1 = sp.key1; rng.have = 0;
+    rng.o0 = rng.o1 = rng.o2 = rng.o3 = 0;
+    const uint32_t F = (uint32_t)g.F;
+    if (weight > F) weight = F;
+    for (uint32_t j = F - weight; j < F; ++j) {
+        const uint32_t t = luf_mulhi(philox_next(rng), j + 1u);
+        const uint32_t et = LUF_LDG(&g.fresh_perm[t]);
+        const uint32_t e = ((s.err[et >> 5] >> (et & 31u)) & 1u) ? (uint32_t)LUF_LDG(&g.fresh_perm[j]) : et;
+        flip_edge(g, s, e);
+    }
+}
+
 }  // namespace luf
 
 // ------------------------------------------------------------- the UF phases

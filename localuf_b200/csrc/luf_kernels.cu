@@ -330,6 +330,25 @@ __global__ void k_sample(GraphView g, Layout l, SampleParams sp, unsigned long l
     }
 }
 
+// Staged fixed-weight sampler (subset sampling, noise/main.py:116-122): every
+// shot flips exactly `weight` distinct fresh edges.
+__global__ void k_sample_weight(GraphView g, Layout l, SampleParams sp, uint32_t weight, unsigned long long shot0,
+                                long long nshots, uint32_t* __restrict__ err, uint32_t* __restrict__ syn)
+{
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    const Shot s = bind(l, warp_slice(l));
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        LUF_PHASE(for (int w = lane; w < g.WE; w += nl) s.err[w] = 0;
+                  for (int w = lane; w < g.WD; w += nl) s.defect[w] = 0);
+        LUF_PHASE(ph_force(g, s, sp, weight, shot0 + (unsigned long long)k, lane));
+        for (int w = lane; w < g.WE; w += nl) err[k * g.WE + w] = s.err[w];
+        for (int w = lane; w < g.WD; w += nl) syn[k * g.WD + w] = s.defect[w];
+        __syncwarp();
+    }
+}
+
 // Staged K4: leftover parity on the west boundary (_schemes.py:123-129,154-155).
 __global__ void k_check(int WE, long long nshots, const uint32_t* __restrict__ west_mask,
                         const uint32_t* __restrict__ err, const uint32_t* __restrict__ corr,
@@ -830,6 +849,26 @@ int luf_sample(luf_graph* g, const double* class_p_host, uint64_t seed, uint64_t
     return 0;
 }
 
+int luf_sample_weight(luf_graph* g, int32_t weight, uint64_t seed, uint64_t shot0, int64_t nshots,
+                      uint32_t* err_bits_dev, uint32_t* syn_bits_dev, void* stream)
+{
+    if (!g || !err_bits_dev || !syn_bits_dev || nshots < 0)
+        return fail(LUF_ERR_INVALID, "luf_sample_weight: bad argument");
+    if (weight < 0 || weight > g->view.F)
+        return fail(LUF_ERR_INVALID, "Sample larger than population or is negative");       // random.sample's message
+    if (nshots == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const double zero[MAX_CLASSES] = {0};
+    const SampleParams sp = make_sample_params(zero, g->view.n_classes, seed);
+    LaunchCfg c;
+    if (int rc = plan_launch(g, k_sample_weight, g->lay_sample.bytes, nshots, &c)) return rc;
+    k_sample_weight<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_sample, sp, (uint32_t)weight, shot0,
+                                                                        nshots, err_bits_dev, syn_bits_dev);
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
 int luf_decode_batch(luf_graph* g, int decoder, int flags, int64_t nshots, const uint32_t* syn_bits_dev,
                      uint32_t* corr_bits_dev, uint32_t* growth2b_dev, int32_t* steps_dev, void* stream)
 {
@@ -1108,6 +1147,24 @@ int luf_sample_host(luf_graph* g, const double* class_p_host, uint64_t seed, uin
     int rc;
     if ((rc = scratch_get(g, 1, n * WD * 4, &syn)) || (rc = scratch_get(g, 2, n * WE * 4, &err))) return rc;
     if ((rc = luf_sample(g, class_p_host, seed, shot0, nshots, (uint32_t*)err, (uint32_t*)syn, 0))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(err_bits_host, err, n * WE * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(syn_bits_host, syn, n * WD * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int luf_sample_weight_host(luf_graph* g, int32_t weight, uint64_t seed, uint64_t shot0, int64_t nshots,
+                           uint32_t* err_bits_host, uint32_t* syn_bits_host)
+{
+    if (!g || !err_bits_host || !syn_bits_host || nshots < 0) return fail(LUF_ERR_INVALID, "luf_sample_weight_host: bad argument");
+    if (nshots == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t n = (size_t)nshots, WE = g->view.WE, WD = g->view.WD;
+    void *err, *syn;
+    int rc;
+    if ((rc = scratch_get(g, 1, n * WD * 4, &syn)) || (rc = scratch_get(g, 2, n * WE * 4, &err))) return rc;
+    if ((rc = luf_sample_weight(g, weight, seed, shot0, nshots, (uint32_t*)err, (uint32_t*)syn, 0))) return rc;
     CUDA_TRY(cudaMemcpyAsync(err_bits_host, err, n * WE * 4, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaMemcpyAsync(syn_bits_host, syn, n * WD * 4, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));

@@ -59,6 +59,69 @@ class Decoder:
         return fails
 
 
+    def _mc_weight(self, weight, n: int, seed=None) -> int:
+        """Failure count of ``n`` shots of weight-``weight`` errors (``Batch.sim_cycles_given_weight``)."""
+        eng = self.engine
+        if isinstance(weight, (int, np.integer)):
+            if not 0 <= weight <= len(self._CODE.NOISE.FRESH_EDGES):
+                raise ValueError('Sample larger than population or is negative')
+            return self._sharded_counts(
+                lambda s, lo, cnt: eng.mc_weight(self._DECODER_ID, self._flags, int(weight), s, lo, cnt), n, seed)
+        # circuit-level: weight vectors over fault populations; the reference's sampler, in batches
+        flat, noise = self._CODE.FLAT, self._CODE.NOISE
+        rank, size = dist.world()
+        lo, cnt = dist.shard(n, rank, size)
+        fails, done = 0, 0
+        while done < cnt:
+            k = min(4096, cnt - done)
+            errors = [noise.force_error(weight) for _ in range(k)]
+            err = np.stack([flat.edges_to_bits(e) for e in errors])
+            syn = np.stack([flat.syndrome_to_bits(self._CODE.get_syndrome(e)) for e in errors])
+            fails += eng.mc_given_errors(self._DECODER_ID, self._flags, err, syn)[0]
+            done += k
+        return dist.allreduce_counts([fails], device=f'cuda:{eng.device}')[0]
+
+    def subset_sample(self, noise_level: float, n: int, tol: float = 5e-1, **kwargs):
+        """Failures per error subset (``_base_classes.py:682-712``): a DataFrame indexed by
+        weight with columns ``['subset prob', 'survival prob', 'm', 'n']``, subsets taken in
+        decreasing probability until the probability left over is below ``tol`` times the
+        failure rate accumulated so far."""
+        import pandas as pd
+        subset_probs = self._CODE.NOISE.subset_probabilities(noise_level)
+        mean, mn, weights = 0, [], []
+        for weight in subset_probs.index:
+            weights.append(weight)
+            weightless = weight == 0 if isinstance(weight, (int, np.integer)) else all(w == 0 for w in weight)
+            if weightless:
+                mn.append((np.nan, np.nan))
+            else:
+                w = int(weight) if isinstance(weight, (int, np.integer)) else tuple(int(x) for x in weight)
+                m, shots = self._CODE.SCHEME.sim_cycles_given_weight(self, w, n, **kwargs)
+                mn.append((m, shots))
+                mean += subset_probs.loc[weight, 'subset prob'] * m / shots
+                if mean * tol > subset_probs.loc[weight, 'survival prob']:
+                    break
+        index = pd.MultiIndex.from_tuples(weights) if type(subset_probs.index) is pd.MultiIndex else pd.Index(weights)
+        subset_failures = pd.DataFrame(mn, index=index, columns=['m', 'n'])
+        return pd.concat([subset_probs, subset_failures], axis=1, join='inner')
+
+    def _mc_global(self, noise_level: float, shots: int = 1, seed=None):
+        """``shots`` windows of the global batch scheme (``_schemes.py:186-203``): sampled and
+        decoded on the device, the logical error strings of each leftover counted on the host."""
+        eng = self.engine
+        rank, size = dist.world()
+        seed = self._draw_seed(seed)
+        if size > 1:
+            seed = dist.allreduce_counts([seed if rank == 0 else 0])[0]
+        lo, cnt = dist.shard(shots, rank, size)
+        total = 0
+        if cnt:
+            err, syn = eng.sample_host(noise_level, seed, lo, cnt)
+            corr, _, _ = eng.decode_batch_host(self._DECODER_ID, self._flags, syn, want_steps=False)
+            for leftover in err ^ corr:
+                total += self._CODE.SCHEME.count_leftover_bits(leftover)
+        return dist.allreduce_counts([total], device=f'cuda:{eng.device}')[0]
+
     def _mc_forward(self, noise_level: float, n: int, shots: int = 1, seed=None, draw=False, log_history=False,
                     **kwargs):
         """``shots`` independent ``Forward.run(n)`` experiments on the device

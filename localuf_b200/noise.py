@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import abc
 import random
-from functools import lru_cache
+from functools import cached_property, lru_cache
 from math import log10, prod
 
 Edge = tuple
@@ -78,10 +78,25 @@ class Noise(abc.ABC):
     def log_odds_of_no_flip(flip_probability: float) -> float:
         return log10((1 - flip_probability) / flip_probability)
 
+    @abc.abstractmethod
     def force_error(self, weight):
-        raise NotImplementedError(
-            "Fixed-weight (subset) sampling is outside the Monte-Carlo hot path of this engine "
-            "(SURVEY.md section 8 row f3).")
+        """Make an error of weight ``weight`` (``noise/main.py:38-40``)."""
+
+    @abc.abstractmethod
+    def subset_probability(self, weights, noise_level: float):
+        """Probability of any error of weight ``weight``, for ``weight`` in ``weights``."""
+
+    def subset_probabilities(self, noise_level: float, survival: bool = True):
+        """DataFrame indexed by subset weight with columns ``['subset prob', 'survival prob']``,
+        most probable subset first (``noise/main.py:50-66``)."""
+        import pandas as pd
+        subset_prob = self.subset_probability(self.ALL_WEIGHTS, noise_level)
+        df = pd.DataFrame({'subset prob': subset_prob}, index=self.ALL_WEIGHTS_INDEX)
+        if survival:
+            df.sort_values(by='subset prob', inplace=True)
+            df['survival prob'] = df['subset prob'].cumsum().shift(fill_value=0)
+        df.sort_values(by='subset prob', ascending=False, inplace=True)
+        return df
 
 
 class _Uniform(Noise):
@@ -106,6 +121,16 @@ class _Uniform(Noise):
     def ALL_WEIGHTS(self):
         return range(len(self._FRESH_EDGES) + 1)
 
+    @property
+    def ALL_WEIGHTS_INDEX(self):
+        import pandas as pd
+        return pd.Index(self.ALL_WEIGHTS, name='weight')
+
+    def subset_probability(self, weights, noise_level: float):
+        """Binomial weight distribution (``noise/main.py:128-134``)."""
+        from scipy.stats import binom
+        return binom.pmf(k=weights, n=len(self._FRESH_EDGES), p=noise_level)
+
     def classes(self):
         return [self._FRESH_EDGES]
 
@@ -128,6 +153,88 @@ class Phenomenological(_Uniform):
     def __str__(self): return 'phenomenological'
 
 
+class _BaseForceByPair:
+    """Error subsets distinguished by how many faults of each pair type occurred
+    (``noise/forcers.py:76-128``): population ``k`` lists every edge once per fault of type
+    ``k`` it stands for; an edge drawn twice flips back."""
+
+    def __init__(self, edges):
+        self._EDGES = edges
+
+    def _populations(self):
+        out = []
+        for k in range(4):
+            pairs = []
+            for m, edges in self._EDGES.items():
+                pairs += m[k] * list(edges)
+            out.append(pairs)
+        return tuple(out)
+
+    def force_error(self, weight):
+        error: set[Edge] = set()
+        if len(weight) != len(self.PAIR_POPULATIONS):
+            raise ValueError('zip() arguments have different lengths')
+        for pairs, w in zip(self.PAIR_POPULATIONS, weight):
+            for e in random.sample(pairs, w):
+                error.symmetric_difference_update((e,))
+        return error
+
+    @property
+    def ALL_WEIGHTS(self):
+        import itertools
+        return tuple(itertools.product(*(range(len(pairs) + 1) for pairs in self.PAIR_POPULATIONS)))
+
+    def subset_probability(self, weights, pi):
+        import numpy as np
+        from scipy.stats import binom
+        probs = np.ones(len(weights))
+        columns = np.array(weights).T
+        for row, pairs, p in zip(columns, self.PAIR_POPULATIONS, pi):
+            probs *= binom.pmf(k=row, n=len(pairs), p=p)
+        return probs
+
+
+class ForceByPair(_BaseForceByPair):
+    """Weights are 4-tuples (``noise/forcers.py:131-141``); any parametrization but 'balanced'."""
+
+    @cached_property
+    def PAIR_POPULATIONS(self):
+        return self._populations()
+
+
+class ForceByPairBalanced(_BaseForceByPair):
+    """The last three pair types share one probability: weights are 2-tuples
+    (``noise/forcers.py:144-155``)."""
+
+    @cached_property
+    def PAIR_POPULATIONS(self):
+        p0, *rest = self._populations()
+        return (p0, sum(rest, start=[]))
+
+
+class ForceByEdge:
+    """Weights count the flipped edges of each multiplicity class (``noise/forcers.py:158-184``)."""
+
+    def __init__(self, edges):
+        self._EDGES = edges
+
+    def force_error(self, weight):
+        if len(weight) != len(self._EDGES):
+            raise ValueError(f'len(weight)={len(weight)} != {len(self._EDGES)}=number of edge subsets')
+        error: set[Edge] = set()
+        for subset, w in zip(self._EDGES.values(), weight):
+            error.update(random.sample(subset, w))
+        return error
+
+    @property
+    def ALL_WEIGHTS(self):
+        import itertools
+        return tuple(itertools.product(*(range(len(subset) + 1) for subset in self._EDGES.values())))
+
+    def subset_probability(self, weights, pi):
+        raise NotImplementedError
+
+
 class CircuitLevel(Noise):
     """Circuit-level depolarising noise: each edge flips with the probability
     that an odd number of the circuit faults it stands for occurred."""
@@ -141,6 +248,12 @@ class CircuitLevel(Noise):
         self._ALL_EDGES = (self._FRESH_EDGES if all_edge_dict is None
                            else self._group(all_edge_dict, demolition, monolingual, all_merges))
         self._probs = lru_cache(maxsize=None)(self._compute_probabilities)
+        if force_by == 'pair':                      # noise/main.py:219-226
+            self._FORCER = (ForceByPairBalanced if parametrization == 'balanced' else ForceByPair)(self._FRESH_EDGES)
+        elif force_by == 'edge':
+            self._FORCER = ForceByEdge(self._FRESH_EDGES)
+        else:
+            raise ValueError(f"Unknown force_by {force_by!r}.")
 
     @staticmethod
     def _make_multiplicities(demolition: bool, monolingual: bool):
@@ -194,6 +307,21 @@ class CircuitLevel(Noise):
         for m, pr in self._probs(noise_level).items():
             error.update(e for e in self._FRESH_EDGES[m] if rnd() < pr)
         return error
+
+    def force_error(self, weight):
+        return self._FORCER.force_error(weight)
+
+    @property
+    def ALL_WEIGHTS(self):
+        return self._FORCER.ALL_WEIGHTS
+
+    @property
+    def ALL_WEIGHTS_INDEX(self):
+        import pandas as pd
+        return pd.MultiIndex.from_tuples(self.ALL_WEIGHTS)
+
+    def subset_probability(self, weights, noise_level: float):
+        return self._FORCER.subset_probability(weights, self._pi(noise_level))
 
     def classes(self):
         return list(self._FRESH_EDGES.values())

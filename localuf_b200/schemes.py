@@ -154,9 +154,7 @@ class Scheme(abc.ABC):
     def run(self, decoder, noise_level: float, n: int, **kwargs): ...
 
     def sim_cycles_given_weight(self, decoder, weight, n):
-        raise NotImplementedError(
-            "Fixed-weight (subset) sampling is outside the Monte-Carlo hot path of this engine "
-            "(SURVEY.md section 8 row f3).")
+        raise NotImplementedError(f"Subset sampling is defined for the batch scheme only, not {self}.")
 
 
 class Batch(Scheme):
@@ -189,6 +187,13 @@ class Batch(Scheme):
         m = decoder._mc_batch(noise_level, n, **kwargs)
         return m, self._slenderness(n)
 
+    def sim_cycles_given_weight(self, decoder, weight, n: int, **kwargs):
+        """``n`` shots whose error has exactly weight ``weight`` (``_schemes.py:157-163``);
+        returns ``(failures, n)``.  Uniform noise models: sampled on the device
+        (``luf_sample_weight``); circuit-level weights (tuples): ``Noise.force_error`` on the
+        host, decoding and the logical check on the device."""
+        return decoder._mc_weight(weight, n, **kwargs), n
+
     def _sim_cycle_given_error(self, decoder, error) -> int:
         """Single shot through the drop-in API (``_schemes.py:143-155``)."""
         syndrome = self._CODE.get_syndrome(error)
@@ -201,7 +206,7 @@ class Batch(Scheme):
 
 
 class Global(Batch):
-    """One tall window of ``d*n`` layers; failures are *counted*
+    """One tall window of ``d*n`` layers; logical error strings are *counted*
     (``_schemes.py:166-203``)."""
 
     def __str__(self) -> str:
@@ -215,15 +220,33 @@ class Global(Batch):
         self.pairs.reset()
 
     def get_logical_error(self, leftover) -> int:
-        for e in leftover:
+        """``_schemes.py:194-203``.  Where three or more leftover edges meet, the pairing of
+        string ends depends on the order of the loads; the reference iterates a ``set``,
+        here the order is ascending edge id (``oracle/gen_golden_gl.py`` stores both counts)."""
+        index = self._CODE.FLAT.edge_index
+        for e in sorted(leftover, key=index.__getitem__):
             self.pairs.load(e)
         a, d = self._CODE.LONG_AXIS, self._CODE.D
         return sum(1 for u, v in self.pairs.as_set if abs(u[a] - v[a]) == d)
 
-    def run(self, decoder, noise_level: float, n: int, **kwargs):
+    def count_leftover_bits(self, leftover_bits) -> int:
+        """The same for one bit-packed leftover (``err ^ corr`` of the device)."""
+        import numpy as np
+        bits = np.unpackbits(np.ascontiguousarray(leftover_bits, dtype=np.uint32).view(np.uint8), bitorder='little')
+        edges = self._CODE.EDGES
+        self.reset()
+        for k in np.flatnonzero(bits[:len(edges)]).tolist():
+            self.pairs.load(edges[k])
+        a, d = self._CODE.LONG_AXIS, self._CODE.D
+        return sum(1 for u, v in self.pairs.as_set if abs(u[a] - v[a]) == d)
+
+    def run(self, decoder, noise_level: float, n: int, shots: int = 1, **kwargs):
+        """``_schemes.py:186-191``: ONE window of ``d*n`` layers is sampled and decoded on the
+        device (K1, K2/K3a), its leftover counted here; ``shots`` > 1 repeats that with
+        independent noise and sums (the reference always runs one)."""
         assert self.WINDOW_HEIGHT == self._CODE.D * n
         self.reset()
-        return self._sim_cycle_given_p(decoder, noise_level), n
+        return decoder._mc_global(noise_level, shots=shots, **kwargs), n * shots
 
 
 class _Streaming(Scheme):

@@ -81,6 +81,28 @@ int emu_decode_uf_cta(const luf_graph_desc* d, int flags, int nl, long long nsho
     return 0;
 }
 
+// Fixed-weight sampler (ph_force): errors and syndromes of shots [shot0, shot0 + nshots).
+int emu_sample_weight(const luf_graph_desc* d, int weight, unsigned long long seed, unsigned long long shot0,
+                      long long nshots, uint32_t* err_out, uint32_t* syn_out)
+{
+    PackedGraph p;
+    if (!pack_graph(*d, p).empty()) return -1;
+    const GraphView g = view_of(p);
+    const Layout l = make_layout(p.N, p.B, p.E, true, true);
+    const double zero[MAX_CLASSES] = {0};
+    const SampleParams sp = make_sample_params(zero, p.n_classes, seed);
+    std::vector<unsigned char> mem(l.bytes);
+    const Shot s = bind(l, mem.data());
+    const int nl = 32;
+    for (long long k = 0; k < nshots; ++k) {
+        LUF_PHASE(ph_reset(g, l, s, lane, nl));
+        LUF_PHASE(ph_force(g, s, sp, (uint32_t)weight, shot0 + k, lane));
+        std::memcpy(err_out + k * g.WE, s.err, 4u * g.WE);
+        std::memcpy(syn_out + k * g.WD, s.defect, 4u * g.WD);
+    }
+    return 0;
+}
+
 // Fused Monte-Carlo shot loop; optionally exports the sampled errors, their
 // syndromes and the corrections so that the oracle can re-decode them.
 int emu_mc_uf(const luf_graph_desc* d, int flags, const double* class_p, unsigned long long seed,

@@ -81,6 +81,14 @@ class Emu:
         assert rc == 0
         return corr, growth, steps
 
+    def sample_weight(self, weight, seed, shot0, nshots):
+        err = np.zeros((nshots, self.WE), np.uint32)
+        syn = np.zeros((nshots, self.WD), np.uint32)
+        rc = lib().emu_sample_weight(C.byref(self.desc), int(weight), C.c_ulonglong(seed), C.c_ulonglong(shot0),
+                                     C.c_longlong(nshots), _vp(err), _vp(syn))
+        assert rc == 0
+        return err, syn
+
     def mc_uf(self, flags, noise_level, seed, shot0, nshots, export=True):
         cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
         counts = (C.c_ulonglong * 2)(0, 0)
