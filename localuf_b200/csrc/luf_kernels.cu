@@ -815,7 +815,7 @@ int64_t luf_launch_count(const luf_graph* g) { return g ? g->launches : 0; }
 static int check_decoder(const luf_graph* g, int decoder, int flags)
 {
     if (decoder == LUF_DEC_UF) {
-        if (flags & ~(LUF_UF_DYNAMIC | LUF_UF_WEST)) return fail(LUF_ERR_INVALID, "unknown UF flag");
+        if (flags & ~(LUF_UF_DYNAMIC | LUF_UF_WEST | LUF_UF_NODE)) return fail(LUF_ERR_INVALID, "unknown UF flag");
         return 0;
     }
     if (decoder == LUF_DEC_MACAR || decoder == LUF_DEC_ACTIS) {
@@ -944,11 +944,15 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
 #define LUF_MC_UF_CTA(TF) { if (int rc = plan_cta_launch(g, k_mc_uf_cta<TF>, g->lay_fused_cta.bytes, nshots, &c)) return rc; \
         k_mc_uf_cta<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused_cta, sp, shot0, nshots, counts_dev); }
         const bool cta = use_cta_tiles(g, g->lay_fused.bytes, g->lay_fused_cta.bytes);
-        switch (flags & 3) {
+        switch (flags & 7) {
             case 0: if (cta) LUF_MC_UF_CTA(0) else LUF_MC_UF(0) break;
             case 1: if (cta) LUF_MC_UF_CTA(1) else LUF_MC_UF(1) break;
             case 2: if (cta) LUF_MC_UF_CTA(2) else LUF_MC_UF(2) break;
-            default: if (cta) LUF_MC_UF_CTA(3) else LUF_MC_UF(3) break;
+            case 3: if (cta) LUF_MC_UF_CTA(3) else LUF_MC_UF(3) break;
+            case 4: if (cta) LUF_MC_UF_CTA(4) else LUF_MC_UF(4) break;
+            case 5: if (cta) LUF_MC_UF_CTA(5) else LUF_MC_UF(5) break;
+            case 6: if (cta) LUF_MC_UF_CTA(6) else LUF_MC_UF(6) break;
+            default: if (cta) LUF_MC_UF_CTA(7) else LUF_MC_UF(7) break;
         }
 #undef LUF_MC_UF
 #undef LUF_MC_UF_CTA

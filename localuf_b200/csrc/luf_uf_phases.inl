@@ -202,13 +202,15 @@ LUF_DEV uint32_t ph_grow_first(const GraphView& g, const Shot& s, int lane, int 
     return total;
 }
 
-LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r)
+// `node`: NodeUF (node_uf.py:45-67) -- every frontier node adds 1 to each of its active edges, also
+// inside its own cluster.
+LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r, bool node)
 {
     for_row(g, u, [&](uint32_t ent) {
         const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
         if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
         const uint32_t o = (ent >> 16) & 0x7FFFu;
-        if (!(ent >> 31)) {                           // second endpoint: skip if same cluster
+        if (!node && !(ent >> 31)) {                  // second endpoint: skip if same cluster
             uint32_t wr;
             if (o == r || find_ro(s, o, wr) == r) return;
         }
@@ -226,27 +228,31 @@ LUF_DEV void ph_grow_gather(const GraphView& g, const Shot& s, int lane, int nl)
 }
 
 // ... keep those whose cluster is active (cnt[1], list2), one per lane ...
-LUF_DEV void ph_grow_filter(const GraphView& g, const Shot& s, int lane, int nl)
+template <int TF>
+LUF_DEV void ph_grow_filter(const GraphView& g, const Shot& s, int flags, int lane, int nl)
 {
+    const bool node = ((TF >= 0 ? TF : flags) & FLAG_NODE) != 0;
     for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
         uint32_t wr;
         const uint32_t r = find_pc(s, u, wr);
         if ((wr >> 16) != (ODD_BIT >> 16)) return;
         const uint32_t idx = luf_atomic_add(&s.cnt[1], 1u);
         if (idx < LUF_T_LIST2_CAP) s.list2[idx] = u | (r << 16);
-        else grow_node(g, s, u, r);
+        else grow_node(g, s, u, r, node);
     });
 }
 
 // ... and grow them, the edge loops spread evenly over the lanes.  Returns the
 // number of active nodes of the round.
-LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int lane, int nl)
+template <int TF>
+LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int flags, int lane, int nl)
 {
+    const bool node = ((TF >= 0 ? TF : flags) & FLAG_NODE) != 0;
     const uint32_t total = s.cnt[1];
     const uint32_t n = total < LUF_T_LIST2_CAP ? total : LUF_T_LIST2_CAP;
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
         const uint32_t it = s.list2[i];
-        grow_node(g, s, it & 0xFFFFu, it >> 16);
+        grow_node(g, s, it & 0xFFFFu, it >> 16, node);
     }
     return total;
 }
@@ -535,8 +541,8 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
             LUF_T_PHASE(active |= ph_grow_first(g, s, lane, nl));
         } else {
             LUF_T_PHASE(ph_grow_gather(g, s, lane, nl));
-            LUF_T_PHASE(ph_grow_filter(g, s, lane, nl));
-            LUF_T_PHASE(active |= ph_grow_exec(g, s, lane, nl));
+            LUF_T_PHASE(ph_grow_filter<TF>(g, s, flags, lane, nl));
+            LUF_T_PHASE(active |= ph_grow_exec<TF>(g, s, flags, lane, nl));
         }
         if (!LUF_T_ANY(active)) break;
         ++rounds;

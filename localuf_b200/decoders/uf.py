@@ -61,3 +61,17 @@ class UF(BaseUF):
         eng = self.engine
         return self._sharded_counts(
             lambda s, lo, cnt: eng.mc_run_host(self._DECODER_ID, self._flags, noise_level, s, lo, cnt), n, seed)
+
+
+class NodeUF(UF):
+    """``localuf/decoders/node_uf.py:5-94``: the original Union-Find growth -- every frontier
+    node of an active cluster grows each of its active edges, so an edge inside one cluster
+    grows from both ends (the growth rule Macar, Actis and Snowflake use too).  Same kernels as
+    :class:`UF` with the ``LUF_UF_NODE`` flag."""
+
+    def __init__(self, code, dynamic: bool = False, inclination: str = 'default'):
+        super().__init__(code, dynamic=dynamic, inclination=inclination)
+        self._flags |= _engine.UF_NODE
+
+    def __repr__(self):
+        return f'NodeUF(code={self.CODE}, syndrome={self.syndrome})'

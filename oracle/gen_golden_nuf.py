@@ -1,0 +1,71 @@
+"""Golden vectors for NodeUF (frontier-node growth, localuf/decoders/node_uf.py),
+exported from the reference.  TEST INFRASTRUCTURE ONLY; imported by
+oracle/gen_golden.py.  Same layout as the ``uf_*`` cases; growth of the
+canonical execution is asserted equal to the unmodified ``NodeUF`` on every shot."""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+
+import ref_shim
+
+localuf = ref_shim.load()
+from localuf.constants import Growth  # noqa: E402
+from localuf.decoders import NodeUF  # noqa: E402
+from ref_canonical import CanonicalNodeUF  # noqa: E402
+
+NUF_CASES = [
+    ('nuf_sf7_cc_p12', dict(code='Surface', d=7, noise='code capacity'), 0.12, 300, 31),
+    ('nuf_sf9_cc_p08', dict(code='Surface', d=9, noise='code capacity'), 0.08, 300, 32),
+    ('nuf_sf5_phen_p05', dict(code='Surface', d=5, noise='phenomenological'), 0.05, 200, 33),
+    ('nuf_sf11_phen_p015', dict(code='Surface', d=11, noise='phenomenological'), 0.015, 50, 34),
+    ('nuf_sf5_cl_p02', dict(code='Surface', d=5, noise='circuit-level'), 0.02, 150, 35),
+    ('nuf_rep7_phen_p06', dict(code='Repetition', d=7, noise='phenomenological'), 0.06, 200, 36),
+    ('nuf_sf4_cl_fwd_p03', dict(code='Surface', d=4, noise='circuit-level', kwargs=dict(scheme='forward')), 0.03, 150, 37),
+]
+
+
+def nuf_case(name, spec, p, shots, seed):
+    import gen_golden as G
+    code = G.make_code(spec)
+    ids, eidx, N, B, eu, ev = G.flatten(code)
+    E, D = len(code.EDGES), N - B
+    variants = {'default': CanonicalNodeUF(code), 'west': CanonicalNodeUF(code, inclination='west'),
+                'dynamic': CanonicalNodeUF(code, dynamic=True)}
+    plain = NodeUF(code)
+    is_batch = str(code.SCHEME) == 'batch'
+    err_bits = np.zeros((shots, G.words(E)), np.uint32)
+    syn_bits = np.zeros((shots, G.words(D)), np.uint32)
+    out = {k: dict(growth=np.zeros((shots, E), np.uint8), corr=np.zeros((shots, G.words(E)), np.uint32),
+                   logical=np.zeros(shots, np.uint8), rounds=np.zeros(shots, np.int32)) for k in variants}
+    random.seed(seed)
+    for s in range(shots):
+        error = code.make_error(p) if is_batch else {e for e in code.EDGES if random.random() < p}
+        syndrome = code.get_syndrome(error)
+        err_bits[s] = G.pack((eidx[e] for e in error), E)
+        syn_bits[s] = G.pack((ids[v] - B for v in syndrome), D)
+        for k, dec in variants.items():
+            dec.reset()
+            dec.decode(set(syndrome))
+            o = out[k]
+            o['growth'][s] = np.array([3 if dec.growth[e] is Growth.BURNT else int(dec.growth[e]) for e in code.EDGES], np.uint8)
+            o['corr'][s] = G.pack((eidx[e] for e in dec.correction), E)
+            o['rounds'][s] = dec.round_count
+            assert code.get_syndrome(dec.correction) == syndrome
+            if is_batch:
+                o['logical'][s] = code.get_logical_error(error ^ dec.correction)
+        plain.reset(); plain.decode(set(syndrome))
+        assert all(plain.growth[e] == variants['default'].growth[e] for e in code.EDGES)
+        assert code.get_syndrome(plain.correction) == syndrome
+    arrays = dict(err_bits=err_bits, syn_bits=syn_bits)
+    for k, o in out.items():
+        for f, a in o.items():
+            arrays[f'{k}_{f}'] = a
+    meta = dict(kind='node uf', spec=spec, p=p, shots=shots, seed=seed, N=N, B=B, E=E,
+                source='reference NodeUF via oracle/ref_canonical.CanonicalNodeUF; growth asserted equal to unmodified NodeUF')
+    return meta, arrays
+
+
+def jobs():
+    return {case[0]: (lambda c=case: nuf_case(*c)) for case in NUF_CASES}

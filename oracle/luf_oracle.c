@@ -130,7 +130,7 @@ static int uf_decode_ws(const oracle_graph *g, uf_ws *w, int flags, const uint32
                         uint32_t *corr_bits, uint8_t *growth_out)
 {
     const int N = g->n_nodes, B = g->n_boundary, E = g->n_edges;
-    const int dynamic = flags & ORACLE_UF_DYNAMIC, west = flags & ORACLE_UF_WEST;
+    const int dynamic = flags & ORACLE_UF_DYNAMIC, west = flags & ORACLE_UF_WEST, node = flags & ORACLE_UF_NODE;
     int n_active = 0, rounds = 0;
 
     /* uf.py:79-96 reset + :496-519 one singleton cluster per node */
@@ -160,7 +160,9 @@ static int uf_decode_ws(const oracle_graph *g, uf_ws *w, int flags, const uint32
                 for (int k = g->inc_off[u]; k < g->inc_off[u + 1]; ++k) {
                     const int e = g->inc_edge[k];
                     if (w->growth[e] >= FULL) continue;                 /* not in any vision */
-                    if (w->seen_round[e] == rounds && w->seen_root[e] == r) continue; /* a set holds e once */
+                    /* UF: a vision (a set) holds e once.  NodeUF (node_uf.py:45-67): every frontier node
+                     * grows its own active edges, so an edge inside the cluster gets one increment per end. */
+                    if (!node && w->seen_round[e] == rounds && w->seen_root[e] == r) continue;
                     w->seen_round[e] = rounds; w->seen_root[e] = r;
                     if (++w->growth[e] == FULL) w->merge_ls[n_merge++] = e;
                 }

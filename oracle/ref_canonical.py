@@ -78,3 +78,36 @@ class CanonicalUF(_RefUF):
                     stack.append(v)
                     tree.append((e, v))
         return tree
+
+
+from localuf.decoders.node_uf import NodeUF as _RefNodeUF  # noqa: E402
+
+
+class CanonicalNodeUF(_RefNodeUF):
+    """The same pinning for ``NodeUF`` (``localuf/decoders/node_uf.py``): every frontier node of
+    an active cluster grows its own active edges (``:45-67``), the round's merge list is
+    processed in ascending edge id, the peeling tree is traversed in ascending edge id."""
+
+    def __init__(self, code, dynamic=False, inclination='default'):
+        self._EDGE_ID = {e: k for k, e in enumerate(code.EDGES)}
+        self.round_count = 0
+        super().__init__(code, dynamic=dynamic, inclination=inclination)
+
+    def reset(self, no_boundaries=False):
+        super().reset()
+        self.round_count = 0
+
+    def _growth_round(self, log_history, clusters_to_grow=None):
+        if clusters_to_grow is None:
+            clusters_to_grow = self.active_clusters
+        self.round_count += 1
+        merge_ls, changed = [], set()
+        for cluster in clusters_to_grow:
+            self._grow(cluster, merge_ls, changed)          # node_uf.py:45-67, unchanged
+        merge_ls.sort(key=self._EDGE_ID.__getitem__)
+        for (u, v) in merge_ls:
+            cu = self.clusters[self._find(u)]
+            cv = self.clusters[self._find(v)]
+            self._FORESTER.merge(cu, cv, (u, v))
+
+    _make_tree = CanonicalUF._make_tree
