@@ -26,6 +26,10 @@ enum { AS_BUSY_SIG = 16, AS_ACTIVE_SIG = 32, AS_OWN_NAS = 64 };
 static const uint32_t PTR_C = 0xFFu;
 static const uint32_t NBR_NONE = 0xFFFFFFFFu;
 enum { FLAG_ACTIS_UNOPTIMAL = 4 };
+#ifndef LUF_CA_TLIST_CAP
+  #define LUF_CA_TLIST_CAP 256
+#endif
+static const uint32_t CA_TLIST_CAP = LUF_CA_TLIST_CAP;    // tests shrink it to force the bitmap path
 
 struct CaView {
     int N, B, E, K;             // K directions; slots >= K/2 are the edges a node owns (it is their first endpoint)
@@ -45,7 +49,8 @@ struct CaLayout {
     uint32_t rx_busy, rx_active;    // u32[2*WN] Actis signals received, double-buffered by timestep parity
     uint32_t defect, err, corr; // u32[WD] / u32[WE] / u32[WE]
     uint32_t touched;           // u32[WN]  Macar: nodes that are a defect or touch a fully grown edge (the only ones that can act)
-    uint32_t glob;              // u32[4]  Actis collection-level next_busy_signal / next_active_signal
+    uint32_t glob;              // u32[4]  Actis collection-level next_busy_signal / next_active_signal; Macar: [2] = fill of tlist
+    uint32_t tlist;             // u16[CA_TLIST_CAP]  Macar: the touched nodes, compacted (rebuilt after every growth step)
     uint32_t bytes;
 };
 
@@ -53,6 +58,7 @@ struct CaShot {
     uint16_t *cid, *ncid;
     uint8_t *ptr, *fl, *ast, *cnt;
     uint32_t *growth, *gacc, *rx_anyon, *rx_defect, *rx_busy, *rx_active, *defect, *err, *corr, *glob, *touched;
+    uint16_t* tlist;
 };
 
 LUF_DEV CaShot ca_bind(const CaLayout& l, unsigned char* b)
@@ -68,6 +74,7 @@ LUF_DEV CaShot ca_bind(const CaLayout& l, unsigned char* b)
     s.corr = (uint32_t*)(b + l.corr);
     s.glob = (uint32_t*)(b + l.glob);
     s.touched = (uint32_t*)(b + l.touched);
+    s.tlist = (uint16_t*)(b + l.tlist);
     return s;
 }
 
@@ -142,15 +149,38 @@ template <bool SPARSE, class F>
 LUF_DEV void ca_for_nodes(const CaView& g, const CaShot& s, int lane, int nl, F&& f)
 {
     if (SPARSE) {
-        for (int w = lane; w < g.WN; w += nl) {
-            uint32_t bits = s.touched[w];
-            while (bits) {
-                const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-                f(32 * w + b);
+        const uint32_t total = s.glob[2];
+        if (total <= CA_TLIST_CAP) {                // balanced: one touched node per lane and trip
+            for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) f((int)s.tlist[i]);
+        } else
+            for (int w = lane; w < g.WN; w += nl) {
+                uint32_t bits = s.touched[w];
+                while (bits) {
+                    const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+                    f(32 * w + b);
+                }
             }
-        }
     } else
         for (int v = lane; v < g.N; v += nl) f(v);
+}
+
+// Compact the touched bitmap into tlist (glob[2] = number of touched nodes; 0 on entry).
+LUF_DEV void ca_gather_touched(const CaView& g, const CaShot& s, int lane, int nl)
+{
+    const int wpl = (g.WN + nl - 1) / nl;
+    const int w0 = lane * wpl, w1 = w0 + wpl < g.WN ? w0 + wpl : g.WN;
+    uint32_t c = 0;
+    for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(s.touched[w]);
+    if (!c) return;
+    uint32_t pos = luf_atomic_add(&s.glob[2], c);
+    if (pos + c > CA_TLIST_CAP) return;
+    for (int w = w0; w < w1; ++w) {
+        uint32_t bits = s.touched[w];
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            s.tlist[pos++] = (uint16_t)(32 * w + b);
+        }
+    }
 }
 
 // _Node.merging, luf/main.py:839-854.  Returns busy.
@@ -407,12 +437,14 @@ LUF_DEV uint32_t ca_decode(const CaView& g, const CaShot& s, int flags, int* t_s
     int tsv = 0, tbp = 0, exported = 0;
     uint32_t parity = 0;
     (void)lane;
+    if (!ACTIS) { LUF_PHASE(ca_gather_touched(g, s, lane, nl)); }     // glob[2] == 0 after ca_reset
     while (c.stage != ST_DONE) {
         if (c.stage == ST_BURNING && !exported) {
             exported = 1;
             if (growth_out) { LUF_PHASE(for (int w = lane; w < g.GW; w += nl) growth_out[w] = s.growth[w]); }
         }
         const int in_sv = c.stage < ST_BURNING;
+        const int grew = !ACTIS && c.stage == ST_GROWING;                // this step may touch new nodes
         int busy, valid;
         if (ACTIS) {
             LUF_PHASE(actis_phase_a(g, s, c, lane, nl));
@@ -431,6 +463,10 @@ LUF_DEV uint32_t ca_decode(const CaView& g, const CaShot& s, int flags, int* t_s
             busy = LUF_ANY(acc & 1u); valid = !LUF_ANY(acc & 2u);
         }
         if (ca_controller_advance(c, busy, valid)) { LUF_PHASE(ca_snapshot_access(g, s, lane, nl)); }
+        if (grew) {                                                      // newly touched nodes join the list
+            LUF_PHASE(if (lane == 0) s.glob[2] = 0);
+            LUF_PHASE(ca_gather_touched(g, s, lane, nl));
+        }
         c.step += 1;
         if (in_sv) ++tsv; else ++tbp;
         if (tsv + tbp >= CA_MAX_STEPS) { tsv = -1; tbp = -1; break; }

@@ -175,6 +175,7 @@ inline CaLayout make_ca_layout(int N, int B, int E, bool actis, bool keep_err)
     l.corr = take(4u * WE);
     l.glob = take(16);
     l.touched = take(4u * WN);
+    l.tlist = take(2u * CA_TLIST_CAP);
     l.err = keep_err ? take(4u * WE) : 0;
     l.bytes = off;
     return l;

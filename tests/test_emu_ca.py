@@ -27,3 +27,17 @@ def test_emu_ca_matches_reference(name):
         np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{key}_growth'],
                                       err_msg=f'{name} {key} erasure after validate')
         np.testing.assert_array_equal(corr, arr[f'{key}_corr'], err_msg=f'{name} {key} correction')
+
+
+def test_emu_macar_bitmap_path_with_tiny_node_list():
+    """A build whose touched-node list holds 4 entries: Macar sweeps the bitmap instead."""
+    emu_binding.use_tiny_lists(True)
+    try:
+        for name in ('ca_sf5_cc_p08', 'ca_sf5_phen_p03', 'ca_sf5_cl_p01'):
+            meta, arr = load_golden(name)
+            emu = emu_binding.Emu(make_code(meta['spec']))
+            corr, growth2b, steps = emu.decode_ca(1, 0, arr['syn_bits'])
+            np.testing.assert_array_equal(steps, arr['macar_steps'])
+            np.testing.assert_array_equal(corr, arr['macar_corr'])
+    finally:
+        emu_binding.use_tiny_lists(False)

@@ -43,14 +43,19 @@ def main():
     tmp = '/tmp/_ncu_src.csv'
     open(tmp, 'w').write(src)
     # per-function aggregation
-    core = open(os.path.join(os.path.dirname(os.path.abspath(so)), 'luf_core.cuh')).read().splitlines()
-    funcs = [(i, m.group(1)) for i, l in enumerate(core, 1) for m in [re.match(r'LUF_DEV\s+\S+\s+(\w+)\(', l)] if m]
+    csrc = os.path.dirname(os.path.abspath(so))
+    funcs = {}
+    for f in os.listdir(csrc):
+        if f.endswith(('.cuh', '.inl', '.cu')):
+            lines = open(os.path.join(csrc, f)).read().splitlines()
+            funcs[f] = [(i, m.group(1)) for i, l in enumerate(lines, 1)
+                        for m in [re.match(r'(?:LUF_DEV|LUF_MEM|__global__)\s+(?:\S+\s+)+?(\w+)\(', l)] if m]
 
     def fn(f, line):
-        if f != 'luf_core.cuh':
+        if f not in funcs:
             return f
-        name = '?'
-        for i, n in funcs:
+        name = f
+        for i, n in funcs[f]:
             if i <= line:
                 name = n
         return name
