@@ -293,6 +293,7 @@ inline SfLayout make_sf_layout(const PackedWindow& p)
     l.corr = take(4u * p.h * ELw); l.err = take(4u * p.h * ELw);
     l.top = take(4u * WLn); l.fb = take(4u * WLn);
     l.partner = take(2u * 2u * p.NL);
+    l.alist = take(2u * SF_ALIST_CAP); l.acnt = take(16);
     l.bytes = off;
     return l;
 }

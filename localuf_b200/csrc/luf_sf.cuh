@@ -43,6 +43,11 @@ struct SfView {
     const uint32_t* class_end;  // [n_classes]
 };
 
+#ifndef LUF_SF_ALIST_CAP
+  #define LUF_SF_ALIST_CAP 384
+#endif
+static const uint32_t SF_ALIST_CAP = LUF_SF_ALIST_CAP;      // tests shrink it to force the bitmap sweep
+
 struct SfLayout {
     uint32_t cid, ncid;         // u16[N]
     uint32_t fl;                // u16[N]
@@ -53,13 +58,16 @@ struct SfLayout {
     uint32_t corr, err;         // u32[h*ELw]
     uint32_t top, fb;           // u32[WLn]  this cycle's top-sheet syndrome / defects on the future boundary
     uint32_t partner;           // i16[2*NL]
+    uint32_t alist, acnt;       // u16[SF_ALIST_CAP] the awake nodes, compacted as sheet << 10 | position (rebuilt after
+                                // every drop and grow step); u32[4] its fill
     uint32_t bytes;
 };
 
 struct SfShot {
     uint16_t *cid, *ncid, *fl;
     uint8_t* ptr;
-    uint32_t *ndef, *awake, *growth, *corr, *err, *top, *fb;
+    uint32_t *ndef, *awake, *growth, *corr, *err, *top, *fb, *acnt;
+    uint16_t* alist;
     int16_t* partner;
 };
 
@@ -69,6 +77,7 @@ LUF_DEV SfShot sf_bind(const SfLayout& l, unsigned char* b)
     s.cid = (uint16_t*)(b + l.cid); s.ncid = (uint16_t*)(b + l.ncid); s.fl = (uint16_t*)(b + l.fl);
     s.ptr = b + l.ptr;
     s.ndef = (uint32_t*)(b + l.ndef); s.awake = (uint32_t*)(b + l.awake); s.growth = (uint32_t*)(b + l.growth);
+    s.alist = (uint16_t*)(b + l.alist); s.acnt = (uint32_t*)(b + l.acnt);
     s.corr = (uint32_t*)(b + l.corr); s.err = (uint32_t*)(b + l.err);
     s.top = (uint32_t*)(b + l.top); s.fb = (uint32_t*)(b + l.fb);
     s.partner = (int16_t*)(b + l.partner);
@@ -313,6 +322,14 @@ LUF_DEV void sf_drop(const SfView& g, const SfShot& s, int lane, int nl)
 template <class F>
 LUF_DEV void sf_for_awake(const SfView& g, const SfShot& s, int lane, int nl, F&& f)
 {
+    const uint32_t total = s.acnt[0];
+    if (total <= SF_ALIST_CAP) {                    // balanced: one awake node per lane and trip
+        for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) {
+            const int it = (int)s.alist[i], r = it >> 10, q = it & 1023;
+            f(r, q, r * g.NL + q);
+        }
+        return;
+    }
     const int words = g.h * g.WLn;
     for (int x = lane; x < words; x += nl) {
         uint32_t bits = s.awake[x];
@@ -325,6 +342,31 @@ LUF_DEV void sf_for_awake(const SfView& g, const SfShot& s, int lane, int nl, F&
         }
     }
 }
+
+// Compact the awake bitmap into alist (acnt[0] = number of awake nodes; must be 0 on entry).
+// Windows taller than 63 sheets keep the bitmap sweep (acnt[0] is then left above the capacity).
+LUF_DEV void sf_gather_awake(const SfView& g, const SfShot& s, int lane, int nl)
+{
+    if (g.h > 63) { if (lane == 0) s.acnt[0] = SF_ALIST_CAP + 1u; return; }
+    const int words = g.h * g.WLn;
+    const int wpl = (words + nl - 1) / nl;
+    const int w0 = lane * wpl, w1 = w0 + wpl < words ? w0 + wpl : words;
+    uint32_t c = 0;
+    for (int x = w0; x < w1; ++x) c += (uint32_t)luf_popc(s.awake[x]);
+    if (!c) return;
+    uint32_t pos = luf_atomic_add(&s.acnt[0], c);
+    if (pos + c > SF_ALIST_CAP) return;
+    for (int x = w0; x < w1; ++x) {
+        uint32_t bits = s.awake[x];
+        if (!bits) continue;
+        const int r = x / g.WLn, w = x - r * g.WLn;
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            s.alist[pos++] = (uint16_t)((r << 10) | (32 * w + b));
+        }
+    }
+}
+#define LUF_SF_REGATHER() { LUF_PHASE(if (lane == 0) s.acnt[0] = 0); LUF_PHASE(sf_gather_awake(g, s, lane, nl)); }
 
 // _Node._grow, snowflake/main.py:1075-1084
 LUF_DEV void sf_grow_node(const SfView& g, const SfShot& s, int r, int q)
@@ -473,13 +515,17 @@ LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t
     LUF_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.corr + (g.h - 1) * g.ELw, m);
               if (floor_out) for (int c = lane; c < g.ELw; c += nl) floor_out[c] = s.corr[(g.h - 1) * g.ELw + c]);
     LUF_PHASE(sf_drop(g, s, lane, nl));
+    LUF_SF_REGATHER();                               // the window moved
     if (one_one) {
         LUF_PHASE(sf_grow(g, s, 0, lane, nl));
+        LUF_SF_REGATHER();                           // growth wakes nodes
         sf_merge(g, s, true, slow, rt_all, rt_unr, lane, nl);
     } else {
         LUF_PHASE(sf_grow(g, s, 1, lane, nl));
+        LUF_SF_REGATHER();
         sf_merge(g, s, true, slow, rt_all, rt_unr, lane, nl);
         LUF_PHASE(sf_grow(g, s, 2, lane, nl));
+        LUF_SF_REGATHER();
         sf_merge(g, s, false, slow, rt_all, rt_unr, lane, nl);
     }
     LUF_PHASE(if (lane == 0) sf_pairs_lower(g, s));

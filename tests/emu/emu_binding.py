@@ -22,7 +22,7 @@ def build(tiny_lists=False):
     if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in SRCS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(['g++', '-O1', '-g', '-fPIC', '-shared', '-std=c++17', '-Wall', '-Wextra']
-                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2', '-DLUF_CTA_LIST_CAP=5', '-DLUF_CTA_LIST2_CAP=3', '-DLUF_CA_TLIST_CAP=4'] if tiny_lists else []) + ['-o', out, SRCS[0]],
+                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2', '-DLUF_CTA_LIST_CAP=5', '-DLUF_CTA_LIST2_CAP=3', '-DLUF_CA_TLIST_CAP=4', '-DLUF_SF_ALIST_CAP=4'] if tiny_lists else []) + ['-o', out, SRCS[0]],
                        check=True, capture_output=True)
     return out
 

@@ -43,3 +43,20 @@ def test_emu_sf_mc_runs_and_is_quiet_without_noise():
     assert (steps[:, :, 0] == 4 * d).all()
     counts, _ = emu.mc(0, 0.02, 5, 0, 40, n)
     assert counts[1] == 40 * total and counts[2] > 40 * n * d * 4
+
+
+def test_emu_sf_bitmap_sweep_with_tiny_awake_list():
+    """A build whose awake-node list holds 4 entries: the sweeps fall back to the bitmap."""
+    emu_binding.use_tiny_lists(True)
+    try:
+        for name in ('sf_sf5_cl', 'sf_sf5_phen', 'sf_rep5_phen'):
+            meta, arr = load_golden(name)
+            emu = emu_binding.EmuStream(make_code(meta['spec']))
+            t = emu.tables
+            fresh = binding.code_bits_to_local(t, arr['fresh_bits'], 0)
+            rt, floor, m = emu.stream(flags_of(meta['decoder_kwargs']), fresh)
+            np.testing.assert_array_equal(rt[:, 0], arr['runtime_all'])
+            np.testing.assert_array_equal(floor, binding.code_bits_to_local(t, arr['floor_bits'], t.h - 1))
+            np.testing.assert_array_equal(m, arr['m_cycle'])
+    finally:
+        emu_binding.use_tiny_lists(False)
