@@ -265,7 +265,9 @@ METRIC = {'shots/s': 'decoded shots/s', 'decoding cycles/s': 'decoding cycles/s'
 DEFAULT_UNITS = {'cfg1': 1 << 26, 'cfg2': 1 << 24, 'cfg3': 1 << 22, 'cfg3-macar': 1 << 19, 'cfg3-actis': 1 << 14,
                  'cfg4': 1 << 16}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full; profiles/)
-TRAFFIC = {'cfg3': (104960, 'profiles/r01_v7_k_mc_uf_summary.txt')}
+TRAFFIC = {'cfg3': (112640, 'profiles/r01_v10_k_mc_uf_summary.txt'),
+           'cfg3-macar': (89856, 'profiles/r01_k_mc_ca_macar_summary.txt'),
+           'cfg4': (112128, 'profiles/r01_k_sf_mc_summary.txt')}
 
 
 def run_ours(args):
