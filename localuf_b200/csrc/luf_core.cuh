@@ -134,7 +134,7 @@ struct GraphView {
     const int16_t* node_long;   // [N]   coordinate along the long axis
     // sampler tables: fresh edges sorted by probability class
     int F, n_classes;
-    const uint16_t* fresh_perm; // [F]
+    const uint16_t* fresh_perm; // [F]; null when it is the identity (one class, every edge fresh)
     const uint32_t* class_end;  // [n_classes] exclusive end position of each class in fresh_perm
 };
 
@@ -275,7 +275,7 @@ LUF_DEV uint32_t ph_sample_tab(const GraphView& g, const SampleTab& t, const Sho
                 if (gap >= hi - pos) break;
                 pos += gap;
             }
-            const uint32_t e = LUF_LDG(&t.perm[pos]);
+            const uint32_t e = t.perm ? (uint32_t)LUF_LDG(&t.perm[pos]) : pos;   // no table when the order is the identity
             if (!skip_mask || !((LUF_LDG(&skip_mask[e >> 5]) >> (e & 31u)) & 1u)) parity ^= flip_edge(g, s, e);
             if (++pos >= hi) break;
         }
@@ -310,8 +310,8 @@ LUF_DEV void ph_force(const GraphView& g, const Shot& s, const SampleParams& sp,
     if (weight > F) weight = F;
     for (uint32_t j = F - weight; j < F; ++j) {
         const uint32_t t = luf_mulhi(philox_next(rng), j + 1u);
-        const uint32_t et = LUF_LDG(&g.fresh_perm[t]);
-        const uint32_t e = ((s.err[et >> 5] >> (et & 31u)) & 1u) ? (uint32_t)LUF_LDG(&g.fresh_perm[j]) : et;
+        const uint32_t et = g.fresh_perm ? (uint32_t)LUF_LDG(&g.fresh_perm[t]) : t;
+        const uint32_t e = !((s.err[et >> 5] >> (et & 31u)) & 1u) ? et : g.fresh_perm ? (uint32_t)LUF_LDG(&g.fresh_perm[j]) : j;
         flip_edge(g, s, e);
     }
 }

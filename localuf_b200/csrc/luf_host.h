@@ -25,6 +25,7 @@ struct luf_graph_desc_dims { int N, B, E, n_classes; };
 struct PackedGraph {
     int N = 0, B = 0, E = 0, F = 0, n_classes = 0;
     int DEG = 0;
+    bool perm_identity = false;
     std::vector<uint32_t> adj, edge_uv, west_mask, class_end;
     std::vector<int16_t> node_long;
     std::vector<uint16_t> fresh_perm;
@@ -77,6 +78,8 @@ inline std::string pack_graph(const luf_graph_desc& d, PackedGraph& out)
         out.class_end[c] = (uint32_t)out.fresh_perm.size();
     }
     out.F = (int)out.fresh_perm.size();
+    out.perm_identity = out.F == E;
+    for (int k = 0; k < out.F && out.perm_identity; ++k) out.perm_identity = out.fresh_perm[k] == k;
     return "";
 }
 

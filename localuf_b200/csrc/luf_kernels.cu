@@ -755,7 +755,8 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     int rc = 0;
     if ((rc = upload(g, p.adj, &v.adj)) ||
         (rc = upload(g, p.edge_uv, &v.edge_uv)) || (rc = upload(g, p.west_mask, &v.west_mask)) ||
-        (rc = upload(g, p.node_long, &v.node_long)) || (rc = upload(g, p.fresh_perm, &v.fresh_perm)) ||
+        (rc = upload(g, p.node_long, &v.node_long)) ||
+        (!p.perm_identity && (rc = upload(g, p.fresh_perm, &v.fresh_perm))) ||
         (rc = upload(g, p.class_end, &v.class_end))) {
         luf_graph_destroy(g);
         return rc;

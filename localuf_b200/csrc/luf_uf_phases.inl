@@ -96,7 +96,8 @@ LUF_DEV void for_items(W word, int nwords, uint32_t id0, const uint32_t* list, u
     } else for_bits(word, nwords, id0, lane, nl, f);
 }
 
-// Row v of the adjacency table, read as 64-bit pairs; f(entry) for every real entry.
+// Row v of the adjacency table, read as 64-bit pairs; f(entry) for every real entry
+// (entry = edge | other end << 16 | this is the edge's first endpoint << 31).
 template <class F>
 LUF_DEV void for_row(const GraphView& g, uint32_t v, F f)
 {
@@ -107,6 +108,12 @@ LUF_DEV void for_row(const GraphView& g, uint32_t v, F f)
         f(p.x);
         if (p.y != ADJ_PAD) f(p.y);
     }
+}
+
+LUF_DEV uint32_t other_end(uint32_t ent, bool& first)
+{
+    first = (ent >> 31) != 0;
+    return (ent >> 16) & 0x7FFFu;
 }
 
 // ------------------------------------------------------------ phase 0: reset
@@ -189,7 +196,7 @@ LUF_DEV void grow_first(const GraphView& g, const Shot& s, uint32_t v)
     for_row(g, v, [&](uint32_t ent) {
         const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
         const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-        if (old == G_HALF) became_full(s, e, v, (ent >> 16) & 0x7FFFu);
+        if (old == G_HALF) { bool first; became_full(s, e, v, other_end(ent, first)); }
     });
 }
 
@@ -209,8 +216,9 @@ LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r
     for_row(g, u, [&](uint32_t ent) {
         const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
         if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
-        const uint32_t o = (ent >> 16) & 0x7FFFu;
-        if (!node && !(ent >> 31)) {                  // second endpoint: skip if same cluster
+        bool first;
+        const uint32_t o = other_end(ent, first);
+        if (!node && !first) {                        // second endpoint: skip if same cluster
             uint32_t wr;
             if (o == r || find_ro(s, o, wr) == r) return;
         }
@@ -470,7 +478,8 @@ LUF_DEV void build_tree(const GraphView& g, const Shot& s, uint32_t root)
         for_row(g, u, [&](uint32_t ent) {
             const uint32_t e = ent & 0xFFFFu;
             if (growth_of(s, e) != G_FULL) return;
-            const uint32_t o = (ent >> 16) & 0x7FFFu;
+            bool first;
+            const uint32_t o = other_end(ent, first);
             const uint32_t bit = 1u << (o & 31u);
             if (visited[o >> 5] & bit) return;
             luf_atomic_or(&visited[o >> 5], bit);

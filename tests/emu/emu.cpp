@@ -22,7 +22,7 @@ static GraphView view_of(const PackedGraph& p)
     g.DEG = p.DEG; g.adj = p.adj.data(); g.edge_uv = p.edge_uv.data();
     g.west_mask = p.west_mask.data(); g.node_long = p.node_long.data();
     g.F = p.F; g.n_classes = p.n_classes;
-    g.fresh_perm = p.fresh_perm.data(); g.class_end = p.class_end.data();
+    g.fresh_perm = p.perm_identity ? nullptr : p.fresh_perm.data(); g.class_end = p.class_end.data();
     return g;
 }
 
