@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('LUF_B200_LIB') or os.path.join(HERE, 'csrc', 'libluf_b200.so')
 
 DEC_UF, DEC_MACAR, DEC_ACTIS, DEC_SNOWFLAKE = 0, 1, 2, 3
-UF_DYNAMIC, UF_WEST, UF_NODE, ACTIS_UNOPTIMAL = 1, 2, 4, 4
+UF_DYNAMIC, UF_WEST, UF_NODE, UF_BUCKET, ACTIS_UNOPTIMAL = 1, 2, 4, 8, 4
 NOISE_KIND = {'code capacity': 0, 'phenomenological': 1, 'circuit-level': 2}
 
 

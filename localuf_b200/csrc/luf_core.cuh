@@ -121,7 +121,7 @@ static const uint32_t LIST2_CAP = LUF_LIST2_CAP;   // active nodes of a round / 
 static const uint32_t LIST_DONE = 0xFFFFFFFFu;
 
 enum { G_UNGROWN = 0, G_HALF = 1, G_FULL = 2, G_BURNT = 3 };
-enum { FLAG_DYNAMIC = 1, FLAG_WEST = 2, FLAG_NODE = 4 };
+enum { FLAG_DYNAMIC = 1, FLAG_WEST = 2, FLAG_NODE = 4, FLAG_BUCKET = 8 };
 
 // Read-only graph tables (global memory, read through L1).
 struct GraphView {

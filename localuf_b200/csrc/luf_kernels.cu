@@ -52,7 +52,7 @@ __device__ __forceinline__ unsigned char* warp_slice(const Layout& l)
 
 // Fused K1 + K2 + K4 for the UF decoder, batch scheme (_schemes.py:116-155).
 template <int TF>
-__global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleParams sp,
+__global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
                         unsigned long long shot0, long long nshots, unsigned long long* counts)
 {
     const int lane = threadIdx.x & 31, nl = WARP;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleP
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
         LUF_PHASE(ph_load(g, s, lane, nl));
-        uf_validate_t<TF>(g, s, TF, lane, nl);
+        uf_validate_t<TF>(g, s, flags, lane, nl);          // TF >= 0: the flags are compile-time constants
         parity ^= uf_peel(g, s, lane, nl);
         fails += LUF_XOR(parity) & 1u;
     }
@@ -102,7 +102,7 @@ __global__ void k_decode_uf(GraphView g, Layout l, int flags, long long nshots,
 // measurement rounds).  The first warp samples, so that a shot's noise does not
 // depend on the tile shape; every other phase runs on all threads of the block.
 template <int TF>
-__global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, SampleParams sp,
+__global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, SampleParams sp, int flags,
                         unsigned long long shot0, long long nshots, unsigned long long* counts)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, Sam
         __syncthreads();
         uf_cta::ph_load(g, s, lane, nl);
         __syncthreads();
-        uf_cta::uf_validate_t<TF>(g, s, TF, lane, nl);
+        uf_cta::uf_validate_t<TF>(g, s, flags, lane, nl);
         parity ^= uf_cta::uf_peel(g, s, lane, nl);
         fails += (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
     }
@@ -816,7 +816,9 @@ int64_t luf_launch_count(const luf_graph* g) { return g ? g->launches : 0; }
 static int check_decoder(const luf_graph* g, int decoder, int flags)
 {
     if (decoder == LUF_DEC_UF) {
-        if (flags & ~(LUF_UF_DYNAMIC | LUF_UF_WEST | LUF_UF_NODE)) return fail(LUF_ERR_INVALID, "unknown UF flag");
+        if (flags & ~(LUF_UF_DYNAMIC | LUF_UF_WEST | LUF_UF_NODE | LUF_UF_BUCKET)) return fail(LUF_ERR_INVALID, "unknown UF flag");
+        if ((flags & LUF_UF_BUCKET) && !(flags & LUF_UF_NODE))
+            return fail(LUF_ERR_UNSUPPORTED, "bucket growth is built for NodeBUF (LUF_UF_NODE | LUF_UF_BUCKET) only");
         return 0;
     }
     if (decoder == LUF_DEC_MACAR || decoder == LUF_DEC_ACTIS) {
@@ -941,11 +943,12 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
     } else {
         // the decoder flags are compile-time constants of the fused kernel
 #define LUF_MC_UF(TF) { if (int rc = plan_launch(g, k_mc_uf<TF>, g->lay_fused.bytes, nshots, &c, 14)) return rc; \
-        k_mc_uf<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, shot0, nshots, counts_dev); }
+        k_mc_uf<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, shot0, nshots, counts_dev); }
 #define LUF_MC_UF_CTA(TF) { if (int rc = plan_cta_launch(g, k_mc_uf_cta<TF>, g->lay_fused_cta.bytes, nshots, &c)) return rc; \
-        k_mc_uf_cta<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused_cta, sp, shot0, nshots, counts_dev); }
+        k_mc_uf_cta<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused_cta, sp, flags, shot0, nshots, counts_dev); }
         const bool cta = use_cta_tiles(g, g->lay_fused.bytes, g->lay_fused_cta.bytes);
-        switch (flags & 7) {
+        // the common flag sets are compile-time constants of the fused kernel; the rest run the generic instance
+        switch (flags <= 7 ? flags : -1) {
             case 0: if (cta) LUF_MC_UF_CTA(0) else LUF_MC_UF(0) break;
             case 1: if (cta) LUF_MC_UF_CTA(1) else LUF_MC_UF(1) break;
             case 2: if (cta) LUF_MC_UF_CTA(2) else LUF_MC_UF(2) break;
@@ -953,7 +956,8 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
             case 4: if (cta) LUF_MC_UF_CTA(4) else LUF_MC_UF(4) break;
             case 5: if (cta) LUF_MC_UF_CTA(5) else LUF_MC_UF(5) break;
             case 6: if (cta) LUF_MC_UF_CTA(6) else LUF_MC_UF(6) break;
-            default: if (cta) LUF_MC_UF_CTA(7) else LUF_MC_UF(7) break;
+            case 7: if (cta) LUF_MC_UF_CTA(7) else LUF_MC_UF(7) break;
+            default: if (cta) LUF_MC_UF_CTA(-1) else LUF_MC_UF(-1) break;
         }
 #undef LUF_MC_UF
 #undef LUF_MC_UF_CTA

@@ -232,21 +232,25 @@ LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r
 LUF_DEV void ph_grow_gather(const GraphView& g, const Shot& s, int lane, int nl)
 {
     gather_bits([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, &s.cnt[0], lane, nl);
-    if (lane == 0) { s.cnt[2] = 0; s.cnt[3] = 0; }
+    if (lane == 0) { s.cnt[2] = 0; s.cnt[3] = 0xFFFFFFFFu; }
 }
 
 // ... keep those whose cluster is active (cnt[1], list2), one per lane ...
+// Bucket mode (NodeBUF, node_buf.py:35-61: always the smallest active clusters first): cnt[3]
+// collects the smallest active cluster size (0xFFFFFFFF on entry); nothing grows in this phase.
 template <int TF>
 LUF_DEV void ph_grow_filter(const GraphView& g, const Shot& s, int flags, int lane, int nl)
 {
-    const bool node = ((TF >= 0 ? TF : flags) & FLAG_NODE) != 0;
+    const int f = TF >= 0 ? TF : flags;
+    const bool node = (f & FLAG_NODE) != 0, bucket = (f & FLAG_BUCKET) != 0;
     for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
         uint32_t wr;
         const uint32_t r = find_pc(s, u, wr);
         if ((wr >> 16) != (ODD_BIT >> 16)) return;
         const uint32_t idx = luf_atomic_add(&s.cnt[1], 1u);
+        if (bucket) luf_atomic_min(&s.cnt[3], wr & SIZE_MASK);
         if (idx < LUF_T_LIST2_CAP) s.list2[idx] = u | (r << 16);
-        else grow_node(g, s, u, r, node);
+        else if (!bucket) grow_node(g, s, u, r, node);
     });
 }
 
@@ -255,11 +259,22 @@ LUF_DEV void ph_grow_filter(const GraphView& g, const Shot& s, int flags, int la
 template <int TF>
 LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int flags, int lane, int nl)
 {
-    const bool node = ((TF >= 0 ? TF : flags) & FLAG_NODE) != 0;
+    const int f = TF >= 0 ? TF : flags;
+    const bool node = (f & FLAG_NODE) != 0, bucket = (f & FLAG_BUCKET) != 0;
     const uint32_t total = s.cnt[1];
+    const uint32_t smallest = s.cnt[3];
+    if (bucket && total > LUF_T_LIST2_CAP) {          // the list could not hold them: look the active nodes up again
+        for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
+            uint32_t wr;
+            const uint32_t r = find_ro(s, u, wr);
+            if ((wr >> 16) == (ODD_BIT >> 16) && (wr & SIZE_MASK) == smallest) grow_node(g, s, u, r, node);
+        });
+        return total;
+    }
     const uint32_t n = total < LUF_T_LIST2_CAP ? total : LUF_T_LIST2_CAP;
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
         const uint32_t it = s.list2[i];
+        if (bucket && (s.S[it >> 16] & SIZE_MASK) != smallest) continue;
         grow_node(g, s, it & 0xFFFFu, it >> 16, node);
     }
     return total;

@@ -75,3 +75,18 @@ class NodeUF(UF):
 
     def __repr__(self):
         return f'NodeUF(code={self.CODE}, syndrome={self.syndrome})'
+
+
+class NodeBUF(NodeUF):
+    """``localuf/decoders/node_buf.py:5-61`` (the bucket UF of Huang et al. 2020): in every
+    growth round only the active clusters of the smallest size grow.  Same kernels with
+    ``LUF_UF_NODE | LUF_UF_BUCKET``.  The reference sizes its bucket table for ``(d+1)*d`` nodes
+    and raises ``KeyError`` when a cluster outgrows it (any graph with measurement rounds, near
+    threshold); the device has no such limit."""
+
+    def __init__(self, code, dynamic: bool = False, inclination: str = 'default'):
+        super().__init__(code, dynamic=dynamic, inclination=inclination)
+        self._flags |= _engine.UF_BUCKET
+
+    def __repr__(self):
+        return f'NodeBUF(code={self.CODE}, syndrome={self.syndrome})'

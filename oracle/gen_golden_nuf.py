@@ -12,8 +12,8 @@ import ref_shim
 
 localuf = ref_shim.load()
 from localuf.constants import Growth  # noqa: E402
-from localuf.decoders import NodeUF  # noqa: E402
-from ref_canonical import CanonicalNodeUF  # noqa: E402
+from localuf.decoders import NodeUF, NodeBUF  # noqa: E402
+from ref_canonical import CanonicalNodeUF, CanonicalNodeBUF  # noqa: E402
 
 NUF_CASES = [
     ('nuf_sf7_cc_p12', dict(code='Surface', d=7, noise='code capacity'), 0.12, 300, 31),
@@ -26,14 +26,14 @@ NUF_CASES = [
 ]
 
 
-def nuf_case(name, spec, p, shots, seed):
+def nuf_case(name, spec, p, shots, seed, canonical=CanonicalNodeUF, unmodified=NodeUF):
     import gen_golden as G
     code = G.make_code(spec)
     ids, eidx, N, B, eu, ev = G.flatten(code)
     E, D = len(code.EDGES), N - B
-    variants = {'default': CanonicalNodeUF(code), 'west': CanonicalNodeUF(code, inclination='west'),
-                'dynamic': CanonicalNodeUF(code, dynamic=True)}
-    plain = NodeUF(code)
+    variants = {'default': canonical(code), 'west': canonical(code, inclination='west'),
+                'dynamic': canonical(code, dynamic=True)}
+    plain = unmodified(code)
     is_batch = str(code.SCHEME) == 'batch'
     err_bits = np.zeros((shots, G.words(E)), np.uint32)
     syn_bits = np.zeros((shots, G.words(D)), np.uint32)
@@ -62,10 +62,24 @@ def nuf_case(name, spec, p, shots, seed):
     for k, o in out.items():
         for f, a in o.items():
             arrays[f'{k}_{f}'] = a
-    meta = dict(kind='node uf', spec=spec, p=p, shots=shots, seed=seed, N=N, B=B, E=E,
-                source='reference NodeUF via oracle/ref_canonical.CanonicalNodeUF; growth asserted equal to unmodified NodeUF')
+    meta = dict(kind=unmodified.__name__, spec=spec, p=p, shots=shots, seed=seed, N=N, B=B, E=E,
+                source=f'reference {unmodified.__name__} via oracle/ref_canonical.{canonical.__name__}; '
+                       f'growth asserted equal to the unmodified decoder')
     return meta, arrays
 
 
+# NodeBUF keys its buckets by cluster size up to (d+1)*d (node_buf.py:26-28) and raises KeyError
+# beyond (already on Surface d=3 with two measurement rounds): code capacity only.
+NBUF_CASES = [
+    ('nbuf_sf7_cc_p12', dict(code='Surface', d=7, noise='code capacity'), 0.12, 300, 41),
+    ('nbuf_sf9_cc_p08', dict(code='Surface', d=9, noise='code capacity'), 0.08, 300, 42),
+    ('nbuf_sf9_cc_p15', dict(code='Surface', d=9, noise='code capacity'), 0.15, 200, 43),
+    ('nbuf_sf5_cc_p20', dict(code='Surface', d=5, noise='code capacity'), 0.20, 300, 44),
+    ('nbuf_sf3_cc_p15', dict(code='Surface', d=3, noise='code capacity'), 0.15, 300, 45),
+]
+
+
 def jobs():
-    return {case[0]: (lambda c=case: nuf_case(*c)) for case in NUF_CASES}
+    out = {case[0]: (lambda c=case: nuf_case(*c)) for case in NUF_CASES}
+    out.update({case[0]: (lambda c=case: nuf_case(*c, canonical=CanonicalNodeBUF, unmodified=NodeBUF)) for case in NBUF_CASES})
+    return out

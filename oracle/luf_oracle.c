@@ -130,7 +130,8 @@ static int uf_decode_ws(const oracle_graph *g, uf_ws *w, int flags, const uint32
                         uint32_t *corr_bits, uint8_t *growth_out)
 {
     const int N = g->n_nodes, B = g->n_boundary, E = g->n_edges;
-    const int dynamic = flags & ORACLE_UF_DYNAMIC, west = flags & ORACLE_UF_WEST, node = flags & ORACLE_UF_NODE;
+    const int dynamic = flags & ORACLE_UF_DYNAMIC, west = flags & ORACLE_UF_WEST, node = flags & ORACLE_UF_NODE,
+              bucket = flags & ORACLE_UF_BUCKET;
     int n_active = 0, rounds = 0;
 
     /* uf.py:79-96 reset + :496-519 one singleton cluster per node */
@@ -154,8 +155,15 @@ static int uf_decode_ws(const oracle_graph *g, uf_ws *w, int flags, const uint32
         /* uf.py:221-222,234-245: every active cluster adds one growth increment to
          * every edge of its vision; an edge seen by two different active clusters
          * gets two.  Saturating (Growth(3) would raise in the reference). */
+        /* NodeBUF (node_buf.py:42-47): only the active clusters of the smallest size grow this round */
+        int smallest = 0;
+        if (bucket) {
+            smallest = N + 1;
+            for (int a = 0; a < n_active; ++a) if (w->size[w->active[a]] < smallest) smallest = w->size[w->active[a]];
+        }
         for (int a = 0; a < n_active; ++a) {
             const int r = w->active[a];
+            if (bucket && w->size[r] != smallest) continue;
             for (int u = r; u != -1; u = w->next[u])
                 for (int k = g->inc_off[u]; k < g->inc_off[u + 1]; ++k) {
                     const int e = g->inc_edge[k];

@@ -43,7 +43,8 @@ typedef struct {
     int32_t noise_kind;                             /* 0 code capacity, 1 phenomenological, 2 circuit-level */
 } oracle_graph;
 
-enum { ORACLE_UF_DYNAMIC = 1, ORACLE_UF_WEST = 2, ORACLE_UF_NODE = 4 /* NodeUF, node_uf.py:45-67 */ };
+enum { ORACLE_UF_DYNAMIC = 1, ORACLE_UF_WEST = 2, ORACLE_UF_NODE = 4 /* NodeUF, node_uf.py:45-67 */,
+       ORACLE_UF_BUCKET = 8 /* with NODE: NodeBUF, node_buf.py:35-61 (smallest active clusters first) */ };
 enum { ORACLE_DEC_UF = 0, ORACLE_DEC_MACAR = 1, ORACLE_DEC_ACTIS = 2 };
 
 /* Bernoulli(class_p[edge_class[e]]) per edge in edge order, as

@@ -111,3 +111,33 @@ class CanonicalNodeUF(_RefNodeUF):
             self._FORESTER.merge(cu, cv, (u, v))
 
     _make_tree = CanonicalUF._make_tree
+
+
+from localuf.decoders.node_buf import NodeBUF as _RefNodeBUF  # noqa: E402
+
+
+class CanonicalNodeBUF(_RefNodeBUF):
+    """``NodeBUF`` (``localuf/decoders/node_buf.py``: always the smallest active clusters first)
+    with the same two pins; buckets, ``validate`` and ``_update_self_after_union`` are inherited."""
+
+    def __init__(self, code, dynamic=False, inclination='default'):
+        self._EDGE_ID = {e: k for k, e in enumerate(code.EDGES)}
+        self.round_count = 0
+        super().__init__(code, dynamic=dynamic, inclination=inclination)
+
+    def reset(self, no_boundaries=False):
+        super().reset()
+        self.round_count = 0
+
+    def _growth_round(self, log_history, clusters_to_grow=None):
+        self.round_count += 1
+        merge_ls, changed = [], set()
+        for cluster in list(clusters_to_grow):
+            self._grow(cluster, merge_ls, changed)          # node_uf.py:45-67, unchanged
+        merge_ls.sort(key=self._EDGE_ID.__getitem__)
+        for (u, v) in merge_ls:
+            cu = self.clusters[self._find(u)]
+            cv = self.clusters[self._find(v)]
+            self._FORESTER.merge(cu, cv, (u, v))
+
+    _make_tree = CanonicalUF._make_tree

@@ -12,12 +12,23 @@ from conftest import ROOT, load_golden, make_code, golden_names
 sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
 
-NODE = 4
+NODE, BUCKET = 4, 8
 FLAGS = {'default': NODE, 'dynamic': NODE | 1, 'west': NODE | 2}
 
 
-@pytest.mark.parametrize('name', golden_names('nuf_'))
-def test_oracle_matches_reference(name):
+def cases():
+    """(golden name, flag sets): NodeUF goldens and NodeBUF goldens (bucket flag added)."""
+    out = [(n, FLAGS) for n in golden_names('nuf_')]
+    out += [(n, {k: v | BUCKET for k, v in FLAGS.items()}) for n in golden_names('nbuf_')]
+    return out
+
+
+CASES = cases()
+IDS = [c[0] for c in CASES]
+
+
+@pytest.mark.parametrize('name,FLAGS', CASES, ids=IDS)
+def test_oracle_matches_reference(name, FLAGS):
     import binding
     meta, arr = load_golden(name)
     orc = binding.Oracle.from_code(make_code(meta['spec']))
@@ -28,8 +39,8 @@ def test_oracle_matches_reference(name):
         np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
 
 
-@pytest.mark.parametrize('name', golden_names('nuf_'))
-def test_emu_matches_reference(name):
+@pytest.mark.parametrize('name,FLAGS', CASES, ids=IDS)
+def test_emu_matches_reference(name, FLAGS):
     import emu_binding
     from localuf_b200._engine import unpack_growth
     meta, arr = load_golden(name)
@@ -55,8 +66,8 @@ def test_growth_rule_differs_from_uf_and_equals_macar():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', golden_names('nuf_'))
-def test_gpu_matches_reference(name):
+@pytest.mark.parametrize('name,FLAGS', CASES, ids=IDS)
+def test_gpu_matches_reference(name, FLAGS):
     from localuf_b200 import _engine
     meta, arr = load_golden(name)
     code = make_code(meta['spec'])
@@ -81,13 +92,34 @@ def test_gpu_fused_and_class_api():
     eng = dec.engine
     orc = binding.Oracle.from_code(code)
     p, n = 0.02, 4000
-    for flags in (NODE, NODE | 1, NODE | 2):
+    for flags in (NODE, NODE | 1, NODE | 2, NODE | BUCKET, NODE | BUCKET | 2):
         err, syn = eng.sample_host(p, 3, 50, n)
         ocorr, _, _ = orc.decode_batch(0, flags, syn, want_growth=False)
         want = int(orc.logical_batch(err, ocorr).sum())
         assert eng.mc_run_host(_engine.DEC_UF, flags, p, 3, 50, n) == (want, n)
     m, slender = code.SCHEME.run(dec, p, n, seed=3)
     assert slender == n and m > 0
+    m2, _ = code.SCHEME.run(L.decoders.NodeBUF(code), p, n, seed=3)
+    assert 0 < m2 < n
     syndrome = code.get_syndrome(code.make_error(0.03))
     dec.reset(); dec.decode(syndrome)
     assert code.get_syndrome(dec.correction) == syndrome
+
+
+def test_emu_bucket_mode_with_tiny_work_lists():
+    """3-entry lists: more active nodes than list2 holds -> the bucket round looks them up again."""
+    import emu_binding
+    from localuf_b200._engine import unpack_growth
+    emu_binding.use_tiny_lists(True)
+    try:
+        for name in ('nbuf_sf9_cc_p15', 'nbuf_sf5_cc_p20', 'nuf_sf5_phen_p05'):
+            meta, arr = load_golden(name)
+            emu = emu_binding.Emu(make_code(meta['spec']))
+            flags = NODE | (BUCKET if name.startswith('nbuf') else 0)
+            for decode in (emu.decode_uf, lambda f, s: emu.decode_uf_cta(f, s, nl=64)):
+                corr, growth2b, steps = decode(flags, arr['syn_bits'])
+                np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr['default_growth'])
+                np.testing.assert_array_equal(steps[:, 0], arr['default_rounds'])
+                np.testing.assert_array_equal(corr, arr['default_corr'])
+    finally:
+        emu_binding.use_tiny_lists(False)
