@@ -12,8 +12,8 @@ import ref_shim
 
 localuf = ref_shim.load()
 from localuf.constants import Growth  # noqa: E402
-from localuf.decoders import NodeUF, NodeBUF  # noqa: E402
-from ref_canonical import CanonicalNodeUF, CanonicalNodeBUF  # noqa: E402
+from localuf.decoders import NodeUF, NodeBUF, BUF  # noqa: E402
+from ref_canonical import CanonicalNodeUF, CanonicalNodeBUF, CanonicalBUF  # noqa: E402
 
 NUF_CASES = [
     ('nuf_sf7_cc_p12', dict(code='Surface', d=7, noise='code capacity'), 0.12, 300, 31),
@@ -79,7 +79,18 @@ NBUF_CASES = [
 ]
 
 
+BUF_CASES = [
+    ('buf_sf7_cc_p12', dict(code='Surface', d=7, noise='code capacity'), 0.12, 300, 51),
+    ('buf_sf9_cc_p08', dict(code='Surface', d=9, noise='code capacity'), 0.08, 300, 52),
+    ('buf_sf5_phen_p05', dict(code='Surface', d=5, noise='phenomenological'), 0.05, 200, 53),
+    ('buf_sf11_phen_p015', dict(code='Surface', d=11, noise='phenomenological'), 0.015, 50, 54),
+    ('buf_sf5_cl_p02', dict(code='Surface', d=5, noise='circuit-level'), 0.02, 150, 55),
+    ('buf_rep7_phen_p06', dict(code='Repetition', d=7, noise='phenomenological'), 0.06, 200, 56),
+]
+
+
 def jobs():
     out = {case[0]: (lambda c=case: nuf_case(*c)) for case in NUF_CASES}
     out.update({case[0]: (lambda c=case: nuf_case(*c, canonical=CanonicalNodeBUF, unmodified=NodeBUF)) for case in NBUF_CASES})
+    out.update({case[0]: (lambda c=case: nuf_case(*c, canonical=CanonicalBUF, unmodified=BUF)) for case in BUF_CASES})
     return out

@@ -141,3 +141,26 @@ class CanonicalNodeBUF(_RefNodeBUF):
             self._FORESTER.merge(cu, cv, (u, v))
 
     _make_tree = CanonicalUF._make_tree
+
+
+from localuf.decoders.buf import BUF as _RefBUF  # noqa: E402
+
+
+class CanonicalBUF(_RefBUF):
+    """``BUF`` (``localuf/decoders/buf.py``: always the active clusters with the shortest vision
+    first) with the same two pins; buckets, ``validate``, the merges and their bucket
+    bookkeeping are inherited."""
+
+    def __init__(self, code, dynamic=False, inclination='default'):
+        self._EDGE_ID = {e: k for k, e in enumerate(code.EDGES)}
+        self.round_count = 0
+        super().__init__(code, dynamic=dynamic, inclination=inclination)
+
+    def reset(self, no_boundaries=False):
+        super().reset()
+        self.round_count = 0
+
+    def _growth_round(self, log_history, clusters_to_grow=None):
+        CanonicalUF._growth_round(self, log_history, list(clusters_to_grow))
+
+    _make_tree = CanonicalUF._make_tree

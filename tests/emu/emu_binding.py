@@ -8,7 +8,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LIB = os.path.join(HERE, '_build', 'libluf_emu.so')
+LIB = os.environ.get('LUF_EMU_LIB') or os.path.join(HERE, '_build', 'libluf_emu.so')
 CSRC = os.path.join(ROOT, 'localuf_b200', 'csrc')
 SRCS = [os.path.join(HERE, 'emu.cpp')] + [
     os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h', '.inl'))
@@ -18,6 +18,8 @@ SRCS = [os.path.join(HERE, 'emu.cpp')] + [
 def build(tiny_lists=False):
     """``tiny_lists``: a second build whose in-kernel work lists hold 3 entries, so that
     every overflow path of the kernel phases runs on ordinary test inputs."""
+    if os.environ.get('LUF_EMU_LIB') and not tiny_lists:
+        return LIB                      # a prebuilt variant (tests/test_emu_sanitized.py)
     out = LIB.replace('.so', '_tiny.so') if tiny_lists else LIB
     if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in SRCS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -36,6 +38,18 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
     return _lib
+
+
+def build_sanitized():
+    """The emulation with AddressSanitizer + UBSan (heap buffers = the shot's shared-memory
+    slice: an out-of-range index of the kernel phases is reported).  Returns (library, libasan)."""
+    out = LIB.replace('.so', '_asan.so')
+    if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in SRCS):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(['g++', '-O1', '-g', '-fPIC', '-shared', '-std=c++17', '-fsanitize=address,undefined',
+                        '-fno-sanitize-recover=all', '-o', out, SRCS[0]], check=True, capture_output=True)
+    asan = subprocess.run(['g++', '-print-file-name=libasan.so'], capture_output=True, text=True).stdout.strip()
+    return out, asan
 
 
 def use_tiny_lists(on: bool):
