@@ -50,7 +50,8 @@ enum {
     LUF_UF_DYNAMIC = 1,        /* decoders/uf.py:23-28  UF(dynamic=True)       */
     LUF_UF_WEST = 2,           /* decoders/uf.py:23-28  UF(inclination='west') */
     LUF_UF_NODE = 4,           /* decoders/node_uf.py:5-67  NodeUF: frontier nodes grow (decoder LUF_DEC_UF) */
-    LUF_UF_BUCKET = 8,         /* with LUF_UF_NODE: decoders/node_buf.py:5-61  NodeBUF (smallest active clusters first) */
+    LUF_UF_BUCKET = 8,         /* decoders/buf.py:6-116  BUF (shortest vision first); with LUF_UF_NODE:
+                                  decoders/node_buf.py:5-61  NodeBUF (smallest active clusters first) */
     LUF_ACTIS_UNOPTIMAL = 4    /* decoders/luf/__init__.py:31-41 Actis(_optimal=False) (decoder LUF_DEC_ACTIS) */
 };
 enum { LUF_NOISE_CODE_CAPACITY = 0, LUF_NOISE_PHENOMENOLOGICAL = 1, LUF_NOISE_CIRCUIT_LEVEL = 2 };

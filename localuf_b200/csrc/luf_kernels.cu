@@ -817,8 +817,8 @@ static int check_decoder(const luf_graph* g, int decoder, int flags)
 {
     if (decoder == LUF_DEC_UF) {
         if (flags & ~(LUF_UF_DYNAMIC | LUF_UF_WEST | LUF_UF_NODE | LUF_UF_BUCKET)) return fail(LUF_ERR_INVALID, "unknown UF flag");
-        if ((flags & LUF_UF_BUCKET) && !(flags & LUF_UF_NODE))
-            return fail(LUF_ERR_UNSUPPORTED, "bucket growth is built for NodeBUF (LUF_UF_NODE | LUF_UF_BUCKET) only");
+        if ((flags & LUF_UF_BUCKET) && !(flags & LUF_UF_NODE) && g->view.E > 32767)
+            return fail(LUF_ERR_UNSUPPORTED, "BUF keeps vision lengths in 15 bits: graphs of up to 32767 edges");
         return 0;
     }
     if (decoder == LUF_DEC_MACAR || decoder == LUF_DEC_ACTIS) {

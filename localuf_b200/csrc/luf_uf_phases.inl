@@ -280,6 +280,77 @@ LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int flags, int 
     return total;
 }
 
+// BUF (buf.py:64-78): in every round only the active clusters with the shortest vision grow;
+// len(vision) = the distinct not-yet-FULL edges at the cluster's nodes (an edge inside the cluster
+// counted once).  The rounds of this mode walk the touched nodes five times: mark the active roots
+// in a bitmap (the reservation table, idle during growth), add up the vision lengths in the
+// boundary field of the root words (an active cluster has no boundary; < 2^15 edges), take the
+// minimum, grow the clusters that attain it, put the words back.
+LUF_DEV uint32_t vision_edges(const GraphView& g, const Shot& s, uint32_t u, uint32_t r)
+{
+    uint32_t c = 0;
+    for_row(g, u, [&](uint32_t ent) {
+        if (growth_of(s, ent & 0xFFFFu) >= G_FULL) return;
+        bool first;
+        const uint32_t o = other_end(ent, first);
+        uint32_t wr;
+        if (!first && (o == r || find_ro(s, o, wr) == r)) return;
+        ++c;
+    });
+    return c;
+}
+
+template <class F>
+LUF_DEV void for_active(const GraphView& g, const Shot& s, int lane, int nl, F f)
+{
+    const uint32_t* act = s.claim;
+    for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
+        uint32_t wr;
+        const uint32_t r = find_ro(s, u, wr);
+        if (bit_of(act, r)) f(u, r, wr);
+    });
+}
+
+LUF_DEV void ph_buf_mark(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    uint32_t* act = s.claim;
+    for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
+        uint32_t wr;
+        const uint32_t r = find_pc(s, u, wr);
+        if ((wr >> 16) != (ODD_BIT >> 16)) return;
+        luf_atomic_or(&act[r >> 5], 1u << (r & 31u));
+        luf_atomic_add(&s.cnt[1], 1u);
+    });
+}
+
+LUF_DEV void ph_buf_count(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    for_active(g, s, lane, nl, [&](uint32_t u, uint32_t r, uint32_t) {
+        const uint32_t c = vision_edges(g, s, u, r);
+        if (c) luf_atomic_add(&s.S[r], c << 16);
+    });
+}
+
+LUF_DEV void ph_buf_min(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    for_active(g, s, lane, nl, [&](uint32_t, uint32_t, uint32_t wr) { luf_atomic_min(&s.cnt[3], (wr >> 16) & 0x7FFFu); });
+}
+
+// Returns the number of active nodes of the round.
+LUF_DEV uint32_t ph_buf_exec(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    const uint32_t shortest = s.cnt[3];
+    for_active(g, s, lane, nl, [&](uint32_t u, uint32_t r, uint32_t wr) {
+        if (((wr >> 16) & 0x7FFFu) == shortest) grow_node(g, s, u, r, false);
+    });
+    return s.cnt[1];
+}
+
+LUF_DEV void ph_buf_restore(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    for_active(g, s, lane, nl, [&](uint32_t, uint32_t r, uint32_t wr) { s.S[r] = (wr & 0xFFFFu) | ODD_BIT; });
+}
+
 // ------------------------------------------------------------ phase 2b: merge
 // uf.py:223-229,256-301 in canonical order: this round's newly FULL edges are
 // merged in ascending edge id.  Union by size, ties keep the cluster of the
@@ -557,11 +628,21 @@ template <int TF>
 LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane, int nl)
 {
     int rounds = 0;
+    const bool vision_buckets = ((TF >= 0 ? TF : flags) & (FLAG_BUCKET | FLAG_NODE)) == FLAG_BUCKET;      // BUF
     uint32_t iter = 0xFFFFu;                 // decreasing reservation tag
     (void)lane;
     for (;;) {
         uint32_t active = 0;
-        if (rounds == 0) {
+        if (vision_buckets) {
+            if (rounds == 0) { LUF_T_PHASE(if (lane == 0) s.cnt[0] = 0); }      // ph_load's list of defects is not used
+            LUF_T_PHASE(ph_grow_gather(g, s, lane, nl); for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0);
+            LUF_T_PHASE(ph_buf_mark(g, s, lane, nl));
+            LUF_T_PHASE(ph_buf_count(g, s, lane, nl));
+            LUF_T_PHASE(ph_buf_min(g, s, lane, nl));
+            LUF_T_PHASE(active |= ph_buf_exec(g, s, lane, nl));
+            LUF_T_PHASE(ph_buf_restore(g, s, lane, nl));
+            LUF_T_PHASE(for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0xFFFFFFFFu);
+        } else if (rounds == 0) {
             LUF_T_PHASE(active |= ph_grow_first(g, s, lane, nl));
         } else {
             LUF_T_PHASE(ph_grow_gather(g, s, lane, nl));

@@ -90,3 +90,18 @@ class NodeBUF(NodeUF):
 
     def __repr__(self):
         return f'NodeBUF(code={self.CODE}, syndrome={self.syndrome})'
+
+
+class BUF(UF):
+    """``localuf/decoders/buf.py:6-116`` (bucket UF): in every growth round only the active
+    clusters with the shortest vision -- the fewest not-yet-fully-grown edges around them --
+    grow.  Same kernels with ``LUF_UF_BUCKET``.  Where the reference raises ``ValueError``
+    (``Growth(3)``: an edge one cluster grew to HALF is later grown by both its clusters in one
+    round) growth saturates at FULL here."""
+
+    def __init__(self, code, dynamic: bool = False, inclination: str = 'default'):
+        super().__init__(code, dynamic=dynamic, inclination=inclination)
+        self._flags |= _engine.UF_BUCKET
+
+    def __repr__(self):
+        return f'BUF(code={self.CODE}, syndrome={self.syndrome})'

@@ -39,6 +39,7 @@ def nuf_case(name, spec, p, shots, seed, canonical=CanonicalNodeUF, unmodified=N
     syn_bits = np.zeros((shots, G.words(D)), np.uint32)
     out = {k: dict(growth=np.zeros((shots, E), np.uint8), corr=np.zeros((shots, G.words(E)), np.uint32),
                    logical=np.zeros(shots, np.uint8), rounds=np.zeros(shots, np.int32)) for k in variants}
+    raised = np.zeros(shots, np.uint8)
     random.seed(seed)
     for s in range(shots):
         error = code.make_error(p) if is_batch else {e for e in code.EDGES if random.random() < p}
@@ -55,10 +56,17 @@ def nuf_case(name, spec, p, shots, seed, canonical=CanonicalNodeUF, unmodified=N
             assert code.get_syndrome(dec.correction) == syndrome
             if is_batch:
                 o['logical'][s] = code.get_logical_error(error ^ dec.correction)
-        plain.reset(); plain.decode(set(syndrome))
-        assert all(plain.growth[e] == variants['default'].growth[e] for e in code.EDGES)
-        assert code.get_syndrome(plain.correction) == syndrome
-    arrays = dict(err_bits=err_bits, syn_bits=syn_bits)
+        # the unmodified decoder; BUF raises ValueError (Growth(3), constants.py:17-31) when an edge that one
+        # cluster grew to HALF is later grown by both its clusters in one round -- those shots are
+        # flagged, the canonical execution saturates at FULL there
+        try:
+            plain.reset(); plain.decode(set(syndrome))
+        except ValueError:
+            raised[s] = 1
+        else:
+            assert all(plain.growth[e] == variants['default'].growth[e] for e in code.EDGES)
+            assert code.get_syndrome(plain.correction) == syndrome
+    arrays = dict(err_bits=err_bits, syn_bits=syn_bits, unmodified_raised=raised)
     for k, o in out.items():
         for f, a in o.items():
             arrays[f'{k}_{f}'] = a

@@ -155,15 +155,34 @@ static int uf_decode_ws(const oracle_graph *g, uf_ws *w, int flags, const uint32
         /* uf.py:221-222,234-245: every active cluster adds one growth increment to
          * every edge of its vision; an edge seen by two different active clusters
          * gets two.  Saturating (Growth(3) would raise in the reference). */
-        /* NodeBUF (node_buf.py:42-47): only the active clusters of the smallest size grow this round */
+        /* Bucket decoders: only the active clusters of the smallest metric grow this round.
+         * NodeBUF (node_buf.py:42-47): metric = cluster size.  BUF (buf.py:64-78): metric = len(vision),
+         * the number of distinct not-yet-FULL edges at the cluster's nodes. */
         int smallest = 0;
         if (bucket) {
-            smallest = N + 1;
-            for (int a = 0; a < n_active; ++a) if (w->size[w->active[a]] < smallest) smallest = w->size[w->active[a]];
+            smallest = 0x7FFFFFFF;
+            for (int a = 0; a < n_active; ++a) {
+                const int r = w->active[a];
+                int metric = w->size[r];
+                if (!node) {
+                    const int mark = -2 - rounds;
+                    metric = 0;
+                    for (int u = r; u != -1; u = w->next[u])
+                        for (int k = g->inc_off[u]; k < g->inc_off[u + 1]; ++k) {
+                            const int e = g->inc_edge[k];
+                            if (w->growth[e] >= FULL) continue;
+                            if (w->seen_round[e] == mark && w->seen_root[e] == r) continue;
+                            w->seen_round[e] = mark; w->seen_root[e] = r;
+                            ++metric;
+                        }
+                }
+                w->stack[a] = metric;                                   /* scratch: the stack is idle during validation */
+                if (metric < smallest) smallest = metric;
+            }
         }
         for (int a = 0; a < n_active; ++a) {
             const int r = w->active[a];
-            if (bucket && w->size[r] != smallest) continue;
+            if (bucket && w->stack[a] != smallest) continue;
             for (int u = r; u != -1; u = w->next[u])
                 for (int k = g->inc_off[u]; k < g->inc_off[u + 1]; ++k) {
                     const int e = g->inc_edge[k];

@@ -44,7 +44,8 @@ typedef struct {
 } oracle_graph;
 
 enum { ORACLE_UF_DYNAMIC = 1, ORACLE_UF_WEST = 2, ORACLE_UF_NODE = 4 /* NodeUF, node_uf.py:45-67 */,
-       ORACLE_UF_BUCKET = 8 /* with NODE: NodeBUF, node_buf.py:35-61 (smallest active clusters first) */ };
+       ORACLE_UF_BUCKET = 8 /* BUF, buf.py:64-78 (shortest vision first); with NODE: NodeBUF, node_buf.py:35-61
+                               (smallest clusters first) */ };
 enum { ORACLE_DEC_UF = 0, ORACLE_DEC_MACAR = 1, ORACLE_DEC_ACTIS = 2 };
 
 /* Bernoulli(class_p[edge_class[e]]) per edge in edge order, as

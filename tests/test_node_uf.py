@@ -1,5 +1,6 @@
-"""NodeUF (localuf/decoders/node_uf.py): frontier-node growth
-through the UF kernels with the LUF_UF_NODE flag.  Goldens: oracle/gen_golden_nuf.py (reference
+"""NodeUF, NodeBUF and BUF (localuf/decoders/node_uf.py, node_buf.py, buf.py; SURVEY.md section 8
+row f4): frontier-node growth and bucket growth through the UF kernels with the LUF_UF_NODE /
+LUF_UF_BUCKET flags.  Goldens: oracle/gen_golden_nuf.py (reference
 NodeUF in canonical order; growth asserted equal to the unmodified reference)."""
 import os
 import sys
@@ -20,6 +21,7 @@ def cases():
     """(golden name, flag sets): NodeUF goldens and NodeBUF goldens (bucket flag added)."""
     out = [(n, FLAGS) for n in golden_names('nuf_')]
     out += [(n, {k: v | BUCKET for k, v in FLAGS.items()}) for n in golden_names('nbuf_')]
+    out += [(n, {k: (v & ~NODE) | BUCKET for k, v in FLAGS.items()}) for n in golden_names('buf_')]   # BUF
     return out
 
 
@@ -92,7 +94,7 @@ def test_gpu_fused_and_class_api():
     eng = dec.engine
     orc = binding.Oracle.from_code(code)
     p, n = 0.02, 4000
-    for flags in (NODE, NODE | 1, NODE | 2, NODE | BUCKET, NODE | BUCKET | 2):
+    for flags in (NODE, NODE | 1, NODE | 2, NODE | BUCKET, NODE | BUCKET | 2, BUCKET, BUCKET | 1):
         err, syn = eng.sample_host(p, 3, 50, n)
         ocorr, _, _ = orc.decode_batch(0, flags, syn, want_growth=False)
         want = int(orc.logical_batch(err, ocorr).sum())
@@ -100,7 +102,8 @@ def test_gpu_fused_and_class_api():
     m, slender = code.SCHEME.run(dec, p, n, seed=3)
     assert slender == n and m > 0
     m2, _ = code.SCHEME.run(L.decoders.NodeBUF(code), p, n, seed=3)
-    assert 0 < m2 < n
+    m3, _ = code.SCHEME.run(L.decoders.BUF(code), p, n, seed=3)
+    assert 0 < m2 < n and 0 < m3 < n
     syndrome = code.get_syndrome(code.make_error(0.03))
     dec.reset(); dec.decode(syndrome)
     assert code.get_syndrome(dec.correction) == syndrome
@@ -112,10 +115,10 @@ def test_emu_bucket_mode_with_tiny_work_lists():
     from localuf_b200._engine import unpack_growth
     emu_binding.use_tiny_lists(True)
     try:
-        for name in ('nbuf_sf9_cc_p15', 'nbuf_sf5_cc_p20', 'nuf_sf5_phen_p05'):
+        for name in ('nbuf_sf9_cc_p15', 'nbuf_sf5_cc_p20', 'nuf_sf5_phen_p05', 'buf_sf5_phen_p05', 'buf_sf5_cl_p02'):
             meta, arr = load_golden(name)
             emu = emu_binding.Emu(make_code(meta['spec']))
-            flags = NODE | (BUCKET if name.startswith('nbuf') else 0)
+            flags = BUCKET if name.startswith('buf') else NODE | (BUCKET if name.startswith('nbuf') else 0)
             for decode in (emu.decode_uf, lambda f, s: emu.decode_uf_cta(f, s, nl=64)):
                 corr, growth2b, steps = decode(flags, arr['syn_bits'])
                 np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr['default_growth'])
