@@ -233,7 +233,11 @@ typedef struct {
 typedef struct luf_stream luf_stream;
 enum {
     LUF_SF_SLOW_MERGER = 1,       /* Snowflake(merger='slow'),  snowflake/main.py:1237-1246 */
-    LUF_SF_ONE_ONE = 2            /* Snowflake(schedule='1:1'), snowflake/main.py:1284-1305 */
+    LUF_SF_ONE_ONE = 2,           /* Snowflake(schedule='1:1'), snowflake/main.py:1284-1305 */
+    LUF_SF_SYNDROME = 4           /* luf_stream_decode only: the input rows hold the new layer's SYNDROME (bit q =
+                                   * defect at in-layer position q; first W(NL) words of each W(EL)-word row) instead
+                                   * of fresh errors -- Snowflake.decode(syndrome) / generate_output,
+                                   * snowflake/main.py:216-256,656-726 */
 };
 
 int luf_stream_create(const luf_window_desc *desc, int device, luf_stream **out);

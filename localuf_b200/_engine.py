@@ -115,7 +115,7 @@ def make_window_desc(t):
     return d, keep
 
 
-SF_SLOW_MERGER, SF_ONE_ONE = 1, 2
+SF_SLOW_MERGER, SF_ONE_ONE, SF_SYNDROME = 1, 2, 4
 
 _lib = None
 _lib_lock = threading.Lock()

@@ -57,10 +57,20 @@ class WindowTables:
     code_edge: np.ndarray        # int32[h*EL]   layered index -> position in code.EDGES
     layered_of_code: np.ndarray  # int32[E]      position in code.EDGES -> layered index
     n_classes: int
+    rep: bool = False            # Repetition (one space axis) or Surface (two)
 
     @property
     def NL(self):
         return self.NLb + self.NLd
+
+    def position_of(self, v) -> int:
+        """In-layer position of node ``v`` (its time coordinate is ignored)."""
+        d = self.d
+        if self.rep:
+            j, = v[:-1]
+            return 0 if j == -1 else 1 if j == d - 1 else 2 + j
+        i, j = v[:-1]
+        return i if j == -1 else d + i if j == d - 1 else 2 * d + d * j + i
 
     def node_id(self, q: int, t: int) -> int:
         if q < self.NLb:
@@ -162,7 +172,7 @@ def build(code, neighbor_order=None) -> WindowTables:
                         nb_valid=nb_valid, nb_q=nb_q, nb_dt=nb_dt, nb_el=nb_el, nb_et=nb_et,
                         edge_q=edge_q, edge_dt=edge_dt, edge_class=edge_class, edge_fb=edge_fb,
                         pos_long=pos_long, code_edge=code_edge, layered_of_code=layered_of_code,
-                        n_classes=len(classes))
+                        n_classes=len(classes), rep=rep)
 
 
 # ---------------------------------------------------------------------------

@@ -284,7 +284,8 @@ __global__ void k_sf_decode(SfView g, SfLayout l, int flags, long long nstreams,
             const size_t row = (size_t)k * ncycles + c;
             int m = 0, ra = 0, ru = 0;
             sf_cycle_head(g, s, m, lane, nl);
-            LUF_PHASE(sf_given_sheet(g, s, fresh + row * g.ELw, lane, nl));
+            if (flags & SF_FLAG_SYNDROME) { LUF_PHASE(sf_given_syndrome(g, s, fresh + row * g.ELw, lane, nl)); }
+            else { LUF_PHASE(sf_given_sheet(g, s, fresh + row * g.ELw, lane, nl)); }
             sf_cycle_tail(g, s, flags, floor_bits ? floor_bits + row * g.ELw : nullptr, m, ra, ru, lane, nl);
             if (lane == 0) { rt[2 * row] = ra; rt[2 * row + 1] = ru; m_out[row] = m; }
         }
@@ -646,7 +647,7 @@ int luf_stream_decode(luf_stream* g, int flags, int64_t nstreams, int32_t ncycle
 {
     if (!g || !fresh_bits_dev || !rt_dev || !m_dev || nstreams < 0 || ncycles < 0)
         return fail(LUF_ERR_INVALID, "luf_stream_decode: bad argument");
-    if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE)) return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
+    if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE | LUF_SF_SYNDROME)) return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
     if (nstreams == 0 || ncycles == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
     LaunchCfg c;

@@ -29,7 +29,7 @@ static const uint32_t SF_PTR_C = 0xFFu;
 // per-node flag word (written by the owning lane only)
 enum { SF_ACTIVE = 1, SF_WHOLE = 2, SF_DEFECT = 4, SF_GROWN = 8, SF_UNROOTED = 16, SF_BUSY = 32,
        SF_N_ACTIVE = 64, SF_N_GROWN = 128, SF_N_UNROOTED = 256 };
-enum { SF_FLAG_SLOW = 1, SF_FLAG_ONE_ONE = 2 };
+enum { SF_FLAG_SLOW = 1, SF_FLAG_ONE_ONE = 2, SF_FLAG_SYNDROME = 4 };
 // string-pair codes of an endpoint's partner (see oracle/luf_oracle_snowflake.c)
 static const int SFP_NONE = -1, SFP_WEST = -2, SFP_EAST = -3, SFP_DEAD = -4;
 
@@ -235,6 +235,13 @@ LUF_DEV void sf_given_sheet(const SfView& g, const SfShot& s, const uint32_t* fr
             sf_flip_fresh(g, s, (uint32_t)(32 * w + b), false);
         }
     }
+}
+
+// The top sheet's syndrome given directly (Snowflake.decode(syndrome), snowflake/main.py:216-256;
+// generate_output, :656-726): bit q of `syn` = defect at in-layer position q of the new layer.
+LUF_DEV void sf_given_syndrome(const SfView& g, const SfShot& s, const uint32_t* syn, int lane, int nl)
+{
+    for (int w = lane; w < g.WLn; w += nl) s.top[w] ^= syn[w];
 }
 
 // Fresh errors sampled on the device: geometric skips over the class-sorted

@@ -9,8 +9,12 @@ drop, grow, merge, floor commit, string pairing, logical count -- inside
 """
 from __future__ import annotations
 
+import numpy as np
+
 from localuf_b200 import _engine, _window, dist
+from localuf_b200.codes import Repetition
 from localuf_b200.decoders._base import Decoder
+from localuf_b200.decoders._bitstrings import Bitstrings
 from localuf_b200.schemes import Frugal
 
 
@@ -33,6 +37,15 @@ class Snowflake(Decoder):
         self._LOOPS = 1 if schedule == '1:1' else 2
         self._tables = _window.build(code, _neighbor_order)
         self._stream_engine = None
+        # bit-string I/O (snowflake/main.py:104-123): the floor edges in output order, as local
+        # indices of the bottom layer block
+        self._BITSTRING_CONVERTER = Bitstrings(code.D, code.SCHEME.WINDOW_HEIGHT, type(code) is Repetition)
+        index = {e: k for k, e in enumerate(code.EDGES)}
+        self._LOWEST_EDGES = self._BITSTRING_CONVERTER.lowest_edges(
+            str(code.NOISE), _include_timelike_lowest_edges=_include_timelike_lowest_edges)
+        self._lowest_local = np.array(
+            [self._tables.layered_of_code[index[e]] % self._tables.EL for e in self._LOWEST_EDGES], np.int64)
+        self._cycles: list = []            # syndrome rows of the decoding cycles since reset()
 
     def __repr__(self) -> str:
         return f'decoders.Snowflake({self.CODE})'
@@ -43,10 +56,94 @@ class Snowflake(Decoder):
             self._stream_engine = _engine.StreamEngine(self._CODE, self._tables)
         return self._stream_engine
 
-    def decode(self, syndrome, **kwargs):
-        raise NotImplementedError(
-            "The device keeps Snowflake's window inside one kernel for a whole memory experiment; "
-            "use code.SCHEME.run(decoder, p, n) (Frugal.run) or StreamEngine.decode_host for given errors.")
+    # -- single decoding cycles and bit-string I/O ------------------------------
+    def reset(self):
+        """``snowflake/main.py:201-214``: an empty window; forgets ``floor_history``."""
+        super().reset()
+        self._cycles = []
+        if hasattr(self, 'floor_history'):
+            del self.floor_history
+
+    def init_history(self):
+        """``snowflake/main.py:181-184`` (only ``floor_history`` is kept here)."""
+        self.floor_history: list = []
+
+    def _syndrome_row(self, syndrome) -> np.ndarray:
+        t = self._tables
+        row = np.zeros((t.EL + 31) // 32, np.uint32)
+        top = t.h - 1
+        for v in syndrome:
+            if v[-1] != top:
+                raise ValueError(f'Defect {v} is not in the top layer {top} of the viewing window.')
+            q = t.position_of(v)
+            if q < t.NLb:
+                raise ValueError(f'{v} is a boundary node, not a detector.')
+            row[q >> 5] ^= np.uint32(1 << (q & 31))
+        return row
+
+    def _floor_vector(self, floor_row: np.ndarray) -> str:
+        bits = (floor_row[self._lowest_local >> 5] >> (self._lowest_local & 31).astype(np.uint32)) & 1
+        return ''.join('1' if b else '0' for b in bits)
+
+    def _run_cycles(self, rows):
+        """One window, the given syndrome rows in order -> (runtimes [n, 2], floor rows [n, W])."""
+        rt, floor, _ = self.engine.decode_host(self._flags | _engine.SF_SYNDROME, np.stack(rows)[None])
+        return rt[0], floor[0]
+
+    def decode(self, syndrome, log_history=False, log_floor_history: bool = False, metrics=(),
+               noise_level_for_priors=None, time_only: str = 'merging', defects_possible: bool = True):
+        """One decoding cycle (``snowflake/main.py:216-281``): ``syndrome`` = the defects of the
+        newly exposed top layer.  Returns the number of timesteps of the cycle.
+
+        The device keeps a window inside one kernel launch, so the state between calls is the
+        list of syndromes since :meth:`reset`; each call replays it (cost grows with the number
+        of cycles -- use :meth:`generate_output` or ``Frugal.run`` for long streams)."""
+        if log_history or tuple(metrics):
+            raise NotImplementedError("Drawing / history / per-cycle metrics are outside this engine.")
+        if not defects_possible:
+            raise NotImplementedError("defects_possible=False (drop only) is not built.")
+        if time_only not in ('all', 'merging', 'unrooting'):
+            raise ValueError(f'Unknown time_only: {time_only}.')
+        self._cycles.append(self._syndrome_row(syndrome))
+        rt, floor = self._run_cycles(self._cycles)
+        if log_floor_history:
+            self.floor_history.append(self._floor_vector(floor[-1]))
+        return self._runtime(rt[-1], time_only)
+
+    def _runtime(self, rt, time_only: str) -> int:
+        if time_only == 'all':
+            return int(rt[0])
+        if time_only == 'merging':
+            return int(rt[0]) - 2 * self._LOOPS
+        return int(rt[1])
+
+    def generate_output(self, syndromes, output_to_csv_file=None, draw=False, **_kwargs):
+        """``snowflake/main.py:656-726``: syndrome vectors (strings of '0' / '1') or sets of
+        top-layer defects, one per decoding cycle, in; the floor vectors -- the correction bits
+        of ``self._LOWEST_EDGES`` just before each drop -- out, padded with ``WINDOW_HEIGHT``
+        empty cycles so that every correction leaves the window.  Optionally saved as CSV
+        (``syndrome_vector``, ``floor_history``)."""
+        if draw:
+            raise NotImplementedError("Drawing is outside this engine.")
+        conv, h = self._BITSTRING_CONVERTER, self._tables.h
+        first, *_ = syndromes
+        if type(first) is str:
+            vectors = list(syndromes) + h * ['0' * conv.LENGTH]
+            sets = conv.syndrome_vectors_to_sets(vectors)
+        else:
+            sets = list(syndromes) + h * [set()]
+            vectors = conv.sets_to_syndrome_vectors(sets)
+        self.init_history()
+        _, floor = self._run_cycles(self._cycles + [self._syndrome_row(s) for s in sets])
+        self._cycles += [self._syndrome_row(s) for s in sets]
+        self.floor_history += [self._floor_vector(f) for f in floor[len(floor) - len(sets):]]
+        if output_to_csv_file is not None:
+            import csv
+            with open(output_to_csv_file, 'w', newline='') as f:
+                w = csv.writer(f)
+                w.writerow(['syndrome_vector', 'floor_history'])
+                w.writerows(zip(vectors, self.floor_history, strict=True))
+        return self.floor_history
 
     def steps_from_sums(self, sums, time_only: str):
         """(sum of 'all' runtimes, sum of 'unrooting' runtimes) over d cycles -> Frugal.step_counts entry

@@ -232,7 +232,8 @@ int emu_sf_stream(const luf_window_desc* d, int flags, int ncycles, const uint32
     for (int c = 0; c < ncycles; ++c) {
         int m = 0, ra = 0, ru = 0;
         sf_cycle_head(g, s, m, 0, nl);
-        LUF_PHASE(sf_given_sheet(g, s, fresh + (size_t)c * g.ELw, lane, nl));
+        if (flags & SF_FLAG_SYNDROME) { LUF_PHASE(sf_given_syndrome(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
+        else { LUF_PHASE(sf_given_sheet(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
         sf_cycle_tail(g, s, flags, floor_bits + (size_t)c * g.ELw, m, ra, ru, 0, nl);
         rt[2 * c] = ra; rt[2 * c + 1] = ru; m_out[c] = m;
     }
