@@ -34,6 +34,8 @@ WORKLOADS = {
     'cfg1': ('Repetition', 5, 'code capacity', 0.05, 'Repetition d=5 code-capacity p=0.05 UF batch'),
     'cfg2': ('Surface', 9, 'code capacity', 0.05, 'Surface d=9 code-capacity p=0.05 UF batch'),
     'cfg3': ('Surface', 11, 'phenomenological', 0.01, 'Surface d=11 phenomenological p=0.01 h=11 UF batch'),
+    'cfg3-staged': ('Surface', 11, 'phenomenological', 0.01,
+                    'Surface d=11 phenomenological p=0.01 h=11 UF batch, staged pipeline: sample -> HBM -> decode -> HBM -> check'),
     'cfg3-macar': ('Surface', 11, 'phenomenological', 0.01, 'Surface d=11 phenomenological p=0.01 h=11 Macar batch',
                    'batch', 'Macar'),
     'cfg3-actis': ('Surface', 11, 'phenomenological', 0.01, 'Surface d=11 phenomenological p=0.01 h=11 Actis batch',
@@ -262,7 +264,7 @@ def run_reference(args):
 
 DTYPE = 'u32 bit-packed / u16 indices'
 METRIC = {'shots/s': 'decoded shots/s', 'decoding cycles/s': 'decoding cycles/s'}
-DEFAULT_UNITS = {'cfg1': 1 << 26, 'cfg2': 1 << 24, 'cfg3': 1 << 22, 'cfg3-macar': 1 << 19, 'cfg3-actis': 1 << 14,
+DEFAULT_UNITS = {'cfg1': 1 << 26, 'cfg2': 1 << 24, 'cfg3': 1 << 22, 'cfg3-staged': 1 << 20, 'cfg3-macar': 1 << 19, 'cfg3-actis': 1 << 14,
                  'cfg4': 1 << 16}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full; profiles/)
 TRAFFIC = {'cfg3': (112640, 'profiles/r01_v10_k_mc_uf_summary.txt'),
@@ -418,6 +420,129 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_staged(args):
+    """The staged pipeline of SURVEY 8d on device buffers -- K1 luf_sample writes bit-packed errors and
+    defects to HBM, K2 luf_decode_batch reads the defects and writes corrections, K4 luf_check reads errors
+    and corrections -- with every kernel timed by its own CUDA events, and, as `e2e`, the decode of HOST
+    syndromes into HOST corrections through luf_decode_batch_host (page-locked buffers, copies inside the
+    timed region, chunks pipelined over three streams)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import localuf_b200 as L
+    from localuf_b200 import _engine
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the engine has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    code, p, desc = make_code(args.workload)
+    eng = _engine.Engine(code, device=local_rank)
+    S = args.shots_per_step or DEFAULT_UNITS[args.workload]
+    WE, WD = eng.WE, eng.WD
+    i32 = dict(dtype=torch.int32, device='cuda')
+    err, syn, corr = torch.empty(S, WE, **i32), torch.empty(S, WD, **i32), torch.empty(S, WE, **i32)
+    logical = torch.empty(S, dtype=torch.uint8, device='cuda')
+    fails = torch.zeros(1, dtype=torch.int64, device='cuda')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    names = ('k_sample', 'k_decode_uf', 'k_check')
+    bytes_per_shot = {'k_sample': 4 * (WE + WD), 'k_decode_uf': 4 * (WD + WE), 'k_check': 8 * WE + 1}
+
+    def step(k, ev=None):
+        marks = ev or [None] * 4
+        if ev: marks[0].record()
+        eng.sample(p, SEED, (k * world + rank) * S, S, err, syn)
+        if ev: marks[1].record()
+        eng.decode_batch(0, 0, S, syn, corr)
+        if ev: marks[2].record()
+        eng.check(S, err, corr, logical, fails)
+        if ev: marks[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    fails.zero_()
+    launches0 = eng.launch_count
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        clocks.mark()
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            step(args.warmup + k, evs[k])
+        barrier()
+        clocks.mark()
+    launches = eng.launch_count - launches0
+    kern_ms = {n: statistics.mean(e[i].elapsed_time(e[i + 1]) for e in evs) for i, n in enumerate(names)}
+    total_ms = torch.tensor([sum(e[0].elapsed_time(e[3]) for e in evs)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fails, op=dist.ReduceOp.SUM)
+    total_ms = float(total_ms.item())
+    value = S * args.steps * world / (total_ms / 1e3)
+
+    # ---- end to end: host syndromes in, host corrections out (page-locked), failures counted on the host side
+    n_e2e = S
+    syn_h = torch.empty(n_e2e, WD, dtype=torch.int32).pin_memory()
+    corr_h = torch.empty(n_e2e, WE, dtype=torch.int32).pin_memory()
+    syn_h.copy_(syn[:n_e2e])
+    torch.cuda.synchronize()
+    syn_np, corr_np = syn_h.numpy().view(np.uint32), corr_h.numpy().view(np.uint32)
+    eng.decode_batch_host(0, 0, syn_np[:1 << 14], want_steps=False, corr_out=corr_np[:1 << 14])
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.decode_batch_host(0, 0, syn_np, want_steps=False, corr_out=corr_np)
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = n_e2e * world * e2e_steps / float(t_e2e.item())
+    same = bool((corr_h.cuda() == corr[:n_e2e]).all().item())     # the host path returns what the device path wrote
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        kernels = {}
+        for n in names:
+            gbs = bytes_per_shot[n] * S / (kern_ms[n] / 1e3) / 1e9
+            kernels[n] = {'ms': kern_ms[n], 'algorithmic_bytes_per_unit': bytes_per_shot[n], 'achieved': gbs,
+                          'frac': gbs / peak}
+        dom = max(names, key=lambda n: kern_ms[n])
+        bpu = algorithmic_bytes_per_shot(code.FLAT)
+        line = {
+            'metric': METRIC['shots/s'], 'value': value, 'unit': 'shots/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
+            'config': {'workload': desc, 'units_per_step_per_gpu': S, 'seed': SEED,
+                       'parallelism': f'dp{world} (shots sharded, no data-path collective)',
+                       'l2': '256 MiB write between timed steps; the buffers of one step (1.1 GB) exceed the L2',
+                       'failures': int(fails.item()), 'host_path_equals_device_path': same},
+            'roofline': {'bound': 'hbm', 'achieved': bpu * S / (kern_ms[dom] / 1e3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                         'frac': bpu * S / (kern_ms[dom] / 1e3) / 1e9 / peak, 'traffic': None, 'kernel': dom,
+                         'algorithmic_bytes_per_unit': bpu, 'peak_source': peak_src, 'kernels': kernels,
+                         'note': 'achieved = the pipeline figure B = 4 W(E) + 2 W(D) per shot over the dominant '
+                                 "kernel's time; `kernels` holds every stage with its own bytes and time"},
+            'e2e': {'value': e2e_value, 'unit': 'shots/s', 'h2d_bytes_per_step': 4 * WD * n_e2e,
+                    'd2h_bytes_per_step': 4 * WE * n_e2e,
+                    'api': 'Engine.decode_batch_host(UF, syndromes) -> luf_decode_batch_host (page-locked host buffers)'},
+            'gpu_launches': launches,
+            'clocks': clocks.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -433,6 +558,8 @@ def main():
         args.warmup = 3
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload.endswith('-staged'):
+        run_staged(args)
     else:
         run_ours(args)
 

@@ -234,10 +234,19 @@ class Engine:
         self.last_step_sums = (int(counts[2]), int(counts[3]))
         return int(counts[0]), int(counts[1])
 
-    def decode_batch_host(self, decoder: int, flags: int, syn_bits, want_growth=False, want_steps=True):
+    def decode_batch_host(self, decoder: int, flags: int, syn_bits, want_growth=False, want_steps=True,
+                          corr_out=None):
+        """Host syndromes [n, W(D)] -> host corrections [n, W(E)] (+ growth, steps); the shots stream through
+        the device in chunks (copies overlap the decode when the arrays are page-locked).  ``corr_out``:
+        an optional preallocated uint32 [n, W(E)] array (e.g. a view of a pinned tensor) to write into."""
         syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
         n = syn.shape[0]
-        corr = np.zeros((n, self.WE), np.uint32)
+        if corr_out is None:
+            corr = np.zeros((n, self.WE), np.uint32)
+        else:
+            corr = corr_out
+            if corr.dtype != np.uint32 or corr.shape != (n, self.WE) or not corr.flags.c_contiguous:
+                raise ValueError(f'corr_out must be a C-contiguous uint32 array of shape {(n, self.WE)}')
         growth = np.zeros((n, self.WG), np.uint32) if want_growth else None
         steps = np.zeros((n, 2), np.int32) if want_steps else None
         _check(_load().luf_decode_batch_host(self._h, decoder, flags, n, _ptr(syn), _ptr(corr),

@@ -395,6 +395,7 @@ struct luf_graph {
     void* scratch[6] = {0, 0, 0, 0, 0, 0};
     size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
     long long launches = 0;
+    cudaStream_t pipe[3] = {0, 0, 0};     // copy / compute pipeline of the *_host batch entry points
     std::mutex mu;
     std::map<std::pair<const void*, uint32_t>, std::pair<int, int>> plans;   // (kernel, slice bytes) -> (warps per block, blocks per SM)
 };
@@ -799,6 +800,7 @@ int luf_graph_destroy(luf_graph* g)
     cudaSetDevice(g->device);
     for (void* p : g->allocs) cudaFree(p);
     for (void* p : g->scratch) if (p) cudaFree(p);
+    for (cudaStream_t st : g->pipe) if (st) cudaStreamDestroy(st);
     delete g;
     return 0;
 }
@@ -1130,18 +1132,31 @@ int luf_decode_batch_host(luf_graph* g, int decoder, int flags, int64_t nshots, 
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
     const size_t n = (size_t)nshots, WE = g->view.WE, WD = g->view.WD, GW = (g->view.E + 15) / 16;
-    void *syn, *corr, *gr = nullptr, *st = nullptr;
+    void *syn, *corr, *gr = nullptr, *st_dev = nullptr;
     int rc;
     if ((rc = scratch_get(g, 1, n * WD * 4, &syn)) || (rc = scratch_get(g, 2, n * WE * 4, &corr))) return rc;
     if (growth2b_host && (rc = scratch_get(g, 3, n * GW * 4, &gr))) return rc;
-    if (steps_host && (rc = scratch_get(g, 4, n * 8, &st))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(syn, syn_bits_host, n * WD * 4, cudaMemcpyHostToDevice, 0));
-    if ((rc = luf_decode_batch(g, decoder, flags, nshots, (const uint32_t*)syn, (uint32_t*)corr,
-                               (uint32_t*)gr, (int32_t*)st, 0))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(corr_bits_host, corr, n * WE * 4, cudaMemcpyDeviceToHost, 0));
-    if (gr) CUDA_TRY(cudaMemcpyAsync(growth2b_host, gr, n * GW * 4, cudaMemcpyDeviceToHost, 0));
-    if (st) CUDA_TRY(cudaMemcpyAsync(steps_host, st, n * 8, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
+    if (steps_host && (rc = scratch_get(g, 4, n * 8, &st_dev))) return rc;
+    // Chunks of shots flow through three streams: while one chunk decodes, the next one's
+    // syndromes arrive and the previous one's corrections leave (full-duplex PCIe; the copies
+    // are asynchronous when the caller's buffers are page-locked, staged by the driver otherwise).
+    const size_t chunk = (size_t)1 << 16;
+    for (cudaStream_t& st : g->pipe) if (!st) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int k = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, ++k) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        cudaStream_t st = g->pipe[k % 3];
+        uint32_t* d_syn = (uint32_t*)syn + lo * WD;
+        uint32_t* d_corr = (uint32_t*)corr + lo * WE;
+        uint32_t* d_gr = gr ? (uint32_t*)gr + lo * GW : nullptr;
+        int32_t* d_st = st_dev ? (int32_t*)st_dev + lo * 2 : nullptr;
+        CUDA_TRY(cudaMemcpyAsync(d_syn, syn_bits_host + lo * WD, m * WD * 4, cudaMemcpyHostToDevice, st));
+        if ((rc = luf_decode_batch(g, decoder, flags, (int64_t)m, d_syn, d_corr, d_gr, d_st, st))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(corr_bits_host + lo * WE, d_corr, m * WE * 4, cudaMemcpyDeviceToHost, st));
+        if (d_gr) CUDA_TRY(cudaMemcpyAsync(growth2b_host + lo * GW, d_gr, m * GW * 4, cudaMemcpyDeviceToHost, st));
+        if (d_st) CUDA_TRY(cudaMemcpyAsync(steps_host + lo * 2, d_st, m * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (cudaStream_t st : g->pipe) CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }
 
