@@ -247,7 +247,7 @@ struct PackedWindow {
 inline std::string pack_window(const luf_window_desc& d, PackedWindow& out)
 {
     const int NL = d.n_boundary_per_layer + d.n_detectors_per_layer, K = d.n_dirs, EL = d.edges_per_layer;
-    if (d.h < 3 || NL <= 0 || EL <= 0 || K <= 0 || K > 16) return "inconsistent window";
+    if (d.h < 3 || NL <= 0 || EL <= 0 || K <= 0 || K > 12) return "inconsistent window (at most 12 neighbour slots)";
     if (NL > 1023 || EL > 4095) return "window layer too large for the packed tables (NL <= 1023, EL <= 4095)";
     if ((long long)NL * d.h > 0xFFFE) return "window too large for 16-bit cluster ids";
     if (d.n_classes < 1 || d.n_classes > MAX_CLASSES) return "n_classes out of range";
@@ -261,6 +261,19 @@ inline std::string pack_window(const luf_window_desc& d, PackedWindow& out)
             return "neighbour table entry out of range";
         out.nbr[x] = 1u | ((uint32_t)d.nb_q[x] << 1) | ((uint32_t)d.nb_el[x] << 11) |
                      ((uint32_t)(dt + 1) << 23) | ((uint32_t)(et + 1) << 25);
+    }
+    // the slot under which the neighbour sees the same edge (same local edge; its block seen from
+    // the other end: et' = et - dt): needed to mark access at both ends when an edge becomes fully grown
+    for (int x = 0; x < NL * K; ++x) {
+        if (!d.nb_valid[x]) continue;
+        const int q = x / K, q2 = d.nb_q[x];
+        int back = -1;
+        for (int k2 = 0; k2 < K; ++k2) {
+            const int y = q2 * K + k2;
+            if (d.nb_valid[y] && d.nb_q[y] == q && d.nb_dt[y] == -d.nb_dt[x] && d.nb_el[y] == d.nb_el[x] &&
+                d.nb_et[y] == d.nb_et[x] - d.nb_dt[x]) { back = k2; break; }
+        }
+        out.nbr[x] |= (uint32_t)(back < 0 ? 15 : back) << 26;    // 15: the far end does not scan this direction
     }
     out.edge_ends.assign(EL, 0);
     for (int l = 0; l < EL; ++l) {
@@ -290,7 +303,7 @@ inline SfLayout make_sf_layout(const PackedWindow& p)
     uint32_t off = 0;
     auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
     const uint32_t N = (uint32_t)p.NL * p.h, ELw = words32(p.EL), WLn = words32(p.NL);
-    l.cid = take(2u * N); l.ncid = take(2u * N); l.fl = take(2u * N); l.ptr = take(N);
+    l.cid = take(2u * N); l.ncid = take(2u * N); l.fl = take(2u * N); l.acp = take(2u * (N + 1u));
     l.ndef = take(4u * p.h * WLn); l.awake = take(4u * p.h * WLn);
     l.growth = take(4u * p.h * 2u * ELw);
     l.corr = take(4u * p.h * ELw); l.err = take(4u * p.h * ELw);

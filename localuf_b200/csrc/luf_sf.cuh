@@ -25,7 +25,7 @@
 namespace luf {
 
 static const uint32_t SF_RESET = 0xFFFFu;     // snowflake/constants.py:5 (RESET = -1)
-static const uint32_t SF_PTR_C = 0xFFu;
+static const uint32_t SF_PTR_C = 0xFu;       // pointer 'C' (no neighbour) in the 4-bit pointer field
 // per-node flag word (written by the owning lane only)
 enum { SF_ACTIVE = 1, SF_WHOLE = 2, SF_DEFECT = 4, SF_GROWN = 8, SF_UNROOTED = 16, SF_BUSY = 32,
        SF_N_ACTIVE = 64, SF_N_GROWN = 128, SF_N_UNROOTED = 256 };
@@ -36,7 +36,7 @@ static const int SFP_NONE = -1, SFP_WEST = -2, SFP_EAST = -3, SFP_DEAD = -4;
 struct SfView {
     int d, h, NLb, NLd, NL, EL, ELw, K, WLn;   // ELw = words per edge block, WLn = words per node-layer bitmap
     int N, n_classes;
-    const uint32_t* nbr;        // [NL*K]  valid:1 | q2:10 | el:12 | dt+1:2 | et+1:1   (see sf_nbr)
+    const uint32_t* nbr;        // [NL*K]  valid:1 | q2:10 | el:12 | dt+1:2 | et+1:1 | slot of this edge at the neighbour:4   (see sf_nbr)
     const uint32_t* edge_ends;  // [EL]    q0:10 | dt0:1 | q1:10 | dt1:1 | fb:1
     const int8_t* pos_long;     // [NL]
     const uint16_t* fresh_perm; // [EL]    local edges sorted by probability class
@@ -51,7 +51,7 @@ static const uint32_t SF_ALIST_CAP = LUF_SF_ALIST_CAP;      // tests shrink it t
 struct SfLayout {
     uint32_t cid, ncid;         // u16[N]
     uint32_t fl;                // u16[N]
-    uint32_t ptr;               // u8[N]
+    uint32_t acp;               // u16[N]  bits 0..11: neighbour slots whose edge is fully grown (access); bits 12..15: pointer
     uint32_t ndef;              // u32[h*WLn]  next_defect (toggled by neighbours)
     uint32_t awake;             // u32[h*WLn]  nodes that ever saw a defect or a fully grown edge while in the window
     uint32_t growth;            // u32[h*2*ELw]  2 bits per edge: block b at word b*2*ELw
@@ -65,7 +65,7 @@ struct SfLayout {
 
 struct SfShot {
     uint16_t *cid, *ncid, *fl;
-    uint8_t* ptr;
+    uint16_t* acp;
     uint32_t *ndef, *awake, *growth, *corr, *err, *top, *fb, *acnt;
     uint16_t* alist;
     int16_t* partner;
@@ -75,7 +75,7 @@ LUF_DEV SfShot sf_bind(const SfLayout& l, unsigned char* b)
 {
     SfShot s;
     s.cid = (uint16_t*)(b + l.cid); s.ncid = (uint16_t*)(b + l.ncid); s.fl = (uint16_t*)(b + l.fl);
-    s.ptr = b + l.ptr;
+    s.acp = (uint16_t*)(b + l.acp);
     s.ndef = (uint32_t*)(b + l.ndef); s.awake = (uint32_t*)(b + l.awake); s.growth = (uint32_t*)(b + l.growth);
     s.alist = (uint16_t*)(b + l.alist); s.acnt = (uint32_t*)(b + l.acnt);
     s.corr = (uint32_t*)(b + l.corr); s.err = (uint32_t*)(b + l.err);
@@ -91,7 +91,7 @@ LUF_DEV uint32_t sf_id(const SfView& g, int r, int q)
 }
 
 // Neighbour slot k of node (r, q).  Returns false if absent in the window.
-struct SfNbr { int node, r2, q2; uint32_t e; };   // node index, and layered edge bit index
+struct SfNbr { int node, r2, q2; uint32_t e, back; };   // node index, layered edge bit index, this edge's slot at the neighbour
 LUF_DEV bool sf_nbr(const SfView& g, int r, int q, int k, SfNbr& o)
 {
     const uint32_t ent = LUF_LDG(&g.nbr[q * g.K + k]);
@@ -103,10 +103,26 @@ LUF_DEV bool sf_nbr(const SfView& g, int r, int q, int k, SfNbr& o)
     o.node = r2 * g.NL + o.q2;
     const int et = (int)((ent >> 25) & 1u) - 1;
     o.e = (uint32_t)((r - et) * g.ELw * 32) + ((ent >> 11) & 4095u);
+    o.back = (ent >> 26) & 15u;
     return true;
 }
 
 LUF_DEV uint32_t sf_growth(const SfShot& s, uint32_t e) { return (s.growth[e >> 4] >> ((e & 15u) * 2u)) & 3u; }
+
+// Access mask and pointer of node v share one 16-bit word.  Lanes other than the owner set access
+// bits (the far end of an edge that just became fully grown), so every update made in a phase with
+// such writers goes through a 32-bit atomic OR on the containing pair of nodes.
+LUF_DEV uint32_t sf_ptr(const SfShot& s, int v) { return (uint32_t)s.acp[v] >> 12; }
+LUF_DEV uint32_t sf_access(const SfShot& s, int v) { return (uint32_t)s.acp[v] & 0xFFFu; }
+LUF_DEV void sf_set_ptr(const SfShot& s, int v, uint32_t ptr) { s.acp[v] = (uint16_t)((s.acp[v] & 0xFFFu) | (ptr << 12)); }
+LUF_DEV void sf_or_acp(const SfShot& s, int v, uint32_t bits)
+{
+#if defined(LUF_HOST_EMU)
+    s.acp[v] = (uint16_t)(s.acp[v] | bits);         // lanes run one after the other
+#else
+    luf_atomic_or((uint32_t*)(s.acp + (v & ~1)), bits << (16 * (v & 1)));
+#endif
+}
 
 // Snowflake.reset + Frugal.reset (snowflake/main.py:201-214,1011-1031,1489-1496; _schemes.py:498-502)
 LUF_DEV void sf_reset(const SfView& g, const SfShot& s, int lane, int nl)
@@ -116,7 +132,7 @@ LUF_DEV void sf_reset(const SfView& g, const SfShot& s, int lane, int nl)
             const int v = r * g.NL + q;
             const uint32_t id = sf_id(g, r, q);
             s.cid[v] = (uint16_t)id; s.ncid[v] = (uint16_t)id;
-            s.fl[v] = (uint16_t)SF_WHOLE; s.ptr[v] = (uint8_t)SF_PTR_C;
+            s.fl[v] = (uint16_t)SF_WHOLE; s.acp[v] = (uint16_t)(SF_PTR_C << 12);
         }
     for (int w = lane; w < g.h * g.WLn; w += nl) { s.ndef[w] = 0; s.awake[w] = 0; }
     for (int w = lane; w < g.h * 2 * g.ELw; w += nl) s.growth[w] = 0;
@@ -303,13 +319,13 @@ LUF_DEV void sf_drop(const SfView& g, const SfShot& s, int lane, int nl)
             if (f & SF_ACTIVE) f |= SF_N_ACTIVE;
             s.fl[v] = (uint16_t)f;
             s.cid[v] = (uint16_t)c; s.ncid[v] = (uint16_t)c;
-            s.ptr[v] = s.ptr[u];
+            s.acp[v] = s.acp[u];
         }
         // top sheet: TopSheetFriendship (:1201-1211); next_cid / next_pointer / next_whole keep their values
         const uint32_t syn = (q >= g.NLb) ? (s.top[q >> 5] >> (q & 31)) & 1u : 0u;
         s.fl[q] = (uint16_t)(SF_WHOLE | (syn ? SF_DEFECT : 0));
         s.cid[q] = s.ncid[q];
-        s.ptr[q] = (uint8_t)SF_PTR_C;
+        s.acp[q] = (uint16_t)(SF_PTR_C << 12);
     }
     // next_defect == defect for every node before a drop (r.next_defect = node.defect, :1195),
     // so it shifts like everything else; the top sheet receives the new syndrome (:312-322)
@@ -388,6 +404,8 @@ LUF_DEV void sf_grow_node(const SfView& g, const SfShot& s, int r, int q)
         else if (old == G_HALF) {                                  // newly FULL: both ends have access from now on
             luf_atomic_or(&s.awake[r * g.WLn + (q >> 5)], 1u << (q & 31));
             luf_atomic_or(&s.awake[nb.r2 * g.WLn + (nb.q2 >> 5)], 1u << (nb.q2 & 31));
+            sf_or_acp(s, r * g.NL + q, 1u << k);
+            if (nb.back != 15u) sf_or_acp(s, nb.node, 1u << nb.back);
         }
     }
 }
@@ -407,9 +425,9 @@ LUF_DEV void sf_grow(const SfView& g, const SfShot& s, int mode, int lane, int n
                 if (mode == 1) f |= SF_GROWN | SF_N_GROWN;
             }
             if (r == g.h - 1) {                                   // bottom sheet: a downward pointer is broken
-                const uint32_t p = s.ptr[v];
+                const uint32_t p = sf_ptr(s, v);
                 if (p != SF_PTR_C && ((LUF_LDG(&g.nbr[q * g.K + p]) >> 23) & 3u) == 0u) {
-                    s.cid[v] = (uint16_t)SF_RESET; s.ptr[v] = (uint8_t)SF_PTR_C;
+                    s.cid[v] = (uint16_t)SF_RESET; sf_or_acp(s, v, SF_PTR_C << 12);     // C = all ones
                 }
             }
         }
@@ -427,9 +445,10 @@ LUF_DEV void sf_flooding(const SfView& g, const SfShot& s, int r, int q, int v, 
         s.ncid[v] = (uint16_t)sf_id(g, r, q);
         return;
     }
-    for (int k = 0; k < g.K; ++k) {
+    for (uint32_t slots = sf_access(s, v); slots; slots &= slots - 1u) {     // ascending slot = the scan order
+        const int k = luf_ffs(slots) - 1;
         SfNbr nb;
-        if (!sf_nbr(g, r, q, k, nb) || sf_growth(s, nb.e) != G_FULL) continue;
+        if (!sf_nbr(g, r, q, k, nb)) continue;                        // the far end left the window
         const uint32_t c = s.cid[nb.node];
         if (whole && c == SF_RESET) {
             if (!(f & SF_UNROOTED)) { f |= SF_BUSY; ncid = SF_RESET; ptr = SF_PTR_C; break; }
@@ -466,10 +485,10 @@ LUF_DEV void sf_syncing(const SfView& g, const SfShot& s, int r, int q, int v, u
 LUF_DEV void sf_merge_a(const SfView& g, const SfShot& s, bool whole, bool slow, int lane, int nl)
 {
     sf_for_awake(g, s, lane, nl, [&](int r, int q, int v) {
-        uint32_t f = s.fl[v] & ~(uint32_t)SF_BUSY, ptr = s.ptr[v];
+        uint32_t f = s.fl[v] & ~(uint32_t)SF_BUSY, ptr = sf_ptr(s, v);
         if (slow) { sf_syncing(g, s, r, q, v, f, ptr); sf_flooding(g, s, r, q, v, whole, f, ptr); }
         else { sf_flooding(g, s, r, q, v, whole, f, ptr); sf_syncing(g, s, r, q, v, f, ptr); }
-        s.fl[v] = (uint16_t)f; s.ptr[v] = (uint8_t)ptr;
+        s.fl[v] = (uint16_t)f; sf_set_ptr(s, v, ptr);
     });
 }
 
