@@ -193,20 +193,29 @@ LUF_DEV void sf_pairs_load_block(const SfView& g, const SfShot& s, const uint32_
     }
 }
 
-// lowering of the kept pairs by one layer (_pairs.py:82-111).  One lane.
-LUF_DEV void sf_pairs_lower(const SfView& g, const SfShot& s)
+// lowering of the kept pairs by one layer (_pairs.py:82-111), two phases over the detectors of a
+// layer.  (a) strings that end in the committed layer 0 are final: both ends in layer 0 -> gone,
+// other end in layer 1 -> that end can no longer be extended (DEAD); every layer-0 key is
+// cleared by the lane that owns it, a layer-1 key is written only by its partner's lane.
+LUF_DEV void sf_pairs_retire(const SfView& g, const SfShot& s, int lane, int nl)
 {
     const int NL = g.NL;
-    for (int q = g.NLb; q < NL; ++q) {
+    for (int q = g.NLb + lane; q < NL; q += nl) {
         const int p = s.partner[q];
         if (p == SFP_NONE) continue;
         s.partner[q] = (int16_t)SFP_NONE;
-        if (p >= 0) s.partner[p] = (int16_t)SFP_DEAD;
+        if (p >= NL) s.partner[p] = (int16_t)SFP_DEAD;
     }
-    for (int q = g.NLb; q < NL; ++q) {
+}
+
+// (b) the keys of layer 1 move down to layer 0
+LUF_DEV void sf_pairs_lower(const SfView& g, const SfShot& s, int lane, int nl)
+{
+    const int NL = g.NL;
+    for (int q = g.NLb + lane; q < NL; q += nl) {
         const int p = s.partner[NL + q];
-        s.partner[NL + q] = (int16_t)SFP_NONE;
         if (p == SFP_NONE) continue;
+        s.partner[NL + q] = (int16_t)SFP_NONE;
         s.partner[q] = (int16_t)(p >= NL ? p - NL : p);
     }
 }
@@ -538,8 +547,13 @@ LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t
     (void)lane;
     rt_all = 0; rt_unr = 0;
     // floor corrections to Pairs (FloorContact.drop), then the window moves
-    LUF_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.corr + (g.h - 1) * g.ELw, m);
-              if (floor_out) for (int c = lane; c < g.ELw; c += nl) floor_out[c] = s.corr[(g.h - 1) * g.ELw + c]);
+    uint32_t any_corr = 0;
+    LUF_PHASE(for (int c = lane; c < g.ELw; c += nl) {
+                  const uint32_t x = s.corr[(g.h - 1) * g.ELw + c];
+                  any_corr |= x;
+                  if (floor_out) floor_out[c] = x;
+              });
+    if (LUF_ANY(any_corr)) { LUF_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.corr + (g.h - 1) * g.ELw, m)); }
     LUF_PHASE(sf_drop(g, s, lane, nl));
     LUF_SF_REGATHER();                               // the window moved
     if (one_one) {
@@ -554,14 +568,17 @@ LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t
         LUF_SF_REGATHER();
         sf_merge(g, s, false, slow, rt_all, rt_unr, lane, nl);
     }
-    LUF_PHASE(if (lane == 0) sf_pairs_lower(g, s));
+    LUF_PHASE(sf_pairs_retire(g, s, lane, nl));
+    LUF_PHASE(sf_pairs_lower(g, s, lane, nl));
 }
 
 // Frugal._raise_window's Pairs half: floor errors in ascending edge id (one lane), then shift.
 LUF_DEV void sf_cycle_head(const SfView& g, const SfShot& s, int& m, int lane, int nl)
 {
     (void)lane;
-    LUF_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.err + (g.h - 1) * g.ELw, m));
+    uint32_t any_err = 0;
+    LUF_PHASE(for (int c = lane; c < g.ELw; c += nl) any_err |= s.err[(g.h - 1) * g.ELw + c]);
+    if (LUF_ANY(any_err)) { LUF_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.err + (g.h - 1) * g.ELw, m)); }
     LUF_PHASE(sf_shift_errors(g, s, lane, nl));
     LUF_PHASE(sf_begin_sheet(g, s, lane, nl));
 }

@@ -60,3 +60,34 @@ def test_emu_sf_bitmap_sweep_with_tiny_awake_list():
             np.testing.assert_array_equal(m, arr['m_cycle'])
     finally:
         emu_binding.use_tiny_lists(False)
+
+
+@pytest.mark.parametrize('spec,p,flags,nstreams,ncycles', [
+    (dict(code='Repetition', d=7, noise='phenomenological', kwargs=dict(scheme='frugal')), 0.08, 0, 40, 60),
+    (dict(code='Surface', d=5, noise='phenomenological', kwargs=dict(scheme='frugal')), 0.03, 0, 30, 40),
+    (dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='frugal')), 0.012, 0, 30, 40),
+    (dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='frugal')), 0.03, 3, 20, 40),
+    (dict(code='Surface', d=7, noise='circuit-level', kwargs=dict(scheme='frugal')), 0.008, 0, 10, 45),
+])
+def test_emu_sf_streams_vs_oracle_on_random_errors(spec, p, flags, nstreams, ncycles):
+    """Seeded host errors, dense enough that clusters merge, unroot and leave through the floor
+    while others are still growing: per-cycle runtimes, floor corrections and logical counts of
+    the kernel phases equal the C oracle's on every stream."""
+    code = make_code(spec)
+    emu = emu_binding.EmuStream(code)
+    t = emu.tables
+    orc = binding.StreamOracle(t, merger='slow' if flags & 1 else 'fast', schedule='1:1' if flags & 2 else '2:1')
+    rng = np.random.default_rng(77)
+    probs = np.array(code.NOISE.class_probabilities(p))[t.edge_class]
+    flips = rng.random((nstreams, ncycles, t.EL)) < probs
+    flips[:, -2 * t.h:, :] = False
+    pad = np.zeros((nstreams, ncycles, 32 * emu.W), np.uint8)
+    pad[:, :, :t.EL] = flips
+    fresh = np.packbits(pad, axis=2, bitorder='little').view(np.uint32)
+    for k in range(nstreams):
+        rt, floor, m = emu.stream(flags, fresh[k])
+        o_all, o_unr, o_floor, o_m = orc.stream(fresh[k])
+        np.testing.assert_array_equal(rt[:, 0], o_all, err_msg=f'stream {k}')
+        np.testing.assert_array_equal(rt[:, 1], o_unr, err_msg=f'stream {k}')
+        np.testing.assert_array_equal(floor, o_floor, err_msg=f'stream {k}')
+        np.testing.assert_array_equal(m, o_m, err_msg=f'stream {k}')
