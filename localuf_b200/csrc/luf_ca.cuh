@@ -23,7 +23,7 @@ enum { ST_GROWING = 0, ST_MERGING = 1, ST_PRESYNCING = 2, ST_SYNCING = 3, ST_BUR
 enum { FL_DEFECT = 1, FL_ACTIVE = 2, FL_ANYON = 4, FL_BUSY = 8, FL_SEEN_ANYON = 16, FL_SEEN_DEFECT = 32 };
 // Actis byte: stage (bits 0-1), next_stage (2-3), busy_signal (4), active_signal (5), own next_active_signal (6)
 enum { AS_BUSY_SIG = 16, AS_ACTIVE_SIG = 32, AS_OWN_NAS = 64 };
-static const uint32_t PTR_C = 0xFFu;
+static const uint32_t PTR_C = 0xFu;          // pointer 'C' (no neighbour) in the 4-bit pointer field
 static const uint32_t NBR_NONE = 0xFFFFFFFFu;
 enum { FLAG_ACTIS_UNOPTIMAL = 4 };
 #ifndef LUF_CA_TLIST_CAP
@@ -43,8 +43,10 @@ struct CaView {
 
 struct CaLayout {
     uint32_t cid, ncid;         // u16[N]
-    uint32_t ptr, fl, ast, cnt; // u8[N]   (ast, cnt only for Actis)
-    uint32_t growth, gacc;      // u32[GW] live growth / snapshot at the last update_access (luf/main.py:434-440)
+    uint32_t acp;               // u16[N]  bits 0..11: the slots whose edge was fully grown at the last update_access
+                                //         (luf/main.py:434-440; what the node may look through); bits 12..15: pointer
+    uint32_t fl, ast, cnt;      // u8[N]   (ast, cnt only for Actis)
+    uint32_t growth;            // u32[GW] live growth
     uint32_t rx_anyon, rx_defect;   // u32[WN] cumulative toggles received from neighbours
     uint32_t rx_busy, rx_active;    // u32[2*WN] Actis signals received, double-buffered by timestep parity
     uint32_t defect, err, corr; // u32[WD] / u32[WE] / u32[WE]
@@ -56,8 +58,9 @@ struct CaLayout {
 
 struct CaShot {
     uint16_t *cid, *ncid;
-    uint8_t *ptr, *fl, *ast, *cnt;
-    uint32_t *growth, *gacc, *rx_anyon, *rx_defect, *rx_busy, *rx_active, *defect, *err, *corr, *glob, *touched;
+    uint16_t* acp;
+    uint8_t *fl, *ast, *cnt;
+    uint32_t *growth, *rx_anyon, *rx_defect, *rx_busy, *rx_active, *defect, *err, *corr, *glob, *touched;
     uint16_t* tlist;
 };
 
@@ -65,8 +68,8 @@ LUF_DEV CaShot ca_bind(const CaLayout& l, unsigned char* b)
 {
     CaShot s;
     s.cid = (uint16_t*)(b + l.cid); s.ncid = (uint16_t*)(b + l.ncid);
-    s.ptr = b + l.ptr; s.fl = b + l.fl; s.ast = b + l.ast; s.cnt = b + l.cnt;
-    s.growth = (uint32_t*)(b + l.growth); s.gacc = (uint32_t*)(b + l.gacc);
+    s.acp = (uint16_t*)(b + l.acp); s.fl = b + l.fl; s.ast = b + l.ast; s.cnt = b + l.cnt;
+    s.growth = (uint32_t*)(b + l.growth);
     s.rx_anyon = (uint32_t*)(b + l.rx_anyon); s.rx_defect = (uint32_t*)(b + l.rx_defect);
     s.rx_busy = (uint32_t*)(b + l.rx_busy); s.rx_active = (uint32_t*)(b + l.rx_active);
     s.defect = (uint32_t*)(b + l.defect);
@@ -88,6 +91,9 @@ struct CaCtl {
 static const int CA_MAX_STEPS = 1 << 20;    // safety net: a shot that runs this long is reported with steps = -1
 
 LUF_DEV uint32_t g2(const uint32_t* a, uint32_t e) { return (a[e >> 4] >> ((e & 15u) * 2u)) & 3u; }
+// access mask | pointer << 12; written by the node's own lane only
+LUF_DEV uint32_t ca_ptr(const CaShot& s, int v) { return (uint32_t)s.acp[v] >> 12; }
+LUF_DEV uint32_t ca_access(const CaShot& s, int v) { return (uint32_t)s.acp[v] & 0xFFFu; }
 
 // LUF.reset / _Node.reset / ActisNode.reset (luf/main.py:173-180,799-809,1004-1012)
 template <bool ACTIS>
@@ -95,10 +101,10 @@ LUF_DEV void ca_reset(const CaView& g, const CaShot& s, int lane, int nl)
 {
     for (int v = lane; v < g.N; v += nl) {
         s.cid[v] = (uint16_t)v; s.ncid[v] = (uint16_t)v;          // dense ids: node index == index_to_id
-        s.ptr[v] = (uint8_t)PTR_C; s.fl[v] = 0;
+        s.acp[v] = (uint16_t)(PTR_C << 12); s.fl[v] = 0;
         if (ACTIS) { s.ast[v] = 0; s.cnt[v] = 0; }
     }
-    for (int w = lane; w < g.GW; w += nl) { s.growth[w] = 0; s.gacc[w] = 0; }
+    for (int w = lane; w < g.GW; w += nl) s.growth[w] = 0;
     for (int w = lane; w < g.WN; w += nl) {
         s.rx_anyon[w] = 0; s.rx_defect[w] = 0; s.touched[w] = 0;
         if (ACTIS) { s.rx_busy[w] = 0; s.rx_busy[g.WN + w] = 0; s.rx_active[w] = 0; s.rx_active[g.WN + w] = 0; }
@@ -186,7 +192,8 @@ LUF_DEV void ca_gather_touched(const CaView& g, const CaShot& s, int lane, int n
 // _Node.merging, luf/main.py:839-854.  Returns busy.
 LUF_DEV uint32_t ca_merging(const CaView& g, const CaShot& s, int v)
 {
-    uint32_t fl = s.fl[v] & ~(uint32_t)FL_BUSY, ptr = s.ptr[v], busy = 0;
+    const uint32_t access = ca_access(s, v);
+    uint32_t fl = s.fl[v] & ~(uint32_t)FL_BUSY, ptr = ca_ptr(s, v), busy = 0;
     if (v >= g.B && ptr != PTR_C && (fl & FL_ANYON)) {             // relay the anyon along the pointer
         busy = 1;
         const uint32_t to = LUF_LDG(&g.nbr[v * g.K + ptr]) >> 16;
@@ -194,13 +201,12 @@ LUF_DEV uint32_t ca_merging(const CaView& g, const CaShot& s, int v)
         fl &= ~(uint32_t)FL_ANYON;
     }
     uint32_t best = s.ncid[v];
-    for (int k = 0; k < g.K; ++k) {
-        const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
-        if (ent == NBR_NONE || g2(s.gacc, ent & 0xFFFFu) != G_FULL) continue;
-        const uint32_t c = s.cid[ent >> 16];
+    for (uint32_t slots = access; slots; slots &= slots - 1u) {      // ascending slot = the scan order
+        const int k = luf_ffs(slots) - 1;
+        const uint32_t c = s.cid[LUF_LDG(&g.nbr[v * g.K + k]) >> 16];
         if (c < best) { best = c; ptr = (uint32_t)k; busy = 1; }
     }
-    s.ncid[v] = (uint16_t)best; s.ptr[v] = (uint8_t)ptr;
+    s.ncid[v] = (uint16_t)best; s.acp[v] = (uint16_t)(access | (ptr << 12));
     s.fl[v] = (uint8_t)(fl | (busy ? FL_BUSY : 0));
     return busy;
 }
@@ -209,7 +215,7 @@ LUF_DEV uint32_t ca_merging(const CaView& g, const CaShot& s, int v)
 LUF_DEV uint32_t ca_presyncing(const CaView& g, const CaShot& s, int v)
 {
     const uint32_t fl = s.fl[v];
-    const uint32_t act = (v >= g.B && s.ptr[v] == PTR_C && (fl & FL_ANYON)) ? 1u : 0u;
+    const uint32_t act = (v >= g.B && ca_ptr(s, v) == PTR_C && (fl & FL_ANYON)) ? 1u : 0u;
     s.fl[v] = (uint8_t)((fl & ~(uint32_t)FL_ACTIVE) | (act ? FL_ACTIVE : 0));
     return act;
 }
@@ -220,9 +226,8 @@ LUF_DEV uint32_t ca_syncing(const CaView& g, const CaShot& s, int v)
     const uint32_t fl = s.fl[v] & ~(uint32_t)FL_BUSY;
     uint32_t busy = 0;
     if (!(fl & FL_ACTIVE))
-        for (int k = 0; k < g.K; ++k) {
-            const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
-            if (ent == NBR_NONE || g2(s.gacc, ent & 0xFFFFu) != G_FULL) continue;
+        for (uint32_t slots = ca_access(s, v); slots; slots &= slots - 1u) {
+            const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + luf_ffs(slots) - 1]);
             if (s.fl[ent >> 16] & FL_ACTIVE) { busy = 1; break; }
         }
     s.fl[v] = (uint8_t)(fl | (busy ? FL_BUSY : 0));
@@ -232,12 +237,12 @@ LUF_DEV uint32_t ca_syncing(const CaView& g, const CaShot& s, int v)
 // _Node.burning, luf/main.py:890-899; OPPOSITE[slot k] = slot K-1-k
 LUF_DEV void ca_burning(const CaView& g, const CaShot& s, int v)
 {
-    const uint32_t ptr = s.ptr[v];
+    const uint32_t ptr = ca_ptr(s, v);
     for (int k = g.K >> 1; k < g.K; ++k) {                          // owned edges
         const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
         if (ent == NBR_NONE) continue;
         const uint32_t e = ent & 0xFFFFu;
-        if (g2(s.growth, e) == G_FULL && ptr != (uint32_t)k && s.ptr[ent >> 16] != (uint32_t)(g.K - 1 - k))
+        if (g2(s.growth, e) == G_FULL && ptr != (uint32_t)k && ca_ptr(s, (int)(ent >> 16)) != (uint32_t)(g.K - 1 - k))
             luf_atomic_and(&s.growth[e >> 4], ~(3u << ((e & 15u) * 2u)));
     }
 }
@@ -247,14 +252,10 @@ LUF_DEV uint32_t ca_peeling(const CaView& g, const CaShot& s, int v)
 {
     uint32_t fl = s.fl[v] & ~(uint32_t)FL_BUSY;
     uint32_t out = 0;
-    if (s.ptr[v] != PTR_C) {
-        uint32_t n_access = 0, only = 0;
-        for (int k = 0; k < g.K; ++k) {
-            const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
-            if (ent == NBR_NONE || g2(s.gacc, ent & 0xFFFFu) != G_FULL) continue;
-            ++n_access; only = ent;
-        }
-        if (n_access == 1) {
+    if (ca_ptr(s, v) != PTR_C) {
+        const uint32_t access = ca_access(s, v);
+        if (access && !(access & (access - 1u))) {                  // exactly one way out: a leaf
+            const uint32_t only = LUF_LDG(&g.nbr[v * g.K + luf_ffs(access) - 1]);
             const uint32_t e = only & 0xFFFFu, to = only >> 16;
             fl |= FL_BUSY; out = 1;
             luf_atomic_and(&s.growth[e >> 4], ~(3u << ((e & 15u) * 2u)));
@@ -338,10 +339,19 @@ LUF_DEV uint32_t macar_phase_b(const CaView& g, const CaShot& s, int stage, int 
     return acc;
 }
 
-// Nodes.update_access, luf/main.py:434-440: snapshot the growth the nodes may look through
+// Nodes.update_access, luf/main.py:434-440: every node records which of its edges are fully grown
+// now; until the next update that is what it looks through.  (Macar: an untouched node has none.)
+template <bool ACTIS>
 LUF_DEV void ca_snapshot_access(const CaView& g, const CaShot& s, int lane, int nl)
 {
-    for (int w = lane; w < g.GW; w += nl) s.gacc[w] = s.growth[w];
+    ca_for_nodes<!ACTIS>(g, s, lane, nl, [&](int v) {
+        uint32_t access = 0;
+        for (int k = 0; k < g.K; ++k) {
+            const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
+            if (ent != NBR_NONE && g2(s.growth, ent & 0xFFFFu) == G_FULL) access |= 1u << k;
+        }
+        s.acp[v] = (uint16_t)((s.acp[v] & 0xF000u) | access);
+    });
 }
 
 // ---------------------------------------------------------------- Actis step
@@ -462,11 +472,12 @@ LUF_DEV uint32_t ca_decode(const CaView& g, const CaShot& s, int flags, int* t_s
             LUF_PHASE(acc |= macar_phase_b(g, s, c.stage, lane, nl));
             busy = LUF_ANY(acc & 1u); valid = !LUF_ANY(acc & 2u);
         }
-        if (ca_controller_advance(c, busy, valid)) { LUF_PHASE(ca_snapshot_access(g, s, lane, nl)); }
+        const int growth_changed = ca_controller_advance(c, busy, valid);
         if (grew) {                                                      // newly touched nodes join the list
             LUF_PHASE(if (lane == 0) s.glob[2] = 0);
             LUF_PHASE(ca_gather_touched(g, s, lane, nl));
         }
+        if (growth_changed) { LUF_PHASE(ca_snapshot_access<ACTIS>(g, s, lane, nl)); }
         c.step += 1;
         if (in_sv) ++tsv; else ++tbp;
         if (tsv + tbp >= CA_MAX_STEPS) { tsv = -1; tbp = -1; break; }

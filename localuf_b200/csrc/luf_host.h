@@ -138,7 +138,7 @@ struct PackedCa {
 inline std::string pack_ca(const luf_graph_desc& d, PackedCa& out)
 {
     const int N = d.n_nodes, K = d.n_dirs;
-    if (K < 2 || K > 16 || (K & 1)) return "neighbour table width must be even and at most 16";
+    if (K < 2 || K > 12 || (K & 1)) return "neighbour table width must be even and at most 12";
     if (N > 0xFFFE || d.n_edges > 0xFFFE) return "graph too large for the 16-bit cellular-automaton layout";
     out.N = N; out.B = d.n_boundary; out.E = d.n_edges; out.K = K; out.global_span = d.actis_global_span;
     out.nbr.assign((size_t)N * K, NBR_NONE);
@@ -169,9 +169,9 @@ inline CaLayout make_ca_layout(int N, int B, int E, bool actis, bool keep_err)
     auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
     const uint32_t WE = words32(E), WD = words32(N - B) ? words32(N - B) : 1, WN = words32(N), GW = (E + 15) / 16;
     l.cid = take(2u * N); l.ncid = take(2u * N);
-    l.ptr = take(N); l.fl = take(N);
+    l.acp = take(2u * N); l.fl = take(N);
     l.ast = actis ? take(N) : 0; l.cnt = actis ? take(N) : 0;
-    l.growth = take(4u * GW); l.gacc = take(4u * GW);
+    l.growth = take(4u * GW);
     l.rx_anyon = take(4u * WN); l.rx_defect = take(4u * WN);
     l.rx_busy = actis ? take(8u * WN) : 0; l.rx_active = actis ? take(8u * WN) : 0;
     l.defect = take(4u * WD);
