@@ -297,7 +297,7 @@ inline std::string pack_window(const luf_window_desc& d, PackedWindow& out)
     return "";
 }
 
-inline SfLayout make_sf_layout(const PackedWindow& p)
+inline SfLayout make_sf_layout(const PackedWindow& p, uint32_t alist_cap = SF_ALIST_CAP)
 {
     SfLayout l;
     uint32_t off = 0;
@@ -309,7 +309,8 @@ inline SfLayout make_sf_layout(const PackedWindow& p)
     l.corr = take(4u * p.h * ELw); l.err = take(4u * p.h * ELw);
     l.top = take(4u * WLn); l.fb = take(4u * WLn);
     l.partner = take(2u * 2u * p.NL);
-    l.alist = take(2u * SF_ALIST_CAP); l.acnt = take(16);
+    l.alist_cap = alist_cap;
+    l.alist = take(2u * alist_cap); l.acnt = take(16);
     l.bytes = off;
     return l;
 }

@@ -312,6 +312,47 @@ __global__ void k_sf_mc(SfView g, SfLayout l, SampleParams sp, int flags, unsign
     }
 }
 
+// The same two kernels with one thread block per window (luf::sf_cta): large windows.
+__global__ void k_sf_decode_cta(SfView g, SfLayout l, int flags, long long nstreams, int ncycles,
+                                const uint32_t* __restrict__ fresh, int32_t* __restrict__ rt,
+                                uint32_t* __restrict__ floor_bits, int32_t* __restrict__ m_out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
+    const SfShot s = sf_bind(l, smem);
+    for (long long k = blockIdx.x; k < nstreams; k += gridDim.x) {
+        sf_reset(g, s, lane, nl);
+        __syncthreads();
+        for (int c = 0; c < ncycles; ++c) {
+            const size_t row = (size_t)k * ncycles + c;
+            int m = 0, ra = 0, ru = 0;
+            sf_cta::sf_cycle_head(g, s, m, lane, nl);
+            if (flags & SF_FLAG_SYNDROME) sf_given_syndrome(g, s, fresh + row * g.ELw, lane, nl);
+            else sf_given_sheet(g, s, fresh + row * g.ELw, lane, nl);
+            __syncthreads();
+            sf_cta::sf_cycle_tail(g, s, flags, floor_bits ? floor_bits + row * g.ELw : nullptr, m, ra, ru, lane, nl);
+            if (lane == 0) { rt[2 * row] = ra; rt[2 * row + 1] = ru; m_out[row] = m; }
+        }
+    }
+}
+
+__global__ void k_sf_mc_cta(SfView g, SfLayout l, SampleParams sp, int flags, unsigned long long stream0,
+                            long long nstreams, int n, unsigned long long* counts, int32_t* steps)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
+    const SfShot s = sf_bind(l, smem);
+    int m_total = 0;
+    long long cycles = 0, ra = 0, ru = 0;
+    for (long long k = blockIdx.x; k < nstreams; k += gridDim.x)
+        sf_cta::sf_run(g, s, sp, flags, stream0 + (unsigned long long)k, n, m_total, cycles, ra, ru,
+                       steps ? steps + (size_t)k * n * 2 : nullptr, lane, nl);
+    if (lane == 0) {
+        atomicAdd(&counts[0], (unsigned long long)m_total); atomicAdd(&counts[1], (unsigned long long)cycles);
+        atomicAdd(&counts[2], (unsigned long long)ra); atomicAdd(&counts[3], (unsigned long long)ru);
+    }
+}
+
 // Staged K1: bit-packed errors and syndromes to HBM
 // (noise/main.py:114-115,309-314; _base_classes.py:427-450).
 __global__ void k_sample(GraphView g, Layout l, SampleParams sp, unsigned long long shot0,
@@ -541,7 +582,7 @@ struct luf_stream {
     int device = 0, sm_count = 0, max_smem = 0;
     PackedWindow host;
     SfView view{};
-    SfLayout lay{};
+    SfLayout lay{}, lay_cta{};        // one warp / one thread block per window
     std::vector<void*> allocs;
     void* scratch[5] = {0, 0, 0, 0, 0};
     size_t scratch_bytes[5] = {0, 0, 0, 0, 0};
@@ -596,6 +637,43 @@ static int plan_stream_launch(luf_stream* g, K kernel, long long nstreams, Launc
     return 0;
 }
 
+// One thread block per window: the block size that keeps the most threads resident.
+template <class K>
+static int plan_stream_cta_launch(luf_stream* g, K kernel, long long nstreams, LaunchCfg* cfg)
+{
+    const uint32_t bytes = g->lay_cta.bytes;
+    if (bytes > (uint32_t)g->max_smem)
+        return fail(LUF_ERR_UNSUPPORTED, "one window's decoder state (" + std::to_string(bytes) +
+                    " B) exceeds the shared memory of an SM");
+    static const int env_threads = getenv("LUF_SF_CTA_THREADS") ? atoi(getenv("LUF_SF_CTA_THREADS")) : 0;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int best = 0, threads = 0, per_sm = 0;
+    for (int cand = 256; cand >= 64; cand -= 32) {
+        if (env_threads > 0 && cand != env_threads) continue;
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, cand, bytes));
+        if (occ * cand > best) { best = occ * cand; threads = cand; per_sm = occ; }       // ties: larger blocks
+    }
+    if (best == 0) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    long long blocks = (long long)g->sm_count * per_sm;
+    if (blocks > nstreams) blocks = nstreams;
+    if (blocks < 1) blocks = 1;
+    cfg->grid = (int)blocks; cfg->block = threads; cfg->smem = bytes;
+    return 0;
+}
+
+// Warp tiles while a window's state leaves at least 16 warps per SM, else one block per window
+// (LUF_SF_TILE=warp|cta overrides, for measurements and tests).
+static bool use_stream_cta(const luf_stream* g)
+{
+    const char* env = getenv("LUF_SF_TILE");
+    if (g->lay_cta.bytes > (uint32_t)g->max_smem) return false;
+    if (env && !strcmp(env, "warp")) return false;
+    if (env && !strcmp(env, "cta")) return true;
+    return (size_t)16 * g->lay.bytes > (size_t)g->max_smem;
+}
+
 extern "C" {
 
 int luf_stream_create(const luf_window_desc* desc, int device, luf_stream** out)
@@ -627,6 +705,24 @@ int luf_stream_create(const luf_window_desc* desc, int device, luf_stream** out)
         return rc;
     }
     g->lay = make_sf_layout(p);
+    // block tiles: the awake-node list takes whatever shared memory the windows resident on an SM leave over
+    {
+        int sm_smem = 0;
+        cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+        const uint32_t min_cap = SF_CTA_ALIST_CAP < 256u ? SF_CTA_ALIST_CAP : 256u;
+        const uint32_t base = make_sf_layout(p, min_cap).bytes + 1024u;       // + the per-block reservation
+        uint32_t cap = SF_CTA_ALIST_CAP;
+        if (SF_CTA_ALIST_CAP >= 256u && base <= (uint32_t)sm_smem) {           // (test builds keep their tiny list)
+            const uint32_t blocks = (uint32_t)sm_smem / base;
+            uint32_t budget = (uint32_t)sm_smem / blocks - 1024u;
+            if (budget > (uint32_t)g->max_smem) budget = (uint32_t)g->max_smem;
+            cap = min_cap + (budget - (base - 1024u)) / 2u;
+            cap &= ~7u;
+            if (cap > (uint32_t)v.N) cap = ((uint32_t)v.N + 7u) & ~7u;
+            if (cap > 16384u) cap = 16384u;
+        }
+        g->lay_cta = make_sf_layout(p, cap);
+    }
     *out = g;
     return 0;
 }
@@ -652,9 +748,15 @@ int luf_stream_decode(luf_stream* g, int flags, int64_t nstreams, int32_t ncycle
     if (nstreams == 0 || ncycles == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
     LaunchCfg c;
-    if (int rc = plan_stream_launch(g, k_sf_decode, nstreams, &c)) return rc;
-    k_sf_decode<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, flags, nstreams, ncycles,
-                                                                    fresh_bits_dev, rt_dev, floor_bits_dev, m_dev);
+    if (use_stream_cta(g)) {
+        if (int rc = plan_stream_cta_launch(g, k_sf_decode_cta, nstreams, &c)) return rc;
+        k_sf_decode_cta<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_cta, flags, nstreams, ncycles,
+                                                                            fresh_bits_dev, rt_dev, floor_bits_dev, m_dev);
+    } else {
+        if (int rc = plan_stream_launch(g, k_sf_decode, nstreams, &c)) return rc;
+        k_sf_decode<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, flags, nstreams, ncycles,
+                                                                        fresh_bits_dev, rt_dev, floor_bits_dev, m_dev);
+    }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;
     return 0;
@@ -670,9 +772,15 @@ int luf_stream_mc(luf_stream* g, int flags, const double* class_p_host, uint64_t
     CUDA_TRY(cudaSetDevice(g->device));
     const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
     LaunchCfg c;
-    if (int rc = plan_stream_launch(g, k_sf_mc, nstreams, &c)) return rc;
-    k_sf_mc<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, sp, flags, stream0, nstreams, n,
-                                                                counts_dev, steps_dev);
+    if (use_stream_cta(g)) {
+        if (int rc = plan_stream_cta_launch(g, k_sf_mc_cta, nstreams, &c)) return rc;
+        k_sf_mc_cta<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_cta, sp, flags, stream0, nstreams, n,
+                                                                        counts_dev, steps_dev);
+    } else {
+        if (int rc = plan_stream_launch(g, k_sf_mc, nstreams, &c)) return rc;
+        k_sf_mc<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, sp, flags, stream0, nstreams, n,
+                                                                    counts_dev, steps_dev);
+    }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;
     return 0;

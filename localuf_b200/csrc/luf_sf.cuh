@@ -46,7 +46,11 @@ struct SfView {
 #ifndef LUF_SF_ALIST_CAP
   #define LUF_SF_ALIST_CAP 384
 #endif
-static const uint32_t SF_ALIST_CAP = LUF_SF_ALIST_CAP;      // tests shrink it to force the bitmap sweep
+static const uint32_t SF_ALIST_CAP = LUF_SF_ALIST_CAP;      // warp tiles; tests shrink it to force the bitmap sweep
+#ifndef LUF_SF_CTA_ALIST_CAP
+  #define LUF_SF_CTA_ALIST_CAP 2048
+#endif
+static const uint32_t SF_CTA_ALIST_CAP = LUF_SF_CTA_ALIST_CAP;   // block tiles (large windows)
 
 struct SfLayout {
     uint32_t cid, ncid;         // u16[N]
@@ -58,7 +62,8 @@ struct SfLayout {
     uint32_t corr, err;         // u32[h*ELw]
     uint32_t top, fb;           // u32[WLn]  this cycle's top-sheet syndrome / defects on the future boundary
     uint32_t partner;           // i16[2*NL]
-    uint32_t alist, acnt;       // u16[SF_ALIST_CAP] the awake nodes, compacted as sheet << 10 | position (rebuilt after
+    uint32_t alist_cap;         // entries of alist (SF_ALIST_CAP for warp tiles, SF_CTA_ALIST_CAP for block tiles)
+    uint32_t alist, acnt;       // u16[alist_cap] the awake nodes, compacted as sheet << 10 | position (rebuilt after
                                 // every drop and grow step); u32[4] its fill
     uint32_t bytes;
 };
@@ -69,6 +74,7 @@ struct SfShot {
     uint32_t *ndef, *awake, *growth, *corr, *err, *top, *fb, *acnt;
     uint16_t* alist;
     int16_t* partner;
+    uint32_t acap;              // capacity of alist
 };
 
 LUF_DEV SfShot sf_bind(const SfLayout& l, unsigned char* b)
@@ -81,6 +87,7 @@ LUF_DEV SfShot sf_bind(const SfLayout& l, unsigned char* b)
     s.corr = (uint32_t*)(b + l.corr); s.err = (uint32_t*)(b + l.err);
     s.top = (uint32_t*)(b + l.top); s.fb = (uint32_t*)(b + l.fb);
     s.partner = (int16_t*)(b + l.partner);
+    s.acap = l.alist_cap;
     return s;
 }
 
@@ -355,7 +362,7 @@ template <class F>
 LUF_DEV void sf_for_awake(const SfView& g, const SfShot& s, int lane, int nl, F&& f)
 {
     const uint32_t total = s.acnt[0];
-    if (total <= SF_ALIST_CAP) {                    // balanced: one awake node per lane and trip
+    if (total <= s.acap) {                          // balanced: one awake node per lane and trip
         for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) {
             const int it = (int)s.alist[i], r = it >> 10, q = it & 1023;
             f(r, q, r * g.NL + q);
@@ -379,7 +386,7 @@ LUF_DEV void sf_for_awake(const SfView& g, const SfShot& s, int lane, int nl, F&
 // Windows taller than 63 sheets keep the bitmap sweep (acnt[0] is then left above the capacity).
 LUF_DEV void sf_gather_awake(const SfView& g, const SfShot& s, int lane, int nl)
 {
-    if (g.h > 63) { if (lane == 0) s.acnt[0] = SF_ALIST_CAP + 1u; return; }
+    if (g.h > 63) { if (lane == 0) s.acnt[0] = s.acap + 1u; return; }
     const int words = g.h * g.WLn;
     const int wpl = (words + nl - 1) / nl;
     const int w0 = lane * wpl, w1 = w0 + wpl < words ? w0 + wpl : words;
@@ -387,7 +394,7 @@ LUF_DEV void sf_gather_awake(const SfView& g, const SfShot& s, int lane, int nl)
     for (int x = w0; x < w1; ++x) c += (uint32_t)luf_popc(s.awake[x]);
     if (!c) return;
     uint32_t pos = luf_atomic_add(&s.acnt[0], c);
-    if (pos + c > SF_ALIST_CAP) return;
+    if (pos + c > s.acap) return;
     for (int x = w0; x < w1; ++x) {
         uint32_t bits = s.awake[x];
         if (!bits) continue;
@@ -398,7 +405,6 @@ LUF_DEV void sf_gather_awake(const SfView& g, const SfShot& s, int lane, int nl)
         }
     }
 }
-#define LUF_SF_REGATHER() { LUF_PHASE(if (lane == 0) s.acnt[0] = 0); LUF_PHASE(sf_gather_awake(g, s, lane, nl)); }
 
 // _Node._grow, snowflake/main.py:1075-1084
 LUF_DEV void sf_grow_node(const SfView& g, const SfShot& s, int r, int q)
@@ -520,99 +526,31 @@ LUF_DEV uint32_t sf_merge_b(const SfView& g, const SfShot& s, int lane, int nl)
     return acc;
 }
 
-// Snowflake.merge (:324-353): adds the 'all' and 'unrooting' runtimes of one merge loop.
-LUF_DEV void sf_merge(const SfView& g, const SfShot& s, bool whole, bool slow, int& rt_all, int& rt_unr, int lane, int nl)
-{
-    (void)lane;
-    rt_all += 1;
-    for (int guard = 0; guard < (1 << 20); ++guard) {
-        LUF_PHASE(sf_merge_a(g, s, whole, slow, lane, nl));
-        uint32_t acc = 0;
-        LUF_PHASE(acc |= sf_merge_b(g, s, lane, nl));
-        rt_all += 1;
-        if (LUF_ANY(acc & 2u)) rt_unr += 1;
-        if (!LUF_ANY(acc & 1u)) break;
-    }
-}
-
-// One decoding cycle after the fresh sheet is in place: Frugal.advance's tail
-// (_schemes.py:524-530) = Snowflake.decode (:216-281), then get_logical_error
-// (_schemes.py:262-276).  `floor_out` (optional, ELw words, global) receives the
-// floor-sheet correction committed by this cycle's drop.  `m` is only
-// meaningful on lane 0 (in the emulation: the single accumulated value).
-LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t* floor_out,
-                           int& m, int& rt_all, int& rt_unr, int lane, int nl)
-{
-    const bool slow = flags & SF_FLAG_SLOW, one_one = flags & SF_FLAG_ONE_ONE;
-    (void)lane;
-    rt_all = 0; rt_unr = 0;
-    // floor corrections to Pairs (FloorContact.drop), then the window moves
-    uint32_t any_corr = 0;
-    LUF_PHASE(for (int c = lane; c < g.ELw; c += nl) {
-                  const uint32_t x = s.corr[(g.h - 1) * g.ELw + c];
-                  any_corr |= x;
-                  if (floor_out) floor_out[c] = x;
-              });
-    if (LUF_ANY(any_corr)) { LUF_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.corr + (g.h - 1) * g.ELw, m)); }
-    LUF_PHASE(sf_drop(g, s, lane, nl));
-    LUF_SF_REGATHER();                               // the window moved
-    if (one_one) {
-        LUF_PHASE(sf_grow(g, s, 0, lane, nl));
-        LUF_SF_REGATHER();                           // growth wakes nodes
-        sf_merge(g, s, true, slow, rt_all, rt_unr, lane, nl);
-    } else {
-        LUF_PHASE(sf_grow(g, s, 1, lane, nl));
-        LUF_SF_REGATHER();
-        sf_merge(g, s, true, slow, rt_all, rt_unr, lane, nl);
-        LUF_PHASE(sf_grow(g, s, 2, lane, nl));
-        LUF_SF_REGATHER();
-        sf_merge(g, s, false, slow, rt_all, rt_unr, lane, nl);
-    }
-    LUF_PHASE(sf_pairs_retire(g, s, lane, nl));
-    LUF_PHASE(sf_pairs_lower(g, s, lane, nl));
-}
-
-// Frugal._raise_window's Pairs half: floor errors in ascending edge id (one lane), then shift.
-LUF_DEV void sf_cycle_head(const SfView& g, const SfShot& s, int& m, int lane, int nl)
-{
-    (void)lane;
-    uint32_t any_err = 0;
-    LUF_PHASE(for (int c = lane; c < g.ELw; c += nl) any_err |= s.err[(g.h - 1) * g.ELw + c]);
-    if (LUF_ANY(any_err)) { LUF_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.err + (g.h - 1) * g.ELw, m)); }
-    LUF_PHASE(sf_shift_errors(g, s, lane, nl));
-    LUF_PHASE(sf_begin_sheet(g, s, lane, nl));
-}
-
-// Frugal.run (_schemes.py:566-649) for one stream with device-sampled noise:
-// transient h cycles, n*d timed cycles, d-1 more, one without future-boundary
-// faults, 2h noiseless cleansing cycles.  `steps_out` (optional, [n][2]) gets the
-// 'all' / 'unrooting' runtimes summed over each timed block of d cycles.
-// m / runtimes are meaningful on lane 0.
-LUF_DEV void sf_run(const SfView& g, const SfShot& s, const SampleParams& sp, int flags, uint64_t stream, int n,
-                    int& m_total, long long& cycles, long long& rt_all_timed, long long& rt_unr_timed,
-                    int32_t* steps_out, int lane, int nl)
-{
-    const int d = g.d, h = g.h;
-    const int total = h + n * d + (d - 1) + 1 + 2 * h;
-    LUF_PHASE(sf_reset(g, s, lane, nl));
-    int blk_all = 0, blk_unr = 0;
-    for (int c = 0; c < total; ++c) {
-        const bool cleanse = c >= total - 2 * h, excl = c == total - 2 * h - 1;
-        const bool timed = c >= h && c < h + n * d;
-        int m = 0, ra = 0, ru = 0;
-        sf_cycle_head(g, s, m, lane, nl);
-        if (!cleanse) { LUF_PHASE(sf_sample_sheet(g, s, sp, stream, (uint32_t)c, excl, lane, nl)); }
-        sf_cycle_tail(g, s, flags, nullptr, m, ra, ru, lane, nl);
-        m_total += m;
-        if (timed) {
-            rt_all_timed += ra; rt_unr_timed += ru; blk_all += ra; blk_unr += ru;
-            if ((c - h) % d == d - 1) {
-                if (steps_out && lane == 0) { steps_out[2 * ((c - h) / d)] = blk_all; steps_out[2 * ((c - h) / d) + 1] = blk_unr; }
-                blk_all = 0; blk_unr = 0;
-            }
-        }
-    }
-    cycles += total;
-}
-
 }  // namespace luf
+
+// ------------------------------------------------------------------ drivers
+// The cycle / stream drivers are written against a tile (LUF_ST_PHASE / LUF_ST_ANY) and compiled
+// once per tile shape: luf::sf_warp (one warp per window) and luf::sf_cta (one thread block per
+// window: large windows, whose state leaves room for only a few per SM and whose sweeps visit
+// hundreds of awake nodes).
+#define LUF_SF_NS sf_warp
+#define LUF_ST_PHASE(stmt) LUF_PHASE(stmt)
+#define LUF_ST_ANY(x) LUF_ANY(x)
+#include "luf_sf_drivers.inl"
+#undef LUF_SF_NS
+#undef LUF_ST_PHASE
+#undef LUF_ST_ANY
+namespace luf { using namespace sf_warp; }
+
+#define LUF_SF_NS sf_cta
+#if defined(LUF_HOST_EMU)
+  #define LUF_ST_PHASE(stmt) LUF_PHASE(stmt)
+  #define LUF_ST_ANY(x) LUF_ANY(x)
+#else
+  #define LUF_ST_PHASE(stmt) { stmt; } __syncthreads();
+  #define LUF_ST_ANY(x) __syncthreads_or((x) != 0)
+#endif
+#include "luf_sf_drivers.inl"
+#undef LUF_SF_NS
+#undef LUF_ST_PHASE
+#undef LUF_ST_ANY

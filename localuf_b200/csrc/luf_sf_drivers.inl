@@ -1,0 +1,108 @@
+// luf_sf_drivers.inl -- one decoding cycle / one Frugal.run of Snowflake, written against a tile of
+// nl cooperating lanes; included by luf_sf.cuh once per tile shape (LUF_SF_NS, LUF_ST_PHASE,
+// LUF_ST_ANY).  The per-node rules and the window bookkeeping they call live in luf_sf.cuh.
+namespace luf {
+namespace LUF_SF_NS {
+
+#define LUF_SF_REGATHER() { LUF_ST_PHASE(if (lane == 0) s.acnt[0] = 0); LUF_ST_PHASE(sf_gather_awake(g, s, lane, nl)); }
+
+// Snowflake.merge (:324-353): adds the 'all' and 'unrooting' runtimes of one merge loop.
+LUF_DEV void sf_merge(const SfView& g, const SfShot& s, bool whole, bool slow, int& rt_all, int& rt_unr, int lane, int nl)
+{
+    (void)lane;
+    rt_all += 1;
+    for (int guard = 0; guard < (1 << 20); ++guard) {
+        LUF_ST_PHASE(sf_merge_a(g, s, whole, slow, lane, nl));
+        uint32_t acc = 0;
+        LUF_ST_PHASE(acc |= sf_merge_b(g, s, lane, nl));
+        rt_all += 1;
+        if (LUF_ST_ANY(acc & 2u)) rt_unr += 1;
+        if (!LUF_ST_ANY(acc & 1u)) break;
+    }
+}
+
+// One decoding cycle after the fresh sheet is in place: Frugal.advance's tail
+// (_schemes.py:524-530) = Snowflake.decode (:216-281), then get_logical_error
+// (_schemes.py:262-276).  `floor_out` (optional, ELw words, global) receives the
+// floor-sheet correction committed by this cycle's drop.  `m` is only
+// meaningful on lane 0 (in the emulation: the single accumulated value).
+LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t* floor_out,
+                           int& m, int& rt_all, int& rt_unr, int lane, int nl)
+{
+    const bool slow = flags & SF_FLAG_SLOW, one_one = flags & SF_FLAG_ONE_ONE;
+    (void)lane;
+    rt_all = 0; rt_unr = 0;
+    // floor corrections to Pairs (FloorContact.drop), then the window moves
+    uint32_t any_corr = 0;
+    LUF_ST_PHASE(for (int c = lane; c < g.ELw; c += nl) {
+                  const uint32_t x = s.corr[(g.h - 1) * g.ELw + c];
+                  any_corr |= x;
+                  if (floor_out) floor_out[c] = x;
+              });
+    if (LUF_ST_ANY(any_corr)) { LUF_ST_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.corr + (g.h - 1) * g.ELw, m)); }
+    LUF_ST_PHASE(sf_drop(g, s, lane, nl));
+    LUF_SF_REGATHER();                               // the window moved
+    if (one_one) {
+        LUF_ST_PHASE(sf_grow(g, s, 0, lane, nl));
+        LUF_SF_REGATHER();                           // growth wakes nodes
+        sf_merge(g, s, true, slow, rt_all, rt_unr, lane, nl);
+    } else {
+        LUF_ST_PHASE(sf_grow(g, s, 1, lane, nl));
+        LUF_SF_REGATHER();
+        sf_merge(g, s, true, slow, rt_all, rt_unr, lane, nl);
+        LUF_ST_PHASE(sf_grow(g, s, 2, lane, nl));
+        LUF_SF_REGATHER();
+        sf_merge(g, s, false, slow, rt_all, rt_unr, lane, nl);
+    }
+    LUF_ST_PHASE(sf_pairs_retire(g, s, lane, nl));
+    LUF_ST_PHASE(sf_pairs_lower(g, s, lane, nl));
+}
+
+// Frugal._raise_window's Pairs half: floor errors in ascending edge id (one lane), then shift.
+LUF_DEV void sf_cycle_head(const SfView& g, const SfShot& s, int& m, int lane, int nl)
+{
+    (void)lane;
+    uint32_t any_err = 0;
+    LUF_ST_PHASE(for (int c = lane; c < g.ELw; c += nl) any_err |= s.err[(g.h - 1) * g.ELw + c]);
+    if (LUF_ST_ANY(any_err)) { LUF_ST_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.err + (g.h - 1) * g.ELw, m)); }
+    LUF_ST_PHASE(sf_shift_errors(g, s, lane, nl));
+    LUF_ST_PHASE(sf_begin_sheet(g, s, lane, nl));
+}
+
+// Frugal.run (_schemes.py:566-649) for one stream with device-sampled noise:
+// transient h cycles, n*d timed cycles, d-1 more, one without future-boundary
+// faults, 2h noiseless cleansing cycles.  `steps_out` (optional, [n][2]) gets the
+// 'all' / 'unrooting' runtimes summed over each timed block of d cycles.
+// m / runtimes are meaningful on lane 0.
+LUF_DEV void sf_run(const SfView& g, const SfShot& s, const SampleParams& sp, int flags, uint64_t stream, int n,
+                    int& m_total, long long& cycles, long long& rt_all_timed, long long& rt_unr_timed,
+                    int32_t* steps_out, int lane, int nl)
+{
+    const int d = g.d, h = g.h;
+    const int total = h + n * d + (d - 1) + 1 + 2 * h;
+    LUF_ST_PHASE(sf_reset(g, s, lane, nl));
+    int blk_all = 0, blk_unr = 0;
+    for (int c = 0; c < total; ++c) {
+        const bool cleanse = c >= total - 2 * h, excl = c == total - 2 * h - 1;
+        const bool timed = c >= h && c < h + n * d;
+        int m = 0, ra = 0, ru = 0;
+        sf_cycle_head(g, s, m, lane, nl);
+        // 32 sampling lanes whatever the tile: a stream's noise does not depend on the tile shape
+        if (!cleanse) { LUF_ST_PHASE(if (lane < 32) sf_sample_sheet(g, s, sp, stream, (uint32_t)c, excl, lane, nl < 32 ? nl : 32)); }
+        sf_cycle_tail(g, s, flags, nullptr, m, ra, ru, lane, nl);
+        m_total += m;
+        if (timed) {
+            rt_all_timed += ra; rt_unr_timed += ru; blk_all += ra; blk_unr += ru;
+            if ((c - h) % d == d - 1) {
+                if (steps_out && lane == 0) { steps_out[2 * ((c - h) / d)] = blk_all; steps_out[2 * ((c - h) / d) + 1] = blk_unr; }
+                blk_all = 0; blk_unr = 0;
+            }
+        }
+    }
+    cycles += total;
+}
+
+#undef LUF_SF_REGATHER
+
+}  // namespace LUF_SF_NS
+}  // namespace luf

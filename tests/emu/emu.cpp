@@ -214,9 +214,10 @@ int emu_fw_stream(const luf_graph_desc* gd, const luf_forward_desc* fd, int deco
 }
 
 // Snowflake + frugal bookkeeping on given fresh errors (one stream).
-int emu_sf_stream(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
-                  int32_t* rt, uint32_t* floor_bits, int32_t* m_out)
+int emu_sf_stream_tile(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
+                       int32_t* rt, uint32_t* floor_bits, int32_t* m_out, int nl)
 {
+    const bool cta = nl != 32;
     PackedWindow p;
     if (!pack_window(*d, p).empty()) return -1;
     SfView g;
@@ -224,26 +225,34 @@ int emu_sf_stream(const luf_window_desc* d, int flags, int ncycles, const uint32
     g.ELw = words32(p.EL); g.WLn = words32(p.NL); g.N = p.NL * p.h; g.n_classes = p.n_classes;
     g.nbr = p.nbr.data(); g.edge_ends = p.edge_ends.data(); g.pos_long = p.pos_long.data();
     g.fresh_perm = p.fresh_perm.data(); g.class_end = p.class_end.data();
-    const SfLayout l = make_sf_layout(p);
+    const SfLayout l = cta ? make_sf_layout(p, SF_CTA_ALIST_CAP) : make_sf_layout(p);
     std::vector<unsigned char> mem(l.bytes);
     const SfShot s = sf_bind(l, mem.data());
-    const int nl = 32;
     LUF_PHASE(sf_reset(g, s, lane, nl));
     for (int c = 0; c < ncycles; ++c) {
         int m = 0, ra = 0, ru = 0;
-        sf_cycle_head(g, s, m, 0, nl);
+        if (cta) sf_cta::sf_cycle_head(g, s, m, 0, nl); else sf_warp::sf_cycle_head(g, s, m, 0, nl);
         if (flags & SF_FLAG_SYNDROME) { LUF_PHASE(sf_given_syndrome(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
         else { LUF_PHASE(sf_given_sheet(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
-        sf_cycle_tail(g, s, flags, floor_bits + (size_t)c * g.ELw, m, ra, ru, 0, nl);
+        if (cta) sf_cta::sf_cycle_tail(g, s, flags, floor_bits + (size_t)c * g.ELw, m, ra, ru, 0, nl);
+        else sf_warp::sf_cycle_tail(g, s, flags, floor_bits + (size_t)c * g.ELw, m, ra, ru, 0, nl);
         rt[2 * c] = ra; rt[2 * c + 1] = ru; m_out[c] = m;
     }
     return 0;
 }
 
-// Frugal.run(n) streams with the device sampler (host arithmetic).
-int emu_sf_mc(const luf_window_desc* d, int flags, const double* class_p, unsigned long long seed,
-              unsigned long long stream0, long long nstreams, int n, unsigned long long counts[4], int32_t* steps)
+int emu_sf_stream(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
+                  int32_t* rt, uint32_t* floor_bits, int32_t* m_out)
 {
+    return emu_sf_stream_tile(d, flags, ncycles, fresh, rt, floor_bits, m_out, 32);
+}
+
+// Frugal.run(n) streams with the device sampler (host arithmetic).
+int emu_sf_mc_tile(const luf_window_desc* d, int flags, const double* class_p, unsigned long long seed,
+                   unsigned long long stream0, long long nstreams, int n, unsigned long long counts[4], int32_t* steps,
+                   int nl)
+{
+    const bool cta = nl != 32;
     PackedWindow p;
     if (!pack_window(*d, p).empty()) return -1;
     SfView g;
@@ -251,16 +260,24 @@ int emu_sf_mc(const luf_window_desc* d, int flags, const double* class_p, unsign
     g.ELw = words32(p.EL); g.WLn = words32(p.NL); g.N = p.NL * p.h; g.n_classes = p.n_classes;
     g.nbr = p.nbr.data(); g.edge_ends = p.edge_ends.data(); g.pos_long = p.pos_long.data();
     g.fresh_perm = p.fresh_perm.data(); g.class_end = p.class_end.data();
-    const SfLayout l = make_sf_layout(p);
+    const SfLayout l = cta ? make_sf_layout(p, SF_CTA_ALIST_CAP) : make_sf_layout(p);
     const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
     std::vector<unsigned char> mem(l.bytes);
     const SfShot s = sf_bind(l, mem.data());
     for (long long k = 0; k < nstreams; ++k) {
         int m = 0; long long cyc = 0, ra = 0, ru = 0;
-        sf_run(g, s, sp, flags, stream0 + k, n, m, cyc, ra, ru, steps ? steps + (size_t)k * n * 2 : nullptr, 0, 32);
+        int32_t* st = steps ? steps + (size_t)k * n * 2 : nullptr;
+        if (cta) sf_cta::sf_run(g, s, sp, flags, stream0 + k, n, m, cyc, ra, ru, st, 0, nl);
+        else sf_warp::sf_run(g, s, sp, flags, stream0 + k, n, m, cyc, ra, ru, st, 0, nl);
         counts[0] += m; counts[1] += cyc; counts[2] += ra; counts[3] += ru;
     }
     return 0;
+}
+
+int emu_sf_mc(const luf_window_desc* d, int flags, const double* class_p, unsigned long long seed,
+              unsigned long long stream0, long long nstreams, int n, unsigned long long counts[4], int32_t* steps)
+{
+    return emu_sf_mc_tile(d, flags, class_p, seed, stream0, nstreams, n, counts, steps, 32);
 }
 
 }  // extern "C"

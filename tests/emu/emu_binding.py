@@ -24,7 +24,7 @@ def build(tiny_lists=False):
     if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in SRCS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(['g++', '-O1', '-g', '-fPIC', '-shared', '-std=c++17', '-Wall', '-Wextra']
-                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2', '-DLUF_CTA_LIST_CAP=5', '-DLUF_CTA_LIST2_CAP=3', '-DLUF_CA_TLIST_CAP=4', '-DLUF_SF_ALIST_CAP=4'] if tiny_lists else []) + ['-o', out, SRCS[0]],
+                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2', '-DLUF_CTA_LIST_CAP=5', '-DLUF_CTA_LIST2_CAP=3', '-DLUF_CA_TLIST_CAP=4', '-DLUF_SF_ALIST_CAP=4', '-DLUF_SF_CTA_ALIST_CAP=6'] if tiny_lists else []) + ['-o', out, SRCS[0]],
                        check=True, capture_output=True)
     return out
 
@@ -151,19 +151,20 @@ class EmuStream:
         self.desc, self._keep = make_window_desc(self.tables)
         self.W = (self.tables.EL + 31) // 32
 
-    def stream(self, flags, fresh_local_bits):
+    def stream(self, flags, fresh_local_bits, nl=32):
+        """``nl`` = 32: the warp-tile drivers; any other width: the block-tile drivers (luf::sf_cta)."""
         fresh = np.ascontiguousarray(fresh_local_bits, dtype=np.uint32).reshape(-1, self.W)
         n = fresh.shape[0]
         rt = np.zeros((n, 2), np.int32); m = np.zeros(n, np.int32); floor = np.zeros((n, self.W), np.uint32)
-        rc = lib().emu_sf_stream(C.byref(self.desc), flags, n, _vp(fresh), _vp(rt), _vp(floor), _vp(m))
+        rc = lib().emu_sf_stream_tile(C.byref(self.desc), flags, n, _vp(fresh), _vp(rt), _vp(floor), _vp(m), nl)
         assert rc == 0, rc
         return rt, floor, m
 
-    def mc(self, flags, noise_level, seed, stream0, nstreams, n):
+    def mc(self, flags, noise_level, seed, stream0, nstreams, n, nl=32):
         cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
         counts = (C.c_ulonglong * 4)(0, 0, 0, 0)
         steps = np.zeros((nstreams, n, 2), np.int32)
-        rc = lib().emu_sf_mc(C.byref(self.desc), flags, _vp(cp), C.c_ulonglong(seed), C.c_ulonglong(stream0),
-                             C.c_longlong(nstreams), n, counts, _vp(steps))
+        rc = lib().emu_sf_mc_tile(C.byref(self.desc), flags, _vp(cp), C.c_ulonglong(seed), C.c_ulonglong(stream0),
+                                  C.c_longlong(nstreams), n, counts, _vp(steps), nl)
         assert rc == 0, rc
         return [int(x) for x in counts], steps

@@ -91,3 +91,31 @@ def test_emu_sf_streams_vs_oracle_on_random_errors(spec, p, flags, nstreams, ncy
         np.testing.assert_array_equal(rt[:, 1], o_unr, err_msg=f'stream {k}')
         np.testing.assert_array_equal(floor, o_floor, err_msg=f'stream {k}')
         np.testing.assert_array_equal(m, o_m, err_msg=f'stream {k}')
+
+
+@pytest.mark.parametrize('nl', [64, 256])
+@pytest.mark.parametrize('name', ['sf_sf5_cl', 'sf_sf5_cl_slow11', 'sf_rep5_phen', 'sf_sf7_cl', 'sf_sf5_phen_b2'])
+def test_emu_sf_block_tile_matches_reference(name, nl):
+    """The block-per-window instance of the drivers (luf::sf_cta; tiles of 64 and 256 lanes)."""
+    meta, arr = load_golden(name)
+    emu = emu_binding.EmuStream(make_code(meta['spec']))
+    t = emu.tables
+    fresh = binding.code_bits_to_local(t, arr['fresh_bits'], 0)
+    rt, floor, m = emu.stream(flags_of(meta['decoder_kwargs']), fresh, nl=nl)
+    np.testing.assert_array_equal(rt[:, 0], arr['runtime_all'])
+    np.testing.assert_array_equal(rt[:, 1], arr['runtime_unrooting'])
+    np.testing.assert_array_equal(floor, binding.code_bits_to_local(t, arr['floor_bits'], t.h - 1))
+    np.testing.assert_array_equal(m, arr['m_cycle'])
+
+
+def test_emu_sf_mc_does_not_depend_on_the_tile():
+    """The sampler keeps 32 lanes whatever the tile, so a seeded memory experiment gives the same
+    counts and step sums on warp and block tiles."""
+    code = make_code(dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='frugal')))
+    emu = emu_binding.EmuStream(code)
+    warp = emu.mc(0, 0.012, 9, 100, 12, 2)
+    for nl in (64, 256):
+        block = emu.mc(0, 0.012, 9, 100, 12, 2, nl=nl)
+        assert block[0] == warp[0]
+        np.testing.assert_array_equal(block[1], warp[1])
+    assert warp[0][0] > 0

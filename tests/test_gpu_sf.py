@@ -94,3 +94,43 @@ def test_sf_mc_rates_and_api():
         L.decoders.Snowflake(L.Surface(3, 'phenomenological'))
     with pytest.raises(NotImplementedError):
         L.decoders.Snowflake(code, unrooter='simple')
+
+
+@pytest.fixture
+def block_tile(monkeypatch):
+    """One thread block per window (luf::sf_cta), whatever the window size."""
+    monkeypatch.setenv('LUF_SF_TILE', 'cta')
+
+
+@pytest.mark.parametrize('name', ['sf_sf5_cl', 'sf_sf5_cl_slow11', 'sf_rep5_phen', 'sf_sf7_cl', 'sf_sf5_phen_b2'])
+def test_sf_block_tile_matches_reference_goldens(name, block_tile):
+    test_sf_matches_reference_goldens(name)
+
+
+@pytest.mark.parametrize('spec,p,flags,nstreams,ncycles', [
+    (dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='frugal')), 0.03, 3, 100, 40),
+    (dict(code='Surface', d=9, noise='circuit-level', kwargs=dict(scheme='frugal')), 0.008, 0, 60, 40),
+    (dict(code='Surface', d=13, noise='circuit-level', kwargs=dict(scheme='frugal')), 0.007, 0, 20, 45),
+])
+def test_sf_block_tile_streams_vs_oracle(spec, p, flags, nstreams, ncycles, block_tile):
+    test_sf_streams_vs_oracle_on_random_errors(spec, p, flags, nstreams, ncycles)
+
+
+def test_sf_large_window_uses_blocks_and_matches_oracle():
+    """d = 17 (53 KB of state per window): the block tile is the default; streams of seeded errors
+    near threshold equal the oracle's."""
+    test_sf_streams_vs_oracle_on_random_errors(
+        dict(code='Surface', d=17, noise='circuit-level', kwargs=dict(scheme='frugal')), 0.006, 0, 6, 40)
+
+
+def test_sf_mc_counts_do_not_depend_on_the_tile(monkeypatch):
+    """The sampler keeps 32 lanes whatever the tile: same seed, same memory experiments, same counts."""
+    import localuf_b200 as L
+    code = L.Surface(9, 'circuit-level', scheme='frugal')
+    dec = L.decoders.Snowflake(code)
+    out = {}
+    for tile in ('warp', 'cta'):
+        monkeypatch.setenv('LUF_SF_TILE', tile)
+        out[tile] = dec.engine.mc_host(0, 0.007, 31, 5, 600, 2, want_steps=True)
+    assert out['warp'][0] == out['cta'][0] and out['warp'][0][0] > 0
+    np.testing.assert_array_equal(out['warp'][1], out['cta'][1])
