@@ -637,25 +637,40 @@ static int plan_stream_launch(luf_stream* g, K kernel, long long nstreams, Launc
     return 0;
 }
 
-// One thread block per window: the block size that keeps the most threads resident.
+// One thread block per window.  `awake_estimate` = the number of awake nodes a sweep is expected to
+// visit (0 = unknown): the block gets about one thread per two of them, at least 128, and at most what
+// fills the SM's thread slots next to the other resident windows (measured, B200: d=13 at p=0.003
+// 27 M cycles/s with 128 threads against 21 with 256; d=25 at p=0.008 the other way round).
 template <class K>
-static int plan_stream_cta_launch(luf_stream* g, K kernel, long long nstreams, LaunchCfg* cfg)
+static int plan_stream_cta_launch(luf_stream* g, K kernel, long long nstreams, LaunchCfg* cfg, double awake_estimate = 0.0)
 {
     const uint32_t bytes = g->lay_cta.bytes;
     if (bytes > (uint32_t)g->max_smem)
         return fail(LUF_ERR_UNSUPPORTED, "one window's decoder state (" + std::to_string(bytes) +
                     " B) exceeds the shared memory of an SM");
-    static const int env_threads = getenv("LUF_SF_CTA_THREADS") ? atoi(getenv("LUF_SF_CTA_THREADS")) : 0;
+    const int env_threads = getenv("LUF_SF_CTA_THREADS") ? atoi(getenv("LUF_SF_CTA_THREADS")) : 0;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    int best = 0, threads = 0, per_sm = 0;
-    for (int cand = 256; cand >= 64; cand -= 32) {
-        if (env_threads > 0 && cand != env_threads) continue;
-        int occ = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, cand, bytes));
-        if (occ * cand > best) { best = occ * cand; threads = cand; per_sm = occ; }       // ties: larger blocks
-    }
-    if (best == 0) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    cudaFuncAttributes attr;
+    CUDA_TRY(cudaFuncGetAttributes(&attr, kernel));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, bytes));
+    if (per_sm < 1) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    int most = (2048 / per_sm) & ~31;                                  // thread slots of an SM ...
+    const int by_regs = (65536 / (attr.numRegs > 0 ? attr.numRegs : 64) / per_sm) & ~31;   // ... and its registers:
+    if (most > by_regs) most = by_regs;                                // never fewer resident windows than shared memory allows
+    if (most > attr.maxThreadsPerBlock) most = attr.maxThreadsPerBlock & ~31;
+    if (most > 1024) most = 1024;
+    if (most < 128) most = 128;
+    int threads = awake_estimate > 0.0 ? (((int)(awake_estimate / 2.0) + 31) & ~31) : most;
+    if (threads < 128) threads = 128;
+    if (threads > most) threads = most;
+    if (env_threads >= 32 && env_threads <= 1024) threads = env_threads & ~31;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, bytes));
+    if (per_sm < 1) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    if (getenv("LUF_DEBUG_PLAN"))
+        fprintf(stderr, "[luf] stream launch plan (block per window): %u B per window, %d threads per block, %d blocks per SM\n",
+                bytes, threads, per_sm);
     long long blocks = (long long)g->sm_count * per_sm;
     if (blocks > nstreams) blocks = nstreams;
     if (blocks < 1) blocks = 1;
@@ -773,7 +788,14 @@ int luf_stream_mc(luf_stream* g, int flags, const double* class_p_host, uint64_t
     const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
     LaunchCfg c;
     if (use_stream_cta(g)) {
-        if (int rc = plan_stream_cta_launch(g, k_sf_mc_cta, nstreams, &c)) return rc;
+        // expected awake nodes of a sweep: about 4 per fresh fault and sheet (two defects, and as many woken neighbours)
+        double faults = 0.0;
+        for (int cl = 0, lo = 0; cl < g->view.n_classes; ++cl) {
+            const int hi = (int)g->host.class_end[cl];
+            faults += class_p_host[cl] * (hi - lo);
+            lo = hi;
+        }
+        if (int rc = plan_stream_cta_launch(g, k_sf_mc_cta, nstreams, &c, 4.0 * faults * g->view.h + 1.0)) return rc;
         k_sf_mc_cta<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_cta, sp, flags, stream0, nstreams, n,
                                                                         counts_dev, steps_dev);
     } else {
