@@ -267,9 +267,9 @@ METRIC = {'shots/s': 'decoded shots/s', 'decoding cycles/s': 'decoding cycles/s'
 DEFAULT_UNITS = {'cfg1': 1 << 26, 'cfg2': 1 << 24, 'cfg3': 1 << 22, 'cfg3-staged': 1 << 20, 'cfg3-macar': 1 << 19, 'cfg3-actis': 1 << 14,
                  'cfg4': 1 << 16}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full; profiles/)
-TRAFFIC = {'cfg3': (112640, 'profiles/r01_v10_k_mc_uf_summary.txt'),
+TRAFFIC = {'cfg3': (104192, 'profiles/r01_final_k_mc_uf_summary.txt'),
            'cfg3-macar': (89856, 'profiles/r01_k_mc_ca_macar_summary.txt'),
-           'cfg4': (112128, 'profiles/r01_k_sf_mc_summary.txt')}
+           'cfg4': (145920, 'profiles/r01_k_sf_mc_acp_summary.txt (warp tile; the block tile reads the same tables)')}
 
 
 def run_ours(args):
@@ -298,7 +298,7 @@ def run_ours(args):
         # a step = S independent Frugal.run(n=1) memory experiments per GPU; unit = decoding cycle
         eng = _engine.StreamEngine(code, device=local_rank)
         decoder._engine = eng
-        unit, kernel = 'decoding cycles/s', 'k_stream_mc'
+        unit, kernel = 'decoding cycles/s', 'k_sf_mc_cta / k_sf_mc'
         bpu = algorithmic_bytes_per_cycle(eng.tables)
         h2d = 8 * eng.tables.n_classes + 40
 
