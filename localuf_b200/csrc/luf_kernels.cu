@@ -412,6 +412,52 @@ __global__ void k_check(int WE, long long nshots, const uint32_t* __restrict__ w
     if (lane == 0 && fails) atomicAdd(fail_count, (unsigned long long)fails);
 }
 
+// Staged K4, streaming form: a warp takes four consecutive shots at a time -- 4*WE words of `err`
+// and of `corr`, contiguous and 16-byte aligned -- with 16-byte loads that are all in flight before
+// the first is used (3.5 KB per warp instead of 0.9 KB: the kernel is bound by how many bytes an SM
+// keeps in flight).  A word's shot is its index / WE, by multiplication with `magic` = ceil(2^32 / WE)
+// (exact below 2^16 words).  The last nshots % 4 shots go through k_check.
+template <int V>        // uint4 loads per lane and array: ceil(WE / 32)
+__global__ void __launch_bounds__(256) k_check4(int WE, uint32_t magic, long long ngroups, const uint32_t* __restrict__ west_mask,
+                                                const uint4* __restrict__ err, const uint4* __restrict__ corr,
+                                                uint8_t* __restrict__ logical, unsigned long long* fail_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const long long stride = (long long)gridDim.x * wpb;
+    unsigned int fails = 0;
+    for (long long grp = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); grp < ngroups; grp += stride) {
+        const uint4* e4 = err + grp * WE;       // 4*WE words = WE uint4
+        const uint4* c4 = corr + grp * WE;
+        uint4 e[V], c[V];
+        #pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int q = lane + 32 * i;
+            if (q < WE) { e[i] = __ldcs(e4 + q); c[i] = __ldcs(c4 + q); }      // streamed once: evict first
+            else { e[i] = make_uint4(0, 0, 0, 0); c[i] = e[i]; }
+        }
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        #pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const uint32_t x[4] = {e[i].x ^ c[i].x, e[i].y ^ c[i].y, e[i].z ^ c[i].z, e[i].w ^ c[i].w};
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!x[k]) continue;                                            // errors and corrections are sparse
+                const uint32_t j = (uint32_t)(4 * (lane + 32 * i) + k);
+                const uint32_t row = __umulhi(j, magic);
+                const uint32_t m = x[k] & __ldg(&west_mask[j - row * (uint32_t)WE]);
+                a0 ^= row == 0 ? m : 0u; a1 ^= row == 1 ? m : 0u; a2 ^= row == 2 ? m : 0u; a3 ^= row == 3 ? m : 0u;
+            }
+        }
+        a0 = __reduce_xor_sync(0xffffffffu, a0); a1 = __reduce_xor_sync(0xffffffffu, a1);
+        a2 = __reduce_xor_sync(0xffffffffu, a2); a3 = __reduce_xor_sync(0xffffffffu, a3);
+        const uint32_t bits = (__popc(a0) & 1u) | (__popc(a1) & 1u) << 8 | (__popc(a2) & 1u) << 16 | (__popc(a3) & 1u) << 24;
+        if (lane == 0 && logical) *(uint32_t*)(logical + 4 * grp) = bits;       // four result bytes at once
+        fails += __popc(bits);
+    }
+    if (lane == 0 && fails) atomicAdd(fail_count, (unsigned long long)fails);
+}
+
 // ------------------------------------------------------------------- graph
 struct luf_graph {
     int device = 0, sm_count = 0, max_smem = 0;
@@ -1047,14 +1093,43 @@ int luf_check(luf_graph* g, int64_t nshots, const uint32_t* err_bits_dev, const 
         return fail(LUF_ERR_INVALID, "luf_check: bad argument");
     if (nshots == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
-    const int block = 256, wpb = block / WARP;
-    long long blocks = (nshots + wpb - 1) / wpb;
+    const int block = 256, wpb = block / WARP, WE = g->view.WE;
     const long long cap = (long long)g->sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    k_check<<<(int)blocks, block, 0, (cudaStream_t)stream>>>(g->view.WE, nshots, g->view.west_mask, err_bits_dev,
-                                                              corr_bits_dev, logical_dev, fail_count_dev);
-    CUDA_TRY(cudaGetLastError());
-    ++g->launches;
+    long long done = 0;
+    // groups of four shots through the streaming kernel when the buffers allow 16-byte loads
+    const bool aligned = !(((uintptr_t)err_bits_dev | (uintptr_t)corr_bits_dev) & 15u) && !((uintptr_t)logical_dev & 3u);
+    if (aligned && nshots >= 4 && WE >= 2 && WE <= 256) {          // (WE == 1: the magic number would be 2^32)
+        const long long ngroups = nshots / 4;
+        long long blocks = (ngroups + wpb - 1) / wpb;
+        if (blocks > cap) blocks = cap;
+        const uint32_t magic = (uint32_t)((0x100000000ull + (uint64_t)WE - 1) / (uint64_t)WE);
+#define LUF_CHECK4(V) k_check4<V><<<(int)blocks, block, 0, (cudaStream_t)stream>>>(WE, magic, ngroups, g->view.west_mask, \
+            (const uint4*)err_bits_dev, (const uint4*)corr_bits_dev, logical_dev, fail_count_dev)
+        switch ((WE + 31) / 32) {
+            case 1: LUF_CHECK4(1); break;
+            case 2: LUF_CHECK4(2); break;
+            case 3: LUF_CHECK4(3); break;
+            case 4: LUF_CHECK4(4); break;
+            case 5: LUF_CHECK4(5); break;
+            case 6: LUF_CHECK4(6); break;
+            case 7: LUF_CHECK4(7); break;
+            default: LUF_CHECK4(8); break;
+        }
+#undef LUF_CHECK4
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+        done = 4 * ngroups;
+    }
+    if (done < nshots) {
+        const long long rest = nshots - done;
+        long long blocks = (rest + wpb - 1) / wpb;
+        if (blocks > cap) blocks = cap;
+        k_check<<<(int)blocks, block, 0, (cudaStream_t)stream>>>(WE, rest, g->view.west_mask, err_bits_dev + done * WE,
+                                                                  corr_bits_dev + done * WE,
+                                                                  logical_dev ? logical_dev + done : nullptr, fail_count_dev);
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+    }
     return 0;
 }
 
