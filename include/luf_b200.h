@@ -234,10 +234,14 @@ typedef struct luf_stream luf_stream;
 enum {
     LUF_SF_SLOW_MERGER = 1,       /* Snowflake(merger='slow'),  snowflake/main.py:1237-1246 */
     LUF_SF_ONE_ONE = 2,           /* Snowflake(schedule='1:1'), snowflake/main.py:1284-1305 */
-    LUF_SF_SYNDROME = 4           /* luf_stream_decode only: the input rows hold the new layer's SYNDROME (bit q =
+    LUF_SF_SYNDROME = 4,          /* luf_stream_decode only: the input rows hold the new layer's SYNDROME (bit q =
                                    * defect at in-layer position q; first W(NL) words of each W(EL)-word row) instead
                                    * of fresh errors -- Snowflake.decode(syndrome) / generate_output,
                                    * snowflake/main.py:216-256,656-726 */
+    LUF_SF_LATENCY_TAIL = 8       /* luf_stream_decode only: the last h-1 cycles are the noiseless tail of
+                                   * Frugal.sample_latency (_schemes.py:651-698): from the first of them that starts
+                                   * with no defect in the window on, the decoder only drops (defects_possible =
+                                   * False, snowflake/main.py:258-264) and rt = (1, 0) */
 };
 
 int luf_stream_create(const luf_window_desc *desc, int device, luf_stream **out);
@@ -270,6 +274,14 @@ int luf_stream_decode_host(luf_stream *s, int flags, int64_t nstreams, int32_t n
                            int32_t *m_host);
 int luf_stream_mc_host(luf_stream *s, int flags, const double *class_p_host, uint64_t seed, uint64_t stream0,
                        int64_t nstreams, int32_t n, unsigned long long counts_host[4], int32_t *steps_host);
+/* Fused K1+K3b -- replaces Frugal.sample_latency (localuf/_schemes.py:651-698; the sample loop of
+ * localuf/sim/latency.py:13-72) for nstreams independent experiments: lat [nstreams][3] = the number of
+ * timesteps from the last measurement round to the final correction, for time_only = 'all' / 'merging' /
+ * 'unrooting'. */
+int luf_stream_latency(luf_stream *s, int flags, const double *class_p_host, uint64_t seed, uint64_t stream0,
+                       int64_t nstreams, int32_t *lat_dev, void *stream);
+int luf_stream_latency_host(luf_stream *s, int flags, const double *class_p_host, uint64_t seed, uint64_t stream0,
+                            int64_t nstreams, int32_t *lat_host);
 int64_t luf_stream_launch_count(const luf_stream *s);
 
 /* Number of kernel launches issued through this graph so far (bench.py's gpu_launches). */

@@ -115,7 +115,7 @@ def make_window_desc(t):
     return d, keep
 
 
-SF_SLOW_MERGER, SF_ONE_ONE, SF_SYNDROME = 1, 2, 4
+SF_SLOW_MERGER, SF_ONE_ONE, SF_SYNDROME, SF_LATENCY_TAIL = 1, 2, 4, 8
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -161,6 +161,8 @@ def _load():
         lib.luf_stream_mc.argtypes = [v, C.c_int, v, u64, u64, i64, C.c_int32, v, v, v]
         lib.luf_stream_decode_host.argtypes = [v, C.c_int, i64, C.c_int32, v, v, v, v]
         lib.luf_stream_mc_host.argtypes = [v, C.c_int, v, u64, u64, i64, C.c_int32, v, v]
+        lib.luf_stream_latency.argtypes = [v, C.c_int, v, u64, u64, i64, v, v]
+        lib.luf_stream_latency_host.argtypes = [v, C.c_int, v, u64, u64, i64, v]
         _lib = lib
         return lib
 
@@ -406,6 +408,14 @@ class StreamEngine:
         _check(_load().luf_stream_mc_host(self._h, flags, cp.ctypes.data, seed, stream0, nstreams, n, counts,
                                           _ptr(steps)))
         return [int(x) for x in counts], steps
+
+    def latency_host(self, flags: int, noise_level: float, seed: int, stream0: int, nstreams: int):
+        """``Frugal.sample_latency`` of ``nstreams`` experiments -> int32 [nstreams, 3]
+        (time_only = 'all', 'merging', 'unrooting')."""
+        cp = self.class_p(noise_level)
+        lat = np.zeros((nstreams, 3), np.int32)
+        _check(_load().luf_stream_latency_host(self._h, flags, cp.ctypes.data, seed, stream0, nstreams, _ptr(lat)))
+        return lat
 
     def mc(self, flags, noise_level, seed, stream0, nstreams, n, counts, steps=None):
         cp = self.class_p(noise_level)

@@ -279,16 +279,9 @@ __global__ void k_sf_decode(SfView g, SfLayout l, int flags, long long nstreams,
     const SfShot s = sf_bind(l, smem + (size_t)(threadIdx.x >> 5) * l.bytes);
     const long long stride = (long long)gridDim.x * wpb;
     for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nstreams; k += stride) {
-        LUF_PHASE(sf_reset(g, s, lane, nl));
-        for (int c = 0; c < ncycles; ++c) {
-            const size_t row = (size_t)k * ncycles + c;
-            int m = 0, ra = 0, ru = 0;
-            sf_cycle_head(g, s, m, lane, nl);
-            if (flags & SF_FLAG_SYNDROME) { LUF_PHASE(sf_given_syndrome(g, s, fresh + row * g.ELw, lane, nl)); }
-            else { LUF_PHASE(sf_given_sheet(g, s, fresh + row * g.ELw, lane, nl)); }
-            sf_cycle_tail(g, s, flags, floor_bits ? floor_bits + row * g.ELw : nullptr, m, ra, ru, lane, nl);
-            if (lane == 0) { rt[2 * row] = ra; rt[2 * row + 1] = ru; m_out[row] = m; }
-        }
+        const size_t row0 = (size_t)k * ncycles;
+        sf_warp::sf_decode_stream(g, s, flags, ncycles, fresh + row0 * g.ELw, rt + 2 * row0,
+                                  floor_bits ? floor_bits + row0 * g.ELw : nullptr, m_out + row0, lane, nl);
     }
 }
 
@@ -321,18 +314,9 @@ __global__ void k_sf_decode_cta(SfView g, SfLayout l, int flags, long long nstre
     const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
     const SfShot s = sf_bind(l, smem);
     for (long long k = blockIdx.x; k < nstreams; k += gridDim.x) {
-        sf_reset(g, s, lane, nl);
-        __syncthreads();
-        for (int c = 0; c < ncycles; ++c) {
-            const size_t row = (size_t)k * ncycles + c;
-            int m = 0, ra = 0, ru = 0;
-            sf_cta::sf_cycle_head(g, s, m, lane, nl);
-            if (flags & SF_FLAG_SYNDROME) sf_given_syndrome(g, s, fresh + row * g.ELw, lane, nl);
-            else sf_given_sheet(g, s, fresh + row * g.ELw, lane, nl);
-            __syncthreads();
-            sf_cta::sf_cycle_tail(g, s, flags, floor_bits ? floor_bits + row * g.ELw : nullptr, m, ra, ru, lane, nl);
-            if (lane == 0) { rt[2 * row] = ra; rt[2 * row + 1] = ru; m_out[row] = m; }
-        }
+        const size_t row0 = (size_t)k * ncycles;
+        sf_cta::sf_decode_stream(g, s, flags, ncycles, fresh + row0 * g.ELw, rt + 2 * row0,
+                                 floor_bits ? floor_bits + row0 * g.ELw : nullptr, m_out + row0, lane, nl);
     }
 }
 
@@ -350,6 +334,35 @@ __global__ void k_sf_mc_cta(SfView g, SfLayout l, SampleParams sp, int flags, un
     if (lane == 0) {
         atomicAdd(&counts[0], (unsigned long long)m_total); atomicAdd(&counts[1], (unsigned long long)cycles);
         atomicAdd(&counts[2], (unsigned long long)ra); atomicAdd(&counts[3], (unsigned long long)ru);
+    }
+}
+
+// Frugal.sample_latency for nstreams independent memory experiments: lat [nstreams][3].
+__global__ void k_sf_latency(SfView g, SfLayout l, SampleParams sp, int flags, unsigned long long stream0,
+                             long long nstreams, int32_t* __restrict__ lat)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, nl = WARP;
+    const int wpb = blockDim.x >> 5;
+    const SfShot s = sf_bind(l, smem + (size_t)(threadIdx.x >> 5) * l.bytes);
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nstreams; k += stride) {
+        int v[3];
+        sf_warp::sf_latency(g, s, sp, flags, stream0 + (unsigned long long)k, v, lane, nl);
+        if (lane == 0) { lat[3 * k] = v[0]; lat[3 * k + 1] = v[1]; lat[3 * k + 2] = v[2]; }
+    }
+}
+
+__global__ void k_sf_latency_cta(SfView g, SfLayout l, SampleParams sp, int flags, unsigned long long stream0,
+                                 long long nstreams, int32_t* __restrict__ lat)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
+    const SfShot s = sf_bind(l, smem);
+    for (long long k = blockIdx.x; k < nstreams; k += gridDim.x) {
+        int v[3];
+        sf_cta::sf_latency(g, s, sp, flags, stream0 + (unsigned long long)k, v, lane, nl);
+        if (lane == 0) { lat[3 * k] = v[0]; lat[3 * k + 1] = v[1]; lat[3 * k + 2] = v[2]; }
     }
 }
 
@@ -807,7 +820,8 @@ int luf_stream_decode(luf_stream* g, int flags, int64_t nstreams, int32_t ncycle
 {
     if (!g || !fresh_bits_dev || !rt_dev || !m_dev || nstreams < 0 || ncycles < 0)
         return fail(LUF_ERR_INVALID, "luf_stream_decode: bad argument");
-    if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE | LUF_SF_SYNDROME)) return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
+    if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE | LUF_SF_SYNDROME | LUF_SF_LATENCY_TAIL))
+        return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
     if (nstreams == 0 || ncycles == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
     LaunchCfg c;
@@ -899,6 +913,48 @@ int luf_stream_mc_host(luf_stream* g, int flags, const double* class_p_host, uin
     if (st) CUDA_TRY(cudaMemcpyAsync(steps_host, st, (size_t)nstreams * n * 8, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaMemcpy(tmp, cnt, 32, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 4; ++i) counts_host[i] += tmp[i];
+    return 0;
+}
+
+int luf_stream_latency(luf_stream* g, int flags, const double* class_p_host, uint64_t seed, uint64_t stream0,
+                       int64_t nstreams, int32_t* lat_dev, void* stream)
+{
+    if (!g || !class_p_host || !lat_dev || nstreams < 0) return fail(LUF_ERR_INVALID, "luf_stream_latency: bad argument");
+    if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE)) return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
+    if (nstreams == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
+    LaunchCfg c;
+    if (use_stream_cta(g)) {
+        double faults = 0.0;
+        for (int cl = 0, lo = 0; cl < g->view.n_classes; ++cl) {
+            const int hi = (int)g->host.class_end[cl];
+            faults += class_p_host[cl] * (hi - lo);
+            lo = hi;
+        }
+        if (int rc = plan_stream_cta_launch(g, k_sf_latency_cta, nstreams, &c, 4.0 * faults * g->view.h + 1.0)) return rc;
+        k_sf_latency_cta<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_cta, sp, flags, stream0, nstreams, lat_dev);
+    } else {
+        if (int rc = plan_stream_launch(g, k_sf_latency, nstreams, &c)) return rc;
+        k_sf_latency<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, sp, flags, stream0, nstreams, lat_dev);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
+    return 0;
+}
+
+int luf_stream_latency_host(luf_stream* g, int flags, const double* class_p_host, uint64_t seed, uint64_t stream0,
+                            int64_t nstreams, int32_t* lat_host)
+{
+    if (!g || !lat_host || nstreams < 0) return fail(LUF_ERR_INVALID, "luf_stream_latency_host: bad argument");
+    if (nstreams == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    void* lat;
+    int rc;
+    if ((rc = scratch_s(g, 1, (size_t)nstreams * 12, &lat))) return rc;
+    if ((rc = luf_stream_latency(g, flags, class_p_host, seed, stream0, nstreams, (int32_t*)lat, 0))) return rc;
+    CUDA_TRY(cudaMemcpy(lat_host, lat, (size_t)nstreams * 12, cudaMemcpyDeviceToHost));
     return 0;
 }
 

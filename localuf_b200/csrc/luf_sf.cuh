@@ -29,7 +29,7 @@ static const uint32_t SF_PTR_C = 0xFu;       // pointer 'C' (no neighbour) in th
 // per-node flag word (written by the owning lane only)
 enum { SF_ACTIVE = 1, SF_WHOLE = 2, SF_DEFECT = 4, SF_GROWN = 8, SF_UNROOTED = 16, SF_BUSY = 32,
        SF_N_ACTIVE = 64, SF_N_GROWN = 128, SF_N_UNROOTED = 256 };
-enum { SF_FLAG_SLOW = 1, SF_FLAG_ONE_ONE = 2, SF_FLAG_SYNDROME = 4 };
+enum { SF_FLAG_SLOW = 1, SF_FLAG_ONE_ONE = 2, SF_FLAG_SYNDROME = 4, SF_FLAG_LATENCY_TAIL = 8 };
 // string-pair codes of an endpoint's partner (see oracle/luf_oracle_snowflake.c)
 static const int SFP_NONE = -1, SFP_WEST = -2, SFP_EAST = -3, SFP_DEAD = -4;
 

@@ -102,6 +102,64 @@ LUF_DEV void sf_run(const SfView& g, const SfShot& s, const SampleParams& sp, in
     cycles += total;
 }
 
+// decoder.syndrome non-empty? (snowflake/main.py:143-149: any detector of the window with a defect -- boundary
+// nodes do not count; defects only sit on awake nodes)
+LUF_DEV bool sf_window_has_defect(const SfView& g, const SfShot& s, int lane, int nl)
+{
+    uint32_t found = 0;
+    (void)lane;
+    LUF_ST_PHASE(sf_for_awake(g, s, lane, nl, [&](int, int q, int v) { if (q >= g.NLb && (s.fl[v] & SF_DEFECT)) found = 1u; }));
+    return LUF_ST_ANY(found);
+}
+
+// K3b parity path for one window: ncycles consecutive cycles whose fresh errors (or, with
+// SF_FLAG_SYNDROME, top-sheet syndromes) are GIVEN as rows of ELw words.  rt [ncycles][2] = decode's
+// return value for time_only = 'all' / 'unrooting'; floor_bits (optional) [ncycles][ELw]; m_out [ncycles].
+// SF_FLAG_LATENCY_TAIL: the last h - 1 cycles are the noiseless tail of Frugal.sample_latency.
+LUF_DEV void sf_decode_stream(const SfView& g, const SfShot& s, int flags, int ncycles, const uint32_t* fresh,
+                              int32_t* rt, uint32_t* floor_bits, int32_t* m_out, int lane, int nl)
+{
+    LUF_ST_PHASE(sf_reset(g, s, lane, nl));
+    bool possible = true;                        // defects_possible of Frugal.sample_latency
+    for (int c = 0; c < ncycles; ++c) {
+        int m = 0, ra = 0, ru = 0;
+        if ((flags & SF_FLAG_LATENCY_TAIL) && possible && c >= ncycles - (g.h - 1))
+            possible = sf_window_has_defect(g, s, lane, nl);
+        if (!possible) {                         // the decoder only drops: 1 timestep ('all'), nothing to unroot
+            if (lane == 0) { rt[2 * c] = 1; rt[2 * c + 1] = 0; m_out[c] = 0; }
+            if (floor_bits) { LUF_ST_PHASE(for (int w = lane; w < g.ELw; w += nl) floor_bits[(size_t)c * g.ELw + w] = 0); }
+            continue;
+        }
+        sf_cycle_head(g, s, m, lane, nl);
+        if (flags & SF_FLAG_SYNDROME) { LUF_ST_PHASE(sf_given_syndrome(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
+        else { LUF_ST_PHASE(sf_given_sheet(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
+        sf_cycle_tail(g, s, flags, floor_bits ? floor_bits + (size_t)c * g.ELw : nullptr, m, ra, ru, lane, nl);
+        if (lane == 0) { rt[2 * c] = ra; rt[2 * c + 1] = ru; m_out[c] = m; }
+    }
+}
+
+// Frugal.sample_latency (_schemes.py:651-698): h + 1 noisy cycles, one more without future-boundary
+// faults, then h - 1 noiseless ones; the latency is the runtime of the last h cycles.  From the first
+// noiseless cycle that starts with no defect in the window on, the decoder only drops
+// (defects_possible = False, snowflake/main.py:258-264): 1 timestep each for time_only = 'all', 0 otherwise.
+// lat[0..2] = latency for time_only 'all' / 'merging' / 'unrooting' (meaningful on lane 0).
+LUF_DEV void sf_latency(const SfView& g, const SfShot& s, const SampleParams& sp, int flags, uint64_t stream,
+                        int lat[3], int lane, int nl)
+{
+    const int h = g.h, total = 2 * h + 1, loops = (flags & SF_FLAG_ONE_ONE) ? 1 : 2;
+    LUF_ST_PHASE(sf_reset(g, s, lane, nl));
+    lat[0] = lat[1] = lat[2] = 0;
+    for (int c = 0; c < total; ++c) {
+        const bool noisy = c <= h + 1, counted = c >= h + 1;
+        if (!noisy && !sf_window_has_defect(g, s, lane, nl)) { lat[0] += total - c; break; }
+        int m = 0, ra = 0, ru = 0;
+        sf_cycle_head(g, s, m, lane, nl);
+        if (noisy) { LUF_ST_PHASE(if (lane < 32) sf_sample_sheet(g, s, sp, stream, (uint32_t)c, c == h + 1, lane, nl < 32 ? nl : 32)); }
+        sf_cycle_tail(g, s, flags, nullptr, m, ra, ru, lane, nl);
+        if (counted) { lat[0] += ra; lat[1] += ra - 2 * loops; lat[2] += ru; }
+    }
+}
+
 #undef LUF_SF_REGATHER
 
 }  // namespace LUF_SF_NS

@@ -145,6 +145,22 @@ class Snowflake(Decoder):
                 w.writerows(zip(vectors, self.floor_history, strict=True))
         return self.floor_history
 
+    def _mc_latency(self, noise_level: float, shots: int, seed=None):
+        """``shots`` independent ``Frugal.sample_latency`` experiments -> int32 [shots, 3]
+        (time_only = 'all', 'merging', 'unrooting'); under torchrun every rank gets all of them."""
+        eng = self.engine
+        rank, size = dist.world()
+        seed = self._draw_seed(seed)
+        if size > 1:
+            seed = dist.allreduce_counts([seed if rank == 0 else 0])[0]
+        lo, cnt = dist.shard(shots, rank, size)
+        out = np.zeros((shots, 3), np.int64)
+        if cnt:
+            out[lo:lo + cnt] = eng.latency_host(self._flags, noise_level, seed, lo, cnt)
+        if size > 1:
+            out = np.array(dist.allreduce_counts(out.reshape(-1).tolist(), device=f'cuda:{eng.device}')).reshape(shots, 3)
+        return out.astype(np.int32)
+
     def steps_from_sums(self, sums, time_only: str):
         """(sum of 'all' runtimes, sum of 'unrooting' runtimes) over d cycles -> Frugal.step_counts entry
         (snowflake/main.py:340,347: 'all' - 'merging' = 2 per merge loop)."""

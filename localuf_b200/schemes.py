@@ -341,3 +341,23 @@ class Frugal(_Streaming):
         m, steps = decoder._mc_frugal(noise_level, n, time_only=time_only, shots=shots, **kwargs)
         self.step_counts.extend(steps)
         return m, shots * (math.ceil(self.WINDOW_HEIGHT / self._COMMIT_HEIGHT) / self._CODE.D + n + 1)
+
+    def sample_latency(self, decoder, noise_level: float, draw=False, log_history=False,
+                       time_only: str = 'merging', shots=None, seed=None, **kwargs_for_draw_decode):
+        """The number of decoder timesteps between the last measurement round and the final
+        correction (``_schemes.py:651-698``): a memory experiment of ``WINDOW_HEIGHT + 1`` noisy
+        cycles, one more without future-boundary faults, then ``WINDOW_HEIGHT - 1`` noiseless
+        ones during which the decoder stops growing and merging once no defect is left; the
+        latency is the runtime of the last ``WINDOW_HEIGHT`` cycles.  Assumes commit height 1.
+
+        Returns one sample like the reference; ``shots=k`` returns a list of ``k`` independent
+        samples from one kernel launch (what ``sim.latency.frugal`` uses)."""
+        if draw or log_history:
+            raise NotImplementedError("Drawing / history are outside this engine.")
+        if time_only not in ('all', 'merging', 'unrooting'):
+            raise ValueError(f'Unknown time_only: {time_only}.')
+        self.reset()
+        decoder.reset()
+        lat = decoder._mc_latency(noise_level, 1 if shots is None else shots, seed=seed)
+        column = lat[:, ('all', 'merging', 'unrooting').index(time_only)]
+        return int(column[0]) if shots is None else [int(x) for x in column]

@@ -1,2 +1,2 @@
 """Experiment drivers (reference: ``localuf/sim``)."""
-from localuf_b200.sim import accuracy, runtime  # noqa: F401
+from localuf_b200.sim import accuracy, latency, runtime  # noqa: F401

@@ -43,3 +43,23 @@ def forward(ds, noise_levels, n, noise, get_commit_height=None, get_buffer_heigh
     df = DataFrame(data).sort_index(axis=1)
     df.columns.set_names(['stage', 'd', 'p'], inplace=True)
     return df
+
+
+def frugal(ds, noise_levels, n, code_class, noise, time_only='merging', get_commit_height=None,
+           get_buffer_height=None, **kwargs_for_Snowflake):
+    """Runtime data of Snowflake under the frugal scheme (``localuf/sim/runtime.py:139-199``):
+    columns ``(d, p)``, one row per timed block of ``d`` decoding cycles of ``Frugal.run(n)``."""
+    from localuf_b200.decoders import Snowflake
+    from localuf_b200.sim._height_calculator import get_heights
+    data = {}
+    for d in ds:
+        _, commit_height, buffer_height = get_heights(d, n, 'frugal', get_commit_height, get_buffer_height)
+        code = code_class(d, noise, scheme='frugal', window_height=None, commit_height=commit_height,
+                          buffer_height=buffer_height)
+        decoder = Snowflake(code, **kwargs_for_Snowflake)
+        for noise_level in noise_levels:
+            code.SCHEME.run(decoder, noise_level, n, time_only=time_only)
+            data[d, noise_level] = tuple(code.SCHEME.step_counts)
+    df = DataFrame(data).sort_index(axis=1)
+    df.columns.set_names(['d', 'p'], inplace=True)
+    return df

@@ -228,15 +228,32 @@ int emu_sf_stream_tile(const luf_window_desc* d, int flags, int ncycles, const u
     const SfLayout l = cta ? make_sf_layout(p, SF_CTA_ALIST_CAP) : make_sf_layout(p);
     std::vector<unsigned char> mem(l.bytes);
     const SfShot s = sf_bind(l, mem.data());
-    LUF_PHASE(sf_reset(g, s, lane, nl));
-    for (int c = 0; c < ncycles; ++c) {
-        int m = 0, ra = 0, ru = 0;
-        if (cta) sf_cta::sf_cycle_head(g, s, m, 0, nl); else sf_warp::sf_cycle_head(g, s, m, 0, nl);
-        if (flags & SF_FLAG_SYNDROME) { LUF_PHASE(sf_given_syndrome(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
-        else { LUF_PHASE(sf_given_sheet(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
-        if (cta) sf_cta::sf_cycle_tail(g, s, flags, floor_bits + (size_t)c * g.ELw, m, ra, ru, 0, nl);
-        else sf_warp::sf_cycle_tail(g, s, flags, floor_bits + (size_t)c * g.ELw, m, ra, ru, 0, nl);
-        rt[2 * c] = ra; rt[2 * c + 1] = ru; m_out[c] = m;
+    if (cta) sf_cta::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, 0, nl);
+    else sf_warp::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, 0, nl);
+    return 0;
+}
+
+// Frugal.sample_latency streams with the device sampler (host arithmetic): lat [nstreams][3].
+int emu_sf_latency(const luf_window_desc* d, int flags, const double* class_p, unsigned long long seed,
+                   unsigned long long stream0, long long nstreams, int32_t* lat, int nl)
+{
+    const bool cta = nl != 32;
+    PackedWindow p;
+    if (!pack_window(*d, p).empty()) return -1;
+    SfView g;
+    g.d = p.d; g.h = p.h; g.NLb = p.NLb; g.NLd = p.NLd; g.NL = p.NL; g.EL = p.EL; g.K = p.K;
+    g.ELw = words32(p.EL); g.WLn = words32(p.NL); g.N = p.NL * p.h; g.n_classes = p.n_classes;
+    g.nbr = p.nbr.data(); g.edge_ends = p.edge_ends.data(); g.pos_long = p.pos_long.data();
+    g.fresh_perm = p.fresh_perm.data(); g.class_end = p.class_end.data();
+    const SfLayout l = cta ? make_sf_layout(p, SF_CTA_ALIST_CAP) : make_sf_layout(p);
+    const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
+    std::vector<unsigned char> mem(l.bytes);
+    const SfShot s = sf_bind(l, mem.data());
+    for (long long k = 0; k < nstreams; ++k) {
+        int v[3];
+        if (cta) sf_cta::sf_latency(g, s, sp, flags, stream0 + k, v, 0, nl);
+        else sf_warp::sf_latency(g, s, sp, flags, stream0 + k, v, 0, nl);
+        lat[3 * k] = v[0]; lat[3 * k + 1] = v[1]; lat[3 * k + 2] = v[2];
     }
     return 0;
 }

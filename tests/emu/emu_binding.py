@@ -160,6 +160,14 @@ class EmuStream:
         assert rc == 0, rc
         return rt, floor, m
 
+    def latency(self, flags, noise_level, seed, stream0, nstreams, nl=32):
+        cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
+        lat = np.zeros((nstreams, 3), np.int32)
+        rc = lib().emu_sf_latency(C.byref(self.desc), flags, _vp(cp), C.c_ulonglong(seed), C.c_ulonglong(stream0),
+                                  C.c_longlong(nstreams), _vp(lat), nl)
+        assert rc == 0, rc
+        return lat
+
     def mc(self, flags, noise_level, seed, stream0, nstreams, n, nl=32):
         cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
         counts = (C.c_ulonglong * 4)(0, 0, 0, 0)
