@@ -37,3 +37,16 @@ def monte_carlo_results_to_sample_counts(results: DataFrame):
     for (d, noise_level), (_, n) in results.items():
         out.setdefault(d, []).append((noise_level, int(n)))
     return out
+
+
+def subset_sample(ds, noise_level: float, n: int, code_class, decoder_class, noise, parametrization='balanced',
+                  tol: float = 5e-1):
+    """Threshold data by subset sampling (``localuf/sim/accuracy/monte_carlo.py:204-233``): a
+    DataFrame indexed by (distance, error weight) with columns 'subset prob', 'survival prob',
+    'm', 'n'; every subset's ``n`` fixed-weight shots run on the device."""
+    import pandas as pd
+    frames = []
+    for d in ds:
+        code = code_class(d, noise=noise, parametrization=parametrization)
+        frames.append(decoder_class(code).subset_sample(noise_level, n, tol=tol))
+    return pd.concat(frames, keys=ds, names=['d'])

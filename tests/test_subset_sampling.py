@@ -152,3 +152,8 @@ def test_subset_sample_dataframe_and_estimate():
     random.seed(4)
     m, shots = cl.SCHEME.sim_cycles_given_weight(macar, (1, 1), 300)
     assert shots == 300 and 0 <= m <= 300
+    # the sweep driver (localuf/sim/accuracy/monte_carlo.py:204-233)
+    random.seed(5)
+    df = L.sim.accuracy.subset_sample([3, 5], 0.05, 2000, L.Surface, L.decoders.UF, 'code capacity')
+    assert df.index.names[0] == 'd' and set(df.index.get_level_values(0)) == {3, 5}
+    assert list(df.columns) == ['subset prob', 'survival prob', 'm', 'n']
