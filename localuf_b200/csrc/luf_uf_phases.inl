@@ -403,25 +403,25 @@ LUF_DEV uint32_t merge_count(const GraphView& g, const Shot& s, int lane, int nl
     return c;
 }
 
-// Compact this round's newly FULL edges into the list in ascending edge id
-// (cnt[2] = their number) and clear the bitmap;
-// if they do not fit, the bitmap is left for merge_rest.
+// Compact this round's newly FULL edges into the list in ascending edge id and clear their bits:
+// cnt[2] = how many were taken (at most the list's capacity), cnt[3] = how many stay in the bitmap for
+// the next chunk.  Chunks are merged one after the other, lowest edge ids first, which is the serial order.
 LUF_DEV void ph_merge_gather(const GraphView& g, const Shot& s, int lane, int nl)
 {
     const int wpl = (g.WE + nl - 1) / nl;
     const int w0 = lane * wpl, w1 = w0 + wpl < g.WE ? w0 + wpl : g.WE;
     uint32_t pos, total;
     LUF_T_EXSCAN(merge_count(g, s, lane, nl), lane, nl, pos, total);
-    if (lane == 0) { s.cnt[0] = 0; s.cnt[1] = 0; s.cnt[2] = total; s.cnt[3] = 0; }
-    if (total > LUF_T_LIST_CAP) return;
-    for (int w = w0; w < w1; ++w) {
+    const uint32_t take = total < LUF_T_LIST_CAP ? total : LUF_T_LIST_CAP;
+    if (lane == 0) { s.cnt[0] = 0; s.cnt[1] = 0; s.cnt[2] = take; s.cnt[3] = total - take; }
+    for (int w = w0; w < w1 && pos < take; ++w) {
         uint32_t bits = s.newfull[w];
         if (!bits) continue;
-        s.newfull[w] = 0;
-        while (bits) {
+        while (bits && pos < take) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             s.list[pos++] = (uint32_t)(32 * w + b);
         }
+        s.newfull[w] = bits;
     }
 }
 
@@ -469,25 +469,6 @@ LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uin
         ++placed;
     }
     return placed;
-}
-
-// Overflow path (more newly FULL edges than the list holds): one lane merges
-// them in ascending edge id, with path compression.
-template <int TF>
-LUF_DEV void merge_rest(const GraphView& g, const Shot& s, int flags)
-{
-    for (int w = 0; w < g.WE; ++w) {
-        uint32_t bits = s.newfull[w];
-        if (!bits) continue;
-        s.newfull[w] = 0;
-        while (bits) {
-            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t e = (uint32_t)(32 * w + b);
-            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-            const uint32_t cu = find_compress(s, uv & 0xFFFFu), cv = find_compress(s, uv >> 16);
-            union_roots<TF>(g, s, flags, e, cu, cv);
-        }
-    }
 }
 
 // ------------------------------------------------------------- phase 3: peel
@@ -652,14 +633,18 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
         if (!LUF_T_ANY(active)) break;
         ++rounds;
         LUF_STAT(0, 1); LUF_STAT(rounds == 1 ? 1 : 2, active);
-        uint32_t n = 0;
-        LUF_T_SCAN_PREP(merge_count(g, s, lane, nl));
-        LUF_T_PHASE(ph_merge_gather(g, s, lane, nl));
-        LUF_T_PHASE(n = s.cnt[2]);
-        LUF_STAT(3, n); LUF_STAT(4, n > 32); LUF_STAT(rounds == 1 ? 8 : 9, n);
-        if (n <= LUF_T_LIST_CAP) {
+        for (;;) {                             // chunks of at most LUF_T_LIST_CAP edges, lowest edge ids first
+            uint32_t n = 0, left = 0;
+            LUF_T_SCAN_PREP(merge_count(g, s, lane, nl));
+            LUF_T_PHASE(ph_merge_gather(g, s, lane, nl));
+            LUF_T_PHASE(n = s.cnt[2]; left = s.cnt[3]);
+            LUF_STAT(3, n); LUF_STAT(4, n > 32); LUF_STAT(rounds == 1 ? 8 : 9, n);
             uint32_t done = 0;
             for (uint32_t guard = 0; guard <= n; ++guard) {           // at least one edge is placed per iteration
+                if (iter == 0) {                                      // tags used up (huge graphs): start over
+                    LUF_T_PHASE(for (int w = lane; w < LUF_T_CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu);
+                    iter = 0xFFFFu;
+                }
                 const uint32_t tag = iter-- << 16;
                 uint32_t placed = 0;
                 LUF_T_PHASE(placed += ph_merge_claim<TF>(g, s, flags, n, tag, guard == 0, lane, nl));
@@ -668,9 +653,7 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
                 LUF_STAT(5, 1); LUF_STAT(rounds == 1 ? 6 : 7, 1);
                 if (done >= n) break;
             }
-        }
-        else {                             // overflow: one lane, ascending edge id, straight from the bitmap
-            LUF_T_PHASE(if (lane == 0) merge_rest<TF>(g, s, flags));
+            if (!left) break;
         }
     }
     // hand over to the peel: counters cleared, visited bitmap (in the claim table) cleared
