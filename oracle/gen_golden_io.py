@@ -31,6 +31,12 @@ IO_CASES = [
     ('io_sf3_cl', dict(code='Surface', d=3, noise='circuit-level', kwargs=dict(scheme='frugal')), {}, 0.10, 50, 76),
     ('io_sf5_cl_11', dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='frugal')),
      dict(schedule='1:1'), 0.04, 24, 77),
+    ('io_rep5_phen_order', dict(code='Repetition', d=5, noise='phenomenological', kwargs=dict(scheme='frugal')),
+     dict(schedule='1:1', _neighbor_order=('U', 'W', 'E', 'D')), 0.20, 60, 79),          # the order of the demo notebook, cell 2
+    ('io_sf5_cl_order', dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='frugal')),
+     dict(_neighbor_order=('SEU', 'S', 'SD', 'EU', 'E', 'U', 'D', 'W', 'WD', 'NU', 'N', 'NWD')), 0.05, 24, 80),
+    ('io_sf5_phen_order', dict(code='Surface', d=5, noise='phenomenological', kwargs=dict(scheme='frugal')),
+     dict(_neighbor_order=('U', 'D', 'E', 'W', 'S', 'N', 'NWD', 'NU', 'WD', 'EU', 'SD', 'SEU')), 0.06, 24, 81),
     ('io_sf5_cl_notime', dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='frugal')),
      dict(_include_timelike_lowest_edges=False), 0.04, 16, 78),
 ]

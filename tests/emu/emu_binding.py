@@ -143,10 +143,10 @@ class Emu:
 class EmuStream:
     """Host emulation of the Snowflake / frugal kernel phases for one window."""
 
-    def __init__(self, code):
+    def __init__(self, code, tables=None):
         from localuf_b200 import _window
         from localuf_b200._engine import make_window_desc
-        self.tables = _window.build(code)
+        self.tables = _window.build(code) if tables is None else tables
         self.noise = code.NOISE
         self.desc, self._keep = make_window_desc(self.tables)
         self.W = (self.tables.EL + 31) // 32

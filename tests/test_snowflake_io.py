@@ -36,7 +36,7 @@ NOTEBOOK_SF3_OUT = ['0000000000000000000000000000', '000000000000000000000000000
 def on_emulation(dec):
     """Route the decoder's device call to the host build of the same kernel phases."""
     import emu_binding
-    emu = emu_binding.EmuStream(dec.CODE)
+    emu = emu_binding.EmuStream(dec.CODE, dec._tables)          # the decoder's own neighbour order
 
     def run(rows):
         rt, floor, _ = emu.stream(dec._flags | _engine.SF_SYNDROME, np.stack(rows))
