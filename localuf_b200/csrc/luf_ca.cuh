@@ -29,7 +29,11 @@ enum { FLAG_ACTIS_UNOPTIMAL = 4 };
 #ifndef LUF_CA_TLIST_CAP
   #define LUF_CA_TLIST_CAP 256
 #endif
-static const uint32_t CA_TLIST_CAP = LUF_CA_TLIST_CAP;    // tests shrink it to force the bitmap path
+static const uint32_t CA_TLIST_CAP = LUF_CA_TLIST_CAP;    // warp tiles; tests shrink it to force the bitmap path
+#ifndef LUF_CA_CTA_TLIST_CAP
+  #define LUF_CA_CTA_TLIST_CAP 2048
+#endif
+static const uint32_t CA_CTA_TLIST_CAP = LUF_CA_CTA_TLIST_CAP;   // block tiles
 
 struct CaView {
     int N, B, E, K;             // K directions; slots >= K/2 are the edges a node owns (it is their first endpoint)
@@ -52,7 +56,8 @@ struct CaLayout {
     uint32_t defect, err, corr; // u32[WD] / u32[WE] / u32[WE]
     uint32_t touched;           // u32[WN]  Macar: nodes that are a defect or touch a fully grown edge (the only ones that can act)
     uint32_t glob;              // u32[4]  Actis collection-level next_busy_signal / next_active_signal; Macar: [2] = fill of tlist
-    uint32_t tlist;             // u16[CA_TLIST_CAP]  Macar: the touched nodes, compacted (rebuilt after every growth step)
+    uint32_t tlist_cap;         // entries of tlist
+    uint32_t tlist;             // u16[tlist_cap]  Macar: the touched nodes, compacted (rebuilt after every growth step)
     uint32_t bytes;
 };
 
@@ -62,6 +67,7 @@ struct CaShot {
     uint8_t *fl, *ast, *cnt;
     uint32_t *growth, *rx_anyon, *rx_defect, *rx_busy, *rx_active, *defect, *err, *corr, *glob, *touched;
     uint16_t* tlist;
+    uint32_t tcap;              // capacity of tlist
 };
 
 LUF_DEV CaShot ca_bind(const CaLayout& l, unsigned char* b)
@@ -78,6 +84,7 @@ LUF_DEV CaShot ca_bind(const CaLayout& l, unsigned char* b)
     s.glob = (uint32_t*)(b + l.glob);
     s.touched = (uint32_t*)(b + l.touched);
     s.tlist = (uint16_t*)(b + l.tlist);
+    s.tcap = l.tlist_cap;
     return s;
 }
 
@@ -156,7 +163,7 @@ LUF_DEV void ca_for_nodes(const CaView& g, const CaShot& s, int lane, int nl, F&
 {
     if (SPARSE) {
         const uint32_t total = s.glob[2];
-        if (total <= CA_TLIST_CAP) {                // balanced: one touched node per lane and trip
+        if (total <= s.tcap) {                      // balanced: one touched node per lane and trip
             for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) f((int)s.tlist[i]);
         } else
             for (int w = lane; w < g.WN; w += nl) {
@@ -179,7 +186,7 @@ LUF_DEV void ca_gather_touched(const CaView& g, const CaShot& s, int lane, int n
     for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(s.touched[w]);
     if (!c) return;
     uint32_t pos = luf_atomic_add(&s.glob[2], c);
-    if (pos + c > CA_TLIST_CAP) return;
+    if (pos + c > s.tcap) return;
     for (int w = w0; w < w1; ++w) {
         uint32_t bits = s.touched[w];
         while (bits) {
@@ -432,58 +439,30 @@ LUF_DEV void actis_waiter_advance(const CaView& g, CaCtl& c, int flags)
         c.n_countdown -= 1;
 }
 
-// ------------------------------------------------------------------- driver
-// LUF.decode = validate (luf/main.py:112-145) then peel (:147-166).  Writes
-// (tSV, tBP) to steps; exports the growth after validation if growth_out.
-// Returns the west parity of the correction (per lane on the device).
-template <bool ACTIS>
-LUF_DEV uint32_t ca_decode(const CaView& g, const CaShot& s, int flags, int* t_sv, int* t_bp,
-                           uint32_t* growth_out, int lane, int nl)
-{
-    CaCtl c;
-    c.stage = ST_GROWING; c.step = 0;
-    c.n_busy = 0; c.n_valid = ACTIS ? 0 : 1; c.n_countdown = 0; c.n_busy_signal = 0; c.n_active_signal = 0;
-    c.n_next_active_signal = 0;
-    int tsv = 0, tbp = 0, exported = 0;
-    uint32_t parity = 0;
-    (void)lane;
-    if (!ACTIS) { LUF_PHASE(ca_gather_touched(g, s, lane, nl)); }     // glob[2] == 0 after ca_reset
-    while (c.stage != ST_DONE) {
-        if (c.stage == ST_BURNING && !exported) {
-            exported = 1;
-            if (growth_out) { LUF_PHASE(for (int w = lane; w < g.GW; w += nl) growth_out[w] = s.growth[w]); }
-        }
-        const int in_sv = c.stage < ST_BURNING;
-        const int grew = !ACTIS && c.stage == ST_GROWING;                // this step may touch new nodes
-        int busy, valid;
-        if (ACTIS) {
-            LUF_PHASE(actis_phase_a(g, s, c, lane, nl));
-            // what node 0 handed to the collection this timestep (ControllerFriendship.relay_signals)
-            const int next_busy_signal = (int)s.glob[0];
-            c.n_next_active_signal |= (int)s.glob[1];
-            actis_waiter_advance(g, c, flags);                       // ActisNodes.advance, :565-567
-            LUF_PHASE(actis_phase_b(g, s, c, lane, nl));
-            c.n_busy_signal = next_busy_signal;                      // _update_unphysicals_for_actis, :575-581
-            c.n_active_signal = c.n_next_active_signal;
-            busy = c.n_busy; valid = c.n_valid;
-        } else {
-            uint32_t acc = 0;
-            LUF_PHASE(parity ^= macar_phase_a(g, s, c.stage, lane, nl));
-            LUF_PHASE(acc |= macar_phase_b(g, s, c.stage, lane, nl));
-            busy = LUF_ANY(acc & 1u); valid = !LUF_ANY(acc & 2u);
-        }
-        const int growth_changed = ca_controller_advance(c, busy, valid);
-        if (grew) {                                                      // newly touched nodes join the list
-            LUF_PHASE(if (lane == 0) s.glob[2] = 0);
-            LUF_PHASE(ca_gather_touched(g, s, lane, nl));
-        }
-        if (growth_changed) { LUF_PHASE(ca_snapshot_access<ACTIS>(g, s, lane, nl)); }
-        c.step += 1;
-        if (in_sv) ++tsv; else ++tbp;
-        if (tsv + tbp >= CA_MAX_STEPS) { tsv = -1; tbp = -1; break; }
-    }
-    *t_sv = tsv; *t_bp = tbp;
-    return parity;
-}
-
 }  // namespace luf
+
+// ------------------------------------------------------------------- driver
+// The decode driver is compiled once per tile shape (LUF_CT_PHASE / LUF_CT_ANY): luf::ca_warp (one warp per
+// shot) and luf::ca_cta (one thread block per shot: Actis, whose every timestep visits every node, and
+// large graphs).
+#define LUF_CA_NS ca_warp
+#define LUF_CT_PHASE(stmt) LUF_PHASE(stmt)
+#define LUF_CT_ANY(x) LUF_ANY(x)
+#include "luf_ca_drivers.inl"
+#undef LUF_CA_NS
+#undef LUF_CT_PHASE
+#undef LUF_CT_ANY
+namespace luf { using namespace ca_warp; }
+
+#define LUF_CA_NS ca_cta
+#if defined(LUF_HOST_EMU)
+  #define LUF_CT_PHASE(stmt) LUF_PHASE(stmt)
+  #define LUF_CT_ANY(x) LUF_ANY(x)
+#else
+  #define LUF_CT_PHASE(stmt) { stmt; } __syncthreads();
+  #define LUF_CT_ANY(x) __syncthreads_or((x) != 0)
+#endif
+#include "luf_ca_drivers.inl"
+#undef LUF_CA_NS
+#undef LUF_CT_PHASE
+#undef LUF_CT_ANY

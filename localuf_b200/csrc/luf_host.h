@@ -162,7 +162,7 @@ inline std::string pack_ca(const luf_graph_desc& d, PackedCa& out)
     return "";
 }
 
-inline CaLayout make_ca_layout(int N, int B, int E, bool actis, bool keep_err)
+inline CaLayout make_ca_layout(int N, int B, int E, bool actis, bool keep_err, uint32_t tlist_cap = CA_TLIST_CAP)
 {
     CaLayout l;
     uint32_t off = 0;
@@ -178,7 +178,8 @@ inline CaLayout make_ca_layout(int N, int B, int E, bool actis, bool keep_err)
     l.corr = take(4u * WE);
     l.glob = take(16);
     l.touched = take(4u * WN);
-    l.tlist = take(2u * CA_TLIST_CAP);
+    l.tlist_cap = tlist_cap;
+    l.tlist = take(2u * tlist_cap);
     l.err = keep_err ? take(4u * WE) : 0;
     l.bytes = off;
     return l;

@@ -206,6 +206,62 @@ __global__ void k_mc_ca(GraphView gv, CaView g, CaLayout l, SampleParams sp, int
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
 }
 
+// The same two kernels with one thread block per shot (luf::ca_cta).
+template <bool ACTIS>
+__global__ void k_decode_ca_cta(CaView g, CaLayout l, int flags, long long nshots,
+                                const uint32_t* __restrict__ syn, uint32_t* __restrict__ corr,
+                                uint32_t* __restrict__ growth2b, int32_t* __restrict__ steps)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
+    const CaShot s = ca_bind(l, smem);
+    for (long long k = blockIdx.x; k < nshots; k += gridDim.x) {
+        ca_reset<ACTIS>(g, s, lane, nl);
+        __syncthreads();
+        for (int w = lane; w < g.WD; w += nl) s.defect[w] = __ldg(&syn[k * g.WD + w]);
+        __syncthreads();
+        ca_load(g, s, lane, nl);
+        __syncthreads();
+        int tsv, tbp;
+        ca_cta::ca_decode<ACTIS>(g, s, flags, &tsv, &tbp, growth2b ? growth2b + k * g.GW : nullptr, lane, nl);
+        for (int w = lane; w < g.WE; w += nl) corr[k * g.WE + w] = s.corr[w];
+        if (steps && lane == 0) { steps[2 * k] = tsv; steps[2 * k + 1] = tbp; }
+        __syncthreads();
+    }
+}
+
+template <bool ACTIS>
+__global__ void k_mc_ca_cta(GraphView gv, CaView g, CaLayout l, SampleParams sp, int flags,
+                            unsigned long long shot0, long long nshots, unsigned long long* counts)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
+    const CaShot s = ca_bind(l, smem);
+    Shot samp;
+    samp.err = nullptr; samp.defect = s.defect;
+    unsigned int fails = 0;
+    unsigned long long sum_sv = 0, sum_bp = 0;
+    for (long long k = blockIdx.x; k < nshots; k += gridDim.x) {
+        uint32_t parity = 0;
+        ca_reset<ACTIS>(g, s, lane, nl);
+        __syncthreads();
+        // 32 sampling lanes whatever the tile: a shot's noise does not depend on the tile shape
+        if (lane < 32) parity ^= ph_sample(gv, samp, sp, shot0 + (unsigned long long)k, lane, 32);
+        __syncthreads();
+        ca_load(g, s, lane, nl);
+        __syncthreads();
+        int tsv, tbp;
+        parity ^= ca_cta::ca_decode<ACTIS>(g, s, flags, &tsv, &tbp, nullptr, lane, nl);
+        fails += (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
+        sum_sv += (unsigned long long)tsv; sum_bp += (unsigned long long)tbp;
+    }
+    if (lane == 0) {
+        if (fails) atomicAdd(&counts[0], (unsigned long long)fails);
+        atomicAdd(&counts[2], sum_sv); atomicAdd(&counts[3], sum_bp);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+}
+
 // Forward scheme (_schemes.py:392-450) around UF (MACAR = false) or Macar.
 struct FwArgs {
     GraphView gv; Layout ul; CaView cv; CaLayout cl; FwView fw; FwLayout fl; SampleTab buffer_tab;
@@ -482,7 +538,7 @@ struct luf_graph {
     PackedCa ca_host;
     std::string ca_why;           // why Macar/Actis cannot run on this graph ("" = they can)
     CaView ca_view{};
-    CaLayout lay_macar{}, lay_actis{};
+    CaLayout lay_macar{}, lay_actis{}, lay_macar_cta{}, lay_actis_cta{};
     // forward scheme (luf_forward_attach)
     bool has_forward = false;
     PackedForward fw_host;
@@ -626,6 +682,59 @@ static bool use_cta_tiles(const luf_graph* g, uint32_t warp_slice_bytes, uint32_
     if (env && !strcmp(env, "warp")) return false;
     if (env && !strcmp(env, "cta")) return true;
     return (size_t)10 * warp_slice_bytes > (size_t)g->max_smem;
+}
+
+// Macar: blocks from about a thousand nodes on (cfg3, N = 1452: 20.8 M shots/s with two warps per shot
+// against 18.3 M with one; d = 21 p = 0.01: 1.53 M against 0.094 M).  Actis visits every node in every
+// timestep, so a block per shot pays from a few hundred nodes on.  LUF_CA_TILE=warp|cta overrides.
+static bool use_ca_cta(const luf_graph* g, bool actis)
+{
+    const char* env = getenv("LUF_CA_TILE");
+    const uint32_t warp_bytes = actis ? g->lay_actis.bytes : g->lay_macar.bytes;
+    const uint32_t cta_bytes = actis ? g->lay_actis_cta.bytes : g->lay_macar_cta.bytes;
+    if (cta_bytes > (uint32_t)g->max_smem) return false;
+    if (env && !strcmp(env, "warp")) return false;
+    if (env && !strcmp(env, "cta")) return true;
+    (void)warp_bytes;
+    return g->ca_view.N >= (actis ? 256 : 1024);
+}
+
+// One block per shot for the cellular automata: `want` threads (a multiple of 32); keep_resident caps them so
+// that no fewer shots stay resident than shared memory allows (Macar: few touched nodes per shot; Actis
+// sweeps all nodes every timestep and prefers the threads: cfg3 328 k shots/s with 128, 279 k with 64).
+template <class K>
+static int plan_ca_cta_launch(luf_graph* g, K kernel, uint32_t bytes, long long nshots, LaunchCfg* cfg, int want,
+                              bool keep_resident = true)
+{
+    if (bytes > (uint32_t)g->max_smem)
+        return fail(LUF_ERR_UNSUPPORTED, "one shot's decoder state (" + std::to_string(bytes) + " B) exceeds the shared memory of an SM");
+    const int env_threads = getenv("LUF_CA_CTA_THREADS") ? atoi(getenv("LUF_CA_CTA_THREADS")) : 0;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    cudaFuncAttributes attr;
+    CUDA_TRY(cudaFuncGetAttributes(&attr, kernel));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 64, bytes));
+    if (per_sm < 1) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    int most = keep_resident ? (2048 / per_sm) & ~31 : 1024;
+    const int by_regs = (65536 / (attr.numRegs > 0 ? attr.numRegs : 64) / per_sm) & ~31;
+    if (keep_resident && most > by_regs) most = by_regs;
+    if (most > attr.maxThreadsPerBlock) most = attr.maxThreadsPerBlock & ~31;
+    if (most > 1024) most = 1024;
+    if (most < 64) most = 64;
+    int threads = (want + 31) & ~31;
+    if (threads < 64) threads = 64;
+    if (threads > most) threads = most;
+    if (env_threads >= 32 && env_threads <= 1024) threads = env_threads & ~31;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, bytes));
+    if (per_sm < 1) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    if (getenv("LUF_DEBUG_PLAN"))
+        fprintf(stderr, "[luf] CA launch plan (block per shot): %u B per shot, %d threads per block, %d blocks per SM\n", bytes, threads, per_sm);
+    long long blocks = (long long)g->sm_count * per_sm;
+    if (blocks > nshots) blocks = nshots;
+    if (blocks < 1) blocks = 1;
+    cfg->grid = (int)blocks; cfg->block = threads; cfg->smem = bytes;
+    return 0;
 }
 
 static int check_device(void)
@@ -1023,6 +1132,12 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
         }
         g->lay_macar = make_ca_layout(q.N, q.B, q.E, false, false);
         g->lay_actis = make_ca_layout(q.N, q.B, q.E, true, false);
+        {   // block tiles: the touched-node list covers every node when that costs less than a tenth of the state
+            uint32_t cap = CA_CTA_TLIST_CAP;
+            if (CA_CTA_TLIST_CAP >= 256u && (uint32_t)q.N > cap && 2u * (uint32_t)q.N < g->lay_macar.bytes / 10u) cap = ((uint32_t)q.N + 7u) & ~7u;
+            g->lay_macar_cta = make_ca_layout(q.N, q.B, q.E, false, false, cap);
+            g->lay_actis_cta = make_ca_layout(q.N, q.B, q.E, true, false, 8);
+        }
     }
     *out = g;
     return 0;
@@ -1119,13 +1234,25 @@ int luf_decode_batch(luf_graph* g, int decoder, int flags, int64_t nshots, const
     CUDA_TRY(cudaSetDevice(g->device));
     LaunchCfg c;
     if (decoder == LUF_DEC_MACAR) {
+        if (use_ca_cta(g, false)) {
+            if (int rc = plan_ca_cta_launch(g, k_decode_ca_cta<false>, g->lay_macar_cta.bytes, nshots, &c, g->ca_view.N / 16)) return rc;
+            k_decode_ca_cta<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(
+                g->ca_view, g->lay_macar_cta, flags, nshots, syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+        } else {
         if (int rc = plan_launch(g, k_decode_ca<false>, g->lay_macar.bytes, nshots, &c)) return rc;
         k_decode_ca<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(
             g->ca_view, g->lay_macar, flags, nshots, syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+        }
     } else if (decoder == LUF_DEC_ACTIS) {
+        if (use_ca_cta(g, true)) {
+            if (int rc = plan_ca_cta_launch(g, k_decode_ca_cta<true>, g->lay_actis_cta.bytes, nshots, &c, g->ca_view.N / 12, false)) return rc;
+            k_decode_ca_cta<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(
+                g->ca_view, g->lay_actis_cta, flags, nshots, syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+        } else {
         if (int rc = plan_launch(g, k_decode_ca<true>, g->lay_actis.bytes, nshots, &c)) return rc;
         k_decode_ca<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(
             g->ca_view, g->lay_actis, flags, nshots, syn_bits_dev, corr_bits_dev, growth2b_dev, steps_dev);
+        }
     } else {
         if (use_cta_tiles(g, g->lay_decode.bytes, g->lay_decode_cta.bytes)) {
             if (int rc = plan_cta_launch(g, k_decode_uf_cta, g->lay_decode_cta.bytes, nshots, &c)) return rc;
@@ -1199,13 +1326,25 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
     const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
     LaunchCfg c;
     if (decoder == LUF_DEC_MACAR) {
-        if (int rc = plan_launch(g, k_mc_ca<false>, g->lay_macar.bytes, nshots, &c)) return rc;
-        k_mc_ca<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_macar, sp, flags,
-                                                                           shot0, nshots, counts_dev);
+        if (use_ca_cta(g, false)) {
+            if (int rc = plan_ca_cta_launch(g, k_mc_ca_cta<false>, g->lay_macar_cta.bytes, nshots, &c, g->ca_view.N / 16)) return rc;
+            k_mc_ca_cta<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_macar_cta, sp, flags,
+                                                                                   shot0, nshots, counts_dev);
+        } else {
+            if (int rc = plan_launch(g, k_mc_ca<false>, g->lay_macar.bytes, nshots, &c)) return rc;
+            k_mc_ca<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_macar, sp, flags,
+                                                                               shot0, nshots, counts_dev);
+        }
     } else if (decoder == LUF_DEC_ACTIS) {
-        if (int rc = plan_launch(g, k_mc_ca<true>, g->lay_actis.bytes, nshots, &c)) return rc;
-        k_mc_ca<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_actis, sp, flags,
-                                                                          shot0, nshots, counts_dev);
+        if (use_ca_cta(g, true)) {
+            if (int rc = plan_ca_cta_launch(g, k_mc_ca_cta<true>, g->lay_actis_cta.bytes, nshots, &c, g->ca_view.N / 12, false)) return rc;
+            k_mc_ca_cta<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_actis_cta, sp, flags,
+                                                                                  shot0, nshots, counts_dev);
+        } else {
+            if (int rc = plan_launch(g, k_mc_ca<true>, g->lay_actis.bytes, nshots, &c)) return rc;
+            k_mc_ca<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_actis, sp, flags,
+                                                                              shot0, nshots, counts_dev);
+        }
     } else {
         // the decoder flags are compile-time constants of the fused kernel
 #define LUF_MC_UF(TF) { if (int rc = plan_launch(g, k_mc_uf<TF>, g->lay_fused.bytes, nshots, &c, 14)) return rc; \

@@ -136,9 +136,10 @@ int emu_mc_uf(const luf_graph_desc* d, int flags, const double* class_p, unsigne
 
 // Macar (decoder 1) / Actis (decoder 2): syndromes in, (tSV, tBP), growth after
 // validation and correction out.
-int emu_decode_ca(const luf_graph_desc* d, int decoder, int flags, long long nshots, const uint32_t* syn,
-                  uint32_t* corr, uint32_t* growth2b, int32_t* steps)
+int emu_decode_ca_tile(const luf_graph_desc* d, int decoder, int flags, long long nshots, const uint32_t* syn,
+                       uint32_t* corr, uint32_t* growth2b, int32_t* steps, int nl)
 {
+    const bool cta = nl != 32;
     PackedCa p;
     if (!pack_ca(*d, p).empty()) return -1;
     const bool actis = decoder == 2;
@@ -149,22 +150,27 @@ int emu_decode_ca(const luf_graph_desc* d, int decoder, int flags, long long nsh
     g.WE = words32(p.E); g.WD = words32(p.N - p.B); g.WN = words32(p.N); g.GW = (p.E + 15) / 16;
     g.nbr = p.nbr.data(); g.west_mask = west.data(); g.span = p.span.data(); g.relay = p.relay.data();
     g.global_span = p.global_span;
-    const CaLayout l = make_ca_layout(p.N, p.B, p.E, actis, false);
+    const CaLayout l = cta ? make_ca_layout(p.N, p.B, p.E, actis, false, CA_CTA_TLIST_CAP) : make_ca_layout(p.N, p.B, p.E, actis, false);
     std::vector<unsigned char> mem(l.bytes);
     const CaShot s = ca_bind(l, mem.data());
-    const int nl = 32;
     for (long long k = 0; k < nshots; ++k) {
         if (actis) { LUF_PHASE(ca_reset<true>(g, s, lane, nl)); } else { LUF_PHASE(ca_reset<false>(g, s, lane, nl)); }
         for (int w = 0; w < g.WD; ++w) s.defect[w] = syn[k * g.WD + w];
         LUF_PHASE(ca_load(g, s, lane, nl));
         int tsv = 0, tbp = 0;
         uint32_t* gout = growth2b ? growth2b + k * g.GW : nullptr;
-        if (actis) ca_decode<true>(g, s, flags, &tsv, &tbp, gout, 0, nl);
-        else ca_decode<false>(g, s, flags, &tsv, &tbp, gout, 0, nl);
+        if (cta) { if (actis) ca_cta::ca_decode<true>(g, s, flags, &tsv, &tbp, gout, 0, nl); else ca_cta::ca_decode<false>(g, s, flags, &tsv, &tbp, gout, 0, nl); }
+        else { if (actis) ca_warp::ca_decode<true>(g, s, flags, &tsv, &tbp, gout, 0, nl); else ca_warp::ca_decode<false>(g, s, flags, &tsv, &tbp, gout, 0, nl); }
         std::memcpy(corr + k * g.WE, s.corr, 4u * g.WE);
         if (steps) { steps[2 * k] = tsv; steps[2 * k + 1] = tbp; }
     }
     return 0;
+}
+
+int emu_decode_ca(const luf_graph_desc* d, int decoder, int flags, long long nshots, const uint32_t* syn,
+                  uint32_t* corr, uint32_t* growth2b, int32_t* steps)
+{
+    return emu_decode_ca_tile(d, decoder, flags, nshots, syn, corr, growth2b, steps, 32);
 }
 
 // Forward scheme on given fresh errors (one stream); decoder 0 = UF, 1 = Macar.

@@ -24,7 +24,7 @@ def build(tiny_lists=False):
     if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in SRCS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(['g++', '-O1', '-g', '-fPIC', '-shared', '-std=c++17', '-Wall', '-Wextra']
-                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2', '-DLUF_CTA_LIST_CAP=5', '-DLUF_CTA_LIST2_CAP=3', '-DLUF_CA_TLIST_CAP=4', '-DLUF_SF_ALIST_CAP=4', '-DLUF_SF_CTA_ALIST_CAP=6'] if tiny_lists else []) + ['-o', out, SRCS[0]],
+                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2', '-DLUF_CTA_LIST_CAP=5', '-DLUF_CTA_LIST2_CAP=3', '-DLUF_CA_TLIST_CAP=4', '-DLUF_SF_ALIST_CAP=4', '-DLUF_SF_CTA_ALIST_CAP=6', '-DLUF_CA_CTA_TLIST_CAP=5'] if tiny_lists else []) + ['-o', out, SRCS[0]],
                        check=True, capture_output=True)
     return out
 
@@ -115,14 +115,14 @@ class Emu:
         assert rc == 0
         return int(counts[0]), err, syn, corr
 
-    def decode_ca(self, decoder, flags, syn_bits):
+    def decode_ca(self, decoder, flags, syn_bits, nl=32):
         syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
         n = syn.shape[0]
         corr = np.zeros((n, self.WE), np.uint32)
         growth = np.zeros((n, self.WG), np.uint32)
         steps = np.zeros((n, 2), np.int32)
-        rc = lib().emu_decode_ca(C.byref(self.desc), decoder, flags, C.c_longlong(n), _vp(syn),
-                                 _vp(corr), _vp(growth), _vp(steps))
+        rc = lib().emu_decode_ca_tile(C.byref(self.desc), decoder, flags, C.c_longlong(n), _vp(syn),
+                                      _vp(corr), _vp(growth), _vp(steps), nl)
         assert rc == 0, rc
         return corr, growth, steps
 

@@ -41,3 +41,18 @@ def test_emu_macar_bitmap_path_with_tiny_node_list():
             np.testing.assert_array_equal(corr, arr['macar_corr'])
     finally:
         emu_binding.use_tiny_lists(False)
+
+
+@pytest.mark.parametrize('nl', [64, 256])
+@pytest.mark.parametrize('name', golden_names('ca_'))
+def test_emu_ca_block_tile_matches_reference(name, nl):
+    """The block-per-shot instance of the decode driver (luf::ca_cta; tiles of 64 and 256 lanes)."""
+    meta, arr = load_golden(name)
+    code = make_code(meta['spec'])
+    emu = emu_binding.Emu(code)
+    for key in meta['decoders']:
+        dec, flags = DECODERS[key]
+        corr, growth2b, steps = emu.decode_ca(dec, flags, arr['syn_bits'], nl=nl)
+        np.testing.assert_array_equal(steps, arr[f'{key}_steps'], err_msg=f'{name} {key} (tSV, tBP)')
+        np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{key}_growth'])
+        np.testing.assert_array_equal(corr, arr[f'{key}_corr'], err_msg=f'{name} {key} correction')

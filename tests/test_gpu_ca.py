@@ -93,3 +93,37 @@ def test_ca_python_api():
         L.decoders.Actis(L.Surface(3, 'phenomenological', scheme='forward'))
     with pytest.raises(ValueError):
         L.decoders.Macar(L.Surface(3, 'phenomenological', scheme='frugal'))
+
+
+@pytest.fixture(params=[128, 512])
+def block_tile(request, monkeypatch):
+    """One thread block per shot (luf::ca_cta), whatever the graph size."""
+    monkeypatch.setenv('LUF_CA_TILE', 'cta')
+    monkeypatch.setenv('LUF_CA_CTA_THREADS', str(request.param))
+
+
+@pytest.mark.parametrize('name', golden_names('ca_'))
+def test_ca_block_tile_matches_reference_goldens(name, block_tile):
+    test_ca_matches_reference_goldens(name)
+
+
+@pytest.mark.parametrize('spec,p,n_macar,n_actis', [
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.01, 1000, 200),
+    (dict(code='Surface', d=11, noise='phenomenological'), 0.01, 600, 48),
+])
+def test_ca_block_tile_pipeline_vs_oracle(spec, p, n_macar, n_actis, block_tile):
+    test_ca_pipeline_vs_oracle_on_gpu_samples(spec, p, n_macar, n_actis)
+
+
+def test_ca_mc_counts_do_not_depend_on_the_tile(monkeypatch):
+    """Same seed, same shots, same failure count and timestep sums on either tile."""
+    from localuf_b200 import _engine
+    code = make_code(dict(code='Surface', d=7, noise='phenomenological'))
+    eng = engine_of(code)
+    out = {}
+    for tile in ('warp', 'cta'):
+        monkeypatch.setenv('LUF_CA_TILE', tile)
+        for dec in (1, 2):
+            out[tile, dec] = (eng.mc_run_host(dec, 0, 0.02, 5, 0, 3000), eng.last_step_sums)
+    assert out['warp', 1] == out['cta', 1] and out['warp', 1][0][0] > 0
+    assert out['warp', 2] == out['cta', 2]

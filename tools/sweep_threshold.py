@@ -21,16 +21,16 @@ def main():
     ap.add_argument('--ps', default='0.015,0.026,0.035')
     ap.add_argument('--noise', default='phenomenological')
     ap.add_argument('--seconds', type=float, default=1.0)
-    ap.add_argument('--decoder', default='UF', choices=['UF', 'Snowflake'])
+    ap.add_argument('--decoder', default='UF', choices=['UF', 'Macar', 'Actis', 'Snowflake'])
     a = ap.parse_args()
     if a.decoder == 'Snowflake':
         return sweep_snowflake(a)
     print(f'{"d":>3s} {"p":>6s} {"N":>6s} {"E":>6s} {"shots":>9s} {"fails":>8s} {"rate":>9s} {"Mshots/s":>9s}')
     for d in (int(x) for x in a.ds.split(',')):
         code = L.Surface(d, a.noise)
-        dec = L.decoders.UF(code)
+        dec = getattr(L.decoders, a.decoder)(code)
         for p in (float(x) for x in a.ps.split(',')):
-            n = 2048
+            n = 64 if a.decoder == 'Actis' else 2048
             code.SCHEME.run(dec, p, n, seed=1)               # warm up (graph upload, launch plan)
             t0 = time.perf_counter(); code.SCHEME.run(dec, p, n, seed=2); dt = time.perf_counter() - t0
             n = max(n, min(1 << 24, int(n * a.seconds / max(dt, 1e-4))))
