@@ -269,6 +269,23 @@ int luf_stream_decode(luf_stream *s, int flags, int64_t nstreams, int32_t ncycle
 int luf_stream_mc(luf_stream *s, int flags, const double *class_p_host, uint64_t seed, uint64_t stream0,
                   int64_t nstreams, int32_t n, unsigned long long *counts_dev, int32_t *steps_dev, void *stream);
 
+/* Per-cycle confidence-score inputs -- replaces the `metrics` argument of Snowflake.decode
+ * (localuf/decoders/snowflake/main.py:222,266-297) and of Frugal.run / Frugal.advance
+ * (localuf/_schemes.py:573,586-590,636-644).  Same calls as above with two more outputs:
+ * growth2b_dev [..cycles][luf_stream_growth_words(s)] = the window's growth after each cycle, 2 bits per
+ * layered edge id (block b from the top at bit 64*W(EL)*b; feed it to luf_dcs_run for swim_distance and
+ * unclustered_edge_fraction); luf_stream_decode_metrics: mins_dev [nstreams][ncycles][2] =
+ * (min_defect_height, min_active_layer) after each cycle; luf_stream_mc_metrics: cycle_dev
+ * [nstreams][n*d][4] = (min_defect_height, min_active_layer, runtime 'all', runtime 'unrooting') after
+ * each TIMED cycle (throughput = 1 / runtime).  Both NULL = the plain calls. */
+int luf_stream_growth_words(const luf_stream *s);
+int luf_stream_decode_metrics(luf_stream *s, int flags, int64_t nstreams, int32_t ncycles,
+                              const uint32_t *fresh_bits_dev, int32_t *rt_dev, uint32_t *floor_bits_dev,
+                              int32_t *m_dev, uint32_t *growth2b_dev, int32_t *mins_dev, void *stream);
+int luf_stream_mc_metrics(luf_stream *s, int flags, const double *class_p_host, uint64_t seed, uint64_t stream0,
+                          int64_t nstreams, int32_t n, unsigned long long *counts_dev, int32_t *steps_dev,
+                          uint32_t *growth2b_dev, int32_t *cycle_dev, void *stream);
+
 int luf_stream_decode_host(luf_stream *s, int flags, int64_t nstreams, int32_t ncycles,
                            const uint32_t *fresh_bits_host, int32_t *rt_host, uint32_t *floor_bits_host,
                            int32_t *m_host);
@@ -283,6 +300,33 @@ int luf_stream_latency(luf_stream *s, int flags, const double *class_p_host, uin
 int luf_stream_latency_host(luf_stream *s, int flags, const double *class_p_host, uint64_t seed, uint64_t stream0,
                             int64_t nstreams, int32_t *lat_host);
 int64_t luf_stream_launch_count(const luf_stream *s);
+
+/* ---- decoder confidence scores of a batch of growth states -------------------------------------------
+ * Replaces BaseUF.unclustered_edge_fraction (localuf/decoders/_base_uf.py:106-121), BaseUF.swim_distance
+ * (:250-316: the shortest path between the two meta boundaries of _cached_swim_graph, where an ungrown edge
+ * costs its weight, a half-grown edge half of it and a fully grown or burnt edge nothing) and
+ * UF.unclustered_node_fraction (localuf/decoders/uf.py:188-197), for nshots growth states at once.  The
+ * graph is given flat, so the same call serves the batch decoders (growth2b of luf_decode_batch, edge ids
+ * of the code) and Snowflake's window (growth of luf_stream_*'s per-cycle export, layered edge ids). */
+typedef struct {
+    int32_t n_nodes, n_edges;
+    const int32_t *edge_u, *edge_v;  /* [n_edges]; an unused edge id has edge_u == edge_v and weight 0 */
+    const double *weight;            /* [n_edges] Noise.get_edge_weights(noise_level)[e][1] (noise/main.py:142-150,332-345); NULL = all 1 */
+    const uint8_t *in_growth;        /* [n_edges] 1 if the edge is a key of decoder.growth (it counts towards the edge
+                                      * fraction; Snowflake leaves the future-boundary edges out); NULL = all 1 */
+    const uint8_t *node_side;        /* [n_nodes] 1 = joined to the west meta boundary, 2 = to the east one, else 0 */
+} luf_dcs_desc;
+typedef struct luf_dcs luf_dcs;
+int luf_dcs_create(const luf_dcs_desc *desc, int device, luf_dcs **out);
+int luf_dcs_destroy(luf_dcs *h);
+/* growth2b_dev [nshots][stride_words] words of 2-bit fields (0 ungrown, 1 half, 2 full, 3 burnt), the first
+ * growth_words of each row valid (edges beyond are ungrown).  Outputs (each optional, [nshots]):
+ * swim_dev = swim distance, uef_dev = unclustered edge fraction, clustered_nodes_dev = number of nodes
+ * with a fully grown edge (unclustered node fraction = 1 - that / NODE_COUNT). */
+int luf_dcs_run(luf_dcs *h, int64_t nshots, const uint32_t *growth2b_dev, int64_t stride_words,
+                int32_t growth_words, double *swim_dev, double *uef_dev, int32_t *clustered_nodes_dev, void *stream);
+int luf_dcs_run_host(luf_dcs *h, int64_t nshots, const uint32_t *growth2b_host, int64_t stride_words,
+                     int32_t growth_words, double *swim_host, double *uef_host, int32_t *clustered_nodes_host);
 
 /* Number of kernel launches issued through this graph so far (bench.py's gpu_launches). */
 int64_t luf_launch_count(const luf_graph *g);

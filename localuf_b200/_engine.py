@@ -161,6 +161,9 @@ def _load():
         lib.luf_stream_mc.argtypes = [v, C.c_int, v, u64, u64, i64, C.c_int32, v, v, v]
         lib.luf_stream_decode_host.argtypes = [v, C.c_int, i64, C.c_int32, v, v, v, v]
         lib.luf_stream_mc_host.argtypes = [v, C.c_int, v, u64, u64, i64, C.c_int32, v, v]
+        lib.luf_stream_growth_words.argtypes = [v]
+        lib.luf_stream_decode_metrics.argtypes = [v, C.c_int, i64, C.c_int32, v, v, v, v, v, v, v]
+        lib.luf_stream_mc_metrics.argtypes = [v, C.c_int, v, u64, u64, i64, C.c_int32, v, v, v, v, v]
         lib.luf_stream_latency.argtypes = [v, C.c_int, v, u64, u64, i64, v, v]
         lib.luf_stream_latency_host.argtypes = [v, C.c_int, v, u64, u64, i64, v]
         _lib = lib
@@ -416,6 +419,47 @@ class StreamEngine:
         lat = np.zeros((nstreams, 3), np.int32)
         _check(_load().luf_stream_latency_host(self._h, flags, cp.ctypes.data, seed, stream0, nstreams, _ptr(lat)))
         return lat
+
+    # ---- per-cycle confidence-score inputs (device buffers are torch tensors: plumbing only)
+    @property
+    def growth_words(self) -> int:
+        return int(_load().luf_stream_growth_words(self._h))
+
+    def decode_metrics(self, flags: int, fresh_bits):
+        """As :meth:`decode_host`, plus the window's growth after every cycle (a DEVICE int32 tensor
+        [nstreams * ncycles, growth_words], input of ``luf_dcs_run``) and mins [nstreams, ncycles, 2] =
+        (min_defect_height, min_active_layer)."""
+        import torch
+        fresh = np.ascontiguousarray(fresh_bits, dtype=np.uint32)
+        ns, nc = fresh.shape[0], fresh.shape[1]
+        dev = torch.device('cuda', self.device)
+        with torch.cuda.device(dev):
+            fr = torch.from_numpy(fresh.view(np.int32)).to(dev)
+            rt = torch.zeros((ns, nc, 2), dtype=torch.int32, device=dev)
+            m = torch.zeros((ns, nc), dtype=torch.int32, device=dev)
+            floor = torch.zeros((ns, nc, self.W), dtype=torch.int32, device=dev)
+            growth = torch.zeros((ns * nc, self.growth_words), dtype=torch.int32, device=dev)
+            mins = torch.zeros((ns, nc, 2), dtype=torch.int32, device=dev)
+            _check(_load().luf_stream_decode_metrics(self._h, flags, ns, nc, _ptr(fr), _ptr(rt), _ptr(floor), _ptr(m),
+                                                     _ptr(growth), _ptr(mins), _stream()))
+            return (rt.cpu().numpy(), floor.cpu().numpy().view(np.uint32), m.cpu().numpy(), growth, mins.cpu().numpy())
+
+    def mc_metrics(self, flags: int, noise_level: float, seed: int, stream0: int, nstreams: int, n: int):
+        """As :meth:`mc_host` with steps, plus the growth after every TIMED cycle (DEVICE int32 tensor
+        [nstreams * n * d, growth_words]) and cycle [nstreams, n * d, 4] = (min_defect_height,
+        min_active_layer, runtime 'all', runtime 'unrooting')."""
+        import torch
+        cp = self.class_p(noise_level)
+        dev = torch.device('cuda', self.device)
+        nd = n * self.tables.d
+        with torch.cuda.device(dev):
+            counts = torch.zeros(4, dtype=torch.int64, device=dev)
+            steps = torch.zeros((nstreams, n, 2), dtype=torch.int32, device=dev)
+            growth = torch.zeros((nstreams * nd, self.growth_words), dtype=torch.int32, device=dev)
+            cycle = torch.zeros((nstreams, nd, 4), dtype=torch.int32, device=dev)
+            _check(_load().luf_stream_mc_metrics(self._h, flags, cp.ctypes.data, seed, stream0, nstreams, n,
+                                                 _ptr(counts), _ptr(steps), _ptr(growth), _ptr(cycle), _stream()))
+            return [int(x) for x in counts.cpu()], steps.cpu().numpy(), growth, cycle.cpu().numpy()
 
     def mc(self, flags, noise_level, seed, stream0, nstreams, n, counts, steps=None):
         cp = self.class_p(noise_level)

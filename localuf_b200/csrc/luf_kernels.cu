@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "luf_host.h"
+#include "luf_dcs.cuh"
 
 using namespace luf;
 
@@ -327,7 +328,8 @@ __global__ void k_fw_mc(FwArgs a, SampleParams sp, unsigned long long stream0, l
 // K3b parity path: Snowflake + frugal bookkeeping on GIVEN fresh errors.
 __global__ void k_sf_decode(SfView g, SfLayout l, int flags, long long nstreams, int ncycles,
                             const uint32_t* __restrict__ fresh, int32_t* __restrict__ rt,
-                            uint32_t* __restrict__ floor_bits, int32_t* __restrict__ m_out)
+                            uint32_t* __restrict__ floor_bits, int32_t* __restrict__ m_out,
+                            uint32_t* __restrict__ mgrowth, int32_t* __restrict__ mins)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, nl = WARP;
@@ -337,13 +339,15 @@ __global__ void k_sf_decode(SfView g, SfLayout l, int flags, long long nstreams,
     for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nstreams; k += stride) {
         const size_t row0 = (size_t)k * ncycles;
         sf_warp::sf_decode_stream(g, s, flags, ncycles, fresh + row0 * g.ELw, rt + 2 * row0,
-                                  floor_bits ? floor_bits + row0 * g.ELw : nullptr, m_out + row0, lane, nl);
+                                  floor_bits ? floor_bits + row0 * g.ELw : nullptr, m_out + row0,
+                                  mgrowth ? mgrowth + row0 * (size_t)(g.h * 2 * g.ELw) : nullptr, mins + 2 * row0, lane, nl);
     }
 }
 
 // Fused K1 + K3b + K4: one Frugal.run(n) memory experiment per warp.
 __global__ void k_sf_mc(SfView g, SfLayout l, SampleParams sp, int flags, unsigned long long stream0,
-                        long long nstreams, int n, unsigned long long* counts, int32_t* steps)
+                        long long nstreams, int n, unsigned long long* counts, int32_t* steps,
+                        uint32_t* __restrict__ mgrowth, int32_t* __restrict__ mcycle)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, nl = WARP;
@@ -354,7 +358,8 @@ __global__ void k_sf_mc(SfView g, SfLayout l, SampleParams sp, int flags, unsign
     long long cycles = 0, ra = 0, ru = 0;
     for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nstreams; k += stride)
         sf_run(g, s, sp, flags, stream0 + (unsigned long long)k, n, m_total, cycles, ra, ru,
-               steps ? steps + (size_t)k * n * 2 : nullptr, lane, nl);
+               steps ? steps + (size_t)k * n * 2 : nullptr,
+               mgrowth ? mgrowth + (size_t)k * n * g.d * (size_t)(g.h * 2 * g.ELw) : nullptr, mcycle + (size_t)k * n * g.d * 4, lane, nl);
     if (lane == 0) {
         atomicAdd(&counts[0], (unsigned long long)m_total); atomicAdd(&counts[1], (unsigned long long)cycles);
         atomicAdd(&counts[2], (unsigned long long)ra); atomicAdd(&counts[3], (unsigned long long)ru);
@@ -364,7 +369,8 @@ __global__ void k_sf_mc(SfView g, SfLayout l, SampleParams sp, int flags, unsign
 // The same two kernels with one thread block per window (luf::sf_cta): large windows.
 __global__ void k_sf_decode_cta(SfView g, SfLayout l, int flags, long long nstreams, int ncycles,
                                 const uint32_t* __restrict__ fresh, int32_t* __restrict__ rt,
-                                uint32_t* __restrict__ floor_bits, int32_t* __restrict__ m_out)
+                                uint32_t* __restrict__ floor_bits, int32_t* __restrict__ m_out,
+                                uint32_t* __restrict__ mgrowth, int32_t* __restrict__ mins)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
@@ -372,12 +378,14 @@ __global__ void k_sf_decode_cta(SfView g, SfLayout l, int flags, long long nstre
     for (long long k = blockIdx.x; k < nstreams; k += gridDim.x) {
         const size_t row0 = (size_t)k * ncycles;
         sf_cta::sf_decode_stream(g, s, flags, ncycles, fresh + row0 * g.ELw, rt + 2 * row0,
-                                 floor_bits ? floor_bits + row0 * g.ELw : nullptr, m_out + row0, lane, nl);
+                                 floor_bits ? floor_bits + row0 * g.ELw : nullptr, m_out + row0,
+                                 mgrowth ? mgrowth + row0 * (size_t)(g.h * 2 * g.ELw) : nullptr, mins + 2 * row0, lane, nl);
     }
 }
 
 __global__ void k_sf_mc_cta(SfView g, SfLayout l, SampleParams sp, int flags, unsigned long long stream0,
-                            long long nstreams, int n, unsigned long long* counts, int32_t* steps)
+                            long long nstreams, int n, unsigned long long* counts, int32_t* steps,
+                            uint32_t* __restrict__ mgrowth, int32_t* __restrict__ mcycle)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
@@ -386,7 +394,8 @@ __global__ void k_sf_mc_cta(SfView g, SfLayout l, SampleParams sp, int flags, un
     long long cycles = 0, ra = 0, ru = 0;
     for (long long k = blockIdx.x; k < nstreams; k += gridDim.x)
         sf_cta::sf_run(g, s, sp, flags, stream0 + (unsigned long long)k, n, m_total, cycles, ra, ru,
-                       steps ? steps + (size_t)k * n * 2 : nullptr, lane, nl);
+                       steps ? steps + (size_t)k * n * 2 : nullptr,
+                       mgrowth ? mgrowth + (size_t)k * n * g.d * (size_t)(g.h * 2 * g.ELw) : nullptr, mcycle + (size_t)k * n * g.d * 4, lane, nl);
     if (lane == 0) {
         atomicAdd(&counts[0], (unsigned long long)m_total); atomicAdd(&counts[1], (unsigned long long)cycles);
         atomicAdd(&counts[2], (unsigned long long)ra); atomicAdd(&counts[3], (unsigned long long)ru);
@@ -927,8 +936,20 @@ int64_t luf_stream_launch_count(const luf_stream* g) { return g ? g->launches : 
 int luf_stream_decode(luf_stream* g, int flags, int64_t nstreams, int32_t ncycles, const uint32_t* fresh_bits_dev,
                       int32_t* rt_dev, uint32_t* floor_bits_dev, int32_t* m_dev, void* stream)
 {
-    if (!g || !fresh_bits_dev || !rt_dev || !m_dev || nstreams < 0 || ncycles < 0)
+    return luf_stream_decode_metrics(g, flags, nstreams, ncycles, fresh_bits_dev, rt_dev, floor_bits_dev, m_dev,
+                                     nullptr, nullptr, stream);
+}
+
+int luf_stream_growth_words(const luf_stream* g) { return g ? g->view.h * 2 * g->view.ELw : 0; }
+
+int luf_stream_decode_metrics(luf_stream* g, int flags, int64_t nstreams, int32_t ncycles, const uint32_t* fresh_bits_dev,
+                              int32_t* rt_dev, uint32_t* floor_bits_dev, int32_t* m_dev, uint32_t* growth2b_dev,
+                              int32_t* mins_dev, void* stream)
+{
+    if (!g || !fresh_bits_dev || !rt_dev || !m_dev || nstreams < 0 || ncycles < 0 || (!growth2b_dev) != (!mins_dev))
         return fail(LUF_ERR_INVALID, "luf_stream_decode: bad argument");
+    if (growth2b_dev && (flags & LUF_SF_LATENCY_TAIL))
+        return fail(LUF_ERR_INVALID, "per-cycle metrics are not recorded on the drop-only tail of sample_latency");
     if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE | LUF_SF_SYNDROME | LUF_SF_LATENCY_TAIL))
         return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
     if (nstreams == 0 || ncycles == 0) return 0;
@@ -937,11 +958,13 @@ int luf_stream_decode(luf_stream* g, int flags, int64_t nstreams, int32_t ncycle
     if (use_stream_cta(g)) {
         if (int rc = plan_stream_cta_launch(g, k_sf_decode_cta, nstreams, &c)) return rc;
         k_sf_decode_cta<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_cta, flags, nstreams, ncycles,
-                                                                            fresh_bits_dev, rt_dev, floor_bits_dev, m_dev);
+                                                                            fresh_bits_dev, rt_dev, floor_bits_dev, m_dev,
+                                                                            growth2b_dev, mins_dev);
     } else {
         if (int rc = plan_stream_launch(g, k_sf_decode, nstreams, &c)) return rc;
         k_sf_decode<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, flags, nstreams, ncycles,
-                                                                        fresh_bits_dev, rt_dev, floor_bits_dev, m_dev);
+                                                                        fresh_bits_dev, rt_dev, floor_bits_dev, m_dev,
+                                                                        growth2b_dev, mins_dev);
     }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;
@@ -951,7 +974,15 @@ int luf_stream_decode(luf_stream* g, int flags, int64_t nstreams, int32_t ncycle
 int luf_stream_mc(luf_stream* g, int flags, const double* class_p_host, uint64_t seed, uint64_t stream0,
                   int64_t nstreams, int32_t n, unsigned long long* counts_dev, int32_t* steps_dev, void* stream)
 {
-    if (!g || !class_p_host || !counts_dev || nstreams < 0) return fail(LUF_ERR_INVALID, "luf_stream_mc: bad argument");
+    return luf_stream_mc_metrics(g, flags, class_p_host, seed, stream0, nstreams, n, counts_dev, steps_dev, nullptr, nullptr, stream);
+}
+
+int luf_stream_mc_metrics(luf_stream* g, int flags, const double* class_p_host, uint64_t seed, uint64_t stream0,
+                          int64_t nstreams, int32_t n, unsigned long long* counts_dev, int32_t* steps_dev,
+                          uint32_t* growth2b_dev, int32_t* cycle_dev, void* stream)
+{
+    if (!g || !class_p_host || !counts_dev || nstreams < 0 || (!growth2b_dev) != (!cycle_dev))
+        return fail(LUF_ERR_INVALID, "luf_stream_mc: bad argument");
     if (n < 1) return fail(LUF_ERR_INVALID, "n must be positive integer.");
     if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE)) return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
     if (nstreams == 0) return 0;
@@ -968,11 +999,11 @@ int luf_stream_mc(luf_stream* g, int flags, const double* class_p_host, uint64_t
         }
         if (int rc = plan_stream_cta_launch(g, k_sf_mc_cta, nstreams, &c, 4.0 * faults * g->view.h + 1.0)) return rc;
         k_sf_mc_cta<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_cta, sp, flags, stream0, nstreams, n,
-                                                                        counts_dev, steps_dev);
+                                                                        counts_dev, steps_dev, growth2b_dev, cycle_dev);
     } else {
         if (int rc = plan_stream_launch(g, k_sf_mc, nstreams, &c)) return rc;
         k_sf_mc<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, sp, flags, stream0, nstreams, n,
-                                                                    counts_dev, steps_dev);
+                                                                    counts_dev, steps_dev, growth2b_dev, cycle_dev);
     }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;
@@ -1620,6 +1651,127 @@ int luf_check_host(luf_graph* g, int64_t nshots, const uint32_t* err_bits_host, 
     if (logical_host) CUDA_TRY(cudaMemcpyAsync(logical_host, lg, n, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaMemcpy(&tmp, cnt, 8, cudaMemcpyDeviceToHost));
     *fail_count_host += tmp;
+    return 0;
+}
+
+// ------------------------------------------------------------------ confidence scores
+struct luf_dcs {
+    int device = 0, sm_count = 0, max_smem = 0;
+    DcsView view{};
+    std::vector<void*> allocs;
+    void* scratch[4] = {0, 0, 0, 0};
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
+    std::mutex mu;
+};
+
+}  // extern "C"
+template <class T>
+static int upload_d(luf_dcs* g, const std::vector<T>& v, const T** out)
+{
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, v.size() * sizeof(T) + 16));
+    g->allocs.push_back(p);
+    CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)p;
+    return 0;
+}
+extern "C" {
+
+int luf_dcs_create(const luf_dcs_desc* d, int device, luf_dcs** out)
+{
+    if (!d || !out || !d->edge_u || !d->edge_v || !d->node_side || d->n_nodes < 1 || d->n_edges < 0)
+        return fail(LUF_ERR_INVALID, "luf_dcs_create: bad argument");
+    if (d->n_nodes > 65535) return fail(LUF_ERR_UNSUPPORTED, "confidence scores: more than 65535 nodes");
+    if (int rc = check_device()) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    const int N = d->n_nodes, E = d->n_edges;
+    std::vector<uint32_t> uv((size_t)E + 1);
+    std::vector<double> w((size_t)E + 1);
+    std::vector<uint8_t> ing((size_t)E + 1), side(d->node_side, d->node_side + N);
+    double total = 0.0;
+    for (int e = 0; e < E; ++e) {
+        if (d->edge_u[e] < 0 || d->edge_u[e] >= N || d->edge_v[e] < 0 || d->edge_v[e] >= N)
+            return fail(LUF_ERR_INVALID, "luf_dcs_create: edge endpoint out of range");
+        uv[e] = (uint32_t)d->edge_u[e] | ((uint32_t)d->edge_v[e] << 16);
+        w[e] = d->weight ? d->weight[e] : 1.0;
+        if (!(w[e] >= 0.0)) return fail(LUF_ERR_INVALID, "luf_dcs_create: negative edge weight (noise level above 1/2)");
+        ing[e] = d->in_growth ? (d->in_growth[e] ? 1 : 0) : 1;
+        if (ing[e]) total += w[e];                       // _total_edge_weight: edge order, left to right
+    }
+    luf_dcs* g = new (std::nothrow) luf_dcs;
+    if (!g) return fail(LUF_ERR_CUDA, "out of host memory");
+    g->device = device;
+    cudaDeviceProp prop;
+    cudaError_t ce = cudaGetDeviceProperties(&prop, device);
+    if (ce != cudaSuccess) { delete g; return fail(LUF_ERR_CUDA, cudaGetErrorString(ce)); }
+    g->sm_count = prop.multiProcessorCount; g->max_smem = (int)prop.sharedMemPerBlockOptin;
+    g->view.N = N; g->view.E = E; g->view.WN = (N + 31) / 32; g->view.total_weight = total;
+    int rc;
+    if ((rc = upload_d(g, uv, &g->view.uv)) || (rc = upload_d(g, w, &g->view.weight)) ||
+        (rc = upload_d(g, ing, &g->view.in_growth)) || (rc = upload_d(g, side, &g->view.side))) {
+        luf_dcs_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return 0;
+}
+
+int luf_dcs_destroy(luf_dcs* g)
+{
+    if (!g) return 0;
+    cudaSetDevice(g->device);
+    for (void* p : g->allocs) cudaFree(p);
+    for (void* p : g->scratch) if (p) cudaFree(p);
+    delete g;
+    return 0;
+}
+
+int luf_dcs_run(luf_dcs* g, int64_t nshots, const uint32_t* growth2b_dev, int64_t stride_words, int32_t growth_words,
+                double* swim_dev, double* uef_dev, int32_t* clustered_nodes_dev, void* stream)
+{
+    if (!g || !growth2b_dev || nshots < 0 || growth_words < 0 || stride_words < growth_words)
+        return fail(LUF_ERR_INVALID, "luf_dcs_run: bad argument");
+    if (nshots == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t bytes = 8u * (size_t)g->view.N + 4u * (size_t)g->view.WN + 4u * (size_t)((g->view.E + 15) / 16) + 16u;
+    if (bytes > (size_t)g->max_smem)
+        return fail(LUF_ERR_UNSUPPORTED, "confidence scores: one shot's distances (" + std::to_string(bytes) + " B) exceed the shared memory of an SM");
+    CUDA_TRY(cudaFuncSetAttribute(k_dcs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dcs, 256, bytes));
+    if (per_sm < 1) return fail(LUF_ERR_UNSUPPORTED, "k_dcs does not fit on an SM");
+    long long blocks = (long long)g->sm_count * per_sm;
+    if (blocks > nshots) blocks = nshots;
+    k_dcs<<<(int)blocks, 256, bytes, (cudaStream_t)stream>>>(g->view, nshots, growth2b_dev, stride_words, growth_words,
+                                                            swim_dev, uef_dev, clustered_nodes_dev);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int luf_dcs_run_host(luf_dcs* g, int64_t nshots, const uint32_t* growth2b_host, int64_t stride_words, int32_t growth_words,
+                     double* swim_host, double* uef_host, int32_t* clustered_nodes_host)
+{
+    if (!g || !growth2b_host || nshots < 0) return fail(LUF_ERR_INVALID, "luf_dcs_run_host: bad argument");
+    if (nshots == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t n = (size_t)nshots;
+    const size_t want[4] = {n * (size_t)stride_words * 4, n * 8, n * 8, n * 4};
+    for (int i = 0; i < 4; ++i)
+        if (want[i] > g->scratch_bytes[i]) {
+            if (g->scratch[i]) CUDA_TRY(cudaFree(g->scratch[i]));
+            g->scratch[i] = nullptr; g->scratch_bytes[i] = 0;
+            CUDA_TRY(cudaMalloc(&g->scratch[i], want[i]));
+            g->scratch_bytes[i] = want[i];
+        }
+    CUDA_TRY(cudaMemcpyAsync(g->scratch[0], growth2b_host, want[0], cudaMemcpyHostToDevice, 0));
+    if (int rc = luf_dcs_run(g, nshots, (const uint32_t*)g->scratch[0], stride_words, growth_words,
+                             swim_host ? (double*)g->scratch[1] : nullptr, uef_host ? (double*)g->scratch[2] : nullptr,
+                             clustered_nodes_host ? (int32_t*)g->scratch[3] : nullptr, 0)) return rc;
+    if (swim_host) CUDA_TRY(cudaMemcpyAsync(swim_host, g->scratch[1], n * 8, cudaMemcpyDeviceToHost, 0));
+    if (uef_host) CUDA_TRY(cudaMemcpyAsync(uef_host, g->scratch[2], n * 8, cudaMemcpyDeviceToHost, 0));
+    if (clustered_nodes_host) CUDA_TRY(cudaMemcpyAsync(clustered_nodes_host, g->scratch[3], n * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
     return 0;
 }
 

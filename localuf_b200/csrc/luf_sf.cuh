@@ -382,6 +382,21 @@ LUF_DEV void sf_for_awake(const SfView& g, const SfShot& s, int lane, int nl, F&
     }
 }
 
+// Per-cycle metrics of Snowflake.decode (snowflake/main.py:266-297), the part that needs the node state:
+// min_defect_height (:283-288: the lowest layer with a defect on a detector, h if none) into acnt[1] and
+// min_active_layer (:290-296: the lowest layer with an active node, h if none) into acnt[2] (both preset to h);
+// the window's growth goes out as it lies (swim distance and unclustered edge fraction are k_dcs's work).
+LUF_DEV void sf_metrics_scan(const SfView& g, const SfShot& s, uint32_t* growth_out, int lane, int nl)
+{
+    const int words = g.h * 2 * g.ELw;
+    for (int w = lane; w < words; w += nl) growth_out[w] = s.growth[w];
+    sf_for_awake(g, s, lane, nl, [&](int r, int q, int v) {
+        const uint32_t f = s.fl[v];
+        if (q >= g.NLb && (f & SF_DEFECT)) luf_atomic_min(&s.acnt[1], (uint32_t)(g.h - 1 - r));
+        if (f & SF_ACTIVE) luf_atomic_min(&s.acnt[2], (uint32_t)(g.h - 1 - r));
+    });
+}
+
 // Compact the awake bitmap into alist (acnt[0] = number of awake nodes; must be 0 on entry).
 // Windows taller than 63 sheets keep the bitmap sweep (acnt[0] is then left above the capacity).
 LUF_DEV void sf_gather_awake(const SfView& g, const SfShot& s, int lane, int nl)

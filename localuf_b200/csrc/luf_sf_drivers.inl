@@ -58,6 +58,15 @@ LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t
     LUF_ST_PHASE(sf_pairs_lower(g, s, lane, nl));
 }
 
+// After a decoding cycle: the window's growth (h * 2 * ELw words) and (min_defect_height, min_active_layer).
+LUF_DEV void sf_cycle_metrics(const SfView& g, const SfShot& s, uint32_t* growth_out, int32_t* mins_out, int lane, int nl)
+{
+    (void)lane;
+    LUF_ST_PHASE(if (lane == 0) { s.acnt[1] = (uint32_t)g.h; s.acnt[2] = (uint32_t)g.h; });
+    LUF_ST_PHASE(sf_metrics_scan(g, s, growth_out, lane, nl));
+    LUF_ST_PHASE(if (lane == 0) { mins_out[0] = (int32_t)s.acnt[1]; mins_out[1] = (int32_t)s.acnt[2]; });
+}
+
 // Frugal._raise_window's Pairs half: floor errors in ascending edge id (one lane), then shift.
 LUF_DEV void sf_cycle_head(const SfView& g, const SfShot& s, int& m, int lane, int nl)
 {
@@ -73,10 +82,12 @@ LUF_DEV void sf_cycle_head(const SfView& g, const SfShot& s, int& m, int lane, i
 // transient h cycles, n*d timed cycles, d-1 more, one without future-boundary
 // faults, 2h noiseless cleansing cycles.  `steps_out` (optional, [n][2]) gets the
 // 'all' / 'unrooting' runtimes summed over each timed block of d cycles.
+// mgrowth / mcycle (optional, [n*d][h*2*ELw] and [n*d][4]): after every timed cycle the window's growth and
+// (min_defect_height, min_active_layer, runtime 'all', runtime 'unrooting') -- Frugal.run(metrics=...).
 // m / runtimes are meaningful on lane 0.
 LUF_DEV void sf_run(const SfView& g, const SfShot& s, const SampleParams& sp, int flags, uint64_t stream, int n,
                     int& m_total, long long& cycles, long long& rt_all_timed, long long& rt_unr_timed,
-                    int32_t* steps_out, int lane, int nl)
+                    int32_t* steps_out, uint32_t* mgrowth, int32_t* mcycle, int lane, int nl)
 {
     const int d = g.d, h = g.h;
     const int total = h + n * d + (d - 1) + 1 + 2 * h;
@@ -91,6 +102,11 @@ LUF_DEV void sf_run(const SfView& g, const SfShot& s, const SampleParams& sp, in
         if (!cleanse) { LUF_ST_PHASE(if (lane < 32) sf_sample_sheet(g, s, sp, stream, (uint32_t)c, excl, lane, nl < 32 ? nl : 32)); }
         sf_cycle_tail(g, s, flags, nullptr, m, ra, ru, lane, nl);
         m_total += m;
+        if (timed && mgrowth) {
+            const size_t tc = (size_t)(c - h);
+            sf_cycle_metrics(g, s, mgrowth + tc * (size_t)(h * 2 * g.ELw), mcycle + 4 * tc, lane, nl);
+            if (lane == 0) { mcycle[4 * tc + 2] = ra; mcycle[4 * tc + 3] = ru; }
+        }
         if (timed) {
             rt_all_timed += ra; rt_unr_timed += ru; blk_all += ra; blk_unr += ru;
             if ((c - h) % d == d - 1) {
@@ -114,10 +130,13 @@ LUF_DEV bool sf_window_has_defect(const SfView& g, const SfShot& s, int lane, in
 
 // K3b parity path for one window: ncycles consecutive cycles whose fresh errors (or, with
 // SF_FLAG_SYNDROME, top-sheet syndromes) are GIVEN as rows of ELw words.  rt [ncycles][2] = decode's
-// return value for time_only = 'all' / 'unrooting'; floor_bits (optional) [ncycles][ELw]; m_out [ncycles].
+// return value for time_only = 'all' / 'unrooting'; floor_bits (optional) [ncycles][ELw]; m_out [ncycles];
+// mgrowth / mins (optional, [ncycles][h*2*ELw] and [ncycles][2]): the window's growth and
+// (min_defect_height, min_active_layer) after every cycle.
 // SF_FLAG_LATENCY_TAIL: the last h - 1 cycles are the noiseless tail of Frugal.sample_latency.
 LUF_DEV void sf_decode_stream(const SfView& g, const SfShot& s, int flags, int ncycles, const uint32_t* fresh,
-                              int32_t* rt, uint32_t* floor_bits, int32_t* m_out, int lane, int nl)
+                              int32_t* rt, uint32_t* floor_bits, int32_t* m_out, uint32_t* mgrowth, int32_t* mins,
+                              int lane, int nl)
 {
     LUF_ST_PHASE(sf_reset(g, s, lane, nl));
     bool possible = true;                        // defects_possible of Frugal.sample_latency
@@ -135,6 +154,7 @@ LUF_DEV void sf_decode_stream(const SfView& g, const SfShot& s, int flags, int n
         else { LUF_ST_PHASE(sf_given_sheet(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
         sf_cycle_tail(g, s, flags, floor_bits ? floor_bits + (size_t)c * g.ELw : nullptr, m, ra, ru, lane, nl);
         if (lane == 0) { rt[2 * c] = ra; rt[2 * c + 1] = ru; m_out[c] = m; }
+        if (mgrowth) sf_cycle_metrics(g, s, mgrowth + (size_t)c * (size_t)(g.h * 2 * g.ELw), mins + 2 * (size_t)c, lane, nl);
     }
 }
 

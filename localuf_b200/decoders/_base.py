@@ -11,7 +11,7 @@ import random
 
 import numpy as np
 
-from localuf_b200 import _engine, dist
+from localuf_b200 import _dcs, _engine, dist
 from localuf_b200.constants import Growth, GROWTH_FROM_DEVICE
 
 
@@ -164,6 +164,68 @@ class BaseUF(Decoder):
         super().reset()
         self.syndrome = set()
         self._growth_codes = np.zeros(self._CODE.N_EDGES, np.uint8)
+
+    # ---- decoder confidence scores (``_base_uf.py:101-121,250-316``; kernel ``csrc/luf_dcs.cuh``)
+    def _dcs_engine(self, noise_level) -> '_dcs.DcsEngine':
+        """The swim graph with the edge weights of ``noise_level``, uploaded once per level."""
+        cache = self.__dict__.setdefault('_dcs_engines', {})
+        if noise_level not in cache:
+            cache[noise_level] = _dcs.DcsEngine(_dcs.flat_tables(self._CODE, noise_level), device=self.engine.device)
+        return cache[noise_level]
+
+    def unclustered_edge_fraction(self, noise_level=None) -> float:
+        """``_base_uf.py:106-121``: the weighted fraction of edge growth that is *not* in a cluster."""
+        _, uef, _ = self._dcs_engine(noise_level).run_host(_dcs.pack_growth(self._growth_codes[None, :]),
+                                                           want_swim=False, want_clustered=False)
+        return float(uef[0])
+
+    def swim_distance(self, noise_level=None, draw=False, **kwargs_for_draw_swim_graph) -> float:
+        """``_base_uf.py:250-279``: the shortest west-east distance when travelling inside clusters is free.
+        Assumes ``validate`` or ``decode`` has been called."""
+        if draw:
+            raise NotImplementedError("Drawing is outside this engine (SURVEY.md section 2, row 14).")
+        swim, _, _ = self._dcs_engine(noise_level).run_host(_dcs.pack_growth(self._growth_codes[None, :]),
+                                                            want_uef=False, want_clustered=False)
+        return float(swim[0])
+
+    def sample_confidence_scores(self, noise_level: float, n: int, noise_level_for_priors=None, seed=None,
+                                 chunk: int = 1 << 16):
+        """``n`` sampled shots, decoded and scored on the device without leaving it: sample (K1) -> decode
+        with growth export (K2 / K3a) -> logical parity (K4) -> confidence scores (``k_dcs``).  Returns a
+        dict of arrays ``swim_distance``, ``unclustered_edge_fraction``, ``unclustered_node_fraction`` and
+        ``logical`` (uint8), one entry per shot -- the batched form of calling ``decode`` and then the three
+        score methods ``n`` times."""
+        import torch
+        eng, dcs = self.engine, self._dcs_engine(noise_level_for_priors)
+        dev = torch.device('cuda', eng.device)
+        seed = self._draw_seed(seed)
+        out = dict(swim_distance=np.zeros(n), unclustered_edge_fraction=np.zeros(n),
+                   unclustered_node_fraction=np.zeros(n), logical=np.zeros(n, np.uint8))
+        with torch.cuda.device(dev):
+            k = min(chunk, max(n, 1))
+            err = torch.empty((k, eng.WE), dtype=torch.int32, device=dev)
+            syn = torch.empty((k, eng.WD), dtype=torch.int32, device=dev)
+            corr = torch.empty((k, eng.WE), dtype=torch.int32, device=dev)
+            growth = torch.empty((k, eng.WG), dtype=torch.int32, device=dev)
+            logical = torch.empty(k, dtype=torch.uint8, device=dev)
+            fails = torch.zeros(1, dtype=torch.int64, device=dev)
+            swim = torch.empty(k, dtype=torch.float64, device=dev)
+            uef = torch.empty(k, dtype=torch.float64, device=dev)
+            cl = torch.empty(k, dtype=torch.int32, device=dev)
+            done = 0
+            while done < n:
+                c = min(k, n - done)
+                eng.sample(noise_level, seed, done, c, err, syn)
+                eng.decode_batch(self._DECODER_ID, self._flags, c, syn, corr, growth2b=growth)
+                eng.check(c, err, corr, logical, fails)
+                dcs.run(c, growth, eng.WG, swim=swim, uef=uef, clustered=cl)
+                sl = slice(done, done + c)
+                out['swim_distance'][sl] = swim[:c].cpu().numpy()
+                out['unclustered_edge_fraction'][sl] = uef[:c].cpu().numpy()
+                out['unclustered_node_fraction'][sl] = 1 - cl[:c].cpu().numpy() / self._CODE.NODE_COUNT
+                out['logical'][sl] = logical[:c].cpu().numpy()
+                done += c
+        return out
 
     def _decode_one(self, syndrome):
         """Decode one syndrome on the device; returns (correction set, steps row)."""

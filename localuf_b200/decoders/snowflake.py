@@ -9,9 +9,12 @@ drop, grow, merge, floor commit, string pairing, logical count -- inside
 """
 from __future__ import annotations
 
+from collections import Counter, defaultdict
+
 import numpy as np
 
-from localuf_b200 import _engine, _window, dist
+from localuf_b200 import _dcs, _engine, _window, dist
+from localuf_b200.constants import GROWTH_FROM_DEVICE
 from localuf_b200.codes import Repetition
 from localuf_b200.decoders._base import Decoder
 from localuf_b200.decoders._bitstrings import Bitstrings
@@ -46,6 +49,10 @@ class Snowflake(Decoder):
         self._lowest_local = np.array(
             [self._tables.layered_of_code[index[e]] % self._tables.EL for e in self._LOWEST_EDGES], np.int64)
         self._cycles: list = []            # syndrome rows of the decoding cycles since reset()
+        self._state = None                 # (number of cycles, growth export, mins) of the last replay with metrics
+        self._dcs_engines: dict = {}
+        self.confidence_score_history = defaultdict(list)      # snowflake/main.py:124-126
+        self.min_active_layers: Counter = Counter()            # snowflake/main.py:127-128
 
     def __repr__(self) -> str:
         return f'decoders.Snowflake({self.CODE})'
@@ -61,6 +68,9 @@ class Snowflake(Decoder):
         """``snowflake/main.py:201-214``: an empty window; forgets ``floor_history``."""
         super().reset()
         self._cycles = []
+        self._state = None
+        self.confidence_score_history = defaultdict(list)
+        self.min_active_layers = Counter()
         if hasattr(self, 'floor_history'):
             del self.floor_history
 
@@ -98,17 +108,120 @@ class Snowflake(Decoder):
         The device keeps a window inside one kernel launch, so the state between calls is the
         list of syndromes since :meth:`reset`; each call replays it (cost grows with the number
         of cycles -- use :meth:`generate_output` or ``Frugal.run`` for long streams)."""
-        if log_history or tuple(metrics):
-            raise NotImplementedError("Drawing / history / per-cycle metrics are outside this engine.")
+        if log_history:
+            raise NotImplementedError("Drawing / history are outside this engine.")
         if not defects_possible:
             raise NotImplementedError("defects_possible=False (drop only) is not built.")
         if time_only not in ('all', 'merging', 'unrooting'):
             raise ValueError(f'Unknown time_only: {time_only}.')
+        metrics = tuple(metrics)
+        self._check_metrics(metrics)
         self._cycles.append(self._syndrome_row(syndrome))
-        rt, floor = self._run_cycles(self._cycles)
+        self._state = None
+        if metrics:
+            rt, floor, growth, mins = self._replay_with_metrics()
+        else:
+            rt, floor = self._run_cycles(self._cycles)
         if log_floor_history:
             self.floor_history.append(self._floor_vector(floor[-1]))
-        return self._runtime(rt[-1], time_only)
+        runtime = self._runtime(rt[-1], time_only)
+        if metrics:
+            swim = uef = None
+            if 'swim_distance' in metrics or 'unclustered_edge_fraction' in metrics:
+                swim, uef, _ = self._scores(growth[-1:], noise_level_for_priors)
+            self._record_metrics(metrics, [runtime], mins[-1:], swim, uef)
+        return runtime
+
+    # ---- decoder confidence scores (snowflake/main.py:266-297; _base_uf.py:101-121,250-316)
+    _METRICS = ('throughput', 'swim_distance', 'min_defect_height', 'unclustered_edge_fraction', 'min_active_layer')
+
+    def _check_metrics(self, metrics):
+        for metric in metrics:
+            if metric not in self._METRICS:
+                raise ValueError(f'Unknown metric: {metric}.')
+
+    def _dcs_engine(self, noise_level) -> '_dcs.DcsEngine':
+        if noise_level not in self._dcs_engines:
+            self._dcs_engines[noise_level] = _dcs.DcsEngine(
+                _dcs.window_tables(self._CODE, self._tables, noise_level), device=self.engine.device)
+        return self._dcs_engines[noise_level]
+
+    def _scores(self, growth_dev, noise_level):
+        """(swim distance, unclustered edge fraction) of growth rows that are already on the device."""
+        import torch
+        n = growth_dev.shape[0]
+        swim = torch.empty(n, dtype=torch.float64, device=growth_dev.device)
+        uef = torch.empty(n, dtype=torch.float64, device=growth_dev.device)
+        with torch.cuda.device(growth_dev.device):
+            self._dcs_engine(noise_level).run(n, growth_dev, growth_dev.shape[1], swim=swim, uef=uef)
+        return swim.cpu().numpy(), uef.cpu().numpy(), None
+
+    def _record_metrics(self, metrics, runtimes, mins, swim, uef):
+        """``snowflake/main.py:266-281`` for a run of cycles (one entry per cycle and metric)."""
+        for k, runtime in enumerate(runtimes):
+            for metric in metrics:
+                if metric == 'throughput':
+                    value = 1 / runtime
+                elif metric == 'swim_distance':
+                    value = float(swim[k])
+                elif metric == 'min_defect_height':
+                    value = int(mins[k][0])
+                elif metric == 'unclustered_edge_fraction':
+                    value = float(uef[k])
+                else:
+                    self.min_active_layers[int(mins[k][1])] += 1
+                    continue
+                self.confidence_score_history[metric].append(value)
+
+    def _replay_with_metrics(self):
+        """Replay the cycles since ``reset`` with the per-cycle export; the last replay is kept."""
+        if self._state is None or self._state[0] != len(self._cycles):
+            rows = self._cycles if self._cycles else [np.zeros(self.engine.W, np.uint32)]
+            rt, floor, _, growth, mins = self.engine.decode_metrics(self._flags | _engine.SF_SYNDROME, np.stack(rows)[None])
+            self._state = (len(self._cycles), rt[0], floor[0], growth, mins[0])
+        return self._state[1:]
+
+    def _current(self):
+        if not self._cycles:
+            raise RuntimeError('no decoding cycle since reset(): the window is empty')
+        return self._replay_with_metrics()
+
+    def swim_distance(self, noise_level=None, draw=False, **kwargs) -> float:
+        """``_base_uf.py:250-279`` on the window after the last decoding cycle."""
+        if draw:
+            raise NotImplementedError("Drawing is outside this engine.")
+        _, _, growth, _ = self._current()
+        return float(self._scores(growth[-1:], noise_level)[0][0])
+
+    def unclustered_edge_fraction(self, noise_level=None) -> float:
+        """``_base_uf.py:106-121`` on the window after the last decoding cycle."""
+        _, _, growth, _ = self._current()
+        return float(self._scores(growth[-1:], noise_level)[1][0])
+
+    def min_defect_height(self) -> int:
+        """``snowflake/main.py:283-288``."""
+        return int(self._current()[3][-1][0])
+
+    def min_active_layer(self) -> int:
+        """``snowflake/main.py:290-296``."""
+        return int(self._current()[3][-1][1])
+
+    @property
+    def growth(self) -> dict:
+        """``snowflake/main.py:151-153``: edge -> Growth over the edges below the future boundary."""
+        t, edges = self._tables, self._CODE.EDGES
+        ELp = 32 * ((t.EL + 31) // 32)
+        if self._cycles:
+            codes = _engine.unpack_growth(self._current()[2][-1:].cpu().numpy().view(np.uint32), t.h * ELp)[0]
+        else:
+            codes = np.zeros(t.h * ELp, np.uint8)
+        ta, h = self._CODE.TIME_AXIS, t.h
+        out = {}
+        for k, e in enumerate(edges):
+            if all(v[ta] < h for v in e):
+                b, l = divmod(int(t.layered_of_code[k]), t.EL)
+                out[e] = GROWTH_FROM_DEVICE[int(codes[b * ELp + l])]
+        return out
 
     def _runtime(self, rt, time_only: str) -> int:
         if time_only == 'all':
@@ -176,15 +289,36 @@ class Snowflake(Decoder):
     def _mc_frugal(self, noise_level: float, n: int, time_only: str = 'merging', shots: int = 1, seed=None,
                    draw=False, log_history=False, metrics=(), **kwargs):
         """``shots`` independent ``Frugal.run(n)`` memory experiments; returns (m, step_counts)."""
-        if draw or log_history or tuple(metrics):
-            raise NotImplementedError("Drawing / history / per-cycle metrics are outside this engine.")
+        if draw or log_history:
+            raise NotImplementedError("Drawing / history are outside this engine.")
+        metrics = tuple(metrics)
+        self._check_metrics(metrics)
+        if time_only not in ('all', 'merging', 'unrooting'):
+            raise ValueError(f'Unknown time_only: {time_only}.')
         eng = self.engine
         rank, size = dist.world()
         seed = self._draw_seed(seed)
         if size > 1:
             seed = dist.allreduce_counts([seed if rank == 0 else 0])[0]
         lo, cnt = dist.shard(shots, rank, size)
-        if cnt:
+        if cnt and metrics:
+            # Frugal.run(metrics=...) (_schemes.py:636-644): the scores of every timed cycle, stream after
+            # stream (under torchrun: this rank's streams), with noise_level_for_priors = noise_level
+            counts, steps = [0, 0, 0, 0], []
+            per_stream = n * self._CODE.D * eng.growth_words * 4
+            chunk = max(1, min(cnt, (256 << 20) // max(per_stream, 1)))
+            for start in range(0, cnt, chunk):
+                k = min(chunk, cnt - start)
+                c, st, growth, cycle = eng.mc_metrics(self._flags, noise_level, seed, lo + start, k, n)
+                counts = [a + b for a, b in zip(counts, c)]
+                steps.append(st)
+                swim = uef = None
+                if 'swim_distance' in metrics or 'unclustered_edge_fraction' in metrics:
+                    swim, uef, _ = self._scores(growth, noise_level)
+                cyc = cycle.reshape(-1, 4)
+                self._record_metrics(metrics, [self._runtime(r[2:], time_only) for r in cyc], cyc[:, :2], swim, uef)
+            steps = np.concatenate(steps)
+        elif cnt:
             counts, steps = eng.mc_host(self._flags, noise_level, seed, lo, cnt, n, want_steps=True)
         else:
             counts, steps = [0, 0, 0, 0], None

@@ -55,6 +55,21 @@ class UF(BaseUF):
         self._pending = set()
         self.round_count = 0
 
+    def unclustered_node_fraction(self) -> float:
+        """``uf.py:188-197``: the fraction of nodes in no cluster of more than one node (the nodes
+        without a fully grown edge -- every such edge has been merged)."""
+        from localuf_b200 import _dcs
+        _, _, cl = self._dcs_engine(None).run_host(_dcs.pack_growth(self._growth_codes[None, :]),
+                                                   want_swim=False, want_uef=False)
+        return 1 - int(cl[0]) / self._CODE.NODE_COUNT
+
+    def complementary_gap(self, noise_level=None, **kwargs):
+        """``uf.py:121-177``: needs ``merge_equivalent_boundary_nodes=True`` graphs, which this engine builds
+        but does not decode (out of scope)."""
+        if not getattr(self._CODE, '_MERGED_EQUIVALENT_BOUNDARY_NODES', False):
+            raise ValueError('Complementary gap requires all equivalent boundary nodes in the decoding graph be merged.')
+        raise NotImplementedError("complementary_gap is outside the hot path (DESIGN.md section 8).")
+
     # -------------------------------------------------------- batched entry
     def _mc_batch(self, noise_level: float, n: int, seed=None) -> int:
         """Failure count of ``n`` fused sample->decode->check shots (``_schemes.py:116-155``)."""

@@ -338,6 +338,7 @@ class Frugal(_Streaming):
         if n < 1:
             raise ValueError("n must be positive integer.")
         self.reset()
+        decoder.reset()
         m, steps = decoder._mc_frugal(noise_level, n, time_only=time_only, shots=shots, **kwargs)
         self.step_counts.extend(steps)
         return m, shots * (math.ceil(self.WINDOW_HEIGHT / self._COMMIT_HEIGHT) / self._CODE.D + n + 1)

@@ -231,3 +231,23 @@ class Oracle:
         if m < 0:
             raise RuntimeError('oracle_mc_batch failed')
         return int(m)
+
+
+def dcs_batch(tables, growth_codes, want=('swim', 'uef', 'clustered')):
+    """oracle/luf_oracle_dcs.c on [n, E'] growth codes over a localuf_b200._dcs.DcsTables-like object
+    -> dict of arrays."""
+    L = lib()
+    g = np.ascontiguousarray(growth_codes, dtype=np.uint8)
+    n, E = g.shape
+    assert E == len(tables.edge_u)
+    eu = np.ascontiguousarray(tables.edge_u, np.int32); ev = np.ascontiguousarray(tables.edge_v, np.int32)
+    w = np.ascontiguousarray(tables.weight, np.float64); ing = np.ascontiguousarray(tables.in_growth, np.uint8)
+    side = np.ascontiguousarray(tables.node_side, np.uint8)
+    out = {k: np.zeros(n, np.int32 if k == 'clustered' else np.float64) for k in want}
+    ptr = lambda k: out[k].ctypes.data if k in out else None
+    L.oracle_dcs_batch.restype = C.c_int
+    L.oracle_dcs_batch.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_longlong] + [C.c_void_p] * 4
+    rc = L.oracle_dcs_batch(int(tables.n_nodes), E, eu.ctypes.data, ev.ctypes.data, w.ctypes.data, ing.ctypes.data,
+                            side.ctypes.data, n, g.ctypes.data, ptr('swim'), ptr('uef'), ptr('clustered'))
+    assert rc == 0
+    return out

@@ -236,7 +236,7 @@ def main():
     jobs = {'graphs': lambda: graph_cases()}
     for case in UF_CASES:
         jobs[case[0]] = (lambda c=case: uf_case(*c))
-    for extra in ('gen_golden_ca', 'gen_golden_sf', 'gen_golden_fw', 'gen_golden_gl', 'gen_golden_subset', 'gen_golden_nuf', 'gen_golden_io', 'gen_golden_lat'):
+    for extra in ('gen_golden_ca', 'gen_golden_sf', 'gen_golden_fw', 'gen_golden_gl', 'gen_golden_subset', 'gen_golden_nuf', 'gen_golden_io', 'gen_golden_lat', 'gen_golden_dcs'):
         try:
             jobs.update(__import__(extra).jobs())
         except ImportError:

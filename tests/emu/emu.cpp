@@ -220,8 +220,8 @@ int emu_fw_stream(const luf_graph_desc* gd, const luf_forward_desc* fd, int deco
 }
 
 // Snowflake + frugal bookkeeping on given fresh errors (one stream).
-int emu_sf_stream_tile(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
-                       int32_t* rt, uint32_t* floor_bits, int32_t* m_out, int nl)
+int emu_sf_stream_metrics(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
+                          int32_t* rt, uint32_t* floor_bits, int32_t* m_out, uint32_t* mgrowth, int32_t* mins, int nl)
 {
     const bool cta = nl != 32;
     PackedWindow p;
@@ -234,9 +234,15 @@ int emu_sf_stream_tile(const luf_window_desc* d, int flags, int ncycles, const u
     const SfLayout l = cta ? make_sf_layout(p, SF_CTA_ALIST_CAP) : make_sf_layout(p);
     std::vector<unsigned char> mem(l.bytes);
     const SfShot s = sf_bind(l, mem.data());
-    if (cta) sf_cta::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, 0, nl);
-    else sf_warp::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, 0, nl);
+    if (cta) sf_cta::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, mgrowth, mins, 0, nl);
+    else sf_warp::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, mgrowth, mins, 0, nl);
     return 0;
+}
+
+int emu_sf_stream_tile(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
+                       int32_t* rt, uint32_t* floor_bits, int32_t* m_out, int nl)
+{
+    return emu_sf_stream_metrics(d, flags, ncycles, fresh, rt, floor_bits, m_out, nullptr, nullptr, nl);
 }
 
 // Frugal.sample_latency streams with the device sampler (host arithmetic): lat [nstreams][3].
@@ -290,8 +296,8 @@ int emu_sf_mc_tile(const luf_window_desc* d, int flags, const double* class_p, u
     for (long long k = 0; k < nstreams; ++k) {
         int m = 0; long long cyc = 0, ra = 0, ru = 0;
         int32_t* st = steps ? steps + (size_t)k * n * 2 : nullptr;
-        if (cta) sf_cta::sf_run(g, s, sp, flags, stream0 + k, n, m, cyc, ra, ru, st, 0, nl);
-        else sf_warp::sf_run(g, s, sp, flags, stream0 + k, n, m, cyc, ra, ru, st, 0, nl);
+        if (cta) sf_cta::sf_run(g, s, sp, flags, stream0 + k, n, m, cyc, ra, ru, st, nullptr, nullptr, 0, nl);
+        else sf_warp::sf_run(g, s, sp, flags, stream0 + k, n, m, cyc, ra, ru, st, nullptr, nullptr, 0, nl);
         counts[0] += m; counts[1] += cyc; counts[2] += ra; counts[3] += ru;
     }
     return 0;

@@ -119,3 +119,35 @@ def test_emu_sf_mc_does_not_depend_on_the_tile():
         assert block[0] == warp[0]
         np.testing.assert_array_equal(block[1], warp[1])
     assert warp[0][0] > 0
+
+
+def layered_growth_to_code_order(t, growth_words, n_code_edges):
+    """[n, h * 2 * W(EL)] exported growth words -> [n, E] codes in code-edge order."""
+    from localuf_b200 import _engine
+    ELp = 32 * ((t.EL + 31) // 32)
+    codes = _engine.unpack_growth(growth_words, t.h * ELp)
+    idx = np.array([(int(x) // t.EL) * ELp + int(x) % t.EL for x in t.layered_of_code[:n_code_edges]])
+    return codes[:, idx]
+
+
+@pytest.mark.parametrize('nl', [32, 128])
+@pytest.mark.parametrize('name', golden_names('dcsf_'))
+def test_emu_sf_cycle_metrics_match_reference(name, nl):
+    """Per-cycle export of the stream drivers: growth of the window, min_defect_height and min_active_layer
+    (snowflake/main.py:266-297) vs the unmodified reference; the scores themselves through the oracle."""
+    from localuf_b200 import _dcs
+    meta, arr = load_golden(name)
+    code = make_code(meta['spec'])
+    emu = emu_binding.EmuStream(code)
+    t = emu.tables
+    fresh = binding.code_bits_to_local(t, arr['fresh_bits'], 0)
+    rt, _, _, growth, mins = emu.stream_metrics(flags_of(meta['decoder_kwargs']), fresh, nl=nl)
+    np.testing.assert_array_equal(rt[:, 0], arr['runtime_all'])
+    np.testing.assert_array_equal(layered_growth_to_code_order(t, growth, meta['E']), arr['growth'])
+    np.testing.assert_array_equal(mins[:, 0], arr['min_defect_height'])
+    np.testing.assert_array_equal(mins[:, 1], arr['min_active_layer'])
+    wt = _dcs.window_tables(code, t, meta['p'])
+    from localuf_b200 import _engine
+    out = binding.dcs_batch(wt, _engine.unpack_growth(growth, wt.n_edges), want=('swim', 'uef'))
+    np.testing.assert_allclose(out['swim'], arr['swim_p'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(out['uef'], arr['uef_p'], rtol=1e-12, atol=1e-12)
