@@ -106,17 +106,22 @@ LUF_DEV uint32_t ca_access(const CaShot& s, int v) { return (uint32_t)s.acp[v] &
 template <bool ACTIS>
 LUF_DEV void ca_reset(const CaView& g, const CaShot& s, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int v = lane; v < g.N; v += nl) {
         s.cid[v] = (uint16_t)v; s.ncid[v] = (uint16_t)v;          // dense ids: node index == index_to_id
         s.acp[v] = (uint16_t)(PTR_C << 12); s.fl[v] = 0;
         if (ACTIS) { s.ast[v] = 0; s.cnt[v] = 0; }
     }
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.GW; w += nl) s.growth[w] = 0;
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WN; w += nl) {
         s.rx_anyon[w] = 0; s.rx_defect[w] = 0; s.touched[w] = 0;
         if (ACTIS) { s.rx_busy[w] = 0; s.rx_busy[g.WN + w] = 0; s.rx_active[w] = 0; s.rx_active[g.WN + w] = 0; }
     }
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WE; w += nl) { s.corr[w] = 0; if (s.err) s.err[w] = 0; }
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WD; w += nl) s.defect[w] = 0;
     if (lane < 4) s.glob[lane] = 0;
 }
@@ -124,8 +129,10 @@ LUF_DEV void ca_reset(const CaView& g, const CaShot& s, int lane, int nl)
 // Nodes.load / make_defect (luf/main.py:405-408,811-815)
 LUF_DEV void ca_load(const CaView& g, const CaShot& s, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WD; w += nl) {
         uint32_t bits = s.defect[w];
+        LUF_NOUNROLL_CA
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             const uint32_t v = (uint32_t)(g.B + 32 * w + b);
@@ -139,6 +146,7 @@ LUF_DEV void ca_load(const CaView& g, const CaShot& s, int lane, int nl)
 LUF_DEV void ca_growing(const CaView& g, const CaShot& s, int v)
 {
     if (!(s.fl[v] & FL_ACTIVE)) return;
+    LUF_NOUNROLL_CA
     for (int k = 0; k < g.K; ++k) {
         const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
         if (ent == NBR_NONE) continue;
@@ -164,16 +172,20 @@ LUF_DEV void ca_for_nodes(const CaView& g, const CaShot& s, int lane, int nl, F&
     if (SPARSE) {
         const uint32_t total = s.glob[2];
         if (total <= s.tcap) {                      // balanced: one touched node per lane and trip
+            LUF_NOUNROLL_CA
             for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) f((int)s.tlist[i]);
         } else
+            LUF_NOUNROLL_CA
             for (int w = lane; w < g.WN; w += nl) {
                 uint32_t bits = s.touched[w];
+                LUF_NOUNROLL_CA
                 while (bits) {
                     const int b = luf_ffs(bits) - 1; bits &= bits - 1;
                     f(32 * w + b);
                 }
             }
     } else
+        LUF_NOUNROLL_CA
         for (int v = lane; v < g.N; v += nl) f(v);
 }
 
@@ -183,12 +195,15 @@ LUF_DEV void ca_gather_touched(const CaView& g, const CaShot& s, int lane, int n
     const int wpl = (g.WN + nl - 1) / nl;
     const int w0 = lane * wpl, w1 = w0 + wpl < g.WN ? w0 + wpl : g.WN;
     uint32_t c = 0;
+    LUF_NOUNROLL_CA
     for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(s.touched[w]);
     if (!c) return;
     uint32_t pos = luf_atomic_add(&s.glob[2], c);
     if (pos + c > s.tcap) return;
+    LUF_NOUNROLL_CA
     for (int w = w0; w < w1; ++w) {
         uint32_t bits = s.touched[w];
+        LUF_NOUNROLL_CA
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             s.tlist[pos++] = (uint16_t)(32 * w + b);
@@ -208,6 +223,7 @@ LUF_DEV uint32_t ca_merging(const CaView& g, const CaShot& s, int v)
         fl &= ~(uint32_t)FL_ANYON;
     }
     uint32_t best = s.ncid[v];
+    LUF_NOUNROLL_CA
     for (uint32_t slots = access; slots; slots &= slots - 1u) {      // ascending slot = the scan order
         const int k = luf_ffs(slots) - 1;
         const uint32_t c = s.cid[LUF_LDG(&g.nbr[v * g.K + k]) >> 16];
@@ -233,6 +249,7 @@ LUF_DEV uint32_t ca_syncing(const CaView& g, const CaShot& s, int v)
     const uint32_t fl = s.fl[v] & ~(uint32_t)FL_BUSY;
     uint32_t busy = 0;
     if (!(fl & FL_ACTIVE))
+        LUF_NOUNROLL_CA
         for (uint32_t slots = ca_access(s, v); slots; slots &= slots - 1u) {
             const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + luf_ffs(slots) - 1]);
             if (s.fl[ent >> 16] & FL_ACTIVE) { busy = 1; break; }
@@ -245,6 +262,7 @@ LUF_DEV uint32_t ca_syncing(const CaView& g, const CaShot& s, int v)
 LUF_DEV void ca_burning(const CaView& g, const CaShot& s, int v)
 {
     const uint32_t ptr = ca_ptr(s, v);
+    LUF_NOUNROLL_CA
     for (int k = g.K >> 1; k < g.K; ++k) {                          // owned edges
         const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
         if (ent == NBR_NONE) continue;
@@ -353,6 +371,7 @@ LUF_DEV void ca_snapshot_access(const CaView& g, const CaShot& s, int lane, int 
 {
     ca_for_nodes<!ACTIS>(g, s, lane, nl, [&](int v) {
         uint32_t access = 0;
+        LUF_NOUNROLL_CA
         for (int k = 0; k < g.K; ++k) {
             const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
             if (ent != NBR_NONE && g2(s.growth, ent & 0xFFFFu) == G_FULL) access |= 1u << k;
@@ -368,6 +387,7 @@ LUF_DEV void actis_phase_a(const CaView& g, const CaShot& s, const CaCtl& c, int
     const int cur = c.step & 1;
     uint32_t* rxb = s.rx_busy + (cur ? g.WN : 0);
     uint32_t* rxa = s.rx_active + (cur ? g.WN : 0);
+    LUF_NOUNROLL_CA
     for (int v = lane; v < g.N; v += nl) {
         uint32_t a = s.ast[v];
         const uint32_t st = a & 3u;
@@ -409,6 +429,7 @@ LUF_DEV void actis_phase_b(const CaView& g, const CaShot& s, const CaCtl& c, int
     uint32_t* rxa = s.rx_active + (cur ? g.WN : 0);
     uint32_t* nxb = s.rx_busy + (cur ? 0 : g.WN);
     uint32_t* nxa = s.rx_active + (cur ? 0 : g.WN);
+    LUF_NOUNROLL_CA
     for (int v = lane; v < g.N; v += nl) {
         ca_commit_node(s, c.stage, v);
         const uint32_t old = s.ast[v];
@@ -418,6 +439,7 @@ LUF_DEV void actis_phase_b(const CaView& g, const CaShot& s, const CaCtl& c, int
         if (((rxa[v >> 5] >> (v & 31)) & 1u) || (old & AS_OWN_NAS)) a |= AS_ACTIVE_SIG;
         s.ast[v] = (uint8_t)a;
     }
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WN; w += nl) { nxb[w] = 0; nxa[w] = 0; }   // buffers of the next timestep
 }
 

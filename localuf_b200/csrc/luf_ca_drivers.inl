@@ -19,6 +19,7 @@ LUF_DEV uint32_t ca_decode(const CaView& g, const CaShot& s, int flags, int* t_s
     uint32_t parity = 0;
     (void)lane;
     if (!ACTIS) { LUF_CT_PHASE(ca_gather_touched(g, s, lane, nl)); }     // glob[2] == 0 after ca_reset
+    LUF_NOUNROLL_CA
     while (c.stage != ST_DONE) {
         if (c.stage == ST_BURNING && !exported) {
             exported = 1;

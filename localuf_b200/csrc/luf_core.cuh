@@ -20,6 +20,28 @@
 #pragma once
 #include <stdint.h>
 
+// LUF_OPT_NOUNROLL (default 1): the data-dependent loops of the UF phases stay rolled.  nvcc's default unrolling
+// made k_mc_uf 3152 instructions / 71 registers and k_decode_uf 96 registers; rolled: 2432 instructions / 63
+// registers, cfg3 fused 58.4 -> 59.3 M shots/s, staged pipeline 48.0 -> 53.7 M shots/s (instruction-cache misses
+// were 14 % of the stalls).  LUF_OPT_NOUNROLL_CA (default 1) does the same for the cellular-automaton sources: Macar
+// 20.7 -> 21.9 M shots/s, Snowflake cfg4 27.2 -> 33.3 M decoding cycles/s.
+#ifndef LUF_OPT_NOUNROLL
+  #define LUF_OPT_NOUNROLL 1
+#endif
+#ifndef LUF_OPT_NOUNROLL_CA
+  #define LUF_OPT_NOUNROLL_CA 1
+#endif
+#if LUF_OPT_NOUNROLL && !defined(LUF_HOST_EMU)
+  #define LUF_NOUNROLL _Pragma("unroll 1")
+#else
+  #define LUF_NOUNROLL
+#endif
+#if LUF_OPT_NOUNROLL_CA && !defined(LUF_HOST_EMU)
+  #define LUF_NOUNROLL_CA _Pragma("unroll 1")
+#else
+  #define LUF_NOUNROLL_CA
+#endif
+
 #if defined(LUF_HOST_EMU)
   #include <math.h>
   #define LUF_DEV static inline
@@ -42,6 +64,7 @@
   static inline void luf_exscan(uint32_t c, int lane, int nl, uint32_t& pos, uint32_t& total)
   {
       (void)c; pos = 0; total = 0;
+      LUF_NOUNROLL
       for (int j = 0; j < nl; ++j) { if (j < lane) pos += luf_scan_scratch[j]; total += luf_scan_scratch[j]; }
   }
   #define LUF_LDG(p) (*(p))
@@ -156,7 +179,8 @@ struct Layout {
     uint32_t err, corr;                 // uint32[WE]  only in the staged kernels (0 = absent)
     uint32_t zero_off, zero_bytes;      // growth .. corr are contiguous: what ph_reset clears
     uint32_t claim;                     // uint32[max(CLAIM_SLOTS,WN)]  merge reservations; visited bitmap of the peel
-    uint32_t list, list2, cnt;          // uint32[LIST_CAP], uint32[LIST2_CAP] work lists; uint32[4] their fill counters
+    uint32_t list, list2, cnt;          // uint32[LIST_CAP], uint32[LIST2_CAP] work lists; uint32[8]: [0..3] their fill counters,
+                                        // [4] set once a union joined clusters whose boundary nodes lie on different sides
     uint32_t bytes;                     // slice size, multiple of 16
 };
 
@@ -198,6 +222,7 @@ LUF_DEV void philox_block(Philox& r)
 #if !defined(LUF_HOST_EMU)
     #pragma unroll
 #endif
+    LUF_NOUNROLL
     for (int i = 0; i < 10; ++i) {
         const uint32_t hi0 = luf_mulhi(M0, c0), lo0 = M0 * c0;
         const uint32_t hi1 = luf_mulhi(M1, c2), lo1 = M1 * c2;
@@ -259,6 +284,7 @@ LUF_DEV uint32_t ph_sample_tab(const GraphView& g, const SampleTab& t, const Sho
     rng.k0 = sp.key0; rng.k1 = sp.key1; rng.have = 0;
     rng.o0 = rng.o1 = rng.o2 = rng.o3 = 0;
     uint32_t parity = 0, start = 0;
+    LUF_NOUNROLL
     for (int c = 0; c < t.n_classes; ++c) {
         const uint32_t end = LUF_LDG(&t.class_end[c]);
         const uint32_t lo = a > start ? a : start, hi = b < end ? b : end;
@@ -267,6 +293,7 @@ LUF_DEV uint32_t ph_sample_tab(const GraphView& g, const SampleTab& t, const Sho
         const float p = sp.p[c];
         if (p <= 0.0f) continue;
         uint32_t pos = lo;
+        LUF_NOUNROLL
         for (;;) {
             if (p < 1.0f) {
                 const float u = ((float)philox_next(rng) + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
@@ -308,6 +335,7 @@ LUF_DEV void ph_force(const GraphView& g, const Shot& s, const SampleParams& sp,
     rng.o0 = rng.o1 = rng.o2 = rng.o3 = 0;
     const uint32_t F = (uint32_t)g.F;
     if (weight > F) weight = F;
+    LUF_NOUNROLL
     for (uint32_t j = F - weight; j < F; ++j) {
         const uint32_t t = luf_mulhi(philox_next(rng), j + 1u);
         const uint32_t et = g.fresh_perm ? (uint32_t)LUF_LDG(&g.fresh_perm[t]) : t;
@@ -365,6 +393,7 @@ namespace luf { using namespace uf_warp; }
       if ((threadIdx.x & 31u) == 0) red[threadIdx.x >> 5] = x;
       __syncthreads();
       uint32_t t = 0;
+      LUF_NOUNROLL
       for (unsigned w = 0; w < (blockDim.x + 31u) >> 5; ++w) t += red[w];
       __syncthreads();
       return t;
@@ -378,6 +407,7 @@ namespace luf { using namespace uf_warp; }
       if ((lane & 31) == 31) red[lane >> 5] = x;
       __syncthreads();
       uint32_t before = 0, all = 0;
+      LUF_NOUNROLL
       for (int w = 0; w < (nl + 31) >> 5; ++w) { const uint32_t r = red[w]; if (w < (lane >> 5)) before += r; all += r; }
       __syncthreads();
       pos = before + x - c; total = all;

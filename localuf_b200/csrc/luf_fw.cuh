@@ -45,7 +45,9 @@ static const int FWP_NONE = -1, FWP_WEST = -2, FWP_EAST = -3, FWP_DEAD = -4;
 
 LUF_DEV void fw_reset(const FwView& g, const FwState& f, const uint32_t* init_buf, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WE; w += nl) { f.buf[w] = init_buf ? init_buf[w] : 0u; f.commit[w] = 0; }
+    LUF_NOUNROLL_CA
     for (int v = lane; v < g.N; v += nl) f.partner[v] = (int16_t)FWP_NONE;
 }
 
@@ -62,8 +64,10 @@ LUF_DEV void fw_toggle_ends(const FwView& g, uint32_t* defect, uint32_t e)
 // and `defect` must be zero on entry (the decoder's reset).
 LUF_DEV void fw_begin_cycle(const FwView& g, const FwState& f, uint32_t* err, uint32_t* defect, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WE; w += nl) {
         uint32_t x = f.buf[w];
+        LUF_NOUNROLL_CA
         while (x) {
             const int b = luf_ffs(x) - 1; x &= x - 1;
             const uint32_t le = LUF_LDG(&g.lower_edge[32 * w + b]);
@@ -72,8 +76,10 @@ LUF_DEV void fw_begin_cycle(const FwView& g, const FwState& f, uint32_t* err, ui
             fw_toggle_ends(g, defect, le);
         }
         x = f.commit[w];
+        LUF_NOUNROLL_CA
         while (x) {
             const int b = luf_ffs(x) - 1; x &= x - 1;
+            LUF_NOUNROLL_CA
             for (int k = 0; k < 2; ++k) {
                 const uint32_t a = LUF_LDG(&g.art_node[2 * (32 * w + b) + k]);
                 if (a != 0xFFFFu) luf_atomic_xor(&defect[(a - g.B) >> 5], 1u << ((a - g.B) & 31u));
@@ -85,8 +91,10 @@ LUF_DEV void fw_begin_cycle(const FwView& g, const FwState& f, uint32_t* err, ui
 // fresh sheet given as bits over code edge ids (parity path)
 LUF_DEV void fw_given_sheet(const FwView& g, const uint32_t* fresh, uint32_t* err, uint32_t* defect, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WE; w += nl) {
         uint32_t x = fresh[w];
+        LUF_NOUNROLL_CA
         while (x) {
             const int b = luf_ffs(x) - 1; x &= x - 1;
             luf_atomic_or(&err[(32 * w + b) >> 5], 1u << b);
@@ -99,6 +107,7 @@ LUF_DEV void fw_given_sheet(const FwView& g, const uint32_t* fresh, uint32_t* er
 LUF_DEV void fw_leftover(const FwView& g, const FwState& f, const uint32_t* err, const uint32_t* corr,
                          uint32_t* commit_out, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WE; w += nl) {
         const uint32_t m = LUF_LDG(&g.commit_mask[w]);
         const uint32_t cm = (err[w] ^ corr[w]) & m;
@@ -130,8 +139,10 @@ LUF_DEV int fw_take(const FwState& f, int u)
 // Forward.get_logical_error (:341-349): commit leftover into Pairs, ascending edge id.  One lane.
 LUF_DEV void fw_pairs_load(const FwView& g, const FwState& f, int& count)
 {
+    LUF_NOUNROLL_CA
     for (int w = 0; w < g.WE; ++w) {
         uint32_t x = f.commit[w];
+        LUF_NOUNROLL_CA
         while (x) {
             const int b = luf_ffs(x) - 1; x &= x - 1;
             const uint32_t uv = LUF_LDG(&g.edge_uv[32 * w + b]);
@@ -151,10 +162,12 @@ LUF_DEV void fw_pairs_load(const FwView& g, const FwState& f, int& count)
 // LogicalCounter.count's lowering by the commit height (_pairs.py:82-111), three lane-parallel sweeps
 LUF_DEV void fw_lower_clear(const FwView& g, const FwState& f, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int v = lane; v < g.N; v += nl) f.partner2[v] = (int16_t)FWP_NONE;
 }
 LUF_DEV void fw_lower_scatter(const FwView& g, const FwState& f, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int v = lane; v < g.N; v += nl) {
         const int p = f.partner[v];
         if (p == FWP_NONE) continue;
@@ -167,6 +180,7 @@ LUF_DEV void fw_lower_scatter(const FwView& g, const FwState& f, int lane, int n
 }
 LUF_DEV void fw_lower_commit(const FwView& g, const FwState& f, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int v = lane; v < g.N; v += nl) f.partner[v] = f.partner2[v];
 }
 
@@ -244,6 +258,7 @@ LUF_DEV void fw_run(const GraphView& gv, const FwView& g, const FwState& f, cons
     LUF_PHASE(ph_sample_tab(gv, buffer_tab, samp, sp, stream, 0u, (const uint32_t*)0, lane, nl));
     LUF_PHASE(for (int w = lane; w < g.WE; w += nl) f.buf[w] = d.err()[w]);
     const int total = n + 1 + n_cleanse;
+    LUF_NOUNROLL_CA
     for (int c = 0; c < total; ++c) {
         int s0 = 0, s1 = 0;
         LUF_PHASE(fw_dec_reset(d, lane, nl));

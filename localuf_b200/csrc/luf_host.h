@@ -103,7 +103,7 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr, ui
     l.corr = keep_corr ? take(4u * WE) : 0;
     l.zero_bytes = off - l.zero_off;                  // ----
     l.claim = take(4u * (claim_slots > WN ? claim_slots : WN));   // visited bitmap of the peel
-    l.list = take(4u * list_cap); l.list2 = take(4u * list2_cap); l.cnt = take(16);
+    l.list = take(4u * list_cap); l.list2 = take(4u * list2_cap); l.cnt = take(32);
     l.bytes = off;
     return l;
 }

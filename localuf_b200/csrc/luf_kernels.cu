@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleP
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
         LUF_PHASE(ph_load(g, s, lane, nl));
         uf_validate_t<TF>(g, s, flags, lane, nl);          // TF >= 0: the flags are compile-time constants
-        parity ^= uf_peel(g, s, lane, nl);
+        parity ^= uf_peel_parity(g, s, lane, nl);
         fails += LUF_XOR(parity) & 1u;
     }
     if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, Sam
         uf_cta::ph_load(g, s, lane, nl);
         __syncthreads();
         uf_cta::uf_validate_t<TF>(g, s, flags, lane, nl);
-        parity ^= uf_cta::uf_peel(g, s, lane, nl);
+        parity ^= uf_cta::uf_peel_parity(g, s, lane, nl);
         fails += (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
     }
     if (threadIdx.x == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);

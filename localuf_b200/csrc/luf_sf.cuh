@@ -134,17 +134,24 @@ LUF_DEV void sf_or_acp(const SfShot& s, int v, uint32_t bits)
 // Snowflake.reset + Frugal.reset (snowflake/main.py:201-214,1011-1031,1489-1496; _schemes.py:498-502)
 LUF_DEV void sf_reset(const SfView& g, const SfShot& s, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int r = 0; r < g.h; ++r)
+        LUF_NOUNROLL_CA
         for (int q = lane; q < g.NL; q += nl) {
             const int v = r * g.NL + q;
             const uint32_t id = sf_id(g, r, q);
             s.cid[v] = (uint16_t)id; s.ncid[v] = (uint16_t)id;
             s.fl[v] = (uint16_t)SF_WHOLE; s.acp[v] = (uint16_t)(SF_PTR_C << 12);
         }
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.h * g.WLn; w += nl) { s.ndef[w] = 0; s.awake[w] = 0; }
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.h * 2 * g.ELw; w += nl) s.growth[w] = 0;
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.h * g.ELw; w += nl) { s.corr[w] = 0; s.err[w] = 0; }
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WLn; w += nl) { s.top[w] = 0; s.fb[w] = 0; }
+    LUF_NOUNROLL_CA
     for (int k = lane; k < 2 * g.NL; k += nl) s.partner[k] = (int16_t)SFP_NONE;
 }
 
@@ -189,8 +196,10 @@ LUF_DEV void sf_pairs_load(const SfShot& s, int u, int v, int& count)
 // order = ascending code edge id.  One lane.
 LUF_DEV void sf_pairs_load_block(const SfView& g, const SfShot& s, const uint32_t* bits, int& count)
 {
+    LUF_NOUNROLL_CA
     for (int w = 0; w < g.ELw; ++w) {
         uint32_t x = bits[w];
+        LUF_NOUNROLL_CA
         while (x) {
             const int b = luf_ffs(x) - 1; x &= x - 1;
             const uint32_t ee = LUF_LDG(&g.edge_ends[32 * w + b]);
@@ -207,6 +216,7 @@ LUF_DEV void sf_pairs_load_block(const SfView& g, const SfShot& s, const uint32_
 LUF_DEV void sf_pairs_retire(const SfView& g, const SfShot& s, int lane, int nl)
 {
     const int NL = g.NL;
+    LUF_NOUNROLL_CA
     for (int q = g.NLb + lane; q < NL; q += nl) {
         const int p = s.partner[q];
         if (p == SFP_NONE) continue;
@@ -219,6 +229,7 @@ LUF_DEV void sf_pairs_retire(const SfView& g, const SfShot& s, int lane, int nl)
 LUF_DEV void sf_pairs_lower(const SfView& g, const SfShot& s, int lane, int nl)
 {
     const int NL = g.NL;
+    LUF_NOUNROLL_CA
     for (int q = g.NLb + lane; q < NL; q += nl) {
         const int p = s.partner[NL + q];
         if (p == SFP_NONE) continue;
@@ -231,7 +242,9 @@ LUF_DEV void sf_pairs_lower(const SfView& g, const SfShot& s, int lane, int nl)
 // Frugal._raise_window (_schemes.py:532-543): shift the error bits one layer down.
 LUF_DEV void sf_shift_errors(const SfView& g, const SfShot& s, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int c = lane; c < g.ELw; c += nl)
+        LUF_NOUNROLL_CA
         for (int b = g.h - 1; b >= 1; --b) s.err[b * g.ELw + c] = s.err[(b - 1) * g.ELw + c];
 }
 
@@ -239,7 +252,9 @@ LUF_DEV void sf_shift_errors(const SfView& g, const SfShot& s, int lane, int nl)
 // defects become this cycle's top-sheet syndrome.
 LUF_DEV void sf_begin_sheet(const SfView& g, const SfShot& s, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WLn; w += nl) { s.top[w] = s.fb[w]; s.fb[w] = 0; }
+    LUF_NOUNROLL_CA
     for (int c = lane; c < g.ELw; c += nl) s.err[c] = 0;
 }
 
@@ -250,6 +265,7 @@ LUF_DEV void sf_flip_fresh(const SfView& g, const SfShot& s, uint32_t l, bool ex
     const uint32_t ee = LUF_LDG(&g.edge_ends[l]);
     if (exclude_fb && ((ee >> 22) & 1u)) return;               // _base_classes.py:418-424
     luf_atomic_or(&s.err[l >> 5], 1u << (l & 31u));
+    LUF_NOUNROLL_CA
     for (int x = 0; x < 2; ++x) {
         const uint32_t q = (ee >> (11 * x)) & 1023u, dt = (ee >> (11 * x + 10)) & 1u;
         if ((int)q < g.NLb) continue;
@@ -260,8 +276,10 @@ LUF_DEV void sf_flip_fresh(const SfView& g, const SfShot& s, uint32_t l, bool ex
 // Fresh errors given as bits (staged / parity path).
 LUF_DEV void sf_given_sheet(const SfView& g, const SfShot& s, const uint32_t* fresh, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.ELw; w += nl) {
         uint32_t x = fresh[w];
+        LUF_NOUNROLL_CA
         while (x) {
             const int b = luf_ffs(x) - 1; x &= x - 1;
             sf_flip_fresh(g, s, (uint32_t)(32 * w + b), false);
@@ -273,6 +291,7 @@ LUF_DEV void sf_given_sheet(const SfView& g, const SfShot& s, const uint32_t* fr
 // generate_output, :656-726): bit q of `syn` = defect at in-layer position q of the new layer.
 LUF_DEV void sf_given_syndrome(const SfView& g, const SfShot& s, const uint32_t* syn, int lane, int nl)
 {
+    LUF_NOUNROLL_CA
     for (int w = lane; w < g.WLn; w += nl) s.top[w] ^= syn[w];
 }
 
@@ -289,6 +308,7 @@ LUF_DEV void sf_sample_sheet(const SfView& g, const SfShot& s, const SampleParam
     rng.k0 = sp.key0; rng.k1 = sp.key1 ^ 0x5F0F5F0Fu; rng.have = 0;
     rng.o0 = rng.o1 = rng.o2 = rng.o3 = 0;
     uint32_t start = 0;
+    LUF_NOUNROLL_CA
     for (int c = 0; c < g.n_classes; ++c) {
         const uint32_t end = LUF_LDG(&g.class_end[c]);
         const uint32_t lo = a > start ? a : start, hi = b < end ? b : end;
@@ -297,6 +317,7 @@ LUF_DEV void sf_sample_sheet(const SfView& g, const SfShot& s, const SampleParam
         const float p = sp.p[c];
         if (p <= 0.0f) continue;
         uint32_t pos = lo;
+        LUF_NOUNROLL_CA
         for (;;) {
             if (p < 1.0f) {
                 const float u = ((float)philox_next(rng) + 1.0f) * 2.3283064365386963e-10f;
@@ -318,15 +339,21 @@ LUF_DEV void sf_sample_sheet(const SfView& g, const SfShot& s, const SampleParam
 LUF_DEV void sf_drop(const SfView& g, const SfShot& s, int lane, int nl)
 {
     const int h = g.h;
+    LUF_NOUNROLL_CA
     for (int c = lane; c < g.ELw; c += nl) {
+        LUF_NOUNROLL_CA
         for (int b = h - 1; b >= 1; --b) s.corr[b * g.ELw + c] = s.corr[(b - 1) * g.ELw + c];
         s.corr[c] = 0;
     }
+    LUF_NOUNROLL_CA
     for (int c = lane; c < 2 * g.ELw; c += nl) {
+        LUF_NOUNROLL_CA
         for (int b = h - 1; b >= 1; --b) s.growth[b * 2 * g.ELw + c] = s.growth[(b - 1) * 2 * g.ELw + c];
         s.growth[c] = 0;
     }
+    LUF_NOUNROLL_CA
     for (int q = lane; q < g.NL; q += nl) {
+        LUF_NOUNROLL_CA
         for (int r = h - 1; r >= 1; --r) {
             const int v = r * g.NL + q, u = v - g.NL;
             const uint32_t fu = s.fl[u], cu = s.cid[u];
@@ -345,7 +372,9 @@ LUF_DEV void sf_drop(const SfView& g, const SfShot& s, int lane, int nl)
     }
     // next_defect == defect for every node before a drop (r.next_defect = node.defect, :1195),
     // so it shifts like everything else; the top sheet receives the new syndrome (:312-322)
+    LUF_NOUNROLL_CA
     for (int c = lane; c < g.WLn; c += nl) {
+        LUF_NOUNROLL_CA
         for (int r = h - 1; r >= 1; --r) {
             s.ndef[r * g.WLn + c] = s.ndef[(r - 1) * g.WLn + c];
             s.awake[r * g.WLn + c] = s.awake[(r - 1) * g.WLn + c];
@@ -363,6 +392,7 @@ LUF_DEV void sf_for_awake(const SfView& g, const SfShot& s, int lane, int nl, F&
 {
     const uint32_t total = s.acnt[0];
     if (total <= s.acap) {                          // balanced: one awake node per lane and trip
+        LUF_NOUNROLL_CA
         for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) {
             const int it = (int)s.alist[i], r = it >> 10, q = it & 1023;
             f(r, q, r * g.NL + q);
@@ -370,10 +400,12 @@ LUF_DEV void sf_for_awake(const SfView& g, const SfShot& s, int lane, int nl, F&
         return;
     }
     const int words = g.h * g.WLn;
+    LUF_NOUNROLL_CA
     for (int x = lane; x < words; x += nl) {
         uint32_t bits = s.awake[x];
         if (!bits) continue;
         const int r = x / g.WLn, w = x - r * g.WLn;
+        LUF_NOUNROLL_CA
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             const int q = 32 * w + b;
@@ -389,6 +421,7 @@ LUF_DEV void sf_for_awake(const SfView& g, const SfShot& s, int lane, int nl, F&
 LUF_DEV void sf_metrics_scan(const SfView& g, const SfShot& s, uint32_t* growth_out, int lane, int nl)
 {
     const int words = g.h * 2 * g.ELw;
+    LUF_NOUNROLL_CA
     for (int w = lane; w < words; w += nl) growth_out[w] = s.growth[w];
     sf_for_awake(g, s, lane, nl, [&](int r, int q, int v) {
         const uint32_t f = s.fl[v];
@@ -406,14 +439,17 @@ LUF_DEV void sf_gather_awake(const SfView& g, const SfShot& s, int lane, int nl)
     const int wpl = (words + nl - 1) / nl;
     const int w0 = lane * wpl, w1 = w0 + wpl < words ? w0 + wpl : words;
     uint32_t c = 0;
+    LUF_NOUNROLL_CA
     for (int x = w0; x < w1; ++x) c += (uint32_t)luf_popc(s.awake[x]);
     if (!c) return;
     uint32_t pos = luf_atomic_add(&s.acnt[0], c);
     if (pos + c > s.acap) return;
+    LUF_NOUNROLL_CA
     for (int x = w0; x < w1; ++x) {
         uint32_t bits = s.awake[x];
         if (!bits) continue;
         const int r = x / g.WLn, w = x - r * g.WLn;
+        LUF_NOUNROLL_CA
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             s.alist[pos++] = (uint16_t)((r << 10) | (32 * w + b));
@@ -424,6 +460,7 @@ LUF_DEV void sf_gather_awake(const SfView& g, const SfShot& s, int lane, int nl)
 // _Node._grow, snowflake/main.py:1075-1084
 LUF_DEV void sf_grow_node(const SfView& g, const SfShot& s, int r, int q)
 {
+    LUF_NOUNROLL_CA
     for (int k = 0; k < g.K; ++k) {
         SfNbr nb;
         if (!sf_nbr(g, r, q, k, nb)) continue;
@@ -475,6 +512,7 @@ LUF_DEV void sf_flooding(const SfView& g, const SfShot& s, int r, int q, int v, 
         s.ncid[v] = (uint16_t)sf_id(g, r, q);
         return;
     }
+    LUF_NOUNROLL_CA
     for (uint32_t slots = sf_access(s, v); slots; slots &= slots - 1u) {     // ascending slot = the scan order
         const int k = luf_ffs(slots) - 1;
         SfNbr nb;

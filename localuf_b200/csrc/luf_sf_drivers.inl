@@ -11,6 +11,7 @@ LUF_DEV void sf_merge(const SfView& g, const SfShot& s, bool whole, bool slow, i
 {
     (void)lane;
     rt_all += 1;
+    LUF_NOUNROLL_CA
     for (int guard = 0; guard < (1 << 20); ++guard) {
         LUF_ST_PHASE(sf_merge_a(g, s, whole, slow, lane, nl));
         uint32_t acc = 0;
@@ -93,6 +94,7 @@ LUF_DEV void sf_run(const SfView& g, const SfShot& s, const SampleParams& sp, in
     const int total = h + n * d + (d - 1) + 1 + 2 * h;
     LUF_ST_PHASE(sf_reset(g, s, lane, nl));
     int blk_all = 0, blk_unr = 0;
+    LUF_NOUNROLL_CA
     for (int c = 0; c < total; ++c) {
         const bool cleanse = c >= total - 2 * h, excl = c == total - 2 * h - 1;
         const bool timed = c >= h && c < h + n * d;
@@ -140,6 +142,7 @@ LUF_DEV void sf_decode_stream(const SfView& g, const SfShot& s, int flags, int n
 {
     LUF_ST_PHASE(sf_reset(g, s, lane, nl));
     bool possible = true;                        // defects_possible of Frugal.sample_latency
+    LUF_NOUNROLL_CA
     for (int c = 0; c < ncycles; ++c) {
         int m = 0, ra = 0, ru = 0;
         if ((flags & SF_FLAG_LATENCY_TAIL) && possible && c >= ncycles - (g.h - 1))
@@ -169,6 +172,7 @@ LUF_DEV void sf_latency(const SfView& g, const SfShot& s, const SampleParams& sp
     const int h = g.h, total = 2 * h + 1, loops = (flags & SF_FLAG_ONE_ONE) ? 1 : 2;
     LUF_ST_PHASE(sf_reset(g, s, lane, nl));
     lat[0] = lat[1] = lat[2] = 0;
+    LUF_NOUNROLL_CA
     for (int c = 0; c < total; ++c) {
         const bool noisy = c <= h + 1, counted = c >= h + 1;
         if (!noisy && !sf_window_has_defect(g, s, lane, nl)) { lat[0] += total - c; break; }

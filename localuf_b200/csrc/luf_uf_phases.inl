@@ -18,6 +18,7 @@ namespace LUF_UF_NS {
 LUF_DEV uint32_t find_ro(const Shot& s, uint32_t v, uint32_t& wr)
 {
     uint32_t w;
+    LUF_NOUNROLL
     while (!((w = s.S[v]) & ROOT_BIT)) v = w & SIZE_MASK;
     wr = w;
     return v;
@@ -34,6 +35,7 @@ LUF_DEV uint32_t find_pc(const Shot& s, uint32_t v, uint32_t& wr)
     if (w & ROOT_BIT) { wr = w; return v; }
     uint32_t r = w & SIZE_MASK, q;
     int hops = 0;
+    LUF_NOUNROLL
     while (!((q = s.S[r]) & ROOT_BIT)) { r = q & SIZE_MASK; ++hops; }
     if (hops) s.S[v] = (w & 0xFFFF0000u) | r;
     wr = q;
@@ -44,7 +46,9 @@ LUF_DEV uint32_t find_pc(const Shot& s, uint32_t v, uint32_t& wr)
 LUF_DEV uint32_t find_compress(const Shot& s, uint32_t v)
 {
     uint32_t r = v, w;
+    LUF_NOUNROLL
     while (!((w = s.S[r]) & ROOT_BIT)) r = w & SIZE_MASK;
+    LUF_NOUNROLL
     while (v != r) { w = s.S[v]; s.S[v] = (w & 0xFFFF0000u) | r; v = w & SIZE_MASK; }
     return r;
 }
@@ -60,12 +64,15 @@ LUF_DEV void gather_bits(W word, int nwords, uint32_t id0, uint32_t* list, uint3
     const int wpl = (nwords + nl - 1) / nl;
     const int w0 = lane * wpl, w1 = w0 + wpl < nwords ? w0 + wpl : nwords;
     uint32_t c = 0;
+    LUF_NOUNROLL
     for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(word(w));
     if (!c) return;
     uint32_t pos = luf_atomic_add(counter, c);
     if (pos + c > LUF_T_LIST_CAP) return;
+    LUF_NOUNROLL
     for (int w = w0; w < w1; ++w) {
         uint32_t bits = word(w);
+        LUF_NOUNROLL
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             list[pos++] = id0 + (uint32_t)(32 * w + b);
@@ -77,8 +84,10 @@ LUF_DEV void gather_bits(W word, int nwords, uint32_t id0, uint32_t* list, uint3
 template <class W, class F>
 LUF_DEV void for_bits(W word, int nwords, uint32_t id0, int lane, int nl, F f)
 {
+    LUF_NOUNROLL
     for (int w = lane; w < nwords; w += nl) {
         uint32_t bits = word(w);
+        LUF_NOUNROLL
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             f(id0 + (uint32_t)(32 * w + b));
@@ -92,6 +101,7 @@ LUF_DEV void for_items(W word, int nwords, uint32_t id0, const uint32_t* list, u
                        int lane, int nl, F f)
 {
     if (total <= LUF_T_LIST_CAP) {
+        LUF_NOUNROLL
         for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) f(list[i]);
     } else for_bits(word, nwords, id0, lane, nl, f);
 }
@@ -102,6 +112,7 @@ template <class F>
 LUF_DEV void for_row(const GraphView& g, uint32_t v, F f)
 {
     const uint32_t* row = g.adj + (size_t)v * (uint32_t)g.DEG;
+    LUF_NOUNROLL
     for (int k = 0; k < g.DEG; k += 2) {
         const luf_u32x2 p = LUF_LDG2(row + k);
         if (p.x == ADJ_PAD) break;
@@ -125,6 +136,7 @@ LUF_DEV uint32_t fresh_word(const GraphView& g, int v) { return ROOT_BIT | 1u | 
 LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int lane, int nl)
 {
     luf_u32x4* S4 = (luf_u32x4*)s.S;
+    LUF_NOUNROLL
     for (int v = 4 * lane; v < g.N; v += 4 * nl) {
         luf_u32x4 w;
         w.x = fresh_word(g, v); w.y = fresh_word(g, v + 1); w.z = fresh_word(g, v + 2); w.w = fresh_word(g, v + 3);
@@ -132,9 +144,11 @@ LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int la
     }
     luf_u32x4* Z4 = (luf_u32x4*)((unsigned char*)s.S + (l.zero_off - l.S));
     luf_u32x4 z; z.x = z.y = z.z = z.w = 0u;
+    LUF_NOUNROLL
     for (int i = lane; i < (int)(l.zero_bytes >> 4); i += nl) Z4[i] = z;
+    LUF_NOUNROLL
     for (int w = lane; w < LUF_T_CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu;
-    if (lane < 4) s.cnt[lane] = 0;
+    if (lane < 8) s.cnt[lane] = 0;
 }
 
 // uf.py:98-104 load: every defect is an odd singleton cluster (hence active).
@@ -145,12 +159,15 @@ LUF_DEV void ph_load(const GraphView& g, const Shot& s, int lane, int nl)
     const int wpl = (g.WD + nl - 1) / nl;
     const int w0 = lane * wpl, w1 = w0 + wpl < g.WD ? w0 + wpl : g.WD;
     uint32_t c = 0;
+    LUF_NOUNROLL
     for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(s.defect[w]);
     if (!c) return;
     uint32_t pos = luf_atomic_add(&s.cnt[0], c);
     const bool fits = pos + c <= LUF_T_LIST_CAP;
+    LUF_NOUNROLL
     for (int w = w0; w < w1; ++w) {
         uint32_t bits = s.defect[w];
+        LUF_NOUNROLL
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             const uint32_t v = (uint32_t)(g.B + 32 * w + b);
@@ -272,6 +289,7 @@ LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int flags, int 
         return total;
     }
     const uint32_t n = total < LUF_T_LIST2_CAP ? total : LUF_T_LIST2_CAP;
+    LUF_NOUNROLL
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
         const uint32_t it = s.list2[i];
         if (bucket && (s.S[it >> 16] & SIZE_MASK) != smallest) continue;
@@ -373,6 +391,8 @@ LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t 
     const uint32_t wl = ul ? wu : wv, ws = ul ? wv : wu;
     uint32_t bl = wl & BND_MASK;
     const uint32_t bs = ws & BND_MASK;
+    // both clusters reach a boundary: remember if the two boundary nodes lie on different sides (uf_peel_parity)
+    if (bl && bs && LUF_LDG(&g.node_long[(bs >> 16) - 1]) != LUF_LDG(&g.node_long[(bl >> 16) - 1])) s.cnt[4] = 1u;
     if (f & FLAG_WEST) {                                          // uf.py:544-549
         if (bs && (!bl || LUF_LDG(&g.node_long[(bs >> 16) - 1]) < LUF_LDG(&g.node_long[(bl >> 16) - 1]))) bl = bs;
     } else if (!bl) bl = bs;                                      // uf.py:536-538
@@ -399,6 +419,7 @@ LUF_DEV uint32_t merge_count(const GraphView& g, const Shot& s, int lane, int nl
     const int wpl = (g.WE + nl - 1) / nl;
     const int w1 = (lane + 1) * wpl < g.WE ? (lane + 1) * wpl : g.WE;
     uint32_t c = 0;
+    LUF_NOUNROLL
     for (int w = lane * wpl; w < w1; ++w) c += (uint32_t)luf_popc(s.newfull[w]);
     return c;
 }
@@ -414,9 +435,11 @@ LUF_DEV void ph_merge_gather(const GraphView& g, const Shot& s, int lane, int nl
     LUF_T_EXSCAN(merge_count(g, s, lane, nl), lane, nl, pos, total);
     const uint32_t take = total < LUF_T_LIST_CAP ? total : LUF_T_LIST_CAP;
     if (lane == 0) { s.cnt[0] = 0; s.cnt[1] = 0; s.cnt[2] = take; s.cnt[3] = total - take; }
+    LUF_NOUNROLL
     for (int w = w0; w < w1 && pos < take; ++w) {
         uint32_t bits = s.newfull[w];
         if (!bits) continue;
+        LUF_NOUNROLL
         while (bits && pos < take) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             s.list[pos++] = (uint32_t)(32 * w + b);
@@ -430,6 +453,7 @@ template <int TF>
 LUF_DEV uint32_t ph_merge_claim(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, bool first, int lane, int nl)
 {
     uint32_t placed = 0;
+    LUF_NOUNROLL
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
         const uint32_t it = s.list[i];
         if (it == LIST_DONE) continue;
@@ -456,6 +480,7 @@ template <int TF>
 LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, int lane, int nl)
 {
     uint32_t placed = 0;
+    LUF_NOUNROLL
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
         const uint32_t it = s.list[i];
         if (it == LIST_DONE) continue;
@@ -539,6 +564,7 @@ LUF_DEV void build_tree(const GraphView& g, const Shot& s, uint32_t root)
     luf_atomic_or(&visited[root >> 5], 1u << (root & 31u));
     s.S[root] = TREE_ROOT | (NONE16 << 16);
     uint32_t top = root;
+    LUF_NOUNROLL
     while (top != NONE16) {
         const uint32_t u = top;
         top = s.S[u] >> 16;
@@ -561,6 +587,7 @@ LUF_DEV void ph_peel_build(const GraphView& g, const Shot& s, int lane, int nl)
 {
     const uint32_t total = s.cnt[1];
     const uint32_t n = total < LUF_T_LIST2_CAP ? total : LUF_T_LIST2_CAP;
+    LUF_NOUNROLL
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) build_tree(g, s, s.list2[i]);
 }
 
@@ -568,8 +595,10 @@ LUF_DEV void ph_peel_build(const GraphView& g, const Shot& s, int lane, int nl)
 LUF_DEV void ph_peel_build_rest(const GraphView& g, const Shot& s, int lane, int nl)
 {
     const uint32_t* troot = s.newfull;
+    LUF_NOUNROLL
     for (int w = lane; w < g.WN; w += nl) {
         uint32_t bits = troot[w] & ~s.claim[w];
+        LUF_NOUNROLL
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
             build_tree(g, s, (uint32_t)(32 * w + b));
@@ -589,6 +618,7 @@ LUF_DEV uint32_t ph_peel_paths(const GraphView& g, const Shot& s, int lane, int 
     for_defects(g, s, lane, nl, [&](uint32_t v) {
         if (!bit_of(visited, v)) return;
         uint32_t e = s.S[v] & 0xFFFFu;
+        LUF_NOUNROLL
         while (e != TREE_ROOT) {
             if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
             parity ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
@@ -612,6 +642,7 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
     const bool vision_buckets = ((TF >= 0 ? TF : flags) & (FLAG_BUCKET | FLAG_NODE)) == FLAG_BUCKET;      // BUF
     uint32_t iter = 0xFFFFu;                 // decreasing reservation tag
     (void)lane;
+    LUF_NOUNROLL
     for (;;) {
         uint32_t active = 0;
         if (vision_buckets) {
@@ -633,6 +664,7 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
         if (!LUF_T_ANY(active)) break;
         ++rounds;
         LUF_STAT(0, 1); LUF_STAT(rounds == 1 ? 1 : 2, active);
+        LUF_NOUNROLL
         for (;;) {                             // chunks of at most LUF_T_LIST_CAP edges, lowest edge ids first
             uint32_t n = 0, left = 0;
             LUF_T_SCAN_PREP(merge_count(g, s, lane, nl));
@@ -640,6 +672,7 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
             LUF_T_PHASE(n = s.cnt[2]; left = s.cnt[3]);
             LUF_STAT(3, n); LUF_STAT(4, n > 32); LUF_STAT(rounds == 1 ? 8 : 9, n);
             uint32_t done = 0;
+            LUF_NOUNROLL
             for (uint32_t guard = 0; guard <= n; ++guard) {           // at least one edge is placed per iteration
                 if (iter == 0) {                                      // tags used up (huge graphs): start over
                     LUF_T_PHASE(for (int w = lane; w < LUF_T_CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu);
@@ -681,6 +714,42 @@ LUF_DEV uint32_t uf_peel(const GraphView& g, const Shot& s, int lane, int nl)
         if (roots > LUF_T_LIST2_CAP) { LUF_T_PHASE(ph_peel_build_rest(g, s, lane, nl)); }
         LUF_T_PHASE(parity ^= ph_peel_paths(g, s, lane, nl));
     }
+    return parity;
+}
+
+// The west parity of the correction without building it (the fused Monte-Carlo kernels need nothing else).
+// As long as no cluster holds boundary nodes of both sides, every correction inside the fully grown edges of
+// a cluster has the same parity on the west boundary: two of them differ by closed cycles (two west edges at
+// every west boundary node they pass) and by paths between boundary nodes of one side (two west edges, or
+// none).  That parity is the number of the cluster's defects if its boundary nodes are west ones (an odd
+// cluster sends one string to the boundary, an even one an even number), else 0 -- so every defect adds 1 iff
+// its cluster's boundary node is a west one; no forest, no traversal.  cnt[4] (union_roots) says whether a
+// cluster with boundary nodes of different sides exists; such shots take the full peel.
+LUF_DEV uint32_t ph_defect_sides(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    uint32_t parity = 0;
+    LUF_NOUNROLL
+    for (int w = lane; w < g.WD; w += nl) {
+        uint32_t bits = s.defect[w];
+        LUF_NOUNROLL
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            uint32_t rr;
+            find_ro(s, (uint32_t)(g.B + 32 * w + b), rr);
+            const uint32_t bn = (rr & BND_MASK) >> 16;
+            if (bn && LUF_LDG(&g.node_long[bn - 1u]) == -1) parity ^= 1u;
+        }
+    }
+    return parity;
+}
+
+LUF_DEV uint32_t uf_peel_parity(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    uint32_t mixed = 0, parity = 0;
+    (void)lane;
+    LUF_T_PHASE(mixed = s.cnt[4]);
+    if (LUF_T_ANY(mixed)) return uf_peel(g, s, lane, nl);
+    LUF_T_PHASE(parity ^= ph_defect_sides(g, s, lane, nl));
     return parity;
 }
 

@@ -134,6 +134,44 @@ int emu_mc_uf(const luf_graph_desc* d, int flags, const double* class_p, unsigne
     return 0;
 }
 
+// The fused kernels' parity-only peel (uf_peel_parity) next to the full peel on the same sampled shots:
+// counts[0] += failures by the full peel, [1] += failures by the parity path, [2] += shots on which the two
+// differ, [3] += shots that hold a cluster with boundary nodes of both sides (they take the full peel).
+int emu_mc_uf_parity(const luf_graph_desc* d, int flags, const double* class_p, unsigned long long seed,
+                     unsigned long long shot0, long long nshots, unsigned long long counts[4], int nl)
+{
+    const bool cta = nl != 32;
+    PackedGraph p;
+    if (!pack_graph(*d, p).empty()) return -1;
+    const GraphView g = view_of(p);
+    const Layout l = cta ? make_layout(p.N, p.B, p.E, true, true, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS)
+                         : make_layout(p.N, p.B, p.E, true, true);
+    const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
+    std::vector<unsigned char> mem(l.bytes);
+    const Shot s = bind(l, mem.data());
+    for (long long k = 0; k < nshots; ++k) {
+        uint32_t parity = 0;
+        if (cta) { LUF_PHASE(uf_cta::ph_reset(g, l, s, lane, nl)); } else { LUF_PHASE(ph_reset(g, l, s, lane, nl)); }
+        LUF_PHASE(if (lane < 32) parity ^= ph_sample(g, s, sp, shot0 + k, lane, 32));
+        if (cta) { LUF_PHASE(uf_cta::ph_load(g, s, lane, nl)); } else { LUF_PHASE(ph_load(g, s, lane, nl)); }
+        uint32_t fast, full;
+        if (cta) {
+            uf_cta::uf_validate(g, s, flags, 0, nl);
+            counts[3] += s.cnt[4] ? 1 : 0;
+            fast = s.cnt[4] ? 2u : uf_cta::uf_peel_parity(g, s, 0, nl);       // read-only on unmixed shots
+            full = uf_cta::uf_peel(g, s, 0, nl);
+        } else {
+            uf_validate(g, s, flags, 0, nl);
+            counts[3] += s.cnt[4] ? 1 : 0;
+            fast = s.cnt[4] ? 2u : uf_peel_parity(g, s, 0, nl);
+            full = uf_peel(g, s, 0, nl);
+        }
+        if (fast == 2u) fast = full;
+        counts[0] += (parity ^ full) & 1u; counts[1] += (parity ^ fast) & 1u; counts[2] += (fast ^ full) & 1u;
+    }
+    return 0;
+}
+
 // Macar (decoder 1) / Actis (decoder 2): syndromes in, (tSV, tBP), growth after
 // validation and correction out.
 int emu_decode_ca_tile(const luf_graph_desc* d, int decoder, int flags, long long nshots, const uint32_t* syn,

@@ -129,3 +129,31 @@ def test_emu_overflow_paths_with_tiny_work_lists():
                 np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
     finally:
         emu_binding.use_tiny_lists(False)
+
+
+@pytest.mark.parametrize('spec,p,flags,n', [
+    (dict(code='Surface', d=5, noise='code capacity'), 0.12, 0, 4000),
+    (dict(code='Surface', d=5, noise='code capacity'), 0.12, 2, 4000),       # west inclination
+    (dict(code='Surface', d=5, noise='code capacity'), 0.12, 1, 4000),       # dynamic
+    (dict(code='Surface', d=9, noise='code capacity'), 0.10, 0, 2000),
+    (dict(code='Surface', d=5, noise='phenomenological'), 0.04, 0, 2000),
+    (dict(code='Surface', d=5, noise='phenomenological'), 0.04, 4, 1500),    # NodeUF
+    (dict(code='Surface', d=5, noise='phenomenological'), 0.04, 8, 1500),    # BUF
+    (dict(code='Surface', d=7, noise='phenomenological'), 0.025, 0, 1500),
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.02, 0, 1500),
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.02, 3, 1500),
+    (dict(code='Repetition', d=7, noise='phenomenological'), 0.08, 0, 3000),
+    (dict(code='Repetition', d=5, noise='code capacity'), 0.2, 0, 4000),
+])
+@pytest.mark.parametrize('nl', [32, 128])
+def test_emu_parity_only_peel_equals_full_peel(spec, p, flags, n, nl):
+    """The fused kernels' shortcut (uf_peel_parity: every defect adds 1 iff its cluster's boundary node is a
+    west one; shots with a cluster that spans both sides take the full peel) gives the logical outcome of
+    the full peel on every shot."""
+    code = make_code(spec)
+    emu = emu_binding.Emu(code)
+    full, fast, differ, mixed = emu.mc_uf_parity(flags, p, 91, n, nl=nl)
+    assert differ == 0 and full == fast
+    assert full > 0
+    if flags == 0 and spec['code'] == 'Surface' and spec['d'] == 5 and spec['noise'] == 'code capacity':
+        assert 0 < mixed < n                     # both branches are exercised
