@@ -76,6 +76,7 @@
   #define LUF_XOR(x) (x)
   #define LUF_SUM(x) (x)
   static inline uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
+  static inline uint32_t luf_atomic_cas(uint32_t* p, uint32_t expect, uint32_t v) { uint32_t o = *p; if (o == expect) *p = v; return o; }
 #else
   #define LUF_DEV __device__ __forceinline__
   #define LUF_MEM __device__ __forceinline__
@@ -106,6 +107,7 @@
   #define LUF_XOR(x) __reduce_xor_sync(0xffffffffu, (x))
   #define LUF_SUM(x) __reduce_add_sync(0xffffffffu, (x))
   LUF_DEV uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
+  LUF_DEV uint32_t luf_atomic_cas(uint32_t* p, uint32_t expect, uint32_t v) { return atomicCAS(p, expect, v); }
 #endif
 
 // Optional event counters of the host emulation (tools/uf_stats.py); compiled out everywhere else.

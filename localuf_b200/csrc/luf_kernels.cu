@@ -66,8 +66,24 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleP
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
         LUF_PHASE(ph_load(g, s, lane, nl));
-        uf_validate_t<TF>(g, s, flags, lane, nl);          // TF >= 0: the flags are compile-time constants
-        parity ^= uf_peel_parity(g, s, lane, nl);
+        if (TF >= 0 && (TF & ~FLAG_WEST) == 0) {           // static UF: merges in any order, no peel ...
+            uf_validate_fast<(TF >= 0 ? TF & FLAG_WEST : 0)>(g, s, lane, nl);
+            if (__any_sync(0xffffffffu, s.cnt[4] != 0u)) { // ... unless a cluster spans both sides: canonical order
+                parity = 0;
+                __syncwarp();
+                LUF_PHASE(ph_reset(g, l, s, lane, nl));
+                LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
+                LUF_PHASE(ph_load(g, s, lane, nl));
+                uf_validate_t<TF>(g, s, flags, lane, nl);
+                parity ^= uf_peel(g, s, lane, nl);
+            } else {
+                parity ^= ph_defect_sides(g, s, lane, nl);
+                __syncwarp();
+            }
+        } else {
+            uf_validate_t<TF>(g, s, flags, lane, nl);      // TF >= 0: the flags are compile-time constants
+            parity ^= uf_peel_parity(g, s, lane, nl);
+        }
         fails += LUF_XOR(parity) & 1u;
     }
     if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
@@ -118,8 +134,26 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, Sam
         __syncthreads();
         uf_cta::ph_load(g, s, lane, nl);
         __syncthreads();
-        uf_cta::uf_validate_t<TF>(g, s, flags, lane, nl);
-        parity ^= uf_cta::uf_peel_parity(g, s, lane, nl);
+        if (TF >= 0 && (TF & ~FLAG_WEST) == 0) {
+            uf_cta::uf_validate_fast<(TF >= 0 ? TF & FLAG_WEST : 0)>(g, s, lane, nl);
+            if (__syncthreads_or(s.cnt[4] != 0u)) {
+                parity = 0;
+                uf_cta::ph_reset(g, l, s, lane, nl);
+                __syncthreads();
+                if (lane < WARP) parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, WARP);
+                __syncthreads();
+                uf_cta::ph_load(g, s, lane, nl);
+                __syncthreads();
+                uf_cta::uf_validate_t<TF>(g, s, flags, lane, nl);
+                parity ^= uf_cta::uf_peel(g, s, lane, nl);
+            } else {
+                parity ^= uf_cta::ph_defect_sides(g, s, lane, nl);
+                __syncthreads();
+            }
+        } else {
+            uf_cta::uf_validate_t<TF>(g, s, flags, lane, nl);
+            parity ^= uf_cta::uf_peel_parity(g, s, lane, nl);
+        }
         fails += (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
     }
     if (threadIdx.x == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);

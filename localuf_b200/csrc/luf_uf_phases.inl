@@ -694,6 +694,99 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
     return rounds;
 }
 
+// ---------------------------------------------------- order-free merge (fused kernels, static UF)
+// What a growth round needs from the merges before it is the partition into clusters and, per cluster, its
+// size, its defect parity and whether it touches a boundary -- none of which depends on the order of the
+// merges.  The order only decides which node is the union-find root and which boundary node represents the
+// cluster, i.e. where the peel roots its trees.  The fused Monte-Carlo kernels do not peel as long as no
+// cluster holds boundary nodes of both sides (uf_peel_parity), so they merge a round's newly FULL edges in
+// any order: one lane per edge hooks the smaller root below the larger with a compare-and-swap (strict
+// order by (size at the start of the trip, index): no cycles whatever the interleaving), then adds the
+// hooked root's size / parity / boundary to the root it ends up under.  Two phases per 32 (or blockDim)
+// edges instead of two per reservation iteration (19 iterations per cfg3 shot).  A shot in which a cluster
+// comes to hold boundary nodes of different sides (cnt[4]) is decoded again in canonical order.
+LUF_DEV void ph_fmerge_hook(const GraphView& g, const Shot& s, uint32_t i, int lane)
+{
+    const uint32_t e = s.list[i] & 0xFFFFu;
+    const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+    const uint32_t u = uv & 0xFFFFu, v = uv >> 16;
+    s.list2[lane] = 0u;                                           // nothing hooked (a payload always has ROOT_BIT)
+    LUF_NOUNROLL
+    for (;;) {
+        uint32_t wu, wv;
+        const uint32_t ru = find_pc(s, u, wu), rv = find_pc(s, v, wv);
+        if (ru == rv) return;
+        const uint32_t su = wu & SIZE_MASK, sv = wv & SIZE_MASK;
+        const bool u_small = su < sv || (su == sv && ru > rv);
+        const uint32_t small = u_small ? ru : rv, large = u_small ? rv : ru, wsmall = u_small ? wu : wv;
+        if (luf_atomic_cas(&s.S[small], wsmall, large | (e << 16)) == wsmall) {
+            s.list[i] = small;
+            s.list2[lane] = wsmall;
+            return;
+        }
+    }
+}
+
+template <int TF>
+LUF_DEV void ph_fmerge_apply(const GraphView& g, const Shot& s, uint32_t i, int lane)
+{
+    const uint32_t pay = s.list2[lane];
+    if (!pay) return;
+    uint32_t wr;
+    const uint32_t R = find_ro(s, s.list[i], wr);                 // roots are stable in this phase
+    const uint32_t bs = pay & BND_MASK;
+    LUF_NOUNROLL
+    for (;;) {
+        uint32_t bl = wr & BND_MASK;
+        if (bl && bs) {
+            const int ll = LUF_LDG(&g.node_long[(bl >> 16) - 1]), ls = LUF_LDG(&g.node_long[(bs >> 16) - 1]);
+            if (ll != ls) s.cnt[4] = 1u;
+            if ((TF & FLAG_WEST) && ls < ll) bl = bs;
+        } else if (!bl) bl = bs;
+        const uint32_t neww = ((wr ^ pay) & ODD_BIT) | bl | ROOT_BIT | ((wr & SIZE_MASK) + (pay & SIZE_MASK));
+        const uint32_t old = luf_atomic_cas(&s.S[R], wr, neww);
+        if (old == wr) return;
+        wr = old;
+    }
+}
+
+// uf_validate_t with the order-free merge.  TF: 0 or FLAG_WEST.
+template <int TF>
+LUF_DEV int uf_validate_fast(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    int rounds = 0;
+    (void)lane;
+    const uint32_t width = (uint32_t)nl < LUF_T_LIST2_CAP ? (uint32_t)nl : LUF_T_LIST2_CAP;
+    LUF_NOUNROLL
+    for (;;) {
+        uint32_t active = 0;
+        if (rounds == 0) {
+            LUF_T_PHASE(active |= ph_grow_first(g, s, lane, nl));
+        } else {
+            LUF_T_PHASE(ph_grow_gather(g, s, lane, nl));
+            LUF_T_PHASE(ph_grow_filter<TF>(g, s, TF, lane, nl));
+            LUF_T_PHASE(active |= ph_grow_exec<TF>(g, s, TF, lane, nl));
+        }
+        if (!LUF_T_ANY(active)) break;
+        ++rounds;
+        LUF_NOUNROLL
+        for (;;) {                             // chunks of at most LUF_T_LIST_CAP edges
+            uint32_t n = 0, left = 0;
+            LUF_T_SCAN_PREP(merge_count(g, s, lane, nl));
+            LUF_T_PHASE(ph_merge_gather(g, s, lane, nl));
+            LUF_T_PHASE(n = s.cnt[2]; left = s.cnt[3]);
+            LUF_NOUNROLL
+            for (uint32_t base = 0; base < n; base += width) {
+                LUF_T_PHASE(if ((uint32_t)lane < width && base + (uint32_t)lane < n) ph_fmerge_hook(g, s, base + (uint32_t)lane, lane));
+                LUF_T_PHASE(if ((uint32_t)lane < width && base + (uint32_t)lane < n) ph_fmerge_apply<TF>(g, s, base + (uint32_t)lane, lane));
+            }
+            if (!left) break;
+        }
+    }
+    LUF_T_PHASE(if (lane < 4) s.cnt[lane] = 0);
+    return rounds;
+}
+
 LUF_DEV int uf_validate(const GraphView& g, const Shot& s, int flags, int lane, int nl)
 {
     return uf_validate_t<-1>(g, s, flags, lane, nl);

@@ -172,6 +172,57 @@ int emu_mc_uf_parity(const luf_graph_desc* d, int flags, const double* class_p, 
     return 0;
 }
 
+// The fused kernels' order-free merge (uf_validate_fast + ph_defect_sides) next to the canonical decode on the
+// same sampled shots: counts[0] += failures canonical, [1] += failures by the fast path (shots it flags as
+// mixed take the canonical result, as in the kernel), [2] += shots where the two differ, [3] += mixed shots,
+// [4] += shots whose numbers of growth rounds differ.  flags: 0 or FLAG_WEST.
+int emu_mc_uf_fast(const luf_graph_desc* d, int flags, const double* class_p, unsigned long long seed,
+                   unsigned long long shot0, long long nshots, unsigned long long counts[5], int nl)
+{
+    const bool cta = nl != 32;
+    PackedGraph p;
+    if (!pack_graph(*d, p).empty() || (flags & ~2)) return -1;
+    const GraphView g = view_of(p);
+    const Layout l = cta ? make_layout(p.N, p.B, p.E, true, true, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS)
+                         : make_layout(p.N, p.B, p.E, true, true);
+    const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
+    std::vector<unsigned char> mem(l.bytes);
+    const Shot s = bind(l, mem.data());
+    for (long long k = 0; k < nshots; ++k) {
+        uint32_t pf = 0, pc = 0;
+        int rf, rc;
+        bool mixed;
+        if (cta) {
+            LUF_PHASE(uf_cta::ph_reset(g, l, s, lane, nl));
+            LUF_PHASE(if (lane < 32) pf ^= ph_sample(g, s, sp, shot0 + k, lane, 32));
+            LUF_PHASE(uf_cta::ph_load(g, s, lane, nl));
+            rf = flags ? uf_cta::uf_validate_fast<2>(g, s, 0, nl) : uf_cta::uf_validate_fast<0>(g, s, 0, nl);
+            mixed = s.cnt[4] != 0;
+            LUF_PHASE(pf ^= uf_cta::ph_defect_sides(g, s, lane, nl));
+            LUF_PHASE(uf_cta::ph_reset(g, l, s, lane, nl));
+            LUF_PHASE(if (lane < 32) pc ^= ph_sample(g, s, sp, shot0 + k, lane, 32));
+            LUF_PHASE(uf_cta::ph_load(g, s, lane, nl));
+            rc = uf_cta::uf_validate(g, s, flags, 0, nl);
+            pc ^= uf_cta::uf_peel(g, s, 0, nl);
+        } else {
+            LUF_PHASE(ph_reset(g, l, s, lane, nl));
+            LUF_PHASE(pf ^= ph_sample(g, s, sp, shot0 + k, lane, nl));
+            LUF_PHASE(ph_load(g, s, lane, nl));
+            rf = flags ? uf_validate_fast<2>(g, s, 0, nl) : uf_validate_fast<0>(g, s, 0, nl);
+            mixed = s.cnt[4] != 0;
+            LUF_PHASE(pf ^= ph_defect_sides(g, s, lane, nl));
+            LUF_PHASE(ph_reset(g, l, s, lane, nl));
+            LUF_PHASE(pc ^= ph_sample(g, s, sp, shot0 + k, lane, nl));
+            LUF_PHASE(ph_load(g, s, lane, nl));
+            rc = uf_validate(g, s, flags, 0, nl);
+            pc ^= uf_peel(g, s, 0, nl);
+        }
+        if (mixed) pf = pc;
+        counts[0] += pc & 1u; counts[1] += pf & 1u; counts[2] += (pf ^ pc) & 1u; counts[3] += mixed; counts[4] += rf != rc;
+    }
+    return 0;
+}
+
 // Macar (decoder 1) / Actis (decoder 2): syndromes in, (tSV, tBP), growth after
 // validation and correction out.
 int emu_decode_ca_tile(const luf_graph_desc* d, int decoder, int flags, long long nshots, const uint32_t* syn,

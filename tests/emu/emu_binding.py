@@ -125,6 +125,16 @@ class Emu:
         assert rc == 0, rc
         return tuple(int(x) for x in counts)
 
+    def mc_uf_fast(self, flags, noise_level, seed, nshots, nl=32):
+        """(failures canonical, failures by the order-free merge + parity path, shots where they differ,
+        mixed shots, shots whose round counts differ)."""
+        cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
+        counts = (C.c_ulonglong * 5)(0, 0, 0, 0, 0)
+        rc = lib().emu_mc_uf_fast(C.byref(self.desc), flags, _vp(cp), C.c_ulonglong(seed), C.c_ulonglong(0),
+                                  C.c_longlong(nshots), counts, nl)
+        assert rc == 0, rc
+        return tuple(int(x) for x in counts)
+
     def decode_ca(self, decoder, flags, syn_bits, nl=32):
         syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
         n = syn.shape[0]

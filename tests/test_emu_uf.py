@@ -157,3 +157,37 @@ def test_emu_parity_only_peel_equals_full_peel(spec, p, flags, n, nl):
     assert full > 0
     if flags == 0 and spec['code'] == 'Surface' and spec['d'] == 5 and spec['noise'] == 'code capacity':
         assert 0 < mixed < n                     # both branches are exercised
+
+
+@pytest.mark.parametrize('spec,p,flags,n', [
+    (dict(code='Surface', d=5, noise='code capacity'), 0.12, 0, 4000),
+    (dict(code='Surface', d=5, noise='code capacity'), 0.12, 2, 4000),
+    (dict(code='Surface', d=9, noise='code capacity'), 0.10, 0, 2000),
+    (dict(code='Surface', d=5, noise='phenomenological'), 0.04, 0, 2000),
+    (dict(code='Surface', d=7, noise='phenomenological'), 0.025, 2, 1000),
+    (dict(code='Surface', d=11, noise='phenomenological'), 0.02, 0, 200),
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.02, 0, 1500),
+    (dict(code='Repetition', d=7, noise='phenomenological'), 0.08, 0, 3000),
+    (dict(code='Repetition', d=5, noise='code capacity'), 0.2, 0, 4000),
+])
+@pytest.mark.parametrize('nl', [32, 128])
+def test_emu_order_free_merge_equals_canonical(spec, p, flags, n, nl):
+    """uf_validate_fast (merges of a round in any order) + ph_defect_sides against the canonical decode with
+    the full peel: same logical outcome and the same number of growth rounds on every shot; shots with a
+    cluster that holds boundary nodes of both sides are flagged (the kernel decodes those canonically)."""
+    code = make_code(spec)
+    emu = emu_binding.Emu(code)
+    canon, fast, differ, mixed, rounds_differ = emu.mc_uf_fast(flags, p, 17, n, nl=nl)
+    assert differ == 0 and canon == fast and rounds_differ == 0
+    assert canon > 0
+
+
+def test_emu_order_free_merge_with_tiny_lists():
+    emu_binding.use_tiny_lists(True)
+    try:
+        emu = emu_binding.Emu(make_code(dict(code='Surface', d=5, noise='phenomenological')))
+        for nl in (32, 64):
+            canon, fast, differ, mixed, rounds_differ = emu.mc_uf_fast(0, 0.04, 3, 1500, nl=nl)
+            assert differ == 0 and rounds_differ == 0 and canon > 0
+    finally:
+        emu_binding.use_tiny_lists(False)
