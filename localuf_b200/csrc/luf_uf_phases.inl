@@ -705,6 +705,9 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
 // hooked root's size / parity / boundary to the root it ends up under.  Two phases per 32 (or blockDim)
 // edges instead of two per reservation iteration (19 iterations per cfg3 shot).  A shot in which a cluster
 // comes to hold boundary nodes of different sides (cnt[4]) is decoded again in canonical order.
+// a cluster is active iff it is odd and has no boundary (uf.py:296-301)
+LUF_DEV uint32_t is_active(uint32_t root_word) { return (root_word >> 16) == (ODD_BIT >> 16) ? 1u : 0u; }
+
 LUF_DEV void ph_fmerge_hook(const GraphView& g, const Shot& s, uint32_t i, int lane)
 {
     const uint32_t e = s.list[i] & 0xFFFFu;
@@ -745,7 +748,11 @@ LUF_DEV void ph_fmerge_apply(const GraphView& g, const Shot& s, uint32_t i, int 
         } else if (!bl) bl = bs;
         const uint32_t neww = ((wr ^ pay) & ODD_BIT) | bl | ROOT_BIT | ((wr & SIZE_MASK) + (pay & SIZE_MASK));
         const uint32_t old = luf_atomic_cas(&s.S[R], wr, neww);
-        if (old == wr) return;
+        if (old == wr) {                                          // cnt[5]: the number of active clusters
+            const int delta = (int)is_active(neww) - (int)is_active(wr) - (int)is_active(pay);
+            if (delta) luf_atomic_add(&s.cnt[5], (uint32_t)delta);
+            return;
+        }
         wr = old;
     }
 }
@@ -760,9 +767,12 @@ LUF_DEV int uf_validate_fast(const GraphView& g, const Shot& s, int lane, int nl
     LUF_NOUNROLL
     for (;;) {
         uint32_t active = 0;
-        if (rounds == 0) {
-            LUF_T_PHASE(active |= ph_grow_first(g, s, lane, nl));
+        if (rounds == 0) {                     // every defect is an active singleton
+            LUF_T_PHASE(active |= ph_grow_first(g, s, lane, nl); if (lane == 0) s.cnt[5] = s.cnt[0]);
         } else {
+            // the merges keep count of the active clusters (cnt[5]): no sweep over the touched nodes just to
+            // find that none is left
+            if (!s.cnt[5]) break;
             LUF_T_PHASE(ph_grow_gather(g, s, lane, nl));
             LUF_T_PHASE(ph_grow_filter<TF>(g, s, TF, lane, nl));
             LUF_T_PHASE(active |= ph_grow_exec<TF>(g, s, TF, lane, nl));
