@@ -374,6 +374,9 @@ LUF_DEV void ph_buf_restore(const GraphView& g, const Shot& s, int lane, int nl)
 // merged in ascending edge id.  Union by size, ties keep the cluster of the
 // edge's first endpoint; parity XOR; boundary by inclination.  TF >= 0 fixes
 // the decoder flags at compile time (the fused kernel), TF < 0 reads `flags`.
+// a cluster is active iff it is odd and has no boundary (uf.py:296-301)
+LUF_DEV uint32_t is_active(uint32_t root_word) { return (root_word >> 16) == (ODD_BIT >> 16) ? 1u : 0u; }
+
 template <int TF>
 LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t e, uint32_t cu, uint32_t cv)
 {
@@ -396,8 +399,11 @@ LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t 
     if (f & FLAG_WEST) {                                          // uf.py:544-549
         if (bs && (!bl || LUF_LDG(&g.node_long[(bs >> 16) - 1]) < LUF_LDG(&g.node_long[(bl >> 16) - 1]))) bl = bs;
     } else if (!bl) bl = bs;                                      // uf.py:536-538
-    s.S[L] = ((wl ^ ws) & ODD_BIT) | bl | ROOT_BIT | (su + sv);
+    const uint32_t neww = ((wl ^ ws) & ODD_BIT) | bl | ROOT_BIT | (su + sv);
+    s.S[L] = neww;
     s.S[Sm] = L | (e << 16);
+    const int delta = (int)is_active(neww) - (int)is_active(wl) - (int)is_active(ws);      // cnt[5]: active clusters
+    if (delta) luf_atomic_add(&s.cnt[5], (uint32_t)delta);
 }
 
 // The serial order is reproduced in parallel by deterministic reservations:
@@ -654,9 +660,10 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
             LUF_T_PHASE(active |= ph_buf_exec(g, s, lane, nl));
             LUF_T_PHASE(ph_buf_restore(g, s, lane, nl));
             LUF_T_PHASE(for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0xFFFFFFFFu);
-        } else if (rounds == 0) {
-            LUF_T_PHASE(active |= ph_grow_first(g, s, lane, nl));
+        } else if (rounds == 0) {              // every defect is an active singleton
+            LUF_T_PHASE(active |= ph_grow_first(g, s, lane, nl); if (lane == 0) s.cnt[5] = s.cnt[0]);
         } else {
+            if (!s.cnt[5]) break;              // union_roots keeps count of the active clusters: none left
             LUF_T_PHASE(ph_grow_gather(g, s, lane, nl));
             LUF_T_PHASE(ph_grow_filter<TF>(g, s, flags, lane, nl));
             LUF_T_PHASE(active |= ph_grow_exec<TF>(g, s, flags, lane, nl));
@@ -705,9 +712,6 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
 // hooked root's size / parity / boundary to the root it ends up under.  Two phases per 32 (or blockDim)
 // edges instead of two per reservation iteration (19 iterations per cfg3 shot).  A shot in which a cluster
 // comes to hold boundary nodes of different sides (cnt[4]) is decoded again in canonical order.
-// a cluster is active iff it is odd and has no boundary (uf.py:296-301)
-LUF_DEV uint32_t is_active(uint32_t root_word) { return (root_word >> 16) == (ODD_BIT >> 16) ? 1u : 0u; }
-
 LUF_DEV void ph_fmerge_hook(const GraphView& g, const Shot& s, uint32_t i, int lane)
 {
     const uint32_t e = s.list[i] & 0xFFFFu;
