@@ -7,7 +7,13 @@
 // (_swim_graph, :281-304) -- is an edge-parallel Bellman-Ford in shared memory: dist[] holds the bit
 // patterns of non-negative doubles, which order like unsigned integers, so a relaxation is one 64-bit
 // atomicMin.  dist[v] is the minimum over paths of the left-to-right sum of the edge costs, the value
-// Dijkstra's algorithm returns.  The unclustered edge fraction is one weighted sum over the edges; the
+// Dijkstra's algorithm returns.  A sweep visits the edges in the order of their hop distance from the west
+// boundary (a table made once per graph): the 256 threads then work on one lattice column after the other,
+// relaxations made earlier in a sweep are seen later in the same sweep, and the wave crosses the lattice in
+// one sweep instead of one column per sweep when the warps keep pace.  Measured on cfg3 (65536 growth states):
+// 0.5 ms for everything but the sweeps, 0.55 ms per sweep, about 10 sweeps until nothing changes -- shortest
+// paths wind through the zero-cost clusters in every direction, so a block barrier after every 256 edges (strict
+// column order) reached the east side in one sweep but converged no sooner and cost 0.9 ms per sweep; not kept.  The unclustered edge fraction is one weighted sum over the edges; the
 // clustered node count marks the ends of fully grown edges in a bitmap (every fully grown edge has been merged;
 // a burnt edge, dynamic UF, was not).
 #pragma once
@@ -21,6 +27,8 @@ struct DcsView {
     const double* weight;        // [E]
     const uint8_t* in_growth;    // [E] edge is a key of decoder.growth (counts towards the edge fraction)
     const uint8_t* side;         // [N] 1 west boundary, 2 east boundary
+    const uint4* rec;            // [E_relax] the real edges sorted by their hop distance from the west boundary:
+    int E_relax;                 //           x = u | v << 16, y = edge id, (z, w) = the bits of its weight
     double total_weight;         // _total_edge_weight (:101-104), summed on the host in edge order
 };
 
@@ -41,14 +49,14 @@ __device__ __forceinline__ double dcs_block_sum(double x, double* scratch)
 // growth2b: [nshots][stride] words of 2-bit fields (0 ungrown, 1 half, 2 full, 3 burnt); edges beyond
 // 16 * growth_words are ungrown.  Outputs are optional.
 __global__ void __launch_bounds__(256) k_dcs(DcsView g, long long nshots, const uint32_t* __restrict__ growth2b,
-                                             long long stride, int growth_words, double* __restrict__ swim,
+                                             long long stride, int growth_words, int max_passes, double* __restrict__ swim,
                                              double* __restrict__ uef, int32_t* __restrict__ clustered)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long* dist = (unsigned long long*)smem;                 // [N]
     uint32_t* mark = (uint32_t*)(smem + 8u * (size_t)g.N);                // [WN]
     uint32_t* gw = mark + g.WN;                                           // [ceil(E / 16)]
-    __shared__ double scratch[8];
+    __shared__ double scratch[16];
     __shared__ unsigned long long best;
     __shared__ int cnt;
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x, GW = (g.E + 15) >> 4;
@@ -71,14 +79,15 @@ __global__ void __launch_bounds__(256) k_dcs(DcsView g, long long nshots, const 
         }
         __syncthreads();
         if (swim) {
-            for (int it = 0; it <= g.N; ++it) {
+            for (int it = 0; it < max_passes; ++it) {
                 int changed = 0;
-                for (int e = tid; e < g.E; e += nt) {
-                    const uint32_t p = __ldg(&g.uv[e]), u = p & 0xFFFFu, v = p >> 16;
+                for (int i = tid; i < g.E_relax; i += nt) {
+                    const uint4 r = __ldg(&g.rec[i]);                      // one 16-byte load per edge and sweep
+                    const uint32_t u = r.x & 0xFFFFu, v = r.x >> 16, e = r.y;
                     const unsigned long long bu = dist[u], bv = dist[v];
                     if (bu == bv) continue;                                // both unreached, or nothing to gain
                     const uint32_t c = (gw[e >> 4] >> ((e & 15) * 2)) & 3u;
-                    const double w = __ldg(&g.weight[e]);
+                    const double w = __hiloint2double((int)r.w, (int)r.z);
                     const double cost = c == 0u ? w : c == 1u ? w / 2 : 0.0;
                     if (bu < bv) {
                         const double x = __longlong_as_double((long long)bu) + cost;

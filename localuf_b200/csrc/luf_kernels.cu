@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <new>
@@ -1732,6 +1733,36 @@ int luf_dcs_create(const luf_dcs_desc* d, int device, luf_dcs** out)
         ing[e] = d->in_growth ? (d->in_growth[e] ? 1 : 0) : 1;
         if (ing[e]) total += w[e];                       // _total_edge_weight: edge order, left to right
     }
+    // sweep order of the relaxations: real edges by hop distance from the west meta boundary (breadth first)
+    std::vector<uint4> order;
+    {
+        std::vector<int> off((size_t)N + 1, 0), adj, hop((size_t)N, -1), queue;
+        for (int e = 0; e < E; ++e) if (d->edge_u[e] != d->edge_v[e]) { ++off[d->edge_u[e] + 1]; ++off[d->edge_v[e] + 1]; }
+        for (int v = 0; v < N; ++v) off[v + 1] += off[v];
+        adj.resize((size_t)off[N]);
+        std::vector<int> pos(off.begin(), off.end() - 1);
+        for (int e = 0; e < E; ++e) if (d->edge_u[e] != d->edge_v[e]) { adj[pos[d->edge_u[e]]++] = d->edge_v[e]; adj[pos[d->edge_v[e]]++] = d->edge_u[e]; }
+        for (int v = 0; v < N; ++v) if (side[v] == 1) { hop[v] = 0; queue.push_back(v); }
+        for (size_t q = 0; q < queue.size(); ++q) {
+            const int v = queue[q];
+            for (int i = off[v]; i < off[v + 1]; ++i) if (hop[adj[i]] < 0) { hop[adj[i]] = hop[v] + 1; queue.push_back(adj[i]); }
+        }
+        std::vector<std::pair<int, uint32_t>> keyed;
+        for (int e = 0; e < E; ++e) {
+            if (d->edge_u[e] == d->edge_v[e]) continue;
+            const int hu = hop[d->edge_u[e]], hv = hop[d->edge_v[e]];
+            if (hu < 0 && hv < 0) continue;                // not connected to the west boundary: never relaxed
+            keyed.push_back({hu < 0 ? hv : hv < 0 ? hu : (hu < hv ? hu : hv), (uint32_t)e});
+        }
+        std::sort(keyed.begin(), keyed.end());
+        for (auto& k : keyed) {
+            const uint32_t e = k.second;
+            uint64_t bits;
+            memcpy(&bits, &w[e], 8);
+            order.push_back(uint4{uv[e], e, (uint32_t)bits, (uint32_t)(bits >> 32)});
+        }
+        order.push_back(uint4{0, 0, 0, 0});
+    }
     luf_dcs* g = new (std::nothrow) luf_dcs;
     if (!g) return fail(LUF_ERR_CUDA, "out of host memory");
     g->device = device;
@@ -1741,7 +1772,9 @@ int luf_dcs_create(const luf_dcs_desc* d, int device, luf_dcs** out)
     g->sm_count = prop.multiProcessorCount; g->max_smem = (int)prop.sharedMemPerBlockOptin;
     g->view.N = N; g->view.E = E; g->view.WN = (N + 31) / 32; g->view.total_weight = total;
     int rc;
-    if ((rc = upload_d(g, uv, &g->view.uv)) || (rc = upload_d(g, w, &g->view.weight)) ||
+    g->view.E_relax = (int)order.size() - 1;
+    if ((rc = upload_d(g, order, &g->view.rec)) ||
+        (rc = upload_d(g, uv, &g->view.uv)) || (rc = upload_d(g, w, &g->view.weight)) ||
         (rc = upload_d(g, ing, &g->view.in_growth)) || (rc = upload_d(g, side, &g->view.side))) {
         luf_dcs_destroy(g);
         return rc;
@@ -1772,12 +1805,16 @@ int luf_dcs_run(luf_dcs* g, int64_t nshots, const uint32_t* growth2b_dev, int64_
         return fail(LUF_ERR_UNSUPPORTED, "confidence scores: one shot's distances (" + std::to_string(bytes) + " B) exceed the shared memory of an SM");
     CUDA_TRY(cudaFuncSetAttribute(k_dcs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dcs, 256, bytes));
+    // 128 threads per growth state measured best on cfg3 (4.8 ms per 65536 states; 64: 5.9, 256: 5.8)
+    int threads = getenv("LUF_DCS_THREADS") ? atoi(getenv("LUF_DCS_THREADS")) : 128;
+    if (threads < 32 || threads > 256 || (threads & 31)) threads = 128;
+    const int max_passes = getenv("LUF_DCS_MAX_PASSES") ? atoi(getenv("LUF_DCS_MAX_PASSES")) : g->view.N + 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dcs, threads, bytes));
     if (per_sm < 1) return fail(LUF_ERR_UNSUPPORTED, "k_dcs does not fit on an SM");
     long long blocks = (long long)g->sm_count * per_sm;
     if (blocks > nshots) blocks = nshots;
-    k_dcs<<<(int)blocks, 256, bytes, (cudaStream_t)stream>>>(g->view, nshots, growth2b_dev, stride_words, growth_words,
-                                                            swim_dev, uef_dev, clustered_nodes_dev);
+    k_dcs<<<(int)blocks, threads, bytes, (cudaStream_t)stream>>>(g->view, nshots, growth2b_dev, stride_words, growth_words,
+                                                                max_passes, swim_dev, uef_dev, clustered_nodes_dev);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
