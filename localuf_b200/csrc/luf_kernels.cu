@@ -52,6 +52,10 @@ __device__ __forceinline__ unsigned char* warp_slice(const Layout& l)
     return smem + (size_t)(threadIdx.x >> 5) * l.bytes;
 }
 
+// Decoder flags whose fused kernels take the order-free merge (luf_uf_phases.inl): not dynamic UF (which merges
+// are burnt depends on their order), not BUF (vision-length buckets have their own round structure).
+#define LUF_FAST_TF(TF) ((TF) >= 0 && !((TF) & FLAG_DYNAMIC) && (((TF) & (FLAG_BUCKET | FLAG_NODE)) != FLAG_BUCKET))
+
 // Fused K1 + K2 + K4 for the UF decoder, batch scheme (_schemes.py:116-155).
 template <int TF>
 __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
@@ -67,8 +71,8 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleP
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
         LUF_PHASE(ph_load(g, s, lane, nl));
-        if (TF >= 0 && (TF & ~FLAG_WEST) == 0) {           // static UF: merges in any order, no peel ...
-            uf_validate_fast<(TF >= 0 ? TF & FLAG_WEST : 0)>(g, s, lane, nl);
+        if (LUF_FAST_TF(TF)) {                             // static UF / NodeUF / NodeBUF: merges in any order, no peel ...
+            uf_validate_fast<(LUF_FAST_TF(TF) ? TF : 0)>(g, s, lane, nl);
             if (__any_sync(0xffffffffu, s.cnt[4] != 0u)) { // ... unless a cluster spans both sides: canonical order
                 parity = 0;
                 __syncwarp();
@@ -135,8 +139,8 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, Sam
         __syncthreads();
         uf_cta::ph_load(g, s, lane, nl);
         __syncthreads();
-        if (TF >= 0 && (TF & ~FLAG_WEST) == 0) {
-            uf_cta::uf_validate_fast<(TF >= 0 ? TF & FLAG_WEST : 0)>(g, s, lane, nl);
+        if (LUF_FAST_TF(TF)) {
+            uf_cta::uf_validate_fast<(LUF_FAST_TF(TF) ? TF : 0)>(g, s, lane, nl);
             if (__syncthreads_or(s.cnt[4] != 0u)) {
                 parity = 0;
                 uf_cta::ph_reset(g, l, s, lane, nl);

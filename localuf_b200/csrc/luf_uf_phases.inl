@@ -761,7 +761,8 @@ LUF_DEV void ph_fmerge_apply(const GraphView& g, const Shot& s, uint32_t i, int 
     }
 }
 
-// uf_validate_t with the order-free merge.  TF: 0 or FLAG_WEST.
+// uf_validate_t with the order-free merge.  TF: any of FLAG_WEST, FLAG_NODE, FLAG_NODE | FLAG_BUCKET (cluster
+// sizes, the bucket key of NodeBUF, do not depend on the merge order either).
 template <int TF>
 LUF_DEV int uf_validate_fast(const GraphView& g, const Shot& s, int lane, int nl)
 {

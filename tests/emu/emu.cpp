@@ -175,13 +175,15 @@ int emu_mc_uf_parity(const luf_graph_desc* d, int flags, const double* class_p, 
 // The fused kernels' order-free merge (uf_validate_fast + ph_defect_sides) next to the canonical decode on the
 // same sampled shots: counts[0] += failures canonical, [1] += failures by the fast path (shots it flags as
 // mixed take the canonical result, as in the kernel), [2] += shots where the two differ, [3] += mixed shots,
-// [4] += shots whose numbers of growth rounds differ.  flags: 0 or FLAG_WEST.
+// [4] += shots whose numbers of growth rounds differ.  flags: west (2), node (4), node + bucket (12) and combinations.
+#define LUF_EMU_FAST(F) (flags == 0 ? F<0>(g, s, 0, nl) : flags == 2 ? F<2>(g, s, 0, nl) : flags == 4 ? F<4>(g, s, 0, nl) : \
+                         flags == 6 ? F<6>(g, s, 0, nl) : flags == 12 ? F<12>(g, s, 0, nl) : F<14>(g, s, 0, nl))
 int emu_mc_uf_fast(const luf_graph_desc* d, int flags, const double* class_p, unsigned long long seed,
                    unsigned long long shot0, long long nshots, unsigned long long counts[5], int nl)
 {
     const bool cta = nl != 32;
     PackedGraph p;
-    if (!pack_graph(*d, p).empty() || (flags & ~2)) return -1;
+    if (!pack_graph(*d, p).empty() || (flags & 1) || (flags & 12) == 8) return -1;
     const GraphView g = view_of(p);
     const Layout l = cta ? make_layout(p.N, p.B, p.E, true, true, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS)
                          : make_layout(p.N, p.B, p.E, true, true);
@@ -196,7 +198,7 @@ int emu_mc_uf_fast(const luf_graph_desc* d, int flags, const double* class_p, un
             LUF_PHASE(uf_cta::ph_reset(g, l, s, lane, nl));
             LUF_PHASE(if (lane < 32) pf ^= ph_sample(g, s, sp, shot0 + k, lane, 32));
             LUF_PHASE(uf_cta::ph_load(g, s, lane, nl));
-            rf = flags ? uf_cta::uf_validate_fast<2>(g, s, 0, nl) : uf_cta::uf_validate_fast<0>(g, s, 0, nl);
+            rf = LUF_EMU_FAST(uf_cta::uf_validate_fast);
             mixed = s.cnt[4] != 0;
             LUF_PHASE(pf ^= uf_cta::ph_defect_sides(g, s, lane, nl));
             LUF_PHASE(uf_cta::ph_reset(g, l, s, lane, nl));
@@ -208,7 +210,7 @@ int emu_mc_uf_fast(const luf_graph_desc* d, int flags, const double* class_p, un
             LUF_PHASE(ph_reset(g, l, s, lane, nl));
             LUF_PHASE(pf ^= ph_sample(g, s, sp, shot0 + k, lane, nl));
             LUF_PHASE(ph_load(g, s, lane, nl));
-            rf = flags ? uf_validate_fast<2>(g, s, 0, nl) : uf_validate_fast<0>(g, s, 0, nl);
+            rf = LUF_EMU_FAST(uf_validate_fast);
             mixed = s.cnt[4] != 0;
             LUF_PHASE(pf ^= ph_defect_sides(g, s, lane, nl));
             LUF_PHASE(ph_reset(g, l, s, lane, nl));

@@ -169,6 +169,10 @@ def test_emu_parity_only_peel_equals_full_peel(spec, p, flags, n, nl):
     (dict(code='Surface', d=5, noise='circuit-level'), 0.02, 0, 1500),
     (dict(code='Repetition', d=7, noise='phenomenological'), 0.08, 0, 3000),
     (dict(code='Repetition', d=5, noise='code capacity'), 0.2, 0, 4000),
+    (dict(code='Surface', d=5, noise='phenomenological'), 0.04, 4, 1500),     # NodeUF
+    (dict(code='Surface', d=7, noise='code capacity'), 0.10, 6, 2000),        # NodeUF, west
+    (dict(code='Surface', d=7, noise='code capacity'), 0.10, 12, 2000),       # NodeBUF
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.02, 14, 1000),       # NodeBUF, west
 ])
 @pytest.mark.parametrize('nl', [32, 128])
 def test_emu_order_free_merge_equals_canonical(spec, p, flags, n, nl):

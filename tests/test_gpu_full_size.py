@@ -88,3 +88,28 @@ def test_macar_fused_equals_staged_and_steps_sum():
     assert sums == (int(steps[:, 0].sum()), int(steps[:, 1].sum()))
     orc = binding.Oracle.from_code(code)
     np.testing.assert_array_equal(orc.syndrome(corr), syn)
+
+
+@pytest.mark.parametrize('spec,p,flags,n,chunk', [
+    (dict(code='Surface', d=11, noise='phenomenological'), 0.026, 0, 2_000_000, 1 << 19),   # 13 % of the shots take the canonical redo
+    (dict(code='Surface', d=11, noise='phenomenological'), 0.02, 2, 1_000_000, 1 << 19),    # west inclination
+    (dict(code='Surface', d=9, noise='code capacity'), 0.10, 2, 2_000_000, 1 << 20),
+    (dict(code='Surface', d=7, noise='circuit-level'), 0.01, 0, 1_000_000, 1 << 19),
+    (dict(code='Surface', d=17, noise='phenomenological'), 0.02, 0, 200_000, 1 << 16),      # one thread block per shot
+    (dict(code='Surface', d=17, noise='phenomenological'), 0.03, 2, 60_000, 1 << 15),
+    (dict(code='Repetition', d=9, noise='phenomenological'), 0.06, 0, 2_000_000, 1 << 20),
+    (dict(code='Surface', d=9, noise='phenomenological'), 0.02, 4, 1_000_000, 1 << 19),     # NodeUF
+    (dict(code='Surface', d=9, noise='code capacity'), 0.10, 12, 1_000_000, 1 << 19),       # NodeBUF
+], ids=['cfg3-threshold', 'cfg3-west', 'sf9cc-west', 'sf7cl', 'sf17-block', 'sf17-block-west', 'rep9', 'nodeuf', 'nodebuf'])
+def test_fused_order_free_path_equals_staged(spec, p, flags, n, chunk):
+    """The fused kernels of static UF merge a round's edges in any order and replace the peel by a pass over
+    the defects; shots in which a cluster spans both sides are decoded again in canonical
+    order.  Same seed, same shots: the failure count equals the staged pipeline's (canonical merge, full
+    peel, luf_check) -- near threshold, with the west inclination, on both tile shapes."""
+    from localuf_b200 import _engine
+    code = make_code(spec)
+    eng = _engine.Engine(code, device=0)
+    seed = 77
+    fused, shots = eng.mc_run_host(_engine.DEC_UF, flags, p, seed, 0, n)
+    staged, _ = staged_failures(eng, _engine.DEC_UF, flags, p, seed, n, chunk)
+    assert shots == n and fused == staged and fused > 0
