@@ -761,6 +761,31 @@ LUF_DEV void ph_fmerge_apply(const GraphView& g, const Shot& s, uint32_t i, int 
     }
 }
 
+// This round's newly FULL edges into the list, in no particular order (one atomic add per lane instead of the
+// ordered compaction's scan).  cnt[6] (0 on entry) hands out the positions and ends up as the number of newly FULL
+// edges; those beyond the list's capacity stay in the bitmap for the next chunk.
+LUF_DEV void ph_fmerge_gather(const GraphView& g, const Shot& s, int lane, int nl)
+{
+    const int wpl = (g.WE + nl - 1) / nl;
+    const int w0 = lane * wpl, w1 = w0 + wpl < g.WE ? w0 + wpl : g.WE;
+    if (lane == 0) { s.cnt[0] = 0; s.cnt[1] = 0; }                // what ph_grow_gather expects
+    uint32_t c = 0;
+    LUF_NOUNROLL
+    for (int w = w0; w < w1; ++w) c += (uint32_t)luf_popc(s.newfull[w]);
+    if (!c) return;
+    uint32_t pos = luf_atomic_add(&s.cnt[6], c);
+    LUF_NOUNROLL
+    for (int w = w0; w < w1 && pos < LUF_T_LIST_CAP; ++w) {
+        uint32_t bits = s.newfull[w];
+        LUF_NOUNROLL
+        while (bits && pos < LUF_T_LIST_CAP) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            s.list[pos++] = (uint32_t)(32 * w + b);
+        }
+        s.newfull[w] = bits;
+    }
+}
+
 // uf_validate_t with the order-free merge.  TF: any of FLAG_WEST, FLAG_NODE, FLAG_NODE | FLAG_BUCKET (cluster
 // sizes, the bucket key of NodeBUF, do not depend on the merge order either).
 template <int TF>
@@ -787,9 +812,9 @@ LUF_DEV int uf_validate_fast(const GraphView& g, const Shot& s, int lane, int nl
         LUF_NOUNROLL
         for (;;) {                             // chunks of at most LUF_T_LIST_CAP edges
             uint32_t n = 0, left = 0;
-            LUF_T_SCAN_PREP(merge_count(g, s, lane, nl));
-            LUF_T_PHASE(ph_merge_gather(g, s, lane, nl));
-            LUF_T_PHASE(n = s.cnt[2]; left = s.cnt[3]);
+            LUF_T_PHASE(ph_fmerge_gather(g, s, lane, nl));
+            LUF_T_PHASE(const uint32_t total = s.cnt[6]; n = total < LUF_T_LIST_CAP ? total : LUF_T_LIST_CAP; left = total - n);
+            LUF_T_PHASE(if (lane == 0) s.cnt[6] = 0);
             LUF_NOUNROLL
             for (uint32_t base = 0; base < n; base += width) {
                 LUF_T_PHASE(if ((uint32_t)lane < width && base + (uint32_t)lane < n) ph_fmerge_hook(g, s, base + (uint32_t)lane, lane));
