@@ -277,11 +277,14 @@ int luf_stream_mc(luf_stream *s, int flags, const double *class_p_host, uint64_t
  * unclustered_edge_fraction); luf_stream_decode_metrics: mins_dev [nstreams][ncycles][2] =
  * (min_defect_height, min_active_layer) after each cycle; luf_stream_mc_metrics: cycle_dev
  * [nstreams][n*d][4] = (min_defect_height, min_active_layer, runtime 'all', runtime 'unrooting') after
- * each TIMED cycle (throughput = 1 / runtime).  Both NULL = the plain calls. */
+ * each TIMED cycle (throughput = 1 / runtime).  Both NULL = the plain calls.
+ * drop_only_dev (optional, [nstreams][ncycles]): 1 = on this cycle the decoder only drops --
+ * Snowflake.decode(defects_possible=False), snowflake/main.py:244-264: rt = (1, 0). */
 int luf_stream_growth_words(const luf_stream *s);
 int luf_stream_decode_metrics(luf_stream *s, int flags, int64_t nstreams, int32_t ncycles,
                               const uint32_t *fresh_bits_dev, int32_t *rt_dev, uint32_t *floor_bits_dev,
-                              int32_t *m_dev, uint32_t *growth2b_dev, int32_t *mins_dev, void *stream);
+                              int32_t *m_dev, uint32_t *growth2b_dev, int32_t *mins_dev,
+                              const uint8_t *drop_only_dev, void *stream);
 int luf_stream_mc_metrics(luf_stream *s, int flags, const double *class_p_host, uint64_t seed, uint64_t stream0,
                           int64_t nstreams, int32_t n, unsigned long long *counts_dev, int32_t *steps_dev,
                           uint32_t *growth2b_dev, int32_t *cycle_dev, void *stream);

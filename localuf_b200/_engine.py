@@ -162,7 +162,7 @@ def _load():
         lib.luf_stream_decode_host.argtypes = [v, C.c_int, i64, C.c_int32, v, v, v, v]
         lib.luf_stream_mc_host.argtypes = [v, C.c_int, v, u64, u64, i64, C.c_int32, v, v]
         lib.luf_stream_growth_words.argtypes = [v]
-        lib.luf_stream_decode_metrics.argtypes = [v, C.c_int, i64, C.c_int32, v, v, v, v, v, v, v]
+        lib.luf_stream_decode_metrics.argtypes = [v, C.c_int, i64, C.c_int32, v, v, v, v, v, v, v, v]
         lib.luf_stream_mc_metrics.argtypes = [v, C.c_int, v, u64, u64, i64, C.c_int32, v, v, v, v, v]
         lib.luf_stream_latency.argtypes = [v, C.c_int, v, u64, u64, i64, v, v]
         lib.luf_stream_latency_host.argtypes = [v, C.c_int, v, u64, u64, i64, v]
@@ -425,23 +425,27 @@ class StreamEngine:
     def growth_words(self) -> int:
         return int(_load().luf_stream_growth_words(self._h))
 
-    def decode_metrics(self, flags: int, fresh_bits):
+    def decode_metrics(self, flags: int, fresh_bits, drop_only=None):
         """As :meth:`decode_host`, plus the window's growth after every cycle (a DEVICE int32 tensor
         [nstreams * ncycles, growth_words], input of ``luf_dcs_run``) and mins [nstreams, ncycles, 2] =
-        (min_defect_height, min_active_layer)."""
+        (min_defect_height, min_active_layer).  ``drop_only`` (optional, bool [nstreams, ncycles]): cycles on
+        which the decoder only drops (``decode(defects_possible=False)``)."""
         import torch
         fresh = np.ascontiguousarray(fresh_bits, dtype=np.uint32)
         ns, nc = fresh.shape[0], fresh.shape[1]
         dev = torch.device('cuda', self.device)
         with torch.cuda.device(dev):
             fr = torch.from_numpy(fresh.view(np.int32)).to(dev)
+            drop = None
+            if drop_only is not None:
+                drop = torch.from_numpy(np.ascontiguousarray(drop_only, dtype=np.uint8).reshape(ns, nc)).to(dev)
             rt = torch.zeros((ns, nc, 2), dtype=torch.int32, device=dev)
             m = torch.zeros((ns, nc), dtype=torch.int32, device=dev)
             floor = torch.zeros((ns, nc, self.W), dtype=torch.int32, device=dev)
             growth = torch.zeros((ns * nc, self.growth_words), dtype=torch.int32, device=dev)
             mins = torch.zeros((ns, nc, 2), dtype=torch.int32, device=dev)
             _check(_load().luf_stream_decode_metrics(self._h, flags, ns, nc, _ptr(fr), _ptr(rt), _ptr(floor), _ptr(m),
-                                                     _ptr(growth), _ptr(mins), _stream()))
+                                                     _ptr(growth), _ptr(mins), _ptr(drop), _stream()))
             return (rt.cpu().numpy(), floor.cpu().numpy().view(np.uint32), m.cpu().numpy(), growth, mins.cpu().numpy())
 
     def mc_metrics(self, flags: int, noise_level: float, seed: int, stream0: int, nstreams: int, n: int):

@@ -368,7 +368,7 @@ __global__ void k_fw_mc(FwArgs a, SampleParams sp, unsigned long long stream0, l
 __global__ void k_sf_decode(SfView g, SfLayout l, int flags, long long nstreams, int ncycles,
                             const uint32_t* __restrict__ fresh, int32_t* __restrict__ rt,
                             uint32_t* __restrict__ floor_bits, int32_t* __restrict__ m_out,
-                            uint32_t* __restrict__ mgrowth, int32_t* __restrict__ mins)
+                            uint32_t* __restrict__ mgrowth, int32_t* __restrict__ mins, const uint8_t* __restrict__ drop_only)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, nl = WARP;
@@ -379,7 +379,7 @@ __global__ void k_sf_decode(SfView g, SfLayout l, int flags, long long nstreams,
         const size_t row0 = (size_t)k * ncycles;
         sf_warp::sf_decode_stream(g, s, flags, ncycles, fresh + row0 * g.ELw, rt + 2 * row0,
                                   floor_bits ? floor_bits + row0 * g.ELw : nullptr, m_out + row0,
-                                  mgrowth ? mgrowth + row0 * (size_t)(g.h * 2 * g.ELw) : nullptr, mins + 2 * row0, lane, nl);
+                                  mgrowth ? mgrowth + row0 * (size_t)(g.h * 2 * g.ELw) : nullptr, mins + 2 * row0, drop_only ? drop_only + row0 : nullptr, lane, nl);
     }
 }
 
@@ -409,7 +409,7 @@ __global__ void k_sf_mc(SfView g, SfLayout l, SampleParams sp, int flags, unsign
 __global__ void k_sf_decode_cta(SfView g, SfLayout l, int flags, long long nstreams, int ncycles,
                                 const uint32_t* __restrict__ fresh, int32_t* __restrict__ rt,
                                 uint32_t* __restrict__ floor_bits, int32_t* __restrict__ m_out,
-                                uint32_t* __restrict__ mgrowth, int32_t* __restrict__ mins)
+                                uint32_t* __restrict__ mgrowth, int32_t* __restrict__ mins, const uint8_t* __restrict__ drop_only)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
@@ -418,7 +418,7 @@ __global__ void k_sf_decode_cta(SfView g, SfLayout l, int flags, long long nstre
         const size_t row0 = (size_t)k * ncycles;
         sf_cta::sf_decode_stream(g, s, flags, ncycles, fresh + row0 * g.ELw, rt + 2 * row0,
                                  floor_bits ? floor_bits + row0 * g.ELw : nullptr, m_out + row0,
-                                 mgrowth ? mgrowth + row0 * (size_t)(g.h * 2 * g.ELw) : nullptr, mins + 2 * row0, lane, nl);
+                                 mgrowth ? mgrowth + row0 * (size_t)(g.h * 2 * g.ELw) : nullptr, mins + 2 * row0, drop_only ? drop_only + row0 : nullptr, lane, nl);
     }
 }
 
@@ -976,19 +976,19 @@ int luf_stream_decode(luf_stream* g, int flags, int64_t nstreams, int32_t ncycle
                       int32_t* rt_dev, uint32_t* floor_bits_dev, int32_t* m_dev, void* stream)
 {
     return luf_stream_decode_metrics(g, flags, nstreams, ncycles, fresh_bits_dev, rt_dev, floor_bits_dev, m_dev,
-                                     nullptr, nullptr, stream);
+                                     nullptr, nullptr, nullptr, stream);
 }
 
 int luf_stream_growth_words(const luf_stream* g) { return g ? g->view.h * 2 * g->view.ELw : 0; }
 
 int luf_stream_decode_metrics(luf_stream* g, int flags, int64_t nstreams, int32_t ncycles, const uint32_t* fresh_bits_dev,
                               int32_t* rt_dev, uint32_t* floor_bits_dev, int32_t* m_dev, uint32_t* growth2b_dev,
-                              int32_t* mins_dev, void* stream)
+                              int32_t* mins_dev, const uint8_t* drop_only_dev, void* stream)
 {
     if (!g || !fresh_bits_dev || !rt_dev || !m_dev || nstreams < 0 || ncycles < 0 || (!growth2b_dev) != (!mins_dev))
         return fail(LUF_ERR_INVALID, "luf_stream_decode: bad argument");
-    if (growth2b_dev && (flags & LUF_SF_LATENCY_TAIL))
-        return fail(LUF_ERR_INVALID, "per-cycle metrics are not recorded on the drop-only tail of sample_latency");
+    if ((growth2b_dev || drop_only_dev) && (flags & LUF_SF_LATENCY_TAIL))
+        return fail(LUF_ERR_INVALID, "per-cycle metrics / drop-only flags do not combine with the tail of sample_latency");
     if (flags & ~(LUF_SF_SLOW_MERGER | LUF_SF_ONE_ONE | LUF_SF_SYNDROME | LUF_SF_LATENCY_TAIL))
         return fail(LUF_ERR_INVALID, "unknown Snowflake flag");
     if (nstreams == 0 || ncycles == 0) return 0;
@@ -998,12 +998,12 @@ int luf_stream_decode_metrics(luf_stream* g, int flags, int64_t nstreams, int32_
         if (int rc = plan_stream_cta_launch(g, k_sf_decode_cta, nstreams, &c)) return rc;
         k_sf_decode_cta<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_cta, flags, nstreams, ncycles,
                                                                             fresh_bits_dev, rt_dev, floor_bits_dev, m_dev,
-                                                                            growth2b_dev, mins_dev);
+                                                                            growth2b_dev, mins_dev, drop_only_dev);
     } else {
         if (int rc = plan_stream_launch(g, k_sf_decode, nstreams, &c)) return rc;
         k_sf_decode<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay, flags, nstreams, ncycles,
                                                                         fresh_bits_dev, rt_dev, floor_bits_dev, m_dev,
-                                                                        growth2b_dev, mins_dev);
+                                                                        growth2b_dev, mins_dev, drop_only_dev);
     }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;

@@ -27,8 +27,10 @@ LUF_DEV void sf_merge(const SfView& g, const SfShot& s, bool whole, bool slow, i
 // (_schemes.py:262-276).  `floor_out` (optional, ELw words, global) receives the
 // floor-sheet correction committed by this cycle's drop.  `m` is only
 // meaningful on lane 0 (in the emulation: the single accumulated value).
+// `drop_only`: decode(defects_possible=False), snowflake/main.py:244-264 -- the window moves, nothing grows or
+// merges; the runtime is 1 timestep for time_only = 'all' and 0 otherwise (rt_all = 1, rt_unr = 0).
 LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t* floor_out,
-                           int& m, int& rt_all, int& rt_unr, int lane, int nl)
+                           int& m, int& rt_all, int& rt_unr, int lane, int nl, bool drop_only = false)
 {
     const bool slow = flags & SF_FLAG_SLOW, one_one = flags & SF_FLAG_ONE_ONE;
     (void)lane;
@@ -43,7 +45,9 @@ LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t
     if (LUF_ST_ANY(any_corr)) { LUF_ST_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.corr + (g.h - 1) * g.ELw, m)); }
     LUF_ST_PHASE(sf_drop(g, s, lane, nl));
     LUF_SF_REGATHER();                               // the window moved
-    if (one_one) {
+    if (drop_only) {
+        rt_all = 1;
+    } else if (one_one) {
         LUF_ST_PHASE(sf_grow(g, s, 0, lane, nl));
         LUF_SF_REGATHER();                           // growth wakes nodes
         sf_merge(g, s, true, slow, rt_all, rt_unr, lane, nl);
@@ -134,11 +138,12 @@ LUF_DEV bool sf_window_has_defect(const SfView& g, const SfShot& s, int lane, in
 // SF_FLAG_SYNDROME, top-sheet syndromes) are GIVEN as rows of ELw words.  rt [ncycles][2] = decode's
 // return value for time_only = 'all' / 'unrooting'; floor_bits (optional) [ncycles][ELw]; m_out [ncycles];
 // mgrowth / mins (optional, [ncycles][h*2*ELw] and [ncycles][2]): the window's growth and
-// (min_defect_height, min_active_layer) after every cycle.
+// (min_defect_height, min_active_layer) after every cycle; drop_only (optional, [ncycles]): cycles on which the
+// decoder only drops (defects_possible = False).
 // SF_FLAG_LATENCY_TAIL: the last h - 1 cycles are the noiseless tail of Frugal.sample_latency.
 LUF_DEV void sf_decode_stream(const SfView& g, const SfShot& s, int flags, int ncycles, const uint32_t* fresh,
                               int32_t* rt, uint32_t* floor_bits, int32_t* m_out, uint32_t* mgrowth, int32_t* mins,
-                              int lane, int nl)
+                              const uint8_t* drop_only, int lane, int nl)
 {
     LUF_ST_PHASE(sf_reset(g, s, lane, nl));
     bool possible = true;                        // defects_possible of Frugal.sample_latency
@@ -155,7 +160,8 @@ LUF_DEV void sf_decode_stream(const SfView& g, const SfShot& s, int flags, int n
         sf_cycle_head(g, s, m, lane, nl);
         if (flags & SF_FLAG_SYNDROME) { LUF_ST_PHASE(sf_given_syndrome(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
         else { LUF_ST_PHASE(sf_given_sheet(g, s, fresh + (size_t)c * g.ELw, lane, nl)); }
-        sf_cycle_tail(g, s, flags, floor_bits ? floor_bits + (size_t)c * g.ELw : nullptr, m, ra, ru, lane, nl);
+        sf_cycle_tail(g, s, flags, floor_bits ? floor_bits + (size_t)c * g.ELw : nullptr, m, ra, ru, lane, nl,
+                      drop_only && drop_only[c]);
         if (lane == 0) { rt[2 * c] = ra; rt[2 * c + 1] = ru; m_out[c] = m; }
         if (mgrowth) sf_cycle_metrics(g, s, mgrowth + (size_t)c * (size_t)(g.h * 2 * g.ELw), mins + 2 * (size_t)c, lane, nl);
     }

@@ -49,6 +49,7 @@ class Snowflake(Decoder):
         self._lowest_local = np.array(
             [self._tables.layered_of_code[index[e]] % self._tables.EL for e in self._LOWEST_EDGES], np.int64)
         self._cycles: list = []            # syndrome rows of the decoding cycles since reset()
+        self._drops: list = []             # per cycle: the decoder only dropped (defects_possible=False)
         self._state = None                 # (number of cycles, growth export, mins) of the last replay with metrics
         self._dcs_engines: dict = {}
         self.confidence_score_history = defaultdict(list)      # snowflake/main.py:124-126
@@ -68,6 +69,7 @@ class Snowflake(Decoder):
         """``snowflake/main.py:201-214``: an empty window; forgets ``floor_history``."""
         super().reset()
         self._cycles = []
+        self._drops = []
         self._state = None
         self.confidence_score_history = defaultdict(list)
         self.min_active_layers = Counter()
@@ -95,8 +97,13 @@ class Snowflake(Decoder):
         bits = (floor_row[self._lowest_local >> 5] >> (self._lowest_local & 31).astype(np.uint32)) & 1
         return ''.join('1' if b else '0' for b in bits)
 
-    def _run_cycles(self, rows):
-        """One window, the given syndrome rows in order -> (runtimes [n, 2], floor rows [n, W])."""
+    def _run_cycles(self, rows, drops=None):
+        """One window, the given syndrome rows in order -> (runtimes [n, 2], floor rows [n, W]).
+        ``drops``: per cycle, whether the decoder only drops (``defects_possible=False``)."""
+        if drops is not None and any(drops):
+            rt, floor, _, _, _ = self.engine.decode_metrics(self._flags | _engine.SF_SYNDROME, np.stack(rows)[None],
+                                                            drop_only=np.array(drops, np.uint8)[None])
+            return rt[0], floor[0]
         rt, floor, _ = self.engine.decode_host(self._flags | _engine.SF_SYNDROME, np.stack(rows)[None])
         return rt[0], floor[0]
 
@@ -110,21 +117,20 @@ class Snowflake(Decoder):
         of cycles -- use :meth:`generate_output` or ``Frugal.run`` for long streams)."""
         if log_history:
             raise NotImplementedError("Drawing / history are outside this engine.")
-        if not defects_possible:
-            raise NotImplementedError("defects_possible=False (drop only) is not built.")
         if time_only not in ('all', 'merging', 'unrooting'):
             raise ValueError(f'Unknown time_only: {time_only}.')
         metrics = tuple(metrics)
         self._check_metrics(metrics)
         self._cycles.append(self._syndrome_row(syndrome))
+        self._drops.append(not defects_possible)       # the decoder only drops (snowflake/main.py:244-264)
         self._state = None
         if metrics:
             rt, floor, growth, mins = self._replay_with_metrics()
         else:
-            rt, floor = self._run_cycles(self._cycles)
+            rt, floor = self._run_cycles(self._cycles, self._drops)
         if log_floor_history:
             self.floor_history.append(self._floor_vector(floor[-1]))
-        runtime = self._runtime(rt[-1], time_only)
+        runtime = self._runtime(rt[-1], time_only) if defects_possible else (1 if time_only == 'all' else 0)
         if metrics:
             swim = uef = None
             if 'swim_distance' in metrics or 'unclustered_edge_fraction' in metrics:
@@ -177,7 +183,9 @@ class Snowflake(Decoder):
         """Replay the cycles since ``reset`` with the per-cycle export; the last replay is kept."""
         if self._state is None or self._state[0] != len(self._cycles):
             rows = self._cycles if self._cycles else [np.zeros(self.engine.W, np.uint32)]
-            rt, floor, _, growth, mins = self.engine.decode_metrics(self._flags | _engine.SF_SYNDROME, np.stack(rows)[None])
+            drops = np.array(self._drops if self._cycles else [False], np.uint8)[None]
+            rt, floor, _, growth, mins = self.engine.decode_metrics(self._flags | _engine.SF_SYNDROME, np.stack(rows)[None],
+                                                                    drop_only=drops if drops.any() else None)
             self._state = (len(self._cycles), rt[0], floor[0], growth, mins[0])
         return self._state[1:]
 
@@ -247,8 +255,9 @@ class Snowflake(Decoder):
             sets = list(syndromes) + h * [set()]
             vectors = conv.sets_to_syndrome_vectors(sets)
         self.init_history()
-        _, floor = self._run_cycles(self._cycles + [self._syndrome_row(s) for s in sets])
+        _, floor = self._run_cycles(self._cycles + [self._syndrome_row(s) for s in sets], self._drops + [False] * len(sets))
         self._cycles += [self._syndrome_row(s) for s in sets]
+        self._drops += [False] * len(sets)
         self.floor_history += [self._floor_vector(f) for f in floor[len(floor) - len(sets):]]
         if output_to_csv_file is not None:
             import csv

@@ -74,4 +74,48 @@ def io_case(name, spec, dec_kw, density, cycles, seed):
 
 
 def jobs():
-    return {case[0]: (lambda c=case: io_case(*c)) for case in IO_CASES}
+    out = {case[0]: (lambda c=case: io_case(*c)) for case in IO_CASES}
+    out.update({case[0]: (lambda c=case: iod_case(*c)) for case in IOD_CASES})
+    return out
+
+
+# ---- decode(..., defects_possible=False): cycles on which the decoder only drops (snowflake/main.py:244-264)
+IOD_CASES = [
+    ('iod_rep5_phen', dict(code='Repetition', d=5, noise='phenomenological', kwargs=dict(scheme='frugal')), {}, 0.20, 60, 91),
+    ('iod_sf3_cl', dict(code='Surface', d=3, noise='circuit-level', kwargs=dict(scheme='frugal')), {}, 0.10, 50, 92),
+    ('iod_sf5_phen', dict(code='Surface', d=5, noise='phenomenological', kwargs=dict(scheme='frugal')), {}, 0.05, 30, 93),
+    ('iod_sf5_cl_11', dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='frugal')),
+     dict(schedule='1:1'), 0.04, 24, 94),
+]
+
+
+def iod_case(name, spec, dec_kw, density, cycles, seed):
+    """Random syndrome vectors; on a random third of the cycles the decoder is told that no defect is possible
+    (it then only drops, whatever the window holds).  Runtimes for the three time_only modes and the floor
+    vectors logged by decode(log_floor_history=True)."""
+    import gen_golden as G
+    code = G.make_code(spec)
+    dec = Snowflake(code, **dec_kw)
+    conv = dec._BITSTRING_CONVERTER
+    rng = random.Random(seed)
+    vectors = [''.join('1' if rng.random() < density else '0' for _ in range(conv.LENGTH)) for _ in range(cycles)]
+    drop_only = [rng.random() < 1 / 3 for _ in range(cycles)]
+    sets = conv.syndrome_vectors_to_sets(vectors)
+    runtimes, floors = {}, None
+    for mode in ('all', 'merging', 'unrooting'):
+        dec.reset()
+        dec.init_history()
+        runtimes[mode] = [dec.decode(set(s), time_only=mode, defects_possible=not d, log_floor_history=True)
+                          for s, d in zip(sets, drop_only)]
+        if floors is None:
+            floors = list(dec.floor_history)
+        assert floors == list(dec.floor_history)
+    arrays = dict(
+        vectors=np.array([[int(c) for c in v] for v in vectors], np.uint8),
+        drop_only=np.array(drop_only, np.uint8),
+        floors=np.array([[int(c) for c in f] for f in floors], np.uint8),
+        runtime_all=np.array(runtimes['all'], np.int32), runtime_merging=np.array(runtimes['merging'], np.int32),
+        runtime_unrooting=np.array(runtimes['unrooting'], np.int32))
+    meta = dict(kind='snowflake decode with defects_possible', spec=spec, decoder_kwargs=dec_kw, density=density,
+                cycles=cycles, seed=seed, source='unmodified reference Snowflake.decode(defects_possible=...)')
+    return meta, arrays

@@ -312,7 +312,8 @@ int emu_fw_stream(const luf_graph_desc* gd, const luf_forward_desc* fd, int deco
 
 // Snowflake + frugal bookkeeping on given fresh errors (one stream).
 int emu_sf_stream_metrics(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
-                          int32_t* rt, uint32_t* floor_bits, int32_t* m_out, uint32_t* mgrowth, int32_t* mins, int nl)
+                          int32_t* rt, uint32_t* floor_bits, int32_t* m_out, uint32_t* mgrowth, int32_t* mins,
+                          const uint8_t* drop_only, int nl)
 {
     const bool cta = nl != 32;
     PackedWindow p;
@@ -325,15 +326,15 @@ int emu_sf_stream_metrics(const luf_window_desc* d, int flags, int ncycles, cons
     const SfLayout l = cta ? make_sf_layout(p, SF_CTA_ALIST_CAP) : make_sf_layout(p);
     std::vector<unsigned char> mem(l.bytes);
     const SfShot s = sf_bind(l, mem.data());
-    if (cta) sf_cta::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, mgrowth, mins, 0, nl);
-    else sf_warp::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, mgrowth, mins, 0, nl);
+    if (cta) sf_cta::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, mgrowth, mins, drop_only, 0, nl);
+    else sf_warp::sf_decode_stream(g, s, flags, ncycles, fresh, rt, floor_bits, m_out, mgrowth, mins, drop_only, 0, nl);
     return 0;
 }
 
 int emu_sf_stream_tile(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
                        int32_t* rt, uint32_t* floor_bits, int32_t* m_out, int nl)
 {
-    return emu_sf_stream_metrics(d, flags, ncycles, fresh, rt, floor_bits, m_out, nullptr, nullptr, nl);
+    return emu_sf_stream_metrics(d, flags, ncycles, fresh, rt, floor_bits, m_out, nullptr, nullptr, nullptr, nl);
 }
 
 // Frugal.sample_latency streams with the device sampler (host arithmetic): lat [nstreams][3].

@@ -180,14 +180,15 @@ class EmuStream:
         assert rc == 0, rc
         return rt, floor, m
 
-    def stream_metrics(self, flags, fresh_local_bits, nl=32):
+    def stream_metrics(self, flags, fresh_local_bits, nl=32, drop_only=None):
         """As :meth:`stream`, plus the window's growth words and (min_defect_height, min_active_layer) per cycle."""
         fresh = np.ascontiguousarray(fresh_local_bits, dtype=np.uint32).reshape(-1, self.W)
         n = fresh.shape[0]
         rt = np.zeros((n, 2), np.int32); m = np.zeros(n, np.int32); floor = np.zeros((n, self.W), np.uint32)
         growth = np.zeros((n, self.tables.h * 2 * self.W), np.uint32); mins = np.zeros((n, 2), np.int32)
+        drop = None if drop_only is None else np.ascontiguousarray(drop_only, dtype=np.uint8)
         rc = lib().emu_sf_stream_metrics(C.byref(self.desc), flags, n, _vp(fresh), _vp(rt), _vp(floor), _vp(m),
-                                         _vp(growth), _vp(mins), nl)
+                                         _vp(growth), _vp(mins), _vp(drop), nl)
         assert rc == 0, rc
         return rt, floor, m, growth, mins
 

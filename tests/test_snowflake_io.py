@@ -38,7 +38,11 @@ def on_emulation(dec):
     import emu_binding
     emu = emu_binding.EmuStream(dec.CODE, dec._tables)          # the decoder's own neighbour order
 
-    def run(rows):
+    def run(rows, drops=None):
+        if drops is not None and any(drops):
+            rt, floor, _, _, _ = emu.stream_metrics(dec._flags | _engine.SF_SYNDROME, np.stack(rows),
+                                                    drop_only=np.array(drops, np.uint8))
+            return rt, floor
         rt, floor, _ = emu.stream(dec._flags | _engine.SF_SYNDROME, np.stack(rows))
         return rt, floor
     dec._run_cycles = run
@@ -80,6 +84,35 @@ def test_emu_generate_output_matches_reference(name):
 @pytest.mark.parametrize('name', golden_names('io_'))
 def test_gpu_generate_output_matches_reference(name):
     check_case(name, lambda dec: dec)
+
+
+def check_drop_only_case(name, prepare):
+    """decode(..., defects_possible=False) on a random third of the cycles (snowflake/main.py:244-264)."""
+    meta, arr = load_golden(name)
+    code = make_code(meta['spec'])
+    dec = prepare(L.decoders.Snowflake(code, **meta['decoder_kwargs']))
+    vectors, floors = strings(arr['vectors']), strings(arr['floors'])
+    sets = dec._BITSTRING_CONVERTER.syndrome_vectors_to_sets(vectors)
+    n = min(len(sets), 24)
+    for mode in ('all', 'merging', 'unrooting'):
+        dec.reset()
+        dec.init_history()
+        got = [dec.decode(s, time_only=mode, defects_possible=not d, log_floor_history=True)
+               for s, d in zip(sets[:n], arr['drop_only'][:n])]
+        assert got == arr[f'runtime_{mode}'][:n].tolist(), mode
+        assert dec.floor_history == floors[:n]
+    assert arr['drop_only'][:n].any() and not arr['drop_only'][:n].all()
+
+
+@pytest.mark.parametrize('name', golden_names('iod_'))
+def test_emu_decode_drop_only_cycles(name):
+    check_drop_only_case(name, on_emulation)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', golden_names('iod_'))
+def test_gpu_decode_drop_only_cycles(name):
+    check_drop_only_case(name, lambda dec: dec)
 
 
 def notebook_cases():
