@@ -46,3 +46,39 @@ def test_no_cpu_fallback(lib):
                  any(('import' in l or 'include' in l or 'CDLL' in l) and 'oracle' in l
                      for l in open(f, errors='ignore'))]
     assert offenders == []
+
+
+def test_no_cpu_fallback_for_scores_and_streams(lib):
+    """The confidence scores and the streaming decoder have no host path either."""
+    import localuf_b200 as L
+    from localuf_b200 import _dcs, _engine
+    if lib.luf_device_count() > 0:
+        pytest.skip('a GPU is present')
+    code = L.Surface(3, 'code capacity')
+    uf = L.decoders.UF(code)
+    with pytest.raises(_engine.EngineUnavailable):
+        uf.swim_distance()
+    with pytest.raises(_engine.EngineUnavailable):
+        _dcs.DcsEngine(_dcs.flat_tables(code))
+    frugal = L.Surface(3, 'phenomenological', scheme='frugal')
+    sf = L.decoders.Snowflake(frugal)
+    with pytest.raises(_engine.EngineUnavailable):
+        sf.decode(set(), metrics=('swim_distance',))
+    with pytest.raises(_engine.EngineUnavailable):
+        frugal.SCHEME.run(sf, 0.01, 1, metrics=('min_defect_height',))
+
+
+def test_bad_arguments_fail_before_any_device_work(lib):
+    """Argument checks of the newer entry points run first: NULL handles and descriptions are rejected with
+    LUF_ERR_INVALID (-1) and a message, with or without a GPU."""
+    lib.luf_last_error.restype = ctypes.c_char_p
+    out = ctypes.c_void_p()
+    assert lib.luf_dcs_create(None, 0, ctypes.byref(out)) == -1
+    assert b'luf_dcs_create' in lib.luf_last_error()
+    assert lib.luf_dcs_run(None, ctypes.c_int64(1), None, ctypes.c_int64(1), 1, None, None, None, None) == -1
+    assert lib.luf_dcs_run_host(None, ctypes.c_int64(1), None, ctypes.c_int64(1), 1, None, None, None) == -1
+    assert lib.luf_stream_decode_metrics(None, 0, ctypes.c_int64(1), 1, None, None, None, None, None, None, None, None) == -1
+    assert lib.luf_stream_mc_metrics(None, 0, None, ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_int64(1), 1,
+                                     None, None, None, None, None) == -1
+    assert lib.luf_stream_growth_words(None) == 0
+    assert lib.luf_dcs_destroy(None) == 0
