@@ -273,6 +273,42 @@ TRAFFIC = {'cfg3': (115968, 'profiles/r01_v12_k_mc_uf_summary.txt'),
            'cfg4': (145920, 'profiles/r01_k_sf_mc_acp_summary.txt (warp tile; the block tile reads the same tables)')}
 
 
+def host_buffer_e2e(eng, p, world, rank, steps, n=1 << 20):
+    """The staged path a hardware-in-the-loop caller uses: HOST syndromes in, HOST corrections out through
+    luf_decode_batch_host (page-locked buffers, host<->device copies inside the timed region, chunks pipelined
+    over three streams).  Returns the `e2e`-style object (shots/s over all ranks)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    WE, WD = eng.WE, eng.WD
+    err = torch.empty(n, WE, dtype=torch.int32, device='cuda')
+    syn = torch.empty(n, WD, dtype=torch.int32, device='cuda')
+    eng.sample(p, SEED + 7, rank * n, n, err, syn)
+    syn_h = torch.empty(n, WD, dtype=torch.int32).pin_memory()
+    corr_h = torch.empty(n, WE, dtype=torch.int32).pin_memory()
+    syn_h.copy_(syn)
+    torch.cuda.synchronize()
+    syn_np, corr_np = syn_h.numpy().view(np.uint32), corr_h.numpy().view(np.uint32)
+    eng.decode_batch_host(0, 0, syn_np, want_steps=False, corr_out=corr_np)       # warm-up: device scratch, streams
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        eng.decode_batch_host(0, 0, syn_np, want_steps=False, corr_out=corr_np)
+        print(f'[bench] host-buffer decode of {n} shots: {1e3 * (time.perf_counter() - t1):.1f} ms', file=sys.stderr)
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {'value': n * world * steps / float(t.item()), 'unit': 'shots/s', 'h2d_bytes_per_step': 4 * WD * n,
+            'd2h_bytes_per_step': 4 * WE * n, 'shots_per_step_per_gpu': n,
+            'api': 'Engine.decode_batch_host(UF, syndromes) -> luf_decode_batch_host: host syndromes in, host '
+                   'corrections out (page-locked buffers, copies inside the timed region)'}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -377,6 +413,11 @@ def run_ours(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = units_per_step_gpu * world * e2e_steps / float(t_e2e.item())
 
+    # ---- and with real host buffers (UF workloads): host syndromes -> host corrections, staged decode kernel
+    e2e_host = None
+    if dec == 'UF' and not stream_mode:
+        e2e_host = host_buffer_e2e(eng, p, world, rank, e2e_steps)
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         kern_ms = statistics.mean(step_ms)
@@ -401,6 +442,7 @@ def run_ours(args):
                                  'issue slots of narrow phases (profiles/)'},
             'e2e': {'value': e2e_value, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 32,
                     'api': api, 'failures': m_e2e},
+            'e2e_host_buffers': e2e_host,
             'gpu_launches': launches,
             'clocks': clocks.summary(),
         }
