@@ -1580,7 +1580,7 @@ int luf_forward_mc_host(luf_graph* g, int decoder, int flags, const double* clas
 
 // ------------------------------------------------------- host-buffer variants
 int luf_mc_run_host(luf_graph* g, int decoder, int flags, const double* class_p_host, uint64_t seed,
-                    uint64_t shot0, int64_t nshots, unsigned long long counts_host[2])
+                    uint64_t shot0, int64_t nshots, unsigned long long counts_host[4])
 {
     if (!g || !counts_host) return fail(LUF_ERR_INVALID, "luf_mc_run_host: bad argument");
     std::lock_guard<std::mutex> lock(g->mu);
