@@ -157,6 +157,7 @@ struct GraphView {
     const uint32_t* edge_uv;    // [E]   u | v<<16
     const uint32_t* west_mask;  // [WE]  edges whose first endpoint is a west boundary node
     const int16_t* node_long;   // [N]   coordinate along the long axis
+    int parity_ok;              // the graph allows the parity-only peel of the fused kernels (pack_graph, luf_host.h)
     // sampler tables: fresh edges sorted by probability class
     int F, n_classes;
     const uint16_t* fresh_perm; // [F]; null when it is the identity (one class, every edge fresh)

@@ -26,6 +26,7 @@ struct PackedGraph {
     int N = 0, B = 0, E = 0, F = 0, n_classes = 0;
     int DEG = 0;
     bool perm_identity = false;
+    bool parity_ok = true;        // see GraphView::parity_ok
     std::vector<uint32_t> adj, edge_uv, west_mask, class_end;
     std::vector<int16_t> node_long;
     std::vector<uint16_t> fresh_perm;
@@ -69,6 +70,16 @@ inline std::string pack_graph(const luf_graph_desc& d, PackedGraph& out)
         }
     }
     out.west_mask.assign(d.west_edge_mask, d.west_edge_mask + words32(E));
+    // What the fused kernels' parity-only peel assumes of the graph (every graph of Surface / Repetition has it):
+    // no edge joins two boundary nodes, and the logical mask is exactly the edges whose FIRST endpoint is a west
+    // boundary node, none of which is ever a second endpoint.  Any other graph takes the full peel.
+    out.parity_ok = true;
+    for (int e = 0; e < E; ++e) {
+        const int u = d.edge_u[e], v = d.edge_v[e];
+        const bool west_first = u < B && d.node_long[u] == -1, west_second = v < B && d.node_long[v] == -1;
+        const bool masked = (d.west_edge_mask[e >> 5] >> (e & 31)) & 1u;
+        if ((u < B && v < B) || west_second || masked != west_first) { out.parity_ok = false; break; }
+    }
     // fresh edges, stably sorted by probability class
     out.class_end.assign(d.n_classes, 0);
     out.fresh_perm.clear();

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleP
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
         LUF_PHASE(ph_load(g, s, lane, nl));
-        if (LUF_FAST_TF(TF)) {                             // static UF / NodeUF / NodeBUF: merges in any order, no peel ...
+        if (LUF_FAST_TF(TF) && g.parity_ok) {                             // static UF / NodeUF / NodeBUF: merges in any order, no peel ...
             uf_validate_fast<(LUF_FAST_TF(TF) ? TF : 0)>(g, s, lane, nl);
             if (__any_sync(0xffffffffu, s.cnt[4] != 0u)) { // ... unless a cluster spans both sides: canonical order
                 parity = 0;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, Sam
         __syncthreads();
         uf_cta::ph_load(g, s, lane, nl);
         __syncthreads();
-        if (LUF_FAST_TF(TF)) {
+        if (LUF_FAST_TF(TF) && g.parity_ok) {
             uf_cta::uf_validate_fast<(LUF_FAST_TF(TF) ? TF : 0)>(g, s, lane, nl);
             if (__syncthreads_or(s.cnt[4] != 0u)) {
                 parity = 0;
@@ -1166,6 +1166,7 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     const PackedGraph& p = g->host;
     GraphView& v = g->view;
     v.N = p.N; v.B = p.B; v.E = p.E; v.F = p.F; v.n_classes = p.n_classes; v.DEG = p.DEG;
+    v.parity_ok = p.parity_ok ? 1 : 0;
     v.WE = words32(p.E); v.WD = words32(p.N - p.B); v.WN = words32(p.N);
     int rc = 0;
     if ((rc = upload(g, p.adj, &v.adj)) ||

@@ -880,7 +880,7 @@ LUF_DEV uint32_t uf_peel_parity(const GraphView& g, const Shot& s, int lane, int
 {
     uint32_t mixed = 0, parity = 0;
     (void)lane;
-    LUF_T_PHASE(mixed = s.cnt[4]);
+    LUF_T_PHASE(mixed = s.cnt[4] | (g.parity_ok ? 0u : 1u));
     if (LUF_T_ANY(mixed)) return uf_peel(g, s, lane, nl);
     LUF_T_PHASE(parity ^= ph_defect_sides(g, s, lane, nl));
     return parity;

@@ -21,7 +21,7 @@ static GraphView view_of(const PackedGraph& p)
     g.WE = words32(p.E); g.WD = words32(p.N - p.B); g.WN = words32(p.N);
     g.DEG = p.DEG; g.adj = p.adj.data(); g.edge_uv = p.edge_uv.data();
     g.west_mask = p.west_mask.data(); g.node_long = p.node_long.data();
-    g.F = p.F; g.n_classes = p.n_classes;
+    g.F = p.F; g.n_classes = p.n_classes; g.parity_ok = p.parity_ok ? 1 : 0;
     g.fresh_perm = p.perm_identity ? nullptr : p.fresh_perm.data(); g.class_end = p.class_end.data();
     return g;
 }
@@ -137,6 +137,14 @@ int emu_mc_uf(const luf_graph_desc* d, int flags, const double* class_p, unsigne
 // The fused kernels' parity-only peel (uf_peel_parity) next to the full peel on the same sampled shots:
 // counts[0] += failures by the full peel, [1] += failures by the parity path, [2] += shots on which the two
 // differ, [3] += shots that hold a cluster with boundary nodes of both sides (they take the full peel).
+// Whether pack_graph found the graph fit for the parity-only peel.
+int emu_parity_ok(const luf_graph_desc* d)
+{
+    PackedGraph p;
+    if (!pack_graph(*d, p).empty()) return -1;
+    return p.parity_ok ? 1 : 0;
+}
+
 int emu_mc_uf_parity(const luf_graph_desc* d, int flags, const double* class_p, unsigned long long seed,
                      unsigned long long shot0, long long nshots, unsigned long long counts[4], int nl)
 {
@@ -147,7 +155,7 @@ int emu_mc_uf_parity(const luf_graph_desc* d, int flags, const double* class_p, 
     const Layout l = cta ? make_layout(p.N, p.B, p.E, true, true, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS)
                          : make_layout(p.N, p.B, p.E, true, true);
     const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
-    std::vector<unsigned char> mem(l.bytes);
+    std::vector<unsigned char> mem(l.bytes), saved;
     const Shot s = bind(l, mem.data());
     for (long long k = 0; k < nshots; ++k) {
         uint32_t parity = 0;
@@ -158,12 +166,16 @@ int emu_mc_uf_parity(const luf_graph_desc* d, int flags, const double* class_p, 
         if (cta) {
             uf_cta::uf_validate(g, s, flags, 0, nl);
             counts[3] += s.cnt[4] ? 1 : 0;
+            if (!g.parity_ok) saved = mem;                                    // the guard sends every shot to the (destructive) full peel
             fast = s.cnt[4] ? 2u : uf_cta::uf_peel_parity(g, s, 0, nl);       // read-only on unmixed shots
+            if (!g.parity_ok) mem = saved;
             full = uf_cta::uf_peel(g, s, 0, nl);
         } else {
             uf_validate(g, s, flags, 0, nl);
             counts[3] += s.cnt[4] ? 1 : 0;
+            if (!g.parity_ok) saved = mem;
             fast = s.cnt[4] ? 2u : uf_peel_parity(g, s, 0, nl);
+            if (!g.parity_ok) mem = saved;
             full = uf_peel(g, s, 0, nl);
         }
         if (fast == 2u) fast = full;

@@ -125,6 +125,10 @@ class Emu:
         assert rc == 0, rc
         return tuple(int(x) for x in counts)
 
+    def parity_ok(self):
+        """Whether pack_graph found the graph fit for the fused kernels' parity-only peel."""
+        return int(lib().emu_parity_ok(C.byref(self.desc)))
+
     def mc_uf_fast(self, flags, noise_level, seed, nshots, nl=32):
         """(failures canonical, failures by the order-free merge + parity path, shots where they differ,
         mixed shots, shots whose round counts differ)."""

@@ -159,6 +159,22 @@ def test_emu_parity_only_peel_equals_full_peel(spec, p, flags, n, nl):
         assert 0 < mixed < n                     # both branches are exercised
 
 
+def test_emu_parity_peel_guard():
+    """pack_graph admits the parity-only peel for the graphs of Surface / Repetition and refuses it for a
+    graph whose logical mask is not "first endpoint is a west boundary node"; a refused graph takes the
+    full peel on every shot, so the fused path still equals the staged one."""
+    for spec in (dict(code='Surface', d=5, noise='code capacity'), dict(code='Surface', d=5, noise='phenomenological'),
+                 dict(code='Surface', d=3, noise='circuit-level'), dict(code='Repetition', d=5, noise='phenomenological')):
+        assert emu_binding.Emu(make_code(spec)).parity_ok() == 1
+    emu = emu_binding.Emu(make_code(dict(code='Surface', d=5, noise='code capacity')))
+    mask = emu._keep['west_edge_mask']
+    e = next(i for i in range(emu.flat.n_edges) if not (mask[i >> 5] >> (i & 31)) & 1)
+    mask[e >> 5] |= np.uint32(1 << (e & 31))         # another logical operator: one bulk edge more
+    assert emu.parity_ok() == 0
+    full, fast, differ, mixed = emu.mc_uf_parity(0, 0.12, 5, 3000)
+    assert differ == 0 and full == fast and full > 0
+
+
 @pytest.mark.parametrize('spec,p,flags,n', [
     (dict(code='Surface', d=5, noise='code capacity'), 0.12, 0, 4000),
     (dict(code='Surface', d=5, noise='code capacity'), 0.12, 2, 4000),
