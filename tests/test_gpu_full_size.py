@@ -113,3 +113,31 @@ def test_fused_order_free_path_equals_staged(spec, p, flags, n, chunk):
     fused, shots = eng.mc_run_host(_engine.DEC_UF, flags, p, seed, 0, n)
     staged, _ = staged_failures(eng, _engine.DEC_UF, flags, p, seed, n, chunk)
     assert shots == n and fused == staged and fused > 0
+
+
+@pytest.mark.parametrize('spec,p,n,chunk', [
+    (dict(code='Surface', d=7, noise='code capacity'), 0.10, 500_000, 1 << 18),
+    (dict(code='Surface', d=17, noise='phenomenological'), 0.02, 40_000, 1 << 15),          # one thread block per shot
+], ids=['warp', 'block'])
+def test_fused_kernel_on_a_graph_that_fails_the_parity_check(spec, p, n, chunk):
+    """luf_graph_create takes any luf_graph_desc.  With a logical mask that is not "first endpoint is a west
+    boundary node" (one bulk edge more) the parity-only peel of the fused kernels would count the wrong bit;
+    pack_graph refuses it for such a graph (parity_ok, csrc/luf_host.h) and every shot takes the full peel,
+    so the fused count still equals the staged pipeline's (whose luf_check reads the same mask) -- and differs
+    from the count under the code's own mask."""
+    import dataclasses
+    import types
+    from localuf_b200 import _engine
+    code = make_code(spec)
+    flat = code.FLAT
+    mask = np.array(flat.west_edge_mask, dtype=np.uint32, copy=True)
+    e = next(i for i in range(flat.n_edges // 2, flat.n_edges) if not (int(mask[i >> 5]) >> (i & 31)) & 1)
+    mask[e >> 5] |= np.uint32(1 << (e & 31))
+    odd = types.SimpleNamespace(FLAT=dataclasses.replace(flat, west_edge_mask=mask), NOISE=code.NOISE)
+    eng, eng0 = _engine.Engine(odd, device=0), _engine.Engine(code, device=0)
+    seed = 31
+    fused, shots = eng.mc_run_host(_engine.DEC_UF, 0, p, seed, 0, n)
+    staged, _ = staged_failures(eng, _engine.DEC_UF, 0, p, seed, n, chunk)
+    plain, _ = eng0.mc_run_host(_engine.DEC_UF, 0, p, seed, 0, n)
+    assert shots == n and fused == staged and fused > 0
+    assert fused != plain
