@@ -47,10 +47,19 @@ SEED = 20260101
 DECODER_ID = {'UF': 0, 'Macar': 1, 'Actis': 2}
 
 
+OVERRIDE = {'p': None, 'd': None}      # --p / --d: the same workload at another noise level / distance (sweeps, profiles)
+
+
 def make_code(name):
     import localuf_b200 as L
     cls, d, noise, p, desc = WORKLOADS[name][:5]
     scheme = WORKLOADS[name][5] if len(WORKLOADS[name]) > 5 else 'batch'
+    if OVERRIDE['d'] is not None:
+        desc = desc.replace(f'd={d} ', f"d={OVERRIDE['d']} ").replace(f'h={d} ', f"h={OVERRIDE['d']} ")
+        d = OVERRIDE['d']
+    if OVERRIDE['p'] is not None:
+        desc = desc.replace(f'p={p}', f"p={OVERRIDE['p']}")
+        p = OVERRIDE['p']
     return getattr(L, cls)(d, noise, scheme=scheme), p, desc
 
 
@@ -596,7 +605,10 @@ def main():
     ap.add_argument('--shots-per-step', type=int, default=0, help='units per step per GPU (0 = workload default)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--p', type=float, default=None, help='noise level override')
+    ap.add_argument('--d', type=int, default=None, help='code distance override')
     args = ap.parse_args()
+    OVERRIDE['p'], OVERRIDE['d'] = args.p, args.d
     if args.warmup < 3:
         args.warmup = 3
     # stdout carries exactly ONE line, the JSON result: whatever libraries write to file descriptor 1 meanwhile

@@ -147,11 +147,23 @@ int luf_mc_run(luf_graph *g, int decoder, int flags, const double *class_p_host,
                uint64_t seed, uint64_t shot0, int64_t nshots,
                unsigned long long *counts_dev, void *stream);
 
+/* The same with the per-shot outcome kept: logical_dev (optional) [nshots] bytes
+ * receives what Batch._sim_cycle_given_p returns for every shot
+ * (localuf/_schemes.py:143-155: get_logical_error(error ^ correction)), so that
+ * the fused kernels can be checked shot by shot against the reference on the
+ * errors luf_sample draws for the same (seed, shot0). */
+int luf_mc_run_logical(luf_graph *g, int decoder, int flags, const double *class_p_host,
+                       uint64_t seed, uint64_t shot0, int64_t nshots,
+                       unsigned long long *counts_dev, uint8_t *logical_dev, void *stream);
+
 /* Host-buffer conveniences (the call a Python user of Scheme.run / Decoder.decode
  * ends up in): stage through device scratch owned by the graph, synchronise. */
 int luf_mc_run_host(luf_graph *g, int decoder, int flags, const double *class_p_host,
                     uint64_t seed, uint64_t shot0, int64_t nshots,
                     unsigned long long counts_host[4]);
+int luf_mc_run_logical_host(luf_graph *g, int decoder, int flags, const double *class_p_host,
+                            uint64_t seed, uint64_t shot0, int64_t nshots,
+                            unsigned long long counts_host[4], uint8_t *logical_host);
 int luf_decode_batch_host(luf_graph *g, int decoder, int flags, int64_t nshots,
                           const uint32_t *syn_bits_host, uint32_t *corr_bits_host,
                           uint32_t *growth2b_host, int32_t *steps_host);

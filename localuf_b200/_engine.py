@@ -143,6 +143,8 @@ def _load():
         lib.luf_check.argtypes = [v, i64, v, v, v, v, v]
         lib.luf_mc_run.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v, v]
         lib.luf_mc_run_host.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v]
+        lib.luf_mc_run_logical.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v, v, v]
+        lib.luf_mc_run_logical_host.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v, v]
         lib.luf_decode_batch_host.argtypes = [v, C.c_int, C.c_int, i64, v, v, v, v]
         lib.luf_sample_host.argtypes = [v, v, u64, u64, i64, v, v]
         lib.luf_check_host.argtypes = [v, i64, v, v, v, v]
@@ -238,6 +240,17 @@ class Engine:
         _check(_load().luf_mc_run_host(self._h, decoder, flags, cp.ctypes.data, seed, shot0, nshots, counts))
         self.last_step_sums = (int(counts[2]), int(counts[3]))
         return int(counts[0]), int(counts[1])
+
+    def mc_logical_host(self, decoder: int, flags: int, noise_level: float, seed: int, shot0: int, nshots: int):
+        """The fused kernels with the per-shot outcome kept (``_schemes.py:143-155``): returns
+        (logical uint8 [nshots], failures, shots)."""
+        cp = self.class_p(noise_level)
+        counts = (C.c_ulonglong * 4)(0, 0, 0, 0)
+        logical = np.zeros(nshots, np.uint8)
+        _check(_load().luf_mc_run_logical_host(self._h, decoder, flags, cp.ctypes.data, seed, shot0, nshots,
+                                               counts, _ptr(logical)))
+        self.last_step_sums = (int(counts[2]), int(counts[3]))
+        return logical, int(counts[0]), int(counts[1])
 
     def decode_batch_host(self, decoder: int, flags: int, syn_bits, want_growth=False, want_steps=True,
                           corr_out=None):

@@ -59,7 +59,8 @@ __device__ __forceinline__ unsigned char* warp_slice(const Layout& l)
 // Fused K1 + K2 + K4 for the UF decoder, batch scheme (_schemes.py:116-155).
 template <int TF>
 __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
-                        unsigned long long shot0, long long nshots, unsigned long long* counts)
+                        unsigned long long shot0, long long nshots, unsigned long long* counts,
+                        uint8_t* __restrict__ logical)
 {
     const int lane = threadIdx.x & 31, nl = WARP;
     const int wpb = blockDim.x >> 5;
@@ -89,7 +90,9 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleP
             uf_validate_t<TF>(g, s, flags, lane, nl);      // TF >= 0: the flags are compile-time constants
             parity ^= uf_peel_parity(g, s, lane, nl);
         }
-        fails += LUF_XOR(parity) & 1u;
+        const uint32_t bit = LUF_XOR(parity) & 1u;
+        fails += bit;
+        if (logical && lane == 0) logical[k] = (uint8_t)bit;          // per-shot outcome (_schemes.py:143-155), optional
     }
     if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
@@ -125,7 +128,8 @@ __global__ void k_decode_uf(GraphView g, Layout l, int flags, long long nshots,
 // depend on the tile shape; every other phase runs on all threads of the block.
 template <int TF>
 __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, SampleParams sp, int flags,
-                        unsigned long long shot0, long long nshots, unsigned long long* counts)
+                        unsigned long long shot0, long long nshots, unsigned long long* counts,
+                        uint8_t* __restrict__ logical)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x, nl = blockDim.x;
@@ -159,7 +163,9 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, Sam
             uf_cta::uf_validate_t<TF>(g, s, flags, lane, nl);
             parity ^= uf_cta::uf_peel_parity(g, s, lane, nl);
         }
-        fails += (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
+        const unsigned int bit = (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
+        fails += bit;
+        if (logical && threadIdx.x == 0) logical[k] = (uint8_t)bit;
     }
     if (threadIdx.x == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
@@ -218,7 +224,8 @@ __global__ void k_decode_ca(CaView g, CaLayout l, int flags, long long nshots,
 // [2] += sum of tSV, [3] += sum of tBP.
 template <bool ACTIS>
 __global__ void k_mc_ca(GraphView gv, CaView g, CaLayout l, SampleParams sp, int flags,
-                        unsigned long long shot0, long long nshots, unsigned long long* counts)
+                        unsigned long long shot0, long long nshots, unsigned long long* counts,
+                        uint8_t* __restrict__ logical)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, nl = WARP;
@@ -236,7 +243,9 @@ __global__ void k_mc_ca(GraphView gv, CaView g, CaLayout l, SampleParams sp, int
         LUF_PHASE(ca_load(g, s, lane, nl));
         int tsv, tbp;
         parity ^= ca_decode<ACTIS>(g, s, flags, &tsv, &tbp, nullptr, lane, nl);
-        fails += LUF_XOR(parity) & 1u;
+        const uint32_t bit = LUF_XOR(parity) & 1u;
+        fails += bit;
+        if (logical && lane == 0) logical[k] = (uint8_t)bit;
         sum_sv += (unsigned long long)tsv; sum_bp += (unsigned long long)tbp;
     }
     if (lane == 0) {
@@ -272,7 +281,8 @@ __global__ void k_decode_ca_cta(CaView g, CaLayout l, int flags, long long nshot
 
 template <bool ACTIS>
 __global__ void k_mc_ca_cta(GraphView gv, CaView g, CaLayout l, SampleParams sp, int flags,
-                            unsigned long long shot0, long long nshots, unsigned long long* counts)
+                            unsigned long long shot0, long long nshots, unsigned long long* counts,
+                            uint8_t* __restrict__ logical)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = (int)threadIdx.x, nl = (int)blockDim.x;
@@ -292,7 +302,9 @@ __global__ void k_mc_ca_cta(GraphView gv, CaView g, CaLayout l, SampleParams sp,
         __syncthreads();
         int tsv, tbp;
         parity ^= ca_cta::ca_decode<ACTIS>(g, s, flags, &tsv, &tbp, nullptr, lane, nl);
-        fails += (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
+        const unsigned int bit = (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
+        fails += bit;
+        if (logical && lane == 0) logical[k] = (uint8_t)bit;
         sum_sv += (unsigned long long)tsv; sum_bp += (unsigned long long)tbp;
     }
     if (lane == 0) {
@@ -1390,6 +1402,12 @@ int luf_check(luf_graph* g, int64_t nshots, const uint32_t* err_bits_dev, const 
 int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host, uint64_t seed,
                uint64_t shot0, int64_t nshots, unsigned long long* counts_dev, void* stream)
 {
+    return luf_mc_run_logical(g, decoder, flags, class_p_host, seed, shot0, nshots, counts_dev, nullptr, stream);
+}
+
+int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class_p_host, uint64_t seed,
+                       uint64_t shot0, int64_t nshots, unsigned long long* counts_dev, uint8_t* logical_dev, void* stream)
+{
     if (!g || !class_p_host || !counts_dev || nshots < 0) return fail(LUF_ERR_INVALID, "luf_mc_run: bad argument");
     if (int rc = check_decoder(g, decoder, flags)) return rc;
     if (nshots == 0) return 0;
@@ -1400,28 +1418,28 @@ int luf_mc_run(luf_graph* g, int decoder, int flags, const double* class_p_host,
         if (use_ca_cta(g, false)) {
             if (int rc = plan_ca_cta_launch(g, k_mc_ca_cta<false>, g->lay_macar_cta.bytes, nshots, &c, g->ca_view.N / 16)) return rc;
             k_mc_ca_cta<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_macar_cta, sp, flags,
-                                                                                   shot0, nshots, counts_dev);
+                                                                                   shot0, nshots, counts_dev, logical_dev);
         } else {
             if (int rc = plan_launch(g, k_mc_ca<false>, g->lay_macar.bytes, nshots, &c)) return rc;
             k_mc_ca<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_macar, sp, flags,
-                                                                               shot0, nshots, counts_dev);
+                                                                               shot0, nshots, counts_dev, logical_dev);
         }
     } else if (decoder == LUF_DEC_ACTIS) {
         if (use_ca_cta(g, true)) {
             if (int rc = plan_ca_cta_launch(g, k_mc_ca_cta<true>, g->lay_actis_cta.bytes, nshots, &c, g->ca_view.N / 12, false)) return rc;
             k_mc_ca_cta<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_actis_cta, sp, flags,
-                                                                                  shot0, nshots, counts_dev);
+                                                                                  shot0, nshots, counts_dev, logical_dev);
         } else {
             if (int rc = plan_launch(g, k_mc_ca<true>, g->lay_actis.bytes, nshots, &c)) return rc;
             k_mc_ca<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_actis, sp, flags,
-                                                                              shot0, nshots, counts_dev);
+                                                                              shot0, nshots, counts_dev, logical_dev);
         }
     } else {
         // the decoder flags are compile-time constants of the fused kernel
 #define LUF_MC_UF(TF) { if (int rc = plan_launch(g, k_mc_uf<TF>, g->lay_fused.bytes, nshots, &c, 14)) return rc; \
-        k_mc_uf<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, shot0, nshots, counts_dev); }
+        k_mc_uf<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, shot0, nshots, counts_dev, logical_dev); }
 #define LUF_MC_UF_CTA(TF) { if (int rc = plan_cta_launch(g, k_mc_uf_cta<TF>, g->lay_fused_cta.bytes, nshots, &c)) return rc; \
-        k_mc_uf_cta<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused_cta, sp, flags, shot0, nshots, counts_dev); }
+        k_mc_uf_cta<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused_cta, sp, flags, shot0, nshots, counts_dev, logical_dev); }
         const bool cta = use_cta_tiles(g, g->lay_fused.bytes, g->lay_fused_cta.bytes);
         // the common flag sets are compile-time constants of the fused kernel; the rest run the generic instance
         switch (flags <= 7 ? flags : -1) {
@@ -1583,14 +1601,27 @@ int luf_forward_mc_host(luf_graph* g, int decoder, int flags, const double* clas
 int luf_mc_run_host(luf_graph* g, int decoder, int flags, const double* class_p_host, uint64_t seed,
                     uint64_t shot0, int64_t nshots, unsigned long long counts_host[4])
 {
-    if (!g || !counts_host) return fail(LUF_ERR_INVALID, "luf_mc_run_host: bad argument");
+    return luf_mc_run_logical_host(g, decoder, flags, class_p_host, seed, shot0, nshots, counts_host, nullptr);
+}
+
+int luf_mc_run_logical_host(luf_graph* g, int decoder, int flags, const double* class_p_host, uint64_t seed,
+                            uint64_t shot0, int64_t nshots, unsigned long long counts_host[4], uint8_t* logical_host)
+{
+    if (!g || !counts_host || nshots < 0) return fail(LUF_ERR_INVALID, "luf_mc_run_host: bad argument");
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
-    void* d = nullptr;
+    void *d = nullptr, *lg = nullptr;
     if (int rc = scratch_get(g, 0, 32, &d)) return rc;
+    if (logical_host && nshots > 0)
+        if (int rc = scratch_get(g, 3, (size_t)nshots, &lg)) return rc;
     CUDA_TRY(cudaMemsetAsync(d, 0, 32, 0));
-    if (int rc = luf_mc_run(g, decoder, flags, class_p_host, seed, shot0, nshots, (unsigned long long*)d, 0)) return rc;
+    if (int rc = luf_mc_run_logical(g, decoder, flags, class_p_host, seed, shot0, nshots, (unsigned long long*)d,
+                                    (uint8_t*)lg, 0)) {
+        cudaStreamSynchronize(0);
+        return rc;
+    }
     unsigned long long tmp[4] = {0, 0, 0, 0};
+    if (lg) CUDA_TRY(cudaMemcpyAsync(logical_host, lg, (size_t)nshots, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaMemcpy(tmp, d, 32, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 4; ++i) counts_host[i] += tmp[i];
     return 0;

@@ -17,26 +17,51 @@ import tempfile
 from collections import defaultdict
 
 
-def line_table(so, kernel):
+def section_tables(so):
+    """{section name: [(file, line) per SASS instruction]} for every .text section of the library's cubin."""
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(so)], cwd=tmp, check=True, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
     txt = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
-    table, cur, inside = [], None, False
+    tables, cur, name = {}, None, None
     for ln in txt.splitlines():
         m = re.match(r'\s*//-+ \.text\.(\S+)', ln)
         if m:
-            inside = kernel in m.group(1)
+            name = m.group(1)
+            tables[name] = []
+            cur = None
             continue
-        if not inside:
+        if name is None:
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
         if re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+\S', ln):
-            table.append(cur)
-    return table
+            tables[name].append(cur)
+    return tables
+
+
+def line_table(so, kernel, n_instructions=None):
+    """The line table of ONE kernel instance: the .text section whose name contains `kernel` (a mangled
+    instance name such as k_mc_ufILi0E picks a template instance) and, when `n_instructions` is given (the
+    number of SASS rows ncu profiled), whose instruction count equals it -- several template instances
+    share a name prefix, and joining ncu's rows with another instance's table mislabels every row."""
+    cands = {n: t for n, t in section_tables(so).items() if kernel in n}
+    if n_instructions is not None:
+        exact = {n: t for n, t in cands.items() if len(t) == n_instructions}
+        if exact:
+            cands = exact
+        elif cands:
+            print(f'warning: no instance of {kernel} has {n_instructions} instructions '
+                  f'({ {n: len(t) for n, t in cands.items()} }); the library differs from the profiled one', file=sys.stderr)
+    if not cands:
+        raise SystemExit(f'no .text section matches {kernel}')
+    if len(cands) > 1:
+        print(f'warning: {len(cands)} sections match {kernel}: {sorted(cands)}; taking the shortest name', file=sys.stderr)
+    name = min(cands, key=len)
+    print(f'[ncu_lines] section .text.{name}: {len(cands[name])} instructions', file=sys.stderr)
+    return cands[name]
 
 
 def main():
@@ -47,7 +72,7 @@ def main():
     hdr = rows[hdr_i]
     col = {h: i for i, h in enumerate(hdr)}
     body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
-    table = line_table(so, kernel)
+    table = line_table(so, kernel, len(body))
     if len(table) != len(body):
         print(f'warning: {len(table)} disassembled vs {len(body)} profiled instructions', file=sys.stderr)
     agg = defaultdict(lambda: [0, 0, 0])

@@ -64,7 +64,7 @@ def main():
     hi = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
     h = rows[hi]; col = {x: i for i, x in enumerate(h)}
     body = [r for r in rows[hi + 1:] if len(r) == len(h)]
-    table = ncu_lines.line_table(so, mangled)
+    table = ncu_lines.line_table(so, mangled, len(body))      # the instance whose SASS ncu profiled
     agg, tot = {}, [0, 0, 0]
     for k, r in enumerate(body):
         key = table[k] if k < len(table) and table[k] else ('?', 0)
