@@ -276,8 +276,9 @@ struct SampleTab {
 // edges whose bit is set in `skip_mask` (optional) are never flipped
 // (exclude_future_boundary, _base_classes.py:418-424).  Returns this lane's
 // parity of flipped west-boundary edges.
-LUF_DEV uint32_t ph_sample_tab(const GraphView& g, const SampleTab& t, const Shot& s, const SampleParams& sp,
-                               uint64_t shot, uint32_t cycle, const uint32_t* skip_mask, int lane, int nl)
+template <class Flip>
+LUF_DEV uint32_t ph_sample_core(const SampleTab& t, const SampleParams& sp, uint64_t shot, uint32_t cycle,
+                                const uint32_t* skip_mask, int lane, int nl, Flip flip)
 {
     const uint32_t a = (uint32_t)(((uint64_t)t.F * (uint32_t)lane) / (uint32_t)nl);
     const uint32_t b = (uint32_t)(((uint64_t)t.F * (uint32_t)(lane + 1)) / (uint32_t)nl);
@@ -306,11 +307,19 @@ LUF_DEV uint32_t ph_sample_tab(const GraphView& g, const SampleTab& t, const Sho
                 pos += gap;
             }
             const uint32_t e = t.perm ? (uint32_t)LUF_LDG(&t.perm[pos]) : pos;   // no table when the order is the identity
-            if (!skip_mask || !((LUF_LDG(&skip_mask[e >> 5]) >> (e & 31u)) & 1u)) parity ^= flip_edge(g, s, e);
+            if (!skip_mask || !((LUF_LDG(&skip_mask[e >> 5]) >> (e & 31u)) & 1u)) parity ^= flip(e);
             if (++pos >= hi) break;
         }
     }
     return parity;
+}
+
+// `flip(e)` records a flipped edge and returns whether it counts for the logical parity: flip_edge on the
+// full tables here, fast::f_flip on the compact ones (luf_uf_fast.cuh) -- one sampler, one random stream.
+LUF_DEV uint32_t ph_sample_tab(const GraphView& g, const SampleTab& t, const Shot& s, const SampleParams& sp,
+                               uint64_t shot, uint32_t cycle, const uint32_t* skip_mask, int lane, int nl)
+{
+    return ph_sample_core(t, sp, shot, cycle, skip_mask, lane, nl, [&](uint32_t e) { return flip_edge(g, s, e); });
 }
 
 LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams& sp,

@@ -12,6 +12,7 @@
 
 #include "../../include/luf_b200.h"
 #include "luf_core.cuh"
+#include "luf_uf_fast.cuh"
 #include "luf_ca.cuh"
 #include "luf_sf.cuh"
 #include "luf_fw.cuh"
@@ -115,6 +116,76 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr, ui
     l.zero_bytes = off - l.zero_off;                  // ----
     l.claim = take(4u * (claim_slots > WN ? claim_slots : WN));   // visited bitmap of the peel
     l.list = take(4u * list_cap); l.list2 = take(4u * list2_cap); l.cnt = take(32);
+    l.bytes = off;
+    return l;
+}
+
+// ------------------------------------------------- compact fast path (luf_uf_fast.cuh)
+struct PackedFast {
+    bool ok = false;              // the graph allows the compact fast path
+    int D = 0, DEG = 0;
+    std::vector<uint32_t> fadj, einfo;
+};
+
+// The compact tables index detectors only.  Needs what the parity-only peel needs (parity_ok) and, on top, that
+// every boundary node has exactly one edge and lies on the west (-1) side or on one other side, and every
+// edge at least one detector end.  Every graph of codes.Surface / codes.Repetition has all of it.
+inline void pack_fast(const luf_graph_desc& d, const PackedGraph& g, PackedFast& out)
+{
+    const int N = g.N, B = g.B, E = g.E, D = N - B;
+    out.ok = false;
+    if (!g.parity_ok || D < 1 || D >= (int)fast::OTHER_EAST) return;
+    int east_long = 0;
+    bool have_east = false;
+    for (int v = 0; v < B; ++v) {
+        if (d.inc_off[v + 1] - d.inc_off[v] != 1) return;
+        if (d.node_long[v] == -1) continue;
+        if (have_east && d.node_long[v] != east_long) return;
+        have_east = true; east_long = d.node_long[v];
+    }
+    auto end_code = [&](int v) -> uint32_t { return v >= B ? (uint32_t)(v - B) : (d.node_long[v] == -1 ? fast::END_WEST : fast::END_EAST); };
+    out.einfo.assign(E, 0);
+    for (int e = 0; e < E; ++e) {
+        if (d.edge_u[e] < B && d.edge_v[e] < B) return;
+        out.einfo[e] = end_code(d.edge_u[e]) | (end_code(d.edge_v[e]) << 16);
+    }
+    int deg = 2;
+    for (int v = B; v < N; ++v) deg = std::max(deg, d.inc_off[v + 1] - d.inc_off[v]);
+    out.D = D; out.DEG = (deg + 1) & ~1;
+    out.fadj.assign((size_t)D * out.DEG, ADJ_PAD);
+    for (int v = B; v < N; ++v)
+        for (int k = d.inc_off[v]; k < d.inc_off[v + 1]; ++k) {
+            const int e = d.inc_edge[k], o = d.inc_other[k];
+            const uint32_t oc = o >= B ? (uint32_t)(o - B) : (d.node_long[o] == -1 ? fast::OTHER_WEST : fast::OTHER_EAST);
+            out.fadj[(size_t)(v - B) * out.DEG + (k - d.inc_off[v])] = (uint32_t)e | (oc << 16) | (d.edge_u[e] == v ? 0x80000000u : 0u);
+        }
+    out.ok = true;
+}
+
+// List capacities follow the expected number of faults per shot `mu` (the launch knows the noise level): the
+// touched nodes (two defects per fault and their neighbours in later rounds), the active nodes of a round and
+// the newly FULL edges of a round.  A shot that overflows one of them is HARD (the canonical kernel decodes
+// it), so the capacities trade shared memory for the share of such shots.
+inline fast::FLayout make_fast_layout(int D, int E, int DEG, double mu)
+{
+    fast::FLayout l;
+    auto cap = [&](double want, int most) { uint32_t c = (uint32_t)std::min<double>(want, most); return (c + 7u) & ~7u; };
+    // fitted to the 99.9th percentiles of the host emulation (Surface d = 9 .. 17, p from 0.005 to threshold):
+    // touched nodes <= 5.6 mu, newly FULL edges of a round <= 4.8 mu, active nodes of a round <= 1.9 mu there
+    const double sq = std::sqrt(mu > 0.0 ? mu : 0.0);
+    // (degree 6; the diagonal edges of circuit-level graphs, degree 12, fill twice as many edges per round)
+    const double f = DEG > 6 ? DEG / 6.0 : 1.0;
+    l.tcap = cap((5.2 * mu + 10.0 * sq + 32.0) * (1.0 + f) / 2.0, D); l.acap = cap(mu + 3.0 * sq + 16.0, D);
+    l.mcap = cap((4.0 * mu + 8.0 * sq + 24.0) * f, E);
+    uint32_t off = 0;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
+    const uint32_t WD = (uint32_t)words32(D);
+    l.P = take(2u * (uint32_t)D);
+    l.fill_words = (off - l.P) / 4u;
+    l.zero_off = off;
+    l.growth = take(4u * (uint32_t)((E + 15) / 16)); l.defect = take(4u * WD); l.touched = take(4u * WD);
+    l.zero_bytes = off - l.zero_off;
+    l.tlist = take(2u * l.tcap); l.alist = take(4u * l.acap); l.mlist = take(4u * l.mcap); l.cnt = take(32);
     l.bytes = off;
     return l;
 }

@@ -57,22 +57,28 @@ __device__ __forceinline__ unsigned char* warp_slice(const Layout& l)
 #define LUF_FAST_TF(TF) ((TF) >= 0 && !((TF) & FLAG_DYNAMIC) && (((TF) & (FLAG_BUCKET | FLAG_NODE)) != FLAG_BUCKET))
 
 // Fused K1 + K2 + K4 for the UF decoder, batch scheme (_schemes.py:116-155).
-template <int TF>
+// QUEUE: the second launch behind k_mc_uf_fast -- the shots listed in queue[0 .. *qcount) (indices relative to
+// shot0), all in canonical order with the full peel where a cluster spans both sides; the fast launch counted
+// the shots already.
+template <int TF, bool QUEUE>
 __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleParams sp, int flags,
                         unsigned long long shot0, long long nshots, unsigned long long* counts,
-                        uint8_t* __restrict__ logical)
+                        uint8_t* __restrict__ logical, const uint32_t* __restrict__ queue,
+                        const uint32_t* __restrict__ qcount)
 {
     const int lane = threadIdx.x & 31, nl = WARP;
     const int wpb = blockDim.x >> 5;
     const Shot s = bind(l, warp_slice(l));
     const long long stride = (long long)gridDim.x * wpb;
     unsigned int fails = 0;
-    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+    if (QUEUE) nshots = (long long)*qcount;
+    for (long long i = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); i < nshots; i += stride) {
+        const long long k = QUEUE ? (long long)queue[i] : i;
         uint32_t parity = 0;
         LUF_PHASE(ph_reset(g, l, s, lane, nl));
         LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
         LUF_PHASE(ph_load(g, s, lane, nl));
-        if (LUF_FAST_TF(TF) && g.parity_ok) {                             // static UF / NodeUF / NodeBUF: merges in any order, no peel ...
+        if (!QUEUE && LUF_FAST_TF(TF) && g.parity_ok) {                   // static UF / NodeUF / NodeBUF: merges in any order, no peel ...
             uf_validate_fast<(LUF_FAST_TF(TF) ? TF : 0)>(g, s, lane, nl);
             if (__any_sync(0xffffffffu, s.cnt[4] != 0u)) { // ... unless a cluster spans both sides: canonical order
                 parity = 0;
@@ -93,6 +99,51 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleP
         const uint32_t bit = LUF_XOR(parity) & 1u;
         fails += bit;
         if (logical && lane == 0) logical[k] = (uint8_t)bit;          // per-shot outcome (_schemes.py:143-155), optional
+    }
+    if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
+    if (!QUEUE && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+}
+
+// The compact fast path (luf_uf_fast.cuh): static UF, default or west inclination.  A block holds the
+// adjacency table (ADJ_SHARED) and `blockDim.x / TW` shots, one per tile of TW threads: a part of a warp
+// (several shots advance through the same instructions), a warp, or TW / 32 warps synchronised by a named
+// barrier.  A shot the path cannot finish (HARD) is appended to `queue` for the canonical launch.
+template <int TW>
+struct TileSync {
+    uint32_t x;          // lane mask of the tile (TW <= 32) or its named barrier (TW > 32; 0 = the whole block)
+    __device__ __forceinline__ void operator()() const
+    {
+        if (TW <= 32) __syncwarp(x);
+        else if (x == 0u) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(x), "n"(TW) : "memory");
+    }
+};
+
+template <int TW, bool ADJ_SHARED>
+__global__ void __launch_bounds__(1024, 1) k_mc_uf_fast(fast::FView g, fast::FLayout l, uint32_t adj_bytes, SampleParams sp,
+                        unsigned long long shot0, long long nshots, unsigned long long* counts,
+                        uint8_t* __restrict__ logical, uint32_t* __restrict__ queue, uint32_t* __restrict__ qcount)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    if (ADJ_SHARED) {
+        const uint4* src = (const uint4*)g.fadj;
+        uint4* dst = (uint4*)smem;
+        for (uint32_t i = threadIdx.x; i < adj_bytes / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+        g.fadj = (const uint32_t*)smem;
+    }
+    const int tile = (int)threadIdx.x / TW, lane = (int)threadIdx.x % TW, tpb = (int)blockDim.x / TW;
+    const fast::FShot s = fast::fbind(l, smem + adj_bytes + (size_t)tile * l.bytes);
+    TileSync<TW> sync;
+    if (TW <= 32) sync.x = TW == 32 ? 0xffffffffu : ((1u << (TW & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TW - 1));
+    else sync.x = tpb == 1 ? 0u : (uint32_t)(1 + tile);
+    unsigned int fails = 0;
+    for (long long k = (long long)blockIdx.x * tpb + tile; k < nshots; k += (long long)gridDim.x * tpb) {
+        const uint32_t r = fast::fast_shot<ADJ_SHARED>(g, l, s, sp, shot0 + (unsigned long long)k, lane, TW, sync);
+        if (lane == 0) {
+            if (r == fast::HARD) queue[atomicAdd(qcount, 1u)] = (uint32_t)k;
+            else { fails += r; if (logical) logical[k] = (uint8_t)r; }
+        }
     }
     if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
@@ -126,16 +177,19 @@ __global__ void k_decode_uf(GraphView g, Layout l, int flags, long long nshots,
 // whose shot state leaves only a few warps per SM (Surface d >= 13 with
 // measurement rounds).  The first warp samples, so that a shot's noise does not
 // depend on the tile shape; every other phase runs on all threads of the block.
-template <int TF>
+template <int TF, bool QUEUE>
 __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, SampleParams sp, int flags,
                         unsigned long long shot0, long long nshots, unsigned long long* counts,
-                        uint8_t* __restrict__ logical)
+                        uint8_t* __restrict__ logical, const uint32_t* __restrict__ queue,
+                        const uint32_t* __restrict__ qcount)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x, nl = blockDim.x;
     const Shot s = bind(l, smem);
     unsigned int fails = 0;
-    for (long long k = blockIdx.x; k < nshots; k += gridDim.x) {
+    if (QUEUE) nshots = (long long)*qcount;
+    for (long long i = blockIdx.x; i < nshots; i += gridDim.x) {
+        const long long k = QUEUE ? (long long)queue[i] : i;
         uint32_t parity = 0;
         uf_cta::ph_reset(g, l, s, lane, nl);
         __syncthreads();
@@ -143,7 +197,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, Sam
         __syncthreads();
         uf_cta::ph_load(g, s, lane, nl);
         __syncthreads();
-        if (LUF_FAST_TF(TF) && g.parity_ok) {
+        if (!QUEUE && LUF_FAST_TF(TF) && g.parity_ok) {
             uf_cta::uf_validate_fast<(LUF_FAST_TF(TF) ? TF : 0)>(g, s, lane, nl);
             if (__syncthreads_or(s.cnt[4] != 0u)) {
                 parity = 0;
@@ -168,7 +222,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, Sam
         if (logical && threadIdx.x == 0) logical[k] = (uint8_t)bit;
     }
     if (threadIdx.x == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+    if (!QUEUE && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
 }
 
 __global__ void __launch_bounds__(448, 2) k_decode_uf_cta(GraphView g, Layout l, int flags, long long nshots,
@@ -614,7 +668,13 @@ struct luf_graph {
     cudaStream_t pipe[3] = {0, 0, 0};     // copy / compute pipeline of the *_host batch entry points
     std::mutex mu;
     std::map<std::pair<const void*, uint32_t>, std::pair<int, int>> plans;   // (kernel, slice bytes) -> (warps per block, blocks per SM)
+    // compact fast path of the fused UF kernel (luf_uf_fast.cuh)
+    PackedFast fast_host;
+    fast::FView fview{};
+    std::map<void*, uint32_t*> queues;       // per stream: uint32[FAST_CHUNK] shot indices + the fill counter behind them
 };
+
+static const long long FAST_CHUNK = 1ll << 22;       // shots per fast launch (the queue of HARD shots holds as many)
 
 template <class T>
 static int upload(luf_graph* g, const std::vector<T>& v, const T** out)
@@ -795,6 +855,106 @@ static int plan_ca_cta_launch(luf_graph* g, K kernel, uint32_t bytes, long long 
     if (blocks < 1) blocks = 1;
     cfg->grid = (int)blocks; cfg->block = threads; cfg->smem = bytes;
     return 0;
+}
+
+// ------------------------------------------------------- compact fast path: launch plan
+struct FastPlan { int tw, spb, bps; bool adj_shared; uint32_t adj_bytes; };
+
+// Tile width, shots per block, blocks per SM and whether the adjacency table is staged in shared memory.
+// The most resident shots win; a tile is as narrow as still leaves about 24 warps per SM (a narrow tile wastes
+// fewer lanes on the short lists of a shot, but the SM needs the warps to hide shared-memory latency).
+// LUF_FAST_TW / LUF_FAST_ADJ / LUF_FAST_SPB / LUF_FAST_BPS override (measurements).  false = does not fit.
+static bool fast_plan(const luf_graph* g, const fast::FLayout& l, FastPlan* out)
+{
+    static const int env_tw = getenv("LUF_FAST_TW") ? atoi(getenv("LUF_FAST_TW")) : 0;
+    static const int env_adj = getenv("LUF_FAST_ADJ") ? atoi(getenv("LUF_FAST_ADJ")) : -1;
+    static const int env_spb = getenv("LUF_FAST_SPB") ? atoi(getenv("LUF_FAST_SPB")) : 0;
+    static const int env_bps = getenv("LUF_FAST_BPS") ? atoi(getenv("LUF_FAST_BPS")) : 0;
+    static const int env_warps = getenv("LUF_FAST_WARPS") ? atoi(getenv("LUF_FAST_WARPS")) : 24;
+    const uint32_t adj_all = align16((uint32_t)g->fast_host.fadj.size() * 4u);
+    const int sm_smem = 228 * 1024;
+    FastPlan best{};
+    int best_shots = 0;
+    for (int adj = 1; adj >= 0; --adj) {
+        if (env_adj >= 0 && adj != env_adj) continue;
+        const uint32_t adj_bytes = adj ? adj_all : 0u;
+        for (int bps = 1; bps <= 2; ++bps) {
+            if (env_bps > 0 && bps != env_bps) continue;
+            long long budget = sm_smem / bps - 1024;
+            if (budget > g->max_smem) budget = g->max_smem;
+            if (budget < (long long)adj_bytes + (long long)l.bytes) continue;
+            const int fit = (int)((budget - adj_bytes) / l.bytes);
+            // the narrowest tile that keeps the warp count: fit shots * tw / 32 ~ env_warps / bps
+            int tw = 8;
+            while (tw < 256 && (long long)fit * bps * tw < 32ll * env_warps) tw <<= 1;
+            if (env_tw > 0) tw = env_tw;
+            int spb = fit;
+            if (spb > 1024 / tw) spb = 1024 / tw;
+            if (tw > 32 && spb > 15) spb = 15;                 // named barriers 1 .. 15
+            if (env_spb > 0 && env_spb < spb) spb = env_spb;
+            if (spb < 1) continue;
+            // adjacency in shared memory is worth a fifth of the resident shots
+            const int score = spb * bps * (adj ? 5 : 4);
+            if (score > best_shots) { best_shots = score; best = FastPlan{tw, spb, bps, adj != 0, adj_bytes}; }
+        }
+    }
+    if (!best_shots) return false;
+    *out = best;
+    return true;
+}
+
+static int fast_queue(luf_graph* g, void* stream, uint32_t** out)
+{
+    std::lock_guard<std::mutex> lock(g->mu);
+    auto it = g->queues.find(stream);
+    if (it == g->queues.end()) {
+        void* p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, (size_t)(FAST_CHUNK + 4) * 4));
+        it = g->queues.emplace(stream, (uint32_t*)p).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+template <int TW, bool ADJ>
+static int fast_launch_t(luf_graph* g, const FastPlan& plan, const fast::FLayout& fl, const SampleParams& sp,
+                         unsigned long long shot0, long long nshots, unsigned long long* counts, uint8_t* logical,
+                         uint32_t* queue, uint32_t* qcount, cudaStream_t stream)
+{
+    static std::mutex once_mu;
+    static bool once[64] = {};
+    {   // the opt-in shared-memory limit is process-wide state of the kernel: raised once, to the device maximum
+        std::lock_guard<std::mutex> lock(once_mu);
+        if (!once[g->device & 63]) {
+            CUDA_TRY(cudaFuncSetAttribute(k_mc_uf_fast<TW, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_mc_uf_fast<TW, ADJ>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            once[g->device & 63] = true;
+        }
+    }
+    const size_t smem = (size_t)plan.adj_bytes + (size_t)plan.spb * fl.bytes;
+    long long blocks = (long long)g->sm_count * plan.bps;
+    const long long need = (nshots + plan.spb - 1) / plan.spb;
+    if (blocks > need) blocks = need;
+    if (getenv("LUF_DEBUG_PLAN"))
+        fprintf(stderr, "[luf] fast plan: %u B per shot (lists %u / %u / %u), tile %d, %d shots per block, %d blocks per SM, adjacency %s (%u B), %zu B of shared memory per block\n",
+                fl.bytes, fl.tcap, fl.acap, fl.mcap, plan.tw, plan.spb, plan.bps, plan.adj_shared ? "shared" : "global", plan.adj_bytes, smem);
+    k_mc_uf_fast<TW, ADJ><<<(int)blocks, plan.spb * TW, smem, stream>>>(g->fview, fl, plan.adj_bytes, sp, shot0, nshots, counts,
+                                                                      logical, queue, qcount);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int fast_launch(luf_graph* g, const FastPlan& plan, const fast::FLayout& fl, const SampleParams& sp,
+                       unsigned long long shot0, long long nshots, unsigned long long* counts, uint8_t* logical,
+                       uint32_t* queue, uint32_t* qcount, cudaStream_t stream)
+{
+#define LUF_FAST_TW(T) case T: return plan.adj_shared ? fast_launch_t<T, true>(g, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream) \
+                                                      : fast_launch_t<T, false>(g, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream);
+    switch (plan.tw) {
+        LUF_FAST_TW(8) LUF_FAST_TW(16) LUF_FAST_TW(32) LUF_FAST_TW(64) LUF_FAST_TW(128) LUF_FAST_TW(256)
+        default: return fail(LUF_ERR_INVALID, "fast path: tile width must be 8, 16, 32, 64, 128 or 256");
+    }
+#undef LUF_FAST_TW
 }
 
 static int check_device(void)
@@ -1202,6 +1362,16 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
         // keep every pointer inside the slice (unused arrays alias the start)
         g->lay_sample = l;
     }
+    pack_fast(*desc, p, g->fast_host);
+    if (g->fast_host.ok) {
+        fast::FView& f = g->fview;
+        f.D = g->fast_host.D; f.E = p.E; f.WD = words32(f.D); f.DEG = g->fast_host.DEG;
+        f.F = p.F; f.n_classes = p.n_classes; f.fresh_perm = v.fresh_perm; f.class_end = v.class_end;
+        if ((rc = upload(g, g->fast_host.fadj, &f.fadj)) || (rc = upload(g, g->fast_host.einfo, &f.einfo))) {
+            luf_graph_destroy(g);
+            return rc;
+        }
+    }
     g->ca_why = pack_ca(*desc, g->ca_host);
     if (g->ca_why.empty()) {
         CaView& c = g->ca_view;
@@ -1232,6 +1402,7 @@ int luf_graph_destroy(luf_graph* g)
     cudaSetDevice(g->device);
     for (void* p : g->allocs) cudaFree(p);
     for (void* p : g->scratch) if (p) cudaFree(p);
+    for (auto& q : g->queues) cudaFree(q.second);
     for (cudaStream_t st : g->pipe) if (st) cudaStreamDestroy(st);
     delete g;
     return 0;
@@ -1435,26 +1606,61 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                                                                               shot0, nshots, counts_dev, logical_dev);
         }
     } else {
-        // the decoder flags are compile-time constants of the fused kernel
-#define LUF_MC_UF(TF) { if (int rc = plan_launch(g, k_mc_uf<TF>, g->lay_fused.bytes, nshots, &c, 14)) return rc; \
-        k_mc_uf<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, shot0, nshots, counts_dev, logical_dev); }
-#define LUF_MC_UF_CTA(TF) { if (int rc = plan_cta_launch(g, k_mc_uf_cta<TF>, g->lay_fused_cta.bytes, nshots, &c)) return rc; \
-        k_mc_uf_cta<TF><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused_cta, sp, flags, shot0, nshots, counts_dev, logical_dev); }
         const bool cta = use_cta_tiles(g, g->lay_fused.bytes, g->lay_fused_cta.bytes);
+        // the decoder flags are compile-time constants of the fused kernel
+#define LUF_MC_UF(TF, Q, SHOT0, NSHOTS, LOGICAL, QUEUE, QCOUNT) { \
+        if (int rc = plan_launch(g, k_mc_uf<TF, Q>, g->lay_fused.bytes, Q ? FAST_CHUNK : (long long)(NSHOTS), &c, 14)) return rc; \
+        k_mc_uf<TF, Q><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused, sp, flags, SHOT0, NSHOTS, counts_dev, LOGICAL, QUEUE, QCOUNT); }
+#define LUF_MC_UF_CTA(TF, Q, SHOT0, NSHOTS, LOGICAL, QUEUE, QCOUNT) { \
+        if (int rc = plan_cta_launch(g, k_mc_uf_cta<TF, Q>, g->lay_fused_cta.bytes, Q ? FAST_CHUNK : (long long)(NSHOTS), &c)) return rc; \
+        k_mc_uf_cta<TF, Q><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_fused_cta, sp, flags, SHOT0, NSHOTS, counts_dev, LOGICAL, QUEUE, QCOUNT); }
+#define LUF_MC_UF_ANY(TF, Q, SHOT0, NSHOTS, LOGICAL, QUEUE, QCOUNT) { \
+        if (cta) LUF_MC_UF_CTA(TF, Q, SHOT0, NSHOTS, LOGICAL, QUEUE, QCOUNT) else LUF_MC_UF(TF, Q, SHOT0, NSHOTS, LOGICAL, QUEUE, QCOUNT) }
+        // static UF, default / west inclination: the compact fast launch, then the canonical launch over the
+        // shots it queued (LUF_FAST=0: the one-launch kernels of round 1)
+        static const bool env_fast = !(getenv("LUF_FAST") && atoi(getenv("LUF_FAST")) == 0);
+        if (env_fast && g->fast_host.ok && (flags & ~LUF_UF_WEST) == 0) {
+            double mu = 0.0;
+            for (int cl = 0, lo = 0; cl < g->view.n_classes; ++cl) {
+                const int hi = (int)g->host.class_end[cl];
+                mu += std::min(1.0, std::max(0.0, class_p_host[cl])) * (hi - lo);
+                lo = hi;
+            }
+            const fast::FLayout fl = make_fast_layout(g->fview.D, g->fview.E, g->fview.DEG, mu);
+            FastPlan plan;
+            if (fast_plan(g, fl, &plan)) {
+                uint32_t* queue = nullptr;
+                if (int rc = fast_queue(g, stream, &queue)) return rc;
+                uint32_t* qcount = queue + FAST_CHUNK;
+                for (int64_t done = 0; done < nshots; done += FAST_CHUNK) {
+                    const long long m = std::min<long long>(FAST_CHUNK, nshots - done);
+                    const unsigned long long first = shot0 + (unsigned long long)done;
+                    uint8_t* lg = logical_dev ? logical_dev + done : nullptr;
+                    CUDA_TRY(cudaMemsetAsync(qcount, 0, 4, (cudaStream_t)stream));
+                    if (int rc = fast_launch(g, plan, fl, sp, first, m, counts_dev, lg, queue, qcount, (cudaStream_t)stream)) return rc;
+                    if (flags & LUF_UF_WEST) LUF_MC_UF_ANY(2, true, first, m, lg, queue, qcount)
+                    else LUF_MC_UF_ANY(0, true, first, m, lg, queue, qcount)
+                    CUDA_TRY(cudaGetLastError());
+                    g->launches += 2;
+                }
+                return 0;
+            }
+        }
         // the common flag sets are compile-time constants of the fused kernel; the rest run the generic instance
         switch (flags <= 7 ? flags : -1) {
-            case 0: if (cta) LUF_MC_UF_CTA(0) else LUF_MC_UF(0) break;
-            case 1: if (cta) LUF_MC_UF_CTA(1) else LUF_MC_UF(1) break;
-            case 2: if (cta) LUF_MC_UF_CTA(2) else LUF_MC_UF(2) break;
-            case 3: if (cta) LUF_MC_UF_CTA(3) else LUF_MC_UF(3) break;
-            case 4: if (cta) LUF_MC_UF_CTA(4) else LUF_MC_UF(4) break;
-            case 5: if (cta) LUF_MC_UF_CTA(5) else LUF_MC_UF(5) break;
-            case 6: if (cta) LUF_MC_UF_CTA(6) else LUF_MC_UF(6) break;
-            case 7: if (cta) LUF_MC_UF_CTA(7) else LUF_MC_UF(7) break;
-            default: if (cta) LUF_MC_UF_CTA(-1) else LUF_MC_UF(-1) break;
+            case 0: LUF_MC_UF_ANY(0, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
+            case 1: LUF_MC_UF_ANY(1, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
+            case 2: LUF_MC_UF_ANY(2, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
+            case 3: LUF_MC_UF_ANY(3, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
+            case 4: LUF_MC_UF_ANY(4, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
+            case 5: LUF_MC_UF_ANY(5, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
+            case 6: LUF_MC_UF_ANY(6, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
+            case 7: LUF_MC_UF_ANY(7, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
+            default: LUF_MC_UF_ANY(-1, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
         }
 #undef LUF_MC_UF
 #undef LUF_MC_UF_CTA
+#undef LUF_MC_UF_ANY
     }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;

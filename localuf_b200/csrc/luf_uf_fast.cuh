@@ -1,0 +1,395 @@
+// luf_uf_fast.cuh -- the compact fast path of the fused Monte-Carlo kernel for static UF
+// (decoders/uf.py:200-301 validate; _schemes.py:116-155 Batch.run), default or west inclination.
+//
+// What a Monte-Carlo shot needs is one bit: the parity of error ^ correction on the west boundary.  As long as
+// no cluster comes to hold boundary nodes of BOTH sides, that bit does not depend on the order of the merges
+// nor on the peeling forest (luf_uf_phases.inl, "order-free merge" and uf_peel_parity): it is the XOR, over the
+// clusters that touch the west boundary, of their defect parity.  So this path keeps per cluster only
+// (odd, touches west, touches east) and per node only a 16-bit word:
+//
+//   P[v]   (detectors only; boundary nodes have no entry: they have one edge each and an active cluster has
+//          no boundary, so a boundary node is never looked up)
+//          root      bit 15 set | bit 0 odd | bit 1 touches west | bit 2 touches east
+//          non-root  the parent (a detector index < 32768)
+//   growth 2 bits per edge (0 ungrown, 1 half, 2 full), as in the canonical path
+//   tlist  the touched detectors in order of appearance (defects first): what later growth rounds visit
+//   alist  the active touched nodes of a round (node | root << 16)
+//   mlist  the edges that became fully grown this round, as endpoint pairs (detector | other end << 16, the
+//          other end being a detector or OTHER_WEST / OTHER_EAST)
+//
+// No union by size: a root is hooked below the root of smaller index with a compare-and-swap (a static strict
+// order, so no interleaving closes a cycle), taking its (odd, west, east) bits along; bits are added to live
+// roots with compare-and-swap too, so a payload always ends up at the root of its tree whatever the
+// interleaving.  Every change of a root word is one atomic transition, and each one adjusts the count of
+// active clusters (odd, no boundary) by the difference it makes -- the round loop ends when that count is 0.
+//
+// A shot that cannot be finished here -- a cluster touches both sides (the peeling forest matters), or a work
+// list overflows -- is reported as HARD; the caller queues it for the canonical kernel.  The state of a cfg3
+// shot is 4.8 KB instead of 8.9 KB, and nothing in a shot's loops reads global memory when the adjacency table
+// is staged in shared memory.
+//
+// The tile of `nl` cooperating lanes may be a part of a warp (8 / 16 lanes: several shots advance through the
+// same instructions), a warp, or several warps of a block (named barrier); the only tile operation is the
+// barrier between phases -- counts and votes go through the shot's counters in shared memory.
+#pragma once
+#include "luf_core.cuh"
+
+namespace luf {
+namespace fast {
+
+static const uint32_t P_ROOT = 0x8000u, P_ODD = 1u, P_WEST = 2u, P_EAST = 4u;
+static const uint32_t P_FRESH = P_ROOT;                  // an untouched detector: even singleton, no boundary
+static const uint32_t P_ACTIVE = P_ROOT | P_ODD;         // odd and no boundary (uf.py:296-301)
+static const uint32_t OTHER_WEST = 0x7FFFu, OTHER_EAST = 0x7FFEu;     // adjacency entry: the other end is a boundary node
+static const uint32_t END_WEST = 0xFFFFu, END_EAST = 0xFFFEu;         // edge table / merge list: ditto, 16-bit form
+// cnt[]: fill counters of the three lists (they only grow: a round's entries start at the previous total), the
+// number of active clusters, the parity accumulator, and two HARD flags -- one written by the growth phases
+// (a list overflowed), one by the merge phase (a cluster touches both sides) -- so that a flag is never
+// written by the phase that follows the barrier after which it is read.
+enum { C_TOUCHED = 0, C_ALIST = 1, C_MLIST = 2, C_ACTIVE = 3, C_HARD_G = 4, C_PARITY = 5, C_HARD_M = 6 };
+static const uint32_t HARD = 2u;                         // result of a shot the canonical kernel has to decode
+
+// Read-only tables (global memory; fadj optionally staged in shared memory by the kernel).
+struct FView {
+    int D, E, WD, DEG;          // detectors, edges, 32-bit words of a detector bitmap, row length of fadj (even)
+    const uint32_t* fadj;       // [D][DEG] edge | other end << 16 (detector index, OTHER_WEST, OTHER_EAST) | first endpoint << 31
+    const uint32_t* einfo;      // [E] first end | second end << 16 (detector index, END_WEST, END_EAST)
+    int F, n_classes;
+    const uint16_t* fresh_perm; // as GraphView
+    const uint32_t* class_end;
+};
+
+struct FLayout {
+    uint32_t P, growth, defect, touched;        // P: uint16[D]; growth: uint32[ceil(E/16)]; bitmaps: uint32[WD]
+    uint32_t fill_words, zero_off, zero_bytes;  // P is filled with P_FRESH pairs; growth .. touched are cleared
+    uint32_t tlist, alist, mlist, cnt;          // uint16[tcap], uint32[acap], uint32[mcap], uint32[8]
+    uint32_t tcap, acap, mcap;
+    uint32_t bytes;                             // slice size, multiple of 16
+};
+
+struct FShot {
+    uint16_t* P;
+    uint32_t *growth, *defect, *touched;
+    uint16_t* tlist;
+    uint32_t *alist, *mlist, *cnt;
+};
+
+LUF_DEV FShot fbind(const FLayout& l, unsigned char* base)
+{
+    FShot s;
+    s.P = (uint16_t*)(base + l.P);
+    s.growth = (uint32_t*)(base + l.growth); s.defect = (uint32_t*)(base + l.defect);
+    s.touched = (uint32_t*)(base + l.touched);
+    s.tlist = (uint16_t*)(base + l.tlist);
+    s.alist = (uint32_t*)(base + l.alist); s.mlist = (uint32_t*)(base + l.mlist); s.cnt = (uint32_t*)(base + l.cnt);
+    return s;
+}
+
+// ---------------------------------------------------------------- node words
+// Compare-and-swap on a 16-bit node word through its 32-bit container (shared memory has no 16-bit
+// compare-and-swap; nvcc emulates atomicCAS(unsigned short*) the same way).  Fails at once when the word is
+// not `expect`; a change of the neighbouring half only repeats the attempt.
+LUF_DEV bool cas16(uint16_t* P, uint32_t v, uint32_t expect, uint32_t val)
+{
+    uint32_t* wp = (uint32_t*)P + (v >> 1);
+    const uint32_t sh = (v & 1u) * 16u;
+    uint32_t cur = *(volatile uint32_t*)wp;
+    LUF_NOUNROLL
+    for (;;) {
+        if (((cur >> sh) & 0xFFFFu) != expect) return false;
+        const uint32_t nw = (cur & ~(0xFFFFu << sh)) | (val << sh);
+        const uint32_t old = luf_atomic_cas(wp, cur, nw);
+        if (old == cur) return true;
+        cur = old;
+    }
+}
+
+LUF_DEV uint32_t pload(const FShot& s, uint32_t v) { return *(volatile uint16_t*)&s.P[v]; }
+
+// find without writes; `wr` = the root's word
+LUF_DEV uint32_t ffind_ro(const FShot& s, uint32_t v, uint32_t& wr)
+{
+    uint32_t w;
+    LUF_NOUNROLL
+    while (!((w = pload(s, v)) & P_ROOT)) v = w;
+    wr = w;
+    return v;
+}
+
+// find that also points the start node at the root it found: safe next to concurrent finds, hooks and payload
+// updates (a non-root never becomes a root again; the value stored is one of its ancestors)
+LUF_DEV uint32_t ffind(const FShot& s, uint32_t v, uint32_t& wr)
+{
+    const uint32_t w = pload(s, v);
+    if (w & P_ROOT) { wr = w; return v; }
+    uint32_t r = w, q;
+    int hops = 0;
+    LUF_NOUNROLL
+    while (!((q = pload(s, r)) & P_ROOT)) { r = q; ++hops; }
+    if (hops) s.P[v] = (uint16_t)r;
+    wr = q;
+    return r;
+}
+
+// Add (odd, west, east) bits to the root of v's tree.
+LUF_DEV void add_bits(const FShot& s, uint32_t v, uint32_t bits)
+{
+    LUF_NOUNROLL
+    for (;;) {
+        uint32_t w;
+        const uint32_t r = ffind_ro(s, v, w);
+        const uint32_t nw = (w ^ (bits & P_ODD)) | (bits & (P_WEST | P_EAST));
+        if (nw == w) return;
+        if (cas16(s.P, r, w, nw)) {
+            const int delta = (nw == P_ACTIVE ? 1 : 0) - (w == P_ACTIVE ? 1 : 0);
+            if (delta) luf_atomic_add(&s.cnt[C_ACTIVE], (uint32_t)delta);
+            if ((nw & (P_WEST | P_EAST)) == (P_WEST | P_EAST)) s.cnt[C_HARD_M] = 1u;    // both sides: the forest matters
+            return;
+        }
+        v = r;
+    }
+}
+
+// uf.py:256-280 without the order: join the clusters of detectors a and b.
+LUF_DEV void join(const FShot& s, uint32_t a, uint32_t b)
+{
+    LUF_NOUNROLL
+    for (;;) {
+        uint32_t wa, wb;
+        uint32_t ra = ffind(s, a, wa), rb = ffind(s, b, wb);
+        if (ra == rb) return;
+        if (ra > rb) { uint32_t t = ra; ra = rb; rb = t; wb = wa; }      // the root of larger index goes below the other
+        if (!cas16(s.P, rb, wb, ra)) continue;
+        if (wb == P_ACTIVE) luf_atomic_sub(&s.cnt[C_ACTIVE], 1u);
+        if (wb & (P_ODD | P_WEST | P_EAST)) add_bits(s, ra, wb);
+        return;
+    }
+}
+
+// ------------------------------------------------------------------- phases
+LUF_DEV void f_reset(const FLayout& l, const FShot& s, int lane, int nl)
+{
+    luf_u32x4* P4 = (luf_u32x4*)s.P;
+    luf_u32x4 f; f.x = f.y = f.z = f.w = P_FRESH | (P_FRESH << 16);
+    LUF_NOUNROLL
+    for (int i = lane; i < (int)(l.fill_words >> 2); i += nl) P4[i] = f;
+    luf_u32x4* Z4 = (luf_u32x4*)((unsigned char*)s.P + (l.zero_off - l.P));
+    luf_u32x4 z; z.x = z.y = z.z = z.w = 0u;
+    LUF_NOUNROLL
+    for (int i = lane; i < (int)(l.zero_bytes >> 4); i += nl) Z4[i] = z;
+    if (lane == 0) { luf_u32x4* c4 = (luf_u32x4*)s.cnt; c4[0] = z; c4[1] = z; }       // lane 0 alone: it read the previous shot's result
+}
+
+// _base_classes.py:427-450 on the compact tables; returns whether the edge counts for the logical parity
+LUF_DEV uint32_t f_flip(const FView& g, const FShot& s, uint32_t e)
+{
+    const uint32_t ei = LUF_LDG(&g.einfo[e]);
+    const uint32_t a = ei & 0xFFFFu, b = ei >> 16;
+    if (a < END_EAST) luf_atomic_xor(&s.defect[a >> 5], 1u << (a & 31u));
+    if (b < END_EAST) luf_atomic_xor(&s.defect[b >> 5], 1u << (b & 31u));
+    return a == END_WEST ? 1u : 0u;
+}
+
+// uf.py:98-104: every defect an odd singleton; the defects open the list of touched nodes
+LUF_DEV void f_load(const FView& g, const FLayout& l, const FShot& s, int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (int w = lane; w < g.WD; w += nl) {
+        uint32_t bits = s.defect[w];
+        if (!bits) continue;
+        s.touched[w] = bits;
+        uint32_t pos = luf_atomic_add(&s.cnt[C_TOUCHED], (uint32_t)luf_popc(bits));
+        LUF_NOUNROLL
+        while (bits) {
+            const int b = luf_ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t v = (uint32_t)(32 * w + b);
+            s.P[v] = (uint16_t)P_ACTIVE;
+            if (pos < l.tcap) s.tlist[pos] = (uint16_t)v;
+            ++pos;
+        }
+    }
+}
+
+template <bool ADJ_SHARED, class F>
+LUF_DEV void f_row(const FView& g, uint32_t v, F f)
+{
+    const uint32_t* row = g.fadj + (size_t)v * (uint32_t)g.DEG;
+    LUF_NOUNROLL
+    for (int k = 0; k < g.DEG; k += 2) {
+        luf_u32x2 p;
+        if (ADJ_SHARED) p = *(const luf_u32x2*)(row + k); else p = LUF_LDG2(row + k);
+        if (p.x == ADJ_PAD) break;
+        f(p.x);
+        if (p.y != ADJ_PAD) f(p.y);
+    }
+}
+
+LUF_DEV void f_newfull(const FLayout& l, const FShot& s, uint32_t u, uint32_t other, uint32_t mbase)
+{
+    const uint32_t idx = luf_atomic_add(&s.cnt[C_MLIST], 1u) - mbase;
+    if (idx < l.mcap) s.mlist[idx] = u | ((other >= OTHER_EAST ? other | 0x8000u : other) << 16);
+    else s.cnt[C_HARD_G] = 1u;
+}
+
+// Round 1 (uf.py:234-245): every defect adds 1 to each of its edges, no look-ups; an edge is newly FULL iff the
+// other end (a defect too, then) got there first.
+template <bool ADJ_SHARED>
+LUF_DEV void f_grow_first(const FView& g, const FLayout& l, const FShot& s, uint32_t nd, int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < nd; i += (uint32_t)nl) {
+        const uint32_t v = s.tlist[i];
+        f_row<ADJ_SHARED>(g, v, [&](uint32_t ent) {
+            const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+            const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+            if (old == G_HALF) f_newfull(l, s, v, (ent >> 16) & 0x7FFFu, 0u);
+        });
+    }
+}
+
+LUF_DEV void f_touch(const FLayout& l, const FShot& s, uint32_t v)
+{
+    const uint32_t bit = 1u << (v & 31u);
+    if (luf_atomic_or(&s.touched[v >> 5], bit) & bit) return;
+    const uint32_t idx = luf_atomic_add(&s.cnt[C_TOUCHED], 1u);
+    if (idx < l.tcap) s.tlist[idx] = (uint16_t)v; else s.cnt[C_HARD_G] = 1u;
+}
+
+// Later rounds: a touched node whose cluster (root r) is active adds 1 to each of its edges that is not FULL;
+// an edge inside one cluster is counted once (only its first endpoint adds); the 2-bit counters saturate.
+template <bool ADJ_SHARED>
+LUF_DEV void f_grow_node(const FView& g, const FLayout& l, const FShot& s, uint32_t u, uint32_t r, uint32_t mbase)
+{
+    f_row<ADJ_SHARED>(g, u, [&](uint32_t ent) {
+        const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+        if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
+        const uint32_t o = (ent >> 16) & 0x7FFFu;
+        if (!(ent >> 31) && o < OTHER_EAST) {          // second endpoint of an edge between detectors: same cluster?
+            uint32_t wr;
+            if (o == r || ffind_ro(s, o, wr) == r) return;
+        }
+        const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+        if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);
+        else if (old == G_HALF) {
+            f_newfull(l, s, u, o, mbase);
+            if (o < OTHER_EAST) f_touch(l, s, o);
+        }
+    });
+}
+
+template <bool ADJ_SHARED>
+LUF_DEV void f_grow_filter(const FView& g, const FLayout& l, const FShot& s, uint32_t nt, uint32_t abase, uint32_t mbase,
+                           int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < nt; i += (uint32_t)nl) {
+        const uint32_t u = s.tlist[i];
+        uint32_t wr;
+        const uint32_t r = ffind(s, u, wr);
+        if (wr != P_ACTIVE) continue;
+        const uint32_t idx = luf_atomic_add(&s.cnt[C_ALIST], 1u) - abase;
+        if (idx < l.acap) s.alist[idx] = u | (r << 16);
+        else f_grow_node<ADJ_SHARED>(g, l, s, u, r, mbase);       // the list is full: grow right away (roots are stable here)
+    }
+}
+
+template <bool ADJ_SHARED>
+LUF_DEV void f_grow_exec(const FView& g, const FLayout& l, const FShot& s, uint32_t na, uint32_t mbase, int lane, int nl)
+{
+    if (na > l.acap) na = l.acap;
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < na; i += (uint32_t)nl) {
+        const uint32_t it = s.alist[i];
+        f_grow_node<ADJ_SHARED>(g, l, s, it & 0xFFFFu, it >> 16, mbase);
+    }
+}
+
+// uf.py:223-229 in any order: one lane per newly FULL edge
+LUF_DEV void f_merge(const FShot& s, uint32_t nm, int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < nm; i += (uint32_t)nl) {
+        const uint32_t it = s.mlist[i];
+        const uint32_t a = it & 0xFFFFu, b = it >> 16;
+        if (b >= END_EAST) add_bits(s, a, b == END_WEST ? P_WEST : P_EAST);
+        else join(s, a, b);
+    }
+}
+
+// every defect adds 1 iff its cluster touches the west boundary (uf_peel_parity, luf_uf_phases.inl)
+LUF_DEV uint32_t f_defect_sides(const FShot& s, uint32_t nd, int lane, int nl)
+{
+    uint32_t parity = 0;
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < nd; i += (uint32_t)nl) {
+        uint32_t wr;
+        ffind_ro(s, s.tlist[i], wr);
+        parity ^= (wr >> 1) & 1u;
+    }
+    return parity;
+}
+
+}  // namespace fast
+}  // namespace luf
+
+// ------------------------------------------------------------------ the shot driver
+// FT_PHASE(stmt): every lane of the tile runs stmt, then the tile synchronises (device: FT_SYNC() must be
+// defined by the including translation unit before fast_shot is instantiated; host emulation: the lanes run
+// one after the other).
+#if defined(LUF_HOST_EMU)
+  #define FT_PHASE(stmt) for (int lane = 0; lane < nl; ++lane) { stmt; }
+#else
+  #define FT_PHASE(stmt) { stmt; } sync();
+#endif
+
+namespace luf {
+namespace fast {
+
+// One shot: reset, sample (32 virtual sampler lanes whatever the tile, so that a shot's noise is the one
+// luf_sample writes for the same seed), load, rounds of grow / merge, parity.  Returns 0 / 1 = the logical bit
+// (_schemes.py:143-155), or HARD.  `sync` is the tile barrier.  stats (emulation only): [0] rounds,
+// [1] touched nodes, [2] most newly FULL edges of a round, [3] most active nodes of a round.
+template <bool ADJ_SHARED, class Sync>
+LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, const SampleParams& sp, uint64_t shot,
+                           int lane, int nl, Sync sync, uint32_t* stats = nullptr)
+{
+    (void)lane; (void)sync;
+    FT_PHASE((void)0);                                  // every lane is done with the previous shot's counters
+    FT_PHASE(f_reset(l, s, lane, nl));
+    FT_PHASE(
+        SampleTab t; t.F = g.F; t.n_classes = g.n_classes; t.perm = g.fresh_perm; t.class_end = g.class_end;
+        uint32_t par = 0;
+        for (int vl = lane; vl < 32; vl += nl)
+            par ^= ph_sample_core(t, sp, shot, 0u, (const uint32_t*)0, vl, 32, [&](uint32_t e) { return f_flip(g, s, e); });
+        if (par & 1u) luf_atomic_xor(&s.cnt[C_PARITY], 1u));
+    FT_PHASE(f_load(g, l, s, lane, nl));
+    const uint32_t nd = s.cnt[C_TOUCHED];
+    uint32_t rounds = 0, abase = 0, mbase = 0, most_m = 0, most_a = 0;
+    if (nd > l.tcap) return HARD;                        // (uniform: every lane reads the same counter)
+    if (nd) {
+        FT_PHASE(if (lane == 0) s.cnt[C_ACTIVE] = nd; f_grow_first<ADJ_SHARED>(g, l, s, nd, lane, nl));
+        LUF_NOUNROLL
+        for (;;) {
+            ++rounds;
+            const uint32_t nm = s.cnt[C_MLIST] - mbase;
+            if (s.cnt[C_HARD_G]) return HARD;
+            if (nm > most_m) most_m = nm;
+            FT_PHASE(f_merge(s, nm, lane, nl));
+            mbase += nm;
+            if (s.cnt[C_HARD_M]) return HARD;
+            if (!s.cnt[C_ACTIVE]) break;
+            const uint32_t nt = s.cnt[C_TOUCHED];
+            FT_PHASE(f_grow_filter<ADJ_SHARED>(g, l, s, nt, abase, mbase, lane, nl));
+            const uint32_t na = s.cnt[C_ALIST] - abase;
+            if (na > most_a) most_a = na;
+            FT_PHASE(f_grow_exec<ADJ_SHARED>(g, l, s, na, mbase, lane, nl));
+            abase += na;
+        }
+        FT_PHASE(const uint32_t par = f_defect_sides(s, nd, lane, nl); if (par) luf_atomic_xor(&s.cnt[C_PARITY], 1u));
+    }
+    if (stats) { stats[0] = rounds; stats[1] = s.cnt[C_TOUCHED]; stats[2] = most_m; stats[3] = most_a; }
+    return s.cnt[C_PARITY] & 1u;
+}
+
+}  // namespace fast
+}  // namespace luf

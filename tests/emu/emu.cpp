@@ -237,6 +237,35 @@ int emu_mc_uf_fast(const luf_graph_desc* d, int flags, const double* class_p, un
     return 0;
 }
 
+// The compact fast path of the fused kernels (luf_uf_fast.cuh) with a tile of `nl` lanes: out[k] = 0 / 1 (the
+// logical bit) or 2 (HARD: a cluster touches both sides or a list overflowed -- the kernel queues such shots for
+// the canonical path); stats (optional) [nshots][4] = rounds, touched nodes, most newly FULL edges of a round,
+// most active nodes of a round.  mu < 0: list capacities from the class probabilities, as the library does.
+int emu_mc_uf_compact(const luf_graph_desc* d, const double* class_p, unsigned long long seed, unsigned long long shot0,
+                      long long nshots, int nl, double mu, uint8_t* out, uint32_t* stats)
+{
+    PackedGraph p;
+    PackedFast pf;
+    if (!pack_graph(*d, p).empty()) return -1;
+    pack_fast(*d, p, pf);
+    if (!pf.ok) return -2;
+    if (mu < 0.0) {
+        mu = 0.0;
+        for (int c = 0, lo = 0; c < p.n_classes; ++c) { mu += class_p[c] * ((int)p.class_end[c] - lo); lo = (int)p.class_end[c]; }
+    }
+    fast::FView g;
+    g.D = pf.D; g.E = p.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
+    g.F = p.F; g.n_classes = p.n_classes;
+    g.fresh_perm = p.perm_identity ? nullptr : p.fresh_perm.data(); g.class_end = p.class_end.data();
+    const fast::FLayout l = make_fast_layout(pf.D, p.E, pf.DEG, mu);
+    const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
+    std::vector<unsigned char> mem(l.bytes + 16);
+    const fast::FShot s = fast::fbind(l, mem.data());
+    for (long long k = 0; k < nshots; ++k)
+        out[k] = (uint8_t)fast::fast_shot<false>(g, l, s, sp, shot0 + k, 0, nl, 0, stats ? stats + 4 * k : nullptr);
+    return 0;
+}
+
 // Macar (decoder 1) / Actis (decoder 2): syndromes in, (tSV, tBP), growth after
 // validation and correction out.
 int emu_decode_ca_tile(const luf_graph_desc* d, int decoder, int flags, long long nshots, const uint32_t* syn,

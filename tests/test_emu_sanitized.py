@@ -35,6 +35,10 @@ for name, flags in (('uf_sf5_phen_p08', 0), ('uf_sf9_cc_p10', 1), ('uf_sf4_cl_fw
 code = make_code(dict(code='Surface', d=5, noise='circuit-level'))
 emu = emu_binding.Emu(code)
 emu.mc_uf(0, 0.02, 5, 0, 200)
+for nl in (8, 32, 128):                      # the compact fast path: fitted lists, starved lists (every overflow branch)
+    emu.mc_uf_compact(0.02, 5, 0, 300, nl=nl)
+    emu.mc_uf_compact(0.02, 5, 0, 300, nl=nl, mu=0.0)
+emu_binding.Emu(make_code(dict(code='Surface', d=9, noise='phenomenological'))).mc_uf_compact(0.03, 5, 0, 200, nl=16)
 emu.sample_weight(7, 3, 0, 100)
 meta, arr = load_golden('ca_sf5_phen_p03')
 emu = emu_binding.Emu(make_code(meta['spec']))

@@ -1,0 +1,95 @@
+"""The compact fast path of the fused UF kernels (localuf_b200/csrc/luf_uf_fast.cuh) on the host emulation:
+the very phase source the kernel k_mc_uf_fast runs, lanes of a tile one after the other.
+
+Every shot the path finishes must carry the logical bit of the canonical decode (oracle-checked emulation of
+the staged path on the same counter-based noise); a shot it gives up on (HARD: a cluster touches both sides, or
+a work list overflowed) is decoded by the canonical kernel on the device, so it may never be wrong, only HARD.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_code
+
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
+import binding  # noqa: E402
+import emu_binding  # noqa: E402
+
+CASES = [
+    (dict(code='Repetition', d=5, noise='code capacity'), 0.05, 3000),
+    (dict(code='Repetition', d=9, noise='phenomenological'), 0.06, 1500),
+    (dict(code='Surface', d=3, noise='code capacity'), 0.12, 3000),
+    (dict(code='Surface', d=9, noise='code capacity'), 0.10, 3000),
+    (dict(code='Surface', d=5, noise='phenomenological'), 0.03, 3000),
+    (dict(code='Surface', d=7, noise='phenomenological', kwargs=dict(window_height=3)), 0.03, 2000),
+    (dict(code='Surface', d=11, noise='phenomenological'), 0.01, 2000),
+    (dict(code='Surface', d=11, noise='phenomenological'), 0.026, 1000),
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.01, 2000),
+    (dict(code='Surface', d=7, noise='circuit-level', kwargs=dict(parametrization='standard')), 0.005, 1500),
+    (dict(code='Surface', d=13, noise='phenomenological'), 0.02, 300),
+]
+
+
+def canonical_bits(code, p, seed, shot0, n):
+    """Logical bit per shot of the canonical decode, and whether a cluster spans both sides."""
+    emu = emu_binding.Emu(code)
+    orc = binding.Oracle.from_code(code)
+    _, err, syn, corr = emu.mc_uf(0, p, seed, shot0, n)
+    ocorr, _, _ = orc.decode_batch(0, 0, syn)
+    np.testing.assert_array_equal(corr, ocorr)
+    return emu, orc.logical_batch(err, ocorr)
+
+
+@pytest.mark.parametrize('spec,p,n', CASES, ids=lambda x: f"{x['code']}{x['d']}-{x['noise'].split()[0]}" if isinstance(x, dict) else str(x))
+def test_compact_path_is_never_wrong(spec, p, n):
+    code = make_code(spec)
+    emu, want = canonical_bits(code, p, 11, 100, n)
+    _, _, _, mixed, _ = emu.mc_uf_fast(0, p, 11, n) if False else (0, 0, 0, None, 0)
+    hard_by_tile = {}
+    for nl in (8, 16, 32, 64, 256):
+        out = emu.mc_uf_compact(p, 11, 100, n, nl=nl, mu=1e6)          # lists that hold everything: HARD = spans both sides
+        hard = out == 2
+        np.testing.assert_array_equal(out[~hard], want[~hard])
+        hard_by_tile[nl] = hard
+    for nl in (8, 16, 64, 256):                                        # which shots are HARD does not depend on the tile
+        np.testing.assert_array_equal(hard_by_tile[nl], hard_by_tile[32])
+    # the library's list capacities (from the expected number of faults): a few more HARD shots, no wrong ones
+    out = emu.mc_uf_compact(p, 11, 100, n, nl=16)
+    more = out == 2
+    assert np.all(more[hard_by_tile[32]])
+    np.testing.assert_array_equal(out[~more], want[~more])
+    assert more.sum() - hard_by_tile[32].sum() <= max(3, n // 100)
+    # starved lists: nearly everything overflows, still nothing wrong
+    out = emu.mc_uf_compact(p, 11, 100, n, nl=32, mu=0.0)
+    tiny = out == 2
+    np.testing.assert_array_equal(out[~tiny], want[~tiny])
+
+
+def test_compact_path_west_and_default_share_the_fast_result():
+    """A shot that the compact path finishes has no cluster on both sides, so the west and the default
+    inclination give the same bit (only the canonical kernel of the HARD shots looks at the flag)."""
+    code = make_code(dict(code='Surface', d=9, noise='code capacity'))
+    emu = emu_binding.Emu(code)
+    orc = binding.Oracle.from_code(code)
+    p, n = 0.10, 3000
+    _, err, syn, _ = emu.mc_uf(0, p, 5, 0, n)
+    out = emu.mc_uf_compact(p, 5, 0, n, nl=32, mu=1e6)
+    ok = out != 2
+    for flags in (0, 2):
+        corr, _, _ = orc.decode_batch(0, flags, syn)
+        np.testing.assert_array_equal(out[ok], orc.logical_batch(err, corr)[ok])
+
+
+def test_compact_path_sampler_is_the_staged_sampler():
+    """Tiles of 8 / 16 lanes walk the 32 virtual sampler lanes in turns: same noise as ph_sample, hence the same
+    defects -- checked through the number of shots without any defect and the HARD pattern above; here the
+    empty and the saturated ends."""
+    code = make_code(dict(code='Surface', d=5, noise='phenomenological'))
+    emu = emu_binding.Emu(code)
+    assert not emu.mc_uf_compact(0.0, 1, 0, 500, nl=8).any()
+    out = emu.mc_uf_compact(0.5, 1, 0, 200, nl=16, mu=1e6)
+    _, want = canonical_bits(code, 0.5, 1, 0, 200)
+    np.testing.assert_array_equal(out[out != 2], want[out != 2])
