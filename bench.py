@@ -50,16 +50,19 @@ DECODER_ID = {'UF': 0, 'Macar': 1, 'Actis': 2}
 OVERRIDE = {'p': None, 'd': None}      # --p / --d: the same workload at another noise level / distance (sweeps, profiles)
 
 
-def make_code(name):
+def make_code(name, p_over=None):
     import localuf_b200 as L
     cls, d, noise, p, desc = WORKLOADS[name][:5]
     scheme = WORKLOADS[name][5] if len(WORKLOADS[name]) > 5 else 'batch'
+    if p_over is not None:
+        desc = desc.replace(f'p={p}', f'p={p_over}')
+        p = p_over
+    elif OVERRIDE['p'] is not None:
+        desc = desc.replace(f'p={p}', f"p={OVERRIDE['p']}")
+        p = OVERRIDE['p']
     if OVERRIDE['d'] is not None:
         desc = desc.replace(f'd={d} ', f"d={OVERRIDE['d']} ").replace(f'h={d} ', f"h={OVERRIDE['d']} ")
         d = OVERRIDE['d']
-    if OVERRIDE['p'] is not None:
-        desc = desc.replace(f'p={p}', f"p={OVERRIDE['p']}")
-        p = OVERRIDE['p']
     return getattr(L, cls)(d, noise, scheme=scheme), p, desc
 
 
@@ -215,6 +218,34 @@ def time_cpu_stream(code, class_p, target_s, threads, seed=SEED):
     return cycles / dt, n, m, dt
 
 
+def workload_config(name, desc, code, p):
+    """The `config` object, identical in both arms (the driver compares them): what is measured, not how."""
+    w = WORKLOADS[name]
+    return {'workload': desc, 'code': w[0], 'd': int(code.D), 'noise': w[2], 'p': p,
+            'scheme': w[5] if len(w) > 5 else 'batch', 'decoder': decoder_name(name), 'seed': SEED,
+            'l2': 'GPU arm: 256 MiB write between timed steps (outside the per-step events), the fused kernels read '
+                  'only the graph tables from HBM; CPU arm: not applicable'}
+
+
+def python_reference_leg(name, p, d, procs, n=None):
+    """The UNMODIFIED Python reference on `procs` host cores (baseline/ref_python.py -> baseline/_ref):
+    code.SCHEME.run(decoder, p, n) in one process per core (_schemes.py:116-121).  None when the vendored
+    reference is absent."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    try:
+        import ref_python
+        if not ref_python.available() or name not in ref_python.WORKLOADS:
+            return None
+        r = ref_python.time_parallel(name, procs, n, p, d)
+    except Exception as e:                                   # the baseline must never take the bench line down
+        return {'unavailable': str(e)[:200]}
+    unit = 'decoding cycles/s' if decoder_name(name) == 'Snowflake' else 'shots/s'
+    return {'value': r['value'], 'unit': unit, 'cores': procs, 'kind': 'reference', 'per_core': r['per_core'],
+            'sample': f"{r['n_per_process']} = n of code.SCHEME.run(decoder, p, n) in each of {procs} processes "
+                      f"({r['units']} units, slowest process {r['seconds']:.1f} s, {r['failures']} failures): the unmodified "
+                      'Python reference from baseline/_ref'}
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm on the host cores.  The
     reference is pure Python and cannot travel to the GPU box, so this is the
@@ -263,10 +294,14 @@ def run_reference(args):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
-        'config': {'workload': desc, 'units_per_step': units // max(args.steps, 1), 'rng': 'xoshiro256** per thread'},
+        'config': workload_config(args.workload, desc, code, p),
+        'run': {'units_per_step': units // max(args.steps, 1),
+                'sampler': 'one Bernoulli draw per edge, xoshiro256** per thread (the GPU arm draws the same '
+                           'distribution by geometric skipping over Philox4x32-10)'},
         'cpu_baseline': {'value': value, 'unit': unit, 'cores': threads, 'kind': 'port',
-                         'sample': f'{what} per step on {threads} threads (C oracle of the reference algorithm; '
-                                   'the pure-Python reference cannot travel to the GPU box)'},
+                         'sample': f'{what} per step on {threads} threads (C restatement of the reference algorithm, '
+                                   'oracle/luf_oracle*.c, pinned to the reference goldens)'},
+        'cpu_baseline_python': None if args.no_python_ref else python_reference_leg(args.workload, args.p, args.d, threads),
         'e2e': {'value': value, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }), file=_RESULT_OUT, flush=True)
 
@@ -318,6 +353,13 @@ def host_buffer_e2e(eng, p, world, rank, steps, n=1 << 20):
                    'corrections out (page-locked buffers, copies inside the timed region)'}
 
 
+# the other BASELINE / SURVEY 8d measurement points, timed briefly next to the headline (N = 1 only):
+# (workload, noise level or None = the workload's own, units per step)
+SIDE_WORKLOADS = [('cfg1', None, 1 << 24), ('cfg2', None, 1 << 22), ('cfg2', 0.10, 1 << 21),
+                  ('cfg3', 0.005, 1 << 21), ('cfg3', 0.02, 1 << 20), ('cfg3', 0.026, 1 << 19),
+                  ('cfg3-macar', None, 1 << 18), ('cfg3-actis', None, 1 << 13), ('cfg4', None, 1 << 14), ('cfg4', 0.001, 1 << 14)]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -332,141 +374,160 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-
-    code, p, desc = make_code(args.workload)
-    dec = decoder_name(args.workload)
-    decoder = getattr(L.decoders, dec)(code)
-    S = args.shots_per_step or DEFAULT_UNITS[args.workload]
-    counts = torch.zeros(4, dtype=torch.int64, device='cuda')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')     # > 126 MB L2
-    stream_mode = dec == 'Snowflake'
-    if stream_mode:
-        # a step = S independent Frugal.run(n=1) memory experiments per GPU; unit = decoding cycle
-        eng = _engine.StreamEngine(code, device=local_rank)
-        decoder._engine = eng
-        unit, kernel = 'decoding cycles/s', 'k_sf_mc_cta / k_sf_mc'
-        bpu = algorithmic_bytes_per_cycle(eng.tables)
-        h2d = 8 * eng.tables.n_classes + 40
-
-        def step(k):
-            eng.mc(decoder._flags, p, SEED, (k * world + rank) * S, S, 1, counts)
-
-        def e2e_run(n_units, seed):
-            return code.SCHEME.run(decoder, p, 1, shots=n_units, seed=seed)[0]
-        api = 'code.SCHEME.run(decoder, p, n=1, shots=S) -> luf_stream_mc_host'
-    else:
-        eng = _engine.Engine(code, device=local_rank)
-        decoder._engine = eng
-        unit, kernel = 'shots/s', {'UF': 'k_mc_uf', 'Macar': 'k_mc_ca', 'Actis': 'k_mc_ca'}[dec]
-        bpu = algorithmic_bytes_per_shot(code.FLAT)
-        h2d = 8 * code.FLAT.n_classes + 40
-        did = DECODER_ID[dec]
-
-        def step(k):
-            # rank r, step k owns global shots [(k*world + r)*S, +S)
-            eng.mc_run(did, 0, p, SEED, (k * world + rank) * S, S, counts)
-
-        def e2e_run(n_units, seed):
-            return code.SCHEME.run(decoder, p, n_units, seed=seed)[0]
-        api = 'code.SCHEME.run(decoder, p, n) -> luf_mc_run_host'
+    peak, peak_src = measured_peak_hbm()
+    threads = len(os.sched_getaffinity(0))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.warmup):
-        step(k)
-    barrier()
-    counts.zero_()
-    launches0 = eng.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
+    def measure(name, S, steps, warmup, p_over=None, e2e_steps=3, host_buffers=False, cpu_seconds=0.0):
+        """One workload: `steps` timed steps of S units per GPU (CUDA events per step, max over ranks), the
+        same through the public API with host arguments (e2e), roofline and CPU port baseline."""
+        code, p, desc = make_code(name, p_over)
+        dec = decoder_name(name)
+        decoder = getattr(L.decoders, dec)(code)
+        counts = torch.zeros(4, dtype=torch.int64, device='cuda')
+        stream_mode = dec == 'Snowflake'
+        if stream_mode:
+            # a step = S independent Frugal.run(n=1) memory experiments per GPU; unit = decoding cycle
+            eng = _engine.StreamEngine(code, device=local_rank)
+            decoder._engine = eng
+            unit, kernel = 'decoding cycles/s', 'k_sf_mc_cta / k_sf_mc'
+            bpu = algorithmic_bytes_per_cycle(eng.tables)
+            h2d = 8 * eng.tables.n_classes + 40
+
+            def step(k):
+                eng.mc(decoder._flags, p, SEED, (k * world + rank) * S, S, 1, counts)
+
+            def e2e_run(n_units, seed):
+                return code.SCHEME.run(decoder, p, 1, shots=n_units, seed=seed)[0]
+            api = 'code.SCHEME.run(decoder, p, n=1, shots=S) -> luf_stream_mc_host'
+        else:
+            eng = _engine.Engine(code, device=local_rank)
+            decoder._engine = eng
+            unit = 'shots/s'
+            kernel = {'UF': 'k_mc_uf_fast (+ k_mc_uf over the queued shots)', 'Macar': 'k_mc_ca', 'Actis': 'k_mc_ca'}[dec]
+            bpu = algorithmic_bytes_per_shot(code.FLAT)
+            h2d = 8 * code.FLAT.n_classes + 40
+            did = DECODER_ID[dec]
+
+            def step(k):
+                # rank r, step k owns global shots [(k*world + r)*S, +S)
+                eng.mc_run(did, 0, p, SEED, (k * world + rank) * S, S, counts)
+
+            def e2e_run(n_units, seed):
+                return code.SCHEME.run(decoder, p, n_units, seed=seed)[0]
+            api = 'code.SCHEME.run(decoder, p, n) -> luf_mc_run_host'
+
+        for k in range(warmup):
+            step(k)
         barrier()
-        clocks.mark()
-        t_wall0 = time.perf_counter()
-        for k in range(args.steps):
-            flush.fill_(k & 0xFF)                       # L2 flush between timed steps
-            ev[k][0].record()
-            step(args.warmup + k)
-            ev[k][1].record()
+        counts.zero_()
+        launches0 = eng.launch_count
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        with ClockSampler(local_rank) as clocks:
+            barrier()
+            clocks.mark()
+            t_wall0 = time.perf_counter()
+            for k in range(steps):
+                flush.fill_(k & 0xFF)                       # L2 flush between timed steps
+                ev[k][0].record()
+                step(warmup + k)
+                ev[k][1].record()
+            barrier()
+            t_wall = time.perf_counter() - t_wall0
+            clocks.mark()
+        launches = eng.launch_count - launches0
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        total_ms = float(total_ms.item())
+        fails, units = (int(x) for x in counts.tolist()[:2])
+        if not stream_mode:
+            assert units == S * steps * world, (units, S, steps, world)
+        value = units / (total_ms / 1e3)
+        units_per_step_gpu = units // (steps * world)
+
+        # ---- end to end through the public API (the call a reference user makes):
+        # host arguments in (class probabilities, seed, counts), counters back on the host
+        for _ in range(2):
+            e2e_run(max(1, min(S, 1 << 12)) * world, 1)
         barrier()
-        t_wall = time.perf_counter() - t_wall0
-        clocks.mark()
-    launches = eng.launch_count - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    total_ms = float(total_ms.item())
-    fails, units = (int(x) for x in counts.tolist()[:2])
-    if not stream_mode:
-        assert units == S * args.steps * world, (units, S, args.steps, world)
-    value = units / (total_ms / 1e3)
-    units_per_step_gpu = units // (args.steps * world)
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(steps, e2e_steps))
+        m_e2e = 0
+        for k in range(e2e_steps):
+            m_e2e += e2e_run(S * world, SEED + 1000 + k)
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e_value = units_per_step_gpu * world * e2e_steps / float(t_e2e.item())
 
-    # ---- end to end through the public API (the call a reference user makes):
-    # host arguments in (class probabilities, seed, counts), counters back on the host
-    for _ in range(2):
-        e2e_run(max(1, min(S, 1 << 12)) * world, 1)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    m_e2e = 0
-    for k in range(e2e_steps):
-        m_e2e += e2e_run(S * world, SEED + 1000 + k)
-    barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = units_per_step_gpu * world * e2e_steps / float(t_e2e.item())
+        # ---- and with real host buffers (UF workloads): host syndromes -> host corrections, staged decode kernel
+        e2e_host = host_buffer_e2e(eng, p, world, rank, e2e_steps) if host_buffers and dec == 'UF' else None
 
-    # ---- and with real host buffers (UF workloads): host syndromes -> host corrections, staged decode kernel
-    e2e_host = None
-    if dec == 'UF' and not stream_mode:
-        e2e_host = host_buffer_e2e(eng, p, world, rank, e2e_steps)
-
-    if rank == 0:
-        peak, peak_src = measured_peak_hbm()
         kern_ms = statistics.mean(step_ms)
         achieved = bpu * units_per_step_gpu / (kern_ms / 1e3) / 1e9
-        traffic, traffic_src = TRAFFIC.get(args.workload, (None, None))
-        line = {
+        traffic, traffic_src = TRAFFIC.get(name, (None, None)) if p_over is None else (None, None)
+        r = {
             'metric': METRIC[unit], 'value': value, 'unit': unit, 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': total_ms / steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': DTYPE, 'data': 'synthetic',
-            'config': {'workload': desc, 'units_per_step_per_gpu': units_per_step_gpu, 'seed': SEED,
-                       'parallelism': f'dp{world} (shots sharded, one all-reduce of counters)',
-                       'l2': '256 MiB write between timed steps (outside the per-step events); '
-                             'the fused kernel reads only the graph tables (~100 KB) from HBM',
-                       'failures': fails, 'failure_rate': fails / max(units, 1), 'wall_s_timed_region': t_wall},
+            'config': workload_config(name, desc, code, p),
+            'run': {'units_per_step_per_gpu': units_per_step_gpu,
+                    'parallelism': f'dp{world} (shots sharded, one all-reduce of counters)',
+                    'failures': fails, 'failure_rate': fails / max(units, 1), 'wall_s_timed_region': t_wall},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'kernel': kernel,
                          'traffic_source': traffic_src,
                          'algorithmic_bytes_per_unit': bpu, 'peak_source': peak_src,
-                         'note': 'the fused kernel keeps a shot in shared memory, so the HBM fraction is low by '
-                                 'construction (SURVEY 8d); the kernel is bound by shared-memory latency at 26 resident warps per SM and by '
-                                 'issue slots of narrow phases (profiles/)'},
+                         'note': 'the fused kernels keep a shot in shared memory, so the HBM fraction is low by '
+                                 'construction (SURVEY 8d): they are bound by shared-memory latency and issue slots '
+                                 '(profiles/)'},
             'e2e': {'value': e2e_value, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 32,
                     'api': api, 'failures': m_e2e},
             'e2e_host_buffers': e2e_host,
             'gpu_launches': launches,
             'clocks': clocks.summary(),
         }
-        if world == 1 and not args.no_cpu:
-            threads = len(os.sched_getaffinity(0))
+        if rank == 0 and world == 1 and cpu_seconds > 0:
             class_p = code.NOISE.class_probabilities(p)
             if stream_mode:
-                rate, n, m, dt = time_cpu_stream(code, class_p, args.cpu_seconds, threads)
+                rate, n, m, dt = time_cpu_stream(code, class_p, cpu_seconds, threads)
                 what = f'{n} Frugal.run(n=1) memory experiments'
             else:
-                rate, n, m, dt = time_cpu(cpu_oracle(code), class_p, args.cpu_seconds, threads, decoder=DECODER_ID[dec])
+                rate, n, m, dt = time_cpu(cpu_oracle(code), class_p, cpu_seconds, threads, decoder=DECODER_ID[dec])
                 what = f'{n} shots'
-            line['cpu_baseline'] = {'value': rate, 'unit': unit, 'cores': threads, 'kind': 'port',
-                                    'sample': f'{what} of the same workload in {dt:.1f} s '
-                                              f'(C oracle of the reference algorithm, {m} failures)'}
+            r['cpu_baseline'] = {'value': rate, 'unit': unit, 'cores': threads, 'kind': 'port',
+                                 'sample': f'{what} of the same workload in {dt:.1f} s '
+                                           f'(C restatement of the reference algorithm, oracle/, {m} failures)'}
+        del eng, decoder
+        return r
+
+    S = args.shots_per_step or DEFAULT_UNITS[args.workload]
+    line = measure(args.workload, S, args.steps, args.warmup, host_buffers=True,
+                   cpu_seconds=0.0 if args.no_cpu else args.cpu_seconds)
+    if rank == 0 and world == 1 and not args.no_python_ref:
+        line['cpu_baseline_python'] = python_reference_leg(args.workload, args.p, args.d, threads)
+    if world == 1 and not args.no_workloads and args.workload == 'cfg3' and args.p is None and args.d is None:
+        side = []
+        for name, p_over, units in SIDE_WORKLOADS:
+            try:
+                r = measure(name, units, 2, 3, p_over=p_over, e2e_steps=1, cpu_seconds=0.0 if args.no_cpu else 1.5)
+            except Exception as e:                       # a side measurement must not take the headline down
+                side.append({'workload': name, 'p': p_over, 'error': str(e)[:200]})
+                continue
+            side.append({k: r[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'config', 'run', 'roofline', 'e2e',
+                                          'gpu_launches', 'clocks', 'cpu_baseline') if k in r})
+        line['workloads'] = side
+    if rank == 0:
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -575,10 +636,10 @@ def run_staged(args):
             'metric': METRIC['shots/s'], 'value': value, 'unit': 'shots/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
-            'config': {'workload': desc, 'units_per_step_per_gpu': S, 'seed': SEED,
-                       'parallelism': f'dp{world} (shots sharded, no data-path collective)',
-                       'l2': '256 MiB write between timed steps; the buffers of one step (1.1 GB) exceed the L2',
-                       'failures': int(fails.item()), 'host_path_equals_device_path': same},
+            'config': workload_config(args.workload, desc, code, p),
+            'run': {'units_per_step_per_gpu': S, 'parallelism': f'dp{world} (shots sharded, no data-path collective)',
+                    'l2': '256 MiB write between timed steps; the buffers of one step (1.1 GB) exceed the L2',
+                    'failures': int(fails.item()), 'host_path_equals_device_path': same},
             'roofline': {'bound': 'hbm', 'achieved': bpu * S / (kern_ms[dom] / 1e3) / 1e9, 'peak': peak, 'unit': 'GB/s',
                          'frac': bpu * S / (kern_ms[dom] / 1e3) / 1e9 / peak, 'traffic': None, 'kernel': dom,
                          'algorithmic_bytes_per_unit': bpu, 'peak_source': peak_src, 'kernels': kernels,
@@ -605,6 +666,8 @@ def main():
     ap.add_argument('--shots-per-step', type=int, default=0, help='units per step per GPU (0 = workload default)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-python-ref', action='store_true', help='skip the unmodified Python reference leg')
+    ap.add_argument('--no-workloads', action='store_true', help='skip the short runs of the other BASELINE configs')
     ap.add_argument('--p', type=float, default=None, help='noise level override')
     ap.add_argument('--d', type=int, default=None, help='code distance override')
     args = ap.parse_args()

@@ -138,6 +138,15 @@ int luf_check(luf_graph *g, int64_t nshots, const uint32_t *err_bits_dev,
               const uint32_t *corr_bits_dev, uint8_t *logical_dev,
               unsigned long long *fail_count_dev, void *stream);
 
+/* K4' -- replaces Global.get_logical_error (localuf/_schemes.py:194-203) and the Pairs it
+ * fills (localuf/_pairs.py:4-66): the edges of leftover = error ^ correction are spliced
+ * into strings in ascending edge id, and the strings that join the west and the east
+ * boundary are counted.  count_dev (optional) [nshots] int32 receives the count of every
+ * shot; total_dev: one uint64 that the sum is atomically ADDED to. */
+int luf_count_strings(luf_graph *g, int64_t nshots, const uint32_t *err_bits_dev,
+                      const uint32_t *corr_bits_dev, int32_t *count_dev,
+                      unsigned long long *total_dev, void *stream);
+
 /* Fused K1+K2/3+K4 -- replaces the shot loop Batch.run
  * (localuf/_schemes.py:116-121,131-155): nshots shots are sampled, decoded and
  * checked without leaving the SM.  counts_dev is uint64[4]: [0] += failures,

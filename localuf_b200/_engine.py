@@ -142,6 +142,7 @@ def _load():
         lib.luf_decode_batch.argtypes = [v, C.c_int, C.c_int, i64, v, v, v, v, v]
         lib.luf_check.argtypes = [v, i64, v, v, v, v, v]
         lib.luf_mc_run.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v, v]
+        lib.luf_count_strings.argtypes = [v, i64, v, v, v, v, v]
         lib.luf_mc_run_host.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v]
         lib.luf_mc_run_logical.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v, v, v]
         lib.luf_mc_run_logical_host.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v, v]
@@ -306,6 +307,76 @@ class Engine:
                 _check(lib.luf_check(self._h, k, _ptr(err), _ptr(corr), None, _ptr(fails), st))
                 done += k
             return int(fails.item()), nshots
+
+    def mc_global(self, decoder: int, flags: int, noise_level: float, seed: int, shot0: int, nshots: int,
+                  chunk: int = 1 << 14, want_counts=False):
+        """``nshots`` windows of the global batch scheme (``_schemes.py:186-203``): sample -> decode ->
+        count the west-east strings of the leftover (``luf_count_strings``), all on device buffers; returns
+        the total (and the per-window counts)."""
+        import torch
+        dev = torch.device('cuda', self.device)
+        chunk = min(chunk, max(1, nshots))
+        err = torch.empty((chunk, self.WE), dtype=torch.int32, device=dev)
+        syn = torch.empty((chunk, self.WD), dtype=torch.int32, device=dev)
+        corr = torch.empty((chunk, self.WE), dtype=torch.int32, device=dev)
+        per = torch.zeros(nshots, dtype=torch.int32, device=dev)
+        total = torch.zeros(1, dtype=torch.int64, device=dev)
+        cp = self.class_p(noise_level)
+        lib, done = _load(), 0
+        with torch.cuda.device(dev):
+            st = _stream()
+            while done < nshots:
+                k = min(chunk, nshots - done)
+                _check(lib.luf_sample(self._h, cp.ctypes.data, seed, shot0 + done, k, _ptr(err), _ptr(syn), st))
+                _check(lib.luf_decode_batch(self._h, decoder, flags, k, _ptr(syn), _ptr(corr), None, None, st))
+                _check(lib.luf_count_strings(self._h, k, _ptr(err), _ptr(corr), per[done:].data_ptr(), _ptr(total), st))
+                done += k
+            out = int(total.item())
+            return (out, per.cpu().numpy()) if want_counts else out
+
+    def mc_special(self, noise_engine: 'Engine', decoder: int, flags: int, noise_level: float, seed: int, shot0: int,
+                   nshots: int, chunk: int = 1 << 18):
+        """``sim.accuracy.monte_carlo_special`` (``monte_carlo.py:162-201``): the errors and syndromes come from
+        ``noise_engine``'s graph (circuit-level noise), this engine's graph (phenomenological, same nodes)
+        decodes them; leftover parity = west parity of the error on its graph XOR west parity of the
+        correction on this one.  Staged kernels on device buffers; returns (failures, shots)."""
+        import torch
+        a, b = noise_engine, self
+        if a.WD != b.WD or a.flat.n_nodes != b.flat.n_nodes or a.flat.n_boundary != b.flat.n_boundary:
+            raise ValueError('monte_carlo_special: the two codes must share their nodes')
+        dev = torch.device('cuda', self.device)
+        chunk = min(chunk, max(1, nshots))
+        i32 = dict(dtype=torch.int32, device=dev)
+        err, syn = torch.empty((chunk, a.WE), **i32), torch.empty((chunk, a.WD), **i32)
+        corr = torch.empty((chunk, b.WE), **i32)
+        zero_a, zero_b = torch.zeros((chunk, a.WE), **i32), torch.zeros((chunk, b.WE), **i32)
+        la, lb = torch.empty(chunk, dtype=torch.uint8, device=dev), torch.empty(chunk, dtype=torch.uint8, device=dev)
+        scratch = torch.zeros(1, dtype=torch.int64, device=dev)
+        fails, done = 0, 0
+        with torch.cuda.device(dev):
+            while done < nshots:
+                k = min(chunk, nshots - done)
+                a.sample(noise_level, seed, shot0 + done, k, err, syn)
+                b.decode_batch(decoder, flags, k, syn, corr)
+                a.check(k, err, zero_a, la, scratch)
+                b.check(k, zero_b, corr, lb, scratch)
+                fails += int((la[:k] ^ lb[:k]).sum().item())
+                done += k
+        return fails, nshots
+
+    def count_strings_host(self, err_bits, corr_bits):
+        """Per-shot counts of west-east strings in ``err ^ corr`` (host arrays in, int32 [n] out)."""
+        import torch
+        dev = torch.device('cuda', self.device)
+        e = torch.from_numpy(np.ascontiguousarray(err_bits, dtype=np.uint32).reshape(-1, self.WE).view(np.int32)).to(dev)
+        c = torch.from_numpy(np.ascontiguousarray(corr_bits, dtype=np.uint32).reshape(-1, self.WE).view(np.int32)).to(dev)
+        per = torch.zeros(e.shape[0], dtype=torch.int32, device=dev)
+        total = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _check(_load().luf_count_strings(self._h, e.shape[0], _ptr(e), _ptr(c), _ptr(per), _ptr(total), _stream()))
+            out = per.cpu().numpy()
+        assert int(total.item()) == int(out.sum())
+        return out
 
     def mc_given_errors(self, decoder: int, flags: int, err_bits, syn_bits):
         """Failures among given (error, syndrome) bit arrays: K2/K3a -> K4; returns (failures, shots)."""

@@ -198,7 +198,7 @@ inline SampleParams make_sample_params(const double* class_p, int n_classes, uin
         const double p = class_p[c];
         sp.p[c] = p >= 1.0 ? 1.0f : (p <= 0.0 ? 0.0f : (float)p);
         if (p > 0.0 && p < 1.0) {
-            if (sp.p[c] <= 0.0f) sp.p[c] = 1e-38f;          // keep tiny p "on"
+            if (sp.p[c] < 1.17549435e-38f) sp.p[c] = 1.17549435e-38f;   // keep tiny p "on": FLT_MIN, not a denormal (--use_fast_math flushes those to 0)
             if (sp.p[c] >= 1.0f) sp.p[c] = 0.99999994f;
             sp.inv_log2_q[c] = (float)(1.0 / (std::log1p(-p) / std::log(2.0)));
         }

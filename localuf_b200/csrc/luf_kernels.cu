@@ -16,8 +16,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
+#include <set>
 #include <new>
 #include <string>
 #include <vector>
@@ -641,6 +643,87 @@ __global__ void __launch_bounds__(256) k_check4(int WE, uint32_t magic, long lon
     if (lane == 0 && fails) atomicAdd(fail_count, (unsigned long long)fails);
 }
 
+// Global.get_logical_error (_schemes.py:194-203) for a batch of leftovers = err ^ corr: the edges are loaded
+// into Pairs in ascending edge id (_pairs.py:49-66) and the strings that join the two sides are counted.  One
+// warp per shot: the partner map (one int16 per node; a boundary node has one edge, so the two sides are two
+// keys) lives in the warp's shared memory; the lanes fetch 32 leftover words at a time, lane 0 splices their
+// edges in order (the pairing where three or more leftover edges meet depends on it), and all lanes clear what
+// the shot touched.
+static const int STR_NONE = -32768, STR_WEST = -1, STR_EAST = -2;
+
+__device__ __forceinline__ int str_key(const GraphView& g, uint32_t v)
+{
+    return v >= (uint32_t)g.B ? (int)v : (__ldg(&g.node_long[v]) == -1 ? STR_WEST : STR_EAST);
+}
+__device__ __forceinline__ void str_add(int16_t* partner, int a, int b, int& count)
+{
+    if (a >= 0) partner[a] = (int16_t)b;
+    if (b >= 0) partner[b] = (int16_t)a;
+    if ((a == STR_WEST && b == STR_EAST) || (a == STR_EAST && b == STR_WEST)) ++count;
+}
+__device__ __forceinline__ int str_take(int16_t* partner, int u)
+{
+    const int w = partner[u];
+    partner[u] = (int16_t)STR_NONE;
+    if (w >= 0) partner[w] = (int16_t)STR_NONE;
+    return w;
+}
+
+__global__ void k_count_strings(GraphView g, long long nshots, const uint32_t* __restrict__ err,
+                                const uint32_t* __restrict__ corr, int32_t* __restrict__ per_shot,
+                                unsigned long long* total, uint32_t slice_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    int16_t* partner = (int16_t*)(smem + (size_t)(threadIdx.x >> 5) * slice_bytes);
+    for (int v = lane; v < g.N; v += 32) partner[v] = (int16_t)STR_NONE;
+    __syncwarp();
+    unsigned long long sum = 0;
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        int count = 0;
+        for (int base = 0; base < g.WE; base += 32) {
+            const int w = base + lane;
+            const uint32_t x = w < g.WE ? (__ldg(&err[k * g.WE + w]) ^ __ldg(&corr[k * g.WE + w])) : 0u;
+            uint32_t lanes = __ballot_sync(0xffffffffu, x != 0u);
+            while (lanes) {                                   // ascending words, ascending bits: ascending edge id
+                const int src = __ffs((int)lanes) - 1; lanes &= lanes - 1;
+                uint32_t bits = __shfl_sync(0xffffffffu, x, src);
+                if (lane == 0) {
+                    while (bits) {
+                        const int b = __ffs((int)bits) - 1; bits &= bits - 1;
+                        const uint32_t uv = __ldg(&g.edge_uv[32 * (base + src) + b]);
+                        const int u = str_key(g, uv & 0xFFFFu), v = str_key(g, uv >> 16);
+                        if (u >= 0 && partner[u] != STR_NONE) {
+                            const int p = str_take(partner, u);
+                            if (v >= 0 && partner[v] != STR_NONE) str_add(partner, p, str_take(partner, v), count);
+                            else if (v != p || v < 0) str_add(partner, v, p, count);
+                        } else if (v >= 0 && partner[v] != STR_NONE)
+                            str_add(partner, u, str_take(partner, v), count);
+                        else
+                            str_add(partner, u, v, count);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // put the map back: every entry the shot wrote belongs to an end of a leftover edge
+        for (int base = 0; base < g.WE; base += 32) {
+            const int w = base + lane;
+            uint32_t bits = w < g.WE ? (__ldg(&err[k * g.WE + w]) ^ __ldg(&corr[k * g.WE + w])) : 0u;
+            while (bits) {
+                const int b = __ffs((int)bits) - 1; bits &= bits - 1;
+                const uint32_t uv = __ldg(&g.edge_uv[32 * w + b]);
+                if ((uv & 0xFFFFu) >= (uint32_t)g.B) partner[uv & 0xFFFFu] = (int16_t)STR_NONE;
+                if ((uv >> 16) >= (uint32_t)g.B) partner[uv >> 16] = (int16_t)STR_NONE;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { if (per_shot) per_shot[k] = count; sum += (unsigned long long)count; }
+    }
+    if (lane == 0 && sum) atomicAdd(total, sum);
+}
+
 // ------------------------------------------------------------------- graph
 struct luf_graph {
     int device = 0, sm_count = 0, max_smem = 0;
@@ -664,7 +747,7 @@ struct luf_graph {
     // grow-only scratch for the *_host entry points
     void* scratch[6] = {0, 0, 0, 0, 0, 0};
     size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
-    long long launches = 0;
+    std::atomic<long long> launches{0};
     cudaStream_t pipe[3] = {0, 0, 0};     // copy / compute pipeline of the *_host batch entry points
     std::mutex mu;
     std::map<std::pair<const void*, uint32_t>, std::pair<int, int>> plans;   // (kernel, slice bytes) -> (warps per block, blocks per SM)
@@ -701,6 +784,24 @@ static int scratch_get(luf_graph* g, int slot, size_t bytes, void** out)
 
 struct LaunchCfg { int grid, block; size_t smem; };
 
+// The opt-in shared-memory limit of a kernel is process-wide state of the function (per device): it is raised
+// once, to the device maximum, and never lowered, so concurrent callers (ctypes releases the GIL) with graphs
+// of different slice sizes cannot undercut each other between a set-attribute and a launch.  The same mutex
+// guards the plan caches of the graphs: the *_dev entry points take no per-graph lock.
+static std::mutex g_plan_mu;
+static std::set<std::pair<int, const void*>> g_smem_raised;
+
+template <class K>
+static int raise_smem_limit(int device, int max_smem, K kernel)
+{
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    const std::pair<int, const void*> key(device, (const void*)kernel);
+    if (g_smem_raised.count(key)) return 0;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    g_smem_raised.insert(key);
+    return 0;
+}
+
 // Warps per block and a persistent grid: as many blocks per SM as the
 // shared-memory budget allows, never more blocks than there is work.
 template <class K>
@@ -720,30 +821,35 @@ static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long n
     const int budget_kb = env_kb > 0 ? env_kb : 228;
     int wpb = 1, per_sm = 1, best = 0;
     const std::pair<const void*, uint32_t> key((const void*)kernel, slice_bytes);
-    auto hit = g->plans.find(key);
-    if (hit != g->plans.end()) { wpb = hit->second.first; per_sm = hit->second.second; best = wpb * per_sm; }
-    else {
+    if (int rc = raise_smem_limit(g->device, g->max_smem, kernel)) return rc;
+    bool cached = false;
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mu);
+        auto hit = g->plans.find(key);
+        if (hit != g->plans.end()) { wpb = hit->second.first; per_sm = hit->second.second; best = wpb * per_sm; cached = true; }
+    }
+    if (!cached) {
         // the occupancy query honours the carve-out preference a previous plan left on the kernel
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        for (int cand = 1; cand <= max_wpb; ++cand) {
+            if (env_wpb > 0 && cand != env_wpb) continue;
+            const size_t sm = (size_t)cand * l.bytes;
+            if (sm > (size_t)g->max_smem) break;
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, cand * WARP, sm));
+            const int by_budget = (int)((size_t)budget_kb * 1024 / (sm + 1024));
+            if (occ > by_budget) occ = by_budget;
+            if (occ * cand >= best && occ > 0) { best = occ * cand; wpb = cand; per_sm = occ; }   // ties: fewer, larger blocks
+        }
+        if (best == 0) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+        if (getenv("LUF_DEBUG_PLAN"))
+            fprintf(stderr, "[luf] launch plan: %u B per shot, %d warps per block, %d blocks per SM\n", slice_bytes, wpb, per_sm);
+        std::lock_guard<std::mutex> lock(g_plan_mu);
+        g->plans[key] = std::make_pair(wpb, per_sm);
     }
-    if (hit == g->plans.end()) for (int cand = 1; cand <= max_wpb; ++cand) {
-        if (env_wpb > 0 && cand != env_wpb) continue;
-        const size_t sm = (size_t)cand * l.bytes;
-        if (sm > (size_t)g->max_smem) break;
-        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        int occ = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, cand * WARP, sm));
-        const int by_budget = (int)((size_t)budget_kb * 1024 / (sm + 1024));
-        if (occ > by_budget) occ = by_budget;
-        if (occ * cand >= best && occ > 0) { best = occ * cand; wpb = cand; per_sm = occ; }   // ties: fewer, larger blocks
-    }
-    if (best == 0) return fail(LUF_ERR_UNSUPPORTED, "kernel does not fit on an SM");
-    if (hit == g->plans.end() && getenv("LUF_DEBUG_PLAN"))
-        fprintf(stderr, "[luf] launch plan: %u B per shot, %d warps per block, %d blocks per SM\n", slice_bytes, wpb, per_sm);
-    g->plans[key] = std::make_pair(wpb, per_sm);
     const size_t smem = (size_t)wpb * l.bytes;
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {   // ask for just enough shared memory for per_sm blocks, leave the rest to L1
+    {   // ask for just enough shared memory for per_sm blocks, leave the rest to L1 (a hint: harmless if another
+        // thread's launch of the same kernel overwrites it)
         int pct = (int)(((smem + 1024) * per_sm * 100 + 228 * 1024 - 1) / (228 * 1024));
         if (pct > 100) pct = 100;
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -765,11 +871,14 @@ static int plan_cta_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long lo
                     " B) exceeds the shared memory of an SM");
     static const int env_threads = getenv("LUF_CTA_THREADS") ? atoi(getenv("LUF_CTA_THREADS")) : 0;
     const std::pair<const void*, uint32_t> key((const void*)kernel, slice_bytes);
-    auto hit = g->plans.find(key);
+    if (int rc = raise_smem_limit(g->device, g->max_smem, kernel)) return rc;
     int threads = 0, per_sm = 0;
-    if (hit != g->plans.end()) { threads = hit->second.first; per_sm = hit->second.second; }
-    else {
-        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_bytes));
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mu);
+        auto hit = g->plans.find(key);
+        if (hit != g->plans.end()) { threads = hit->second.first; per_sm = hit->second.second; }
+    }
+    if (!threads) {
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int best = 0;
         for (int cand = 448; cand >= 64; cand -= 32) {
@@ -782,6 +891,7 @@ static int plan_cta_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long lo
         if (getenv("LUF_DEBUG_PLAN"))
             fprintf(stderr, "[luf] launch plan (block per shot): %u B per shot, %d threads per block, %d blocks per SM\n",
                     slice_bytes, threads, per_sm);
+        std::lock_guard<std::mutex> lock(g_plan_mu);
         g->plans[key] = std::make_pair(threads, per_sm);
     }
     long long blocks = (long long)g->sm_count * per_sm;
@@ -829,7 +939,7 @@ static int plan_ca_cta_launch(luf_graph* g, K kernel, uint32_t bytes, long long 
     if (bytes > (uint32_t)g->max_smem)
         return fail(LUF_ERR_UNSUPPORTED, "one shot's decoder state (" + std::to_string(bytes) + " B) exceeds the shared memory of an SM");
     const int env_threads = getenv("LUF_CA_CTA_THREADS") ? atoi(getenv("LUF_CA_CTA_THREADS")) : 0;
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (int rc = raise_smem_limit(g->device, g->max_smem, kernel)) return rc;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     cudaFuncAttributes attr;
     CUDA_TRY(cudaFuncGetAttributes(&attr, kernel));
@@ -905,7 +1015,7 @@ static bool fast_plan(const luf_graph* g, const fast::FLayout& l, FastPlan* out)
 
 static int fast_queue(luf_graph* g, void* stream, uint32_t** out)
 {
-    std::lock_guard<std::mutex> lock(g->mu);
+    std::lock_guard<std::mutex> lock(g_plan_mu);       // (not g->mu: the *_host entry points hold that one while they call in here)
     auto it = g->queues.find(stream);
     if (it == g->queues.end()) {
         void* p = nullptr;
@@ -921,15 +1031,10 @@ static int fast_launch_t(luf_graph* g, const FastPlan& plan, const fast::FLayout
                          unsigned long long shot0, long long nshots, unsigned long long* counts, uint8_t* logical,
                          uint32_t* queue, uint32_t* qcount, cudaStream_t stream)
 {
-    static std::mutex once_mu;
-    static bool once[64] = {};
-    {   // the opt-in shared-memory limit is process-wide state of the kernel: raised once, to the device maximum
-        std::lock_guard<std::mutex> lock(once_mu);
-        if (!once[g->device & 63]) {
-            CUDA_TRY(cudaFuncSetAttribute(k_mc_uf_fast<TW, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_smem));
-            CUDA_TRY(cudaFuncSetAttribute(k_mc_uf_fast<TW, ADJ>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            once[g->device & 63] = true;
-        }
+    if (int rc = raise_smem_limit(g->device, g->max_smem, k_mc_uf_fast<TW, ADJ>)) return rc;
+    {
+        static std::atomic<bool> carved{false};
+        if (!carved.exchange(true)) CUDA_TRY(cudaFuncSetAttribute(k_mc_uf_fast<TW, ADJ>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     const size_t smem = (size_t)plan.adj_bytes + (size_t)plan.spb * fl.bytes;
     long long blocks = (long long)g->sm_count * plan.bps;
@@ -957,6 +1062,9 @@ static int fast_launch(luf_graph* g, const FastPlan& plan, const fast::FLayout& 
 #undef LUF_FAST_TW
 }
 
+// *_host entry points on stream 0: no asynchronous copy into a caller's buffer outlives the call, error or not
+struct DrainDefaultStream { ~DrainDefaultStream() { cudaStreamSynchronize(0); } };
+
 static int check_device(void)
 {
     int n = 0;
@@ -976,7 +1084,7 @@ struct luf_stream {
     std::vector<void*> allocs;
     void* scratch[5] = {0, 0, 0, 0, 0};
     size_t scratch_bytes[5] = {0, 0, 0, 0, 0};
-    long long launches = 0;
+    std::atomic<long long> launches{0};
     std::mutex mu;
 };
 
@@ -1014,7 +1122,7 @@ static int plan_stream_launch(luf_stream* g, K kernel, long long nstreams, Launc
     int wpb = g->max_smem / (int)bytes;
     if (wpb > 4) wpb = 4;
     const size_t smem = (size_t)wpb * bytes;
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = raise_smem_limit(g->device, g->max_smem, kernel)) return rc;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * WARP, smem));
@@ -1039,7 +1147,7 @@ static int plan_stream_cta_launch(luf_stream* g, K kernel, long long nstreams, L
         return fail(LUF_ERR_UNSUPPORTED, "one window's decoder state (" + std::to_string(bytes) +
                     " B) exceeds the shared memory of an SM");
     const int env_threads = getenv("LUF_SF_CTA_THREADS") ? atoi(getenv("LUF_SF_CTA_THREADS")) : 0;
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (int rc = raise_smem_limit(g->device, g->max_smem, kernel)) return rc;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     cudaFuncAttributes attr;
     CUDA_TRY(cudaFuncGetAttributes(&attr, kernel));
@@ -1142,7 +1250,7 @@ int luf_stream_destroy(luf_stream* g)
     return 0;
 }
 
-int64_t luf_stream_launch_count(const luf_stream* g) { return g ? g->launches : 0; }
+int64_t luf_stream_launch_count(const luf_stream* g) { return g ? g->launches.load() : 0; }
 
 int luf_stream_decode(luf_stream* g, int flags, int64_t nstreams, int32_t ncycles, const uint32_t* fresh_bits_dev,
                       int32_t* rt_dev, uint32_t* floor_bits_dev, int32_t* m_dev, void* stream)
@@ -1229,6 +1337,7 @@ int luf_stream_decode_host(luf_stream* g, int flags, int64_t nstreams, int32_t n
     if (nstreams == 0 || ncycles == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     const size_t rows = (size_t)nstreams * ncycles, W = g->view.ELw;
     void *fr, *rt, *fl = nullptr, *mm;
     int rc;
@@ -1253,6 +1362,7 @@ int luf_stream_mc_host(luf_stream* g, int flags, const double* class_p_host, uin
     if (nstreams == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     void *cnt, *st = nullptr;
     int rc;
     if ((rc = scratch_s(g, 4, 32, &cnt))) return rc;
@@ -1301,6 +1411,7 @@ int luf_stream_latency_host(luf_stream* g, int flags, const double* class_p_host
     if (nstreams == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     void* lat;
     int rc;
     if ((rc = scratch_s(g, 1, (size_t)nstreams * 12, &lat))) return rc;
@@ -1417,7 +1528,7 @@ int luf_graph_words(const luf_graph* g, int32_t* edge_words, int32_t* detector_w
     return 0;
 }
 
-int64_t luf_launch_count(const luf_graph* g) { return g ? g->launches : 0; }
+int64_t luf_launch_count(const luf_graph* g) { return g ? g->launches.load() : 0; }
 
 static int check_decoder(const luf_graph* g, int decoder, int flags)
 {
@@ -1567,6 +1678,31 @@ int luf_check(luf_graph* g, int64_t nshots, const uint32_t* err_bits_dev, const 
         CUDA_TRY(cudaGetLastError());
         ++g->launches;
     }
+    return 0;
+}
+
+int luf_count_strings(luf_graph* g, int64_t nshots, const uint32_t* err_bits_dev, const uint32_t* corr_bits_dev,
+                      int32_t* count_dev, unsigned long long* total_dev, void* stream)
+{
+    if (!g || !err_bits_dev || !corr_bits_dev || !total_dev || nshots < 0)
+        return fail(LUF_ERR_INVALID, "luf_count_strings: bad argument");
+    if (nshots == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    const uint32_t slice = align16(2u * (uint32_t)g->view.N);
+    int wpb = g->max_smem / (int)slice;
+    if (wpb < 1) return fail(LUF_ERR_UNSUPPORTED, "luf_count_strings: the partner map of one shot exceeds the shared memory of an SM");
+    if (wpb > 8) wpb = 8;
+    if (int rc = raise_smem_limit(g->device, g->max_smem, k_count_strings)) return rc;
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count_strings, wpb * WARP, (size_t)wpb * slice));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)g->sm_count * per_sm;
+    const long long need = (nshots + wpb - 1) / wpb;
+    if (blocks > need) blocks = need;
+    k_count_strings<<<(int)blocks, wpb * WARP, (size_t)wpb * slice, (cudaStream_t)stream>>>(
+        g->view, nshots, err_bits_dev, corr_bits_dev, count_dev, total_dev, slice);
+    CUDA_TRY(cudaGetLastError());
+    ++g->launches;
     return 0;
 }
 
@@ -1763,6 +1899,7 @@ int luf_forward_decode_host(luf_graph* g, int decoder, int flags, int64_t nstrea
     if (nstreams == 0 || ncycles == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     const size_t rows = (size_t)nstreams * ncycles, W = g->view.WE;
     void *ib, *fr, *st, *cm = nullptr, *mm;
     int rc;
@@ -1789,6 +1926,7 @@ int luf_forward_mc_host(luf_graph* g, int decoder, int flags, const double* clas
     if (nstreams == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     void *cnt, *st = nullptr;
     int rc;
     if ((rc = scratch_get(g, 0, 32, &cnt))) return rc;
@@ -1816,6 +1954,7 @@ int luf_mc_run_logical_host(luf_graph* g, int decoder, int flags, const double* 
     if (!g || !counts_host || nshots < 0) return fail(LUF_ERR_INVALID, "luf_mc_run_host: bad argument");
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     void *d = nullptr, *lg = nullptr;
     if (int rc = scratch_get(g, 0, 32, &d)) return rc;
     if (logical_host && nshots > 0)
@@ -1841,6 +1980,7 @@ int luf_decode_batch_host(luf_graph* g, int decoder, int flags, int64_t nshots, 
     if (nshots == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     const size_t n = (size_t)nshots, WE = g->view.WE, WD = g->view.WD, GW = (g->view.E + 15) / 16;
     void *syn, *corr, *gr = nullptr, *st_dev = nullptr;
     int rc;
@@ -1852,6 +1992,12 @@ int luf_decode_batch_host(luf_graph* g, int decoder, int flags, int64_t nshots, 
     // are asynchronous when the caller's buffers are page-locked, staged by the driver otherwise).
     const size_t chunk = (size_t)1 << 16;
     for (cudaStream_t& st : g->pipe) if (!st) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    // whatever happens after the first enqueue, every pipe stream is drained before the call returns: the
+    // copies in flight write into the caller's buffers and into scratch the next call may reallocate
+    struct Drain {
+        luf_graph* g;
+        ~Drain() { for (cudaStream_t st : g->pipe) if (st) cudaStreamSynchronize(st); }
+    } drain{g};
     int k = 0;
     for (size_t lo = 0; lo < n; lo += chunk, ++k) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
@@ -1877,6 +2023,7 @@ int luf_sample_host(luf_graph* g, const double* class_p_host, uint64_t seed, uin
     if (nshots == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     const size_t n = (size_t)nshots, WE = g->view.WE, WD = g->view.WD;
     void *err, *syn;
     int rc;
@@ -1895,6 +2042,7 @@ int luf_sample_weight_host(luf_graph* g, int32_t weight, uint64_t seed, uint64_t
     if (nshots == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     const size_t n = (size_t)nshots, WE = g->view.WE, WD = g->view.WD;
     void *err, *syn;
     int rc;
@@ -1914,6 +2062,7 @@ int luf_check_host(luf_graph* g, int64_t nshots, const uint32_t* err_bits_host, 
     if (nshots == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     const size_t n = (size_t)nshots, WE = g->view.WE;
     void *err, *corr, *lg, *cnt;
     int rc;
@@ -2045,7 +2194,7 @@ int luf_dcs_run(luf_dcs* g, int64_t nshots, const uint32_t* growth2b_dev, int64_
     const size_t bytes = 8u * (size_t)g->view.N + 4u * (size_t)g->view.WN + 4u * (size_t)((g->view.E + 15) / 16) + 16u;
     if (bytes > (size_t)g->max_smem)
         return fail(LUF_ERR_UNSUPPORTED, "confidence scores: one shot's distances (" + std::to_string(bytes) + " B) exceed the shared memory of an SM");
-    CUDA_TRY(cudaFuncSetAttribute(k_dcs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (int rc = raise_smem_limit(g->device, g->max_smem, k_dcs)) return rc;
     int per_sm = 0;
     // 128 threads per growth state measured best on cfg3 (4.8 ms per 65536 states; 64: 5.9, 256: 5.8)
     int threads = getenv("LUF_DCS_THREADS") ? atoi(getenv("LUF_DCS_THREADS")) : 128;
@@ -2068,6 +2217,7 @@ int luf_dcs_run_host(luf_dcs* g, int64_t nshots, const uint32_t* growth2b_host, 
     if (nshots == 0) return 0;
     std::lock_guard<std::mutex> lock(g->mu);
     CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
     const size_t n = (size_t)nshots;
     const size_t want[4] = {n * (size_t)stride_words * 4, n * 8, n * 8, n * 4};
     for (int i = 0; i < 4; ++i)

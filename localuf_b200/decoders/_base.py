@@ -51,7 +51,7 @@ class Decoder:
         rank, size = dist.world()
         seed = self._draw_seed(seed)
         if size > 1:
-            seed = dist.allreduce_counts([seed if rank == 0 else 0])[0]   # rank 0's seed for everybody
+            seed = dist.allreduce_counts([seed if rank == 0 else 0], device=f'cuda:{self.engine.device}')[0]   # rank 0's seed for everybody
         lo, cnt = dist.shard(n, rank, size)
         fails, shots = run_local(seed, lo, cnt) if cnt else (0, 0)
         fails, shots = dist.allreduce_counts([fails, shots], device=f'cuda:{self.engine.device}')
@@ -71,14 +71,29 @@ class Decoder:
         flat, noise = self._CODE.FLAT, self._CODE.NOISE
         rank, size = dist.world()
         lo, cnt = dist.shard(n, rank, size)
+        # the forcers draw from Python's global `random` stream like the reference (noise/forcers.py).  One rank:
+        # that stream as it stands (or seeded with `seed`).  Several ranks: every rank would draw the SAME errors
+        # from equally seeded streams and the all-reduced count would hold each shot `size` times, so each rank
+        # draws from its own stream derived from rank 0's seed, and the caller's stream is put back afterwards.
+        state = None
+        if size > 1 or seed is not None:
+            seed = self._draw_seed(seed)
+            if size > 1:
+                seed = dist.allreduce_counts([seed if rank == 0 else 0], device=f'cuda:{eng.device}')[0]
+            state = random.getstate()
+            random.seed(seed * 1_000_003 + rank)
         fails, done = 0, 0
-        while done < cnt:
-            k = min(4096, cnt - done)
-            errors = [noise.force_error(weight) for _ in range(k)]
-            err = np.stack([flat.edges_to_bits(e) for e in errors])
-            syn = np.stack([flat.syndrome_to_bits(self._CODE.get_syndrome(e)) for e in errors])
-            fails += eng.mc_given_errors(self._DECODER_ID, self._flags, err, syn)[0]
-            done += k
+        try:
+            while done < cnt:
+                k = min(4096, cnt - done)
+                errors = [noise.force_error(weight) for _ in range(k)]
+                err = np.stack([flat.edges_to_bits(e) for e in errors])
+                syn = np.stack([flat.syndrome_to_bits(self._CODE.get_syndrome(e)) for e in errors])
+                fails += eng.mc_given_errors(self._DECODER_ID, self._flags, err, syn)[0]
+                done += k
+        finally:
+            if state is not None:
+                random.setstate(state)
         return dist.allreduce_counts([fails], device=f'cuda:{eng.device}')[0]
 
     def subset_sample(self, noise_level: float, n: int, tol: float = 5e-1, **kwargs):
@@ -107,19 +122,17 @@ class Decoder:
 
     def _mc_global(self, noise_level: float, shots: int = 1, seed=None):
         """``shots`` windows of the global batch scheme (``_schemes.py:186-203``): sampled and
-        decoded on the device, the logical error strings of each leftover counted on the host."""
+        decoded on the device, the logical error strings of each leftover counted there too
+        (``luf_count_strings``: the in-kernel ``Pairs`` of the forward scheme, ascending edge id)."""
         eng = self.engine
         rank, size = dist.world()
         seed = self._draw_seed(seed)
         if size > 1:
-            seed = dist.allreduce_counts([seed if rank == 0 else 0])[0]
+            seed = dist.allreduce_counts([seed if rank == 0 else 0], device=f'cuda:{eng.device}')[0]
         lo, cnt = dist.shard(shots, rank, size)
         total = 0
-        if cnt:
-            err, syn = eng.sample_host(noise_level, seed, lo, cnt)
-            corr, _, _ = eng.decode_batch_host(self._DECODER_ID, self._flags, syn, want_steps=False)
-            for leftover in err ^ corr:
-                total += self._CODE.SCHEME.count_leftover_bits(leftover)
+        if cnt:           # sample -> decode -> count strings, all on the device (luf_count_strings)
+            total = eng.mc_global(self._DECODER_ID, self._flags, noise_level, seed, lo, cnt)
         return dist.allreduce_counts([total], device=f'cuda:{eng.device}')[0]
 
     def _mc_forward(self, noise_level: float, n: int, shots: int = 1, seed=None, draw=False, log_history=False,
@@ -132,7 +145,7 @@ class Decoder:
         rank, size = dist.world()
         seed = self._draw_seed(seed)
         if size > 1:
-            seed = dist.allreduce_counts([seed if rank == 0 else 0])[0]
+            seed = dist.allreduce_counts([seed if rank == 0 else 0], device=f'cuda:{eng.device}')[0]
         lo, cnt = dist.shard(shots, rank, size)
         counts, steps = ([0, 0, 0, 0], None)
         if cnt:

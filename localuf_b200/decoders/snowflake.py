@@ -274,7 +274,7 @@ class Snowflake(Decoder):
         rank, size = dist.world()
         seed = self._draw_seed(seed)
         if size > 1:
-            seed = dist.allreduce_counts([seed if rank == 0 else 0])[0]
+            seed = dist.allreduce_counts([seed if rank == 0 else 0], device=f'cuda:{eng.device}')[0]
         lo, cnt = dist.shard(shots, rank, size)
         out = np.zeros((shots, 3), np.int64)
         if cnt:
@@ -308,7 +308,7 @@ class Snowflake(Decoder):
         rank, size = dist.world()
         seed = self._draw_seed(seed)
         if size > 1:
-            seed = dist.allreduce_counts([seed if rank == 0 else 0])[0]
+            seed = dist.allreduce_counts([seed if rank == 0 else 0], device=f'cuda:{eng.device}')[0]
         lo, cnt = dist.shard(shots, rank, size)
         if cnt and metrics:
             # Frugal.run(metrics=...) (_schemes.py:636-644): the scores of every timed cycle, stream after

@@ -35,7 +35,10 @@ def allreduce_counts(values, device=None):
     import torch
     import torch.distributed as dist
     if dist.get_backend() == 'nccl':        # NCCL reduces device tensors only
-        dev = device if device is not None else f'cuda:{torch.cuda.current_device()}'
+        # no device given: the one the engines pick by default (LOCAL_RANK), not torch's current device --
+        # under torchrun that is cuda:0 on every rank unless the caller set it, and NCCL then sees one GPU twice
+        import os
+        dev = device if device is not None else f"cuda:{int(os.environ.get('LOCAL_RANK', torch.cuda.current_device())) % max(torch.cuda.device_count(), 1)}"
     else:
         dev = 'cpu'
     t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)

@@ -1,2 +1,2 @@
 from localuf_b200.sim.accuracy.monte_carlo import (  # noqa: F401
-    monte_carlo, monte_carlo_results_to_sample_counts, subset_sample)
+    monte_carlo, monte_carlo_results_to_sample_counts, monte_carlo_special, subset_sample)

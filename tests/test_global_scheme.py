@@ -58,6 +58,8 @@ def test_device_decode_and_count(name):
             np.testing.assert_array_equal(steps, arr['macar_steps'])
         counts = [code.SCHEME.count_leftover_bits(l) for l in arr['err_bits'] ^ corr]
         np.testing.assert_array_equal(counts, arr[f'{key}_count'])
+        # the device counts the strings itself (luf_count_strings): per window, equal to the reference's count
+        np.testing.assert_array_equal(eng.count_strings_host(arr['err_bits'], corr), arr[f'{key}_count'])
     # Global.run end to end: device-sampled windows, rate near the goldens' (loose 6 sigma bound)
     uf = L.decoders.UF(code)
     shots = 400
@@ -65,6 +67,12 @@ def test_device_decode_and_count(name):
     assert slender == meta['n'] * shots
     mean = arr['uf_count'].mean()
     assert abs(m / shots - mean) < 6 * (max(arr['uf_count'].var(), 0.05) * (1 / shots + 1 / len(arr['uf_count']))) ** 0.5 + 0.05
+    # ... and the per-window counts of a device-sampled run equal the host mirror's on the same windows
+    total, per = eng.mc_global(_engine.DEC_UF, 0, meta['p'], 5, 0, 300, chunk=128, want_counts=True)
+    err, syn2 = eng.sample_host(meta['p'], 5, 0, 300)
+    corr2, _, _ = eng.decode_batch_host(_engine.DEC_UF, 0, syn2, want_steps=False)
+    np.testing.assert_array_equal(per, [code.SCHEME.count_leftover_bits(l) for l in err ^ corr2])
+    assert total == int(per.sum())
     # sim.accuracy.monte_carlo takes the scheme by name, like the reference (window height = d * n)
     df = L.sim.accuracy.monte_carlo({code.D: [(meta['p'], meta['n'])]}, type(code), L.decoders.UF,
                                     meta['spec']['noise'], scheme='global batch')
