@@ -1027,7 +1027,7 @@ static int fast_queue(luf_graph* g, void* stream, uint32_t** out)
 }
 
 template <int TW, bool ADJ>
-static int fast_launch_t(luf_graph* g, const FastPlan& plan, const fast::FLayout& fl, const SampleParams& sp,
+static int fast_launch_t(luf_graph* g, const fast::FView& fv, const FastPlan& plan, const fast::FLayout& fl, const SampleParams& sp,
                          unsigned long long shot0, long long nshots, unsigned long long* counts, uint8_t* logical,
                          uint32_t* queue, uint32_t* qcount, cudaStream_t stream)
 {
@@ -1043,18 +1043,18 @@ static int fast_launch_t(luf_graph* g, const FastPlan& plan, const fast::FLayout
     if (getenv("LUF_DEBUG_PLAN"))
         fprintf(stderr, "[luf] fast plan: %u B per shot (lists %u / %u / %u), tile %d, %d shots per block, %d blocks per SM, adjacency %s (%u B), %zu B of shared memory per block\n",
                 fl.bytes, fl.tcap, fl.acap, fl.mcap, plan.tw, plan.spb, plan.bps, plan.adj_shared ? "shared" : "global", plan.adj_bytes, smem);
-    k_mc_uf_fast<TW, ADJ><<<(int)blocks, plan.spb * TW, smem, stream>>>(g->fview, fl, plan.adj_bytes, sp, shot0, nshots, counts,
+    k_mc_uf_fast<TW, ADJ><<<(int)blocks, plan.spb * TW, smem, stream>>>(fv, fl, plan.adj_bytes, sp, shot0, nshots, counts,
                                                                       logical, queue, qcount);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-static int fast_launch(luf_graph* g, const FastPlan& plan, const fast::FLayout& fl, const SampleParams& sp,
+static int fast_launch(luf_graph* g, const fast::FView& fv, const FastPlan& plan, const fast::FLayout& fl, const SampleParams& sp,
                        unsigned long long shot0, long long nshots, unsigned long long* counts, uint8_t* logical,
                        uint32_t* queue, uint32_t* qcount, cudaStream_t stream)
 {
-#define LUF_FAST_TW(T) case T: return plan.adj_shared ? fast_launch_t<T, true>(g, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream) \
-                                                      : fast_launch_t<T, false>(g, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream);
+#define LUF_FAST_TW(T) case T: return plan.adj_shared ? fast_launch_t<T, true>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream) \
+                                                      : fast_launch_t<T, false>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream);
     switch (plan.tw) {
         LUF_FAST_TW(8) LUF_FAST_TW(16) LUF_FAST_TW(32) LUF_FAST_TW(64) LUF_FAST_TW(128) LUF_FAST_TW(256)
         default: return fail(LUF_ERR_INVALID, "fast path: tile width must be 8, 16, 32, 64, 128 or 256");
@@ -1772,12 +1772,16 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                     const long long m = std::min<long long>(FAST_CHUNK, nshots - done);
                     const unsigned long long first = shot0 + (unsigned long long)done;
                     uint8_t* lg = logical_dev ? logical_dev + done : nullptr;
-                    CUDA_TRY(cudaMemsetAsync(qcount, 0, 4, (cudaStream_t)stream));
-                    if (int rc = fast_launch(g, plan, fl, sp, first, m, counts_dev, lg, queue, qcount, (cudaStream_t)stream)) return rc;
-                    if (flags & LUF_UF_WEST) LUF_MC_UF_ANY(2, true, first, m, lg, queue, qcount)
-                    else LUF_MC_UF_ANY(0, true, first, m, lg, queue, qcount)
-                    CUDA_TRY(cudaGetLastError());
-                    g->launches += 2;
+                    fast::FView fv = g->fview;
+                    fv.west = (flags & LUF_UF_WEST) ? 1 : 0;
+                    if (!fv.west) CUDA_TRY(cudaMemsetAsync(qcount, 0, 4, (cudaStream_t)stream));
+                    if (int rc = fast_launch(g, fv, plan, fl, sp, first, m, counts_dev, lg, queue, qcount, (cudaStream_t)stream)) return rc;
+                    ++g->launches;
+                    if (!fv.west) {             // (the west inclination leaves no HARD shots: luf_uf_fast.cuh)
+                        LUF_MC_UF_ANY(0, true, first, m, lg, queue, qcount)
+                        CUDA_TRY(cudaGetLastError());
+                        ++g->launches;
+                    }
                 }
                 return 0;
             }

@@ -23,10 +23,14 @@
 // interleaving.  Every change of a root word is one atomic transition, and each one adjusts the count of
 // active clusters (odd, no boundary) by the difference it makes -- the round loop ends when that count is 0.
 //
-// A shot that cannot be finished here -- a cluster touches both sides (the peeling forest matters), or a work
-// list overflows -- is reported as HARD; the caller queues it for the canonical kernel.  The state of a cfg3
-// shot is 4.8 KB instead of 8.9 KB, and nothing in a shot's loops reads global memory when the adjacency table
-// is staged in shared memory.
+// A shot in which a cluster comes to touch both sides is reported as HARD under the default inclination (which
+// boundary node roots the peeling tree depends on the merge order); the caller queues it for the canonical
+// kernel.  Under the west inclination (uf.py:544-549) such a cluster keeps a west boundary node; that node has
+// one edge, every defect's path to the root runs through it, so the cluster adds its defect parity like any
+// other that touches the west side -- no HARD shots at all.  A work list that overflows is not fatal either:
+// its consumers walk the bitmap behind it (touched nodes, defects) or the growth words themselves (fully grown
+// edges; joining an edge twice is harmless).  The state of a cfg3 shot is about 5 KB instead of 8.9 KB, and
+// nothing in a shot's loops reads global memory when the adjacency table is staged in shared memory.
 //
 // The tile of `nl` cooperating lanes may be a part of a warp (8 / 16 lanes: several shots advance through the
 // same instructions), a warp, or several warps of a block (named barrier); the only tile operation is the
@@ -42,11 +46,11 @@ static const uint32_t P_FRESH = P_ROOT;                  // an untouched detecto
 static const uint32_t P_ACTIVE = P_ROOT | P_ODD;         // odd and no boundary (uf.py:296-301)
 static const uint32_t OTHER_WEST = 0x7FFFu, OTHER_EAST = 0x7FFEu;     // adjacency entry: the other end is a boundary node
 static const uint32_t END_WEST = 0xFFFFu, END_EAST = 0xFFFEu;         // edge table / merge list: ditto, 16-bit form
-// cnt[]: fill counters of the three lists (they only grow: a round's entries start at the previous total), the
-// number of active clusters, the parity accumulator, and two HARD flags -- one written by the growth phases
-// (a list overflowed), one by the merge phase (a cluster touches both sides) -- so that a flag is never
-// written by the phase that follows the barrier after which it is read.
-enum { C_TOUCHED = 0, C_ALIST = 1, C_MLIST = 2, C_ACTIVE = 3, C_HARD_G = 4, C_PARITY = 5, C_HARD_M = 6 };
+// cnt[]: fill counters of the three lists (they only grow: a round's entries start at the previous total; a
+// counter beyond its capacity says the list overflowed), the number of active clusters, the parity
+// accumulator, and the HARD flag (a cluster touches both sides; written by the merge phase only, read after
+// the barrier that ends it -- never written by the phase that follows).
+enum { C_TOUCHED = 0, C_ALIST = 1, C_MLIST = 2, C_ACTIVE = 3, C_PARITY = 5, C_HARD_M = 6 };
 static const uint32_t HARD = 2u;                         // result of a shot the canonical kernel has to decode
 
 // Read-only tables (global memory; fadj optionally staged in shared memory by the kernel).
@@ -57,6 +61,7 @@ struct FView {
     int F, n_classes;
     const uint16_t* fresh_perm; // as GraphView
     const uint32_t* class_end;
+    int west;                   // west inclination: a cluster on both sides is not HARD
 };
 
 struct FLayout {
@@ -132,7 +137,7 @@ LUF_DEV uint32_t ffind(const FShot& s, uint32_t v, uint32_t& wr)
 }
 
 // Add (odd, west, east) bits to the root of v's tree.
-LUF_DEV void add_bits(const FShot& s, uint32_t v, uint32_t bits)
+LUF_DEV void add_bits(const FShot& s, uint32_t v, uint32_t bits, int west)
 {
     LUF_NOUNROLL
     for (;;) {
@@ -143,7 +148,7 @@ LUF_DEV void add_bits(const FShot& s, uint32_t v, uint32_t bits)
         if (cas16(s.P, r, w, nw)) {
             const int delta = (nw == P_ACTIVE ? 1 : 0) - (w == P_ACTIVE ? 1 : 0);
             if (delta) luf_atomic_add(&s.cnt[C_ACTIVE], (uint32_t)delta);
-            if ((nw & (P_WEST | P_EAST)) == (P_WEST | P_EAST)) s.cnt[C_HARD_M] = 1u;    // both sides: the forest matters
+            if (!west && (nw & (P_WEST | P_EAST)) == (P_WEST | P_EAST)) s.cnt[C_HARD_M] = 1u;    // both sides: the forest matters
             return;
         }
         v = r;
@@ -151,7 +156,7 @@ LUF_DEV void add_bits(const FShot& s, uint32_t v, uint32_t bits)
 }
 
 // uf.py:256-280 without the order: join the clusters of detectors a and b.
-LUF_DEV void join(const FShot& s, uint32_t a, uint32_t b)
+LUF_DEV void join(const FShot& s, uint32_t a, uint32_t b, int west)
 {
     LUF_NOUNROLL
     for (;;) {
@@ -161,7 +166,7 @@ LUF_DEV void join(const FShot& s, uint32_t a, uint32_t b)
         if (ra > rb) { uint32_t t = ra; ra = rb; rb = t; wb = wa; }      // the root of larger index goes below the other
         if (!cas16(s.P, rb, wb, ra)) continue;
         if (wb == P_ACTIVE) luf_atomic_sub(&s.cnt[C_ACTIVE], 1u);
-        if (wb & (P_ODD | P_WEST | P_EAST)) add_bits(s, ra, wb);
+        if (wb & (P_ODD | P_WEST | P_EAST)) add_bits(s, ra, wb, west);
         return;
     }
 }
@@ -228,7 +233,26 @@ LUF_DEV void f_newfull(const FLayout& l, const FShot& s, uint32_t u, uint32_t ot
 {
     const uint32_t idx = luf_atomic_add(&s.cnt[C_MLIST], 1u) - mbase;
     if (idx < l.mcap) s.mlist[idx] = u | ((other >= OTHER_EAST ? other | 0x8000u : other) << 16);
-    else s.cnt[C_HARD_G] = 1u;
+    // else: the counter alone says the list overflowed; the merge phase then reads the growth words
+}
+
+// Run f(v) for the first n entries of the touched list -- or, when the list could not hold them (total beyond
+// its capacity), for every set bit of the bitmap behind it.
+template <class F>
+LUF_DEV void f_for_nodes(const FView& g, const FLayout& l, const FShot& s, const uint32_t* bitmap, uint32_t n, uint32_t total,
+                         int lane, int nl, F f)
+{
+    if (total <= l.tcap) {
+        LUF_NOUNROLL
+        for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) f((uint32_t)s.tlist[i]);
+    } else {
+        LUF_NOUNROLL
+        for (int w = lane; w < g.WD; w += nl) {
+            uint32_t bits = bitmap[w];
+            LUF_NOUNROLL
+            while (bits) { const int b = luf_ffs(bits) - 1; bits &= bits - 1; f((uint32_t)(32 * w + b)); }
+        }
+    }
 }
 
 // Round 1 (uf.py:234-245): every defect adds 1 to each of its edges, no look-ups; an edge is newly FULL iff the
@@ -236,15 +260,13 @@ LUF_DEV void f_newfull(const FLayout& l, const FShot& s, uint32_t u, uint32_t ot
 template <bool ADJ_SHARED>
 LUF_DEV void f_grow_first(const FView& g, const FLayout& l, const FShot& s, uint32_t nd, int lane, int nl)
 {
-    LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < nd; i += (uint32_t)nl) {
-        const uint32_t v = s.tlist[i];
+    f_for_nodes(g, l, s, s.defect, nd, nd, lane, nl, [&](uint32_t v) {
         f_row<ADJ_SHARED>(g, v, [&](uint32_t ent) {
             const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
             const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
             if (old == G_HALF) f_newfull(l, s, v, (ent >> 16) & 0x7FFFu, 0u);
         });
-    }
+    });
 }
 
 LUF_DEV void f_touch(const FLayout& l, const FShot& s, uint32_t v)
@@ -252,7 +274,7 @@ LUF_DEV void f_touch(const FLayout& l, const FShot& s, uint32_t v)
     const uint32_t bit = 1u << (v & 31u);
     if (luf_atomic_or(&s.touched[v >> 5], bit) & bit) return;
     const uint32_t idx = luf_atomic_add(&s.cnt[C_TOUCHED], 1u);
-    if (idx < l.tcap) s.tlist[idx] = (uint16_t)v; else s.cnt[C_HARD_G] = 1u;
+    if (idx < l.tcap) s.tlist[idx] = (uint16_t)v;          // else: the consumers walk the touched bitmap
 }
 
 // Later rounds: a touched node whose cluster (root r) is active adds 1 to each of its edges that is not FULL;
@@ -281,16 +303,14 @@ template <bool ADJ_SHARED>
 LUF_DEV void f_grow_filter(const FView& g, const FLayout& l, const FShot& s, uint32_t nt, uint32_t abase, uint32_t mbase,
                            int lane, int nl)
 {
-    LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < nt; i += (uint32_t)nl) {
-        const uint32_t u = s.tlist[i];
+    f_for_nodes(g, l, s, s.touched, nt, nt, lane, nl, [&](uint32_t u) {
         uint32_t wr;
         const uint32_t r = ffind(s, u, wr);
-        if (wr != P_ACTIVE) continue;
+        if (wr != P_ACTIVE) return;
         const uint32_t idx = luf_atomic_add(&s.cnt[C_ALIST], 1u) - abase;
         if (idx < l.acap) s.alist[idx] = u | (r << 16);
         else f_grow_node<ADJ_SHARED>(g, l, s, u, r, mbase);       // the list is full: grow right away (roots are stable here)
-    }
+    });
 }
 
 template <bool ADJ_SHARED>
@@ -304,28 +324,49 @@ LUF_DEV void f_grow_exec(const FView& g, const FLayout& l, const FShot& s, uint3
     }
 }
 
-// uf.py:223-229 in any order: one lane per newly FULL edge
-LUF_DEV void f_merge(const FShot& s, uint32_t nm, int lane, int nl)
+// uf.py:223-229 in any order: one lane per newly FULL edge.  A round with more of them than the list holds
+// joins every fully grown edge of the growth words instead (an edge joined before is inside one cluster by now:
+// nothing happens), endpoints from the edge table.
+LUF_DEV void f_merge_pair(const FView& g, const FShot& s, uint32_t a, uint32_t b)
 {
+    if (b >= END_EAST) add_bits(s, a, b == END_WEST ? P_WEST : P_EAST, g.west);
+    else join(s, a, b, g.west);
+}
+
+LUF_DEV void f_merge(const FView& g, const FLayout& l, const FShot& s, uint32_t nm, int lane, int nl)
+{
+    if (nm <= l.mcap) {
+        LUF_NOUNROLL
+        for (uint32_t i = (uint32_t)lane; i < nm; i += (uint32_t)nl) {
+            const uint32_t it = s.mlist[i];
+            f_merge_pair(g, s, it & 0xFFFFu, it >> 16);
+        }
+        return;
+    }
+    const int GW = (g.E + 15) >> 4;
     LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < nm; i += (uint32_t)nl) {
-        const uint32_t it = s.mlist[i];
-        const uint32_t a = it & 0xFFFFu, b = it >> 16;
-        if (b >= END_EAST) add_bits(s, a, b == END_WEST ? P_WEST : P_EAST);
-        else join(s, a, b);
+    for (int w = lane; w < GW; w += nl) {
+        const uint32_t x = s.growth[w];
+        uint32_t full = (x >> 1) & 0x55555555u;                   // bit 2k: edge 16 w + k is FULL
+        LUF_NOUNROLL
+        while (full) {
+            const int b = luf_ffs(full) - 1; full &= full - 1;
+            const uint32_t ei = LUF_LDG(&g.einfo[16 * w + (b >> 1)]);
+            const uint32_t u = ei & 0xFFFFu, v = ei >> 16;
+            if (u >= END_EAST) f_merge_pair(g, s, v, u); else f_merge_pair(g, s, u, v);
+        }
     }
 }
 
 // every defect adds 1 iff its cluster touches the west boundary (uf_peel_parity, luf_uf_phases.inl)
-LUF_DEV uint32_t f_defect_sides(const FShot& s, uint32_t nd, int lane, int nl)
+LUF_DEV uint32_t f_defect_sides(const FView& g, const FLayout& l, const FShot& s, uint32_t nd, int lane, int nl)
 {
     uint32_t parity = 0;
-    LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < nd; i += (uint32_t)nl) {
+    f_for_nodes(g, l, s, s.defect, nd, nd, lane, nl, [&](uint32_t v) {
         uint32_t wr;
-        ffind_ro(s, s.tlist[i], wr);
+        ffind_ro(s, v, wr);
         parity ^= (wr >> 1) & 1u;
-    }
+    });
     return parity;
 }
 
@@ -365,18 +406,16 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
     FT_PHASE(f_load(g, l, s, lane, nl));
     const uint32_t nd = s.cnt[C_TOUCHED];
     uint32_t rounds = 0, abase = 0, mbase = 0, most_m = 0, most_a = 0;
-    if (nd > l.tcap) return HARD;                        // (uniform: every lane reads the same counter)
     if (nd) {
         FT_PHASE(if (lane == 0) s.cnt[C_ACTIVE] = nd; f_grow_first<ADJ_SHARED>(g, l, s, nd, lane, nl));
         LUF_NOUNROLL
         for (;;) {
             ++rounds;
             const uint32_t nm = s.cnt[C_MLIST] - mbase;
-            if (s.cnt[C_HARD_G]) return HARD;
             if (nm > most_m) most_m = nm;
-            FT_PHASE(f_merge(s, nm, lane, nl));
+            FT_PHASE(f_merge(g, l, s, nm, lane, nl));
             mbase += nm;
-            if (s.cnt[C_HARD_M]) return HARD;
+            if (s.cnt[C_HARD_M]) return HARD;            // (uniform: every lane reads the same word after the barrier)
             if (!s.cnt[C_ACTIVE]) break;
             const uint32_t nt = s.cnt[C_TOUCHED];
             FT_PHASE(f_grow_filter<ADJ_SHARED>(g, l, s, nt, abase, mbase, lane, nl));
@@ -385,7 +424,7 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
             FT_PHASE(f_grow_exec<ADJ_SHARED>(g, l, s, na, mbase, lane, nl));
             abase += na;
         }
-        FT_PHASE(const uint32_t par = f_defect_sides(s, nd, lane, nl); if (par) luf_atomic_xor(&s.cnt[C_PARITY], 1u));
+        FT_PHASE(const uint32_t par = f_defect_sides(g, l, s, nd, lane, nl); if (par) luf_atomic_xor(&s.cnt[C_PARITY], 1u));
     }
     if (stats) { stats[0] = rounds; stats[1] = s.cnt[C_TOUCHED]; stats[2] = most_m; stats[3] = most_a; }
     return s.cnt[C_PARITY] & 1u;

@@ -238,10 +238,10 @@ int emu_mc_uf_fast(const luf_graph_desc* d, int flags, const double* class_p, un
 }
 
 // The compact fast path of the fused kernels (luf_uf_fast.cuh) with a tile of `nl` lanes: out[k] = 0 / 1 (the
-// logical bit) or 2 (HARD: a cluster touches both sides or a list overflowed -- the kernel queues such shots for
-// the canonical path); stats (optional) [nshots][4] = rounds, touched nodes, most newly FULL edges of a round,
+// logical bit) or 2 (HARD: a cluster touches both sides under the default inclination -- the kernel queues such
+// shots for the canonical path; never under the west inclination); stats (optional) [nshots][4] = rounds, touched nodes, most newly FULL edges of a round,
 // most active nodes of a round.  mu < 0: list capacities from the class probabilities, as the library does.
-int emu_mc_uf_compact(const luf_graph_desc* d, const double* class_p, unsigned long long seed, unsigned long long shot0,
+int emu_mc_uf_compact(const luf_graph_desc* d, int west, const double* class_p, unsigned long long seed, unsigned long long shot0,
                       long long nshots, int nl, double mu, uint8_t* out, uint32_t* stats)
 {
     PackedGraph p;
@@ -257,6 +257,7 @@ int emu_mc_uf_compact(const luf_graph_desc* d, const double* class_p, unsigned l
     g.D = pf.D; g.E = p.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
     g.F = p.F; g.n_classes = p.n_classes;
     g.fresh_perm = p.perm_identity ? nullptr : p.fresh_perm.data(); g.class_end = p.class_end.data();
+    g.west = west;
     const fast::FLayout l = make_fast_layout(pf.D, p.E, pf.DEG, mu);
     const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
     std::vector<unsigned char> mem(l.bytes + 16);

@@ -139,15 +139,15 @@ class Emu:
         assert rc == 0, rc
         return tuple(int(x) for x in counts)
 
-    def mc_uf_compact(self, noise_level, seed, shot0, nshots, nl=32, mu=-1.0, want_stats=False):
+    def mc_uf_compact(self, noise_level, seed, shot0, nshots, nl=32, mu=-1.0, want_stats=False, west=False):
         """The compact fast path (luf_uf_fast.cuh): per shot 0 / 1 = logical bit, 2 = HARD (queued for the
-        canonical kernel); stats [nshots, 4] = rounds, touched nodes, most newly FULL edges / active nodes of a round."""
+        canonical kernel; none with ``west``); stats [nshots, 4] = rounds, touched nodes, most newly FULL edges / active nodes of a round."""
         cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
         out = np.zeros(nshots, np.uint8)
         stats = np.zeros((nshots, 4), np.uint32) if want_stats else None
-        lib().emu_mc_uf_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_longlong, C.c_int,
+        lib().emu_mc_uf_compact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_longlong, C.c_int,
                                             C.c_double, C.c_void_p, C.c_void_p]
-        rc = lib().emu_mc_uf_compact(C.addressof(self.desc), _vp(cp), seed, shot0, nshots, nl, float(mu), _vp(out), _vp(stats))
+        rc = lib().emu_mc_uf_compact(C.addressof(self.desc), int(west), _vp(cp), seed, shot0, nshots, nl, float(mu), _vp(out), _vp(stats))
         assert rc == 0, rc
         return (out, stats) if want_stats else out
 

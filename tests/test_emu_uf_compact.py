@@ -43,29 +43,37 @@ def canonical_bits(code, p, seed, shot0, n):
     return emu, orc.logical_batch(err, ocorr)
 
 
+def canonical_west_bits(code, p, seed, shot0, n):
+    emu = emu_binding.Emu(code)
+    orc = binding.Oracle.from_code(code)
+    _, err, syn, _ = emu.mc_uf(0, p, seed, shot0, n)
+    corr, _, _ = orc.decode_batch(0, 2, syn)
+    return orc.logical_batch(err, corr)
+
+
 @pytest.mark.parametrize('spec,p,n', CASES, ids=lambda x: f"{x['code']}{x['d']}-{x['noise'].split()[0]}" if isinstance(x, dict) else str(x))
 def test_compact_path_is_never_wrong(spec, p, n):
     code = make_code(spec)
     emu, want = canonical_bits(code, p, 11, 100, n)
-    _, _, _, mixed, _ = emu.mc_uf_fast(0, p, 11, n) if False else (0, 0, 0, None, 0)
     hard_by_tile = {}
     for nl in (8, 16, 32, 64, 256):
-        out = emu.mc_uf_compact(p, 11, 100, n, nl=nl, mu=1e6)          # lists that hold everything: HARD = spans both sides
-        hard = out == 2
+        out = emu.mc_uf_compact(p, 11, 100, n, nl=nl, mu=1e6)          # lists that hold everything
+        hard = out == 2                                                # HARD = a cluster touches both sides
         np.testing.assert_array_equal(out[~hard], want[~hard])
         hard_by_tile[nl] = hard
     for nl in (8, 16, 64, 256):                                        # which shots are HARD does not depend on the tile
         np.testing.assert_array_equal(hard_by_tile[nl], hard_by_tile[32])
-    # the library's list capacities (from the expected number of faults): a few more HARD shots, no wrong ones
-    out = emu.mc_uf_compact(p, 11, 100, n, nl=16)
-    more = out == 2
-    assert np.all(more[hard_by_tile[32]])
-    np.testing.assert_array_equal(out[~more], want[~more])
-    assert more.sum() - hard_by_tile[32].sum() <= max(3, n // 100)
-    # starved lists: nearly everything overflows, still nothing wrong
-    out = emu.mc_uf_compact(p, 11, 100, n, nl=32, mu=0.0)
-    tiny = out == 2
-    np.testing.assert_array_equal(out[~tiny], want[~tiny])
+    # the library's list capacities (from the expected number of faults), and starved lists where every list
+    # overflows in nearly every shot: the consumers fall back on the bitmaps / growth words -- same bits, same HARD shots
+    for mu, nl in ((-1.0, 16), (0.0, 32), (0.0, 8)):
+        out = emu.mc_uf_compact(p, 11, 100, n, nl=nl, mu=mu)
+        np.testing.assert_array_equal(out == 2, hard_by_tile[32])
+        np.testing.assert_array_equal(out[~hard_by_tile[32]], want[~hard_by_tile[32]])
+    # west inclination: never HARD, and the bit of the canonical west decode on every shot
+    want_west = canonical_west_bits(code, p, 11, 100, n)
+    for mu, nl in ((-1.0, 16), (0.0, 32), (1e6, 64)):
+        out = emu.mc_uf_compact(p, 11, 100, n, nl=nl, mu=mu, west=True)
+        np.testing.assert_array_equal(out, want_west)
 
 
 def test_compact_path_west_and_default_share_the_fast_result():
