@@ -266,6 +266,7 @@ struct SampleTab {
     int F, n_classes;
     const uint16_t* perm;       // [F]
     const uint32_t* class_end;  // [n_classes]
+    const uint32_t* perm32;     // [F] instead of perm, for graphs of more than 65535 edges (compact fast path only); else null
 };
 
 // Each lane owns a contiguous range of the class-sorted edge list and walks it
@@ -306,7 +307,7 @@ LUF_DEV uint32_t ph_sample_core(const SampleTab& t, const SampleParams& sp, uint
                 if (gap >= hi - pos) break;
                 pos += gap;
             }
-            const uint32_t e = t.perm ? (uint32_t)LUF_LDG(&t.perm[pos]) : pos;   // no table when the order is the identity
+            const uint32_t e = t.perm32 ? LUF_LDG(&t.perm32[pos]) : t.perm ? (uint32_t)LUF_LDG(&t.perm[pos]) : pos;   // no table when the order is the identity
             if (!skip_mask || !((LUF_LDG(&skip_mask[e >> 5]) >> (e & 31u)) & 1u)) parity ^= flip(e);
             if (++pos >= hi) break;
         }
@@ -326,7 +327,7 @@ LUF_DEV uint32_t ph_sample(const GraphView& g, const Shot& s, const SampleParams
                            uint64_t shot, int lane, int nl)
 {
     SampleTab t;
-    t.F = g.F; t.n_classes = g.n_classes; t.perm = g.fresh_perm; t.class_end = g.class_end;
+    t.F = g.F; t.n_classes = g.n_classes; t.perm = g.fresh_perm; t.class_end = g.class_end; t.perm32 = 0;
     return ph_sample_tab(g, t, s, sp, shot, 0u, (const uint32_t*)0, lane, nl);
 }
 

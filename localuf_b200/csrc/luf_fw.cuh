@@ -250,7 +250,7 @@ LUF_DEV void fw_run(const GraphView& gv, const FwView& g, const FwState& f, cons
                     long long& sum0, long long& sum1, int32_t* steps_out, int lane, int nl)
 {
     SampleTab fresh;
-    fresh.F = gv.F; fresh.n_classes = gv.n_classes; fresh.perm = gv.fresh_perm; fresh.class_end = gv.class_end;
+    fresh.F = gv.F; fresh.n_classes = gv.n_classes; fresh.perm = gv.fresh_perm; fresh.class_end = gv.class_end; fresh.perm32 = 0;
     Shot samp;                                   // the sampler writes the decoder's error / defect bitmaps
     samp.err = d.err(); samp.defect = d.defect();
     // _make_error_in_buffer_region: every buffer edge flips once with its class probability

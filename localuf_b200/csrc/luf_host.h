@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -123,18 +124,34 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr, ui
 // ------------------------------------------------- compact fast path (luf_uf_fast.cuh)
 struct PackedFast {
     bool ok = false;              // the graph allows the compact fast path
-    int D = 0, DEG = 0;
+    int D = 0, DEG = 0, E = 0, F = 0, n_classes = 0;
+    uint32_t ebits = 16, emask = 0xFFFFu, omask = 0x7FFFu;
     std::vector<uint32_t> fadj, einfo;
+    // sampler tables of graphs too large for the 16-bit layout (pack_graph refuses them): the compact path is
+    // then the only one, and brings its own
+    std::vector<uint32_t> fresh_perm32, class_end, west_mask;
+    bool perm_identity = false;
 };
 
-// The compact tables index detectors only.  Needs what the parity-only peel needs (parity_ok) and, on top, that
-// every boundary node has exactly one edge and lies on the west (-1) side or on one other side, and every
-// edge at least one detector end.  Every graph of codes.Surface / codes.Repetition has all of it.
-inline void pack_fast(const luf_graph_desc& d, const PackedGraph& g, PackedFast& out)
+// The compact tables index detectors only.  Needs what the parity-only peel needs (pack_graph's parity_ok: no
+// edge joins two boundary nodes, the logical mask is exactly the edges whose FIRST endpoint is a west boundary
+// node, none of which is ever a second endpoint) and, on top, that every boundary node has exactly one edge and
+// lies on the west (-1) side or on one other side.  Every graph of codes.Surface / codes.Repetition has all of
+// it.  Works from the description alone, so that it also serves graphs beyond the 16-bit layout of the
+// canonical kernels (up to 32766 detectors; the edge / other-end split of an adjacency entry moves with the
+// edge count: Surface(25, 'circuit-level') has 85297 edges and 15000 detectors -> 17 + 14 bits).
+inline void pack_fast(const luf_graph_desc& d, PackedFast& out)
 {
-    const int N = g.N, B = g.B, E = g.E, D = N - B;
+    const int N = d.n_nodes, B = d.n_boundary, E = d.n_edges, D = N - B;
     out.ok = false;
-    if (!g.parity_ok || D < 1 || D >= (int)fast::OTHER_EAST) return;
+    if (N <= 0 || E <= 0 || B < 0 || B > N || D < 1 || D > fast::MAX_DETECTORS) return;
+    if (d.n_classes < 1 || d.n_classes > MAX_CLASSES || d.inc_off[N] != 2 * E) return;
+    uint32_t ebits = 16;
+    while (ebits < 31 && ((uint64_t)1 << ebits) < (uint64_t)E + 1) ++ebits;
+    const uint32_t omask = (1u << (31 - ebits)) - 1u;
+    if ((uint64_t)D + 2 > (uint64_t)omask + 1) return;               // detector indices and the two boundary codes
+    for (int v = 0; v < N; ++v)
+        if (((d.node_flags[v] & 1) != 0) != (v < B)) return;
     int east_long = 0;
     bool have_east = false;
     for (int v = 0; v < B; ++v) {
@@ -146,19 +163,41 @@ inline void pack_fast(const luf_graph_desc& d, const PackedGraph& g, PackedFast&
     auto end_code = [&](int v) -> uint32_t { return v >= B ? (uint32_t)(v - B) : (d.node_long[v] == -1 ? fast::END_WEST : fast::END_EAST); };
     out.einfo.assign(E, 0);
     for (int e = 0; e < E; ++e) {
-        if (d.edge_u[e] < B && d.edge_v[e] < B) return;
-        out.einfo[e] = end_code(d.edge_u[e]) | (end_code(d.edge_v[e]) << 16);
+        const int u = d.edge_u[e], v = d.edge_v[e];
+        if (u < 0 || u >= N || v < 0 || v >= N) return;
+        const bool west_first = u < B && d.node_long[u] == -1, west_second = v < B && d.node_long[v] == -1;
+        const bool masked = (d.west_edge_mask[e >> 5] >> (e & 31)) & 1u;
+        if ((u < B && v < B) || west_second || masked != west_first) return;
+        out.einfo[e] = end_code(u) | (end_code(v) << 16);
     }
     int deg = 2;
     for (int v = B; v < N; ++v) deg = std::max(deg, d.inc_off[v + 1] - d.inc_off[v]);
-    out.D = D; out.DEG = (deg + 1) & ~1;
+    out.D = D; out.E = E; out.DEG = (deg + 1) & ~1;
+    out.ebits = ebits; out.emask = (1u << ebits) - 1u; out.omask = omask;
     out.fadj.assign((size_t)D * out.DEG, ADJ_PAD);
-    for (int v = B; v < N; ++v)
+    for (int v = B; v < N; ++v) {
+        int prev = -1;
         for (int k = d.inc_off[v]; k < d.inc_off[v + 1]; ++k) {
             const int e = d.inc_edge[k], o = d.inc_other[k];
-            const uint32_t oc = o >= B ? (uint32_t)(o - B) : (d.node_long[o] == -1 ? fast::OTHER_WEST : fast::OTHER_EAST);
-            out.fadj[(size_t)(v - B) * out.DEG + (k - d.inc_off[v])] = (uint32_t)e | (oc << 16) | (d.edge_u[e] == v ? 0x80000000u : 0u);
+            if (e <= prev || e >= E) return;
+            prev = e;
+            const bool first = d.edge_u[e] == v;
+            if ((first ? d.edge_v[e] : d.edge_u[e]) != o || (!first && d.edge_v[e] != v)) return;
+            const uint32_t oc = o >= B ? (uint32_t)(o - B) : (d.node_long[o] == -1 ? omask : omask - 1u);
+            out.fadj[(size_t)(v - B) * out.DEG + (k - d.inc_off[v])] = (uint32_t)e | (oc << ebits) | (first ? 0x80000000u : 0u);
         }
+    }
+    out.class_end.assign(d.n_classes, 0);
+    out.fresh_perm32.clear();
+    for (int c = 0; c < d.n_classes; ++c) {
+        for (int e = 0; e < E; ++e)
+            if (d.edge_class[e] == c) out.fresh_perm32.push_back((uint32_t)e);
+        out.class_end[c] = (uint32_t)out.fresh_perm32.size();
+    }
+    out.F = (int)out.fresh_perm32.size(); out.n_classes = d.n_classes;
+    out.perm_identity = out.F == E;
+    for (int k = 0; k < out.F && out.perm_identity; ++k) out.perm_identity = out.fresh_perm32[k] == (uint32_t)k;
+    out.west_mask.assign(d.west_edge_mask, d.west_edge_mask + words32(E));
     out.ok = true;
 }
 
@@ -174,8 +213,11 @@ inline fast::FLayout make_fast_layout(int D, int E, int DEG, double mu)
     // touched nodes <= 5.6 mu, newly FULL edges of a round <= 4.8 mu, active nodes of a round <= 1.9 mu there
     const double sq = std::sqrt(mu > 0.0 ? mu : 0.0);
     // (degree 6; the diagonal edges of circuit-level graphs, degree 12, fill twice as many edges per round)
-    const double f = DEG > 6 ? DEG / 6.0 : 1.0;
-    l.tcap = cap((5.2 * mu + 10.0 * sq + 32.0) * (1.0 + f) / 2.0, D); l.acap = cap(mu + 3.0 * sq + 16.0, D);
+    // LUF_FAST_CAP_SCALE (measurements): an overflowing list is not fatal (its consumers read the bitmaps), so the
+    // capacities trade shared memory per shot against how often that slower path runs
+    static const double scale = getenv("LUF_FAST_CAP_SCALE") ? atof(getenv("LUF_FAST_CAP_SCALE")) : 1.0;
+    const double f = (DEG > 6 ? DEG / 6.0 : 1.0) * scale;
+    l.tcap = cap((5.2 * mu + 10.0 * sq + 32.0) * (scale + f) / 2.0, D); l.acap = cap((mu + 3.0 * sq + 16.0) * scale, D);
     l.mcap = cap((4.0 * mu + 8.0 * sq + 24.0) * f, E);
     uint32_t off = 0;
     auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };

@@ -576,6 +576,26 @@ __global__ void k_sample_weight(GraphView g, Layout l, SampleParams sp, uint32_t
     }
 }
 
+// Staged K1 on the compact tables: graphs beyond the 16-bit layout (fast::f_sample_record).
+__global__ void k_sample_fast(fast::FView g, int WE, uint32_t slice_bytes, SampleParams sp, unsigned long long shot0,
+                              long long nshots, uint32_t* __restrict__ err, uint32_t* __restrict__ syn)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    uint32_t* e = (uint32_t*)(smem + (size_t)(threadIdx.x >> 5) * slice_bytes);
+    uint32_t* d = e + WE;
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        for (int w = lane; w < WE + g.WD; w += WARP) e[w] = 0;
+        __syncwarp();
+        fast::f_sample_record(g, e, d, sp, shot0 + (unsigned long long)k, lane, WARP);
+        __syncwarp();
+        for (int w = lane; w < WE; w += WARP) err[k * WE + w] = e[w];
+        for (int w = lane; w < g.WD; w += WARP) syn[k * g.WD + w] = d[w];
+        __syncwarp();
+    }
+}
+
 // Staged K4: leftover parity on the west boundary (_schemes.py:123-129,154-155).
 __global__ void k_check(int WE, long long nshots, const uint32_t* __restrict__ west_mask,
                         const uint32_t* __restrict__ err, const uint32_t* __restrict__ corr,
@@ -752,6 +772,7 @@ struct luf_graph {
     std::mutex mu;
     std::map<std::pair<const void*, uint32_t>, std::pair<int, int>> plans;   // (kernel, slice bytes) -> (warps per block, blocks per SM)
     // compact fast path of the fused UF kernel (luf_uf_fast.cuh)
+    bool canonical_ok = true;     // false: a graph beyond the 16-bit layout -- only the compact path's entry points run
     PackedFast fast_host;
     fast::FView fview{};
     std::map<void*, uint32_t*> queues;       // per stream: uint32[FAST_CHUNK] shot indices + the fill counter behind them
@@ -797,7 +818,9 @@ static int raise_smem_limit(int device, int max_smem, K kernel)
     std::lock_guard<std::mutex> lock(g_plan_mu);
     const std::pair<int, const void*> key(device, (const void*)kernel);
     if (g_smem_raised.count(key)) return 0;
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    cudaFuncAttributes attr;
+    CUDA_TRY(cudaFuncGetAttributes(&attr, kernel));           // static shared memory counts against the same limit
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)attr.sharedSizeBytes));
     g_smem_raised.insert(key);
     return 0;
 }
@@ -981,21 +1004,31 @@ static bool fast_plan(const luf_graph* g, const fast::FLayout& l, FastPlan* out)
     static const int env_spb = getenv("LUF_FAST_SPB") ? atoi(getenv("LUF_FAST_SPB")) : 0;
     static const int env_bps = getenv("LUF_FAST_BPS") ? atoi(getenv("LUF_FAST_BPS")) : 0;
     static const int env_warps = getenv("LUF_FAST_WARPS") ? atoi(getenv("LUF_FAST_WARPS")) : 24;
+    static const int env_l1 = getenv("LUF_FAST_L1_KB") ? atoi(getenv("LUF_FAST_L1_KB")) : -1;
     const uint32_t adj_all = align16((uint32_t)g->fast_host.fadj.size() * 4u);
     const int sm_smem = 228 * 1024;
     FastPlan best{};
     int best_shots = 0;
+    // Measured on cfg3 (B200, M shots/s; adjacency 29 KB): shared, 1 block of 32 shots 175.8; shared, 2 x 16 173.6;
+    // global with 84 KB of L1 left (1 x 32) 165.3; global with 28 KB of L1 left (2 x 21 = 42 shots) 119.8 -- the
+    // table has to stay on chip, in shared memory or in L1, before more resident shots pay.  Tiles narrower
+    // than a warp lose outright (16 lanes 72, 8 lanes 29: the shots of a warp serialise each other's branches).
     for (int adj = 1; adj >= 0; --adj) {
         if (env_adj >= 0 && adj != env_adj) continue;
+        if (adj && env_adj < 0 && adj_all > 40u * 1024u) continue;       // a large table is worth more as resident shots
         const uint32_t adj_bytes = adj ? adj_all : 0u;
+        // adjacency in global memory: leave it room in L1 (up to 64 KB) when that costs less than half the shots
+        int l1_kb = adj ? 0 : (int)std::min<uint32_t>((adj_all + 16u * 1024u) / 1024u, 64u);
+        if (!adj && adj_all > 64u * 1024u) l1_kb = 0;                     // cannot be kept anyway
+        if (env_l1 >= 0) l1_kb = adj ? 0 : env_l1;
         for (int bps = 1; bps <= 2; ++bps) {
             if (env_bps > 0 && bps != env_bps) continue;
-            long long budget = sm_smem / bps - 1024;
+            long long budget = (sm_smem - l1_kb * 1024) / bps - 1024;
             if (budget > g->max_smem) budget = g->max_smem;
             if (budget < (long long)adj_bytes + (long long)l.bytes) continue;
             const int fit = (int)((budget - adj_bytes) / l.bytes);
-            // the narrowest tile that keeps the warp count: fit shots * tw / 32 ~ env_warps / bps
-            int tw = 8;
+            // the narrowest tile, a warp at least, that keeps the warp count: fit shots * tw / 32 ~ env_warps / bps
+            int tw = 32;
             while (tw < 256 && (long long)fit * bps * tw < 32ll * env_warps) tw <<= 1;
             if (env_tw > 0) tw = env_tw;
             int spb = fit;
@@ -1003,8 +1036,7 @@ static bool fast_plan(const luf_graph* g, const fast::FLayout& l, FastPlan* out)
             if (tw > 32 && spb > 15) spb = 15;                 // named barriers 1 .. 15
             if (env_spb > 0 && env_spb < spb) spb = env_spb;
             if (spb < 1) continue;
-            // adjacency in shared memory is worth a fifth of the resident shots
-            const int score = spb * bps * (adj ? 5 : 4);
+            const int score = spb * bps * 16 + (adj ? 1 : 0) * 8 + (2 - bps);       // shots, then shared adjacency, then fewer blocks
             if (score > best_shots) { best_shots = score; best = FastPlan{tw, spb, bps, adj != 0, adj_bytes}; }
         }
     }
@@ -1056,8 +1088,8 @@ static int fast_launch(luf_graph* g, const fast::FView& fv, const FastPlan& plan
 #define LUF_FAST_TW(T) case T: return plan.adj_shared ? fast_launch_t<T, true>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream) \
                                                       : fast_launch_t<T, false>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream);
     switch (plan.tw) {
-        LUF_FAST_TW(8) LUF_FAST_TW(16) LUF_FAST_TW(32) LUF_FAST_TW(64) LUF_FAST_TW(128) LUF_FAST_TW(256)
-        default: return fail(LUF_ERR_INVALID, "fast path: tile width must be 8, 16, 32, 64, 128 or 256");
+        LUF_FAST_TW(16) LUF_FAST_TW(32) LUF_FAST_TW(64) LUF_FAST_TW(128) LUF_FAST_TW(256)
+        default: return fail(LUF_ERR_INVALID, "fast path: tile width must be 16, 32, 64, 128 or 256");
     }
 #undef LUF_FAST_TW
 }
@@ -1437,7 +1469,9 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     luf_graph* g = new (std::nothrow) luf_graph();
     if (!g) return fail(LUF_ERR_INVALID, "out of host memory");
     const std::string why = pack_graph(*desc, g->host);
-    if (!why.empty()) {
+    pack_fast(*desc, g->fast_host);
+    g->canonical_ok = why.empty();
+    if (!why.empty() && !(why.find("too large") != std::string::npos && g->fast_host.ok)) {
         delete g;
         return fail(why.find("too large") != std::string::npos ? LUF_ERR_UNSUPPORTED : LUF_ERR_INVALID, why);
     }
@@ -1448,10 +1482,32 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     cudaDeviceGetAttribute(&g->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const PackedGraph& p = g->host;
     GraphView& v = g->view;
+    int rc = 0;
+    if (g->fast_host.ok) {
+        const PackedFast& q = g->fast_host;
+        fast::FView& f = g->fview;
+        f.D = q.D; f.E = q.E; f.WD = words32(q.D); f.DEG = q.DEG; f.ebits = q.ebits; f.emask = q.emask; f.omask = q.omask;
+        f.F = q.F; f.n_classes = q.n_classes; f.fresh_perm = nullptr; f.fresh_perm32 = nullptr; f.west = 0;
+        if ((rc = upload(g, q.fadj, &f.fadj)) || (rc = upload(g, q.einfo, &f.einfo)) || (rc = upload(g, q.class_end, &f.class_end)) ||
+            (!q.perm_identity && (rc = upload(g, q.fresh_perm32, &f.fresh_perm32)))) {
+            luf_graph_destroy(g);
+            return rc;
+        }
+    }
+    if (!g->canonical_ok) {
+        // beyond the 16-bit layout of the canonical kernels: the compact path alone (luf_sample, luf_check,
+        // luf_mc_run[_logical] with UF under the west inclination); everything else answers LUF_ERR_UNSUPPORTED
+        memset(&v, 0, sizeof(v));
+        v.N = desc->n_nodes; v.B = desc->n_boundary; v.E = desc->n_edges; v.F = g->fast_host.F; v.n_classes = desc->n_classes;
+        v.WE = words32(v.E); v.WD = words32(v.N - v.B); v.WN = words32(v.N);
+        if ((rc = upload(g, g->fast_host.west_mask, &v.west_mask))) { luf_graph_destroy(g); return rc; }
+        g->ca_why = "graph too large for the 16-bit cellular-automaton layout";
+        *out = g;
+        return 0;
+    }
     v.N = p.N; v.B = p.B; v.E = p.E; v.F = p.F; v.n_classes = p.n_classes; v.DEG = p.DEG;
     v.parity_ok = p.parity_ok ? 1 : 0;
     v.WE = words32(p.E); v.WD = words32(p.N - p.B); v.WN = words32(p.N);
-    int rc = 0;
     if ((rc = upload(g, p.adj, &v.adj)) ||
         (rc = upload(g, p.edge_uv, &v.edge_uv)) || (rc = upload(g, p.west_mask, &v.west_mask)) ||
         (rc = upload(g, p.node_long, &v.node_long)) ||
@@ -1472,16 +1528,6 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
         l.bytes = off;
         // keep every pointer inside the slice (unused arrays alias the start)
         g->lay_sample = l;
-    }
-    pack_fast(*desc, p, g->fast_host);
-    if (g->fast_host.ok) {
-        fast::FView& f = g->fview;
-        f.D = g->fast_host.D; f.E = p.E; f.WD = words32(f.D); f.DEG = g->fast_host.DEG;
-        f.F = p.F; f.n_classes = p.n_classes; f.fresh_perm = v.fresh_perm; f.class_end = v.class_end;
-        if ((rc = upload(g, g->fast_host.fadj, &f.fadj)) || (rc = upload(g, g->fast_host.einfo, &f.einfo))) {
-            luf_graph_destroy(g);
-            return rc;
-        }
     }
     g->ca_why = pack_ca(*desc, g->ca_host);
     if (g->ca_why.empty()) {
@@ -1561,6 +1607,17 @@ int luf_sample(luf_graph* g, const double* class_p_host, uint64_t seed, uint64_t
     CUDA_TRY(cudaSetDevice(g->device));
     const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
     LaunchCfg c;
+    if (!g->canonical_ok) {               // the sampler of the compact tables (same random stream)
+        const uint32_t slice = align16(4u * (uint32_t)(g->view.WE + g->view.WD));
+        if (int rc = raise_smem_limit(g->device, g->max_smem, k_sample_fast)) return rc;
+        int wpb = std::max(1, std::min(8, g->max_smem / (int)slice));
+        long long blocks = std::min<long long>((long long)g->sm_count * 4, (nshots + wpb - 1) / wpb);
+        k_sample_fast<<<(int)blocks, wpb * WARP, (size_t)wpb * slice, (cudaStream_t)stream>>>(g->fview, g->view.WE, slice, sp, shot0,
+                                                                                       nshots, err_bits_dev, syn_bits_dev);
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+        return 0;
+    }
     if (int rc = plan_launch(g, k_sample, g->lay_sample.bytes, nshots, &c)) return rc;
     k_sample<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_sample, sp, shot0, nshots,
                                                                  err_bits_dev, syn_bits_dev);
@@ -1574,6 +1631,7 @@ int luf_sample_weight(luf_graph* g, int32_t weight, uint64_t seed, uint64_t shot
 {
     if (!g || !err_bits_dev || !syn_bits_dev || nshots < 0)
         return fail(LUF_ERR_INVALID, "luf_sample_weight: bad argument");
+    if (!g->canonical_ok) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     if (weight < 0 || weight > g->view.F)
         return fail(LUF_ERR_INVALID, "Sample larger than population or is negative");       // random.sample's message
     if (nshots == 0) return 0;
@@ -1594,6 +1652,7 @@ int luf_decode_batch(luf_graph* g, int decoder, int flags, int64_t nshots, const
 {
     if (!g || !syn_bits_dev || !corr_bits_dev || nshots < 0)
         return fail(LUF_ERR_INVALID, "luf_decode_batch: bad argument");
+    if (!g->canonical_ok) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     if (int rc = check_decoder(g, decoder, flags)) return rc;
     if (nshots == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
@@ -1686,6 +1745,7 @@ int luf_count_strings(luf_graph* g, int64_t nshots, const uint32_t* err_bits_dev
 {
     if (!g || !err_bits_dev || !corr_bits_dev || !total_dev || nshots < 0)
         return fail(LUF_ERR_INVALID, "luf_count_strings: bad argument");
+    if (!g->canonical_ok) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     if (nshots == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
     const uint32_t slice = align16(2u * (uint32_t)g->view.N);
@@ -1716,6 +1776,7 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                        uint64_t shot0, int64_t nshots, unsigned long long* counts_dev, uint8_t* logical_dev, void* stream)
 {
     if (!g || !class_p_host || !counts_dev || nshots < 0) return fail(LUF_ERR_INVALID, "luf_mc_run: bad argument");
+    if (!g->canonical_ok && !(decoder == LUF_DEC_UF && flags == LUF_UF_WEST)) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     if (int rc = check_decoder(g, decoder, flags)) return rc;
     if (nshots == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
@@ -1742,7 +1803,7 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                                                                               shot0, nshots, counts_dev, logical_dev);
         }
     } else {
-        const bool cta = use_cta_tiles(g, g->lay_fused.bytes, g->lay_fused_cta.bytes);
+        const bool cta = g->canonical_ok && use_cta_tiles(g, g->lay_fused.bytes, g->lay_fused_cta.bytes);
         // the decoder flags are compile-time constants of the fused kernel
 #define LUF_MC_UF(TF, Q, SHOT0, NSHOTS, LOGICAL, QUEUE, QCOUNT) { \
         if (int rc = plan_launch(g, k_mc_uf<TF, Q>, g->lay_fused.bytes, Q ? FAST_CHUNK : (long long)(NSHOTS), &c, 14)) return rc; \
@@ -1758,7 +1819,7 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
         if (env_fast && g->fast_host.ok && (flags & ~LUF_UF_WEST) == 0) {
             double mu = 0.0;
             for (int cl = 0, lo = 0; cl < g->view.n_classes; ++cl) {
-                const int hi = (int)g->host.class_end[cl];
+                const int hi = (int)g->fast_host.class_end[cl];
                 mu += std::min(1.0, std::max(0.0, class_p_host[cl])) * (hi - lo);
                 lo = hi;
             }
@@ -1786,6 +1847,8 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                 return 0;
             }
         }
+        if (!g->canonical_ok)
+            return fail(LUF_ERR_UNSUPPORTED, "one shot's compact state exceeds the shared memory of an SM and the graph is beyond the canonical kernels");
         // the common flag sets are compile-time constants of the fused kernel; the rest run the generic instance
         switch (flags <= 7 ? flags : -1) {
             case 0: LUF_MC_UF_ANY(0, false, shot0, nshots, logical_dev, nullptr, nullptr) break;
@@ -1811,6 +1874,7 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
 int luf_forward_attach(luf_graph* g, const luf_forward_desc* d)
 {
     if (!g || !d) return fail(LUF_ERR_INVALID, "null argument");
+    if (!g->canonical_ok) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     CUDA_TRY(cudaSetDevice(g->device));
     const luf_graph_desc_dims dims = {g->view.N, g->view.B, g->view.E, g->view.n_classes};
     const std::string why = pack_forward(dims, *d, g->fw_host);

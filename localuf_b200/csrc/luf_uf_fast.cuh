@@ -15,7 +15,7 @@
 //   tlist  the touched detectors in order of appearance (defects first): what later growth rounds visit
 //   alist  the active touched nodes of a round (node | root << 16)
 //   mlist  the edges that became fully grown this round, as endpoint pairs (detector | other end << 16, the
-//          other end being a detector or OTHER_WEST / OTHER_EAST)
+//          other end being a detector or END_WEST / END_EAST)
 //
 // No union by size: a root is hooked below the root of smaller index with a compare-and-swap (a static strict
 // order, so no interleaving closes a cycle), taking its (odd, west, east) bits along; bits are added to live
@@ -44,8 +44,8 @@ namespace fast {
 static const uint32_t P_ROOT = 0x8000u, P_ODD = 1u, P_WEST = 2u, P_EAST = 4u;
 static const uint32_t P_FRESH = P_ROOT;                  // an untouched detector: even singleton, no boundary
 static const uint32_t P_ACTIVE = P_ROOT | P_ODD;         // odd and no boundary (uf.py:296-301)
-static const uint32_t OTHER_WEST = 0x7FFFu, OTHER_EAST = 0x7FFEu;     // adjacency entry: the other end is a boundary node
-static const uint32_t END_WEST = 0xFFFFu, END_EAST = 0xFFFEu;         // edge table / merge list: ditto, 16-bit form
+static const uint32_t END_WEST = 0xFFFFu, END_EAST = 0xFFFEu;         // edge table / merge list: the end is a boundary node
+static const int MAX_DETECTORS = 0x7FFE;                              // a non-root word is a parent index below 0x8000
 // cnt[]: fill counters of the three lists (they only grow: a round's entries start at the previous total; a
 // counter beyond its capacity says the list overflowed), the number of active clusters, the parity
 // accumulator, and the HARD flag (a cluster touches both sides; written by the merge phase only, read after
@@ -56,10 +56,13 @@ static const uint32_t HARD = 2u;                         // result of a shot the
 // Read-only tables (global memory; fadj optionally staged in shared memory by the kernel).
 struct FView {
     int D, E, WD, DEG;          // detectors, edges, 32-bit words of a detector bitmap, row length of fadj (even)
-    const uint32_t* fadj;       // [D][DEG] edge | other end << 16 (detector index, OTHER_WEST, OTHER_EAST) | first endpoint << 31
+    const uint32_t* fadj;       // [D][DEG] edge | other end << ebits | this is the edge's first endpoint << 31; other end =
+                                // detector index, or the two top values of its field: omask = west, omask - 1 = east
+    uint32_t ebits, emask, omask;   // 16 / 0xFFFF / 0x7FFF up to 65533 edges; graphs with more edges and fewer detectors shift the split
     const uint32_t* einfo;      // [E] first end | second end << 16 (detector index, END_WEST, END_EAST)
     int F, n_classes;
     const uint16_t* fresh_perm; // as GraphView
+    const uint32_t* fresh_perm32;   // instead, for more than 65535 edges
     const uint32_t* class_end;
     int west;                   // west inclination: a cluster on both sides is not HARD
 };
@@ -195,6 +198,24 @@ LUF_DEV uint32_t f_flip(const FView& g, const FShot& s, uint32_t e)
     return a == END_WEST ? 1u : 0u;
 }
 
+// Staged K1 on the compact tables (graphs beyond the 16-bit layout have no other): the 32 virtual sampler lanes
+// record the flipped edges in `err` (W(E) words) and toggle the defects (noise/main.py:114-115,309-314;
+// _base_classes.py:427-450).  Same random stream as fast_shot and, where both exist, as ph_sample.
+LUF_DEV void f_sample_record(const FView& g, uint32_t* err, uint32_t* defect, const SampleParams& sp, uint64_t shot,
+                             int lane, int nl)
+{
+    SampleTab t; t.F = g.F; t.n_classes = g.n_classes; t.perm = g.fresh_perm; t.class_end = g.class_end; t.perm32 = g.fresh_perm32;
+    for (int vl = lane; vl < 32; vl += nl)
+        ph_sample_core(t, sp, shot, 0u, (const uint32_t*)0, vl, 32, [&](uint32_t e) {
+            luf_atomic_xor(&err[e >> 5], 1u << (e & 31u));
+            const uint32_t ei = LUF_LDG(&g.einfo[e]);
+            const uint32_t a = ei & 0xFFFFu, b = ei >> 16;
+            if (a < END_EAST) luf_atomic_xor(&defect[a >> 5], 1u << (a & 31u));
+            if (b < END_EAST) luf_atomic_xor(&defect[b >> 5], 1u << (b & 31u));
+            return 0u;
+        });
+}
+
 // uf.py:98-104: every defect an odd singleton; the defects open the list of touched nodes
 LUF_DEV void f_load(const FView& g, const FLayout& l, const FShot& s, int lane, int nl)
 {
@@ -229,10 +250,11 @@ LUF_DEV void f_row(const FView& g, uint32_t v, F f)
     }
 }
 
-LUF_DEV void f_newfull(const FLayout& l, const FShot& s, uint32_t u, uint32_t other, uint32_t mbase)
+// `other16`: the other end as a detector index, END_WEST or END_EAST
+LUF_DEV void f_newfull(const FLayout& l, const FShot& s, uint32_t u, uint32_t other16, uint32_t mbase)
 {
     const uint32_t idx = luf_atomic_add(&s.cnt[C_MLIST], 1u) - mbase;
-    if (idx < l.mcap) s.mlist[idx] = u | ((other >= OTHER_EAST ? other | 0x8000u : other) << 16);
+    if (idx < l.mcap) s.mlist[idx] = u | (other16 << 16);
     // else: the counter alone says the list overflowed; the merge phase then reads the growth words
 }
 
@@ -262,9 +284,9 @@ LUF_DEV void f_grow_first(const FView& g, const FLayout& l, const FShot& s, uint
 {
     f_for_nodes(g, l, s, s.defect, nd, nd, lane, nl, [&](uint32_t v) {
         f_row<ADJ_SHARED>(g, v, [&](uint32_t ent) {
-            const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+            const uint32_t e = ent & g.emask, sh = (e & 15u) * 2u;
             const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-            if (old == G_HALF) f_newfull(l, s, v, (ent >> 16) & 0x7FFFu, 0u);
+            if (old == G_HALF) f_newfull(l, s, v, (ent >> g.ebits) & g.omask, 0u);       // (the other end grew too: a detector)
         });
     });
 }
@@ -283,18 +305,19 @@ template <bool ADJ_SHARED>
 LUF_DEV void f_grow_node(const FView& g, const FLayout& l, const FShot& s, uint32_t u, uint32_t r, uint32_t mbase)
 {
     f_row<ADJ_SHARED>(g, u, [&](uint32_t ent) {
-        const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+        const uint32_t e = ent & g.emask, sh = (e & 15u) * 2u;
         if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
-        const uint32_t o = (ent >> 16) & 0x7FFFu;
-        if (!(ent >> 31) && o < OTHER_EAST) {          // second endpoint of an edge between detectors: same cluster?
+        const uint32_t o = (ent >> g.ebits) & g.omask;
+        const bool detector = o < g.omask - 1u;
+        if (!(ent >> 31) && detector) {                // second endpoint of an edge between detectors: same cluster?
             uint32_t wr;
             if (o == r || ffind_ro(s, o, wr) == r) return;
         }
         const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
         if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);
         else if (old == G_HALF) {
-            f_newfull(l, s, u, o, mbase);
-            if (o < OTHER_EAST) f_touch(l, s, o);
+            f_newfull(l, s, u, detector ? o : (o == g.omask ? END_WEST : END_EAST), mbase);
+            if (detector) f_touch(l, s, o);
         }
     });
 }
@@ -398,7 +421,7 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
     FT_PHASE((void)0);                                  // every lane is done with the previous shot's counters
     FT_PHASE(f_reset(l, s, lane, nl));
     FT_PHASE(
-        SampleTab t; t.F = g.F; t.n_classes = g.n_classes; t.perm = g.fresh_perm; t.class_end = g.class_end;
+        SampleTab t; t.F = g.F; t.n_classes = g.n_classes; t.perm = g.fresh_perm; t.class_end = g.class_end; t.perm32 = g.fresh_perm32;
         uint32_t par = 0;
         for (int vl = lane; vl < 32; vl += nl)
             par ^= ph_sample_core(t, sp, shot, 0u, (const uint32_t*)0, vl, 32, [&](uint32_t e) { return f_flip(g, s, e); });

@@ -244,19 +244,19 @@ int emu_mc_uf_fast(const luf_graph_desc* d, int flags, const double* class_p, un
 int emu_mc_uf_compact(const luf_graph_desc* d, int west, const double* class_p, unsigned long long seed, unsigned long long shot0,
                       long long nshots, int nl, double mu, uint8_t* out, uint32_t* stats)
 {
-    PackedGraph p;
     PackedFast pf;
-    if (!pack_graph(*d, p).empty()) return -1;
-    pack_fast(*d, p, pf);
+    pack_fast(*d, pf);
     if (!pf.ok) return -2;
+    struct { int E, n_classes; const std::vector<uint32_t>& class_end; } p = {pf.E, pf.n_classes, pf.class_end};
     if (mu < 0.0) {
         mu = 0.0;
         for (int c = 0, lo = 0; c < p.n_classes; ++c) { mu += class_p[c] * ((int)p.class_end[c] - lo); lo = (int)p.class_end[c]; }
     }
     fast::FView g;
-    g.D = pf.D; g.E = p.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
-    g.F = p.F; g.n_classes = p.n_classes;
-    g.fresh_perm = p.perm_identity ? nullptr : p.fresh_perm.data(); g.class_end = p.class_end.data();
+    g.D = pf.D; g.E = pf.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
+    g.ebits = pf.ebits; g.emask = pf.emask; g.omask = pf.omask;
+    g.F = pf.F; g.n_classes = pf.n_classes;
+    g.fresh_perm = nullptr; g.fresh_perm32 = pf.perm_identity ? nullptr : pf.fresh_perm32.data(); g.class_end = pf.class_end.data();
     g.west = west;
     const fast::FLayout l = make_fast_layout(pf.D, p.E, pf.DEG, mu);
     const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
@@ -264,6 +264,28 @@ int emu_mc_uf_compact(const luf_graph_desc* d, int west, const double* class_p, 
     const fast::FShot s = fast::fbind(l, mem.data());
     for (long long k = 0; k < nshots; ++k)
         out[k] = (uint8_t)fast::fast_shot<false>(g, l, s, sp, shot0 + k, 0, nl, 0, stats ? stats + 4 * k : nullptr);
+    return 0;
+}
+
+// Staged sampler on the compact tables (f_sample_record): errors and syndromes of shots [shot0, shot0 + nshots).
+int emu_sample_compact(const luf_graph_desc* d, const double* class_p, unsigned long long seed, unsigned long long shot0,
+                       long long nshots, uint32_t* err_out, uint32_t* syn_out)
+{
+    PackedFast pf;
+    pack_fast(*d, pf);
+    if (!pf.ok) return -2;
+    fast::FView g;
+    g.D = pf.D; g.E = pf.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
+    g.ebits = pf.ebits; g.emask = pf.emask; g.omask = pf.omask; g.F = pf.F; g.n_classes = pf.n_classes;
+    g.fresh_perm = nullptr; g.fresh_perm32 = pf.perm_identity ? nullptr : pf.fresh_perm32.data(); g.class_end = pf.class_end.data();
+    g.west = 0;
+    const SampleParams sp = make_sample_params(class_p, pf.n_classes, seed);
+    const int WE = words32(pf.E), nl = 32;
+    for (long long k = 0; k < nshots; ++k) {
+        std::memset(err_out + k * WE, 0, 4u * WE);
+        std::memset(syn_out + k * g.WD, 0, 4u * g.WD);
+        LUF_PHASE(fast::f_sample_record(g, err_out + k * WE, syn_out + k * g.WD, sp, shot0 + k, lane, nl));
+    }
     return 0;
 }
 

@@ -151,6 +151,16 @@ class Emu:
         assert rc == 0, rc
         return (out, stats) if want_stats else out
 
+    def sample_compact(self, noise_level, seed, shot0, nshots):
+        """The staged sampler on the compact tables (f_sample_record): (err [n, W(E)], syn [n, W(D)])."""
+        cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
+        err = np.zeros((nshots, self.WE), np.uint32)
+        syn = np.zeros((nshots, self.WD), np.uint32)
+        lib().emu_sample_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_longlong, C.c_void_p, C.c_void_p]
+        rc = lib().emu_sample_compact(C.addressof(self.desc), _vp(cp), seed, shot0, nshots, _vp(err), _vp(syn))
+        assert rc == 0, rc
+        return err, syn
+
     def decode_ca(self, decoder, flags, syn_bits, nl=32):
         syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
         n = syn.shape[0]

@@ -101,3 +101,36 @@ def test_compact_path_sampler_is_the_staged_sampler():
     out = emu.mc_uf_compact(0.5, 1, 0, 200, nl=16, mu=1e6)
     _, want = canonical_bits(code, 0.5, 1, 0, 200)
     np.testing.assert_array_equal(out[out != 2], want[out != 2])
+
+
+def test_compact_sampler_equals_the_canonical_sampler():
+    code = make_code(dict(code='Surface', d=5, noise='circuit-level'))
+    emu = emu_binding.Emu(code)
+    _, err, syn, _ = emu.mc_uf(0, 0.02, 5, 40, 300)
+    err2, syn2 = emu.sample_compact(0.02, 5, 40, 300)
+    np.testing.assert_array_equal(err, err2)
+    np.testing.assert_array_equal(syn, syn2)
+
+
+@pytest.mark.parametrize('d,p,n', [(23, 0.004, 40), (25, 0.006, 30)])
+def test_compact_path_on_graphs_beyond_the_16_bit_layout(d, p, n):
+    """Surface(23 | 25, 'circuit-level'): 65869 / 85297 edges -- the canonical kernels' 16-bit edge ids do not
+    reach; the compact path moves the edge / other-end split of its adjacency entries (17 + 14 bits) and, under
+    the west inclination, decodes every shot itself.  Errors from the compact sampler, logical bits against the
+    oracle's west decode (equal to the unmodified reference on every shot)."""
+    code = make_code(dict(code='Surface', d=d, noise='circuit-level'))
+    assert code.N_EDGES > 65533
+    emu = emu_binding.Emu(code)
+    orc = binding.Oracle.from_code(code)
+    err, syn = emu.sample_compact(p, 3, 7, n)
+    np.testing.assert_array_equal(orc.syndrome(err), syn)
+    corr, _, _ = orc.decode_batch(0, 2, syn)
+    want = orc.logical_batch(err, corr)
+    for nl, mu in ((256, -1.0), (32, 0.0)):
+        out = emu.mc_uf_compact(p, 3, 7, n, nl=nl, mu=mu, west=True)
+        np.testing.assert_array_equal(out, want)
+    # default inclination: the shots it finishes agree with the canonical default decode
+    corr0, _, _ = orc.decode_batch(0, 0, syn)
+    out = emu.mc_uf_compact(p, 3, 7, n, nl=128)
+    ok = out != 2
+    np.testing.assert_array_equal(out[ok], orc.logical_batch(err, corr0)[ok])
