@@ -158,6 +158,8 @@ struct GraphView {
     const uint32_t* west_mask;  // [WE]  edges whose first endpoint is a west boundary node
     const int16_t* node_long;   // [N]   coordinate along the long axis
     int parity_ok;              // the graph allows the parity-only peel of the fused kernels (pack_graph, luf_host.h)
+    int leaf_bnd;               // ... and every boundary node has exactly one edge (pack_fast): then the peel is never
+                                // needed for the logical bit, not even when a cluster holds boundary nodes of both sides
     // sampler tables: fresh edges sorted by probability class
     int F, n_classes;
     const uint16_t* fresh_perm; // [F]; null when it is the identity (one class, every edge fresh)

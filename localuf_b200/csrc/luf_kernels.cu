@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf(GraphView g, Layout l, SampleP
                 LUF_PHASE(parity ^= ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
                 LUF_PHASE(ph_load(g, s, lane, nl));
                 uf_validate_t<TF>(g, s, flags, lane, nl);
-                parity ^= uf_peel(g, s, lane, nl);
+                parity ^= uf_peel_parity(g, s, lane, nl);      // (no peel at all on graphs whose boundary nodes are leaves)
             } else {
                 parity ^= ph_defect_sides(g, s, lane, nl);
                 __syncwarp();
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(448, 2) k_mc_uf_cta(GraphView g, Layout l, Sam
                 uf_cta::ph_load(g, s, lane, nl);
                 __syncthreads();
                 uf_cta::uf_validate_t<TF>(g, s, flags, lane, nl);
-                parity ^= uf_cta::uf_peel(g, s, lane, nl);
+                parity ^= uf_cta::uf_peel_parity(g, s, lane, nl);
             } else {
                 parity ^= uf_cta::ph_defect_sides(g, s, lane, nl);
                 __syncthreads();
@@ -1507,6 +1507,7 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     }
     v.N = p.N; v.B = p.B; v.E = p.E; v.F = p.F; v.n_classes = p.n_classes; v.DEG = p.DEG;
     v.parity_ok = p.parity_ok ? 1 : 0;
+    v.leaf_bnd = g->fast_host.ok ? 1 : 0;
     v.WE = words32(p.E); v.WD = words32(p.N - p.B); v.WN = words32(p.N);
     if ((rc = upload(g, p.adj, &v.adj)) ||
         (rc = upload(g, p.edge_uv, &v.edge_uv)) || (rc = upload(g, p.west_mask, &v.west_mask)) ||

@@ -857,7 +857,13 @@ LUF_DEV uint32_t uf_peel(const GraphView& g, const Shot& s, int lane, int nl)
 // none).  That parity is the number of the cluster's defects if its boundary nodes are west ones (an odd
 // cluster sends one string to the boundary, an even one an even number), else 0 -- so every defect adds 1 iff
 // its cluster's boundary node is a west one; no forest, no traversal.  cnt[4] (union_roots) says whether a
-// cluster with boundary nodes of different sides exists; such shots take the full peel.
+// cluster with boundary nodes of different sides exists; such shots take the full peel -- unless every
+// boundary node of the graph has exactly one edge (g.leaf_bnd; every Surface / Repetition graph): the peel
+// roots a cluster's tree at cluster.boundary (uf.py:314-324), every other boundary node of the cluster is then
+// a leaf that is no defect, so its edge is never in the correction (uf.py:305-312), and the root's single
+// edge is iff the cluster is odd.  The west parity of the correction is the cluster's defect parity if
+// cluster.boundary is a west node, else 0 -- the same pass over the defects, whatever sides the cluster
+// touches, as long as the merges ran in canonical order (which decides which boundary node the cluster keeps).
 LUF_DEV uint32_t ph_defect_sides(const GraphView& g, const Shot& s, int lane, int nl)
 {
     uint32_t parity = 0;
@@ -880,7 +886,7 @@ LUF_DEV uint32_t uf_peel_parity(const GraphView& g, const Shot& s, int lane, int
 {
     uint32_t mixed = 0, parity = 0;
     (void)lane;
-    LUF_T_PHASE(mixed = s.cnt[4] | (g.parity_ok ? 0u : 1u));
+    LUF_T_PHASE(mixed = (g.leaf_bnd ? 0u : s.cnt[4]) | (g.parity_ok ? 0u : 1u));
     if (LUF_T_ANY(mixed)) return uf_peel(g, s, lane, nl);
     LUF_T_PHASE(parity ^= ph_defect_sides(g, s, lane, nl));
     return parity;

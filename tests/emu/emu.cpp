@@ -21,7 +21,7 @@ static GraphView view_of(const PackedGraph& p)
     g.WE = words32(p.E); g.WD = words32(p.N - p.B); g.WN = words32(p.N);
     g.DEG = p.DEG; g.adj = p.adj.data(); g.edge_uv = p.edge_uv.data();
     g.west_mask = p.west_mask.data(); g.node_long = p.node_long.data();
-    g.F = p.F; g.n_classes = p.n_classes; g.parity_ok = p.parity_ok ? 1 : 0;
+    g.F = p.F; g.n_classes = p.n_classes; g.parity_ok = p.parity_ok ? 1 : 0; g.leaf_bnd = 0;
     g.fresh_perm = p.perm_identity ? nullptr : p.fresh_perm.data(); g.class_end = p.class_end.data();
     return g;
 }
@@ -180,6 +180,47 @@ int emu_mc_uf_parity(const luf_graph_desc* d, int flags, const double* class_p, 
         }
         if (fast == 2u) fast = full;
         counts[0] += (parity ^ full) & 1u; counts[1] += (parity ^ fast) & 1u; counts[2] += (fast ^ full) & 1u;
+    }
+    return 0;
+}
+
+// Canonical validate + the pass over the defects (uf_peel_parity with g.leaf_bnd) next to the full peel on EVERY
+// shot, also those with a cluster on both sides: counts[0] += failures by the full peel, [1] += failures by the
+// pass over the defects, [2] += shots where they differ, [3] += shots with a cluster on both sides; -3 when the
+// graph has a boundary node with more than one edge (pack_fast).
+int emu_mc_uf_sides(const luf_graph_desc* d, int flags, const double* class_p, unsigned long long seed,
+                    unsigned long long shot0, long long nshots, unsigned long long counts[4], int nl)
+{
+    const bool cta = nl != 32;
+    PackedGraph p;
+    PackedFast pf;
+    if (!pack_graph(*d, p).empty()) return -1;
+    pack_fast(*d, pf);
+    if (!pf.ok) return -3;
+    GraphView g = view_of(p);
+    g.leaf_bnd = 1;
+    const Layout l = cta ? make_layout(p.N, p.B, p.E, true, true, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS)
+                         : make_layout(p.N, p.B, p.E, true, true);
+    const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
+    std::vector<unsigned char> mem(l.bytes);
+    const Shot s = bind(l, mem.data());
+    for (long long k = 0; k < nshots; ++k) {
+        uint32_t parity = 0, sides, full;
+        if (cta) { LUF_PHASE(uf_cta::ph_reset(g, l, s, lane, nl)); } else { LUF_PHASE(ph_reset(g, l, s, lane, nl)); }
+        LUF_PHASE(if (lane < 32) parity ^= ph_sample(g, s, sp, shot0 + k, lane, 32));
+        if (cta) { LUF_PHASE(uf_cta::ph_load(g, s, lane, nl)); } else { LUF_PHASE(ph_load(g, s, lane, nl)); }
+        if (cta) {
+            uf_cta::uf_validate(g, s, flags, 0, nl);
+            counts[3] += s.cnt[4] ? 1 : 0;
+            sides = uf_cta::uf_peel_parity(g, s, 0, nl);         // read-only with leaf_bnd
+            full = uf_cta::uf_peel(g, s, 0, nl);
+        } else {
+            uf_validate(g, s, flags, 0, nl);
+            counts[3] += s.cnt[4] ? 1 : 0;
+            sides = uf_peel_parity(g, s, 0, nl);
+            full = uf_peel(g, s, 0, nl);
+        }
+        counts[0] += (parity ^ full) & 1u; counts[1] += (parity ^ sides) & 1u; counts[2] += (sides ^ full) & 1u;
     }
     return 0;
 }

@@ -125,6 +125,17 @@ class Emu:
         assert rc == 0, rc
         return tuple(int(x) for x in counts)
 
+    def mc_uf_sides(self, flags, noise_level, seed, nshots, nl=32):
+        """Canonical validate, then the west parity by the pass over the defects (no peel, g.leaf_bnd) and by the
+        full peel, on every shot: (failures full peel, failures defect pass, shots where they differ, shots with
+        a cluster on both sides)."""
+        cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
+        counts = (C.c_ulonglong * 4)(0, 0, 0, 0)
+        rc = lib().emu_mc_uf_sides(C.byref(self.desc), flags, _vp(cp), C.c_ulonglong(seed), C.c_ulonglong(0),
+                                   C.c_longlong(nshots), counts, nl)
+        assert rc == 0, rc
+        return tuple(int(x) for x in counts)
+
     def parity_ok(self):
         """Whether pack_graph found the graph fit for the fused kernels' parity-only peel."""
         return int(lib().emu_parity_ok(C.byref(self.desc)))

@@ -211,3 +211,24 @@ def test_emu_order_free_merge_with_tiny_lists():
             assert differ == 0 and rounds_differ == 0 and canon > 0
     finally:
         emu_binding.use_tiny_lists(False)
+
+
+@pytest.mark.parametrize('spec,p,n', [
+    (dict(code='Surface', d=9, noise='code capacity'), 0.12, 3000),
+    (dict(code='Surface', d=11, noise='phenomenological'), 0.03, 600),
+    (dict(code='Surface', d=7, noise='circuit-level'), 0.012, 1000),
+    (dict(code='Repetition', d=9, noise='phenomenological'), 0.08, 2000),
+], ids=['sf9cc', 'sf11phen', 'sf7cl', 'rep9'])
+def test_no_peel_needed_when_boundary_nodes_are_leaves(spec, p, n):
+    """Every boundary node of a Surface / Repetition graph has one edge.  The peel roots a cluster's tree at
+    cluster.boundary (uf.py:314-324); the cluster's other boundary nodes are leaves and no defects, so their
+    edges never enter the correction (uf.py:305-312), and the root's edge does iff the cluster is odd.  After
+    the merges in canonical order the pass over the defects (uf_peel_parity with g.leaf_bnd) therefore gives
+    the full peel's west parity on EVERY shot -- also on those with a cluster on both sides, for every flag
+    set and both tile shapes; the fused kernels never build the forest on such graphs."""
+    emu = emu_binding.Emu(make_code(spec))
+    for flags in (0, 1, 2, 3, 4, 6) + ((8, 12) if spec['noise'] == 'code capacity' else ()):
+        for nl in (32, 128):
+            full, sides, differ, mixed = emu.mc_uf_sides(flags, p, 7, n, nl=nl)
+            assert differ == 0 and full == sides
+            assert mixed > 0 or (flags & 1)          # (dynamic UF never joins two boundary clusters)
