@@ -56,6 +56,7 @@ static const uint32_t HARD = 2u;                         // result of a shot the
 // Read-only tables (global memory; fadj optionally staged in shared memory by the kernel).
 struct FView {
     int D, E, WD, DEG;          // detectors, edges, 32-bit words of a detector bitmap, row length of fadj (even)
+    uint32_t deg_magic;         // floor(2^32 / DEG) + 1: w / DEG == mulhi(w, deg_magic) for the item counts of a shot
     const uint32_t* fadj;       // [D][DEG] edge | other end << ebits | this is the edge's first endpoint << 31; other end =
                                 // detector index, or the two top values of its field: omask = west, omask - 1 = east
     uint32_t ebits, emask, omask;   // 16 / 0xFFFF / 0x7FFF up to 65533 edges; graphs with more edges and fewer detectors shift the split
@@ -277,17 +278,39 @@ LUF_DEV void f_for_nodes(const FView& g, const FLayout& l, const FShot& s, const
     }
 }
 
+template <bool ADJ_SHARED>
+LUF_DEV uint32_t f_entry(const FView& g, uint32_t v, uint32_t k)
+{
+    const uint32_t* p = g.fadj + (size_t)v * (uint32_t)g.DEG + k;
+    return ADJ_SHARED ? *p : LUF_LDG(p);
+}
+
+LUF_DEV void f_grow_first_entry(const FView& g, const FLayout& l, const FShot& s, uint32_t v, uint32_t ent)
+{
+    const uint32_t e = ent & g.emask, sh = (e & 15u) * 2u;
+    const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+    if (old == G_HALF) f_newfull(l, s, v, (ent >> g.ebits) & g.omask, 0u);       // (the other end grew too: a detector)
+}
+
 // Round 1 (uf.py:234-245): every defect adds 1 to each of its edges, no look-ups; an edge is newly FULL iff the
-// other end (a defect too, then) got there first.
+// other end (a defect too, then) got there first.  One lane per (defect, adjacency slot): a shot's defects
+// number about two per fault, fewer than a warp's lanes at the noise levels of interest, their slots several
+// times more.
 template <bool ADJ_SHARED>
 LUF_DEV void f_grow_first(const FView& g, const FLayout& l, const FShot& s, uint32_t nd, int lane, int nl)
 {
+    if (nd <= l.tcap) {
+        const uint32_t items = nd * (uint32_t)g.DEG;
+        LUF_NOUNROLL
+        for (uint32_t w = (uint32_t)lane; w < items; w += (uint32_t)nl) {
+            const uint32_t i = luf_mulhi(w, g.deg_magic), v = s.tlist[i];
+            const uint32_t ent = f_entry<ADJ_SHARED>(g, v, w - i * (uint32_t)g.DEG);
+            if (ent != ADJ_PAD) f_grow_first_entry(g, l, s, v, ent);
+        }
+        return;
+    }
     f_for_nodes(g, l, s, s.defect, nd, nd, lane, nl, [&](uint32_t v) {
-        f_row<ADJ_SHARED>(g, v, [&](uint32_t ent) {
-            const uint32_t e = ent & g.emask, sh = (e & 15u) * 2u;
-            const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-            if (old == G_HALF) f_newfull(l, s, v, (ent >> g.ebits) & g.omask, 0u);       // (the other end grew too: a detector)
-        });
+        f_row<ADJ_SHARED>(g, v, [&](uint32_t ent) { f_grow_first_entry(g, l, s, v, ent); });
     });
 }
 
@@ -301,25 +324,28 @@ LUF_DEV void f_touch(const FLayout& l, const FShot& s, uint32_t v)
 
 // Later rounds: a touched node whose cluster (root r) is active adds 1 to each of its edges that is not FULL;
 // an edge inside one cluster is counted once (only its first endpoint adds); the 2-bit counters saturate.
+LUF_DEV void f_grow_entry(const FView& g, const FLayout& l, const FShot& s, uint32_t u, uint32_t r, uint32_t ent, uint32_t mbase)
+{
+    const uint32_t e = ent & g.emask, sh = (e & 15u) * 2u;
+    if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
+    const uint32_t o = (ent >> g.ebits) & g.omask;
+    const bool detector = o < g.omask - 1u;
+    if (!(ent >> 31) && detector) {                // second endpoint of an edge between detectors: same cluster?
+        uint32_t wr;
+        if (o == r || ffind_ro(s, o, wr) == r) return;
+    }
+    const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
+    if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);
+    else if (old == G_HALF) {
+        f_newfull(l, s, u, detector ? o : (o == g.omask ? END_WEST : END_EAST), mbase);
+        if (detector) f_touch(l, s, o);
+    }
+}
+
 template <bool ADJ_SHARED>
 LUF_DEV void f_grow_node(const FView& g, const FLayout& l, const FShot& s, uint32_t u, uint32_t r, uint32_t mbase)
 {
-    f_row<ADJ_SHARED>(g, u, [&](uint32_t ent) {
-        const uint32_t e = ent & g.emask, sh = (e & 15u) * 2u;
-        if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
-        const uint32_t o = (ent >> g.ebits) & g.omask;
-        const bool detector = o < g.omask - 1u;
-        if (!(ent >> 31) && detector) {                // second endpoint of an edge between detectors: same cluster?
-            uint32_t wr;
-            if (o == r || ffind_ro(s, o, wr) == r) return;
-        }
-        const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-        if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);
-        else if (old == G_HALF) {
-            f_newfull(l, s, u, detector ? o : (o == g.omask ? END_WEST : END_EAST), mbase);
-            if (detector) f_touch(l, s, o);
-        }
-    });
+    f_row<ADJ_SHARED>(g, u, [&](uint32_t ent) { f_grow_entry(g, l, s, u, r, ent, mbase); });
 }
 
 template <bool ADJ_SHARED>
@@ -336,14 +362,17 @@ LUF_DEV void f_grow_filter(const FView& g, const FLayout& l, const FShot& s, uin
     });
 }
 
+// one lane per (active node, adjacency slot)
 template <bool ADJ_SHARED>
 LUF_DEV void f_grow_exec(const FView& g, const FLayout& l, const FShot& s, uint32_t na, uint32_t mbase, int lane, int nl)
 {
     if (na > l.acap) na = l.acap;
+    const uint32_t items = na * (uint32_t)g.DEG;
     LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < na; i += (uint32_t)nl) {
-        const uint32_t it = s.alist[i];
-        f_grow_node<ADJ_SHARED>(g, l, s, it & 0xFFFFu, it >> 16, mbase);
+    for (uint32_t w = (uint32_t)lane; w < items; w += (uint32_t)nl) {
+        const uint32_t i = luf_mulhi(w, g.deg_magic), it = s.alist[i];
+        const uint32_t ent = f_entry<ADJ_SHARED>(g, it & 0xFFFFu, w - i * (uint32_t)g.DEG);
+        if (ent != ADJ_PAD) f_grow_entry(g, l, s, it & 0xFFFFu, it >> 16, ent, mbase);
     }
 }
 

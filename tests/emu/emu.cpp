@@ -294,7 +294,7 @@ int emu_mc_uf_compact(const luf_graph_desc* d, int west, const double* class_p, 
         for (int c = 0, lo = 0; c < p.n_classes; ++c) { mu += class_p[c] * ((int)p.class_end[c] - lo); lo = (int)p.class_end[c]; }
     }
     fast::FView g;
-    g.D = pf.D; g.E = pf.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
+    g.D = pf.D; g.E = pf.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.deg_magic = (uint32_t)(0x100000000ull / (uint64_t)pf.DEG) + 1u; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
     g.ebits = pf.ebits; g.emask = pf.emask; g.omask = pf.omask;
     g.F = pf.F; g.n_classes = pf.n_classes;
     g.fresh_perm = nullptr; g.fresh_perm32 = pf.perm_identity ? nullptr : pf.fresh_perm32.data(); g.class_end = pf.class_end.data();
@@ -316,7 +316,7 @@ int emu_sample_compact(const luf_graph_desc* d, const double* class_p, unsigned 
     pack_fast(*d, pf);
     if (!pf.ok) return -2;
     fast::FView g;
-    g.D = pf.D; g.E = pf.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
+    g.D = pf.D; g.E = pf.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.deg_magic = (uint32_t)(0x100000000ull / (uint64_t)pf.DEG) + 1u; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
     g.ebits = pf.ebits; g.emask = pf.emask; g.omask = pf.omask; g.F = pf.F; g.n_classes = pf.n_classes;
     g.fresh_perm = nullptr; g.fresh_perm32 = pf.perm_identity ? nullptr : pf.fresh_perm32.data(); g.class_end = pf.class_end.data();
     g.west = 0;

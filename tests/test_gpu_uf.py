@@ -226,8 +226,19 @@ def test_python_api_drop_in():
 
 
 def test_graph_too_large_is_reported():
+    """Beyond the 16-bit layout the canonical kernels do not apply: the graph is accepted for the compact path
+    (tests/test_gpu_large.py) and every canonical entry point says why it cannot run; a graph that not even the
+    compact tables hold (more than 32766 detectors) is refused at creation."""
     import localuf_b200 as L
     from localuf_b200 import _engine
-    big = L.Surface(23, 'circuit-level')          # E > 65533: 16-bit state layout does not apply
+    big = L.Surface(23, 'circuit-level')          # E > 65533
+    eng = _engine.Engine(big, device=0)
+    with pytest.raises(NotImplementedError, match='16-bit layout'):
+        eng.mc_run_host(_engine.DEC_UF, 0, 0.001, 1, 0, 10)           # default inclination: needs the canonical kernels
+    with pytest.raises(NotImplementedError, match='16-bit layout'):
+        eng.mc_run_host(_engine.DEC_MACAR, 0, 0.001, 1, 0, 10)
     with pytest.raises(NotImplementedError):
-        _engine.Engine(big, device=0)
+        eng.sample_weight_host(3, 1, 0, 10)
+    huge = L.Surface(11, 'phenomenological', scheme='global batch', window_height=11 * 30)     # 36300 detectors
+    with pytest.raises(NotImplementedError):
+        _engine.Engine(huge, device=0)
