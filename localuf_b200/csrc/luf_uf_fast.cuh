@@ -119,8 +119,9 @@ LUF_DEV uint32_t pload(const FShot& s, uint32_t v) { return *(volatile uint16_t*
 LUF_DEV uint32_t ffind_ro(const FShot& s, uint32_t v, uint32_t& wr)
 {
     uint32_t w;
+    LUF_STAT(20, 1);
     LUF_NOUNROLL
-    while (!((w = pload(s, v)) & P_ROOT)) v = w;
+    while (!((w = pload(s, v)) & P_ROOT)) { v = w; LUF_STAT(21, 1); }
     wr = w;
     return v;
 }
@@ -130,11 +131,13 @@ LUF_DEV uint32_t ffind_ro(const FShot& s, uint32_t v, uint32_t& wr)
 LUF_DEV uint32_t ffind(const FShot& s, uint32_t v, uint32_t& wr)
 {
     const uint32_t w = pload(s, v);
+    LUF_STAT(22, 1);
     if (w & P_ROOT) { wr = w; return v; }
     uint32_t r = w, q;
     int hops = 0;
+    LUF_STAT(23, 1);
     LUF_NOUNROLL
-    while (!((q = pload(s, r)) & P_ROOT)) { r = q; ++hops; }
+    while (!((q = pload(s, r)) & P_ROOT)) { r = q; ++hops; LUF_STAT(23, 1); }
     if (hops) s.P[v] = (uint16_t)r;
     wr = q;
     return r;

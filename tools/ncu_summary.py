@@ -34,7 +34,8 @@ def main():
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
-    row = next(r for r in rows[2:] if kernel in ' '.join(r[:8]))
+    which = next(i for i, r in enumerate(rows[2:]) if kernel in ' '.join(r[:8]))     # the first profiled launch that matches
+    row = rows[2 + which]
     for k in KEYS:
         if k in hdr:
             i = hdr.index(k)
@@ -61,9 +62,11 @@ def main():
         return name
 
     rows = list(csv.reader(open(tmp)))
-    hi = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
+    heads = [i for i, r in enumerate(rows) if r and r[0] == 'Address']       # one table per profiled launch, in order
+    hi = heads[which] if which < len(heads) else heads[0]
+    end = heads[heads.index(hi) + 1] if heads.index(hi) + 1 < len(heads) else len(rows)
     h = rows[hi]; col = {x: i for i, x in enumerate(h)}
-    body = [r for r in rows[hi + 1:] if len(r) == len(h)]
+    body = [r for r in rows[hi + 1:end] if len(r) == len(h)]
     table = ncu_lines.line_table(so, mangled, len(body))      # the instance whose SASS ncu profiled
     agg, tot = {}, [0, 0, 0]
     for k, r in enumerate(body):
