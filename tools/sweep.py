@@ -8,14 +8,19 @@ scheme) and Snowflake (circuit-level, frugal scheme), through the reference's ow
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
            tools/sweep.py ...                      # the shots of every point shard over the ranks
 
-Every (decoder, d, p) point is run in rounds: round r calls ``monte_carlo({d: [(p, n)]}, ...)`` after
-``random.seed(seed + r)`` -- the reference's reproducibility contract; under torchrun ``SCHEME.run`` shards the
-n shots over the ranks and all-reduces the counters (NCCL).  After every round rank 0 rewrites the resume file
-``{point: {seed, rounds, shots_done, fails, seconds}}``; a restarted sweep skips what is done and continues the
-round numbering, so a resumed run draws the noise an uninterrupted one would have drawn.  n is chosen per point
-from a probe round so that a point takes about ``--seconds`` (the 10^9 shots per point of BASELINE.json need
-hours near threshold at d = 25; reduced counts are what this tool is for).  Output: a table per decoder with
-shots, failures, rate and shots/s per point, and the crossing of consecutive distances.
+UF: per distance, rounds of ONE ``monte_carlo({d: [(p, n_p), ...]}, Surface, UF, 'phenomenological')`` call over
+the distance's open points -- a warm-up and a probe round of a few thousand shots, then the main round with n_p
+chosen from the probe so that a point takes about ``--seconds`` (the 10^9 shots per point of BASELINE.json need
+hours near threshold at d = 25; reduced counts are what this tool is for).  ``random.seed(seed + round)``
+precedes every call -- the reference's reproducibility contract; under torchrun ``SCHEME.run`` shards the shots
+of every point over the ranks and all-reduces the counters (NCCL).  The time of a point is the wall time of
+its ``Scheme.run`` call inside ``monte_carlo`` (a timing wrapper around ``Batch.run`` / ``Frugal.run``; maximum
+over the ranks).  Snowflake: ``monte_carlo``'s n is the LENGTH of one memory experiment (``Frugal.run``,
+_schemes.py:566-649) -- one window, one thread block; the sweep runs many experiments of n = 1 side by side
+instead (``SCHEME.run(decoder, p, 1, shots=n)``).  After every distance (UF) / point (Snowflake) rank 0 rewrites
+the resume file ``{point: {seed, rounds, shots_done, fails, seconds}}``; a restarted sweep skips what is done
+and continues the round numbering.  Output: a table per decoder with shots, failures, rate and units/s per
+point, and the crossing of consecutive distances.
 """
 import argparse
 import json
@@ -80,63 +85,107 @@ def main():
                 json.dump(state, f, indent=1)
             os.replace(tmp, a.resume)
 
-    def one_round(dec_name, d, p, n, entry):
-        """monte_carlo on n shots with the round's seed; every rank calls it (the shots shard inside)."""
-        grid = GRIDS[dec_name]
-        random.seed(entry['seed'] + entry['rounds'])
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        if dec_name == 'Snowflake':      # one "shot" = one Frugal.run(n=1) memory experiment
-            code, decoder = decoders[d]
-            m, _ = code.SCHEME.run(decoder, p, 1, shots=n)
-        else:
-            df = L.sim.accuracy.monte_carlo({d: [(p, n)]}, L.Surface, L.decoders.UF, grid['noise'], scheme=grid['scheme'])
-            m = int(df.loc['m', (d, p)])
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        entry['rounds'] += 1; entry['shots_done'] += n; entry['fails'] += int(m); entry['seconds'] += float(dt.item())
-        return float(dt.item())
+    # per-call wall time of Scheme.run, taken inside monte_carlo (it builds code, decoder and engine once per
+    # distance and then calls run for every (p, n) of that distance)
+    run_times = []
+
+    def timed(cls):
+        inner = cls.run
+
+        def run(self, *args, **kw):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = inner(self, *args, **kw)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            run_times.append(float(dt.item()))
+            return out
+        cls.run = run
+    timed(L.schemes.Batch)
+    timed(L.schemes.Frugal)
+
+    def book(entry, n, m, dt):
+        entry['rounds'] += 1; entry['shots_done'] += n; entry['fails'] += int(m); entry['seconds'] += dt
+
+    def report(dec_name, d, p, entry):
+        if rank == 0:
+            timed_shots = entry['shots_done'] - entry.get('probe_shots', 0)
+            print(f"{dec_name:9s} d={d:2d} p={p:.5f} shots={entry['shots_done']:10d} fails={entry['fails']:9d} "
+                  f"rate={entry['fails'] / entry['shots_done']:.3e} {timed_shots / max(entry['seconds'], 1e-9) / 1e6:9.4f} M shots/s",
+                  flush=True)
 
     names = ['UF', 'Snowflake'] if a.decoder == 'both' else [a.decoder]
     ds = [int(x) for x in a.ds.split(',')]
     for dec_name in names:
         grid = GRIDS[dec_name]
-        decoders = {}
+        ps = [round(p, 6) for p in grid['ps']]
         for d in ds:
-            if dec_name == 'Snowflake':
-                code = L.Surface(d, grid['noise'], scheme='frugal')
-                decoders[d] = (code, L.decoders.Snowflake(code))
-            for p in grid['ps']:
-                p = round(p, 6)
-                key = f'{dec_name}|{d}|{p}'
-                entry = state.setdefault(key, {'seed': a.seed + 7919 * d + int(round(p * 1e6)), 'rounds': 0,
-                                               'shots_done': 0, 'fails': 0, 'seconds': 0.0, 'target_seconds': 0.0})
-                if entry['rounds'] >= 2 and entry['target_seconds'] >= a.seconds:
-                    continue                                     # done in an earlier run
-                probe = a.probe or (256 * world if dec_name == 'Snowflake' else 4096 * world)
-                if entry['rounds'] == 0:
-                    one_round(dec_name, d, p, probe, entry)      # warm-up: graph upload, launch plans, first timing
-                    entry['seconds'] = 0.0                       # (its time is not representative)
-                    entry['probe_shots'] = probe
-                    t = one_round(dec_name, d, p, probe, entry)
-                else:
-                    t = entry['seconds'] / max(entry['rounds'] - 1, 1)
-                    probe = max(1, (entry['shots_done'] - entry.get('probe_shots', 0)) // max(entry['rounds'] - 1, 1))
-                n = int(min(a.max_shots, max(probe, probe * a.seconds / max(t, 1e-4))))
-                n -= n % world
-                one_round(dec_name, d, p, max(n, world), entry)
-                entry['target_seconds'] = a.seconds
+            entries = {p: state.setdefault(f'{dec_name}|{d}|{p}', {'seed': a.seed + 7919 * d + int(round(p * 1e6)), 'rounds': 0,
+                                                                  'shots_done': 0, 'fails': 0, 'seconds': 0.0, 'target_seconds': 0.0})
+                       for p in ps}
+            todo = [p for p in ps if not (entries[p]['rounds'] >= 2 and entries[p]['target_seconds'] >= a.seconds)]
+            if not todo:
+                continue                                         # done in an earlier run
+            probe = a.probe or (256 * world if dec_name == 'Snowflake' else 16384 * world)
+            if dec_name == 'UF':
+                # rounds of ONE monte_carlo call over the distance's open points (warm-up, probe, main)
+                def mc_round(counts):
+                    """counts: {p: n}; every point uses its own round number as the seed offset"""
+                    run_times.clear()
+                    random.seed(entries[todo[0]]['seed'] + entries[todo[0]]['rounds'])
+                    df = L.sim.accuracy.monte_carlo({d: [(p, counts[p]) for p in todo]}, L.Surface, L.decoders.UF,
+                                                    grid['noise'], scheme=grid['scheme'])
+                    return {p: (int(df.loc['m', (d, p)]), run_times[k]) for k, p in enumerate(todo)}
+                fresh = [p for p in todo if entries[p]['rounds'] == 0]
+                if fresh:
+                    out = mc_round({p: probe for p in todo})                 # warm-up: graph upload, launch plans
+                    for p in fresh:
+                        book(entries[p], probe, out[p][0], 0.0)
+                        entries[p]['probe_shots'] = probe
+                out = mc_round({p: probe for p in todo})                     # probe: the time of a small call
+                n_of = {}
+                for p in todo:
+                    n_of[p] = int(min(a.max_shots, max(probe, probe * a.seconds / max(out[p][1], 1e-5))))
+                    n_of[p] -= n_of[p] % world
+                    book(entries[p], probe, out[p][0], 0.0)
+                    entries[p]['probe_shots'] = entries[p].get('probe_shots', 0) + probe
+                out = mc_round(n_of)
+                for p in todo:
+                    book(entries[p], n_of[p], out[p][0], out[p][1])
+                    entries[p]['target_seconds'] = a.seconds
+                    report(dec_name, d, p, entries[p])
                 save()
-                if rank == 0:
-                    timed = entry['shots_done'] - entry['probe_shots']
-                    print(f"{dec_name:9s} d={d:2d} p={p:.5f} shots={entry['shots_done']:10d} fails={entry['fails']:9d} "
-                          f"rate={entry['fails'] / entry['shots_done']:.3e} {timed / max(entry['seconds'], 1e-9) / 1e6:9.4f} M shots/s",
-                          flush=True)
-            decoders.pop(d, None)
+            else:
+                # Snowflake: monte_carlo's n is the LENGTH of one memory experiment (Frugal.run, _schemes.py:566-649),
+                # one window = one thread block; the sweep runs many experiments of n = 1 side by side instead
+                code = L.Surface(d, grid['noise'], scheme='frugal')
+                decoder = L.decoders.Snowflake(code)
+                for p in todo:
+                    entry = entries[p]
+
+                    def sf_round(n):
+                        run_times.clear()
+                        random.seed(entry['seed'] + entry['rounds'])
+                        m, _ = code.SCHEME.run(decoder, p, 1, shots=n)
+                        return int(m), run_times[-1]
+                    if entry['rounds'] == 0:
+                        m, _ = sf_round(probe)
+                        book(entry, probe, m, 0.0)
+                        entry['probe_shots'] = probe
+                    m, t = sf_round(probe)
+                    book(entry, probe, m, 0.0)
+                    entry['probe_shots'] = entry.get('probe_shots', 0) + probe
+                    n = int(min(a.max_shots, max(probe, probe * a.seconds / max(t, 1e-5))))
+                    n -= n % world
+                    m, t = sf_round(max(n, world))
+                    book(entry, max(n, world), m, t)
+                    entry['target_seconds'] = a.seconds
+                    report(dec_name, d, p, entry)
+                    save()
     if rank == 0:
         for dec_name in names:
             grid = GRIDS[dec_name]
