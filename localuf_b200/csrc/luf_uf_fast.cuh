@@ -23,8 +23,9 @@
 // interleaving.  Every change of a root word is one atomic transition, and each one adjusts the count of
 // active clusters (odd, no boundary) by the difference it makes -- the round loop ends when that count is 0.
 //
-// A shot in which a cluster comes to touch both sides is reported as HARD under the default inclination (which
-// boundary node roots the peeling tree depends on the merge order); the caller queues it for the canonical
+// A shot that ends with an ODD cluster touching both sides is reported as HARD under the default inclination
+// (which boundary node such a cluster keeps, and so where its one string to the boundary goes, depends on the
+// merge order; an even cluster on both sides adds nothing either way); the caller queues it for the canonical
 // kernel.  Under the west inclination (uf.py:544-549) such a cluster keeps a west boundary node; that node has
 // one edge, every defect's path to the root runs through it, so the cluster adds its defect parity like any
 // other that touches the west side -- no HARD shots at all.  A work list that overflows is not fatal either:
@@ -48,8 +49,8 @@ static const uint32_t END_WEST = 0xFFFFu, END_EAST = 0xFFFEu;         // edge ta
 static const int MAX_DETECTORS = 0x7FFE;                              // a non-root word is a parent index below 0x8000
 // cnt[]: fill counters of the three lists (they only grow: a round's entries start at the previous total; a
 // counter beyond its capacity says the list overflowed), the number of active clusters, the parity
-// accumulator, and the HARD flag (a cluster touches both sides; written by the merge phase only, read after
-// the barrier that ends it -- never written by the phase that follows).
+// accumulator, and the HARD flag (an odd cluster on both sides; written by the last phase only, read after the
+// barrier that ends it).
 enum { C_TOUCHED = 0, C_ALIST = 1, C_MLIST = 2, C_ACTIVE = 3, C_PARITY = 5, C_HARD_M = 6 };
 static const uint32_t HARD = 2u;                         // result of a shot the canonical kernel has to decode
 
@@ -155,7 +156,6 @@ LUF_DEV void add_bits(const FShot& s, uint32_t v, uint32_t bits, int west)
         if (cas16(s.P, r, w, nw)) {
             const int delta = (nw == P_ACTIVE ? 1 : 0) - (w == P_ACTIVE ? 1 : 0);
             if (delta) luf_atomic_add(&s.cnt[C_ACTIVE], (uint32_t)delta);
-            if (!west && (nw & (P_WEST | P_EAST)) == (P_WEST | P_EAST)) s.cnt[C_HARD_M] = 1u;    // both sides: the forest matters
             return;
         }
         v = r;
@@ -379,25 +379,76 @@ LUF_DEV void f_grow_exec(const FView& g, const FLayout& l, const FShot& s, uint3
     }
 }
 
-// uf.py:223-229 in any order: one lane per newly FULL edge.  A round with more of them than the list holds
-// joins every fully grown edge of the growth words instead (an edge joined before is inside one cluster by now:
-// nothing happens), endpoints from the edge table.
+// uf.py:223-229 in any order, two phases over the list of newly FULL edges.
+//   hook   one lane per edge: the root of larger index goes below the other (compare-and-swap on its word, which
+//          is read back as the payload: the bits the hooked cluster carried); an edge to a boundary node has its
+//          side as the payload.  The list entry becomes (node to credit | payload << 16 | valid).
+//   apply  roots do not move in this phase, so a payload is added to the root of its node with plain atomic
+//          OR / XOR on the word's 32-bit container -- no compare-and-swap loop -- and the old value each atomic
+//          returns gives the change in the number of active clusters.
+static const uint32_t PAY_VALID = 0x80000000u;
+
+LUF_DEV void f_hook(const FShot& s, uint32_t nm, int lane, int nl)
+{
+    int dact = 0;
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < nm; i += (uint32_t)nl) {
+        const uint32_t it = s.mlist[i];
+        const uint32_t a = it & 0xFFFFu, b = it >> 16;
+        if (b >= END_EAST) { s.mlist[i] = a | ((b == END_WEST ? P_WEST : P_EAST) << 16) | PAY_VALID; continue; }
+        uint32_t out = 0;
+        LUF_NOUNROLL
+        for (;;) {
+            uint32_t wa, wb;
+            uint32_t ra = ffind(s, a, wa), rb = ffind(s, b, wb);
+            if (ra == rb) break;
+            if (ra > rb) { uint32_t t = ra; ra = rb; rb = t; wb = wa; }
+            if (!cas16(s.P, rb, wb, ra)) continue;
+            if (wb == P_ACTIVE) --dact;
+            if (wb & (P_ODD | P_WEST | P_EAST)) out = ra | ((wb & (P_ODD | P_WEST | P_EAST)) << 16) | PAY_VALID;
+            break;
+        }
+        s.mlist[i] = out;
+    }
+    if (dact) luf_atomic_add(&s.cnt[C_ACTIVE], (uint32_t)dact);
+}
+
+LUF_DEV void f_apply(const FView& g, const FShot& s, uint32_t nm, int lane, int nl)
+{
+    int dact = 0;
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < nm; i += (uint32_t)nl) {
+        const uint32_t it = s.mlist[i];
+        if (!(it & PAY_VALID)) continue;
+        const uint32_t bits = (it >> 16) & (P_ODD | P_WEST | P_EAST);
+        uint32_t w;
+        const uint32_t r = ffind_ro(s, it & 0xFFFFu, w);
+        uint32_t* wp = (uint32_t*)s.P + (r >> 1);
+        const uint32_t sh = (r & 1u) * 16u;
+        if (bits & (P_WEST | P_EAST)) {
+            const uint32_t old = (luf_atomic_or(wp, (bits & (P_WEST | P_EAST)) << sh) >> sh) & 0xFFFFu;
+            const uint32_t nw = old | (bits & (P_WEST | P_EAST));
+            dact += (nw == P_ACTIVE ? 1 : 0) - (old == P_ACTIVE ? 1 : 0);
+        }
+        if (bits & P_ODD) {
+            const uint32_t old = (luf_atomic_xor(wp, P_ODD << sh) >> sh) & 0xFFFFu;
+            dact += ((old ^ P_ODD) == P_ACTIVE ? 1 : 0) - (old == P_ACTIVE ? 1 : 0);
+        }
+    }
+    if (dact) luf_atomic_add(&s.cnt[C_ACTIVE], (uint32_t)dact);
+}
+
+// A round with more newly FULL edges than the list holds joins every fully grown edge of the growth words in one
+// phase instead (compare-and-swap payloads; an edge joined before is inside one cluster by now: nothing
+// happens), endpoints from the edge table.
 LUF_DEV void f_merge_pair(const FView& g, const FShot& s, uint32_t a, uint32_t b)
 {
     if (b >= END_EAST) add_bits(s, a, b == END_WEST ? P_WEST : P_EAST, g.west);
     else join(s, a, b, g.west);
 }
 
-LUF_DEV void f_merge(const FView& g, const FLayout& l, const FShot& s, uint32_t nm, int lane, int nl)
+LUF_DEV void f_merge_overflow(const FView& g, const FShot& s, int lane, int nl)
 {
-    if (nm <= l.mcap) {
-        LUF_NOUNROLL
-        for (uint32_t i = (uint32_t)lane; i < nm; i += (uint32_t)nl) {
-            const uint32_t it = s.mlist[i];
-            f_merge_pair(g, s, it & 0xFFFFu, it >> 16);
-        }
-        return;
-    }
     const int GW = (g.E + 15) >> 4;
     LUF_NOUNROLL
     for (int w = lane; w < GW; w += nl) {
@@ -421,6 +472,10 @@ LUF_DEV uint32_t f_defect_sides(const FView& g, const FLayout& l, const FShot& s
         uint32_t wr;
         ffind_ro(s, v, wr);
         parity ^= (wr >> 1) & 1u;
+        // an ODD cluster on both sides adds its parity iff the boundary node it kept is a west one: under the
+        // default inclination that depends on the order of the merges (an even one adds 0 either way, and
+        // under the west inclination the node kept is a west one: the line above is right)
+        if (!g.west && (wr & (P_ODD | P_WEST | P_EAST)) == (P_ODD | P_WEST | P_EAST)) s.cnt[C_HARD_M] = 1u;
     });
     return parity;
 }
@@ -468,9 +523,13 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
             ++rounds;
             const uint32_t nm = s.cnt[C_MLIST] - mbase;
             if (nm > most_m) most_m = nm;
-            FT_PHASE(f_merge(g, l, s, nm, lane, nl));
+            if (nm <= l.mcap) {
+                FT_PHASE(f_hook(s, nm, lane, nl));
+                FT_PHASE(f_apply(g, s, nm, lane, nl));
+            } else {
+                FT_PHASE(f_merge_overflow(g, s, lane, nl));
+            }
             mbase += nm;
-            if (s.cnt[C_HARD_M]) return HARD;            // (uniform: every lane reads the same word after the barrier)
             if (!s.cnt[C_ACTIVE]) break;
             const uint32_t nt = s.cnt[C_TOUCHED];
             FT_PHASE(f_grow_filter<ADJ_SHARED>(g, l, s, nt, abase, mbase, lane, nl));
@@ -480,6 +539,7 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
             abase += na;
         }
         FT_PHASE(const uint32_t par = f_defect_sides(g, l, s, nd, lane, nl); if (par) luf_atomic_xor(&s.cnt[C_PARITY], 1u));
+        if (s.cnt[C_HARD_M]) return HARD;                // (uniform: every lane reads the same word after the barrier)
     }
     if (stats) { stats[0] = rounds; stats[1] = s.cnt[C_TOUCHED]; stats[2] = most_m; stats[3] = most_a; }
     return s.cnt[C_PARITY] & 1u;
