@@ -77,6 +77,11 @@
   #define LUF_SUM(x) (x)
   static inline uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
   static inline uint32_t luf_atomic_cas(uint32_t* p, uint32_t expect, uint32_t v) { uint32_t o = *p; if (o == expect) *p = v; return o; }
+  // 64-bit words of the wide layout (luf_uf_wide.cuh)
+  static inline uint64_t luf_atomic_add(uint64_t* p, uint64_t v) { uint64_t o = *p; *p = o + v; return o; }
+  static inline uint64_t luf_atomic_min(uint64_t* p, uint64_t v) { uint64_t o = *p; if (v < o) *p = v; return o; }
+  static inline uint64_t luf_atomic_cas(uint64_t* p, uint64_t expect, uint64_t v) { uint64_t o = *p; if (o == expect) *p = v; return o; }
+  #define LUF_LDG64(p) (*(p))
 #else
   #define LUF_DEV __device__ __forceinline__
   #define LUF_MEM __device__ __forceinline__
@@ -108,6 +113,11 @@
   #define LUF_SUM(x) __reduce_add_sync(0xffffffffu, (x))
   LUF_DEV uint32_t luf_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
   LUF_DEV uint32_t luf_atomic_cas(uint32_t* p, uint32_t expect, uint32_t v) { return atomicCAS(p, expect, v); }
+  // 64-bit words of the wide layout (luf_uf_wide.cuh)
+  LUF_DEV uint64_t luf_atomic_add(uint64_t* p, uint64_t v) { return atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+  LUF_DEV uint64_t luf_atomic_min(uint64_t* p, uint64_t v) { return atomicMin((unsigned long long*)p, (unsigned long long)v); }
+  LUF_DEV uint64_t luf_atomic_cas(uint64_t* p, uint64_t expect, uint64_t v) { return atomicCAS((unsigned long long*)p, (unsigned long long)expect, (unsigned long long)v); }
+  #define LUF_LDG64(p) ((uint64_t)__ldg((const unsigned long long*)(p)))
 #endif
 
 // Optional event counters of the host emulation (tools/uf_stats.py); compiled out everywhere else.

@@ -14,6 +14,7 @@
 #include "../../include/luf_b200.h"
 #include "luf_core.cuh"
 #include "luf_uf_fast.cuh"
+#include "luf_uf_wide.cuh"
 #include "luf_ca.cuh"
 #include "luf_sf.cuh"
 #include "luf_fw.cuh"
@@ -118,6 +119,95 @@ inline Layout make_layout(int N, int B, int E, bool keep_err, bool keep_corr, ui
     l.claim = take(4u * (claim_slots > WN ? claim_slots : WN));   // visited bitmap of the peel
     l.list = take(4u * list_cap); l.list2 = take(4u * list2_cap); l.cnt = take(32);
     l.bytes = off;
+    return l;
+}
+
+// ------------------------------------------------- wide instance (luf_uf_wide.cuh)
+struct PackedWide {
+    int N = 0, B = 0, E = 0, F = 0, n_classes = 0, DEG = 0;
+    bool perm_identity = false, parity_ok = true;
+    std::vector<uint64_t> adj, edge_uv;
+    std::vector<uint32_t> west_mask, class_end, fresh_perm32;
+    std::vector<int16_t> node_long;
+};
+
+// pack_graph for graphs of any size the description's 32-bit integers can name.  Returns "" on success.
+inline std::string pack_wide(const luf_graph_desc& d, PackedWide& out)
+{
+    const int N = d.n_nodes, B = d.n_boundary, E = d.n_edges;
+    if (N <= 0 || E <= 0 || B < 0 || B > N) return "empty or inconsistent graph";
+    if (N > 0x7FFFFFF0 || E > 0x7FFFFFF0) return "graph too large";
+    if (d.n_classes < 1 || d.n_classes > MAX_CLASSES) return "n_classes out of range";
+    out.N = N; out.B = B; out.E = E; out.n_classes = d.n_classes;
+    out.edge_uv.assign(E, 0);
+    out.node_long.assign(N, 0);
+    for (int e = 0; e < E; ++e) {
+        const int u = d.edge_u[e], v = d.edge_v[e];
+        if (u < 0 || u >= N || v < 0 || v >= N) return "edge endpoint out of range";
+        out.edge_uv[e] = (uint64_t)(uint32_t)u | ((uint64_t)(uint32_t)v << 32);
+    }
+    for (int v = 0; v < N; ++v) {
+        if (((d.node_flags[v] & 1) != 0) != (v < B)) return "boundary nodes must be node indices [0, B)";
+        if (d.node_long[v] < -32768 || d.node_long[v] > 32767) return "node coordinate out of range";
+        out.node_long[v] = (int16_t)d.node_long[v];
+    }
+    if (d.inc_off[N] != 2 * E) return "CSR size mismatch";
+    int deg = 1;
+    for (int v = 0; v < N; ++v) deg = std::max(deg, d.inc_off[v + 1] - d.inc_off[v]);
+    out.DEG = deg;
+    out.adj.assign((size_t)N * out.DEG, uf_wide::ADJ_PAD64);
+    for (int v = 0; v < N; ++v) {
+        int prev = -1;
+        for (int k = d.inc_off[v]; k < d.inc_off[v + 1]; ++k) {
+            const int e = d.inc_edge[k], o = d.inc_other[k];
+            if (e <= prev || e >= E) return "incident edges must ascend in edge id";
+            prev = e;
+            const bool first = d.edge_u[e] == v;
+            if ((first ? d.edge_v[e] : d.edge_u[e]) != o || (!first && d.edge_v[e] != v))
+                return "CSR entry does not match the edge list";
+            out.adj[(size_t)v * out.DEG + (k - d.inc_off[v])] =
+                (uint64_t)(uint32_t)e | ((uint64_t)(uint32_t)o << 32) | (first ? 0x8000000000000000ull : 0ull);
+        }
+    }
+    out.west_mask.assign(d.west_edge_mask, d.west_edge_mask + words32(E));
+    out.parity_ok = true;               // as pack_graph
+    for (int e = 0; e < E; ++e) {
+        const int u = d.edge_u[e], v = d.edge_v[e];
+        const bool west_first = u < B && d.node_long[u] == -1, west_second = v < B && d.node_long[v] == -1;
+        const bool masked = (d.west_edge_mask[e >> 5] >> (e & 31)) & 1u;
+        if ((u < B && v < B) || west_second || masked != west_first) { out.parity_ok = false; break; }
+    }
+    out.class_end.assign(d.n_classes, 0);
+    out.fresh_perm32.clear();
+    for (int c = 0; c < d.n_classes; ++c) {
+        for (int e = 0; e < E; ++e)
+            if (d.edge_class[e] == c) out.fresh_perm32.push_back((uint32_t)e);
+        out.class_end[c] = (uint32_t)out.fresh_perm32.size();
+    }
+    out.F = (int)out.fresh_perm32.size();
+    out.perm_identity = out.F == E;
+    for (int k = 0; k < out.F && out.perm_identity; ++k) out.perm_identity = out.fresh_perm32[k] == (uint32_t)k;
+    return "";
+}
+
+inline uf_wide::Layout make_wide_layout(int N, int B, int E, bool keep_err, bool keep_corr, uint32_t list_cap = LUF_WIDE_LIST_CAP,
+                                        uint32_t list2_cap = LUF_WIDE_LIST2_CAP, uint32_t claim_slots = LUF_WIDE_CLAIM_SLOTS)
+{
+    uf_wide::Layout l;
+    uint32_t off = 0;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off = (off + bytes + 15u) & ~15u; return o; };
+    const uint32_t WE = words32(E), WD = words32(N - B) ? words32(N - B) : 1, WN = words32(N);
+    l.S = take(8u * (uint32_t)N);
+    l.zero_off = off;                                 // ---- cleared by ph_reset
+    l.growth = take(4u * ((E + 15) / 16));
+    l.newfull = take(4u * (WE > WN ? WE : WN));
+    l.defect = take(4u * WD); l.full1 = take(4u * WN); l.full2 = take(4u * WN);
+    l.err = keep_err ? take(4u * WE) : 0;
+    l.corr = keep_corr ? take(4u * WE) : 0;
+    l.zero_bytes = off - l.zero_off;                  // ----
+    l.claim = take(std::max(8u * claim_slots, 4u * WN));   // visited bitmap of the peel
+    l.list = take(8u * list_cap); l.list2 = take(8u * list2_cap); l.cnt = take(32);
+    l.bytes = (off + 127u) & ~127u;                   // slabs of consecutive blocks start on their own cache lines
     return l;
 }
 

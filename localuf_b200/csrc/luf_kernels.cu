@@ -744,6 +744,167 @@ __global__ void k_count_strings(GraphView g, long long nshots, const uint32_t* _
     if (lane == 0 && sum) atomicAdd(total, sum);
 }
 
+// ------------------------------------------------------------ wide instance (luf_uf_wide.cuh)
+// Graphs beyond the 16-bit layout: one thread block per shot, 64-bit node words, the shot's state slab in the
+// block's dynamic shared memory (slab == nullptr) or in global memory at slab + blockIdx.x * l.bytes -- the
+// state-spill tile; a persistent grid keeps the slabs of all blocks in L2.  The first warp samples (32 sampler
+// lanes whatever the tile: the random stream of the 16-bit kernels).
+__device__ __forceinline__ unsigned char* wide_state(const uf_wide::Layout& l, unsigned char* slab)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    return slab ? slab + (size_t)blockIdx.x * l.bytes : smem;
+}
+
+// Staged K2 (uf.py:106-119): syndromes in, corrections (+ growth, rounds) out.
+__global__ void __launch_bounds__(512, 2) k_decode_uf_wide(uf_wide::GraphView g, uf_wide::Layout l, int flags, long long nshots,
+                            const uint32_t* __restrict__ syn, uint32_t* __restrict__ corr,
+                            uint32_t* __restrict__ growth2b, int32_t* __restrict__ steps, unsigned char* slab)
+{
+    const int lane = threadIdx.x, nl = blockDim.x;
+    const uf_wide::Shot s = uf_wide::bind(l, wide_state(l, slab));
+    const int GW = (g.E + 15) >> 4;
+    for (long long k = blockIdx.x; k < nshots; k += gridDim.x) {
+        uf_wide::ph_reset(g, l, s, lane, nl);
+        __syncthreads();
+        for (int w = lane; w < g.WD; w += nl) s.defect[w] = __ldg(&syn[k * g.WD + w]);
+        __syncthreads();
+        uf_wide::ph_load(g, s, lane, nl);
+        __syncthreads();
+        const int rounds = uf_wide::uf_validate_t<-1>(g, s, flags, lane, nl);
+        if (growth2b)
+            for (int w = lane; w < GW; w += nl) growth2b[k * GW + w] = s.growth[w];
+        uf_wide::uf_peel(g, s, lane, nl);
+        for (int w = lane; w < g.WE; w += nl) corr[k * g.WE + w] = s.corr[w];
+        if (steps && lane == 0) { steps[2 * k] = rounds; steps[2 * k + 1] = 0; }
+        __syncthreads();
+    }
+}
+
+// Fused K1 + K2 + K4 (_schemes.py:116-155), canonical order.  QUEUE: the launch behind k_mc_uf_fast (as k_mc_uf).
+template <bool QUEUE>
+__global__ void __launch_bounds__(512, 2) k_mc_uf_wide(uf_wide::GraphView g, uf_wide::Layout l, SampleParams sp, int flags,
+                        unsigned long long shot0, long long nshots, unsigned long long* counts,
+                        uint8_t* __restrict__ logical, const uint32_t* __restrict__ queue,
+                        const uint32_t* __restrict__ qcount, unsigned char* slab)
+{
+    const int lane = threadIdx.x, nl = blockDim.x;
+    const uf_wide::Shot s = uf_wide::bind(l, wide_state(l, slab));
+    unsigned int fails = 0;
+    if (QUEUE) nshots = (long long)*qcount;
+    for (long long i = blockIdx.x; i < nshots; i += gridDim.x) {
+        const long long k = QUEUE ? (long long)queue[i] : i;
+        uint32_t parity = 0;
+        uf_wide::ph_reset(g, l, s, lane, nl);
+        __syncthreads();
+        if (lane < WARP) parity ^= uf_wide::ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, WARP);
+        __syncthreads();
+        uf_wide::ph_load(g, s, lane, nl);
+        __syncthreads();
+        uf_wide::uf_validate_t<-1>(g, s, flags, lane, nl);
+        parity ^= uf_wide::uf_peel_parity(g, s, lane, nl);
+        const unsigned int bit = (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
+        fails += bit;
+        if (logical && threadIdx.x == 0) logical[k] = (uint8_t)bit;
+    }
+    if (threadIdx.x == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
+    if (!QUEUE && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+}
+
+// Staged K1 on the wide tables: a warp per shot flips the bits of the shot's rows in HBM directly (a row of a
+// large graph is tens of KB; its few hundred faults are scattered atomics either way).
+template <bool WEIGHT>
+__global__ void k_sample_wide(uf_wide::GraphView g, SampleParams sp, uint32_t weight, unsigned long long shot0, long long nshots,
+                              uint32_t* __restrict__ err, uint32_t* __restrict__ syn)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        uf_wide::Shot s;
+        s.err = err + k * g.WE; s.defect = syn + k * g.WD;
+        for (int w = lane; w < g.WE; w += WARP) s.err[w] = 0;
+        for (int w = lane; w < g.WD; w += WARP) s.defect[w] = 0;
+        __syncwarp();
+        if (WEIGHT) uf_wide::ph_force(g, s, sp, weight, shot0 + (unsigned long long)k, lane);
+        else uf_wide::ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, WARP);
+        __syncwarp();
+    }
+}
+
+// k_count_strings on the wide tables: the partner map (one int32 per node) of a warp lives in global memory.
+static const int WSTR_NONE = INT32_MIN;
+__device__ __forceinline__ int wstr_key(const uf_wide::GraphView& g, uint32_t v)
+{
+    return v >= (uint32_t)g.B ? (int)v : (__ldg(&g.node_long[v]) == -1 ? STR_WEST : STR_EAST);
+}
+__device__ __forceinline__ void wstr_add(int32_t* partner, int a, int b, int& count)
+{
+    if (a >= 0) partner[a] = b;
+    if (b >= 0) partner[b] = a;
+    if ((a == STR_WEST && b == STR_EAST) || (a == STR_EAST && b == STR_WEST)) ++count;
+}
+__device__ __forceinline__ int wstr_take(int32_t* partner, int u)
+{
+    const int w = partner[u];
+    partner[u] = WSTR_NONE;
+    if (w >= 0) partner[w] = WSTR_NONE;
+    return w;
+}
+
+__global__ void k_count_strings_wide(uf_wide::GraphView g, long long nshots, const uint32_t* __restrict__ err,
+                                     const uint32_t* __restrict__ corr, int32_t* __restrict__ per_shot,
+                                     unsigned long long* total, int32_t* maps)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    int32_t* partner = maps + ((size_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * (size_t)g.N;
+    for (int v = lane; v < g.N; v += 32) partner[v] = WSTR_NONE;
+    __syncwarp();
+    unsigned long long sum = 0;
+    const long long stride = (long long)gridDim.x * wpb;
+    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
+        int count = 0;
+        for (int base = 0; base < g.WE; base += 32) {
+            const int w = base + lane;
+            const uint32_t x = w < g.WE ? (__ldg(&err[k * g.WE + w]) ^ __ldg(&corr[k * g.WE + w])) : 0u;
+            uint32_t lanes = __ballot_sync(0xffffffffu, x != 0u);
+            while (lanes) {                                   // ascending words, ascending bits: ascending edge id
+                const int src = __ffs((int)lanes) - 1; lanes &= lanes - 1;
+                uint32_t bits = __shfl_sync(0xffffffffu, x, src);
+                if (lane == 0) {
+                    while (bits) {
+                        const int b = __ffs((int)bits) - 1; bits &= bits - 1;
+                        uint32_t eu, ev;
+                        uf_wide::edge_ends(g, (uint32_t)(32 * (base + src) + b), eu, ev);
+                        const int u = wstr_key(g, eu), v = wstr_key(g, ev);
+                        if (u >= 0 && partner[u] != WSTR_NONE) {       // Pairs.load, _pairs.py:49-66
+                            const int p = wstr_take(partner, u);
+                            if (v >= 0 && partner[v] != WSTR_NONE) wstr_add(partner, p, wstr_take(partner, v), count);
+                            else if (v != p || v < 0) wstr_add(partner, v, p, count);
+                        } else if (v >= 0 && partner[v] != WSTR_NONE)
+                            wstr_add(partner, u, wstr_take(partner, v), count);
+                        else
+                            wstr_add(partner, u, v, count);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        for (int base = 0; base < g.WE; base += 32) {        // put the map back
+            const int w = base + lane;
+            uint32_t bits = w < g.WE ? (__ldg(&err[k * g.WE + w]) ^ __ldg(&corr[k * g.WE + w])) : 0u;
+            while (bits) {
+                const int b = __ffs((int)bits) - 1; bits &= bits - 1;
+                uint32_t eu, ev;
+                uf_wide::edge_ends(g, (uint32_t)(32 * w + b), eu, ev);
+                if (eu >= (uint32_t)g.B) partner[eu] = WSTR_NONE;
+                if (ev >= (uint32_t)g.B) partner[ev] = WSTR_NONE;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { if (per_shot) per_shot[k] = count; sum += (unsigned long long)count; }
+    }
+    if (lane == 0 && sum) atomicAdd(total, sum);
+}
+
 // ------------------------------------------------------------------- graph
 struct luf_graph {
     int device = 0, sm_count = 0, max_smem = 0;
@@ -776,6 +937,12 @@ struct luf_graph {
     PackedFast fast_host;
     fast::FView fview{};
     std::map<void*, uint32_t*> queues;       // per stream: uint32[FAST_CHUNK] shot indices + the fill counter behind them
+    // wide instance (luf_uf_wide.cuh): what runs when the graph is beyond the 16-bit layout (or LUF_FORCE_WIDE=1)
+    bool wide = false;
+    PackedWide wide_host;
+    uf_wide::GraphView wview{};
+    uf_wide::Layout wlay_fused{}, wlay_decode{};
+    std::map<std::pair<void*, int>, std::pair<void*, size_t>> slabs;    // per (stream, use): the state slabs of a persistent grid
 };
 
 static const long long FAST_CHUNK = 1ll << 22;       // shots per fast launch (the queue of HARD shots holds as many)
@@ -1094,6 +1261,68 @@ static int fast_launch(luf_graph* g, const fast::FView& fv, const FastPlan& plan
         default: return fail(LUF_ERR_INVALID, "fast path: tile width must be 16, 32, 64, 128 or 256");
     }
 #undef LUF_FAST_TW
+}
+
+// ------------------------------------------------------- wide instance: launch plan
+struct WidePlan { int grid, threads; size_t smem; unsigned char* slab; };
+
+// Grow-only device scratch per (stream, use).  cudaFree waits for the device, so a slab still read by an earlier
+// launch on the stream is never pulled away.
+static int wide_slab(luf_graph* g, void* stream, int use, size_t bytes, void** out)
+{
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    auto& e = g->slabs[std::make_pair(stream, use)];
+    if (bytes > e.second) {
+        if (e.first) CUDA_TRY(cudaFree(e.first));
+        e.first = nullptr; e.second = 0;
+        CUDA_TRY(cudaMalloc(&e.first, bytes));
+        e.second = bytes;
+    }
+    *out = e.first;
+    return 0;
+}
+
+// One block per shot.  The state slab goes to shared memory when two blocks' slabs fit on an SM, else to global
+// memory with as many resident blocks as keep all slabs of the grid inside L2 (LUF_WIDE_L2_MB, default 96 of
+// the B200's 126 MB).  LUF_WIDE_STATE=smem|global, LUF_WIDE_THREADS override (measurements).
+template <class K>
+static int wide_plan(luf_graph* g, K kernel, const uf_wide::Layout& l, long long nshots, void* stream, WidePlan* out)
+{
+    const char* env_state = getenv("LUF_WIDE_STATE");
+    const int env_threads = getenv("LUF_WIDE_THREADS") ? atoi(getenv("LUF_WIDE_THREADS")) : 0;
+    const int env_l2 = getenv("LUF_WIDE_L2_MB") ? atoi(getenv("LUF_WIDE_L2_MB")) : 96;
+    bool in_smem = (size_t)2 * l.bytes + 2048 <= (size_t)g->max_smem;
+    if (env_state && !strcmp(env_state, "global")) in_smem = false;
+    if (env_state && !strcmp(env_state, "smem")) in_smem = l.bytes <= (uint32_t)g->max_smem;
+    if (int rc = raise_smem_limit(g->device, g->max_smem, kernel)) return rc;
+    int threads = env_threads >= 32 && env_threads <= 512 ? env_threads & ~31 : 256;
+    const size_t smem = in_smem ? l.bytes : 0;
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) return fail(LUF_ERR_UNSUPPORTED, "wide kernel does not fit on an SM");
+    if (!in_smem) {
+        const long long by_l2 = std::max<long long>(1, (long long)env_l2 * 1024 * 1024 / ((long long)g->sm_count * l.bytes));
+        if (per_sm > by_l2) per_sm = (int)by_l2;
+        if (!env_threads && per_sm <= 3) {          // few resident blocks: wider ones
+            threads = 512;
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+            if (occ < 1) threads = 256; else if (per_sm > occ) per_sm = occ;
+        }
+    }
+    long long blocks = (long long)g->sm_count * per_sm;
+    if (blocks > nshots) blocks = nshots;
+    if (blocks < 1) blocks = 1;
+    out->grid = (int)blocks; out->threads = threads; out->smem = smem; out->slab = nullptr;
+    if (!in_smem) {
+        void* p = nullptr;
+        if (int rc = wide_slab(g, stream, 0, (size_t)g->sm_count * per_sm * l.bytes, &p)) return rc;
+        out->slab = (unsigned char*)p;
+    }
+    if (getenv("LUF_DEBUG_PLAN"))
+        fprintf(stderr, "[luf] wide plan: %u B per shot in %s memory, %d threads per block, %d blocks per SM\n", l.bytes,
+                in_smem ? "shared" : "global", threads, per_sm);
+    return 0;
 }
 
 // *_host entry points on stream 0: no asynchronous copy into a caller's buffer outlives the call, error or not
@@ -1473,9 +1702,12 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     const std::string why = pack_graph(*desc, g->host);
     pack_fast(*desc, g->fast_host);
     g->canonical_ok = why.empty();
-    if (!why.empty() && !(why.find("too large") != std::string::npos && g->fast_host.ok)) {
-        delete g;
-        return fail(why.find("too large") != std::string::npos ? LUF_ERR_UNSUPPORTED : LUF_ERR_INVALID, why);
+    // beyond the 16-bit layout -- or LUF_FORCE_WIDE=1 (tests: any graph through the wide kernels)
+    g->wide = (!why.empty() && why.find("too large") != std::string::npos) || (getenv("LUF_FORCE_WIDE") && atoi(getenv("LUF_FORCE_WIDE")) != 0);
+    if (!why.empty() && !g->wide) { delete g; return fail(LUF_ERR_INVALID, why); }
+    if (g->wide) {
+        const std::string wwhy = pack_wide(*desc, g->wide_host);
+        if (!wwhy.empty()) { delete g; return fail(LUF_ERR_INVALID, wwhy); }
     }
     g->device = device;
     cudaError_t e = cudaSetDevice(device);
@@ -1496,13 +1728,28 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
             return rc;
         }
     }
+    if (g->wide) {
+        const PackedWide& q = g->wide_host;
+        uf_wide::GraphView& w = g->wview;
+        w.N = q.N; w.B = q.B; w.E = q.E; w.F = q.F; w.n_classes = q.n_classes; w.DEG = q.DEG;
+        w.WE = words32(q.E); w.WD = words32(q.N - q.B); w.WN = words32(q.N);
+        w.parity_ok = q.parity_ok ? 1 : 0; w.leaf_bnd = g->fast_host.ok ? 1 : 0; w.fresh_perm32 = nullptr;
+        if ((rc = upload(g, q.adj, &w.adj)) || (rc = upload(g, q.edge_uv, &w.edge_uv)) || (rc = upload(g, q.west_mask, &w.west_mask)) ||
+            (rc = upload(g, q.node_long, &w.node_long)) || (rc = upload(g, q.class_end, &w.class_end)) ||
+            (!q.perm_identity && (rc = upload(g, q.fresh_perm32, &w.fresh_perm32)))) {
+            luf_graph_destroy(g);
+            return rc;
+        }
+        g->wlay_fused = make_wide_layout(q.N, q.B, q.E, false, false);
+        g->wlay_decode = make_wide_layout(q.N, q.B, q.E, false, true);
+    }
     if (!g->canonical_ok) {
-        // beyond the 16-bit layout of the canonical kernels: the compact path alone (luf_sample, luf_check,
-        // luf_mc_run[_logical] with UF under the west inclination); everything else answers LUF_ERR_UNSUPPORTED
+        // beyond the 16-bit layout: UF runs through the wide instance (luf_uf_wide.cuh) and, for the fused
+        // Monte-Carlo entry points, the compact fast path; Macar / Actis answer LUF_ERR_UNSUPPORTED
         memset(&v, 0, sizeof(v));
         v.N = desc->n_nodes; v.B = desc->n_boundary; v.E = desc->n_edges; v.F = g->fast_host.F; v.n_classes = desc->n_classes;
         v.WE = words32(v.E); v.WD = words32(v.N - v.B); v.WN = words32(v.N);
-        if ((rc = upload(g, g->fast_host.west_mask, &v.west_mask))) { luf_graph_destroy(g); return rc; }
+        v.west_mask = g->wview.west_mask;
         g->ca_why = "graph too large for the 16-bit cellular-automaton layout";
         *out = g;
         return 0;
@@ -1563,6 +1810,7 @@ int luf_graph_destroy(luf_graph* g)
     for (void* p : g->allocs) cudaFree(p);
     for (void* p : g->scratch) if (p) cudaFree(p);
     for (auto& q : g->queues) cudaFree(q.second);
+    for (auto& q : g->slabs) if (q.second.first) cudaFree(q.second.first);
     for (cudaStream_t st : g->pipe) if (st) cudaStreamDestroy(st);
     delete g;
     return 0;
@@ -1583,7 +1831,7 @@ static int check_decoder(const luf_graph* g, int decoder, int flags)
 {
     if (decoder == LUF_DEC_UF) {
         if (flags & ~(LUF_UF_DYNAMIC | LUF_UF_WEST | LUF_UF_NODE | LUF_UF_BUCKET)) return fail(LUF_ERR_INVALID, "unknown UF flag");
-        if ((flags & LUF_UF_BUCKET) && !(flags & LUF_UF_NODE) && g->view.E > 32767)
+        if ((flags & LUF_UF_BUCKET) && !(flags & LUF_UF_NODE) && g->view.E > 32767 && !g->wide)
             return fail(LUF_ERR_UNSUPPORTED, "BUF keeps vision lengths in 15 bits: graphs of up to 32767 edges");
         return 0;
     }
@@ -1610,6 +1858,14 @@ int luf_sample(luf_graph* g, const double* class_p_host, uint64_t seed, uint64_t
     CUDA_TRY(cudaSetDevice(g->device));
     const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
     LaunchCfg c;
+    if (g->wide && (g->canonical_ok || !g->fast_host.ok)) {       // the sampler of the wide tables (same random stream)
+        const int wpb = 8;
+        long long blocks = std::min<long long>((long long)g->sm_count * 8, (nshots + wpb - 1) / wpb);
+        k_sample_wide<false><<<(int)blocks, wpb * WARP, 0, (cudaStream_t)stream>>>(g->wview, sp, 0u, shot0, nshots, err_bits_dev, syn_bits_dev);
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+        return 0;
+    }
     if (!g->canonical_ok) {               // the sampler of the compact tables (same random stream)
         const uint32_t slice = align16(4u * (uint32_t)(g->view.WE + g->view.WD));
         if (int rc = raise_smem_limit(g->device, g->max_smem, k_sample_fast)) return rc;
@@ -1634,7 +1890,6 @@ int luf_sample_weight(luf_graph* g, int32_t weight, uint64_t seed, uint64_t shot
 {
     if (!g || !err_bits_dev || !syn_bits_dev || nshots < 0)
         return fail(LUF_ERR_INVALID, "luf_sample_weight: bad argument");
-    if (!g->canonical_ok) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     if (weight < 0 || weight > g->view.F)
         return fail(LUF_ERR_INVALID, "Sample larger than population or is negative");       // random.sample's message
     if (nshots == 0) return 0;
@@ -1642,6 +1897,14 @@ int luf_sample_weight(luf_graph* g, int32_t weight, uint64_t seed, uint64_t shot
     const double zero[MAX_CLASSES] = {0};
     const SampleParams sp = make_sample_params(zero, g->view.n_classes, seed);
     LaunchCfg c;
+    if (g->wide) {
+        const int wpb = 8;
+        long long blocks = std::min<long long>((long long)g->sm_count * 8, (nshots + wpb - 1) / wpb);
+        k_sample_wide<true><<<(int)blocks, wpb * WARP, 0, (cudaStream_t)stream>>>(g->wview, sp, (uint32_t)weight, shot0, nshots, err_bits_dev, syn_bits_dev);
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+        return 0;
+    }
     if (int rc = plan_launch(g, k_sample_weight, g->lay_sample.bytes, nshots, &c)) return rc;
     k_sample_weight<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_sample, sp, (uint32_t)weight, shot0,
                                                                         nshots, err_bits_dev, syn_bits_dev);
@@ -1655,11 +1918,19 @@ int luf_decode_batch(luf_graph* g, int decoder, int flags, int64_t nshots, const
 {
     if (!g || !syn_bits_dev || !corr_bits_dev || nshots < 0)
         return fail(LUF_ERR_INVALID, "luf_decode_batch: bad argument");
-    if (!g->canonical_ok) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     if (int rc = check_decoder(g, decoder, flags)) return rc;
     if (nshots == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
     LaunchCfg c;
+    if (decoder == LUF_DEC_UF && g->wide) {
+        WidePlan w;
+        if (int rc = wide_plan(g, k_decode_uf_wide, g->wlay_decode, nshots, stream, &w)) return rc;
+        k_decode_uf_wide<<<w.grid, w.threads, w.smem, (cudaStream_t)stream>>>(g->wview, g->wlay_decode, flags, nshots, syn_bits_dev,
+                                                                           corr_bits_dev, growth2b_dev, steps_dev, w.slab);
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+        return 0;
+    }
     if (decoder == LUF_DEC_MACAR) {
         if (use_ca_cta(g, false)) {
             if (int rc = plan_ca_cta_launch(g, k_decode_ca_cta<false>, g->lay_macar_cta.bytes, nshots, &c, g->ca_view.N / 16)) return rc;
@@ -1748,9 +2019,19 @@ int luf_count_strings(luf_graph* g, int64_t nshots, const uint32_t* err_bits_dev
 {
     if (!g || !err_bits_dev || !corr_bits_dev || !total_dev || nshots < 0)
         return fail(LUF_ERR_INVALID, "luf_count_strings: bad argument");
-    if (!g->canonical_ok) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     if (nshots == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
+    if (g->wide) {
+        const int wpb = 4;
+        long long blocks = std::min<long long>((long long)g->sm_count * 4, (nshots + wpb - 1) / wpb);
+        void* maps = nullptr;
+        if (int rc = wide_slab(g, stream, 1, (size_t)blocks * wpb * (size_t)g->wview.N * 4, &maps)) return rc;
+        k_count_strings_wide<<<(int)blocks, wpb * WARP, 0, (cudaStream_t)stream>>>(g->wview, nshots, err_bits_dev, corr_bits_dev,
+                                                                              count_dev, total_dev, (int32_t*)maps);
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+        return 0;
+    }
     const uint32_t slice = align16(2u * (uint32_t)g->view.N);
     int wpb = g->max_smem / (int)slice;
     if (wpb < 1) return fail(LUF_ERR_UNSUPPORTED, "luf_count_strings: the partner map of one shot exceeds the shared memory of an SM");
@@ -1779,7 +2060,6 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                        uint64_t shot0, int64_t nshots, unsigned long long* counts_dev, uint8_t* logical_dev, void* stream)
 {
     if (!g || !class_p_host || !counts_dev || nshots < 0) return fail(LUF_ERR_INVALID, "luf_mc_run: bad argument");
-    if (!g->canonical_ok && !(decoder == LUF_DEC_UF && flags == LUF_UF_WEST)) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     if (int rc = check_decoder(g, decoder, flags)) return rc;
     if (nshots == 0) return 0;
     CUDA_TRY(cudaSetDevice(g->device));
@@ -1841,7 +2121,14 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                     if (!fv.west) CUDA_TRY(cudaMemsetAsync(qcount, 0, 4, (cudaStream_t)stream));
                     if (int rc = fast_launch(g, fv, plan, fl, sp, first, m, counts_dev, lg, queue, qcount, (cudaStream_t)stream)) return rc;
                     ++g->launches;
-                    if (!fv.west) {             // (the west inclination leaves no HARD shots: luf_uf_fast.cuh)
+                    if (!fv.west && g->wide) {  // the HARD shots of a graph beyond the 16-bit layout: the wide instance
+                        WidePlan w;
+                        if (int rc = wide_plan(g, k_mc_uf_wide<true>, g->wlay_fused, 4096, stream, &w)) return rc;
+                        k_mc_uf_wide<true><<<w.grid, w.threads, w.smem, (cudaStream_t)stream>>>(g->wview, g->wlay_fused, sp, flags, first, m,
+                                                                                             counts_dev, lg, queue, qcount, w.slab);
+                        CUDA_TRY(cudaGetLastError());
+                        ++g->launches;
+                    } else if (!fv.west) {      // (the west inclination leaves no HARD shots: luf_uf_fast.cuh)
                         LUF_MC_UF_ANY(0, true, first, m, lg, queue, qcount)
                         CUDA_TRY(cudaGetLastError());
                         ++g->launches;
@@ -1850,8 +2137,15 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                 return 0;
             }
         }
-        if (!g->canonical_ok)
-            return fail(LUF_ERR_UNSUPPORTED, "one shot's compact state exceeds the shared memory of an SM and the graph is beyond the canonical kernels");
+        if (g->wide) {
+            WidePlan w;
+            if (int rc = wide_plan(g, k_mc_uf_wide<false>, g->wlay_fused, nshots, stream, &w)) return rc;
+            k_mc_uf_wide<false><<<w.grid, w.threads, w.smem, (cudaStream_t)stream>>>(g->wview, g->wlay_fused, sp, flags, shot0, nshots,
+                                                                                  counts_dev, logical_dev, nullptr, nullptr, w.slab);
+            CUDA_TRY(cudaGetLastError());
+            ++g->launches;
+            return 0;
+        }
         // the common flag sets are compile-time constants of the fused kernel; the rest run the generic instance
         switch (flags <= 7 ? flags : -1) {
             case 0: LUF_MC_UF_ANY(0, false, shot0, nshots, logical_dev, nullptr, nullptr) break;

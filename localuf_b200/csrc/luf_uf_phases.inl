@@ -11,15 +11,36 @@
 // oracle/ref_canonical.py):
 //   K2a validate            uf.py:200-301  (grow a half-edge per round, merge in ascending edge id)
 //   K2b peel                uf.py:305-344  (LIFO spanning tree in ascending edge id, leaf-up peeling)
+//
+// Word width.  The two 16-bit instances pack a node word into 32 bits (indices below 2^15 / 2^16: luf_core.cuh);
+// the wide instance (luf_uf_wide.cuh, LUF_T_WIDE: graphs beyond that, state in global or shared memory) packs the
+// same fields into 64 bits.  word_t = a node word / list entry / reservation; HSH = where its upper half starts;
+// LO_MASK = its lower half; IDX_NONE / TREE_ROOT = the two reserved index values of the peel; ent_t = an
+// adjacency entry.  The wide instance defines them, and its own GraphView / Shot / Layout, before including this.
 namespace luf {
 namespace LUF_UF_NS {
 
-// find without writes: safe while other lanes read or extend the forest.  `wr` = the root's word.
-LUF_DEV uint32_t find_ro(const Shot& s, uint32_t v, uint32_t& wr)
+#if !defined(LUF_T_WIDE)
+typedef uint32_t word_t;
+typedef uint32_t ent_t;
+static const int HSH = 16;
+static const word_t LO_MASK = 0xFFFFu, IDX_NONE = NONE16, TREE_ROOT_W = TREE_ROOT;
+LUF_DEV uint32_t ent_edge(ent_t ent) { return ent & 0xFFFFu; }
+LUF_DEV void edge_ends(const GraphView& g, uint32_t e, uint32_t& u, uint32_t& v)
 {
-    uint32_t w;
+    const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
+    u = uv & 0xFFFFu; v = uv >> 16;
+}
+#endif
+static const word_t WORD_ONES = ~(word_t)0;
+LUF_DEV uint32_t* claim_bits(const Shot& s) { return (uint32_t*)s.claim; }      // the reservation table doubles as a node bitmap
+
+// find without writes: safe while other lanes read or extend the forest.  `wr` = the root's word.
+LUF_DEV uint32_t find_ro(const Shot& s, uint32_t v, word_t& wr)
+{
+    word_t w;
     LUF_NOUNROLL
-    while (!((w = s.S[v]) & ROOT_BIT)) v = w & SIZE_MASK;
+    while (!((w = s.S[v]) & ROOT_BIT)) v = (uint32_t)(w & SIZE_MASK);
     wr = w;
     return v;
 }
@@ -29,15 +50,16 @@ LUF_DEV uint32_t find_ro(const Shot& s, uint32_t v, uint32_t& wr)
 // root again and the value written is one of its ancestors (32-bit stores are
 // atomic; the union edge in the upper half is kept), so every interleaving
 // leaves a valid forest with the same roots.
-LUF_DEV uint32_t find_pc(const Shot& s, uint32_t v, uint32_t& wr)
+LUF_DEV uint32_t find_pc(const Shot& s, uint32_t v, word_t& wr)
 {
-    const uint32_t w = s.S[v];
+    const word_t w = s.S[v];
     if (w & ROOT_BIT) { wr = w; return v; }
-    uint32_t r = w & SIZE_MASK, q;
+    uint32_t r = (uint32_t)(w & SIZE_MASK);
+    word_t q;
     int hops = 0;
     LUF_NOUNROLL
-    while (!((q = s.S[r]) & ROOT_BIT)) { r = q & SIZE_MASK; ++hops; }
-    if (hops) s.S[v] = (w & 0xFFFF0000u) | r;
+    while (!((q = s.S[r]) & ROOT_BIT)) { r = (uint32_t)(q & SIZE_MASK); ++hops; }
+    if (hops) s.S[v] = (w & ~LO_MASK) | r;
     wr = q;
     return r;
 }
@@ -45,11 +67,12 @@ LUF_DEV uint32_t find_pc(const Shot& s, uint32_t v, uint32_t& wr)
 // uf.py:247-254 -- find with full path compression (single lane only)
 LUF_DEV uint32_t find_compress(const Shot& s, uint32_t v)
 {
-    uint32_t r = v, w;
+    uint32_t r = v;
+    word_t w;
     LUF_NOUNROLL
-    while (!((w = s.S[r]) & ROOT_BIT)) r = w & SIZE_MASK;
+    while (!((w = s.S[r]) & ROOT_BIT)) r = (uint32_t)(w & SIZE_MASK);
     LUF_NOUNROLL
-    while (v != r) { w = s.S[v]; s.S[v] = (w & 0xFFFF0000u) | r; v = w & SIZE_MASK; }
+    while (v != r) { w = s.S[v]; s.S[v] = (w & ~LO_MASK) | r; v = (uint32_t)(w & SIZE_MASK); }
     return r;
 }
 
@@ -59,7 +82,7 @@ LUF_DEV uint32_t find_compress(const Shot& s, uint32_t v)
 // consumers walk the bitmap itself (same per-item code, unbalanced lanes).
 // `word(w)` yields word w of the bitmap.
 template <class W>
-LUF_DEV void gather_bits(W word, int nwords, uint32_t id0, uint32_t* list, uint32_t* counter, int lane, int nl)
+LUF_DEV void gather_bits(W word, int nwords, uint32_t id0, word_t* list, uint32_t* counter, int lane, int nl)
 {
     const int wpl = (nwords + nl - 1) / nl;
     const int w0 = lane * wpl, w1 = w0 + wpl < nwords ? w0 + wpl : nwords;
@@ -97,17 +120,18 @@ LUF_DEV void for_bits(W word, int nwords, uint32_t id0, int lane, int nl, F f)
 
 // Run f(id) for every item: from the list if it held them all, else from the bitmap.
 template <class W, class F>
-LUF_DEV void for_items(W word, int nwords, uint32_t id0, const uint32_t* list, uint32_t total,
+LUF_DEV void for_items(W word, int nwords, uint32_t id0, const word_t* list, uint32_t total,
                        int lane, int nl, F f)
 {
     if (total <= LUF_T_LIST_CAP) {
         LUF_NOUNROLL
-        for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) f(list[i]);
+        for (uint32_t i = (uint32_t)lane; i < total; i += (uint32_t)nl) f((uint32_t)list[i]);
     } else for_bits(word, nwords, id0, lane, nl, f);
 }
 
 // Row v of the adjacency table, read as 64-bit pairs; f(entry) for every real entry
 // (entry = edge | other end << 16 | this is the edge's first endpoint << 31).
+#if !defined(LUF_T_WIDE)
 template <class F>
 LUF_DEV void for_row(const GraphView& g, uint32_t v, F f)
 {
@@ -126,15 +150,20 @@ LUF_DEV uint32_t other_end(uint32_t ent, bool& first)
     first = (ent >> 31) != 0;
     return (ent >> 16) & 0x7FFFu;
 }
+#endif
 
 // ------------------------------------------------------------ phase 0: reset
 // uf.py:79-96,496-519 -- every node a singleton cluster; a boundary node is its
 // own cluster boundary.  (The reference re-allocates N Python objects here,
 // 40-58 % of its time; this is N*4 + ~3 KB of 16-byte shared-memory stores.)
-LUF_DEV uint32_t fresh_word(const GraphView& g, int v) { return ROOT_BIT | 1u | (v < g.B ? ((uint32_t)v + 1u) << 16 : 0u); }
+LUF_DEV word_t fresh_word(const GraphView& g, int v) { return ROOT_BIT | 1u | (v < g.B ? ((word_t)v + 1u) << HSH : (word_t)0); }
 
 LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int lane, int nl)
 {
+#if defined(LUF_T_WIDE)
+    LUF_NOUNROLL
+    for (int v = lane; v < g.N; v += nl) s.S[v] = fresh_word(g, v);
+#else
     luf_u32x4* S4 = (luf_u32x4*)s.S;
     LUF_NOUNROLL
     for (int v = 4 * lane; v < g.N; v += 4 * nl) {
@@ -142,12 +171,13 @@ LUF_DEV void ph_reset(const GraphView& g, const Layout& l, const Shot& s, int la
         w.x = fresh_word(g, v); w.y = fresh_word(g, v + 1); w.z = fresh_word(g, v + 2); w.w = fresh_word(g, v + 3);
         S4[v >> 2] = w;
     }
+#endif
     luf_u32x4* Z4 = (luf_u32x4*)((unsigned char*)s.S + (l.zero_off - l.S));
     luf_u32x4 z; z.x = z.y = z.z = z.w = 0u;
     LUF_NOUNROLL
     for (int i = lane; i < (int)(l.zero_bytes >> 4); i += nl) Z4[i] = z;
     LUF_NOUNROLL
-    for (int w = lane; w < LUF_T_CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu;
+    for (int w = lane; w < LUF_T_CLAIM_SLOTS; w += nl) s.claim[w] = WORD_ONES;
     if (lane < 8) s.cnt[lane] = 0;
 }
 
@@ -210,8 +240,8 @@ LUF_DEV void became_full(const Shot& s, uint32_t e, uint32_t u, uint32_t o)
 // the other end got there first.
 LUF_DEV void grow_first(const GraphView& g, const Shot& s, uint32_t v)
 {
-    for_row(g, v, [&](uint32_t ent) {
-        const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+    for_row(g, v, [&](ent_t ent) {
+        const uint32_t e = ent_edge(ent), sh = (e & 15u) * 2u;
         const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
         if (old == G_HALF) { bool first; became_full(s, e, v, other_end(ent, first)); }
     });
@@ -230,13 +260,13 @@ LUF_DEV uint32_t ph_grow_first(const GraphView& g, const Shot& s, int lane, int 
 // inside its own cluster.
 LUF_DEV void grow_node(const GraphView& g, const Shot& s, uint32_t u, uint32_t r, bool node)
 {
-    for_row(g, u, [&](uint32_t ent) {
-        const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
+    for_row(g, u, [&](ent_t ent) {
+        const uint32_t e = ent_edge(ent), sh = (e & 15u) * 2u;
         if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
         bool first;
         const uint32_t o = other_end(ent, first);
         if (!node && !first) {                        // second endpoint: skip if same cluster
-            uint32_t wr;
+            word_t wr;
             if (o == r || find_ro(s, o, wr) == r) return;
         }
         const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
@@ -261,12 +291,12 @@ LUF_DEV void ph_grow_filter(const GraphView& g, const Shot& s, int flags, int la
     const int f = TF >= 0 ? TF : flags;
     const bool node = (f & FLAG_NODE) != 0, bucket = (f & FLAG_BUCKET) != 0;
     for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
-        uint32_t wr;
+        word_t wr;
         const uint32_t r = find_pc(s, u, wr);
-        if ((wr >> 16) != (ODD_BIT >> 16)) return;
+        if ((wr >> HSH) != (ODD_BIT >> HSH)) return;
         const uint32_t idx = luf_atomic_add(&s.cnt[1], 1u);
-        if (bucket) luf_atomic_min(&s.cnt[3], wr & SIZE_MASK);
-        if (idx < LUF_T_LIST2_CAP) s.list2[idx] = u | (r << 16);
+        if (bucket) luf_atomic_min(&s.cnt[3], (uint32_t)(wr & SIZE_MASK));
+        if (idx < LUF_T_LIST2_CAP) s.list2[idx] = (word_t)u | ((word_t)r << HSH);
         else if (!bucket) grow_node(g, s, u, r, node);
     });
 }
@@ -282,18 +312,18 @@ LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int flags, int 
     const uint32_t smallest = s.cnt[3];
     if (bucket && total > LUF_T_LIST2_CAP) {          // the list could not hold them: look the active nodes up again
         for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
-            uint32_t wr;
+            word_t wr;
             const uint32_t r = find_ro(s, u, wr);
-            if ((wr >> 16) == (ODD_BIT >> 16) && (wr & SIZE_MASK) == smallest) grow_node(g, s, u, r, node);
+            if ((wr >> HSH) == (ODD_BIT >> HSH) && (uint32_t)(wr & SIZE_MASK) == smallest) grow_node(g, s, u, r, node);
         });
         return total;
     }
     const uint32_t n = total < LUF_T_LIST2_CAP ? total : LUF_T_LIST2_CAP;
     LUF_NOUNROLL
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t it = s.list2[i];
-        if (bucket && (s.S[it >> 16] & SIZE_MASK) != smallest) continue;
-        grow_node(g, s, it & 0xFFFFu, it >> 16, node);
+        const word_t it = s.list2[i];
+        if (bucket && (uint32_t)(s.S[it >> HSH] & SIZE_MASK) != smallest) continue;
+        grow_node(g, s, (uint32_t)(it & LO_MASK), (uint32_t)(it >> HSH), node);
     }
     return total;
 }
@@ -307,11 +337,11 @@ LUF_DEV uint32_t ph_grow_exec(const GraphView& g, const Shot& s, int flags, int 
 LUF_DEV uint32_t vision_edges(const GraphView& g, const Shot& s, uint32_t u, uint32_t r)
 {
     uint32_t c = 0;
-    for_row(g, u, [&](uint32_t ent) {
-        if (growth_of(s, ent & 0xFFFFu) >= G_FULL) return;
+    for_row(g, u, [&](ent_t ent) {
+        if (growth_of(s, ent_edge(ent)) >= G_FULL) return;
         bool first;
         const uint32_t o = other_end(ent, first);
-        uint32_t wr;
+        word_t wr;
         if (!first && (o == r || find_ro(s, o, wr) == r)) return;
         ++c;
     });
@@ -321,9 +351,9 @@ LUF_DEV uint32_t vision_edges(const GraphView& g, const Shot& s, uint32_t u, uin
 template <class F>
 LUF_DEV void for_active(const GraphView& g, const Shot& s, int lane, int nl, F f)
 {
-    const uint32_t* act = s.claim;
+    const uint32_t* act = claim_bits(s);
     for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
-        uint32_t wr;
+        word_t wr;
         const uint32_t r = find_ro(s, u, wr);
         if (bit_of(act, r)) f(u, r, wr);
     });
@@ -331,11 +361,11 @@ LUF_DEV void for_active(const GraphView& g, const Shot& s, int lane, int nl, F f
 
 LUF_DEV void ph_buf_mark(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    uint32_t* act = s.claim;
+    uint32_t* act = claim_bits(s);
     for_items([&](int w) { return s.full1[w]; }, g.WN, 0u, s.list, s.cnt[0], lane, nl, [&](uint32_t u) {
-        uint32_t wr;
+        word_t wr;
         const uint32_t r = find_pc(s, u, wr);
-        if ((wr >> 16) != (ODD_BIT >> 16)) return;
+        if ((wr >> HSH) != (ODD_BIT >> HSH)) return;
         luf_atomic_or(&act[r >> 5], 1u << (r & 31u));
         luf_atomic_add(&s.cnt[1], 1u);
     });
@@ -343,30 +373,30 @@ LUF_DEV void ph_buf_mark(const GraphView& g, const Shot& s, int lane, int nl)
 
 LUF_DEV void ph_buf_count(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    for_active(g, s, lane, nl, [&](uint32_t u, uint32_t r, uint32_t) {
+    for_active(g, s, lane, nl, [&](uint32_t u, uint32_t r, word_t) {
         const uint32_t c = vision_edges(g, s, u, r);
-        if (c) luf_atomic_add(&s.S[r], c << 16);
+        if (c) luf_atomic_add(&s.S[r], (word_t)c << HSH);
     });
 }
 
 LUF_DEV void ph_buf_min(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    for_active(g, s, lane, nl, [&](uint32_t, uint32_t, uint32_t wr) { luf_atomic_min(&s.cnt[3], (wr >> 16) & 0x7FFFu); });
+    for_active(g, s, lane, nl, [&](uint32_t, uint32_t, word_t wr) { luf_atomic_min(&s.cnt[3], (uint32_t)((wr & BND_MASK) >> HSH)); });
 }
 
 // Returns the number of active nodes of the round.
 LUF_DEV uint32_t ph_buf_exec(const GraphView& g, const Shot& s, int lane, int nl)
 {
     const uint32_t shortest = s.cnt[3];
-    for_active(g, s, lane, nl, [&](uint32_t u, uint32_t r, uint32_t wr) {
-        if (((wr >> 16) & 0x7FFFu) == shortest) grow_node(g, s, u, r, false);
+    for_active(g, s, lane, nl, [&](uint32_t u, uint32_t r, word_t wr) {
+        if ((uint32_t)((wr & BND_MASK) >> HSH) == shortest) grow_node(g, s, u, r, false);
     });
     return s.cnt[1];
 }
 
 LUF_DEV void ph_buf_restore(const GraphView& g, const Shot& s, int lane, int nl)
 {
-    for_active(g, s, lane, nl, [&](uint32_t, uint32_t r, uint32_t wr) { s.S[r] = (wr & 0xFFFFu) | ODD_BIT; });
+    for_active(g, s, lane, nl, [&](uint32_t, uint32_t r, word_t wr) { s.S[r] = (wr & LO_MASK) | ODD_BIT; });
 }
 
 // ------------------------------------------------------------ phase 2b: merge
@@ -375,33 +405,33 @@ LUF_DEV void ph_buf_restore(const GraphView& g, const Shot& s, int lane, int nl)
 // edge's first endpoint; parity XOR; boundary by inclination.  TF >= 0 fixes
 // the decoder flags at compile time (the fused kernel), TF < 0 reads `flags`.
 // a cluster is active iff it is odd and has no boundary (uf.py:296-301)
-LUF_DEV uint32_t is_active(uint32_t root_word) { return (root_word >> 16) == (ODD_BIT >> 16) ? 1u : 0u; }
+LUF_DEV uint32_t is_active(word_t root_word) { return (root_word >> HSH) == (ODD_BIT >> HSH) ? 1u : 0u; }
 
 template <int TF>
 LUF_DEV void union_roots(const GraphView& g, const Shot& s, int flags, uint32_t e, uint32_t cu, uint32_t cv)
 {
     const int f = TF >= 0 ? TF : flags;
-    const uint32_t wu = s.S[cu], wv = s.S[cv];
+    const word_t wu = s.S[cu], wv = s.S[cv];
     if (f & FLAG_DYNAMIC) {                                       // uf.py:261-266
         if (cu == cv || ((wu & BND_MASK) && (wv & BND_MASK))) {
             luf_atomic_or(&s.growth[e >> 4], 3u << ((e & 15u) * 2u));     // FULL(2) -> BURNT(3)
             return;
         }
     } else if (cu == cv) return;                                  // uf.py:256-259
-    const uint32_t su = wu & SIZE_MASK, sv = wv & SIZE_MASK;
+    const uint32_t su = (uint32_t)(wu & SIZE_MASK), sv = (uint32_t)(wv & SIZE_MASK);
     const bool ul = su >= sv;                                     // uf.py:270-273
     const uint32_t L = ul ? cu : cv, Sm = ul ? cv : cu;
-    const uint32_t wl = ul ? wu : wv, ws = ul ? wv : wu;
-    uint32_t bl = wl & BND_MASK;
-    const uint32_t bs = ws & BND_MASK;
+    const word_t wl = ul ? wu : wv, ws = ul ? wv : wu;
+    word_t bl = wl & BND_MASK;
+    const word_t bs = ws & BND_MASK;
     // both clusters reach a boundary: remember if the two boundary nodes lie on different sides (uf_peel_parity)
-    if (bl && bs && LUF_LDG(&g.node_long[(bs >> 16) - 1]) != LUF_LDG(&g.node_long[(bl >> 16) - 1])) s.cnt[4] = 1u;
+    if (bl && bs && LUF_LDG(&g.node_long[(uint32_t)(bs >> HSH) - 1]) != LUF_LDG(&g.node_long[(uint32_t)(bl >> HSH) - 1])) s.cnt[4] = 1u;
     if (f & FLAG_WEST) {                                          // uf.py:544-549
-        if (bs && (!bl || LUF_LDG(&g.node_long[(bs >> 16) - 1]) < LUF_LDG(&g.node_long[(bl >> 16) - 1]))) bl = bs;
+        if (bs && (!bl || LUF_LDG(&g.node_long[(uint32_t)(bs >> HSH) - 1]) < LUF_LDG(&g.node_long[(uint32_t)(bl >> HSH) - 1]))) bl = bs;
     } else if (!bl) bl = bs;                                      // uf.py:536-538
-    const uint32_t neww = ((wl ^ ws) & ODD_BIT) | bl | ROOT_BIT | (su + sv);
+    const word_t neww = ((wl ^ ws) & ODD_BIT) | bl | ROOT_BIT | (word_t)(su + sv);
     s.S[L] = neww;
-    s.S[Sm] = L | (e << 16);
+    s.S[Sm] = (word_t)L | ((word_t)e << HSH);
     const int delta = (int)is_active(neww) - (int)is_active(wl) - (int)is_active(ws);      // cnt[5]: active clusters
     if (delta) luf_atomic_add(&s.cnt[5], (uint32_t)delta);
 }
@@ -456,47 +486,49 @@ LUF_DEV void ph_merge_gather(const GraphView& g, const Shot& s, int lane, int nl
 
 // Returns how many edges this lane placed (edges inside one cluster).
 template <int TF>
-LUF_DEV uint32_t ph_merge_claim(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, bool first, int lane, int nl)
+LUF_DEV uint32_t ph_merge_claim(const GraphView& g, const Shot& s, int flags, uint32_t n, word_t tag, bool first, int lane, int nl)
 {
     uint32_t placed = 0;
     LUF_NOUNROLL
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t it = s.list[i];
-        if (it == LIST_DONE) continue;
-        const uint32_t e = it & 0xFFFFu;
-        uint32_t wu, wv;
-        const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-        const uint32_t u = uv & 0xFFFFu, v = uv >> 16;
-        const uint32_t cu = find_pc(s, first ? u : (it >> 16), wu), cv = find_pc(s, v, wv);
+        const word_t it = s.list[i];
+        if (it == WORD_ONES) continue;
+        const uint32_t e = (uint32_t)(it & LO_MASK);
+        word_t wu, wv;
+        uint32_t u, v;
+        edge_ends(g, e, u, v);
+        const uint32_t cu = find_pc(s, first ? u : (uint32_t)(it >> HSH), wu), cv = find_pc(s, v, wv);
         if (cu == cv) {                               // inside one cluster whatever runs before it
             union_roots<TF>(g, s, flags, e, cu, cv);
-            s.list[i] = LIST_DONE;
+            s.list[i] = WORD_ONES;
             ++placed;
             continue;
         }
         luf_atomic_min(&s.claim[claim_slot(cu)], tag | e);
         luf_atomic_min(&s.claim[claim_slot(cv)], tag | e);
-        s.list[i] = e | (cu << 16);                   // the root of the first endpoint cannot change before this edge runs
+        s.list[i] = (word_t)e | ((word_t)cu << HSH);                   // the root of the first endpoint cannot change before this edge runs
     }
     return placed;
 }
 
 // Returns how many edges this lane placed.
 template <int TF>
-LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uint32_t n, uint32_t tag, int lane, int nl)
+LUF_DEV uint32_t ph_merge_exec(const GraphView& g, const Shot& s, int flags, uint32_t n, word_t tag, int lane, int nl)
 {
     uint32_t placed = 0;
     LUF_NOUNROLL
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t it = s.list[i];
-        if (it == LIST_DONE) continue;
-        const uint32_t e = it & 0xFFFFu, r0 = (it >> 16) & 0x7FFFu;
+        const word_t it = s.list[i];
+        if (it == WORD_ONES) continue;
+        const uint32_t e = (uint32_t)(it & LO_MASK), r0 = (uint32_t)((it >> HSH) & SIZE_MASK);
         if (s.claim[claim_slot(r0)] != (tag | e)) continue;
-        uint32_t wr;
-        const uint32_t cv = find_ro(s, LUF_LDG(&g.edge_uv[e]) >> 16, wr);
+        word_t wr;
+        uint32_t eu, ev;
+        edge_ends(g, e, eu, ev);
+        const uint32_t cv = find_ro(s, ev, wr);
         if (s.claim[claim_slot(cv)] != (tag | e)) continue;
         union_roots<TF>(g, s, flags, e, r0, cv);
-        s.list[i] = LIST_DONE;
+        s.list[i] = WORD_ONES;
         ++placed;
     }
     return placed;
@@ -535,20 +567,20 @@ LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int 
     uint32_t out = 0;
     uint32_t* troot = s.newfull;
     for_defects(g, s, lane, nl, [&](uint32_t dn) {
-        uint32_t rr;
+        word_t rr;
         const uint32_t r = find_ro(s, dn, rr);
         if ((rr & SIZE_MASK) == 2u) {
             uint32_t x = dn;                                  // the member whose word holds the union edge
             if (dn == r) {
                 if (!(rr & ODD_BIT)) return;                  // both are defects: the other member acts
-                x = ((rr & BND_MASK) >> 16) - 1u;             // single defect: its partner is the boundary node
+                x = (uint32_t)((rr & BND_MASK) >> HSH) - 1u;  // single defect: its partner is the boundary node
             }
-            const uint32_t e = s.S[x] >> 16;
+            const uint32_t e = (uint32_t)(s.S[x] >> HSH);
             if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
             out ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
             return;
         }
-        const uint32_t bn = (rr & BND_MASK) >> 16;
+        const uint32_t bn = (uint32_t)((rr & BND_MASK) >> HSH);
         const uint32_t t = bn ? bn - 1u : r;
         out |= 2u;
         const uint32_t bit = 1u << (t & 31u);
@@ -566,24 +598,24 @@ LUF_DEV uint32_t ph_tree_roots(const GraphView& g, const Shot& s, int lane, int 
 // discovered node) is kept.  `visited` marks discovered nodes.
 LUF_DEV void build_tree(const GraphView& g, const Shot& s, uint32_t root)
 {
-    uint32_t* visited = s.claim;
+    uint32_t* visited = claim_bits(s);
     luf_atomic_or(&visited[root >> 5], 1u << (root & 31u));
-    s.S[root] = TREE_ROOT | (NONE16 << 16);
+    s.S[root] = TREE_ROOT_W | (IDX_NONE << HSH);
     uint32_t top = root;
     LUF_NOUNROLL
-    while (top != NONE16) {
+    while (top != (uint32_t)IDX_NONE) {
         const uint32_t u = top;
-        top = s.S[u] >> 16;
-        for_row(g, u, [&](uint32_t ent) {
-            const uint32_t e = ent & 0xFFFFu;
+        top = (uint32_t)(s.S[u] >> HSH);
+        for_row(g, u, [&](ent_t ent) {
+            const uint32_t e = ent_edge(ent);
             if (growth_of(s, e) != G_FULL) return;
             bool first;
             const uint32_t o = other_end(ent, first);
             const uint32_t bit = 1u << (o & 31u);
             if (visited[o >> 5] & bit) return;
             luf_atomic_or(&visited[o >> 5], bit);
-            if (!(s.full2[o >> 5] & bit)) { s.S[o] = e | (NONE16 << 16); return; }     // a leaf: nothing to discover from it
-            s.S[o] = e | (top << 16); top = o;
+            if (!(s.full2[o >> 5] & bit)) { s.S[o] = (word_t)e | (IDX_NONE << HSH); return; }     // a leaf: nothing to discover from it
+            s.S[o] = (word_t)e | ((word_t)top << HSH); top = o;
         });
     }
 }
@@ -594,7 +626,7 @@ LUF_DEV void ph_peel_build(const GraphView& g, const Shot& s, int lane, int nl)
     const uint32_t total = s.cnt[1];
     const uint32_t n = total < LUF_T_LIST2_CAP ? total : LUF_T_LIST2_CAP;
     LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) build_tree(g, s, s.list2[i]);
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) build_tree(g, s, (uint32_t)s.list2[i]);
 }
 
 // overflow: roots that did not fit the list are still undiscovered; by bitmap word
@@ -603,7 +635,7 @@ LUF_DEV void ph_peel_build_rest(const GraphView& g, const Shot& s, int lane, int
     const uint32_t* troot = s.newfull;
     LUF_NOUNROLL
     for (int w = lane; w < g.WN; w += nl) {
-        uint32_t bits = troot[w] & ~s.claim[w];
+        uint32_t bits = troot[w] & ~claim_bits(s)[w];
         LUF_NOUNROLL
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
@@ -620,17 +652,18 @@ LUF_DEV void ph_peel_build_rest(const GraphView& g, const Shot& s, int lane, int
 LUF_DEV uint32_t ph_peel_paths(const GraphView& g, const Shot& s, int lane, int nl)
 {
     uint32_t parity = 0;
-    const uint32_t* visited = s.claim;
+    const uint32_t* visited = claim_bits(s);
     for_defects(g, s, lane, nl, [&](uint32_t v) {
         if (!bit_of(visited, v)) return;
-        uint32_t e = s.S[v] & 0xFFFFu;
+        uint32_t e = (uint32_t)(s.S[v] & LO_MASK);
         LUF_NOUNROLL
-        while (e != TREE_ROOT) {
+        while (e != (uint32_t)TREE_ROOT_W) {
             if (s.corr) luf_atomic_xor(&s.corr[e >> 5], 1u << (e & 31u));
             parity ^= (LUF_LDG(&g.west_mask[e >> 5]) >> (e & 31u)) & 1u;
-            const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-            v = (uv & 0xFFFFu) == v ? (uv >> 16) : (uv & 0xFFFFu);
-            e = s.S[v] & 0xFFFFu;
+            uint32_t eu, ev;
+            edge_ends(g, e, eu, ev);
+            v = eu == v ? ev : eu;
+            e = (uint32_t)(s.S[v] & LO_MASK);
         }
     });
     return parity;
@@ -653,13 +686,13 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
         uint32_t active = 0;
         if (vision_buckets) {
             if (rounds == 0) { LUF_T_PHASE(if (lane == 0) s.cnt[0] = 0); }      // ph_load's list of defects is not used
-            LUF_T_PHASE(ph_grow_gather(g, s, lane, nl); for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0);
+            LUF_T_PHASE(ph_grow_gather(g, s, lane, nl); for (int w = lane; w < g.WN; w += nl) claim_bits(s)[w] = 0);
             LUF_T_PHASE(ph_buf_mark(g, s, lane, nl));
             LUF_T_PHASE(ph_buf_count(g, s, lane, nl));
             LUF_T_PHASE(ph_buf_min(g, s, lane, nl));
             LUF_T_PHASE(active |= ph_buf_exec(g, s, lane, nl));
             LUF_T_PHASE(ph_buf_restore(g, s, lane, nl));
-            LUF_T_PHASE(for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0xFFFFFFFFu);
+            LUF_T_PHASE(for (int w = lane; w < g.WN; w += nl) claim_bits(s)[w] = 0xFFFFFFFFu);
         } else if (rounds == 0) {              // every defect is an active singleton
             LUF_T_PHASE(active |= ph_grow_first(g, s, lane, nl); if (lane == 0) s.cnt[5] = s.cnt[0]);
         } else {
@@ -682,10 +715,10 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
             LUF_NOUNROLL
             for (uint32_t guard = 0; guard <= n; ++guard) {           // at least one edge is placed per iteration
                 if (iter == 0) {                                      // tags used up (huge graphs): start over
-                    LUF_T_PHASE(for (int w = lane; w < LUF_T_CLAIM_SLOTS; w += nl) s.claim[w] = 0xFFFFFFFFu);
+                    LUF_T_PHASE(for (int w = lane; w < LUF_T_CLAIM_SLOTS; w += nl) s.claim[w] = WORD_ONES);
                     iter = 0xFFFFu;
                 }
-                const uint32_t tag = iter-- << 16;
+                const word_t tag = (word_t)(iter--) << HSH;
                 uint32_t placed = 0;
                 LUF_T_PHASE(placed += ph_merge_claim<TF>(g, s, flags, n, tag, guard == 0, lane, nl));
                 LUF_T_PHASE(placed += ph_merge_exec<TF>(g, s, flags, n, tag, lane, nl));
@@ -697,7 +730,7 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
         }
     }
     // hand over to the peel: counters cleared, visited bitmap (in the claim table) cleared
-    LUF_T_PHASE(if (lane < 4) s.cnt[lane] = 0; for (int w = lane; w < g.WN; w += nl) s.claim[w] = 0);
+    LUF_T_PHASE(if (lane < 4) s.cnt[lane] = 0; for (int w = lane; w < g.WN; w += nl) claim_bits(s)[w] = 0);
     return rounds;
 }
 
@@ -714,19 +747,20 @@ LUF_DEV int uf_validate_t(const GraphView& g, const Shot& s, int flags, int lane
 // comes to hold boundary nodes of different sides (cnt[4]) is decoded again in canonical order.
 LUF_DEV void ph_fmerge_hook(const GraphView& g, const Shot& s, uint32_t i, int lane)
 {
-    const uint32_t e = s.list[i] & 0xFFFFu;
-    const uint32_t uv = LUF_LDG(&g.edge_uv[e]);
-    const uint32_t u = uv & 0xFFFFu, v = uv >> 16;
+    const uint32_t e = (uint32_t)(s.list[i] & LO_MASK);
+    uint32_t u, v;
+    edge_ends(g, e, u, v);
     s.list2[lane] = 0u;                                           // nothing hooked (a payload always has ROOT_BIT)
     LUF_NOUNROLL
     for (;;) {
-        uint32_t wu, wv;
+        word_t wu, wv;
         const uint32_t ru = find_pc(s, u, wu), rv = find_pc(s, v, wv);
         if (ru == rv) return;
-        const uint32_t su = wu & SIZE_MASK, sv = wv & SIZE_MASK;
+        const uint32_t su = (uint32_t)(wu & SIZE_MASK), sv = (uint32_t)(wv & SIZE_MASK);
         const bool u_small = su < sv || (su == sv && ru > rv);
-        const uint32_t small = u_small ? ru : rv, large = u_small ? rv : ru, wsmall = u_small ? wu : wv;
-        if (luf_atomic_cas(&s.S[small], wsmall, large | (e << 16)) == wsmall) {
+        const uint32_t small = u_small ? ru : rv, large = u_small ? rv : ru;
+        const word_t wsmall = u_small ? wu : wv;
+        if (luf_atomic_cas(&s.S[small], wsmall, (word_t)large | ((word_t)e << HSH)) == wsmall) {
             s.list[i] = small;
             s.list2[lane] = wsmall;
             return;
@@ -737,21 +771,21 @@ LUF_DEV void ph_fmerge_hook(const GraphView& g, const Shot& s, uint32_t i, int l
 template <int TF>
 LUF_DEV void ph_fmerge_apply(const GraphView& g, const Shot& s, uint32_t i, int lane)
 {
-    const uint32_t pay = s.list2[lane];
+    const word_t pay = s.list2[lane];
     if (!pay) return;
-    uint32_t wr;
-    const uint32_t R = find_ro(s, s.list[i], wr);                 // roots are stable in this phase
-    const uint32_t bs = pay & BND_MASK;
+    word_t wr;
+    const uint32_t R = find_ro(s, (uint32_t)s.list[i], wr);       // roots are stable in this phase
+    const word_t bs = pay & BND_MASK;
     LUF_NOUNROLL
     for (;;) {
-        uint32_t bl = wr & BND_MASK;
+        word_t bl = wr & BND_MASK;
         if (bl && bs) {
-            const int ll = LUF_LDG(&g.node_long[(bl >> 16) - 1]), ls = LUF_LDG(&g.node_long[(bs >> 16) - 1]);
+            const int ll = LUF_LDG(&g.node_long[(uint32_t)(bl >> HSH) - 1]), ls = LUF_LDG(&g.node_long[(uint32_t)(bs >> HSH) - 1]);
             if (ll != ls) s.cnt[4] = 1u;
             if ((TF & FLAG_WEST) && ls < ll) bl = bs;
         } else if (!bl) bl = bs;
-        const uint32_t neww = ((wr ^ pay) & ODD_BIT) | bl | ROOT_BIT | ((wr & SIZE_MASK) + (pay & SIZE_MASK));
-        const uint32_t old = luf_atomic_cas(&s.S[R], wr, neww);
+        const word_t neww = ((wr ^ pay) & ODD_BIT) | bl | ROOT_BIT | ((wr & SIZE_MASK) + (pay & SIZE_MASK));
+        const word_t old = luf_atomic_cas(&s.S[R], wr, neww);
         if (old == wr) {                                          // cnt[5]: the number of active clusters
             const int delta = (int)is_active(neww) - (int)is_active(wr) - (int)is_active(pay);
             if (delta) luf_atomic_add(&s.cnt[5], (uint32_t)delta);
@@ -873,9 +907,9 @@ LUF_DEV uint32_t ph_defect_sides(const GraphView& g, const Shot& s, int lane, in
         LUF_NOUNROLL
         while (bits) {
             const int b = luf_ffs(bits) - 1; bits &= bits - 1;
-            uint32_t rr;
+            word_t rr;
             find_ro(s, (uint32_t)(g.B + 32 * w + b), rr);
-            const uint32_t bn = (rr & BND_MASK) >> 16;
+            const uint32_t bn = (uint32_t)((rr & BND_MASK) >> HSH);
             if (bn && LUF_LDG(&g.node_long[bn - 1u]) == -1) parity ^= 1u;
         }
     }

@@ -81,6 +81,77 @@ int emu_decode_uf_cta(const luf_graph_desc* d, int flags, int nl, long long nsho
     return 0;
 }
 
+// The wide instance of the phases (luf::uf_wide, luf_uf_wide.cuh: 64-bit node words, 32-bit indices): a tile
+// of `nl` lanes, the state slab in host memory.
+static uf_wide::GraphView wide_view_of(const PackedWide& p)
+{
+    uf_wide::GraphView g;
+    g.N = p.N; g.B = p.B; g.E = p.E;
+    g.WE = words32(p.E); g.WD = words32(p.N - p.B); g.WN = words32(p.N);
+    g.DEG = p.DEG; g.adj = p.adj.data(); g.edge_uv = p.edge_uv.data();
+    g.west_mask = p.west_mask.data(); g.node_long = p.node_long.data();
+    g.F = p.F; g.n_classes = p.n_classes; g.parity_ok = p.parity_ok ? 1 : 0; g.leaf_bnd = 0;
+    g.fresh_perm32 = p.perm_identity ? nullptr : p.fresh_perm32.data(); g.class_end = p.class_end.data();
+    return g;
+}
+
+int emu_decode_uf_wide(const luf_graph_desc* d, int flags, int nl, long long nshots, const uint32_t* syn,
+                       uint32_t* corr, uint32_t* growth2b, int32_t* steps)
+{
+    PackedWide p;
+    if (!pack_wide(*d, p).empty() || nl < 32 || nl > 1024) return -1;
+    const uf_wide::GraphView g = wide_view_of(p);
+    const uf_wide::Layout l = make_wide_layout(p.N, p.B, p.E, false, true);
+    std::vector<unsigned char> mem(l.bytes);
+    const uf_wide::Shot s = uf_wide::bind(l, mem.data());
+    const int GW = (g.E + 15) / 16;
+    for (long long k = 0; k < nshots; ++k) {
+        LUF_PHASE(uf_wide::ph_reset(g, l, s, lane, nl));
+        for (int w = 0; w < g.WD; ++w) s.defect[w] = syn[k * g.WD + w];
+        LUF_PHASE(uf_wide::ph_load(g, s, lane, nl));
+        const int rounds = uf_wide::uf_validate_t<-1>(g, s, flags, 0, nl);
+        if (growth2b) std::memcpy(growth2b + k * GW, s.growth, 4u * GW);
+        uf_wide::uf_peel(g, s, 0, nl);
+        std::memcpy(corr + k * g.WE, s.corr, 4u * g.WE);
+        if (steps) { steps[2 * k] = rounds; steps[2 * k + 1] = 0; }
+    }
+    return 0;
+}
+
+// Fused shot loop of the wide instance; exports as emu_mc_uf.  parity_only: the logical bit through
+// uf_peel_parity (what k_mc_uf_wide runs) instead of the full peel.
+int emu_mc_uf_wide(const luf_graph_desc* d, int flags, int nl, int parity_only, const double* class_p, unsigned long long seed,
+                   unsigned long long shot0, long long nshots, unsigned long long counts[2],
+                   uint32_t* err_out, uint32_t* syn_out, uint32_t* corr_out, uint8_t* logical_out)
+{
+    PackedWide p;
+    PackedFast pf;
+    if (!pack_wide(*d, p).empty() || nl < 32 || nl > 1024) return -1;
+    pack_fast(*d, pf);
+    uf_wide::GraphView g = wide_view_of(p);
+    g.leaf_bnd = pf.ok || (p.parity_ok && [&] { for (int v = 0; v < d->n_boundary; ++v) if (d->inc_off[v + 1] - d->inc_off[v] != 1) return false; return true; }()) ? 1 : 0;
+    const uf_wide::Layout l = make_wide_layout(p.N, p.B, p.E, true, true);
+    const SampleParams sp = make_sample_params(class_p, p.n_classes, seed);
+    std::vector<unsigned char> mem(l.bytes);
+    const uf_wide::Shot s = uf_wide::bind(l, mem.data());
+    unsigned long long fails = 0;
+    for (long long k = 0; k < nshots; ++k) {
+        uint32_t parity = 0;
+        LUF_PHASE(uf_wide::ph_reset(g, l, s, lane, nl));
+        LUF_PHASE(if (lane < 32) parity ^= uf_wide::ph_sample(g, s, sp, shot0 + k, lane, 32));
+        if (err_out) std::memcpy(err_out + k * g.WE, s.err, 4u * g.WE);
+        if (syn_out) std::memcpy(syn_out + k * g.WD, s.defect, 4u * g.WD);
+        LUF_PHASE(uf_wide::ph_load(g, s, lane, nl));
+        uf_wide::uf_validate_t<-1>(g, s, flags, 0, nl);
+        parity ^= parity_only ? uf_wide::uf_peel_parity(g, s, 0, nl) : uf_wide::uf_peel(g, s, 0, nl);
+        if (corr_out) std::memcpy(corr_out + k * g.WE, s.corr, 4u * g.WE);
+        if (logical_out) logical_out[k] = (uint8_t)(parity & 1u);
+        fails += parity & 1u;
+    }
+    counts[0] += fails; counts[1] += (unsigned long long)nshots;
+    return 0;
+}
+
 // Fixed-weight sampler (ph_force): errors and syndromes of shots [shot0, shot0 + nshots).
 int emu_sample_weight(const luf_graph_desc* d, int weight, unsigned long long seed, unsigned long long shot0,
                       long long nshots, uint32_t* err_out, uint32_t* syn_out)

@@ -24,7 +24,7 @@ def build(tiny_lists=False):
     if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in SRCS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(['g++', '-O1', '-g', '-fPIC', '-shared', '-std=c++17', '-Wall', '-Wextra']
-                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2', '-DLUF_CTA_LIST_CAP=5', '-DLUF_CTA_LIST2_CAP=3', '-DLUF_CA_TLIST_CAP=4', '-DLUF_SF_ALIST_CAP=4', '-DLUF_SF_CTA_ALIST_CAP=6', '-DLUF_CA_CTA_TLIST_CAP=5'] if tiny_lists else []) + ['-o', out, SRCS[0]],
+                       + (['-DLUF_LIST_CAP=3', '-DLUF_LIST2_CAP=2', '-DLUF_CTA_LIST_CAP=5', '-DLUF_CTA_LIST2_CAP=3', '-DLUF_CA_TLIST_CAP=4', '-DLUF_SF_ALIST_CAP=4', '-DLUF_SF_CTA_ALIST_CAP=6', '-DLUF_CA_CTA_TLIST_CAP=5', '-DLUF_WIDE_LIST_CAP=5', '-DLUF_WIDE_LIST2_CAP=3'] if tiny_lists else []) + ['-o', out, SRCS[0]],
                        check=True, capture_output=True)
     return out
 
@@ -94,6 +94,32 @@ class Emu:
                                      _vp(corr), _vp(growth), _vp(steps))
         assert rc == 0
         return corr, growth, steps
+
+    def decode_uf_wide(self, flags, syn_bits, nl=128):
+        """The wide instance of the phases (luf::uf_wide: 64-bit node words) with a tile of ``nl`` lanes."""
+        syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
+        n = syn.shape[0]
+        corr = np.zeros((n, self.WE), np.uint32)
+        growth = np.zeros((n, self.WG), np.uint32)
+        steps = np.zeros((n, 2), np.int32)
+        rc = lib().emu_decode_uf_wide(C.byref(self.desc), flags, nl, C.c_longlong(n), _vp(syn),
+                                      _vp(corr), _vp(growth), _vp(steps))
+        assert rc == 0
+        return corr, growth, steps
+
+    def mc_uf_wide(self, flags, noise_level, seed, shot0, nshots, nl=128, parity_only=False):
+        """Fused shot loop of the wide instance: (failures, err, syn, corr, logical)."""
+        cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
+        counts = (C.c_ulonglong * 2)(0, 0)
+        err = np.zeros((nshots, self.WE), np.uint32)
+        syn = np.zeros((nshots, self.WD), np.uint32)
+        corr = np.zeros((nshots, self.WE), np.uint32)
+        logical = np.zeros(nshots, np.uint8)
+        rc = lib().emu_mc_uf_wide(C.byref(self.desc), flags, nl, int(parity_only), _vp(cp), C.c_ulonglong(seed),
+                                  C.c_ulonglong(shot0), C.c_longlong(nshots), counts,
+                                  _vp(err), _vp(syn), _vp(corr), _vp(logical))
+        assert rc == 0
+        return int(counts[0]), err, syn, corr, logical
 
     def sample_weight(self, weight, seed, shot0, nshots):
         err = np.zeros((nshots, self.WE), np.uint32)

@@ -127,6 +127,9 @@ def test_emu_overflow_paths_with_tiny_work_lists():
                 corr, growth2b, steps = emu.decode_uf_cta(flags, arr['syn_bits'], nl=96)
                 np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{variant}_growth'])
                 np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
+                corr, growth2b, steps = emu.decode_uf_wide(flags, arr['syn_bits'], nl=96)      # luf::uf_wide, lists of 5 / 3
+                np.testing.assert_array_equal(unpack_growth(growth2b, meta['E']), arr[f'{variant}_growth'])
+                np.testing.assert_array_equal(corr, arr[f'{variant}_corr'])
     finally:
         emu_binding.use_tiny_lists(False)
 
