@@ -18,6 +18,7 @@
 #include "luf_ca.cuh"
 #include "luf_sf.cuh"
 #include "luf_fw.cuh"
+#include "luf_fw_wide.cuh"
 
 namespace luf {
 
@@ -449,6 +450,57 @@ inline FwLayout make_fw_layout(int N, int E, uint32_t base)
     l.buf = take(4u * words32(E)); l.commit = take(4u * words32(E));
     l.partner = take(2u * N); l.partner2 = take(2u * N);
     l.bytes = off;
+    return l;
+}
+
+// forward scheme on the wide instance (luf_fw_wide.cuh): the same tables with 32-bit entries
+struct PackedForwardWide {
+    int c = 0, n_cleanse = 0, n_buffer = 0;
+    std::vector<uint32_t> lower_edge, art_node, node_lower, buffer_perm, commit_mask, fb_mask, buffer_class_end;
+    std::vector<uint8_t> node_side;
+};
+
+inline std::string pack_forward_wide(const luf_graph_desc_dims& dims, const luf_forward_desc& d, PackedForwardWide& out)
+{
+    const int N = dims.N, E = dims.E, B = dims.B, C = dims.n_classes;
+    if (d.commit_height < 1 || d.n_cleanse < 1) return "bad commit height";
+    out.c = d.commit_height; out.n_cleanse = d.n_cleanse;
+    out.lower_edge.assign(E, fw_wide::W_NONE); out.art_node.assign(2 * (size_t)E, fw_wide::W_NONE);
+    out.commit_mask.assign(d.commit_mask, d.commit_mask + words32(E));
+    out.fb_mask.assign(words32(E), 0);
+    for (int e = 0; e < E; ++e) {
+        if (d.lower_edge[e] >= E) return "lower_edge out of range";
+        if (d.lower_edge[e] >= 0) out.lower_edge[e] = (uint32_t)d.lower_edge[e];
+        for (int x = 0; x < 2; ++x) {
+            const int a = d.art_node[2 * e + x];
+            if (a >= N || (a >= 0 && a < B)) return "artificial defect must be a detector";
+            if (a >= 0) out.art_node[2 * (size_t)e + x] = (uint32_t)a;
+        }
+        if (d.edge_fb[e]) out.fb_mask[e >> 5] |= 1u << (e & 31);
+    }
+    out.node_lower.assign(N, fw_wide::W_NONE); out.node_side.assign(d.node_side, d.node_side + N);
+    for (int v = 0; v < N; ++v) {
+        if (d.node_lower[v] >= N) return "node_lower out of range";
+        if (d.node_lower[v] >= 0) out.node_lower[v] = (uint32_t)d.node_lower[v];
+    }
+    out.buffer_class_end.assign(C, 0); out.buffer_perm.clear();
+    for (int c = 0; c < C; ++c) {
+        for (int e = 0; e < E; ++e)
+            if (d.buffer_class[e] == c) out.buffer_perm.push_back((uint32_t)e);
+        out.buffer_class_end[c] = (uint32_t)out.buffer_perm.size();
+    }
+    out.n_buffer = (int)out.buffer_perm.size();
+    return "";
+}
+
+inline fw_wide::FwLayout make_fw_wide_layout(int N, int E, uint32_t base)
+{
+    fw_wide::FwLayout l;
+    uint32_t off = base;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off = align16(off + bytes); return o; };
+    l.buf = take(4u * words32(E)); l.commit = take(4u * words32(E)); l.nz = take(4u * ((words32(E) + 31) / 32));
+    l.partner = take(4u * N); l.partner2 = take(4u * N);
+    l.bytes = (off + 127u) & ~127u;
     return l;
 }
 

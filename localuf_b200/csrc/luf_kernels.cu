@@ -830,6 +830,58 @@ __global__ void k_sample_wide(uf_wide::GraphView g, SampleParams sp, uint32_t we
     }
 }
 
+// Forward scheme (_schemes.py:392-450) around the wide UF instance: one block per stream (luf_fw_wide.cuh).
+struct FwWideArgs {
+    uf_wide::GraphView gv; uf_wide::Layout ul; fw_wide::FwView fw; fw_wide::FwLayout fl; SampleTab buffer_tab;
+    int flags, n_cleanse;
+};
+
+__device__ __forceinline__ unsigned char* fw_wide_state(const fw_wide::FwLayout& l, unsigned char* slab)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    return slab ? slab + (size_t)blockIdx.x * l.bytes : smem;
+}
+
+__global__ void __launch_bounds__(512, 2) k_fw_decode_wide(FwWideArgs a, long long nstreams, int ncycles, const uint32_t* __restrict__ init_buf,
+                            const uint32_t* __restrict__ fresh, int32_t* __restrict__ steps,
+                            uint32_t* __restrict__ commit_out, int32_t* __restrict__ m_out, unsigned char* slab)
+{
+    const int lane = threadIdx.x, nl = blockDim.x;
+    unsigned char* base = fw_wide_state(a.fl, slab);
+    const fw_wide::FwState f = fw_wide::fw_bind(a.fl, base);
+    const fw_wide::FwUf d{a.gv, a.ul, uf_wide::bind(a.ul, base), a.flags};
+    const int WE = a.fw.WE;
+    for (long long k = blockIdx.x; k < nstreams; k += gridDim.x) {
+        fw_wide::fw_reset(a.fw, f, init_buf + (size_t)k * WE, lane, nl);
+        __syncthreads();
+        for (int c = 0; c < ncycles; ++c) {
+            const size_t row = (size_t)k * ncycles + c;
+            int s0 = 0, s1 = 0;
+            const int m = fw_wide::fw_cycle_given(a.fw, f, d, fresh + row * WE, commit_out ? commit_out + row * WE : nullptr,
+                                                  s0, s1, lane, nl);
+            if (lane == 0) { steps[2 * row] = s0; steps[2 * row + 1] = s1; m_out[row] = m; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512, 2) k_fw_mc_wide(FwWideArgs a, SampleParams sp, unsigned long long stream0, long long nstreams, int n,
+                        unsigned long long* counts, int32_t* steps, unsigned char* slab)
+{
+    const int lane = threadIdx.x, nl = blockDim.x;
+    unsigned char* base = fw_wide_state(a.fl, slab);
+    const fw_wide::FwState f = fw_wide::fw_bind(a.fl, base);
+    const fw_wide::FwUf d{a.gv, a.ul, uf_wide::bind(a.ul, base), a.flags};
+    int m_total = 0;
+    long long cycles = 0, s0 = 0, s1 = 0;
+    for (long long k = blockIdx.x; k < nstreams; k += gridDim.x)
+        fw_wide::fw_run(a.fw, f, d, a.buffer_tab, sp, stream0 + (unsigned long long)k, n, a.n_cleanse, m_total, cycles,
+                        s0, s1, steps ? steps + (size_t)k * n * 2 : nullptr, lane, nl);
+    if (lane == 0) {
+        atomicAdd(&counts[0], (unsigned long long)m_total); atomicAdd(&counts[1], (unsigned long long)cycles);
+        atomicAdd(&counts[2], (unsigned long long)s0); atomicAdd(&counts[3], (unsigned long long)s1);
+    }
+}
+
 // k_count_strings on the wide tables: the partner map (one int32 per node) of a warp lives in global memory.
 static const int WSTR_NONE = INT32_MIN;
 __device__ __forceinline__ int wstr_key(const uf_wide::GraphView& g, uint32_t v)
@@ -941,7 +993,11 @@ struct luf_graph {
     bool wide = false;
     PackedWide wide_host;
     uf_wide::GraphView wview{};
-    uf_wide::Layout wlay_fused{}, wlay_decode{};
+    uf_wide::Layout wlay_fused{}, wlay_decode{}, wfw_lay_uf{};
+    PackedForwardWide wfw_host;
+    fw_wide::FwView wfw_view{};
+    fw_wide::FwLayout wfw_ext{};
+    SampleTab wfw_buffer_tab{};
     std::map<std::pair<void*, int>, std::pair<void*, size_t>> slabs;    // per (stream, use): the state slabs of a persistent grid
 };
 
@@ -1283,14 +1339,17 @@ static int wide_slab(luf_graph* g, void* stream, int use, size_t bytes, void** o
 }
 
 // One block per shot.  The state slab goes to shared memory when two blocks' slabs fit on an SM, else to global
-// memory with as many resident blocks as keep all slabs of the grid inside L2 (LUF_WIDE_L2_MB, default 96 of
-// the B200's 126 MB).  LUF_WIDE_STATE=smem|global, LUF_WIDE_THREADS override (measurements).
+// memory with as many resident blocks as the registers allow while the slabs of the grid stay within
+// LUF_WIDE_L2_MB (default 192: Surface(23, 'circuit-level'), 197 KB per shot, 820 k shots/s with four blocks of
+// 256 threads per SM = 116 MB of slabs against 710 k with three and 330 k with one; the B200's L2 holds 126 MB
+// and what spills is streamed from HBM).  LUF_WIDE_STATE=smem|global, LUF_WIDE_THREADS override (measurements).
 template <class K>
-static int wide_plan(luf_graph* g, K kernel, const uf_wide::Layout& l, long long nshots, void* stream, WidePlan* out)
+static int wide_plan_bytes(luf_graph* g, K kernel, uint32_t slab_bytes, long long nshots, void* stream, WidePlan* out)
 {
+    struct { uint32_t bytes; } l = {slab_bytes};
     const char* env_state = getenv("LUF_WIDE_STATE");
     const int env_threads = getenv("LUF_WIDE_THREADS") ? atoi(getenv("LUF_WIDE_THREADS")) : 0;
-    const int env_l2 = getenv("LUF_WIDE_L2_MB") ? atoi(getenv("LUF_WIDE_L2_MB")) : 96;
+    const int env_l2 = getenv("LUF_WIDE_L2_MB") ? atoi(getenv("LUF_WIDE_L2_MB")) : 192;
     bool in_smem = (size_t)2 * l.bytes + 2048 <= (size_t)g->max_smem;
     if (env_state && !strcmp(env_state, "global")) in_smem = false;
     if (env_state && !strcmp(env_state, "smem")) in_smem = l.bytes <= (uint32_t)g->max_smem;
@@ -1323,6 +1382,12 @@ static int wide_plan(luf_graph* g, K kernel, const uf_wide::Layout& l, long long
         fprintf(stderr, "[luf] wide plan: %u B per shot in %s memory, %d threads per block, %d blocks per SM\n", l.bytes,
                 in_smem ? "shared" : "global", threads, per_sm);
     return 0;
+}
+
+template <class K>
+static int wide_plan(luf_graph* g, K kernel, const uf_wide::Layout& l, long long nshots, void* stream, WidePlan* out)
+{
+    return wide_plan_bytes(g, kernel, l.bytes, nshots, stream, out);
 }
 
 // *_host entry points on stream 0: no asynchronous copy into a caller's buffer outlives the call, error or not
@@ -1705,7 +1770,8 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     // beyond the 16-bit layout -- or LUF_FORCE_WIDE=1 (tests: any graph through the wide kernels)
     g->wide = (!why.empty() && why.find("too large") != std::string::npos) || (getenv("LUF_FORCE_WIDE") && atoi(getenv("LUF_FORCE_WIDE")) != 0);
     if (!why.empty() && !g->wide) { delete g; return fail(LUF_ERR_INVALID, why); }
-    if (g->wide) {
+    {   // the wide tables are kept for every graph: a forward window or a decode state that does not fit the
+        // shared memory of an SM in the 16-bit layout runs through the wide instance too
         const std::string wwhy = pack_wide(*desc, g->wide_host);
         if (!wwhy.empty()) { delete g; return fail(LUF_ERR_INVALID, wwhy); }
     }
@@ -1728,7 +1794,7 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
             return rc;
         }
     }
-    if (g->wide) {
+    {
         const PackedWide& q = g->wide_host;
         uf_wide::GraphView& w = g->wview;
         w.N = q.N; w.B = q.B; w.E = q.E; w.F = q.F; w.n_classes = q.n_classes; w.DEG = q.DEG;
@@ -1770,6 +1836,7 @@ int luf_graph_create(const luf_graph_desc* desc, int device, luf_graph** out)
     g->lay_decode = make_layout(p.N, p.B, p.E, false, true);
     g->lay_fused_cta = make_layout(p.N, p.B, p.E, false, false, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS);
     g->lay_decode_cta = make_layout(p.N, p.B, p.E, false, true, LUF_CTA_LIST_CAP, LUF_CTA_LIST2_CAP, LUF_CTA_CLAIM_SLOTS);
+    if (g->lay_decode.bytes > (uint32_t)g->max_smem && g->lay_decode_cta.bytes > (uint32_t)g->max_smem) g->wide = true;   // no 16-bit tile holds a shot
     {   // the sampler only needs the error and defect bitmaps
         Layout l; memset(&l, 0, sizeof(l));
         uint32_t off = 0;
@@ -2171,9 +2238,28 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
 int luf_forward_attach(luf_graph* g, const luf_forward_desc* d)
 {
     if (!g || !d) return fail(LUF_ERR_INVALID, "null argument");
-    if (!g->canonical_ok) return fail(LUF_ERR_UNSUPPORTED, "this graph is beyond the 16-bit layout of the canonical kernels (N <= 32767, E <= 65533): only luf_sample, luf_check and luf_mc_run with UF under the west inclination run on it (the compact path, luf_uf_fast.cuh)");
     CUDA_TRY(cudaSetDevice(g->device));
     const luf_graph_desc_dims dims = {g->view.N, g->view.B, g->view.E, g->view.n_classes};
+    {                               // the forward scheme around the wide UF instance (luf_fw_wide.cuh)
+        const std::string wwhy = pack_forward_wide(dims, *d, g->wfw_host);
+        if (!wwhy.empty()) return fail(LUF_ERR_INVALID, wwhy);
+        const PackedForwardWide& p = g->wfw_host;
+        fw_wide::FwView& v = g->wfw_view;
+        v.N = dims.N; v.B = dims.B; v.E = dims.E; v.WE = g->view.WE; v.WD = g->view.WD; v.c = p.c;
+        v.edge_uv = g->wview.edge_uv;
+        int rc = 0;
+        g->wfw_buffer_tab.perm = nullptr;
+        if ((rc = upload(g, p.lower_edge, &v.lower_edge)) || (rc = upload(g, p.commit_mask, &v.commit_mask)) ||
+            (rc = upload(g, p.art_node, &v.art_node)) || (rc = upload(g, p.fb_mask, &v.fb_mask)) ||
+            (rc = upload(g, p.node_lower, &v.node_lower)) || (rc = upload(g, p.node_side, &v.node_side)) ||
+            (rc = upload(g, p.buffer_perm, &g->wfw_buffer_tab.perm32)) ||
+            (rc = upload(g, p.buffer_class_end, &g->wfw_buffer_tab.class_end))) return rc;
+        g->wfw_buffer_tab.F = p.n_buffer; g->wfw_buffer_tab.n_classes = dims.n_classes;
+        g->wfw_lay_uf = make_wide_layout(dims.N, dims.B, dims.E, true, true);
+        g->wfw_ext = make_fw_wide_layout(dims.N, dims.E, g->wfw_lay_uf.bytes);
+        g->has_forward = true;
+        if (!g->canonical_ok) return 0;
+    }
     const std::string why = pack_forward(dims, *d, g->fw_host);
     if (!why.empty()) return fail(LUF_ERR_INVALID, why);
     const PackedForward& p = g->fw_host;
@@ -2207,12 +2293,40 @@ static int fw_args(luf_graph* g, int decoder, int flags, FwArgs* a)
     return 0;
 }
 
+// UF streams take the wide instance when the graph does (luf_graph::wide) or when a stream's state in the 16-bit
+// layout exceeds the shared memory of an SM (the 16-bit forward kernels keep a warp's slice there)
+static bool fw_is_wide(const luf_graph* g, int decoder)
+{
+    return g->has_forward && decoder == LUF_DEC_UF && (g->wide || g->fw_ext_uf.bytes > (uint32_t)g->max_smem);
+}
+
+static int fw_wide_args(luf_graph* g, int flags, FwWideArgs* a)
+{
+    if (int rc = check_decoder(g, LUF_DEC_UF, flags)) return rc;
+    a->gv = g->wview; a->ul = g->wfw_lay_uf; a->fw = g->wfw_view; a->fl = g->wfw_ext; a->buffer_tab = g->wfw_buffer_tab;
+    a->flags = flags; a->n_cleanse = g->wfw_host.n_cleanse;
+    return 0;
+}
+
 int luf_forward_decode(luf_graph* g, int decoder, int flags, int64_t nstreams, int32_t ncycles,
                        const uint32_t* init_buffer_dev, const uint32_t* fresh_bits_dev, int32_t* steps_dev,
                        uint32_t* commit_bits_dev, int32_t* m_dev, void* stream)
 {
     if (!g || !init_buffer_dev || !fresh_bits_dev || !steps_dev || !m_dev || nstreams < 0 || ncycles < 0)
         return fail(LUF_ERR_INVALID, "luf_forward_decode: bad argument");
+    if (fw_is_wide(g, decoder)) {
+        FwWideArgs wa;
+        if (int rc = fw_wide_args(g, flags, &wa)) return rc;
+        if (nstreams == 0 || ncycles == 0) return 0;
+        CUDA_TRY(cudaSetDevice(g->device));
+        WidePlan w;
+        if (int rc = wide_plan_bytes(g, k_fw_decode_wide, wa.fl.bytes, nstreams, stream, &w)) return rc;
+        k_fw_decode_wide<<<w.grid, w.threads, w.smem, (cudaStream_t)stream>>>(wa, nstreams, ncycles, init_buffer_dev, fresh_bits_dev,
+                                                                           steps_dev, commit_bits_dev, m_dev, w.slab);
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+        return 0;
+    }
     FwArgs a;
     if (int rc = fw_args(g, decoder, flags, &a)) return rc;
     if (nstreams == 0 || ncycles == 0) return 0;
@@ -2237,6 +2351,19 @@ int luf_forward_mc(luf_graph* g, int decoder, int flags, const double* class_p_h
 {
     if (!g || !class_p_host || !counts_dev || nstreams < 0) return fail(LUF_ERR_INVALID, "luf_forward_mc: bad argument");
     if (n < 1) return fail(LUF_ERR_INVALID, "n must be positive integer.");
+    if (fw_is_wide(g, decoder)) {
+        FwWideArgs wa;
+        if (int rc = fw_wide_args(g, flags, &wa)) return rc;
+        if (nstreams == 0) return 0;
+        CUDA_TRY(cudaSetDevice(g->device));
+        const SampleParams wsp = make_sample_params(class_p_host, g->view.n_classes, seed);
+        WidePlan w;
+        if (int rc = wide_plan_bytes(g, k_fw_mc_wide, wa.fl.bytes, nstreams, stream, &w)) return rc;
+        k_fw_mc_wide<<<w.grid, w.threads, w.smem, (cudaStream_t)stream>>>(wa, wsp, stream0, nstreams, n, counts_dev, steps_dev, w.slab);
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+        return 0;
+    }
     FwArgs a;
     if (int rc = fw_args(g, decoder, flags, &a)) return rc;
     if (nstreams == 0) return 0;

@@ -486,6 +486,32 @@ int emu_fw_stream(const luf_graph_desc* gd, const luf_forward_desc* fd, int deco
     return 0;
 }
 
+// Forward scheme on the wide instance (luf_fw_wide.cuh), UF, one stream, a tile of `nl` lanes.
+int emu_fw_stream_wide(const luf_graph_desc* gd, const luf_forward_desc* fd, int flags, int nl, int ncycles,
+                       const uint32_t* init_buf, const uint32_t* fresh, int32_t* steps, uint32_t* commit_out, int32_t* m_out)
+{
+    PackedWide pg; PackedForwardWide pf;
+    if (!pack_wide(*gd, pg).empty()) return -1;
+    const luf_graph_desc_dims dims = {pg.N, pg.B, pg.E, pg.n_classes};
+    if (!pack_forward_wide(dims, *fd, pf).empty()) return -3;
+    const uf_wide::GraphView gv = wide_view_of(pg);
+    fw_wide::FwView g;
+    g.N = pg.N; g.B = pg.B; g.E = pg.E; g.WE = words32(pg.E); g.WD = words32(pg.N - pg.B); g.c = pf.c;
+    g.edge_uv = pg.edge_uv.data(); g.lower_edge = pf.lower_edge.data(); g.commit_mask = pf.commit_mask.data();
+    g.art_node = pf.art_node.data(); g.fb_mask = pf.fb_mask.data(); g.node_lower = pf.node_lower.data();
+    g.node_side = pf.node_side.data();
+    const uf_wide::Layout ul = make_wide_layout(pg.N, pg.B, pg.E, true, true);
+    const fw_wide::FwLayout fl = make_fw_wide_layout(pg.N, pg.E, ul.bytes);
+    std::vector<unsigned char> mem(fl.bytes);
+    const fw_wide::FwState f = fw_wide::fw_bind(fl, mem.data());
+    fw_wide::FwUf d{gv, ul, uf_wide::bind(ul, mem.data()), flags};
+    LUF_PHASE(fw_wide::fw_reset(g, f, init_buf, lane, nl));
+    for (int c = 0; c < ncycles; ++c)
+        m_out[c] = fw_wide::fw_cycle_given(g, f, d, fresh + (size_t)c * g.WE, commit_out + (size_t)c * g.WE,
+                                           steps[2 * c], steps[2 * c + 1], 0, nl);
+    return 0;
+}
+
 // Snowflake + frugal bookkeeping on given fresh errors (one stream).
 int emu_sf_stream_metrics(const luf_window_desc* d, int flags, int ncycles, const uint32_t* fresh,
                           int32_t* rt, uint32_t* floor_bits, int32_t* m_out, uint32_t* mgrowth, int32_t* mins,

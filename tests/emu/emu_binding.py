@@ -223,6 +223,24 @@ class Emu:
         return steps, commit, m
 
 
+    def _forward_stream_wide(self, code, flags, init_bits, fresh_bits, nl=96):
+        """The forward scheme on the wide instance (luf_fw_wide.cuh), UF."""
+        from localuf_b200 import _window
+        from localuf_b200._engine import make_forward_desc
+        fdesc, keep = make_forward_desc(_window.build_forward(code))
+        fresh = np.ascontiguousarray(fresh_bits, dtype=np.uint32).reshape(-1, self.WE)
+        init = np.ascontiguousarray(init_bits, dtype=np.uint32).reshape(self.WE)
+        n = fresh.shape[0]
+        steps = np.zeros((n, 2), np.int32); commit = np.zeros((n, self.WE), np.uint32); m = np.zeros(n, np.int32)
+        rc = lib().emu_fw_stream_wide(C.byref(self.desc), C.byref(fdesc), flags, nl, n, _vp(init), _vp(fresh),
+                                      _vp(steps), _vp(commit), _vp(m))
+        assert rc == 0, rc
+        return steps, commit, m
+
+
+Emu.forward_stream_wide = Emu._forward_stream_wide
+
+
 class EmuStream:
     """Host emulation of the Snowflake / frugal kernel phases for one window."""
 

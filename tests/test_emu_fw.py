@@ -22,3 +22,16 @@ def test_emu_forward_matches_reference(name):
         np.testing.assert_array_equal(steps, arr[f'{key}_steps'], err_msg=f'{name} {key} steps')
         np.testing.assert_array_equal(commit, arr[f'{key}_commit'], err_msg=f'{name} {key} commit leftover')
         np.testing.assert_array_equal(m, arr[f'{key}_m'], err_msg=f'{name} {key} logical errors')
+
+
+@pytest.mark.parametrize('name', golden_names('fw_'))
+@pytest.mark.parametrize('nl', [32, 160])
+def test_emu_forward_wide_matches_reference(name, nl):
+    """The forward scheme on the wide instance (luf_fw_wide.cuh: 32-bit tables, block tile), UF."""
+    meta, arr = load_golden(name)
+    code = make_code(meta['spec'])
+    emu = emu_binding.Emu(code)
+    steps, commit, m = emu.forward_stream_wide(code, 0, arr['uf_init'], arr['uf_fresh'], nl=nl)
+    np.testing.assert_array_equal(steps, arr['uf_steps'])
+    np.testing.assert_array_equal(commit, arr['uf_commit'])
+    np.testing.assert_array_equal(m, arr['uf_m'])

@@ -71,3 +71,68 @@ def test_wide_graph_canonical_decode_vs_oracle(d, p, n, state, monkeypatch):
         assert (fails, shots) == (int(want.sum()), n)
     m, slender = code.SCHEME.run(L.decoders.UF(code), p, 500, seed=3)
     assert slender == 500 and 0 <= m <= 500
+
+
+def test_global_batch_window_beyond_16bit_layout():
+    """Global batch scheme (_schemes.py:166-203) with h = d * n = 1650 layers: 33000 detectors, 100630 edges.
+    Sampled, decoded (wide instance) and counted (k_count_strings_wide) on the device; corrections equal the
+    oracle's, per-window counts equal the host mirror of Global.get_logical_error on the same windows."""
+    import localuf_b200 as L
+    from localuf_b200 import _engine
+    n = 330
+    code = L.Surface(5, 'phenomenological', scheme='global batch', window_height=5 * n)
+    assert code.FLAT.n_detectors > 32766
+    eng = _engine.Engine(code, device=0)
+    orc = binding.Oracle.from_code(code)
+    p, shots = 0.01, 12
+    err, syn = eng.sample_host(p, 5, 0, shots)
+    np.testing.assert_array_equal(orc.syndrome(err), syn)
+    corr, _, steps = eng.decode_batch_host(_engine.DEC_UF, 0, syn)
+    ocorr, _, osteps = orc.decode_batch(0, 0, syn, want_growth=False)
+    np.testing.assert_array_equal(corr, ocorr)
+    np.testing.assert_array_equal(steps[:, 0], osteps[:, 0])
+    total, per = eng.mc_global(_engine.DEC_UF, 0, p, 5, 0, shots, chunk=8, want_counts=True)
+    np.testing.assert_array_equal(per, [code.SCHEME.count_leftover_bits(l) for l in err ^ corr])
+    assert total == int(per.sum())
+    m, slender = code.SCHEME.run(L.decoders.UF(code), p, n, shots=4, seed=5)
+    assert slender == 4 * n and m >= 0
+
+
+@pytest.mark.parametrize('d,noise,p,nstreams,ncycles', [
+    (23, 'circuit-level', 0.004, 6, 5),          # 135608 edges, 25898 nodes: beyond the 16-bit layout
+    (25, 'phenomenological', 0.02, 6, 5),        # 33100 nodes: beyond the 16-bit layout
+    (17, 'phenomenological', 0.02, 12, 6),       # fits the 16-bit indices, but a stream's state exceeds an SM's shared memory
+])
+def test_forward_windows_beyond_16bit_layout(d, noise, p, nstreams, ncycles):
+    """The forward scheme (_schemes.py:282-450) around the wide UF instance (luf_fw_wide.cuh): per-cycle round
+    counts, commit leftovers and logical counts equal the oracle's on the same fresh errors; Forward.run runs."""
+    import localuf_b200 as L
+    from localuf_b200 import _engine
+    code = L.Surface(d, noise, scheme='forward')
+    eng = _engine.Engine(code, device=0)
+    ft = eng.attach_forward()
+    orc = binding.ForwardOracle(code, ft)
+    g = code.FLAT
+    rng = np.random.default_rng(11)
+    probs = np.array(code.NOISE.class_probabilities(p))
+
+    def bits(mask):
+        pad = np.zeros(mask.shape[:-1] + (32 * eng.WE,), np.uint8)
+        pad[..., :g.n_edges] = mask
+        return np.packbits(pad, axis=-1, bitorder='little').view(np.uint32)
+
+    fresh_p = np.where(g.edge_class != 255, probs[np.minimum(g.edge_class, len(probs) - 1)], 0.0)
+    buf_p = np.where(ft.buffer_class != 255, probs[np.minimum(ft.buffer_class, len(probs) - 1)], 0.0)
+    fresh = rng.random((nstreams, ncycles, g.n_edges)) < fresh_p
+    fresh[:, -ft.n_cleanse:, :] = False
+    init = rng.random((nstreams, g.n_edges)) < buf_p
+    fresh_b, init_b = bits(fresh), bits(init)
+    for flags in (0, 2):
+        steps, commit, m = eng.forward_decode_host(_engine.DEC_UF, flags, init_b, fresh_b)
+        for k in range(nstreams):
+            o_steps, o_commit, o_m = orc.stream(0, flags, init_b[k], fresh_b[k])
+            np.testing.assert_array_equal(steps[k], o_steps)
+            np.testing.assert_array_equal(commit[k], o_commit)
+            np.testing.assert_array_equal(m[k], o_m)
+    m, slender = code.SCHEME.run(L.decoders.UF(code), p / 4, 2, shots=4)
+    assert m >= 0 and slender > 0

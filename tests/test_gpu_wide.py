@@ -101,3 +101,31 @@ def test_wide_string_counter_equals_16bit_kernel(spec, p, monkeypatch):
     err, syn = narrow.sample_host(p, 3, 0, 500)
     corr, _, _ = narrow.decode_batch_host(_engine.DEC_UF, 0, syn)
     np.testing.assert_array_equal(eng.count_strings_host(err, corr), narrow.count_strings_host(err, corr))
+
+
+@pytest.mark.parametrize('name', golden_names('fw_'))
+@pytest.mark.parametrize('state', ['smem', 'global'])
+def test_wide_forward_matches_reference_goldens(name, state, wide):
+    """The forward scheme around the wide UF instance (luf_fw_wide.cuh) on the reference's forward goldens."""
+    from localuf_b200 import _engine
+    wide.setenv('LUF_WIDE_STATE', state)
+    meta, arr = load_golden(name)
+    code = make_code(meta['spec'])
+    eng = _engine.Engine(code, device=0)
+    steps, commit, m = eng.forward_decode_host(0, 0, arr['uf_init'][None], arr['uf_fresh'][None])
+    np.testing.assert_array_equal(steps[0], arr['uf_steps'])
+    np.testing.assert_array_equal(commit[0], arr['uf_commit'])
+    np.testing.assert_array_equal(m[0], arr['uf_m'])
+
+
+def test_wide_forward_mc_equals_16bit_kernels(monkeypatch):
+    """Forward.run with device-sampled noise: same random stream, same counts as the 16-bit forward kernels."""
+    from localuf_b200 import _engine
+    code = make_code(dict(code='Surface', d=5, noise='circuit-level', kwargs=dict(scheme='forward')))
+    narrow = _engine.Engine(code, device=0)
+    a, sa = narrow.forward_mc_host(_engine.DEC_UF, 0, 0.01, 9, 0, 64, 6, want_steps=True)
+    monkeypatch.setenv('LUF_FORCE_WIDE', '1')
+    eng = _engine.Engine(code, device=0)
+    b, sb = eng.forward_mc_host(_engine.DEC_UF, 0, 0.01, 9, 0, 64, 6, want_steps=True)
+    assert a == b
+    np.testing.assert_array_equal(sa, sb)
