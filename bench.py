@@ -347,10 +347,30 @@ def host_buffer_e2e(eng, p, world, rank, steps, n=1 << 20):
     t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {'value': n * world * steps / float(t.item()), 'unit': 'shots/s', 'h2d_bytes_per_step': 4 * WD * n,
-            'd2h_bytes_per_step': 4 * WE * n, 'shots_per_step_per_gpu': n,
-            'api': 'Engine.decode_batch_host(UF, syndromes) -> luf_decode_batch_host: host syndromes in, host '
-                   'corrections out (page-locked buffers, copies inside the timed region)'}
+    out = {'value': n * world * steps / float(t.item()), 'unit': 'shots/s', 'h2d_bytes_per_step': 4 * WD * n,
+           'd2h_bytes_per_step': 4 * WE * n, 'shots_per_step_per_gpu': n,
+           'api': 'Engine.decode_batch_host(UF, syndromes) -> luf_decode_batch_host: host syndromes in, host '
+                  'corrections out (page-locked buffers, copies inside the timed region)'}
+    # the same with logical frames out (luf_decode_frames_host): one byte per shot leaves the device
+    frame_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    frame_np = frame_h.numpy()
+    eng.decode_frames_host(0, 0, syn_np, frame_out=frame_np)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.decode_frames_host(0, 0, syn_np, frame_out=frame_np)
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out['frames'] = {'value': n * world * steps / float(t.item()), 'unit': 'shots/s', 'h2d_bytes_per_step': 4 * WD * n,
+                     'd2h_bytes_per_step': n,
+                     'api': 'Engine.decode_frames_host(UF, syndromes) -> luf_decode_frames_host: host syndromes in, one '
+                            'logical-frame byte per shot out'}
+    return out
 
 
 # the other BASELINE / SURVEY 8d measurement points, timed briefly next to the headline (N = 1 only):

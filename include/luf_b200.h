@@ -176,6 +176,16 @@ int luf_mc_run_logical_host(luf_graph *g, int decoder, int flags, const double *
 int luf_decode_batch_host(luf_graph *g, int decoder, int flags, int64_t nshots,
                           const uint32_t *syn_bits_host, uint32_t *corr_bits_host,
                           uint32_t *growth2b_host, int32_t *steps_host);
+/* Logical frames only: frame[k] = parity of shot k's correction on the logical mask
+ * (what Batch.get_logical_error, localuf/_schemes.py:123-129, sees of decoder.correction:
+ * logical error = parity(error on the mask) XOR frame).  One byte per shot leaves the
+ * device instead of W(E) words, so many ranks decoding from host buffers do not saturate
+ * the host's memory / PCIe (round-1 verdict, item 5).  steps (optional) as luf_decode_batch. */
+int luf_decode_frames(luf_graph *g, int decoder, int flags, int64_t nshots,
+                      const uint32_t *syn_bits_dev, uint8_t *frame_dev, int32_t *steps_dev,
+                      void *stream);
+int luf_decode_frames_host(luf_graph *g, int decoder, int flags, int64_t nshots,
+                           const uint32_t *syn_bits_host, uint8_t *frame_host, int32_t *steps_host);
 int luf_sample_host(luf_graph *g, const double *class_p_host, uint64_t seed, uint64_t shot0,
                     int64_t nshots, uint32_t *err_bits_host, uint32_t *syn_bits_host);
 int luf_check_host(luf_graph *g, int64_t nshots, const uint32_t *err_bits_host,

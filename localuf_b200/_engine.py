@@ -147,6 +147,8 @@ def _load():
         lib.luf_mc_run_logical.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v, v, v]
         lib.luf_mc_run_logical_host.argtypes = [v, C.c_int, C.c_int, v, u64, u64, i64, v, v]
         lib.luf_decode_batch_host.argtypes = [v, C.c_int, C.c_int, i64, v, v, v, v]
+        lib.luf_decode_frames.argtypes = [v, C.c_int, C.c_int, i64, v, v, v, v]
+        lib.luf_decode_frames_host.argtypes = [v, C.c_int, C.c_int, i64, v, v, v]
         lib.luf_sample_host.argtypes = [v, v, u64, u64, i64, v, v]
         lib.luf_check_host.argtypes = [v, i64, v, v, v, v]
         lib.luf_sample_weight.argtypes = [v, C.c_int32, u64, u64, i64, v, v, v]
@@ -271,6 +273,19 @@ class Engine:
         _check(_load().luf_decode_batch_host(self._h, decoder, flags, n, _ptr(syn), _ptr(corr),
                                              _ptr(growth), _ptr(steps)))
         return corr, growth, steps
+
+    def decode_frames_host(self, decoder: int, flags: int, syn_bits, want_steps=False, frame_out=None):
+        """Host syndromes [n, W(D)] -> host logical frames uint8 [n] (the parity of each shot's correction on
+        the logical mask; logical error = parity(error on the mask) ^ frame): one byte per shot leaves the
+        device instead of W(E) words."""
+        syn = np.ascontiguousarray(syn_bits, dtype=np.uint32).reshape(-1, self.WD)
+        n = syn.shape[0]
+        frame = np.zeros(n, np.uint8) if frame_out is None else frame_out
+        if frame.dtype != np.uint8 or frame.shape != (n,) or not frame.flags.c_contiguous:
+            raise ValueError(f'frame_out must be a C-contiguous uint8 array of shape {(n,)}')
+        steps = np.zeros((n, 2), np.int32) if want_steps else None
+        _check(_load().luf_decode_frames_host(self._h, decoder, flags, n, _ptr(syn), _ptr(frame), _ptr(steps)))
+        return (frame, steps) if want_steps else frame
 
     def sample_host(self, noise_level: float, seed: int, shot0: int, nshots: int):
         cp = self.class_p(noise_level)

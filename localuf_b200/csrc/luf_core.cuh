@@ -31,6 +31,9 @@
 #ifndef LUF_OPT_NOUNROLL_CA
   #define LUF_OPT_NOUNROLL_CA 1
 #endif
+#ifndef LUF_OPT_PHILOX_UNROLL
+  #define LUF_OPT_PHILOX_UNROLL 0
+#endif
 #if LUF_OPT_NOUNROLL && !defined(LUF_HOST_EMU)
   #define LUF_NOUNROLL _Pragma("unroll 1")
 #else
@@ -234,10 +237,13 @@ LUF_DEV void philox_block(Philox& r)
 {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
     uint32_t c0 = r.c0, c1 = r.c1, c2 = r.c2, c3 = r.c3, k0 = r.k0, k1 = r.k1;
-#if !defined(LUF_HOST_EMU)
+    // LUF_OPT_PHILOX_UNROLL: the ten rounds as straight-line code (8 instructions a round instead of 12 with the
+    // loop counter and branch)
+#if LUF_OPT_PHILOX_UNROLL && !defined(LUF_HOST_EMU)
     #pragma unroll
-#endif
+#else
     LUF_NOUNROLL
+#endif
     for (int i = 0; i < 10; ++i) {
         const uint32_t hi0 = luf_mulhi(M0, c0), lo0 = M0 * c0;
         const uint32_t hi1 = luf_mulhi(M1, c2), lo1 = M1 * c2;

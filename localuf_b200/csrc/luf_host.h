@@ -296,7 +296,9 @@ inline void pack_fast(const luf_graph_desc& d, PackedFast& out)
 // touched nodes (two defects per fault and their neighbours in later rounds), the active nodes of a round and
 // the newly FULL edges of a round.  A shot that overflows one of them is HARD (the canonical kernel decodes
 // it), so the capacities trade shared memory for the share of such shots.
-inline fast::FLayout make_fast_layout(int D, int E, int DEG, double mu)
+// `log`: room for the merge log (every newly FULL edge of a shot: about two per fault near threshold) -- what lets
+// shots with odd clusters on both sides skip the canonical kernel (hard_resolve, luf_uf_fast.cuh).
+inline fast::FLayout make_fast_layout(int D, int E, int DEG, double mu, bool log = false)
 {
     fast::FLayout l;
     auto cap = [&](double want, int most) { uint32_t c = (uint32_t)std::min<double>(want, most); return (c + 7u) & ~7u; };
@@ -320,6 +322,13 @@ inline fast::FLayout make_fast_layout(int D, int E, int DEG, double mu)
     l.growth = take(4u * (uint32_t)((E + 15) / 16)); l.defect = take(4u * WD); l.touched = take(4u * WD);
     l.zero_bytes = off - l.zero_off;
     l.tlist = take(2u * l.tcap); l.alist = take(4u * l.acap); l.mlist = take(4u * l.mcap); l.cnt = take(32);
+    // (host emulation, Surface d = 5 .. 17 near threshold: the shots that need the log make 6 mu newly FULL edges on
+    // average and 10 mu at their 99th percentile -- every edge inside a cluster becomes FULL at some point; the
+    // diagonal edges of circuit-level graphs make that 37 mu.  Only the second pass over the HARD shots carries a log.)
+    // An edge becomes FULL once, so E entries always suffice; a shot beyond the log goes to the canonical launch, whose
+    // latency for ONE such shot is milliseconds (5 ms for 11 shots of d = 17 at p = 0.026): be generous.
+    l.lcap = log ? cap((16.0 * mu + 40.0 * sq + 128.0) * (DEG > 6 ? 3.0 : 1.0), E) : 0u;
+    l.elog = l.lcap ? take(4u * l.lcap) : 0u;
     l.bytes = off;
     return l;
 }

@@ -121,10 +121,14 @@ struct TileSync {
     }
 };
 
-template <int TW, bool ADJ_SHARED>
+// LOGQ: the second pass, over the HARD shots the first one queued (`qin`, *qin_count): the same decode with
+// the merge log (luf_uf_fast.cuh); the merges inside the odd clusters on both sides are exported for
+// k_hard_resolve (x.queue), and only a shot whose log or export did not fit goes on to `queue` -- the canonical launch.
+template <int TW, bool ADJ_SHARED, bool LOGQ>
 __global__ void __launch_bounds__(1024, 1) k_mc_uf_fast(fast::FView g, fast::FLayout l, uint32_t adj_bytes, SampleParams sp,
                         unsigned long long shot0, long long nshots, unsigned long long* counts,
-                        uint8_t* __restrict__ logical, uint32_t* __restrict__ queue, uint32_t* __restrict__ qcount)
+                        uint8_t* __restrict__ logical, uint32_t* __restrict__ queue, uint32_t* __restrict__ qcount,
+                        fast::FExport x, const uint32_t* __restrict__ qin, const uint32_t* __restrict__ qin_count)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     if (ADJ_SHARED) {
@@ -140,15 +144,45 @@ __global__ void __launch_bounds__(1024, 1) k_mc_uf_fast(fast::FView g, fast::FLa
     if (TW <= 32) sync.x = TW == 32 ? 0xffffffffu : ((1u << (TW & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TW - 1));
     else sync.x = tpb == 1 ? 0u : (uint32_t)(1 + tile);
     unsigned int fails = 0;
-    for (long long k = (long long)blockIdx.x * tpb + tile; k < nshots; k += (long long)gridDim.x * tpb) {
-        const uint32_t r = fast::fast_shot<ADJ_SHARED>(g, l, s, sp, shot0 + (unsigned long long)k, lane, TW, sync);
+    if (LOGQ) nshots = (long long)*qin_count;
+    for (long long i = (long long)blockIdx.x * tpb + tile; i < nshots; i += (long long)gridDim.x * tpb) {
+        const long long k = LOGQ ? (long long)qin[i] : i;
+        const uint32_t r = fast::fast_shot<ADJ_SHARED>(g, l, s, sp, shot0 + (unsigned long long)k, lane, TW, sync, nullptr,
+                                                       LOGQ ? &x : nullptr);
         if (lane == 0) {
             if (r == fast::HARD) queue[atomicAdd(qcount, 1u)] = (uint32_t)k;
-            else { fails += r; if (logical) logical[k] = (uint8_t)r; }
+            else if (r == fast::HARD_LOGGED) {
+                const uint32_t pos = atomicAdd(x.qcount, 1u);
+                x.queue[2u * pos] = (uint32_t)k; x.queue[2u * pos + 1u] = s.cnt[fast::C_XBASE];
+            } else { fails += r; if (logical) logical[k] = (uint8_t)r; }
         }
     }
     if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+    if (!LOGQ && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+}
+
+// The exported HARD clusters of a launch: one tile (= block of TW threads) per shot sorts the shot's keys, one
+// lane replays the unions (fast::hard_resolve).  Shared memory: keycap sort words, one word per detector, one result word.
+template <int TW>
+__global__ void __launch_bounds__(TW) k_hard_resolve(fast::FView g, fast::FExport x, uint32_t keycap, unsigned long long* counts,
+                                                    uint8_t* __restrict__ logical)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* key = (uint32_t*)smem;
+    uint32_t* S = key + keycap;
+    uint32_t* out = S + g.D;
+    const int lane = threadIdx.x;
+    TileSync<TW> sync;
+    sync.x = TW == 32 ? 0xffffffffu : 0u;
+    unsigned int fails = 0;
+    const uint32_t n = *x.qcount;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t k = x.queue[2u * i], base = x.queue[2u * i + 1u];
+        const uint32_t bit = fast::hard_resolve(g, x.buf + base, key, S, out, lane, TW, sync);
+        if (lane == 0) { fails += bit; if (logical) logical[k] = (uint8_t)bit; }
+        sync();
+    }
+    if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
 }
 
 // Staged K2: syndromes in, corrections (+ growth, rounds) out (uf.py:106-119).
@@ -540,19 +574,45 @@ __global__ void k_sf_latency_cta(SfView g, SfLayout l, SampleParams sp, int flag
 
 // Staged K1: bit-packed errors and syndromes to HBM
 // (noise/main.py:114-115,309-314; _base_classes.py:427-450).
-__global__ void k_sample(GraphView g, Layout l, SampleParams sp, unsigned long long shot0,
+// A warp takes four consecutive shots at a time: their rows are 4 W(E) and 4 W(D) contiguous words of `err` and
+// `syn` -- multiples of 16 bytes whatever W is -- so the warp's slice of shared memory (err[4][WE] | syn[4][WD]) is
+// cleared and written out with 16-byte accesses (streaming stores: the rows are not read again by this kernel);
+// round 1 cleared and stored word by word, 22 % of the kernel's instructions (ncu r2m).  VEC = false: the
+// buffers are not 16-byte aligned.
+template <bool VEC>
+__global__ void k_sample(GraphView g, SampleParams sp, unsigned long long shot0,
                          long long nshots, uint32_t* __restrict__ err, uint32_t* __restrict__ syn)
 {
+    extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, nl = WARP;
     const int wpb = blockDim.x >> 5;
-    const Shot s = bind(l, warp_slice(l));
-    const long long stride = (long long)gridDim.x * wpb;
-    for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
-        LUF_PHASE(for (int w = lane; w < g.WE; w += nl) s.err[w] = 0;
-                  for (int w = lane; w < g.WD; w += nl) s.defect[w] = 0);
-        LUF_PHASE(ph_sample(g, s, sp, shot0 + (unsigned long long)k, lane, nl));
-        for (int w = lane; w < g.WE; w += nl) err[k * g.WE + w] = s.err[w];
-        for (int w = lane; w < g.WD; w += nl) syn[k * g.WD + w] = s.defect[w];
+    const int WE = g.WE, WD = g.WD, words = 4 * (WE + WD);
+    uint32_t* slice = (uint32_t*)smem + (size_t)(threadIdx.x >> 5) * words;
+    const long long stride = (long long)gridDim.x * wpb, ngroups = (nshots + 3) >> 2;
+    for (long long grp = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); grp < ngroups; grp += stride) {
+        {
+            uint4* z = (uint4*)slice;
+            for (int i = lane; i < WE + WD; i += nl) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncwarp();
+        const int in_group = (int)(nshots - 4 * grp < 4 ? nshots - 4 * grp : 4);
+        for (int j = 0; j < in_group; ++j) {
+            Shot s;
+            s.err = slice + j * WE; s.defect = slice + 4 * WE + j * WD;
+            ph_sample(g, s, sp, shot0 + (unsigned long long)(4 * grp + j), lane, nl);
+        }
+        __syncwarp();
+        uint32_t* eo = err + 4 * grp * WE;
+        uint32_t* so = syn + 4 * grp * WD;
+        if (VEC && in_group == 4) {
+            const uint4* e4 = (const uint4*)slice;
+            const uint4* d4 = (const uint4*)(slice + 4 * WE);
+            for (int i = lane; i < WE; i += nl) __stcs((uint4*)eo + i, e4[i]);
+            for (int i = lane; i < WD; i += nl) __stcs((uint4*)so + i, d4[i]);
+        } else {
+            for (int i = lane; i < in_group * WE; i += nl) eo[i] = slice[i];
+            for (int i = lane; i < in_group * WD; i += nl) so[i] = slice[4 * WE + i];
+        }
         __syncwarp();
     }
 }
@@ -608,7 +668,7 @@ __global__ void k_check(int WE, long long nshots, const uint32_t* __restrict__ w
     for (long long k = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); k < nshots; k += stride) {
         uint32_t acc = 0;
         for (int w = lane; w < WE; w += WARP)
-            acc ^= (__ldg(&err[k * WE + w]) ^ __ldg(&corr[k * WE + w])) & __ldg(&west_mask[w]);
+            acc ^= ((err ? __ldg(&err[k * WE + w]) : 0u) ^ __ldg(&corr[k * WE + w])) & __ldg(&west_mask[w]);      // err == nullptr: the frame of the correction alone
         acc = __reduce_xor_sync(0xffffffffu, acc);
         const unsigned int bit = __popc(acc) & 1u;
         if (lane == 0 && logical) logical[k] = (uint8_t)bit;
@@ -1276,22 +1336,25 @@ static int fast_queue(luf_graph* g, void* stream, uint32_t** out)
     auto it = g->queues.find(stream);
     if (it == g->queues.end()) {
         void* p = nullptr;
-        CUDA_TRY(cudaMalloc(&p, (size_t)(FAST_CHUNK + 4) * 4));
+        // Q1 [FAST_CHUNK] | counters [16] | Q3 [FAST_CHUNK] | Q2 pairs [2 * FAST_CHUNK]  (fast_queue_layout)
+        CUDA_TRY(cudaMalloc(&p, ((size_t)4 * FAST_CHUNK + 16) * 4));
         it = g->queues.emplace(stream, (uint32_t*)p).first;
     }
     *out = it->second;
     return 0;
 }
 
-template <int TW, bool ADJ>
+struct FastLogArgs { fast::FExport x; const uint32_t* qin; const uint32_t* qin_count; };
+
+template <int TW, bool ADJ, bool LOGQ>
 static int fast_launch_t(luf_graph* g, const fast::FView& fv, const FastPlan& plan, const fast::FLayout& fl, const SampleParams& sp,
                          unsigned long long shot0, long long nshots, unsigned long long* counts, uint8_t* logical,
-                         uint32_t* queue, uint32_t* qcount, cudaStream_t stream)
+                         uint32_t* queue, uint32_t* qcount, const FastLogArgs& la, cudaStream_t stream)
 {
-    if (int rc = raise_smem_limit(g->device, g->max_smem, k_mc_uf_fast<TW, ADJ>)) return rc;
+    if (int rc = raise_smem_limit(g->device, g->max_smem, k_mc_uf_fast<TW, ADJ, LOGQ>)) return rc;
     {
         static std::atomic<bool> carved{false};
-        if (!carved.exchange(true)) CUDA_TRY(cudaFuncSetAttribute(k_mc_uf_fast<TW, ADJ>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (!carved.exchange(true)) CUDA_TRY(cudaFuncSetAttribute(k_mc_uf_fast<TW, ADJ, LOGQ>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     const size_t smem = (size_t)plan.adj_bytes + (size_t)plan.spb * fl.bytes;
     long long blocks = (long long)g->sm_count * plan.bps;
@@ -1300,18 +1363,22 @@ static int fast_launch_t(luf_graph* g, const fast::FView& fv, const FastPlan& pl
     if (getenv("LUF_DEBUG_PLAN"))
         fprintf(stderr, "[luf] fast plan: %u B per shot (lists %u / %u / %u), tile %d, %d shots per block, %d blocks per SM, adjacency %s (%u B), %zu B of shared memory per block\n",
                 fl.bytes, fl.tcap, fl.acap, fl.mcap, plan.tw, plan.spb, plan.bps, plan.adj_shared ? "shared" : "global", plan.adj_bytes, smem);
-    k_mc_uf_fast<TW, ADJ><<<(int)blocks, plan.spb * TW, smem, stream>>>(fv, fl, plan.adj_bytes, sp, shot0, nshots, counts,
-                                                                      logical, queue, qcount);
+    k_mc_uf_fast<TW, ADJ, LOGQ><<<(int)blocks, plan.spb * TW, smem, stream>>>(fv, fl, plan.adj_bytes, sp, shot0, nshots, counts,
+                                                                            logical, queue, qcount, la.x, la.qin, la.qin_count);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
+// `la` (optional): the second pass over the queued HARD shots, with the merge log
 static int fast_launch(luf_graph* g, const fast::FView& fv, const FastPlan& plan, const fast::FLayout& fl, const SampleParams& sp,
                        unsigned long long shot0, long long nshots, unsigned long long* counts, uint8_t* logical,
-                       uint32_t* queue, uint32_t* qcount, cudaStream_t stream)
+                       uint32_t* queue, uint32_t* qcount, cudaStream_t stream, const FastLogArgs* la = nullptr)
 {
-#define LUF_FAST_TW(T) case T: return plan.adj_shared ? fast_launch_t<T, true>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream) \
-                                                      : fast_launch_t<T, false>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, stream);
+    static const FastLogArgs none{};
+#define LUF_FAST_TW(T) case T: return la ? (plan.adj_shared ? fast_launch_t<T, true, true>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, *la, stream) \
+                                                            : fast_launch_t<T, false, true>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, *la, stream)) \
+                                         : (plan.adj_shared ? fast_launch_t<T, true, false>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, none, stream) \
+                                                            : fast_launch_t<T, false, false>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, none, stream));
     switch (plan.tw) {
         LUF_FAST_TW(16) LUF_FAST_TW(32) LUF_FAST_TW(64) LUF_FAST_TW(128) LUF_FAST_TW(256)
         default: return fail(LUF_ERR_INVALID, "fast path: tile width must be 16, 32, 64, 128 or 256");
@@ -1944,9 +2011,15 @@ int luf_sample(luf_graph* g, const double* class_p_host, uint64_t seed, uint64_t
         ++g->launches;
         return 0;
     }
-    if (int rc = plan_launch(g, k_sample, g->lay_sample.bytes, nshots, &c)) return rc;
-    k_sample<<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->lay_sample, sp, shot0, nshots,
-                                                                 err_bits_dev, syn_bits_dev);
+    const uint32_t group_bytes = 16u * (uint32_t)(g->view.WE + g->view.WD);            // four shots per warp at a time
+    const long long ngroups = (nshots + 3) / 4;
+    if (!(((uintptr_t)err_bits_dev | (uintptr_t)syn_bits_dev) & 15u)) {
+        if (int rc = plan_launch(g, k_sample<true>, group_bytes, ngroups, &c)) return rc;
+        k_sample<true><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, sp, shot0, nshots, err_bits_dev, syn_bits_dev);
+    } else {
+        if (int rc = plan_launch(g, k_sample<false>, group_bytes, ngroups, &c)) return rc;
+        k_sample<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, sp, shot0, nshots, err_bits_dev, syn_bits_dev);
+    }
     CUDA_TRY(cudaGetLastError());
     ++g->launches;
     return 0;
@@ -2178,27 +2251,78 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
             if (fast_plan(g, fl, &plan)) {
                 uint32_t* queue = nullptr;
                 if (int rc = fast_queue(g, stream, &queue)) return rc;
-                uint32_t* qcount = queue + FAST_CHUNK;
+                // Q1: the HARD shots of the first pass; Q3: those the second pass could not log (canonical launch);
+                // Q2: (shot, offset) of the exported ones; counters: |Q1|, |Q3|, |Q2|, export cursor
+                uint32_t* cnt = queue + FAST_CHUNK;
+                uint32_t* q3 = cnt + 16;
+                uint32_t* q2 = q3 + FAST_CHUNK;
+                uint32_t* qcount = cnt;
+                // Second pass over the HARD shots with the merge log, then k_hard_resolve -- instead of the canonical
+                // launch, whose reservation merge needs about one iteration per edge of a lattice-spanning cluster (5 ms
+                // for ONE shot of d = 17 at p = 0.026).  Measured at p = 0.026 (M shots/s, with / without): d = 17 4.5 / 3.0,
+                // d = 25 0.88 / 0.61, d = 11 36.1 / 36.9 -- the replay of a shot's unions is one lane's dependent chain
+                // (about 0.8 us per key), which pays from about d = 13 on.  LUF_FAST_LOG=0 / 1 forces it off / on.
+                const int env_log_v = getenv("LUF_FAST_LOG") ? atoi(getenv("LUF_FAST_LOG")) : -1;
+                const bool env_log = env_log_v < 0 ? g->fview.D >= 1500 : env_log_v != 0;
+                const fast::FLayout fl2 = make_fast_layout(g->fview.D, g->fview.E, g->fview.DEG, mu, true);
+                FastPlan plan2;
+                uint32_t keycap = 32;
+                while (keycap < fast::RESOLVE_MAX_KEYS && keycap < fl2.lcap) keycap <<= 1;
+                const size_t resolve_smem = 4 * ((size_t)keycap + (size_t)g->fview.D + 4 + 2 * fast::RESOLVE_SEGS);
+                const bool log_pass = env_log && !(flags & LUF_UF_WEST) && fast_plan(g, fl2, &plan2) && resolve_smem <= (size_t)g->max_smem;
                 for (int64_t done = 0; done < nshots; done += FAST_CHUNK) {
                     const long long m = std::min<long long>(FAST_CHUNK, nshots - done);
                     const unsigned long long first = shot0 + (unsigned long long)done;
                     uint8_t* lg = logical_dev ? logical_dev + done : nullptr;
                     fast::FView fv = g->fview;
                     fv.west = (flags & LUF_UF_WEST) ? 1 : 0;
-                    if (!fv.west) CUDA_TRY(cudaMemsetAsync(qcount, 0, 4, (cudaStream_t)stream));
+                    if (!fv.west) CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, (cudaStream_t)stream));
                     if (int rc = fast_launch(g, fv, plan, fl, sp, first, m, counts_dev, lg, queue, qcount, (cudaStream_t)stream)) return rc;
                     ++g->launches;
+                    uint32_t *cq = queue, *cqc = qcount;         // what the canonical launch takes
+                    if (log_pass) {
+                        // export buffer: 64 words per shot of the chunk, between 2^22 and 2^27 (a shot that finds no room goes to Q3)
+                        const size_t xcap = (size_t)std::min<long long>(1ll << 27, std::max<long long>(1ll << 22, (long long)m * 64));
+                        void* xbuf = nullptr;
+                        if (int rc = wide_slab(g, stream, 4, xcap * 4, &xbuf)) return rc;
+                        FastLogArgs la;
+                        la.x.buf = (uint32_t*)xbuf; la.x.cursor = cnt + 3; la.x.cap = (uint32_t)xcap; la.x.max_keys = keycap;
+                        la.x.queue = q2; la.x.qcount = cnt + 2;
+                        la.qin = queue; la.qin_count = cnt;
+                        if (int rc = fast_launch(g, fv, plan2, fl2, sp, first, m, counts_dev, lg, q3, cnt + 1, (cudaStream_t)stream, &la)) return rc;
+                        ++g->launches;
+                        // (the replay of a shot is one lane's dependent chain: as many resident tiles as shared memory allows)
+                        const bool narrow_tile = keycap <= 4096;
+                        const long long rblocks = (long long)g->sm_count * std::max<size_t>(1, std::min<size_t>(narrow_tile ? 32 : 8, (size_t)(228 * 1024) / (resolve_smem + 1024)));
+                        if (narrow_tile) {
+                            if (int rc = raise_smem_limit(g->device, g->max_smem, k_hard_resolve<32>)) return rc;
+                            k_hard_resolve<32><<<(int)rblocks, 32, resolve_smem, (cudaStream_t)stream>>>(fv, la.x, keycap, counts_dev, lg);
+                        } else {
+                            if (int rc = raise_smem_limit(g->device, g->max_smem, k_hard_resolve<256>)) return rc;
+                            k_hard_resolve<256><<<(int)rblocks, 256, resolve_smem, (cudaStream_t)stream>>>(fv, la.x, keycap, counts_dev, lg);
+                        }
+                        CUDA_TRY(cudaGetLastError());
+                        ++g->launches;
+                        cq = q3; cqc = cnt + 1;                  // only what the second pass could not log
+                    }
                     if (!fv.west && g->wide) {  // the HARD shots of a graph beyond the 16-bit layout: the wide instance
                         WidePlan w;
                         if (int rc = wide_plan(g, k_mc_uf_wide<true>, g->wlay_fused, 4096, stream, &w)) return rc;
                         k_mc_uf_wide<true><<<w.grid, w.threads, w.smem, (cudaStream_t)stream>>>(g->wview, g->wlay_fused, sp, flags, first, m,
-                                                                                             counts_dev, lg, queue, qcount, w.slab);
+                                                                                             counts_dev, lg, cq, cqc, w.slab);
                         CUDA_TRY(cudaGetLastError());
                         ++g->launches;
                     } else if (!fv.west) {      // (the west inclination leaves no HARD shots: luf_uf_fast.cuh)
-                        LUF_MC_UF_ANY(0, true, first, m, lg, queue, qcount)
+                        LUF_MC_UF_ANY(0, true, first, m, lg, cq, cqc)
                         CUDA_TRY(cudaGetLastError());
                         ++g->launches;
+                    }
+                    if (!fv.west && getenv("LUF_DEBUG_PLAN")) {
+                        uint32_t h[4];
+                        CUDA_TRY(cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+                        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+                        fprintf(stderr, "[luf] HARD shots of %lld: %u queued by the first pass, %u exported for hard_resolve (%u words), %u left to the canonical launch\n",
+                                m, h[0], h[2], h[3], log_pass ? h[1] : h[0]);
                     }
                 }
                 return 0;
@@ -2502,6 +2626,65 @@ int luf_decode_batch_host(luf_graph* g, int decoder, int flags, int64_t nshots, 
         if ((rc = luf_decode_batch(g, decoder, flags, (int64_t)m, d_syn, d_corr, d_gr, d_st, st))) return rc;
         CUDA_TRY(cudaMemcpyAsync(corr_bits_host + lo * WE, d_corr, m * WE * 4, cudaMemcpyDeviceToHost, st));
         if (d_gr) CUDA_TRY(cudaMemcpyAsync(growth2b_host + lo * GW, d_gr, m * GW * 4, cudaMemcpyDeviceToHost, st));
+        if (d_st) CUDA_TRY(cudaMemcpyAsync(steps_host + lo * 2, d_st, m * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (cudaStream_t st : g->pipe) CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// Decode into device scratch and keep one byte per shot: the parity of the correction on the logical mask.
+int luf_decode_frames(luf_graph* g, int decoder, int flags, int64_t nshots, const uint32_t* syn_bits_dev,
+                      uint8_t* frame_dev, int32_t* steps_dev, void* stream)
+{
+    if (!g || !syn_bits_dev || !frame_dev || nshots < 0) return fail(LUF_ERR_INVALID, "luf_decode_frames: bad argument");
+    if (nshots == 0) return 0;
+    CUDA_TRY(cudaSetDevice(g->device));
+    void *corr = nullptr, *cnt = nullptr;
+    const size_t chunk = (size_t)1 << 18, WE = g->view.WE, WD = g->view.WD;
+    if (int rc = wide_slab(g, stream, 2, std::min<size_t>(chunk, (size_t)nshots) * WE * 4 + 16, &corr)) return rc;
+    if (int rc = wide_slab(g, stream, 3, 16, &cnt)) return rc;
+    const int block = 256, wpb = block / WARP;
+    for (size_t lo = 0; lo < (size_t)nshots; lo += chunk) {
+        const size_t m = std::min<size_t>(chunk, (size_t)nshots - lo);
+        if (int rc = luf_decode_batch(g, decoder, flags, (int64_t)m, syn_bits_dev + lo * WD, (uint32_t*)corr, nullptr,
+                                      steps_dev ? steps_dev + 2 * lo : nullptr, stream)) return rc;
+        long long blocks = std::min<long long>((long long)g->sm_count * 8, ((long long)m + wpb - 1) / wpb);
+        k_check<<<(int)blocks, block, 0, (cudaStream_t)stream>>>((int)WE, (long long)m, g->view.west_mask, nullptr, (const uint32_t*)corr,
+                                                                  frame_dev + lo, (unsigned long long*)cnt);
+        CUDA_TRY(cudaGetLastError());
+        ++g->launches;
+    }
+    return 0;
+}
+
+int luf_decode_frames_host(luf_graph* g, int decoder, int flags, int64_t nshots, const uint32_t* syn_bits_host,
+                           uint8_t* frame_host, int32_t* steps_host)
+{
+    if (!g || !syn_bits_host || !frame_host || nshots < 0) return fail(LUF_ERR_INVALID, "luf_decode_frames_host: bad argument");
+    if (nshots == 0) return 0;
+    std::lock_guard<std::mutex> lock(g->mu);
+    CUDA_TRY(cudaSetDevice(g->device));
+    DrainDefaultStream drain_on_exit;
+    const size_t n = (size_t)nshots, WD = g->view.WD;
+    void *syn, *fr, *st_dev = nullptr;
+    int rc;
+    if ((rc = scratch_get(g, 1, n * WD * 4, &syn)) || (rc = scratch_get(g, 3, n, &fr))) return rc;
+    if (steps_host && (rc = scratch_get(g, 4, n * 8, &st_dev))) return rc;
+    const size_t chunk = (size_t)1 << 18;           // as luf_decode_batch_host: copies of one chunk overlap the decode of another
+    for (cudaStream_t& st : g->pipe) if (!st) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct Drain {
+        luf_graph* g;
+        ~Drain() { for (cudaStream_t st : g->pipe) if (st) cudaStreamSynchronize(st); }
+    } drain{g};
+    int k = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, ++k) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        cudaStream_t st = g->pipe[k % 3];
+        uint32_t* d_syn = (uint32_t*)syn + lo * WD;
+        int32_t* d_st = st_dev ? (int32_t*)st_dev + lo * 2 : nullptr;
+        CUDA_TRY(cudaMemcpyAsync(d_syn, syn_bits_host + lo * WD, m * WD * 4, cudaMemcpyHostToDevice, st));
+        if ((rc = luf_decode_frames(g, decoder, flags, (int64_t)m, d_syn, (uint8_t*)fr + lo, d_st, st))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(frame_host + lo, (uint8_t*)fr + lo, m, cudaMemcpyDeviceToHost, st));
         if (d_st) CUDA_TRY(cudaMemcpyAsync(steps_host + lo * 2, d_st, m * 8, cudaMemcpyDeviceToHost, st));
     }
     for (cudaStream_t st : g->pipe) CUDA_TRY(cudaStreamSynchronize(st));

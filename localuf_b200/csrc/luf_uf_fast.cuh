@@ -51,8 +51,22 @@ static const int MAX_DETECTORS = 0x7FFE;                              // a non-r
 // counter beyond its capacity says the list overflowed), the number of active clusters, the parity
 // accumulator, and the HARD flag (an odd cluster on both sides; written by the last phase only, read after the
 // barrier that ends it).
-enum { C_TOUCHED = 0, C_ALIST = 1, C_MLIST = 2, C_ACTIVE = 3, C_PARITY = 5, C_HARD_M = 6 };
+enum { C_TOUCHED = 0, C_ALIST = 1, C_MLIST = 2, C_ACTIVE = 3, C_XBASE = 4, C_PARITY = 5, C_HARD_M = 6, C_XCOUNT = 7 };
 static const uint32_t HARD = 2u;                         // result of a shot the canonical kernel has to decode
+static const uint32_t HARD_LOGGED = 3u;                  // ... or whose odd clusters on both sides were exported for hard_resolve
+static const uint32_t KEY_EDGE_BITS = 20u, KEY_EDGE_MASK = 0xFFFFFu;      // merge-log key = growth round << 20 | edge id
+static const uint32_t RESOLVE_MAX_KEYS = 16384u;         // most log entries of one shot's HARD clusters that hard_resolve sorts (a power of two)
+
+// Where the HARD clusters of a launch go (global memory): per shot `count | fast bit << 31` followed by `count` keys,
+// reserved with one atomic add on *cursor; (shot, offset) pairs in `queue`, *qcount of them.
+struct FExport {
+    uint32_t* buf;
+    uint32_t* cursor;
+    uint32_t cap;               // words of buf
+    uint32_t max_keys;          // most keys per shot (hard_resolve's sort buffer)
+    uint32_t* queue;            // [2 * shots of the launch]
+    uint32_t* qcount;
+};
 
 // Read-only tables (global memory; fadj optionally staged in shared memory by the kernel).
 struct FView {
@@ -74,6 +88,7 @@ struct FLayout {
     uint32_t fill_words, zero_off, zero_bytes;  // P is filled with P_FRESH pairs; growth .. touched are cleared
     uint32_t tlist, alist, mlist, cnt;          // uint16[tcap], uint32[acap], uint32[mcap], uint32[8]
     uint32_t tcap, acap, mcap;
+    uint32_t elog, lcap;                        // uint32[lcap]: the merge log (every newly FULL edge of the shot, keyed by round); lcap = 0: none
     uint32_t bytes;                             // slice size, multiple of 16
 };
 
@@ -81,7 +96,7 @@ struct FShot {
     uint16_t* P;
     uint32_t *growth, *defect, *touched;
     uint16_t* tlist;
-    uint32_t *alist, *mlist, *cnt;
+    uint32_t *alist, *mlist, *cnt, *elog;
 };
 
 LUF_DEV FShot fbind(const FLayout& l, unsigned char* base)
@@ -92,6 +107,7 @@ LUF_DEV FShot fbind(const FLayout& l, unsigned char* base)
     s.touched = (uint32_t*)(base + l.touched);
     s.tlist = (uint16_t*)(base + l.tlist);
     s.alist = (uint32_t*)(base + l.alist); s.mlist = (uint32_t*)(base + l.mlist); s.cnt = (uint32_t*)(base + l.cnt);
+    s.elog = (uint32_t*)(base + l.elog);
     return s;
 }
 
@@ -255,9 +271,12 @@ LUF_DEV void f_row(const FView& g, uint32_t v, F f)
 }
 
 // `other16`: the other end as a detector index, END_WEST or END_EAST
-LUF_DEV void f_newfull(const FLayout& l, const FShot& s, uint32_t u, uint32_t other16, uint32_t mbase)
+// `key`: growth round << 20 | edge id, for the merge log (the order of the canonical merges: uf.py:223-229 takes a
+// round's newly FULL edges in ascending edge id)
+LUF_DEV void f_newfull(const FLayout& l, const FShot& s, uint32_t u, uint32_t other16, uint32_t mbase, uint32_t key)
 {
-    const uint32_t idx = luf_atomic_add(&s.cnt[C_MLIST], 1u) - mbase;
+    const uint32_t tot = luf_atomic_add(&s.cnt[C_MLIST], 1u), idx = tot - mbase;
+    if (tot < l.lcap) s.elog[tot] = key;
     if (idx < l.mcap) s.mlist[idx] = u | (other16 << 16);
     // else: the counter alone says the list overflowed; the merge phase then reads the growth words
 }
@@ -292,7 +311,7 @@ LUF_DEV void f_grow_first_entry(const FView& g, const FLayout& l, const FShot& s
 {
     const uint32_t e = ent & g.emask, sh = (e & 15u) * 2u;
     const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
-    if (old == G_HALF) f_newfull(l, s, v, (ent >> g.ebits) & g.omask, 0u);       // (the other end grew too: a detector)
+    if (old == G_HALF) f_newfull(l, s, v, (ent >> g.ebits) & g.omask, 0u, (1u << KEY_EDGE_BITS) | e);       // (the other end grew too: a detector)
 }
 
 // Round 1 (uf.py:234-245): every defect adds 1 to each of its edges, no look-ups; an edge is newly FULL iff the
@@ -327,7 +346,7 @@ LUF_DEV void f_touch(const FLayout& l, const FShot& s, uint32_t v)
 
 // Later rounds: a touched node whose cluster (root r) is active adds 1 to each of its edges that is not FULL;
 // an edge inside one cluster is counted once (only its first endpoint adds); the 2-bit counters saturate.
-LUF_DEV void f_grow_entry(const FView& g, const FLayout& l, const FShot& s, uint32_t u, uint32_t r, uint32_t ent, uint32_t mbase)
+LUF_DEV void f_grow_entry(const FView& g, const FLayout& l, const FShot& s, uint32_t u, uint32_t r, uint32_t ent, uint32_t mbase, uint32_t rkey)
 {
     const uint32_t e = ent & g.emask, sh = (e & 15u) * 2u;
     if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) return;
@@ -340,20 +359,20 @@ LUF_DEV void f_grow_entry(const FView& g, const FLayout& l, const FShot& s, uint
     const uint32_t old = (luf_atomic_add(&s.growth[e >> 4], 1u << sh) >> sh) & 3u;
     if (old >= G_FULL) luf_atomic_sub(&s.growth[e >> 4], 1u << sh);
     else if (old == G_HALF) {
-        f_newfull(l, s, u, detector ? o : (o == g.omask ? END_WEST : END_EAST), mbase);
+        f_newfull(l, s, u, detector ? o : (o == g.omask ? END_WEST : END_EAST), mbase, rkey | e);
         if (detector) f_touch(l, s, o);
     }
 }
 
 template <bool ADJ_SHARED>
-LUF_DEV void f_grow_node(const FView& g, const FLayout& l, const FShot& s, uint32_t u, uint32_t r, uint32_t mbase)
+LUF_DEV void f_grow_node(const FView& g, const FLayout& l, const FShot& s, uint32_t u, uint32_t r, uint32_t mbase, uint32_t rkey)
 {
-    f_row<ADJ_SHARED>(g, u, [&](uint32_t ent) { f_grow_entry(g, l, s, u, r, ent, mbase); });
+    f_row<ADJ_SHARED>(g, u, [&](uint32_t ent) { f_grow_entry(g, l, s, u, r, ent, mbase, rkey); });
 }
 
 template <bool ADJ_SHARED>
 LUF_DEV void f_grow_filter(const FView& g, const FLayout& l, const FShot& s, uint32_t nt, uint32_t abase, uint32_t mbase,
-                           int lane, int nl)
+                           uint32_t rkey, int lane, int nl)
 {
     f_for_nodes(g, l, s, s.touched, nt, nt, lane, nl, [&](uint32_t u) {
         uint32_t wr;
@@ -361,13 +380,13 @@ LUF_DEV void f_grow_filter(const FView& g, const FLayout& l, const FShot& s, uin
         if (wr != P_ACTIVE) return;
         const uint32_t idx = luf_atomic_add(&s.cnt[C_ALIST], 1u) - abase;
         if (idx < l.acap) s.alist[idx] = u | (r << 16);
-        else f_grow_node<ADJ_SHARED>(g, l, s, u, r, mbase);       // the list is full: grow right away (roots are stable here)
+        else f_grow_node<ADJ_SHARED>(g, l, s, u, r, mbase, rkey);       // the list is full: grow right away (roots are stable here)
     });
 }
 
 // one lane per (active node, adjacency slot)
 template <bool ADJ_SHARED>
-LUF_DEV void f_grow_exec(const FView& g, const FLayout& l, const FShot& s, uint32_t na, uint32_t mbase, int lane, int nl)
+LUF_DEV void f_grow_exec(const FView& g, const FLayout& l, const FShot& s, uint32_t na, uint32_t mbase, uint32_t rkey, int lane, int nl)
 {
     if (na > l.acap) na = l.acap;
     const uint32_t items = na * (uint32_t)g.DEG;
@@ -375,7 +394,7 @@ LUF_DEV void f_grow_exec(const FView& g, const FLayout& l, const FShot& s, uint3
     for (uint32_t w = (uint32_t)lane; w < items; w += (uint32_t)nl) {
         const uint32_t i = luf_mulhi(w, g.deg_magic), it = s.alist[i];
         const uint32_t ent = f_entry<ADJ_SHARED>(g, it & 0xFFFFu, w - i * (uint32_t)g.DEG);
-        if (ent != ADJ_PAD) f_grow_entry(g, l, s, it & 0xFFFFu, it >> 16, ent, mbase);
+        if (ent != ADJ_PAD) f_grow_entry(g, l, s, it & 0xFFFFu, it >> 16, ent, mbase, rkey);
     }
 }
 
@@ -480,6 +499,187 @@ LUF_DEV uint32_t f_defect_sides(const FView& g, const FLayout& l, const FShot& s
     return parity;
 }
 
+// ---------------------------------------------------------------- HARD clusters without the canonical kernel
+// Which boundary node an ODD cluster on both sides keeps under the default inclination (uf.py:536-538: the larger
+// cluster of a union keeps its own) depends on the sizes of the clusters at every union, i.e. on the canonical
+// order of the merges INSIDE that cluster -- and on nothing else: growth, the partition after every round and
+// every other cluster's contribution to the logical bit are order-free.  So a shot with such clusters is not
+// decoded again: the merge log of the shot (every newly FULL edge, keyed by round and edge id) is filtered to the
+// edges inside those clusters and exported; hard_resolve sorts the keys, replays those unions alone in canonical
+// order (union by size, ties keep the cluster of the edge's first endpoint; every boundary edge brings a
+// boundary node of its own: size 1, its side) and reports how many of the clusters keep an EAST node -- for each
+// of them the fast bit, which counted the cluster as west, is flipped.
+LUF_DEV bool f_in_hard_cluster(const FView& g, const FShot& s, uint32_t key)
+{
+    const uint32_t ei = LUF_LDG(&g.einfo[key & KEY_EDGE_MASK]);
+    const uint32_t a = ei & 0xFFFFu, b = ei >> 16;
+    uint32_t wr;
+    ffind_ro(s, a < END_EAST ? a : b, wr);
+    return (wr & (P_ODD | P_WEST | P_EAST)) == (P_ODD | P_WEST | P_EAST);
+}
+
+LUF_DEV void f_export_count(const FView& g, const FShot& s, uint32_t ntot, int lane, int nl)
+{
+    uint32_t c = 0;
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < ntot; i += (uint32_t)nl) c += f_in_hard_cluster(g, s, s.elog[i]) ? 1u : 0u;
+    if (c) luf_atomic_add(&s.cnt[C_XCOUNT], c);
+}
+
+// one lane: room for `count | bit << 31` and the keys; C_XBASE = where, or 0xFFFFFFFF (no room, too many keys)
+LUF_DEV void f_export_reserve(const FShot& s, const FExport& x, uint32_t fast_bit)
+{
+    const uint32_t n = s.cnt[C_XCOUNT];
+    uint32_t base = 0xFFFFFFFFu;
+    if (n <= x.max_keys) {
+        base = luf_atomic_add(x.cursor, n + 1u);
+        if (base + n + 1u > x.cap || base + n + 1u < base) base = 0xFFFFFFFFu;
+        else x.buf[base] = n | (fast_bit << 31);
+    }
+    s.cnt[C_XBASE] = base;
+    s.cnt[C_XCOUNT] = 0u;
+}
+
+LUF_DEV void f_export_write(const FView& g, const FShot& s, const FExport& x, uint32_t ntot, int lane, int nl)
+{
+    const uint32_t base = s.cnt[C_XBASE];
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < ntot; i += (uint32_t)nl) {
+        const uint32_t key = s.elog[i];
+        if (f_in_hard_cluster(g, s, key)) x.buf[base + 1u + luf_atomic_add(&s.cnt[C_XCOUNT], 1u)] = key;
+    }
+}
+
+// hard_resolve's node words (scratch, one per detector): root = R_ROOT | kept side << 28 | counted << 27 | size,
+// non-root = parent
+static const uint32_t R_ROOT = 0x80000000u, R_SIDE_SHIFT = 28u, R_SIDE_MASK = 3u << 28, R_COUNTED = 1u << 27, R_SIZE_MASK = (1u << 27) - 1u;
+static const uint32_t R_WEST = 1u, R_EAST = 2u;
+
+// One dependent load per hop (union by size keeps the trees shallow); a start node two or more hops from its
+// root is pointed at it.  `wr` = the root's word.
+LUF_DEV uint32_t r_find(uint32_t* S, uint32_t v, uint32_t& wr)
+{
+    uint32_t w = S[v];
+    if (w & R_ROOT) { wr = w; return v; }
+    const uint32_t start = v;
+    int hops = 0;
+    LUF_NOUNROLL
+    do { v = w; w = S[v]; ++hops; } while (!(w & R_ROOT));
+    if (hops > 1) S[start] = v;
+    wr = w;
+    return v;
+}
+
+LUF_DEV void r_sort_step(uint32_t* key, uint32_t np, uint32_t k, uint32_t j, int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < np; i += (uint32_t)nl) {
+        const uint32_t o = i ^ j;
+        if (o <= i) continue;
+        const uint32_t a = key[i], b = key[o];
+        if ((a > b) == ((i & k) == 0u)) { key[i] = b; key[o] = a; }
+    }
+}
+
+// The sorted keys give way to the endpoint pairs of their edges (the lane that replays the unions then reads
+// shared memory only); every detector they name starts as a singleton without a boundary.
+LUF_DEV void r_init(const FView& g, uint32_t* key, uint32_t n, uint32_t* S, int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
+        const uint32_t ei = LUF_LDG(&g.einfo[key[i] & KEY_EDGE_MASK]);
+        const uint32_t a = ei & 0xFFFFu, b = ei >> 16;
+        key[i] = ei;
+        if (a < END_EAST) S[a] = R_ROOT | 1u;
+        if (b < END_EAST) S[b] = R_ROOT | 1u;
+    }
+}
+
+// Where the keys of every growth round start in the sorted list: seg[r] = first index of round r (rounds from
+// RESOLVE_SEGS - 1 on share the last entry), 0xFFFFFFFF = none; seg[RESOLVE_SEGS + r] = the end (r_seg_ends).
+static const uint32_t RESOLVE_SEGS = 64u;
+
+LUF_DEV uint32_t r_round_of(uint32_t key) { const uint32_t r = key >> KEY_EDGE_BITS; return r < RESOLVE_SEGS ? r : RESOLVE_SEGS - 1u; }
+
+LUF_DEV void r_seg_starts(const uint32_t* key, uint32_t n, uint32_t* seg, int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
+        const uint32_t r = r_round_of(key[i]);
+        if (i == 0u || r_round_of(key[i - 1u]) != r) seg[r] = i;
+    }
+}
+
+LUF_DEV void r_seg_ends(uint32_t n, uint32_t* seg)       // one lane
+{
+    uint32_t e = n;
+    LUF_NOUNROLL
+    for (int r = (int)RESOLVE_SEGS - 1; r >= 0; --r)
+        if (seg[r] != 0xFFFFFFFFu) { seg[RESOLVE_SEGS + r] = e; e = seg[r]; }
+}
+
+// All lanes, between two rounds (no union in flight): every detector of the edges so far points at its root, so
+// that the finds of the next round's unions are one or two hops.
+LUF_DEV void r_flatten(const uint32_t* ends, uint32_t n, uint32_t* S, int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
+        const uint32_t ei = ends[i];
+        LUF_NOUNROLL
+        for (int x = 0; x < 2; ++x) {
+            const uint32_t v0 = x ? ei >> 16 : ei & 0xFFFFu;
+            if (v0 >= END_EAST) continue;
+            uint32_t w = S[v0];
+            if (w & R_ROOT) continue;
+            uint32_t v = w;
+            LUF_NOUNROLL
+            while (!((w = S[v]) & R_ROOT)) v = w;
+            S[v0] = v;
+        }
+    }
+}
+
+// One lane: the unions of the sorted edges [lo, hi) (endpoint pairs, r_init) in order.
+LUF_DEV void r_replay(const uint32_t* ends, uint32_t lo, uint32_t n, uint32_t* S)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = lo; i < n; ++i) {
+        const uint32_t ei = ends[i];
+        const uint32_t a = ei & 0xFFFFu, b = ei >> 16;
+        if (a >= END_EAST || b >= END_EAST) {            // a boundary node of its own (one edge each): size 1, boundary = itself
+            const uint32_t side = (a >= END_EAST ? a : b) == END_WEST ? R_WEST : R_EAST;
+            uint32_t w;
+            const uint32_t r = r_find(S, a >= END_EAST ? b : a, w);
+            w += 1u;
+            if (!(w & R_SIDE_MASK)) w |= side << R_SIDE_SHIFT;     // uf.py:536-538 (a detector cluster that is no larger has no boundary yet)
+            S[r] = w;
+            continue;
+        }
+        uint32_t wa, wb;
+        const uint32_t ra = r_find(S, a, wa), rb = r_find(S, b, wb);
+        if (ra == rb) continue;
+        const bool a_large = (wa & R_SIZE_MASK) >= (wb & R_SIZE_MASK);             // uf.py:270-273: ties keep the first endpoint's cluster
+        const uint32_t L = a_large ? ra : rb, Sm = a_large ? rb : ra, wl = a_large ? wa : wb, ws = a_large ? wb : wa;
+        const uint32_t side = (wl & R_SIDE_MASK) ? (wl & R_SIDE_MASK) : (ws & R_SIDE_MASK);
+        S[L] = R_ROOT | side | ((wl & R_SIZE_MASK) + (ws & R_SIZE_MASK));
+        S[Sm] = L;
+    }
+}
+
+// All lanes: every cluster once (the roots are stable now); *out ^= 1 per cluster that keeps an east node.
+LUF_DEV void r_count_east(const uint32_t* ends, uint32_t n, uint32_t* S, uint32_t* out, int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
+        const uint32_t ei = ends[i];
+        uint32_t v = (ei & 0xFFFFu) < END_EAST ? (ei & 0xFFFFu) : (ei >> 16), w;
+        LUF_NOUNROLL
+        while (!((w = S[v]) & R_ROOT)) v = w;
+        if (luf_atomic_or(&S[v], R_COUNTED) & R_COUNTED) continue;
+        if (((w & R_SIDE_MASK) >> R_SIDE_SHIFT) == R_EAST) luf_atomic_xor(out, 1u);
+    }
+}
+
 }  // namespace fast
 }  // namespace luf
 
@@ -502,7 +702,7 @@ namespace fast {
 // [1] touched nodes, [2] most newly FULL edges of a round, [3] most active nodes of a round.
 template <bool ADJ_SHARED, class Sync>
 LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, const SampleParams& sp, uint64_t shot,
-                           int lane, int nl, Sync sync, uint32_t* stats = nullptr)
+                           int lane, int nl, Sync sync, uint32_t* stats = nullptr, const FExport* x = nullptr)
 {
     (void)lane; (void)sync;
     FT_PHASE((void)0);                                  // every lane is done with the previous shot's counters
@@ -532,17 +732,58 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
             mbase += nm;
             if (!s.cnt[C_ACTIVE]) break;
             const uint32_t nt = s.cnt[C_TOUCHED];
-            FT_PHASE(f_grow_filter<ADJ_SHARED>(g, l, s, nt, abase, mbase, lane, nl));
+            const uint32_t rkey = (rounds + 1u) << KEY_EDGE_BITS;
+            FT_PHASE(f_grow_filter<ADJ_SHARED>(g, l, s, nt, abase, mbase, rkey, lane, nl));
             const uint32_t na = s.cnt[C_ALIST] - abase;
             if (na > most_a) most_a = na;
-            FT_PHASE(f_grow_exec<ADJ_SHARED>(g, l, s, na, mbase, lane, nl));
+            FT_PHASE(f_grow_exec<ADJ_SHARED>(g, l, s, na, mbase, rkey, lane, nl));
             abase += na;
         }
         FT_PHASE(const uint32_t par = f_defect_sides(g, l, s, nd, lane, nl); if (par) luf_atomic_xor(&s.cnt[C_PARITY], 1u));
-        if (s.cnt[C_HARD_M]) return HARD;                // (uniform: every lane reads the same word after the barrier)
+        if (s.cnt[C_HARD_M]) {                           // (uniform: every lane reads the same word after the barrier)
+            const uint32_t ntot = s.cnt[C_MLIST];
+            if (!x || !x->buf || !l.lcap || ntot > l.lcap) return HARD;           // no log, or it could not hold the shot's merges
+            FT_PHASE(f_export_count(g, s, ntot, lane, nl));
+            FT_PHASE(if (lane == 0) f_export_reserve(s, *x, s.cnt[C_PARITY] & 1u));
+            if (s.cnt[C_XBASE] == 0xFFFFFFFFu) return HARD;
+            FT_PHASE(f_export_write(g, s, *x, ntot, lane, nl));
+            return HARD_LOGGED;                          // the caller queues (shot, s.cnt[C_XBASE])
+        }
     }
     if (stats) { stats[0] = rounds; stats[1] = s.cnt[C_TOUCHED]; stats[2] = most_m; stats[3] = most_a; }
     return s.cnt[C_PARITY] & 1u;
+}
+
+// One exported shot: x.buf[base] = count | fast bit << 31, then the keys.  `key` = scratch for the sorted keys (a
+// power of two >= count words), `S` = one word per detector.  Returns the shot's logical bit.
+// `out`: 1 + 2 * RESOLVE_SEGS scratch words (the result, the rounds' segments).
+template <class Sync>
+LUF_DEV uint32_t hard_resolve(const FView& g, const uint32_t* rec, uint32_t* key, uint32_t* S, uint32_t* out, int lane, int nl, Sync sync)
+{
+    (void)lane; (void)sync;
+    const uint32_t n = rec[0] & 0x7FFFFFFFu, bit = rec[0] >> 31;
+    uint32_t np = 1;
+    while (np < n) np <<= 1;
+    FT_PHASE(for (uint32_t i = (uint32_t)lane; i < np; i += (uint32_t)nl) key[i] = i < n ? rec[1u + i] : 0xFFFFFFFFu);
+    LUF_NOUNROLL
+    for (uint32_t k = 2; k <= np; k <<= 1) {             // bitonic sort, ascending (round, edge id)
+        LUF_NOUNROLL
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) { FT_PHASE(r_sort_step(key, np, k, j, lane, nl)); }
+    }
+    uint32_t* seg = out + 1;
+    FT_PHASE(for (uint32_t r = (uint32_t)lane; r < RESOLVE_SEGS; r += (uint32_t)nl) seg[r] = 0xFFFFFFFFu);
+    FT_PHASE(r_seg_starts(key, n, seg, lane, nl));
+    FT_PHASE(r_init(g, key, n, S, lane, nl); if (lane == 0) { *out = bit; r_seg_ends(n, seg); });
+    LUF_NOUNROLL
+    for (uint32_t r = 0; r < RESOLVE_SEGS; ++r) {        // round by round: one lane's unions, then all lanes flatten
+        const uint32_t lo = seg[r];
+        if (lo == 0xFFFFFFFFu) continue;
+        const uint32_t hi = seg[RESOLVE_SEGS + r];
+        FT_PHASE(if (lane == 0) r_replay(key, lo, hi, S));
+        FT_PHASE(r_flatten(key, hi, S, lane, nl));
+    }
+    FT_PHASE(r_count_east(key, n, S, out, lane, nl));
+    return *out;
 }
 
 }  // namespace fast

@@ -379,6 +379,51 @@ int emu_mc_uf_compact(const luf_graph_desc* d, int west, const double* class_p, 
     return 0;
 }
 
+// The compact fast path with the merge log (default inclination): a shot with odd clusters on both sides exports
+// their merges and hard_resolve replays them in canonical order -- out[k] = the logical bit, or 2 when the log or
+// the export buffer could not hold the shot (the kernel then queues it for the canonical launch).  nkeys
+// (optional) [nshots]: exported keys (0: the shot had no such cluster).  log_scale < 0: the library's log size.
+int emu_mc_uf_compact_log(const luf_graph_desc* d, const double* class_p, unsigned long long seed, unsigned long long shot0,
+                          long long nshots, int nl, double mu, int lcap, uint8_t* out, uint32_t* nkeys, uint32_t* nlog)
+{
+    PackedFast pf;
+    pack_fast(*d, pf);
+    if (!pf.ok) return -2;
+    if (mu < 0.0) {
+        mu = 0.0;
+        for (int c = 0, lo = 0; c < pf.n_classes; ++c) { mu += class_p[c] * ((int)pf.class_end[c] - lo); lo = (int)pf.class_end[c]; }
+    }
+    fast::FView g;
+    g.D = pf.D; g.E = pf.E; g.WD = words32(pf.D); g.DEG = pf.DEG; g.deg_magic = (uint32_t)(0x100000000ull / (uint64_t)pf.DEG) + 1u; g.fadj = pf.fadj.data(); g.einfo = pf.einfo.data();
+    g.ebits = pf.ebits; g.emask = pf.emask; g.omask = pf.omask;
+    g.F = pf.F; g.n_classes = pf.n_classes;
+    g.fresh_perm = nullptr; g.fresh_perm32 = pf.perm_identity ? nullptr : pf.fresh_perm32.data(); g.class_end = pf.class_end.data();
+    g.west = 0;
+    fast::FLayout l = make_fast_layout(pf.D, pf.E, pf.DEG, mu, true);
+    if (lcap >= 0) {                 // a log of the caller's size behind the state
+        l.lcap = (uint32_t)lcap; l.elog = l.bytes; l.bytes += 4u * (uint32_t)lcap + 16u;
+    }
+    const SampleParams sp = make_sample_params(class_p, pf.n_classes, seed);
+    std::vector<unsigned char> mem(l.bytes + 16);
+    const fast::FShot s = fast::fbind(l, mem.data());
+    std::vector<uint32_t> xbuf(fast::RESOLVE_MAX_KEYS + 8), key(fast::RESOLVE_MAX_KEYS), S(pf.D, 0xDEADBEEFu);
+    uint32_t cursor = 0, q[2], qn = 0, res[1 + 2 * fast::RESOLVE_SEGS];
+    for (long long k = 0; k < nshots; ++k) {
+        cursor = 0;
+        fast::FExport x{xbuf.data(), &cursor, (uint32_t)xbuf.size(), fast::RESOLVE_MAX_KEYS, q, &qn};
+        uint32_t r = fast::fast_shot<false>(g, l, s, sp, shot0 + k, 0, nl, 0, nullptr, &x);
+        if (nkeys) nkeys[k] = 0;
+        if (nlog) nlog[k] = s.cnt[fast::C_MLIST];
+        if (r == fast::HARD_LOGGED) {
+            const uint32_t base = s.cnt[fast::C_XBASE];
+            if (nkeys) nkeys[k] = xbuf[base] & 0x7FFFFFFFu;
+            r = fast::hard_resolve(g, xbuf.data() + base, key.data(), S.data(), res, 0, nl > 32 ? 256 : 32, 0);
+        }
+        out[k] = (uint8_t)r;
+    }
+    return 0;
+}
+
 // Staged sampler on the compact tables (f_sample_record): errors and syndromes of shots [shot0, shot0 + nshots).
 int emu_sample_compact(const luf_graph_desc* d, const double* class_p, unsigned long long seed, unsigned long long shot0,
                        long long nshots, uint32_t* err_out, uint32_t* syn_out)

@@ -134,3 +134,28 @@ def test_compact_path_on_graphs_beyond_the_16_bit_layout(d, p, n):
     out = emu.mc_uf_compact(p, 3, 7, n, nl=128)
     ok = out != 2
     np.testing.assert_array_equal(out[ok], orc.logical_batch(err, corr0)[ok])
+
+
+@pytest.mark.parametrize('spec,p,n', [c for c in CASES if c[1] >= 0.02 or c[0]['noise'] == 'code capacity'] + [
+    (dict(code='Surface', d=7, noise='phenomenological'), 0.04, 3000),
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.03, 2000),
+    (dict(code='Surface', d=9, noise='phenomenological'), 0.035, 1500),
+], ids=lambda x: f"{x['code']}{x['d']}-{x['noise'].split()[0]}" if isinstance(x, dict) else str(x))
+def test_hard_clusters_resolved_from_the_merge_log(spec, p, n):
+    """Shots with odd clusters on both sides: the merges inside those clusters, replayed in canonical order from
+    the merge log (hard_resolve), give the bit of the canonical decode -- on every shot, for every tile width."""
+    code = make_code(spec)
+    emu, want = canonical_bits(code, p, 11, 100, n)
+    hard = emu.mc_uf_compact(p, 11, 100, n, nl=32, mu=1e6) == 2
+    for nl, mu in ((32, 1e6), (8, 1e6), (128, -1.0)):
+        out, nkeys = emu.mc_uf_compact_log(p, 11, 100, n, nl=nl, mu=mu, lcap=100000, want_keys=True)
+        np.testing.assert_array_equal(out, want)
+        np.testing.assert_array_equal(nkeys > 0, hard)
+    assert hard.sum() > 0 or p < 0.1
+    # the library's log size: a shot it cannot hold is HARD (2) as before, never wrong
+    out = emu.mc_uf_compact_log(p, 11, 100, n, nl=32)
+    np.testing.assert_array_equal(out[out != 2], want[out != 2])
+    assert (out == 2).mean() <= 0.02 + 0.2 * hard.mean()
+    # a starved log: every such shot falls back
+    out = emu.mc_uf_compact_log(p, 11, 100, n, nl=32, lcap=1)
+    np.testing.assert_array_equal(out == 2, hard)

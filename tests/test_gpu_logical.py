@@ -143,3 +143,31 @@ def test_large_distance_snowflake_streams_vs_oracle(d, p, nstreams):
     corrections and logical counts of every stream equal the oracle's."""
     from test_gpu_sf import test_sf_streams_vs_oracle_on_random_errors as run
     run(dict(code='Surface', d=d, noise='circuit-level', kwargs=dict(scheme='frugal')), p, 0, nstreams, 3 * d)
+
+
+@pytest.mark.parametrize('spec,p', [
+    (dict(code='Surface', d=11, noise='phenomenological'), 0.02),
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.02),
+    (dict(code='Surface', d=17, noise='phenomenological'), 0.015),
+])
+def test_logical_frames_only(spec, p):
+    """luf_decode_frames_host: one byte per shot = the parity of the correction on the logical mask
+    (_schemes.py:123-129); XOR with the error's parity it is the shot's logical error."""
+    from localuf_b200 import _engine
+    code = make_code(spec)
+    eng = _engine.Engine(code, device=0)
+    orc = binding.Oracle.from_code(code)
+    n = 70000 if spec['d'] == 11 else 3000          # more than one chunk of the pipelined host path
+    err, syn = eng.sample_host(p, 21, 0, n)
+    for dec, flags in ((_engine.DEC_UF, 0), (_engine.DEC_UF, 2), (_engine.DEC_MACAR, 0)):
+        frame, steps = eng.decode_frames_host(dec, flags, syn, want_steps=True)
+        corr, _, steps2 = eng.decode_batch_host(dec, flags, syn)
+        want, _ = eng.check_host(np.zeros_like(corr), corr)
+        np.testing.assert_array_equal(frame, want)
+        np.testing.assert_array_equal(steps, steps2)
+        logical, _ = eng.check_host(err, corr)
+        err_par, _ = eng.check_host(err, np.zeros_like(corr))
+        np.testing.assert_array_equal(frame ^ err_par, logical)
+    ocorr, _, _ = orc.decode_batch(0, 0, syn[:500], want_growth=False)
+    frame = eng.decode_frames_host(_engine.DEC_UF, 0, syn[:500])
+    np.testing.assert_array_equal(frame ^ orc.logical_batch(err[:500], np.zeros_like(ocorr)), orc.logical_batch(err[:500], ocorr))

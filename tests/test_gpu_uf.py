@@ -225,20 +225,21 @@ def test_python_api_drop_in():
         L.decoders.UF(L.Surface(3, 'phenomenological', scheme='frugal'))
 
 
-def test_graph_too_large_is_reported():
-    """Beyond the 16-bit layout the canonical kernels do not apply: the graph is accepted for the compact path
-    (tests/test_gpu_large.py) and every canonical entry point says why it cannot run; a graph that not even the
-    compact tables hold (more than 32766 detectors) is refused at creation."""
+def test_graphs_beyond_the_16bit_layout_run_on_the_wide_instance():
+    """Beyond the 16-bit layout (N <= 32767, E <= 65533) UF takes the wide instance of the kernels (luf_uf_wide.cuh;
+    parity in tests/test_gpu_large.py); Macar / Actis keep their 16-bit cellular-automaton layout and say so."""
     import localuf_b200 as L
     from localuf_b200 import _engine
     big = L.Surface(23, 'circuit-level')          # E > 65533
     eng = _engine.Engine(big, device=0)
-    with pytest.raises(NotImplementedError, match='16-bit layout'):
-        eng.mc_run_host(_engine.DEC_UF, 0, 0.001, 1, 0, 10)           # default inclination: needs the canonical kernels
-    with pytest.raises(NotImplementedError, match='16-bit layout'):
+    fails, shots = eng.mc_run_host(_engine.DEC_UF, 0, 0.001, 1, 0, 10)
+    assert shots == 10 and 0 <= fails <= 10
+    with pytest.raises(NotImplementedError, match='16-bit'):
         eng.mc_run_host(_engine.DEC_MACAR, 0, 0.001, 1, 0, 10)
-    with pytest.raises(NotImplementedError):
-        eng.sample_weight_host(3, 1, 0, 10)
+    err, syn = eng.sample_weight_host(3, 1, 0, 10)
+    assert np.unpackbits(err.view(np.uint8), axis=1).sum(axis=1).tolist() == [3] * 10
     huge = L.Surface(11, 'phenomenological', scheme='global batch', window_height=11 * 30)     # 36300 detectors
-    with pytest.raises(NotImplementedError):
-        _engine.Engine(huge, device=0)
+    eng = _engine.Engine(huge, device=0)
+    err, syn = eng.sample_host(0.005, 1, 0, 4)
+    corr, _, _ = eng.decode_batch_host(_engine.DEC_UF, 0, syn)
+    assert corr.shape == err.shape
