@@ -328,6 +328,7 @@ inline fast::FLayout make_fast_layout(int D, int E, int DEG, double mu, bool log
     // An edge becomes FULL once, so E entries always suffice; a shot beyond the log goes to the canonical launch, whose
     // latency for ONE such shot is milliseconds (5 ms for 11 shots of d = 17 at p = 0.026): be generous.
     l.lcap = log ? cap((16.0 * mu + 40.0 * sq + 128.0) * (DEG > 6 ? 3.0 : 1.0), E) : 0u;
+    if (l.lcap) { uint32_t p2 = 64; while (p2 < l.lcap) p2 <<= 1; l.lcap = p2; }      // sorted in place by a bitonic network
     l.elog = l.lcap ? take(4u * l.lcap) : 0u;
     l.bytes = off;
     return l;

@@ -161,26 +161,23 @@ __global__ void __launch_bounds__(1024, 1) k_mc_uf_fast(fast::FView g, fast::FLa
     if (!LOGQ && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
 }
 
-// The exported HARD clusters of a launch: one tile (= block of TW threads) per shot sorts the shot's keys, one
-// lane replays the unions (fast::hard_resolve).  Shared memory: keycap sort words, one word per detector, one result word.
-template <int TW>
-__global__ void __launch_bounds__(TW) k_hard_resolve(fast::FView g, fast::FExport x, uint32_t keycap, unsigned long long* counts,
-                                                    uint8_t* __restrict__ logical)
+// The exported HARD clusters of a launch: one warp per shot replays the shot's unions (fast::hard_resolve).
+// Shared memory per warp: one word per detector and the result word.
+__global__ void k_hard_resolve(int D, fast::FExport x, unsigned long long* counts, uint8_t* __restrict__ logical)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t* key = (uint32_t*)smem;
-    uint32_t* S = key + keycap;
-    uint32_t* out = S + g.D;
-    const int lane = threadIdx.x;
-    TileSync<TW> sync;
-    sync.x = TW == 32 ? 0xffffffffu : 0u;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    uint32_t* S = (uint32_t*)smem + (size_t)(threadIdx.x >> 5) * (size_t)(D + 4);
+    uint32_t* out = S + D;
+    TileSync<32> sync;
+    sync.x = 0xffffffffu;
     unsigned int fails = 0;
     const uint32_t n = *x.qcount;
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    for (uint32_t i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
         const uint32_t k = x.queue[2u * i], base = x.queue[2u * i + 1u];
-        const uint32_t bit = fast::hard_resolve(g, x.buf + base, key, S, out, lane, TW, sync);
+        const uint32_t bit = fast::hard_resolve(x.buf + base, S, out, lane, WARP, sync);
         if (lane == 0) { fails += bit; if (logical) logical[k] = (uint8_t)bit; }
-        sync();
+        __syncwarp();
     }
     if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
 }
@@ -2259,17 +2256,14 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                 uint32_t* qcount = cnt;
                 // Second pass over the HARD shots with the merge log, then k_hard_resolve -- instead of the canonical
                 // launch, whose reservation merge needs about one iteration per edge of a lattice-spanning cluster (5 ms
-                // for ONE shot of d = 17 at p = 0.026).  Measured at p = 0.026 (M shots/s, with / without): d = 17 4.5 / 3.0,
-                // d = 25 0.88 / 0.61, d = 11 36.1 / 36.9 -- the replay of a shot's unions is one lane's dependent chain
-                // (about 0.8 us per key), which pays from about d = 13 on.  LUF_FAST_LOG=0 / 1 forces it off / on.
-                const int env_log_v = getenv("LUF_FAST_LOG") ? atoi(getenv("LUF_FAST_LOG")) : -1;
-                const bool env_log = env_log_v < 0 ? g->fview.D >= 1500 : env_log_v != 0;
+                // for ONE shot of d = 17 at p = 0.026).  Measured at p = 0.026 (M shots/s, with / without; profiles/
+                // r02_hard_resolve.txt): d = 11 38.8 / 37.0, d = 13 18.4 / 17.0, d = 17 4.66 / 3.08, d = 21 2.15 / 1.21,
+                // d = 25 1.04 / 0.58.  LUF_FAST_LOG=0 sends the HARD shots straight to the canonical launch.
+                const bool env_log = !(getenv("LUF_FAST_LOG") && atoi(getenv("LUF_FAST_LOG")) == 0);
                 const fast::FLayout fl2 = make_fast_layout(g->fview.D, g->fview.E, g->fview.DEG, mu, true);
                 FastPlan plan2;
-                uint32_t keycap = 32;
-                while (keycap < fast::RESOLVE_MAX_KEYS && keycap < fl2.lcap) keycap <<= 1;
-                const size_t resolve_smem = 4 * ((size_t)keycap + (size_t)g->fview.D + 4 + 2 * fast::RESOLVE_SEGS);
-                const bool log_pass = env_log && !(flags & LUF_UF_WEST) && fast_plan(g, fl2, &plan2) && resolve_smem <= (size_t)g->max_smem;
+                const size_t resolve_warp = 4 * ((size_t)g->fview.D + 4);         // hard_resolve: one word per detector per warp
+                const bool log_pass = env_log && !(flags & LUF_UF_WEST) && fast_plan(g, fl2, &plan2) && resolve_warp <= (size_t)g->max_smem;
                 for (int64_t done = 0; done < nshots; done += FAST_CHUNK) {
                     const long long m = std::min<long long>(FAST_CHUNK, nshots - done);
                     const unsigned long long first = shot0 + (unsigned long long)done;
@@ -2277,8 +2271,15 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                     fast::FView fv = g->fview;
                     fv.west = (flags & LUF_UF_WEST) ? 1 : 0;
                     if (!fv.west) CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, (cudaStream_t)stream));
+                    // LUF_DEBUG_TIMES=1: CUDA events around the launches of a chunk (measurements; synchronises)
+                    const bool env_times = getenv("LUF_DEBUG_TIMES") && atoi(getenv("LUF_DEBUG_TIMES")) != 0;
+                    cudaEvent_t ev[5] = {0, 0, 0, 0, 0};
+                    int nev = 0;
+                    auto mark = [&]() { if (env_times && nev < 5) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], (cudaStream_t)stream); ++nev; } };
+                    mark();
                     if (int rc = fast_launch(g, fv, plan, fl, sp, first, m, counts_dev, lg, queue, qcount, (cudaStream_t)stream)) return rc;
                     ++g->launches;
+                    mark();
                     uint32_t *cq = queue, *cqc = qcount;         // what the canonical launch takes
                     if (log_pass) {
                         // export buffer: 64 words per shot of the chunk, between 2^22 and 2^27 (a shot that finds no room goes to Q3)
@@ -2286,23 +2287,23 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                         void* xbuf = nullptr;
                         if (int rc = wide_slab(g, stream, 4, xcap * 4, &xbuf)) return rc;
                         FastLogArgs la;
-                        la.x.buf = (uint32_t*)xbuf; la.x.cursor = cnt + 3; la.x.cap = (uint32_t)xcap; la.x.max_keys = keycap;
+                        la.x.buf = (uint32_t*)xbuf; la.x.cursor = cnt + 3; la.x.cap = (uint32_t)xcap;
                         la.x.queue = q2; la.x.qcount = cnt + 2;
                         la.qin = queue; la.qin_count = cnt;
                         if (int rc = fast_launch(g, fv, plan2, fl2, sp, first, m, counts_dev, lg, q3, cnt + 1, (cudaStream_t)stream, &la)) return rc;
                         ++g->launches;
-                        // (the replay of a shot is one lane's dependent chain: as many resident tiles as shared memory allows)
-                        const bool narrow_tile = keycap <= 4096;
-                        const long long rblocks = (long long)g->sm_count * std::max<size_t>(1, std::min<size_t>(narrow_tile ? 32 : 8, (size_t)(228 * 1024) / (resolve_smem + 1024)));
-                        if (narrow_tile) {
-                            if (int rc = raise_smem_limit(g->device, g->max_smem, k_hard_resolve<32>)) return rc;
-                            k_hard_resolve<32><<<(int)rblocks, 32, resolve_smem, (cudaStream_t)stream>>>(fv, la.x, keycap, counts_dev, lg);
-                        } else {
-                            if (int rc = raise_smem_limit(g->device, g->max_smem, k_hard_resolve<256>)) return rc;
-                            k_hard_resolve<256><<<(int)rblocks, 256, resolve_smem, (cudaStream_t)stream>>>(fv, la.x, keycap, counts_dev, lg);
+                        mark();
+                        // (the replay of a shot is one dependent chain: as many resident warps as shared memory allows)
+                        {
+                            if (int rc = raise_smem_limit(g->device, g->max_smem, k_hard_resolve)) return rc;
+                            const int rwpb = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)g->max_smem / resolve_warp));
+                            const size_t rsmem = (size_t)rwpb * resolve_warp;
+                            const long long per_sm = std::max<long long>(1, std::min<long long>(64 / rwpb, (long long)(228 * 1024) / (long long)(rsmem + 1024)));
+                            k_hard_resolve<<<(int)(g->sm_count * per_sm), rwpb * WARP, rsmem, (cudaStream_t)stream>>>(g->fview.D, la.x, counts_dev, lg);
                         }
                         CUDA_TRY(cudaGetLastError());
                         ++g->launches;
+                        mark();
                         cq = q3; cqc = cnt + 1;                  // only what the second pass could not log
                     }
                     if (!fv.west && g->wide) {  // the HARD shots of a graph beyond the 16-bit layout: the wide instance
@@ -2316,6 +2317,15 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                         LUF_MC_UF_ANY(0, true, first, m, lg, cq, cqc)
                         CUDA_TRY(cudaGetLastError());
                         ++g->launches;
+                    }
+                    mark();
+                    if (env_times) {
+                        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+                        float t[4] = {0, 0, 0, 0};
+                        for (int i = 0; i + 1 < nev; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+                        for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+                        if (log_pass) fprintf(stderr, "[luf] chunk of %lld shots: first pass %.3f ms, log pass %.3f ms, hard_resolve %.3f ms, canonical launch %.3f ms\n", m, t[0], t[1], t[2], t[3]);
+                        else fprintf(stderr, "[luf] chunk of %lld shots: first pass %.3f ms, canonical launch %.3f ms\n", m, t[0], t[1]);
                     }
                     if (!fv.west && getenv("LUF_DEBUG_PLAN")) {
                         uint32_t h[4];

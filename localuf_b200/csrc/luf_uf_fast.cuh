@@ -55,7 +55,6 @@ enum { C_TOUCHED = 0, C_ALIST = 1, C_MLIST = 2, C_ACTIVE = 3, C_XBASE = 4, C_PAR
 static const uint32_t HARD = 2u;                         // result of a shot the canonical kernel has to decode
 static const uint32_t HARD_LOGGED = 3u;                  // ... or whose odd clusters on both sides were exported for hard_resolve
 static const uint32_t KEY_EDGE_BITS = 20u, KEY_EDGE_MASK = 0xFFFFFu;      // merge-log key = growth round << 20 | edge id
-static const uint32_t RESOLVE_MAX_KEYS = 16384u;         // most log entries of one shot's HARD clusters that hard_resolve sorts (a power of two)
 
 // Where the HARD clusters of a launch go (global memory): per shot `count | fast bit << 31` followed by `count` keys,
 // reserved with one atomic add on *cursor; (shot, offset) pairs in `queue`, *qcount of them.
@@ -63,7 +62,6 @@ struct FExport {
     uint32_t* buf;
     uint32_t* cursor;
     uint32_t cap;               // words of buf
-    uint32_t max_keys;          // most keys per shot (hard_resolve's sort buffer)
     uint32_t* queue;            // [2 * shots of the launch]
     uint32_t* qcount;
 };
@@ -505,7 +503,7 @@ LUF_DEV uint32_t f_defect_sides(const FView& g, const FLayout& l, const FShot& s
 // order of the merges INSIDE that cluster -- and on nothing else: growth, the partition after every round and
 // every other cluster's contribution to the logical bit are order-free.  So a shot with such clusters is not
 // decoded again: the merge log of the shot (every newly FULL edge, keyed by round and edge id) is filtered to the
-// edges inside those clusters and exported; hard_resolve sorts the keys, replays those unions alone in canonical
+// edges inside those clusters, sorted and exported; hard_resolve replays those unions alone in canonical
 // order (union by size, ties keep the cluster of the edge's first endpoint; every boundary edge brings a
 // boundary node of its own: size 1, its side) and reports how many of the clusters keep an EAST node -- for each
 // of them the fast bit, which counted the cluster as west, is flipped.
@@ -518,40 +516,51 @@ LUF_DEV bool f_in_hard_cluster(const FView& g, const FShot& s, uint32_t key)
     return (wr & (P_ODD | P_WEST | P_EAST)) == (P_ODD | P_WEST | P_EAST);
 }
 
-LUF_DEV void f_export_count(const FView& g, const FShot& s, uint32_t ntot, int lane, int nl)
+// The shot is decoded; its log becomes the export.  Entries outside the HARD clusters are blanked (all ones: they
+// sort to the end), the rest is counted ...
+LUF_DEV void f_export_mark(const FView& g, const FShot& s, uint32_t ntot, uint32_t np, int lane, int nl)
 {
     uint32_t c = 0;
     LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < ntot; i += (uint32_t)nl) c += f_in_hard_cluster(g, s, s.elog[i]) ? 1u : 0u;
+    for (uint32_t i = (uint32_t)lane; i < np; i += (uint32_t)nl) {
+        if (i < ntot && f_in_hard_cluster(g, s, s.elog[i])) ++c; else s.elog[i] = 0xFFFFFFFFu;
+    }
     if (c) luf_atomic_add(&s.cnt[C_XCOUNT], c);
 }
 
-// one lane: room for `count | bit << 31` and the keys; C_XBASE = where, or 0xFFFFFFFF (no room, too many keys)
+// ... sorted by (round, edge id) in place, a bitonic network over the tile's lanes ...
+LUF_DEV void r_sort_step(uint32_t* key, uint32_t np, uint32_t k, uint32_t j, int lane, int nl)
+{
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < np; i += (uint32_t)nl) {
+        const uint32_t o = i ^ j;
+        if (o <= i) continue;
+        const uint32_t a = key[i], b = key[o];
+        if ((a > b) == ((i & k) == 0u)) { key[i] = b; key[o] = a; }
+    }
+}
+
+// ... one lane reserves room for `count | bit << 31` and the edges; C_XBASE = where, or 0xFFFFFFFF (no room) ...
 LUF_DEV void f_export_reserve(const FShot& s, const FExport& x, uint32_t fast_bit)
 {
     const uint32_t n = s.cnt[C_XCOUNT];
-    uint32_t base = 0xFFFFFFFFu;
-    if (n <= x.max_keys) {
-        base = luf_atomic_add(x.cursor, n + 1u);
-        if (base + n + 1u > x.cap || base + n + 1u < base) base = 0xFFFFFFFFu;
-        else x.buf[base] = n | (fast_bit << 31);
-    }
+    uint32_t base = luf_atomic_add(x.cursor, n + 1u);
+    if (base + n + 1u > x.cap || base + n + 1u < base) base = 0xFFFFFFFFu;
+    else x.buf[base] = n | (fast_bit << 31);
     s.cnt[C_XBASE] = base;
-    s.cnt[C_XCOUNT] = 0u;
 }
 
-LUF_DEV void f_export_write(const FView& g, const FShot& s, const FExport& x, uint32_t ntot, int lane, int nl)
+// ... and the edges go out in canonical order as endpoint pairs (first end | second end << 16: hard_resolve needs
+// no table).
+LUF_DEV void f_export_write(const FView& g, const FShot& s, const FExport& x, int lane, int nl)
 {
-    const uint32_t base = s.cnt[C_XBASE];
+    const uint32_t base = s.cnt[C_XBASE], n = s.cnt[C_XCOUNT];
     LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < ntot; i += (uint32_t)nl) {
-        const uint32_t key = s.elog[i];
-        if (f_in_hard_cluster(g, s, key)) x.buf[base + 1u + luf_atomic_add(&s.cnt[C_XCOUNT], 1u)] = key;
-    }
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) x.buf[base + 1u + i] = LUF_LDG(&g.einfo[s.elog[i] & KEY_EDGE_MASK]);
 }
 
-// hard_resolve's node words (scratch, one per detector): root = R_ROOT | kept side << 28 | counted << 27 | size,
-// non-root = parent
+// hard_resolve's node words (one per detector, in the warp's shared memory): root = R_ROOT | kept side << 28 |
+// counted << 27 | size, non-root = parent
 static const uint32_t R_ROOT = 0x80000000u, R_SIDE_SHIFT = 28u, R_SIDE_MASK = 3u << 28, R_COUNTED = 1u << 27, R_SIZE_MASK = (1u << 27) - 1u;
 static const uint32_t R_WEST = 1u, R_EAST = 2u;
 
@@ -570,100 +579,39 @@ LUF_DEV uint32_t r_find(uint32_t* S, uint32_t v, uint32_t& wr)
     return v;
 }
 
-LUF_DEV void r_sort_step(uint32_t* key, uint32_t np, uint32_t k, uint32_t j, int lane, int nl)
-{
-    LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < np; i += (uint32_t)nl) {
-        const uint32_t o = i ^ j;
-        if (o <= i) continue;
-        const uint32_t a = key[i], b = key[o];
-        if ((a > b) == ((i & k) == 0u)) { key[i] = b; key[o] = a; }
-    }
-}
-
-// The sorted keys give way to the endpoint pairs of their edges (the lane that replays the unions then reads
-// shared memory only); every detector they name starts as a singleton without a boundary.
-LUF_DEV void r_init(const FView& g, uint32_t* key, uint32_t n, uint32_t* S, int lane, int nl)
+// every detector the edges name starts as a singleton without a boundary
+LUF_DEV void r_init(const uint32_t* ends, uint32_t n, uint32_t* S, int lane, int nl)
 {
     LUF_NOUNROLL
     for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t ei = LUF_LDG(&g.einfo[key[i] & KEY_EDGE_MASK]);
+        const uint32_t ei = ends[i];
         const uint32_t a = ei & 0xFFFFu, b = ei >> 16;
-        key[i] = ei;
         if (a < END_EAST) S[a] = R_ROOT | 1u;
         if (b < END_EAST) S[b] = R_ROOT | 1u;
     }
 }
 
-// Where the keys of every growth round start in the sorted list: seg[r] = first index of round r (rounds from
-// RESOLVE_SEGS - 1 on share the last entry), 0xFFFFFFFF = none; seg[RESOLVE_SEGS + r] = the end (r_seg_ends).
-static const uint32_t RESOLVE_SEGS = 64u;
-
-LUF_DEV uint32_t r_round_of(uint32_t key) { const uint32_t r = key >> KEY_EDGE_BITS; return r < RESOLVE_SEGS ? r : RESOLVE_SEGS - 1u; }
-
-LUF_DEV void r_seg_starts(const uint32_t* key, uint32_t n, uint32_t* seg, int lane, int nl)
+// uf.py:256-301 for one edge (endpoint pair) on the scratch forest
+LUF_DEV void r_union(uint32_t* S, uint32_t ei)
 {
-    LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t r = r_round_of(key[i]);
-        if (i == 0u || r_round_of(key[i - 1u]) != r) seg[r] = i;
+    const uint32_t a = ei & 0xFFFFu, b = ei >> 16;
+    if (a >= END_EAST || b >= END_EAST) {            // a boundary node of its own (one edge each): size 1, boundary = itself
+        const uint32_t side = (a >= END_EAST ? a : b) == END_WEST ? R_WEST : R_EAST;
+        uint32_t w;
+        const uint32_t r = r_find(S, a >= END_EAST ? b : a, w);
+        w += 1u;
+        if (!(w & R_SIDE_MASK)) w |= side << R_SIDE_SHIFT;     // uf.py:536-538 (a detector cluster that is no larger has no boundary yet)
+        S[r] = w;
+        return;
     }
-}
-
-LUF_DEV void r_seg_ends(uint32_t n, uint32_t* seg)       // one lane
-{
-    uint32_t e = n;
-    LUF_NOUNROLL
-    for (int r = (int)RESOLVE_SEGS - 1; r >= 0; --r)
-        if (seg[r] != 0xFFFFFFFFu) { seg[RESOLVE_SEGS + r] = e; e = seg[r]; }
-}
-
-// All lanes, between two rounds (no union in flight): every detector of the edges so far points at its root, so
-// that the finds of the next round's unions are one or two hops.
-LUF_DEV void r_flatten(const uint32_t* ends, uint32_t n, uint32_t* S, int lane, int nl)
-{
-    LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) {
-        const uint32_t ei = ends[i];
-        LUF_NOUNROLL
-        for (int x = 0; x < 2; ++x) {
-            const uint32_t v0 = x ? ei >> 16 : ei & 0xFFFFu;
-            if (v0 >= END_EAST) continue;
-            uint32_t w = S[v0];
-            if (w & R_ROOT) continue;
-            uint32_t v = w;
-            LUF_NOUNROLL
-            while (!((w = S[v]) & R_ROOT)) v = w;
-            S[v0] = v;
-        }
-    }
-}
-
-// One lane: the unions of the sorted edges [lo, hi) (endpoint pairs, r_init) in order.
-LUF_DEV void r_replay(const uint32_t* ends, uint32_t lo, uint32_t n, uint32_t* S)
-{
-    LUF_NOUNROLL
-    for (uint32_t i = lo; i < n; ++i) {
-        const uint32_t ei = ends[i];
-        const uint32_t a = ei & 0xFFFFu, b = ei >> 16;
-        if (a >= END_EAST || b >= END_EAST) {            // a boundary node of its own (one edge each): size 1, boundary = itself
-            const uint32_t side = (a >= END_EAST ? a : b) == END_WEST ? R_WEST : R_EAST;
-            uint32_t w;
-            const uint32_t r = r_find(S, a >= END_EAST ? b : a, w);
-            w += 1u;
-            if (!(w & R_SIDE_MASK)) w |= side << R_SIDE_SHIFT;     // uf.py:536-538 (a detector cluster that is no larger has no boundary yet)
-            S[r] = w;
-            continue;
-        }
-        uint32_t wa, wb;
-        const uint32_t ra = r_find(S, a, wa), rb = r_find(S, b, wb);
-        if (ra == rb) continue;
-        const bool a_large = (wa & R_SIZE_MASK) >= (wb & R_SIZE_MASK);             // uf.py:270-273: ties keep the first endpoint's cluster
-        const uint32_t L = a_large ? ra : rb, Sm = a_large ? rb : ra, wl = a_large ? wa : wb, ws = a_large ? wb : wa;
-        const uint32_t side = (wl & R_SIDE_MASK) ? (wl & R_SIDE_MASK) : (ws & R_SIDE_MASK);
-        S[L] = R_ROOT | side | ((wl & R_SIZE_MASK) + (ws & R_SIZE_MASK));
-        S[Sm] = L;
-    }
+    uint32_t wa, wb;
+    const uint32_t ra = r_find(S, a, wa), rb = r_find(S, b, wb);
+    if (ra == rb) return;
+    const bool a_large = (wa & R_SIZE_MASK) >= (wb & R_SIZE_MASK);             // uf.py:270-273: ties keep the first endpoint's cluster
+    const uint32_t L = a_large ? ra : rb, Sm = a_large ? rb : ra, wl = a_large ? wa : wb, ws = a_large ? wb : wa;
+    const uint32_t side = (wl & R_SIDE_MASK) ? (wl & R_SIDE_MASK) : (ws & R_SIDE_MASK);
+    S[L] = R_ROOT | side | ((wl & R_SIZE_MASK) + (ws & R_SIZE_MASK));
+    S[Sm] = L;
 }
 
 // All lanes: every cluster once (the roots are stable now); *out ^= 1 per cluster that keeps an east node.
@@ -743,10 +691,17 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
         if (s.cnt[C_HARD_M]) {                           // (uniform: every lane reads the same word after the barrier)
             const uint32_t ntot = s.cnt[C_MLIST];
             if (!x || !x->buf || !l.lcap || ntot > l.lcap) return HARD;           // no log, or it could not hold the shot's merges
-            FT_PHASE(f_export_count(g, s, ntot, lane, nl));
+            uint32_t np = 1;
+            while (np < ntot) np <<= 1;                  // (lcap is a power of two)
+            FT_PHASE(f_export_mark(g, s, ntot, np, lane, nl));
+            LUF_NOUNROLL
+            for (uint32_t k = 2; k <= np; k <<= 1) {
+                LUF_NOUNROLL
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) { FT_PHASE(r_sort_step(s.elog, np, k, j, lane, nl)); }
+            }
             FT_PHASE(if (lane == 0) f_export_reserve(s, *x, s.cnt[C_PARITY] & 1u));
             if (s.cnt[C_XBASE] == 0xFFFFFFFFu) return HARD;
-            FT_PHASE(f_export_write(g, s, *x, ntot, lane, nl));
+            FT_PHASE(f_export_write(g, s, *x, lane, nl));
             return HARD_LOGGED;                          // the caller queues (shot, s.cnt[C_XBASE])
         }
     }
@@ -754,35 +709,30 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
     return s.cnt[C_PARITY] & 1u;
 }
 
-// One exported shot: x.buf[base] = count | fast bit << 31, then the keys.  `key` = scratch for the sorted keys (a
-// power of two >= count words), `S` = one word per detector.  Returns the shot's logical bit.
-// `out`: 1 + 2 * RESOLVE_SEGS scratch words (the result, the rounds' segments).
+// One exported shot, one warp: rec[0] = count | fast bit << 31, then the edges of the shot's HARD clusters in
+// canonical order.  `S` = one word per detector, `out` = one word (both the warp's own).  The unions are one
+// dependent chain; every lane of the warp runs it on the same values (same cost as one lane, and the warp can
+// fetch the edges 32 at a time).  Returns the shot's logical bit.
 template <class Sync>
-LUF_DEV uint32_t hard_resolve(const FView& g, const uint32_t* rec, uint32_t* key, uint32_t* S, uint32_t* out, int lane, int nl, Sync sync)
+LUF_DEV uint32_t hard_resolve(const uint32_t* rec, uint32_t* S, uint32_t* out, int lane, int nl, Sync sync)
 {
     (void)lane; (void)sync;
     const uint32_t n = rec[0] & 0x7FFFFFFFu, bit = rec[0] >> 31;
-    uint32_t np = 1;
-    while (np < n) np <<= 1;
-    FT_PHASE(for (uint32_t i = (uint32_t)lane; i < np; i += (uint32_t)nl) key[i] = i < n ? rec[1u + i] : 0xFFFFFFFFu);
+    const uint32_t* ends = rec + 1;
+    FT_PHASE(r_init(ends, n, S, lane, nl); if (lane == 0) *out = bit);
+#if defined(LUF_HOST_EMU)
+    for (uint32_t i = 0; i < n; ++i) r_union(S, ends[i]);
+#else
     LUF_NOUNROLL
-    for (uint32_t k = 2; k <= np; k <<= 1) {             // bitonic sort, ascending (round, edge id)
+    for (uint32_t c = 0; c < n; c += 32u) {
+        const uint32_t mine = c + (uint32_t)lane < n ? __ldg(&ends[c + (uint32_t)lane]) : 0u;
+        const int m = (int)(n - c < 32u ? n - c : 32u);
         LUF_NOUNROLL
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) { FT_PHASE(r_sort_step(key, np, k, j, lane, nl)); }
+        for (int j = 0; j < m; ++j) { r_union(S, __shfl_sync(0xffffffffu, mine, j)); __syncwarp(); }
     }
-    uint32_t* seg = out + 1;
-    FT_PHASE(for (uint32_t r = (uint32_t)lane; r < RESOLVE_SEGS; r += (uint32_t)nl) seg[r] = 0xFFFFFFFFu);
-    FT_PHASE(r_seg_starts(key, n, seg, lane, nl));
-    FT_PHASE(r_init(g, key, n, S, lane, nl); if (lane == 0) { *out = bit; r_seg_ends(n, seg); });
-    LUF_NOUNROLL
-    for (uint32_t r = 0; r < RESOLVE_SEGS; ++r) {        // round by round: one lane's unions, then all lanes flatten
-        const uint32_t lo = seg[r];
-        if (lo == 0xFFFFFFFFu) continue;
-        const uint32_t hi = seg[RESOLVE_SEGS + r];
-        FT_PHASE(if (lane == 0) r_replay(key, lo, hi, S));
-        FT_PHASE(r_flatten(key, hi, S, lane, nl));
-    }
-    FT_PHASE(r_count_east(key, n, S, out, lane, nl));
+    sync();
+#endif
+    FT_PHASE(r_count_east(ends, n, S, out, lane, nl));
     return *out;
 }
 

@@ -400,24 +400,25 @@ int emu_mc_uf_compact_log(const luf_graph_desc* d, const double* class_p, unsign
     g.fresh_perm = nullptr; g.fresh_perm32 = pf.perm_identity ? nullptr : pf.fresh_perm32.data(); g.class_end = pf.class_end.data();
     g.west = 0;
     fast::FLayout l = make_fast_layout(pf.D, pf.E, pf.DEG, mu, true);
-    if (lcap >= 0) {                 // a log of the caller's size behind the state
-        l.lcap = (uint32_t)lcap; l.elog = l.bytes; l.bytes += 4u * (uint32_t)lcap + 16u;
+    if (lcap >= 0) {                 // a log of the caller's size (rounded up to a power of two) behind the state
+        uint32_t p2 = 1; while (p2 < (uint32_t)lcap) p2 <<= 1;
+        l.lcap = p2; l.elog = l.bytes; l.bytes += 4u * p2 + 16u;
     }
     const SampleParams sp = make_sample_params(class_p, pf.n_classes, seed);
     std::vector<unsigned char> mem(l.bytes + 16);
     const fast::FShot s = fast::fbind(l, mem.data());
-    std::vector<uint32_t> xbuf(fast::RESOLVE_MAX_KEYS + 8), key(fast::RESOLVE_MAX_KEYS), S(pf.D, 0xDEADBEEFu);
-    uint32_t cursor = 0, q[2], qn = 0, res[1 + 2 * fast::RESOLVE_SEGS];
+    std::vector<uint32_t> xbuf((size_t)pf.E + 8), S(pf.D, 0xDEADBEEFu);
+    uint32_t cursor = 0, q[2], qn = 0, res = 0;
     for (long long k = 0; k < nshots; ++k) {
         cursor = 0;
-        fast::FExport x{xbuf.data(), &cursor, (uint32_t)xbuf.size(), fast::RESOLVE_MAX_KEYS, q, &qn};
+        fast::FExport x{xbuf.data(), &cursor, (uint32_t)xbuf.size(), q, &qn};
         uint32_t r = fast::fast_shot<false>(g, l, s, sp, shot0 + k, 0, nl, 0, nullptr, &x);
         if (nkeys) nkeys[k] = 0;
         if (nlog) nlog[k] = s.cnt[fast::C_MLIST];
         if (r == fast::HARD_LOGGED) {
             const uint32_t base = s.cnt[fast::C_XBASE];
             if (nkeys) nkeys[k] = xbuf[base] & 0x7FFFFFFFu;
-            r = fast::hard_resolve(g, xbuf.data() + base, key.data(), S.data(), res, 0, nl > 32 ? 256 : 32, 0);
+            r = fast::hard_resolve(xbuf.data() + base, S.data(), &res, 0, 32, 0);
         }
         out[k] = (uint8_t)r;
     }
