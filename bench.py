@@ -40,6 +40,11 @@ WORKLOADS = {
                    'batch', 'Macar'),
     'cfg3-actis': ('Surface', 11, 'phenomenological', 0.01, 'Surface d=11 phenomenological p=0.01 h=11 Actis batch',
                    'batch', 'Actis'),
+    # BASELINE configs[4] (threshold sweep), two of its hard corners: near threshold at a large distance (shots with odd
+    # clusters on both sides go through the merge-log pass and k_hard_resolve), and a graph beyond the 16-bit layout
+    # (compact fast launch + the wide instance for its HARD shots)
+    'cfg5-d17': ('Surface', 17, 'phenomenological', 0.026, 'Surface d=17 phenomenological p=0.026 h=17 UF batch'),
+    'cfg5-wide': ('Surface', 23, 'circuit-level', 0.004, 'Surface d=23 circuit-level p=0.004 h=23 UF batch (65869 edges: wide instance)'),
     'cfg4': ('Surface', 13, 'circuit-level', 0.003,
              'Surface d=13 circuit-level p=0.003 frugal (c=1, b=12) Snowflake; unit = decoding cycle', 'frugal', 'Snowflake'),
 }
@@ -310,7 +315,7 @@ _RESULT_OUT = sys.stdout          # main() points it at the real stdout and send
 DTYPE = 'u32 bit-packed / u16 indices'
 METRIC = {'shots/s': 'decoded shots/s', 'decoding cycles/s': 'decoding cycles/s'}
 DEFAULT_UNITS = {'cfg1': 1 << 26, 'cfg2': 1 << 24, 'cfg3': 1 << 22, 'cfg3-staged': 1 << 20, 'cfg3-macar': 1 << 19, 'cfg3-actis': 1 << 14,
-                 'cfg4': 1 << 16}
+                 'cfg4': 1 << 16, 'cfg5-d17': 1 << 17, 'cfg5-wide': 1 << 15}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full; profiles/)
 TRAFFIC = {'cfg3': (76288, 'profiles/r02_v1_k_mc_uf_fast_summary.txt (one launch of 2^20 shots: the graph tables once per block; no per-shot HBM traffic)'),
            'cfg3-macar': (89856, 'profiles/r01_k_mc_ca_macar_summary.txt'),
@@ -377,7 +382,8 @@ def host_buffer_e2e(eng, p, world, rank, steps, n=1 << 20):
 # (workload, noise level or None = the workload's own, units per step)
 SIDE_WORKLOADS = [('cfg1', None, 1 << 24), ('cfg2', None, 1 << 22), ('cfg2', 0.10, 1 << 21),
                   ('cfg3', 0.005, 1 << 21), ('cfg3', 0.02, 1 << 20), ('cfg3', 0.026, 1 << 19),
-                  ('cfg3-macar', None, 1 << 18), ('cfg3-actis', None, 1 << 13), ('cfg4', None, 1 << 14), ('cfg4', 0.001, 1 << 14)]
+                  ('cfg3-macar', None, 1 << 18), ('cfg3-actis', None, 1 << 13), ('cfg4', None, 1 << 14), ('cfg4', 0.001, 1 << 14),
+                  ('cfg5-d17', None, 1 << 16), ('cfg5-wide', None, 1 << 14)]
 
 
 def run_ours(args):
@@ -429,7 +435,7 @@ def run_ours(args):
             eng = _engine.Engine(code, device=local_rank)
             decoder._engine = eng
             unit = 'shots/s'
-            kernel = {'UF': 'k_mc_uf_fast (+ k_mc_uf over the queued shots)', 'Macar': 'k_mc_ca', 'Actis': 'k_mc_ca'}[dec]
+            kernel = {'UF': 'k_mc_uf_fast (+ its merge-log pass and k_hard_resolve over the queued shots)', 'Macar': 'k_mc_ca', 'Actis': 'k_mc_ca'}[dec]
             bpu = algorithmic_bytes_per_shot(code.FLAT)
             h2d = 8 * code.FLAT.n_classes + 40
             did = DECODER_ID[dec]

@@ -124,8 +124,11 @@ struct TileSync {
 // LOGQ: the second pass, over the HARD shots the first one queued (`qin`, *qin_count): the same decode with
 // the merge log (luf_uf_fast.cuh); the merges inside the odd clusters on both sides are exported for
 // k_hard_resolve (x.queue), and only a shot whose log or export did not fit goes on to `queue` -- the canonical launch.
+// (48 registers: two blocks of 640 threads -- five shots of 128 lanes, the d = 17 plan -- have to fit an SM's register
+// file, which is allocated in units of 8 per thread: with 50 the second block did not, 10.4 -> 6.2 M shots/s there;
+// the warp tile of cfg3 is 8 % slower when capped -- 38 registers instead of 46 -- and keeps the 64 of its launch shape)
 template <int TW, bool ADJ_SHARED, bool LOGQ>
-__global__ void __launch_bounds__(1024, 1) k_mc_uf_fast(fast::FView g, fast::FLayout l, uint32_t adj_bytes, SampleParams sp,
+__global__ void __maxnreg__(TW >= 64 ? 48 : 64) k_mc_uf_fast(fast::FView g, fast::FLayout l, uint32_t adj_bytes, SampleParams sp,
                         unsigned long long shot0, long long nshots, unsigned long long* counts,
                         uint8_t* __restrict__ logical, uint32_t* __restrict__ queue, uint32_t* __restrict__ qcount,
                         fast::FExport x, const uint32_t* __restrict__ qin, const uint32_t* __restrict__ qin_count)
