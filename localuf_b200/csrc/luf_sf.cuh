@@ -602,8 +602,10 @@ namespace luf { using namespace sf_warp; }
 #else
   #define LUF_ST_PHASE(stmt) { stmt; } __syncthreads();
   #define LUF_ST_ANY(x) __syncthreads_or((x) != 0)
+  #define LUF_ST_BLOCK_VOTES 1
 #endif
 #include "luf_sf_drivers.inl"
+#undef LUF_ST_BLOCK_VOTES
 #undef LUF_SF_NS
 #undef LUF_ST_PHASE
 #undef LUF_ST_ANY

@@ -13,12 +13,31 @@ LUF_DEV void sf_merge(const SfView& g, const SfShot& s, bool whole, bool slow, i
     rt_all += 1;
     LUF_NOUNROLL_CA
     for (int guard = 0; guard < (1 << 20); ++guard) {
+#if defined(LUF_ST_BLOCK_VOTES)
+        // Block tile: the two votes of a timestep (any busy, any RESET) are one OR into a word of shared memory --
+        // two alternating words, the next one cleared by lane 0 while this one is filled -- so that a timestep costs
+        // two block barriers instead of four (phase A, phase B, and a __syncthreads_or per vote).
+        uint32_t* vote = &s.acnt[1 + (guard & 1)];
+        if (guard == 0 && lane == 0) *vote = 0u;
+        LUF_ST_PHASE(sf_merge_a(g, s, whole, slow, lane, nl));
+        {
+            const uint32_t mine = sf_merge_b(g, s, lane, nl);
+            if (mine) luf_atomic_or(vote, mine);
+            if (lane == 0) s.acnt[1 + ((guard + 1) & 1)] = 0u;
+        }
+        __syncthreads();
+        const uint32_t acc = *vote;
+        rt_all += 1;
+        if (acc & 2u) rt_unr += 1;
+        if (!(acc & 1u)) break;
+#else
         LUF_ST_PHASE(sf_merge_a(g, s, whole, slow, lane, nl));
         uint32_t acc = 0;
         LUF_ST_PHASE(acc |= sf_merge_b(g, s, lane, nl));
         rt_all += 1;
         if (LUF_ST_ANY(acc & 2u)) rt_unr += 1;
         if (!LUF_ST_ANY(acc & 1u)) break;
+#endif
     }
 }
 
@@ -36,13 +55,10 @@ LUF_DEV void sf_cycle_tail(const SfView& g, const SfShot& s, int flags, uint32_t
     (void)lane;
     rt_all = 0; rt_unr = 0;
     // floor corrections to Pairs (FloorContact.drop), then the window moves
-    uint32_t any_corr = 0;
-    LUF_ST_PHASE(for (int c = lane; c < g.ELw; c += nl) {
-                  const uint32_t x = s.corr[(g.h - 1) * g.ELw + c];
-                  any_corr |= x;
-                  if (floor_out) floor_out[c] = x;
-              });
-    if (LUF_ST_ANY(any_corr)) { LUF_ST_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.corr + (g.h - 1) * g.ELw, m)); }
+    // (one phase: the lane that owns Pairs walks the floor sheet itself -- a dozen words, mostly empty -- instead of a
+    // vote of the tile on whether there is anything to load)
+    LUF_ST_PHASE(if (floor_out) for (int c = lane; c < g.ELw; c += nl) floor_out[c] = s.corr[(g.h - 1) * g.ELw + c];
+                 if (lane == 0) sf_pairs_load_block(g, s, s.corr + (g.h - 1) * g.ELw, m));
     LUF_ST_PHASE(sf_drop(g, s, lane, nl));
     LUF_SF_REGATHER();                               // the window moved
     if (drop_only) {
@@ -76,9 +92,7 @@ LUF_DEV void sf_cycle_metrics(const SfView& g, const SfShot& s, uint32_t* growth
 LUF_DEV void sf_cycle_head(const SfView& g, const SfShot& s, int& m, int lane, int nl)
 {
     (void)lane;
-    uint32_t any_err = 0;
-    LUF_ST_PHASE(for (int c = lane; c < g.ELw; c += nl) any_err |= s.err[(g.h - 1) * g.ELw + c]);
-    if (LUF_ST_ANY(any_err)) { LUF_ST_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.err + (g.h - 1) * g.ELw, m)); }
+    LUF_ST_PHASE(if (lane == 0) sf_pairs_load_block(g, s, s.err + (g.h - 1) * g.ELw, m));
     LUF_ST_PHASE(sf_shift_errors(g, s, lane, nl));
     LUF_ST_PHASE(sf_begin_sheet(g, s, lane, nl));
 }
