@@ -317,7 +317,7 @@ METRIC = {'shots/s': 'decoded shots/s', 'decoding cycles/s': 'decoding cycles/s'
 DEFAULT_UNITS = {'cfg1': 1 << 26, 'cfg2': 1 << 24, 'cfg3': 1 << 22, 'cfg3-staged': 1 << 20, 'cfg3-macar': 1 << 19, 'cfg3-actis': 1 << 14,
                  'cfg4': 1 << 16, 'cfg5-d17': 1 << 17, 'cfg5-wide': 1 << 15}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full; profiles/)
-TRAFFIC = {'cfg3': (76288, 'profiles/r02_v1_k_mc_uf_fast_summary.txt (one launch of 2^20 shots: the graph tables once per block; no per-shot HBM traffic)'),
+TRAFFIC = {'cfg3': (76288, 'profiles/r02_v3_k_mc_uf_fast_summary.txt (one launch of 2^20 shots: the graph tables once per block; no per-shot HBM traffic)'),
            'cfg3-macar': (89856, 'profiles/r01_k_mc_ca_macar_summary.txt'),
            'cfg4': (145920, 'profiles/r01_k_sf_mc_acp_summary.txt (warp tile; the block tile reads the same tables)')}
 

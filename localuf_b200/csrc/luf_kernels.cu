@@ -2299,7 +2299,7 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                         // (the replay of a shot is one dependent chain: as many resident warps as shared memory allows)
                         {
                             if (int rc = raise_smem_limit(g->device, g->max_smem, k_hard_resolve)) return rc;
-                            const int rwpb = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)g->max_smem / resolve_warp));
+                            const int rwpb = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)g->max_smem / resolve_warp));
                             const size_t rsmem = (size_t)rwpb * resolve_warp;
                             const long long per_sm = std::max<long long>(1, std::min<long long>(64 / rwpb, (long long)(228 * 1024) / (long long)(rsmem + 1024)));
                             k_hard_resolve<<<(int)(g->sm_count * per_sm), rwpb * WARP, rsmem, (cudaStream_t)stream>>>(g->fview.D, la.x, counts_dev, lg);
