@@ -2252,7 +2252,7 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                 uint32_t* queue = nullptr;
                 if (int rc = fast_queue(g, stream, &queue)) return rc;
                 // Q1: the HARD shots of the first pass; Q3: those the second pass could not log (canonical launch);
-                // Q2: (shot, offset) of the exported ones; counters: |Q1|, |Q3|, |Q2|, export cursor
+                // Q2: (shot, offset) of the exported ones; counters: |Q1|, |Q3|, |Q2|, -, export cursor (64 bits)
                 uint32_t* cnt = queue + FAST_CHUNK;
                 uint32_t* q3 = cnt + 16;
                 uint32_t* q2 = q3 + FAST_CHUNK;
@@ -2273,7 +2273,7 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                     uint8_t* lg = logical_dev ? logical_dev + done : nullptr;
                     fast::FView fv = g->fview;
                     fv.west = (flags & LUF_UF_WEST) ? 1 : 0;
-                    if (!fv.west) CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, (cudaStream_t)stream));
+                    if (!fv.west) CUDA_TRY(cudaMemsetAsync(cnt, 0, 32, (cudaStream_t)stream));
                     // LUF_DEBUG_TIMES=1: CUDA events around the launches of a chunk (measurements; synchronises)
                     const bool env_times = getenv("LUF_DEBUG_TIMES") && atoi(getenv("LUF_DEBUG_TIMES")) != 0;
                     cudaEvent_t ev[5] = {0, 0, 0, 0, 0};
@@ -2286,11 +2286,12 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                     uint32_t *cq = queue, *cqc = qcount;         // what the canonical launch takes
                     if (log_pass) {
                         // export buffer: 64 words per shot of the chunk, between 2^22 and 2^27 (a shot that finds no room goes to Q3)
-                        const size_t xcap = (size_t)std::min<long long>(1ll << 27, std::max<long long>(1ll << 22, (long long)m * 64));
+                        size_t xcap = (size_t)std::min<long long>(1ll << 27, std::max<long long>(1ll << 22, (long long)m * 64));
+                        if (getenv("LUF_FAST_XCAP_WORDS")) xcap = (size_t)std::max(64, atoi(getenv("LUF_FAST_XCAP_WORDS")));     // (tests: the no-room path)
                         void* xbuf = nullptr;
                         if (int rc = wide_slab(g, stream, 4, xcap * 4, &xbuf)) return rc;
                         FastLogArgs la;
-                        la.x.buf = (uint32_t*)xbuf; la.x.cursor = cnt + 3; la.x.cap = (uint32_t)xcap;
+                        la.x.buf = (uint32_t*)xbuf; la.x.cursor = (uint64_t*)(cnt + 4); la.x.cap = (uint32_t)xcap;
                         la.x.queue = q2; la.x.qcount = cnt + 2;
                         la.qin = queue; la.qin_count = cnt;
                         if (int rc = fast_launch(g, fv, plan2, fl2, sp, first, m, counts_dev, lg, q3, cnt + 1, (cudaStream_t)stream, &la)) return rc;
@@ -2331,11 +2332,11 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                         else fprintf(stderr, "[luf] chunk of %lld shots: first pass %.3f ms, canonical launch %.3f ms\n", m, t[0], t[1]);
                     }
                     if (!fv.west && getenv("LUF_DEBUG_PLAN")) {
-                        uint32_t h[4];
-                        CUDA_TRY(cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+                        uint32_t h[6];
+                        CUDA_TRY(cudaMemcpyAsync(h, cnt, 24, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
                         CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-                        fprintf(stderr, "[luf] HARD shots of %lld: %u queued by the first pass, %u exported for hard_resolve (%u words), %u left to the canonical launch\n",
-                                m, h[0], h[2], h[3], log_pass ? h[1] : h[0]);
+                        fprintf(stderr, "[luf] HARD shots of %lld: %u queued by the first pass, %u exported for hard_resolve (%llu words), %u left to the canonical launch\n",
+                                m, h[0], h[2], (unsigned long long)h[4] | ((unsigned long long)h[5] << 32), log_pass ? h[1] : h[0]);
                     }
                 }
                 return 0;

@@ -60,7 +60,7 @@ static const uint32_t KEY_EDGE_BITS = 20u, KEY_EDGE_MASK = 0xFFFFFu;      // mer
 // reserved with one atomic add on *cursor; (shot, offset) pairs in `queue`, *qcount of them.
 struct FExport {
     uint32_t* buf;
-    uint32_t* cursor;
+    uint64_t* cursor;           // (64 bits: reservations that find no room still add to it)
     uint32_t cap;               // words of buf
     uint32_t* queue;            // [2 * shots of the launch]
     uint32_t* qcount;
@@ -544,9 +544,9 @@ LUF_DEV void r_sort_step(uint32_t* key, uint32_t np, uint32_t k, uint32_t j, int
 LUF_DEV void f_export_reserve(const FShot& s, const FExport& x, uint32_t fast_bit)
 {
     const uint32_t n = s.cnt[C_XCOUNT];
-    uint32_t base = luf_atomic_add(x.cursor, n + 1u);
-    if (base + n + 1u > x.cap || base + n + 1u < base) base = 0xFFFFFFFFu;
-    else x.buf[base] = n | (fast_bit << 31);
+    const uint64_t at = luf_atomic_add(x.cursor, (uint64_t)n + 1u);
+    uint32_t base = 0xFFFFFFFFu;
+    if (at + n + 1u <= (uint64_t)x.cap) { base = (uint32_t)at; x.buf[base] = n | (fast_bit << 31); }
     s.cnt[C_XBASE] = base;
 }
 

@@ -408,7 +408,8 @@ int emu_mc_uf_compact_log(const luf_graph_desc* d, const double* class_p, unsign
     std::vector<unsigned char> mem(l.bytes + 16);
     const fast::FShot s = fast::fbind(l, mem.data());
     std::vector<uint32_t> xbuf((size_t)pf.E + 8), S(pf.D, 0xDEADBEEFu);
-    uint32_t cursor = 0, q[2], qn = 0, res = 0;
+    uint64_t cursor = 0;
+    uint32_t q[2], qn = 0, res = 0;
     for (long long k = 0; k < nshots; ++k) {
         cursor = 0;
         fast::FExport x{xbuf.data(), &cursor, (uint32_t)xbuf.size(), q, &qn};

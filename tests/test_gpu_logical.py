@@ -171,3 +171,30 @@ def test_logical_frames_only(spec, p):
     ocorr, _, _ = orc.decode_batch(0, 0, syn[:500], want_growth=False)
     frame = eng.decode_frames_host(_engine.DEC_UF, 0, syn[:500])
     np.testing.assert_array_equal(frame ^ orc.logical_batch(err[:500], np.zeros_like(ocorr)), orc.logical_batch(err[:500], ocorr))
+
+
+@pytest.mark.parametrize('spec,p,n', [
+    (dict(code='Surface', d=9, noise='phenomenological'), 0.03, 6000),
+    (dict(code='Surface', d=5, noise='circuit-level'), 0.03, 6000),
+    (dict(code='Surface', d=17, noise='phenomenological'), 0.027, 1500),
+])
+def test_hard_shots_every_route_gives_the_same_bits(spec, p, n, monkeypatch):
+    """Shots with an odd cluster on both sides (default inclination): merge-log pass + k_hard_resolve, the same with
+    an export buffer that holds only a few shots (the rest falls back to the canonical launch), and the canonical
+    launch alone -- per-shot bits equal to the oracle's on every route."""
+    from localuf_b200 import _engine
+    code = make_code(spec)
+    eng = _engine.Engine(code, device=0)
+    orc = binding.Oracle.from_code(code)
+    err, syn = eng.sample_host(p, 13, 50, n)
+    ocorr, _, _ = orc.decode_batch(0, 0, syn, want_growth=False)
+    want = orc.logical_batch(err, ocorr)
+    for env in ({}, {'LUF_FAST_XCAP_WORDS': '3000'}, {'LUF_FAST_LOG': '0'}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng2 = _engine.Engine(code, device=0)
+        logical, fails, shots = eng2.mc_logical_host(_engine.DEC_UF, 0, p, 13, 50, n)
+        np.testing.assert_array_equal(logical, want)
+        assert (fails, shots) == (int(want.sum()), n)
+        for k in env:
+            monkeypatch.delenv(k)
