@@ -43,6 +43,7 @@ struct CaView {
     const uint8_t* span;        // [N]   Actis per-node countdown start (luf/main.py:970-976)
     const uint16_t* relay;      // [N]   Actis neighbour towards node 0 (luf/main.py:1138-1163); 0xFFFF = controller
     int global_span;            // luf/main.py:517-523
+    int nbr_shared;             // nbr points at a copy in shared memory (k_mc_ca_tiles): plain loads instead of ld.global.nc
 };
 
 struct CaLayout {
@@ -97,6 +98,7 @@ struct CaCtl {
 };
 static const int CA_MAX_STEPS = 1 << 20;    // safety net: a shot that runs this long is reported with steps = -1
 
+LUF_DEV uint32_t ca_nbr(const CaView& g, int idx) { return g.nbr_shared ? g.nbr[idx] : LUF_LDG(&g.nbr[idx]); }
 LUF_DEV uint32_t g2(const uint32_t* a, uint32_t e) { return (a[e >> 4] >> ((e & 15u) * 2u)) & 3u; }
 // access mask | pointer << 12; written by the node's own lane only
 LUF_DEV uint32_t ca_ptr(const CaShot& s, int v) { return (uint32_t)s.acp[v] >> 12; }
@@ -148,7 +150,7 @@ LUF_DEV void ca_growing(const CaView& g, const CaShot& s, int v)
     if (!(s.fl[v] & FL_ACTIVE)) return;
     LUF_NOUNROLL_CA
     for (int k = 0; k < g.K; ++k) {
-        const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
+        const uint32_t ent = ca_nbr(g, v * g.K + k);
         if (ent == NBR_NONE) continue;
         const uint32_t e = ent & 0xFFFFu, sh = (e & 15u) * 2u;
         if (((s.growth[e >> 4] >> sh) & 3u) >= G_FULL) continue;
@@ -218,7 +220,7 @@ LUF_DEV uint32_t ca_merging(const CaView& g, const CaShot& s, int v)
     uint32_t fl = s.fl[v] & ~(uint32_t)FL_BUSY, ptr = ca_ptr(s, v), busy = 0;
     if (v >= g.B && ptr != PTR_C && (fl & FL_ANYON)) {             // relay the anyon along the pointer
         busy = 1;
-        const uint32_t to = LUF_LDG(&g.nbr[v * g.K + ptr]) >> 16;
+        const uint32_t to = ca_nbr(g, v * g.K + ptr) >> 16;
         luf_atomic_xor(&s.rx_anyon[to >> 5], 1u << (to & 31u));
         fl &= ~(uint32_t)FL_ANYON;
     }
@@ -226,7 +228,7 @@ LUF_DEV uint32_t ca_merging(const CaView& g, const CaShot& s, int v)
     LUF_NOUNROLL_CA
     for (uint32_t slots = access; slots; slots &= slots - 1u) {      // ascending slot = the scan order
         const int k = luf_ffs(slots) - 1;
-        const uint32_t c = s.cid[LUF_LDG(&g.nbr[v * g.K + k]) >> 16];
+        const uint32_t c = s.cid[ca_nbr(g, v * g.K + k) >> 16];
         if (c < best) { best = c; ptr = (uint32_t)k; busy = 1; }
     }
     s.ncid[v] = (uint16_t)best; s.acp[v] = (uint16_t)(access | (ptr << 12));
@@ -251,7 +253,7 @@ LUF_DEV uint32_t ca_syncing(const CaView& g, const CaShot& s, int v)
     if (!(fl & FL_ACTIVE))
         LUF_NOUNROLL_CA
         for (uint32_t slots = ca_access(s, v); slots; slots &= slots - 1u) {
-            const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + luf_ffs(slots) - 1]);
+            const uint32_t ent = ca_nbr(g, v * g.K + luf_ffs(slots) - 1);
             if (s.fl[ent >> 16] & FL_ACTIVE) { busy = 1; break; }
         }
     s.fl[v] = (uint8_t)(fl | (busy ? FL_BUSY : 0));
@@ -264,7 +266,7 @@ LUF_DEV void ca_burning(const CaView& g, const CaShot& s, int v)
     const uint32_t ptr = ca_ptr(s, v);
     LUF_NOUNROLL_CA
     for (int k = g.K >> 1; k < g.K; ++k) {                          // owned edges
-        const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
+        const uint32_t ent = ca_nbr(g, v * g.K + k);
         if (ent == NBR_NONE) continue;
         const uint32_t e = ent & 0xFFFFu;
         if (g2(s.growth, e) == G_FULL && ptr != (uint32_t)k && ca_ptr(s, (int)(ent >> 16)) != (uint32_t)(g.K - 1 - k))
@@ -280,7 +282,7 @@ LUF_DEV uint32_t ca_peeling(const CaView& g, const CaShot& s, int v)
     if (ca_ptr(s, v) != PTR_C) {
         const uint32_t access = ca_access(s, v);
         if (access && !(access & (access - 1u))) {                  // exactly one way out: a leaf
-            const uint32_t only = LUF_LDG(&g.nbr[v * g.K + luf_ffs(access) - 1]);
+            const uint32_t only = ca_nbr(g, v * g.K + luf_ffs(access) - 1);
             const uint32_t e = only & 0xFFFFu, to = only >> 16;
             fl |= FL_BUSY; out = 1;
             luf_atomic_and(&s.growth[e >> 4], ~(3u << ((e & 15u) * 2u)));
@@ -373,7 +375,7 @@ LUF_DEV void ca_snapshot_access(const CaView& g, const CaShot& s, int lane, int 
         uint32_t access = 0;
         LUF_NOUNROLL_CA
         for (int k = 0; k < g.K; ++k) {
-            const uint32_t ent = LUF_LDG(&g.nbr[v * g.K + k]);
+            const uint32_t ent = ca_nbr(g, v * g.K + k);
             if (ent != NBR_NONE && g2(s.growth, ent & 0xFFFFu) == G_FULL) access |= 1u << k;
         }
         s.acp[v] = (uint16_t)((s.acp[v] & 0xF000u) | access);
@@ -483,8 +485,29 @@ namespace luf { using namespace ca_warp; }
 #else
   #define LUF_CT_PHASE(stmt) { stmt; } __syncthreads();
   #define LUF_CT_ANY(x) __syncthreads_or((x) != 0)
+  #define LUF_CT_SYNC() __syncthreads()
+  #define LUF_CT_WORD_VOTES 1
 #endif
 #include "luf_ca_drivers.inl"
 #undef LUF_CA_NS
 #undef LUF_CT_PHASE
 #undef LUF_CT_ANY
+#undef LUF_CT_SYNC
+#undef LUF_CT_WORD_VOTES
+
+// Tile = nl threads (a multiple of 32) of a block that holds several shots next to one copy of the neighbour
+// table (k_mc_ca_tiles): named barrier 1 + threadIdx.x / nl.  Macar only (its votes go through a word of the
+// shot's state, LUF_CT_WORD_VOTES); device only.
+#if !defined(LUF_HOST_EMU)
+#define LUF_CA_NS ca_tile
+#define LUF_CT_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1u + threadIdx.x / (unsigned)nl), "r"(nl) : "memory")
+#define LUF_CT_PHASE(stmt) { stmt; } LUF_CT_SYNC();
+#define LUF_CT_ANY(x) ((x) != 0)          /* (only on the Actis path, which this tile does not run) */
+#define LUF_CT_WORD_VOTES 1
+#include "luf_ca_drivers.inl"
+#undef LUF_CA_NS
+#undef LUF_CT_PHASE
+#undef LUF_CT_ANY
+#undef LUF_CT_SYNC
+#undef LUF_CT_WORD_VOTES
+#endif

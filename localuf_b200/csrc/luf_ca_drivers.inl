@@ -39,10 +39,26 @@ LUF_DEV uint32_t ca_decode(const CaView& g, const CaShot& s, int flags, int* t_s
             c.n_active_signal = c.n_next_active_signal;
             busy = c.n_busy; valid = c.n_valid;
         } else {
+#if defined(LUF_CT_WORD_VOTES)
+            // Multi-warp tiles: the two votes of a timestep (any busy, any invalid) are one OR into a word of the
+            // shot's state -- glob[0] / glob[1] in turns (Actis's inbox, idle under Macar), the next one cleared by
+            // lane 0 while this one is filled -- so that a timestep costs two tile barriers instead of four.
+            uint32_t* vote = &s.glob[c.step & 1];
+            LUF_CT_PHASE(parity ^= macar_phase_a(g, s, c.stage, lane, nl));
+            {
+                const uint32_t mine = macar_phase_b(g, s, c.stage, lane, nl);
+                if (mine) luf_atomic_or(vote, mine);
+                if (lane == 0) s.glob[(c.step + 1) & 1] = 0u;
+            }
+            LUF_CT_SYNC();
+            const uint32_t acc = *vote;
+            busy = (acc & 1u) != 0; valid = !(acc & 2u);
+#else
             uint32_t acc = 0;
             LUF_CT_PHASE(parity ^= macar_phase_a(g, s, c.stage, lane, nl));
             LUF_CT_PHASE(acc |= macar_phase_b(g, s, c.stage, lane, nl));
             busy = LUF_CT_ANY(acc & 1u); valid = !LUF_CT_ANY(acc & 2u);
+#endif
         }
         const int growth_changed = ca_controller_advance(c, busy, valid);
         if (grew) {                                                      // newly touched nodes join the list

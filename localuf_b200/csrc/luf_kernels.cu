@@ -47,6 +47,7 @@ static int fail(int code, const std::string& msg)
 
 // ------------------------------------------------------------------ kernels
 static const int WARP = 32;
+#define LUF_TILE_SYNC(tile, tw) asm volatile("bar.sync %0, %1;" ::"r"(1u + (unsigned)(tile)), "r"(tw) : "memory")
 
 __device__ __forceinline__ unsigned char* warp_slice(const Layout& l)
 {
@@ -393,6 +394,54 @@ __global__ void k_mc_ca_cta(GraphView gv, CaView g, CaLayout l, SampleParams sp,
         int tsv, tbp;
         parity ^= ca_cta::ca_decode<ACTIS>(g, s, flags, &tsv, &tbp, nullptr, lane, nl);
         const unsigned int bit = (unsigned int)__syncthreads_count((int)(parity & 1u)) & 1u;
+        fails += bit;
+        if (logical && lane == 0) logical[k] = (uint8_t)bit;
+        sum_sv += (unsigned long long)tsv; sum_bp += (unsigned long long)tbp;
+    }
+    if (lane == 0) {
+        if (fails) atomicAdd(&counts[0], (unsigned long long)fails);
+        atomicAdd(&counts[2], sum_sv); atomicAdd(&counts[3], sum_bp);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+}
+
+// Macar, several shots per block next to ONE copy of the neighbour table in shared memory (35 KB for cfg3: in
+// global memory it hit L1 55 % of the time under the shot states, ncu r01 v13: long-scoreboard stalls 4.6 per
+// issue).  A tile of `tw` threads per shot, named barrier 1 + tile (luf::ca_tile); the first warp of a tile samples.
+__global__ void __launch_bounds__(1024, 1) k_mc_ca_tiles(GraphView gv, CaView g, CaLayout l, uint32_t table_bytes, int tw, SampleParams sp, int flags,
+                              unsigned long long shot0, long long nshots, unsigned long long* counts,
+                              uint8_t* __restrict__ logical)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    {
+        const uint4* src = (const uint4*)g.nbr;
+        uint4* dst = (uint4*)smem;
+        for (uint32_t i = threadIdx.x; i < table_bytes / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+        g.nbr = (const uint32_t*)smem; g.nbr_shared = 1;
+    }
+    const int tile = (int)threadIdx.x / tw, lane = (int)threadIdx.x % tw, nl = tw, tpb = (int)blockDim.x / tw;
+    const CaShot s = ca_bind(l, smem + table_bytes + (size_t)tile * l.bytes);
+    Shot samp;
+    samp.err = nullptr; samp.defect = s.defect;
+    unsigned int fails = 0;
+    unsigned long long sum_sv = 0, sum_bp = 0;
+    uint32_t* red = s.glob + 3;                      // the tile's parity word (idle under Macar)
+    for (long long k = (long long)blockIdx.x * tpb + tile; k < nshots; k += (long long)gridDim.x * tpb) {
+        uint32_t parity = 0;
+        ca_reset<false>(g, s, lane, nl);
+        LUF_TILE_SYNC(tile, tw);
+        if (lane < 32) parity ^= ph_sample(gv, samp, sp, shot0 + (unsigned long long)k, lane, 32);
+        LUF_TILE_SYNC(tile, tw);
+        ca_load(g, s, lane, nl);
+        LUF_TILE_SYNC(tile, tw);
+        int tsv, tbp;
+        parity ^= ca_tile::ca_decode<false>(g, s, flags, &tsv, &tbp, nullptr, lane, nl);
+        parity = __reduce_xor_sync(0xffffffffu, parity & 1u);
+        if ((lane & 31) == 0 && parity) atomicXor(red, 1u);
+        LUF_TILE_SYNC(tile, tw);
+        const unsigned int bit = *red & 1u;
+        LUF_TILE_SYNC(tile, tw);                     // (ca_reset clears the word for the next shot)
         fails += bit;
         if (logical && lane == 0) logical[k] = (uint8_t)bit;
         sum_sv += (unsigned long long)tsv; sum_bp += (unsigned long long)tbp;
@@ -2206,6 +2255,31 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
     const SampleParams sp = make_sample_params(class_p_host, g->view.n_classes, seed);
     LaunchCfg c;
     if (decoder == LUF_DEC_MACAR) {
+        // several shots per block around one copy of the neighbour table in shared memory, when it leaves room for at
+        // least half the shots that would be resident without it (LUF_CA_TILES=0: the one-shot blocks)
+        static const bool env_tiles = !(getenv("LUF_CA_TILES") && atoi(getenv("LUF_CA_TILES")) == 0);
+        const uint32_t table_bytes = align16((uint32_t)g->ca_host.nbr.size() * 4u);
+        const uint32_t shot_bytes = g->lay_macar_cta.bytes;
+        if (env_tiles && use_ca_cta(g, false) && (size_t)table_bytes + 2 * (size_t)shot_bytes <= (size_t)g->max_smem) {
+            int tw = ((g->ca_view.N / 16) + 31) & ~31;
+            tw = std::max(64, std::min(256, tw));
+            if (getenv("LUF_CA_TILE_TW")) tw = std::max(32, std::min(256, atoi(getenv("LUF_CA_TILE_TW")) & ~31));
+            int tiles = (int)(((size_t)g->max_smem - table_bytes) / shot_bytes);
+            tiles = std::min(tiles, std::min(15, 1024 / tw));
+            const int without = (int)std::min<size_t>(2048 / tw, (size_t)(228 * 1024) / (shot_bytes + 1024));
+            if (tiles >= 8 && tiles * 3 >= without * 2) {       // (d = 17: 2 shots next to a 132 KB table lose to 4 without it)
+                if (int rc = raise_smem_limit(g->device, g->max_smem, k_mc_ca_tiles)) return rc;
+                const size_t smem = (size_t)table_bytes + (size_t)tiles * shot_bytes;
+                long long blocks = std::min<long long>(g->sm_count, (nshots + tiles - 1) / tiles);
+                if (getenv("LUF_DEBUG_PLAN"))
+                    fprintf(stderr, "[luf] Macar plan: %d shots of %d threads per block around the neighbour table (%u B), %zu B of shared memory\n", tiles, tw, table_bytes, smem);
+                k_mc_ca_tiles<<<(int)blocks, tiles * tw, smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_macar_cta, table_bytes, tw, sp, flags,
+                                                                                      shot0, nshots, counts_dev, logical_dev);
+                CUDA_TRY(cudaGetLastError());
+                ++g->launches;
+                return 0;
+            }
+        }
         if (use_ca_cta(g, false)) {
             if (int rc = plan_ca_cta_launch(g, k_mc_ca_cta<false>, g->lay_macar_cta.bytes, nshots, &c, g->ca_view.N / 16)) return rc;
             k_mc_ca_cta<false><<<c.grid, c.block, c.smem, (cudaStream_t)stream>>>(g->view, g->ca_view, g->lay_macar_cta, sp, flags,

@@ -463,7 +463,7 @@ int emu_decode_ca_tile(const luf_graph_desc* d, int decoder, int flags, long lon
     g.N = p.N; g.B = p.B; g.E = p.E; g.K = p.K;
     g.WE = words32(p.E); g.WD = words32(p.N - p.B); g.WN = words32(p.N); g.GW = (p.E + 15) / 16;
     g.nbr = p.nbr.data(); g.west_mask = west.data(); g.span = p.span.data(); g.relay = p.relay.data();
-    g.global_span = p.global_span;
+    g.global_span = p.global_span; g.nbr_shared = 0;
     const CaLayout l = cta ? make_ca_layout(p.N, p.B, p.E, actis, false, CA_CTA_TLIST_CAP) : make_ca_layout(p.N, p.B, p.E, actis, false);
     std::vector<unsigned char> mem(l.bytes);
     const CaShot s = ca_bind(l, mem.data());
@@ -519,7 +519,7 @@ int emu_fw_stream(const luf_graph_desc* gd, const luf_forward_desc* fd, int deco
         cv.N = pc.N; cv.B = pc.B; cv.E = pc.E; cv.K = pc.K;
         cv.WE = words32(pc.E); cv.WD = words32(pc.N - pc.B); cv.WN = words32(pc.N); cv.GW = (pc.E + 15) / 16;
         cv.nbr = pc.nbr.data(); cv.west_mask = west.data(); cv.span = pc.span.data(); cv.relay = pc.relay.data();
-        cv.global_span = pc.global_span;
+        cv.global_span = pc.global_span; cv.nbr_shared = 0;
         const CaLayout cl = make_ca_layout(pc.N, pc.B, pc.E, false, true);
         const FwLayout fl = make_fw_layout(pg.N, pg.E, cl.bytes);
         std::vector<unsigned char> mem(fl.bytes);
