@@ -94,7 +94,14 @@ const char *luf_last_error(void);
 int luf_device_count(void);
 
 /* Upload a graph to `device`.  Replaces Code.__init__ (localuf/_base_classes.py:23-175)
- * as far as the device is concerned; the host object is built by localuf_b200.codes. */
+ * as far as the device is concerned; the host object is built by localuf_b200.codes.
+ * Any size the 32-bit fields above can name: graphs of up to 32767 nodes and 65533 edges
+ * keep a shot's decoder state in 16-bit indices in shared memory; larger ones (Surface(23 | 25,
+ * 'circuit-level'), localuf/codes.py:155-251; global-batch windows of d * n layers,
+ * localuf/_schemes.py:166-191; forward windows of large codes) run the same UF entry points
+ * through a wide instance of the kernels (64-bit node words; the state in shared memory or
+ * in an L2-resident slab of global memory).  Macar / Actis answer LUF_ERR_UNSUPPORTED beyond
+ * 65534 nodes or edges. */
 int luf_graph_create(const luf_graph_desc *desc, int device, luf_graph **out);
 int luf_graph_destroy(luf_graph *g);
 
