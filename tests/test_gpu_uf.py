@@ -243,3 +243,28 @@ def test_graphs_beyond_the_16bit_layout_run_on_the_wide_instance():
     err, syn = eng.sample_host(0.005, 1, 0, 4)
     corr, _, _ = eng.decode_batch_host(_engine.DEC_UF, 0, syn)
     assert corr.shape == err.shape
+
+
+def test_sampler_groups_of_four_and_unaligned_buffers():
+    """k_sample takes four shots per warp with 16-byte stores when the buffers allow: any shot count, any shot
+    offset and buffers that are only 4-byte aligned give the rows of one big aligned run."""
+    import torch
+    from localuf_b200 import _engine
+    code = make_code(dict(code='Surface', d=7, noise='phenomenological'))        # W(E) = 29, W(D) = 10: rows of 116 / 40 bytes
+    eng = engine_of(code)
+    p, seed = 0.03, 17
+    err, syn = eng.sample_host(p, seed, 0, 1001)
+    for shot0, n in ((0, 1), (3, 2), (5, 3), (6, 5), (997, 4), (10, 7)):
+        e, s = eng.sample_host(p, seed, shot0, n)
+        np.testing.assert_array_equal(e, err[shot0:shot0 + n])
+        np.testing.assert_array_equal(s, syn[shot0:shot0 + n])
+    dev = torch.device('cuda', 0)
+    n = 37
+    ebuf = torch.zeros(n * eng.WE + 1, dtype=torch.int32, device=dev)
+    sbuf = torch.zeros(n * eng.WD + 3, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        eng.sample(p, seed, 100, n, ebuf[1:], sbuf[3:])                          # 4-byte aligned only
+        torch.cuda.synchronize()
+    np.testing.assert_array_equal(ebuf[1:].cpu().numpy().view(np.uint32).reshape(n, eng.WE), err[100:100 + n])
+    np.testing.assert_array_equal(sbuf[3:].cpu().numpy().view(np.uint32).reshape(n, eng.WD), syn[100:100 + n])
+    assert int(ebuf[0]) == 0 and not sbuf[:3].any()
