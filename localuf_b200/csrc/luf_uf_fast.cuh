@@ -528,6 +528,18 @@ LUF_DEV void f_export_mark(const FView& g, const FShot& s, uint32_t ntot, uint32
     if (c) luf_atomic_add(&s.cnt[C_XCOUNT], c);
 }
 
+// The same when the log fills at most half of its array: the entries of the HARD clusters are gathered into the
+// upper half (C_XCOUNT hands out the places), so that the network sorts them alone and not the whole log.
+LUF_DEV void f_export_gather(const FView& g, const FLayout& l, const FShot& s, uint32_t ntot, int lane, int nl)
+{
+    uint32_t* dst = s.elog + (l.lcap >> 1);
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < ntot; i += (uint32_t)nl) {
+        const uint32_t key = s.elog[i];
+        if (f_in_hard_cluster(g, s, key)) dst[luf_atomic_add(&s.cnt[C_XCOUNT], 1u)] = key;
+    }
+}
+
 // ... sorted by (round, edge id) in place, a bitonic network over the tile's lanes ...
 LUF_DEV void r_sort_step(uint32_t* key, uint32_t np, uint32_t k, uint32_t j, int lane, int nl)
 {
@@ -552,11 +564,11 @@ LUF_DEV void f_export_reserve(const FShot& s, const FExport& x, uint32_t fast_bi
 
 // ... and the edges go out in canonical order as endpoint pairs (first end | second end << 16: hard_resolve needs
 // no table).
-LUF_DEV void f_export_write(const FView& g, const FShot& s, const FExport& x, int lane, int nl)
+LUF_DEV void f_export_write(const FView& g, const FShot& s, const uint32_t* sorted, const FExport& x, int lane, int nl)
 {
     const uint32_t base = s.cnt[C_XBASE], n = s.cnt[C_XCOUNT];
     LUF_NOUNROLL
-    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) x.buf[base + 1u + i] = LUF_LDG(&g.einfo[s.elog[i] & KEY_EDGE_MASK]);
+    for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) x.buf[base + 1u + i] = LUF_LDG(&g.einfo[sorted[i] & KEY_EDGE_MASK]);
 }
 
 // hard_resolve's node words (one per detector, in the warp's shared memory): root = R_ROOT | kept side << 28 |
@@ -692,16 +704,25 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
             const uint32_t ntot = s.cnt[C_MLIST];
             if (!x || !x->buf || !l.lcap || ntot > l.lcap) return HARD;           // no log, or it could not hold the shot's merges
             uint32_t np = 1;
-            while (np < ntot) np <<= 1;                  // (lcap is a power of two)
-            FT_PHASE(f_export_mark(g, s, ntot, np, lane, nl));
+            uint32_t* sorted = s.elog;
+            if (2u * ntot <= l.lcap) {                   // room to gather the HARD clusters' entries apart: a smaller sort
+                sorted = s.elog + (l.lcap >> 1);
+                FT_PHASE(f_export_gather(g, l, s, ntot, lane, nl));
+                const uint32_t nh = s.cnt[C_XCOUNT];
+                while (np < nh) np <<= 1;
+                FT_PHASE(for (uint32_t i = nh + (uint32_t)lane; i < np; i += (uint32_t)nl) sorted[i] = 0xFFFFFFFFu);
+            } else {
+                while (np < ntot) np <<= 1;              // (lcap is a power of two)
+                FT_PHASE(f_export_mark(g, s, ntot, np, lane, nl));
+            }
             LUF_NOUNROLL
             for (uint32_t k = 2; k <= np; k <<= 1) {
                 LUF_NOUNROLL
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) { FT_PHASE(r_sort_step(s.elog, np, k, j, lane, nl)); }
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) { FT_PHASE(r_sort_step(sorted, np, k, j, lane, nl)); }
             }
             FT_PHASE(if (lane == 0) f_export_reserve(s, *x, s.cnt[C_PARITY] & 1u));
             if (s.cnt[C_XBASE] == 0xFFFFFFFFu) return HARD;
-            FT_PHASE(f_export_write(g, s, *x, lane, nl));
+            FT_PHASE(f_export_write(g, s, sorted, *x, lane, nl));
             return HARD_LOGGED;                          // the caller queues (shot, s.cnt[C_XBASE])
         }
     }

@@ -156,6 +156,12 @@ def test_hard_clusters_resolved_from_the_merge_log(spec, p, n):
     out = emu.mc_uf_compact_log(p, 11, 100, n, nl=32)
     np.testing.assert_array_equal(out[out != 2], want[out != 2])
     assert (out == 2).mean() <= 0.02 + 0.2 * hard.mean()
+    # logs between half full and full sort in place (no room to gather the HARD clusters' entries apart)
+    for lcap in (64, 256, 512):
+        out = emu.mc_uf_compact_log(p, 11, 100, n, nl=64, lcap=lcap)
+        np.testing.assert_array_equal(out[out != 2], want[out != 2])
+        entries = emu.last_log_entries
+        np.testing.assert_array_equal(out == 2, hard & (entries > lcap))
     # a starved log: every such shot falls back
     out = emu.mc_uf_compact_log(p, 11, 100, n, nl=32, lcap=1)
     np.testing.assert_array_equal(out == 2, hard)
