@@ -2,14 +2,17 @@
 // Union-Find decoding engine.  See include/luf_b200.h for the interface and
 // luf_core.cuh for the per-shot phases.
 //
-// Execution model: one warp owns one shot at a time; a block is a handful of
-// independent warps; the grid is persistent (a multiple of the SM count) and
-// every warp strides over the shot range.  All decoder state of a shot lives
-// in the warp's slice of dynamic shared memory; the read-only graph tables sit
-// in global memory and are served by L1/L2.  There is no tensor-core work in
-// this path (no dense contraction) and nothing to tile with TMA at these sizes:
-// HBM sees only the bit-packed inputs/outputs of the staged kernels, and
-// nothing at all in the fused Monte-Carlo kernel.
+// Execution model: a tile of lanes -- a warp, a part of a block on a named
+// barrier, or a whole block -- owns one shot at a time; the grid is persistent
+// (a multiple of the SM count) and the tiles stride over the shot range.  All
+// decoder state of a shot lives in the tile's slice of dynamic shared memory
+// (the wide instance may bind it to an L2-resident slab of global memory
+// instead); the read-only graph tables sit in global memory and are served by
+// L1/L2, or are staged once per block in shared memory (compact fast path,
+// Macar tiles).  There is no tensor-core work in this path (no dense
+// contraction) and nothing to tile with TMA: HBM sees only the bit-packed
+// inputs/outputs of the staged kernels, and nothing at all in the fused
+// Monte-Carlo kernels.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1165,7 +1168,7 @@ static int plan_launch(luf_graph* g, K kernel, uint32_t slice_bytes, long long n
     struct { uint32_t bytes; } l = {slice_bytes};
     if (l.bytes > (uint32_t)g->max_smem)
         return fail(LUF_ERR_UNSUPPORTED, "one shot's decoder state (" + std::to_string(l.bytes) +
-                    " B) exceeds the shared memory of an SM; CTA-per-shot kernels are not built yet");
+                    " B) exceeds the shared memory of an SM");
     // Tunables (for sweeps; the defaults are what bench.py measures):
     //   LUF_WARPS_PER_BLOCK  warps (= concurrent shots) per block
     //   LUF_SMEM_KB_PER_SM   shared-memory budget per SM for shot state; the
