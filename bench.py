@@ -316,6 +316,8 @@ DTYPE = 'u32 bit-packed / u16 indices'
 METRIC = {'shots/s': 'decoded shots/s', 'decoding cycles/s': 'decoding cycles/s'}
 DEFAULT_UNITS = {'cfg1': 1 << 26, 'cfg2': 1 << 24, 'cfg3': 1 << 22, 'cfg3-staged': 1 << 20, 'cfg3-macar': 1 << 19, 'cfg3-actis': 1 << 14,
                  'cfg4': 1 << 16, 'cfg5-d17': 1 << 17, 'cfg5-wide': 1 << 15}
+# warp-instructions per unit and lanes per instruction of the dominant kernel (ncu --set full of the same workload)
+ISSUE = {'cfg3': (3071.0, 15.04, 'profiles/r02_v3_k_mc_uf_fast_summary.txt (3.22 G warp-instructions per 2^20 shots)')}
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full; profiles/)
 TRAFFIC = {'cfg3': (76288, 'profiles/r02_v3_k_mc_uf_fast_summary.txt (one launch of 2^20 shots: the graph tables once per block; no per-shot HBM traffic)'),
            'cfg3-macar': (89856, 'profiles/r01_k_mc_ca_macar_summary.txt'),
@@ -501,6 +503,18 @@ def run_ours(args):
         kern_ms = statistics.mean(step_ms)
         achieved = bpu * units_per_step_gpu / (kern_ms / 1e3) / 1e9
         traffic, traffic_src = TRAFFIC.get(name, (None, None)) if p_over is None else (None, None)
+        # the ceiling that binds the fused UF kernel is the SMs' instruction issue rate, not HBM: warp-instructions per
+        # shot and lanes per instruction from the committed ncu capture of the same kernel and workload
+        issue = None
+        if name in ISSUE and p_over is None and OVERRIDE['p'] is None and OVERRIDE['d'] is None:
+            wi, lanes, src = ISSUE[name]
+            sm_count = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            mhz = (clocks.summary() or {}).get('sm_mhz') or 1965.0
+            peak_wi = sm_count * 4 * mhz * 1e6                       # four schedulers per SM, one warp-instruction per cycle each
+            ach_wi = wi * units_per_step_gpu / (kern_ms / 1e3)
+            issue = {'unit': 'warp-instructions/s', 'achieved': ach_wi, 'peak': peak_wi, 'frac': ach_wi / peak_wi,
+                     'warp_instructions_per_unit': wi, 'lanes_per_instruction': lanes,
+                     'thread_instruction_frac': ach_wi / peak_wi * lanes / 32.0, 'source': src}
         r = {
             'metric': METRIC[unit], 'value': value, 'unit': unit, 'n_gpus': world,
             'steps': steps, 'warmup': warmup, 'ms_per_step': total_ms / steps,
@@ -516,7 +530,8 @@ def run_ours(args):
                          'algorithmic_bytes_per_unit': bpu, 'peak_source': peak_src,
                          'note': 'the fused kernels keep a shot in shared memory, so the HBM fraction is low by '
                                  'construction (SURVEY 8d): they are bound by shared-memory latency and issue slots '
-                                 '(profiles/)'},
+                                 '(profiles/)',
+                         'issue_slots': issue},
             'e2e': {'value': e2e_value, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 32,
                     'api': api, 'failures': m_e2e},
             'e2e_host_buffers': e2e_host,
