@@ -131,11 +131,15 @@ struct TileSync {
 // (48 registers: two blocks of 640 threads -- five shots of 128 lanes, the d = 17 plan -- have to fit an SM's register
 // file, which is allocated in units of 8 per thread: with 50 the second block did not, 10.4 -> 6.2 M shots/s there;
 // the warp tile of cfg3 is 8 % slower when capped -- 38 registers instead of 46 -- and keeps the 64 of its launch shape)
-template <int TW, bool ADJ_SHARED, bool LOGQ>
+// LOGQ = 2: one pass -- every shot keeps its merge log in a slab of global memory (`glog`, lcap words per resident
+// tile: written once per newly FULL edge, never read unless the shot turns out HARD); a HARD shot exports the keys
+// of its clusters as they lie, k_hard_sort orders them.  Chosen at noise levels where HARD shots are common.
+template <int TW, bool ADJ_SHARED, int LOGQ>
 __global__ void __maxnreg__(TW >= 64 ? 48 : 64) k_mc_uf_fast(fast::FView g, fast::FLayout l, uint32_t adj_bytes, SampleParams sp,
                         unsigned long long shot0, long long nshots, unsigned long long* counts,
                         uint8_t* __restrict__ logical, uint32_t* __restrict__ queue, uint32_t* __restrict__ qcount,
-                        fast::FExport x, const uint32_t* __restrict__ qin, const uint32_t* __restrict__ qin_count)
+                        fast::FExport x, const uint32_t* __restrict__ qin, const uint32_t* __restrict__ qin_count,
+                        uint32_t* __restrict__ glog)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     if (ADJ_SHARED) {
@@ -146,14 +150,15 @@ __global__ void __maxnreg__(TW >= 64 ? 48 : 64) k_mc_uf_fast(fast::FView g, fast
         g.fadj = (const uint32_t*)smem;
     }
     const int tile = (int)threadIdx.x / TW, lane = (int)threadIdx.x % TW, tpb = (int)blockDim.x / TW;
-    const fast::FShot s = fast::fbind(l, smem + adj_bytes + (size_t)tile * l.bytes);
+    fast::FShot s = fast::fbind(l, smem + adj_bytes + (size_t)tile * l.bytes);
+    if (LOGQ == 2) s.elog = glog + ((size_t)blockIdx.x * tpb + tile) * (size_t)l.lcap;
     TileSync<TW> sync;
     if (TW <= 32) sync.x = TW == 32 ? 0xffffffffu : ((1u << (TW & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TW - 1));
     else sync.x = tpb == 1 ? 0u : (uint32_t)(1 + tile);
     unsigned int fails = 0;
-    if (LOGQ) nshots = (long long)*qin_count;
+    if (LOGQ == 1) nshots = (long long)*qin_count;
     for (long long i = (long long)blockIdx.x * tpb + tile; i < nshots; i += (long long)gridDim.x * tpb) {
-        const long long k = LOGQ ? (long long)qin[i] : i;
+        const long long k = LOGQ == 1 ? (long long)qin[i] : i;
         const uint32_t r = fast::fast_shot<ADJ_SHARED>(g, l, s, sp, shot0 + (unsigned long long)k, lane, TW, sync, nullptr,
                                                        LOGQ ? &x : nullptr);
         if (lane == 0) {
@@ -165,7 +170,21 @@ __global__ void __maxnreg__(TW >= 64 ? 48 : 64) k_mc_uf_fast(fast::FView g, fast
         }
     }
     if (lane == 0 && fails) atomicAdd(&counts[0], (unsigned long long)fails);
-    if (!LOGQ && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+    if (LOGQ != 1 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counts[1], (unsigned long long)nshots);
+}
+
+// One-pass mode: the exported keys of every queued shot, sorted in place into endpoint pairs (fast::hard_sort).
+// One block per shot at a time; shared memory: keycap words.
+__global__ void __launch_bounds__(256) k_hard_sort(fast::FView g, fast::FExport x)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    TileSync<256> sync;
+    sync.x = 0u;
+    const uint32_t n = *x.qcount;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        fast::hard_sort(g, x.buf + x.queue[2u * i + 1u], (uint32_t*)smem, (int)threadIdx.x, 256, sync);
+        __syncthreads();
+    }
 }
 
 // The exported HARD clusters of a launch: one warp per shot replays the shot's unions (fast::hard_resolve).
@@ -1396,9 +1415,9 @@ static int fast_queue(luf_graph* g, void* stream, uint32_t** out)
     return 0;
 }
 
-struct FastLogArgs { fast::FExport x; const uint32_t* qin; const uint32_t* qin_count; };
+struct FastLogArgs { fast::FExport x; const uint32_t* qin; const uint32_t* qin_count; uint32_t* glog; int mode; };     // mode: 1 second pass, 2 one pass
 
-template <int TW, bool ADJ, bool LOGQ>
+template <int TW, bool ADJ, int LOGQ>
 static int fast_launch_t(luf_graph* g, const fast::FView& fv, const FastPlan& plan, const fast::FLayout& fl, const SampleParams& sp,
                          unsigned long long shot0, long long nshots, unsigned long long* counts, uint8_t* logical,
                          uint32_t* queue, uint32_t* qcount, const FastLogArgs& la, cudaStream_t stream)
@@ -1416,7 +1435,7 @@ static int fast_launch_t(luf_graph* g, const fast::FView& fv, const FastPlan& pl
         fprintf(stderr, "[luf] fast plan: %u B per shot (lists %u / %u / %u), tile %d, %d shots per block, %d blocks per SM, adjacency %s (%u B), %zu B of shared memory per block\n",
                 fl.bytes, fl.tcap, fl.acap, fl.mcap, plan.tw, plan.spb, plan.bps, plan.adj_shared ? "shared" : "global", plan.adj_bytes, smem);
     k_mc_uf_fast<TW, ADJ, LOGQ><<<(int)blocks, plan.spb * TW, smem, stream>>>(fv, fl, plan.adj_bytes, sp, shot0, nshots, counts,
-                                                                            logical, queue, qcount, la.x, la.qin, la.qin_count);
+                                                                            logical, queue, qcount, la.x, la.qin, la.qin_count, la.glog);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1427,10 +1446,12 @@ static int fast_launch(luf_graph* g, const fast::FView& fv, const FastPlan& plan
                        uint32_t* queue, uint32_t* qcount, cudaStream_t stream, const FastLogArgs* la = nullptr)
 {
     static const FastLogArgs none{};
-#define LUF_FAST_TW(T) case T: return la ? (plan.adj_shared ? fast_launch_t<T, true, true>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, *la, stream) \
-                                                            : fast_launch_t<T, false, true>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, *la, stream)) \
-                                         : (plan.adj_shared ? fast_launch_t<T, true, false>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, none, stream) \
-                                                            : fast_launch_t<T, false, false>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, none, stream));
+#define LUF_FAST_TW(T) case T: return la && la->mode == 2 ? (plan.adj_shared ? fast_launch_t<T, true, 2>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, *la, stream) \
+                                                            : fast_launch_t<T, false, 2>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, *la, stream)) \
+                                  : la ? (plan.adj_shared ? fast_launch_t<T, true, 1>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, *la, stream) \
+                                                            : fast_launch_t<T, false, 1>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, *la, stream)) \
+                                         : (plan.adj_shared ? fast_launch_t<T, true, 0>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, none, stream) \
+                                                            : fast_launch_t<T, false, 0>(g, fv, plan, fl, sp, shot0, nshots, counts, logical, queue, qcount, none, stream));
     switch (plan.tw) {
         LUF_FAST_TW(16) LUF_FAST_TW(32) LUF_FAST_TW(64) LUF_FAST_TW(128) LUF_FAST_TW(256)
         default: return fail(LUF_ERR_INVALID, "fast path: tile width must be 16, 32, 64, 128 or 256");
@@ -2336,14 +2357,26 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                 uint32_t* qcount = cnt;
                 // Second pass over the HARD shots with the merge log, then k_hard_resolve -- instead of the canonical
                 // launch, whose reservation merge needs about one iteration per edge of a lattice-spanning cluster (5 ms
-                // for ONE shot of d = 17 at p = 0.026).  Measured at p = 0.026 (M shots/s, with / without; profiles/
-                // r02_hard_resolve.txt): d = 11 38.8 / 37.0, d = 13 18.4 / 17.0, d = 17 4.66 / 3.08, d = 21 2.15 / 1.21,
-                // d = 25 1.04 / 0.58.  LUF_FAST_LOG=0 sends the HARD shots straight to the canonical launch.
+                // for ONE shot of d = 17 at p = 0.026).  LUF_FAST_LOG=0 sends the HARD shots straight to the canonical launch.
                 const bool env_log = !(getenv("LUF_FAST_LOG") && atoi(getenv("LUF_FAST_LOG")) == 0);
                 const fast::FLayout fl2 = make_fast_layout(g->fview.D, g->fview.E, g->fview.DEG, mu, true);
                 FastPlan plan2;
                 const size_t resolve_warp = 4 * ((size_t)g->fview.D + 4);         // hard_resolve: one word per detector per warp
                 const bool log_pass = env_log && !(flags & LUF_UF_WEST) && fast_plan(g, fl2, &plan2) && resolve_warp <= (size_t)g->max_smem;
+                // One pass instead (LUF_FAST_ONEPASS=0 / 1 forces it off / on): where HARD shots are common -- from 0.06
+                // expected faults per detector on (p = 0.021 on the phenomenological surface code: a percent of the
+                // shots) -- every shot writes its merge log to a slab of global memory (one store per newly FULL edge,
+                // read back only by a HARD shot: + 3 - 6 % on the first pass, - 2 % on cfg3 at p = 0.01, which therefore
+                // keeps the two passes), the HARD shots export their clusters' keys at once and k_hard_sort orders
+                // them: no second decode of the heaviest shots.  p = 0.026, M shots/s, one pass / two passes /
+                // canonical launch (profiles/r02_hard_resolve.txt): d = 11 41.5 / 38.4 / 37.0, d = 13 20.7 / 18.5 / 17.1,
+                // d = 17 7.84 / 6.96 / 3.80, d = 21 2.51 / 2.21 / 1.19, d = 25 1.25 / 1.07 / 0.59.
+                const int env_one = getenv("LUF_FAST_ONEPASS") ? atoi(getenv("LUF_FAST_ONEPASS")) : -1;
+                uint32_t sortcap = 64;
+                while (sortcap < fl2.lcap) sortcap <<= 1;
+                const bool one_pass = log_pass && (env_one < 0 ? mu >= 0.06 * g->fview.D : env_one != 0) && 4 * (size_t)sortcap <= (size_t)g->max_smem;
+                fast::FLayout fl1 = fl;
+                if (one_pass) fl1.lcap = fl2.lcap;           // (the log itself lies in global memory: fl1.elog is not used)
                 for (int64_t done = 0; done < nshots; done += FAST_CHUNK) {
                     const long long m = std::min<long long>(FAST_CHUNK, nshots - done);
                     const unsigned long long first = shot0 + (unsigned long long)done;
@@ -2357,22 +2390,45 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                     int nev = 0;
                     auto mark = [&]() { if (env_times && nev < 5) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], (cudaStream_t)stream); ++nev; } };
                     mark();
-                    if (int rc = fast_launch(g, fv, plan, fl, sp, first, m, counts_dev, lg, queue, qcount, (cudaStream_t)stream)) return rc;
-                    ++g->launches;
-                    mark();
                     uint32_t *cq = queue, *cqc = qcount;         // what the canonical launch takes
+                    FastLogArgs la;
+                    memset(&la, 0, sizeof(la));
                     if (log_pass) {
-                        // export buffer: 64 words per shot of the chunk, between 2^22 and 2^27 (a shot that finds no room goes to Q3)
+                        // export buffer: 64 words per shot of the chunk, between 2^22 and 2^27 (a shot that finds no room goes on
+                        // to the canonical launch)
                         size_t xcap = (size_t)std::min<long long>(1ll << 27, std::max<long long>(1ll << 22, (long long)m * 64));
                         if (getenv("LUF_FAST_XCAP_WORDS")) xcap = (size_t)std::max(64, atoi(getenv("LUF_FAST_XCAP_WORDS")));     // (tests: the no-room path)
                         void* xbuf = nullptr;
                         if (int rc = wide_slab(g, stream, 4, xcap * 4, &xbuf)) return rc;
-                        FastLogArgs la;
                         la.x.buf = (uint32_t*)xbuf; la.x.cursor = (uint64_t*)(cnt + 4); la.x.cap = (uint32_t)xcap;
                         la.x.queue = q2; la.x.qcount = cnt + 2;
-                        la.qin = queue; la.qin_count = cnt;
-                        if (int rc = fast_launch(g, fv, plan2, fl2, sp, first, m, counts_dev, lg, q3, cnt + 1, (cudaStream_t)stream, &la)) return rc;
+                    }
+                    if (one_pass) {
+                        const long long tiles = (long long)g->sm_count * plan.bps * plan.spb;
+                        void* glog = nullptr;
+                        if (int rc = wide_slab(g, stream, 5, (size_t)tiles * fl1.lcap * 4, &glog)) return rc;
+                        la.x.unsorted = 1u; la.x.max_keys = sortcap; la.glog = (uint32_t*)glog; la.mode = 2;
+                        if (int rc = fast_launch(g, fv, plan, fl1, sp, first, m, counts_dev, lg, queue, qcount, (cudaStream_t)stream, &la)) return rc;
                         ++g->launches;
+                        mark();
+                        if (int rc = raise_smem_limit(g->device, g->max_smem, k_hard_sort)) return rc;
+                        const size_t ssmem = 4 * (size_t)sortcap;
+                        const long long sper = std::max<long long>(1, std::min<long long>(8, (long long)(228 * 1024) / (long long)(ssmem + 1024)));
+                        k_hard_sort<<<(int)(g->sm_count * sper), 256, ssmem, (cudaStream_t)stream>>>(fv, la.x);
+                        CUDA_TRY(cudaGetLastError());
+                        ++g->launches;
+                    } else {
+                        if (int rc = fast_launch(g, fv, plan, fl, sp, first, m, counts_dev, lg, queue, qcount, (cudaStream_t)stream)) return rc;
+                        ++g->launches;
+                        mark();
+                    }
+                    if (log_pass) {
+                        if (!one_pass) {                     // second pass over the queued HARD shots, the log in shared memory
+                            la.qin = queue; la.qin_count = cnt; la.mode = 1;
+                            if (int rc = fast_launch(g, fv, plan2, fl2, sp, first, m, counts_dev, lg, q3, cnt + 1, (cudaStream_t)stream, &la)) return rc;
+                            ++g->launches;
+                            cq = q3; cqc = cnt + 1;          // only what the second pass could not log
+                        }
                         mark();
                         // (the replay of a shot is one dependent chain: as many resident warps as shared memory allows)
                         {
@@ -2385,7 +2441,6 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                         CUDA_TRY(cudaGetLastError());
                         ++g->launches;
                         mark();
-                        cq = q3; cqc = cnt + 1;                  // only what the second pass could not log
                     }
                     if (!fv.west && g->wide) {  // the HARD shots of a graph beyond the 16-bit layout: the wide instance
                         WidePlan w;
@@ -2405,7 +2460,7 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                         float t[4] = {0, 0, 0, 0};
                         for (int i = 0; i + 1 < nev; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
                         for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
-                        if (log_pass) fprintf(stderr, "[luf] chunk of %lld shots: first pass %.3f ms, log pass %.3f ms, hard_resolve %.3f ms, canonical launch %.3f ms\n", m, t[0], t[1], t[2], t[3]);
+                        if (log_pass) fprintf(stderr, "[luf] chunk of %lld shots: first pass %.3f ms, %s %.3f ms, hard_resolve %.3f ms, canonical launch %.3f ms\n", m, t[0], one_pass ? "hard_sort" : "log pass", t[1], t[2], t[3]);
                         else fprintf(stderr, "[luf] chunk of %lld shots: first pass %.3f ms, canonical launch %.3f ms\n", m, t[0], t[1]);
                     }
                     if (!fv.west && getenv("LUF_DEBUG_PLAN")) {
@@ -2413,7 +2468,7 @@ int luf_mc_run_logical(luf_graph* g, int decoder, int flags, const double* class
                         CUDA_TRY(cudaMemcpyAsync(h, cnt, 24, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
                         CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
                         fprintf(stderr, "[luf] HARD shots of %lld: %u queued by the first pass, %u exported for hard_resolve (%llu words), %u left to the canonical launch\n",
-                                m, h[0], h[2], (unsigned long long)h[4] | ((unsigned long long)h[5] << 32), log_pass ? h[1] : h[0]);
+                                m, one_pass ? h[0] + h[2] : h[0], h[2], (unsigned long long)h[4] | ((unsigned long long)h[5] << 32), log_pass && !one_pass ? h[1] : h[0]);
                     }
                 }
                 return 0;

@@ -52,6 +52,7 @@ static const int MAX_DETECTORS = 0x7FFE;                              // a non-r
 // accumulator, and the HARD flag (an odd cluster on both sides; written by the last phase only, read after the
 // barrier that ends it).
 enum { C_TOUCHED = 0, C_ALIST = 1, C_MLIST = 2, C_ACTIVE = 3, C_XBASE = 4, C_PARITY = 5, C_HARD_M = 6, C_XCOUNT = 7 };
+static const int C_XPOS = C_ALIST;        // (the active list is done with when a shot is exported)
 static const uint32_t HARD = 2u;                         // result of a shot the canonical kernel has to decode
 static const uint32_t HARD_LOGGED = 3u;                  // ... or whose odd clusters on both sides were exported for hard_resolve
 static const uint32_t KEY_EDGE_BITS = 20u, KEY_EDGE_MASK = 0xFFFFFu;      // merge-log key = growth round << 20 | edge id
@@ -64,6 +65,10 @@ struct FExport {
     uint32_t cap;               // words of buf
     uint32_t* queue;            // [2 * shots of the launch]
     uint32_t* qcount;
+    uint32_t unsorted;          // 1: the log lies in global memory (a slab per resident tile, bound to FShot::elog by the
+                                //    kernel) and the keys go out as they lie -- k_hard_sort orders them; 0: the log is
+                                //    in the tile's shared memory, sorted there and exported as endpoint pairs
+    uint32_t max_keys;          // unsorted: most keys per shot (the sort kernel's buffer)
 };
 
 // Read-only tables (global memory; fadj optionally staged in shared memory by the kernel).
@@ -540,6 +545,25 @@ LUF_DEV void f_export_gather(const FView& g, const FLayout& l, const FShot& s, u
     }
 }
 
+// One-pass mode (the log in global memory): count the entries of the HARD clusters, then write the keys as they lie.
+LUF_DEV void f_export_count(const FView& g, const FShot& s, uint32_t ntot, int lane, int nl)
+{
+    uint32_t c = 0;
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < ntot; i += (uint32_t)nl) c += f_in_hard_cluster(g, s, s.elog[i]) ? 1u : 0u;
+    if (c) luf_atomic_add(&s.cnt[C_XCOUNT], c);
+}
+
+LUF_DEV void f_export_keys(const FView& g, const FShot& s, const FExport& x, uint32_t ntot, int lane, int nl)
+{
+    const uint32_t base = s.cnt[C_XBASE];
+    LUF_NOUNROLL
+    for (uint32_t i = (uint32_t)lane; i < ntot; i += (uint32_t)nl) {
+        const uint32_t key = s.elog[i];
+        if (f_in_hard_cluster(g, s, key)) x.buf[base + 1u + luf_atomic_add(&s.cnt[C_XPOS], 1u)] = key;
+    }
+}
+
 // ... sorted by (round, edge id) in place, a bitonic network over the tile's lanes ...
 LUF_DEV void r_sort_step(uint32_t* key, uint32_t np, uint32_t k, uint32_t j, int lane, int nl)
 {
@@ -703,6 +727,14 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
         if (s.cnt[C_HARD_M]) {                           // (uniform: every lane reads the same word after the barrier)
             const uint32_t ntot = s.cnt[C_MLIST];
             if (!x || !x->buf || !l.lcap || ntot > l.lcap) return HARD;           // no log, or it could not hold the shot's merges
+            if (x->unsorted) {                           // one-pass mode: the keys as they lie; k_hard_sort orders them
+                FT_PHASE(f_export_count(g, s, ntot, lane, nl); if (lane == 0) s.cnt[C_XPOS] = 0u);
+                if (s.cnt[C_XCOUNT] > x->max_keys) return HARD;
+                FT_PHASE(if (lane == 0) f_export_reserve(s, *x, s.cnt[C_PARITY] & 1u));
+                if (s.cnt[C_XBASE] == 0xFFFFFFFFu) return HARD;
+                FT_PHASE(f_export_keys(g, s, *x, ntot, lane, nl));
+                return HARD_LOGGED;
+            }
             uint32_t np = 1;
             uint32_t* sorted = s.elog;
             if (2u * ntot <= l.lcap) {                   // room to gather the HARD clusters' entries apart: a smaller sort
@@ -728,6 +760,24 @@ LUF_DEV uint32_t fast_shot(const FView& g, const FLayout& l, const FShot& s, con
     }
     if (stats) { stats[0] = rounds; stats[1] = s.cnt[C_TOUCHED]; stats[2] = most_m; stats[3] = most_a; }
     return s.cnt[C_PARITY] & 1u;
+}
+
+// One exported shot of the one-pass mode, one tile: the keys of rec[1 .. n] sorted through `key` (np = the power
+// of two >= n words of shared memory) and written back as endpoint pairs, which is what hard_resolve reads.
+template <class Sync>
+LUF_DEV void hard_sort(const FView& g, uint32_t* rec, uint32_t* key, int lane, int nl, Sync sync)
+{
+    (void)lane; (void)sync;
+    const uint32_t n = rec[0] & 0x7FFFFFFFu;
+    uint32_t np = 1;
+    while (np < n) np <<= 1;
+    FT_PHASE(for (uint32_t i = (uint32_t)lane; i < np; i += (uint32_t)nl) key[i] = i < n ? rec[1u + i] : 0xFFFFFFFFu);
+    LUF_NOUNROLL
+    for (uint32_t k = 2; k <= np; k <<= 1) {
+        LUF_NOUNROLL
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) { FT_PHASE(r_sort_step(key, np, k, j, lane, nl)); }
+    }
+    FT_PHASE(for (uint32_t i = (uint32_t)lane; i < n; i += (uint32_t)nl) rec[1u + i] = LUF_LDG(&g.einfo[key[i] & KEY_EDGE_MASK]));
 }
 
 // One exported shot, one warp: rec[0] = count | fast bit << 31, then the edges of the shot's HARD clusters in

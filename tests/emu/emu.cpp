@@ -384,7 +384,7 @@ int emu_mc_uf_compact(const luf_graph_desc* d, int west, const double* class_p, 
 // the export buffer could not hold the shot (the kernel then queues it for the canonical launch).  nkeys
 // (optional) [nshots]: exported keys (0: the shot had no such cluster).  log_scale < 0: the library's log size.
 int emu_mc_uf_compact_log(const luf_graph_desc* d, const double* class_p, unsigned long long seed, unsigned long long shot0,
-                          long long nshots, int nl, double mu, int lcap, uint8_t* out, uint32_t* nkeys, uint32_t* nlog)
+                          long long nshots, int nl, double mu, int lcap, int onepass, uint8_t* out, uint32_t* nkeys, uint32_t* nlog)
 {
     PackedFast pf;
     pack_fast(*d, pf);
@@ -406,19 +406,28 @@ int emu_mc_uf_compact_log(const luf_graph_desc* d, const double* class_p, unsign
     }
     const SampleParams sp = make_sample_params(class_p, pf.n_classes, seed);
     std::vector<unsigned char> mem(l.bytes + 16);
-    const fast::FShot s = fast::fbind(l, mem.data());
+    fast::FShot s = fast::fbind(l, mem.data());
+    std::vector<uint32_t> glog(l.lcap + 1), sortbuf;
+    if (onepass) s.elog = glog.data();               // one-pass mode: the log outside the tile's state (global memory on the device)
     std::vector<uint32_t> xbuf((size_t)pf.E + 8), S(pf.D, 0xDEADBEEFu);
     uint64_t cursor = 0;
     uint32_t q[2], qn = 0, res = 0;
     for (long long k = 0; k < nshots; ++k) {
         cursor = 0;
         fast::FExport x{xbuf.data(), &cursor, (uint32_t)xbuf.size(), q, &qn};
+        x.unsorted = onepass ? 1u : 0u; x.max_keys = (uint32_t)pf.E;
         uint32_t r = fast::fast_shot<false>(g, l, s, sp, shot0 + k, 0, nl, 0, nullptr, &x);
         if (nkeys) nkeys[k] = 0;
         if (nlog) nlog[k] = s.cnt[fast::C_MLIST];
         if (r == fast::HARD_LOGGED) {
             const uint32_t base = s.cnt[fast::C_XBASE];
             if (nkeys) nkeys[k] = xbuf[base] & 0x7FFFFFFFu;
+            if (onepass) {
+                uint32_t np = 1;
+                while (np < (xbuf[base] & 0x7FFFFFFFu)) np <<= 1;
+                sortbuf.assign(np, 0);
+                fast::hard_sort(g, xbuf.data() + base, sortbuf.data(), 0, nl > 32 ? 256 : 32, 0);
+            }
             r = fast::hard_resolve(xbuf.data() + base, S.data(), &res, 0, 32, 0);
         }
         out[k] = (uint8_t)r;

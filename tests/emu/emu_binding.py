@@ -188,7 +188,7 @@ class Emu:
         assert rc == 0, rc
         return (out, stats) if want_stats else out
 
-    def mc_uf_compact_log(self, noise_level, seed, shot0, nshots, nl=32, mu=-1.0, lcap=-1, want_keys=False):
+    def mc_uf_compact_log(self, noise_level, seed, shot0, nshots, nl=32, mu=-1.0, lcap=-1, want_keys=False, onepass=False):
         """The compact fast path with the merge log and hard_resolve (default inclination): per shot the logical
         bit, or 2 where the log could not hold the shot; optionally the number of exported keys per shot."""
         cp = np.ascontiguousarray(self.noise.class_probabilities(noise_level), dtype=np.float64)
@@ -196,8 +196,8 @@ class Emu:
         nkeys = np.zeros(nshots, np.uint32)
         self.last_log_entries = np.zeros(nshots, np.uint32)            # newly FULL edges of each shot (what the log has to hold)
         lib().emu_mc_uf_compact_log.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_longlong, C.c_int,
-                                                C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        rc = lib().emu_mc_uf_compact_log(C.addressof(self.desc), _vp(cp), seed, shot0, nshots, nl, float(mu), int(lcap), _vp(out), _vp(nkeys),
+                                                C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = lib().emu_mc_uf_compact_log(C.addressof(self.desc), _vp(cp), seed, shot0, nshots, nl, float(mu), int(lcap), int(onepass), _vp(out), _vp(nkeys),
                                          _vp(self.last_log_entries))
         assert rc == 0, rc
         return (out, nkeys) if want_keys else out

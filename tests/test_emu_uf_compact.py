@@ -152,6 +152,13 @@ def test_hard_clusters_resolved_from_the_merge_log(spec, p, n):
         np.testing.assert_array_equal(out, want)
         np.testing.assert_array_equal(nkeys > 0, hard)
     assert hard.sum() > 0 or p < 0.1
+    # one-pass mode: the log outside the tile's state, the keys exported as they lie, hard_sort, hard_resolve
+    for nl, lcap in ((32, 100000), (128, -1), (64, 256)):
+        out, nkeys = emu.mc_uf_compact_log(p, 11, 100, n, nl=nl, lcap=lcap, want_keys=True, onepass=True)
+        np.testing.assert_array_equal(out[out != 2], want[out != 2])
+        if lcap == 100000:
+            np.testing.assert_array_equal(out, want)
+            np.testing.assert_array_equal(nkeys > 0, hard)
     # the library's log size: a shot it cannot hold is HARD (2) as before, never wrong
     out = emu.mc_uf_compact_log(p, 11, 100, n, nl=32)
     np.testing.assert_array_equal(out[out != 2], want[out != 2])

@@ -179,9 +179,10 @@ def test_logical_frames_only(spec, p):
     (dict(code='Surface', d=17, noise='phenomenological'), 0.027, 1500),
 ])
 def test_hard_shots_every_route_gives_the_same_bits(spec, p, n, monkeypatch):
-    """Shots with an odd cluster on both sides (default inclination): merge-log pass + k_hard_resolve, the same with
-    an export buffer that holds only a few shots (the rest falls back to the canonical launch), and the canonical
-    launch alone -- per-shot bits equal to the oracle's on every route."""
+    """Shots with an odd cluster on both sides (default inclination): one pass with the merge log in global memory +
+    k_hard_sort + k_hard_resolve, second pass with the log in shared memory + k_hard_resolve, both with an export
+    buffer that holds only a few shots (the rest falls back to the canonical launch), and the canonical launch
+    alone -- per-shot bits equal to the oracle's on every route."""
     from localuf_b200 import _engine
     code = make_code(spec)
     eng = _engine.Engine(code, device=0)
@@ -189,7 +190,8 @@ def test_hard_shots_every_route_gives_the_same_bits(spec, p, n, monkeypatch):
     err, syn = eng.sample_host(p, 13, 50, n)
     ocorr, _, _ = orc.decode_batch(0, 0, syn, want_growth=False)
     want = orc.logical_batch(err, ocorr)
-    for env in ({}, {'LUF_FAST_XCAP_WORDS': '3000'}, {'LUF_FAST_LOG': '0'}):
+    for env in ({}, {'LUF_FAST_ONEPASS': '1'}, {'LUF_FAST_ONEPASS': '0'}, {'LUF_FAST_ONEPASS': '1', 'LUF_FAST_XCAP_WORDS': '3000'},
+                {'LUF_FAST_ONEPASS': '0', 'LUF_FAST_XCAP_WORDS': '3000'}, {'LUF_FAST_LOG': '0'}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         eng2 = _engine.Engine(code, device=0)

@@ -1,7 +1,8 @@
-# Near-threshold fused Monte Carlo (default inclination) with and without the merge-log pass, with the per-launch
+# Near-threshold fused Monte Carlo (default inclination): 1 = one pass with the merge log in global memory,
+# 2 = second pass over the HARD shots with the log in shared memory, 0 = canonical launch over the HARD shots; with the per-launch
 # times of a chunk (CUDA events).  usage: bash tools/hard_bench.sh [p]
 P=${1:-0.026}
-for d in 11 13 17 21 25; do n=$((d<=11 ? 1048576 : (d<=13 ? 262144 : (d<=17 ? 65536 : 16384)))); for lg in 1 0; do echo "LUF_FAST_LOG=$lg d=$d p=$P"; LUF_FAST_LOG=$lg python - <<PY 2>&1 | grep -E "RESULT|HARD shots|chunk of" | tail -3
+for d in 11 13 17 21 25; do n=$((d<=11 ? 1048576 : (d<=13 ? 262144 : (d<=17 ? 65536 : 16384)))); for lg in 1 2 0; do echo "LUF_FAST_LOG=$lg d=$d p=$P"; LUF_FAST_LOG=$((lg>0)) LUF_FAST_ONEPASS=$((lg==1)) python - <<PY 2>&1 | grep -E "RESULT|HARD shots|chunk of" | tail -3
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 import localuf_b200 as L
