@@ -2752,7 +2752,8 @@ int luf_decode_batch_host(luf_graph* g, int decoder, int flags, int64_t nshots, 
     // Chunks of shots flow through three streams: while one chunk decodes, the next one's
     // syndromes arrive and the previous one's corrections leave (full-duplex PCIe; the copies
     // are asynchronous when the caller's buffers are page-locked, staged by the driver otherwise).
-    const size_t chunk = (size_t)1 << 16;
+    size_t chunk = (size_t)1 << 16;
+    if (getenv("LUF_HOST_CHUNK")) chunk = (size_t)std::max(1024, atoi(getenv("LUF_HOST_CHUNK")));
     for (cudaStream_t& st : g->pipe) if (!st) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     // whatever happens after the first enqueue, every pipe stream is drained before the call returns: the
     // copies in flight write into the caller's buffers and into scratch the next call may reallocate
