@@ -25,8 +25,9 @@
 //
 // A shot that ends with an ODD cluster touching both sides is reported as HARD under the default inclination
 // (which boundary node such a cluster keeps, and so where its one string to the boundary goes, depends on the
-// merge order; an even cluster on both sides adds nothing either way); the caller queues it for the canonical
-// kernel.  Under the west inclination (uf.py:544-549) such a cluster keeps a west boundary node; that node has
+// merge order; an even cluster on both sides adds nothing either way): with a merge log (further down) the unions
+// inside those clusters are exported and replayed in canonical order, without one the caller queues the shot -- for
+// a second pass with a log, or for the canonical kernel.  Under the west inclination (uf.py:544-549) such a cluster keeps a west boundary node; that node has
 // one edge, every defect's path to the root runs through it, so the cluster adds its defect parity like any
 // other that touches the west side -- no HARD shots at all.  A work list that overflows is not fatal either:
 // its consumers walk the bitmap behind it (touched nodes, defects) or the growth words themselves (fully grown
